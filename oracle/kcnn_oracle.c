@@ -1,0 +1,97 @@
+/*
+ * oracle/kcnn_oracle.c -- CPU oracle for the kaldi-cnn CNN-layer hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see kcnn_oracle_impl.h).  Built by
+ * __graft_entry__.build() / oracle/Makefile into oracle/liboracle.so and
+ * loaded with ctypes by tests/, smoke() and bench.py's CPU-baseline legs.
+ *
+ * The same body is compiled for float (oraF_*, the reference's BaseFloat) and
+ * for double (oraD_*, used to budget the FP32 / TF32 tolerances).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORA_CAT(a, b) a##b
+
+#define REAL float
+#define ORA(name) ORA_CAT(oraF_, name)
+#include "kcnn_oracle_impl.h"
+#undef REAL
+#undef ORA
+
+#define REAL double
+#define ORA(name) ORA_CAT(oraD_, name)
+#include "kcnn_oracle_impl.h"
+#undef REAL
+#undef ORA
+
+/* ---- glue between the hot-path layers, float only ---------- */
+
+/* RectifiedLinearComponent::Propagate / Backprop.
+ * nnet2/nnet-component.cc:799-827: out = max(in, 0); in_deriv = out_deriv * (out > 0). */
+void oraF_relu_propagate(const float *in, int rows, int cols, int in_stride,
+                         float *out, int out_stride) {
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) {
+      float v = in[(size_t)i * in_stride + j];
+      out[(size_t)i * out_stride + j] = v > 0.0f ? v : 0.0f;
+    }
+}
+
+void oraF_relu_backprop(const float *out_value, int rows, int cols, int ov_stride,
+                        const float *out_deriv, int od_stride, float *in_deriv,
+                        int id_stride) {
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++)
+      in_deriv[(size_t)i * id_stride + j] =
+          out_value[(size_t)i * ov_stride + j] > 0.0f
+              ? out_deriv[(size_t)i * od_stride + j] : 0.0f;
+}
+
+/* SoftmaxComponent::Propagate.  nnet2/nnet-component.cc:930-950:
+ * row-wise softmax (max-subtracted) then ApplyFloor(1e-20). */
+void oraF_softmax_propagate(const float *in, int rows, int cols, int in_stride,
+                            float *out, int out_stride) {
+  for (int i = 0; i < rows; i++) {
+    const float *x = in + (size_t)i * in_stride;
+    float *y = out + (size_t)i * out_stride;
+    float mx = x[0];
+    for (int j = 1; j < cols; j++) if (x[j] > mx) mx = x[j];
+    double sum = 0.0;
+    for (int j = 0; j < cols; j++) { y[j] = expf(x[j] - mx); sum += y[j]; }
+    float inv = (float)(1.0 / sum);
+    for (int j = 0; j < cols; j++) { y[j] *= inv; if (y[j] < 1e-20f) y[j] = 1e-20f; }
+  }
+}
+
+/* The objective nnet2's NnetUpdater::ComputeObjfAndDeriv forms for hard labels
+ * (upstream nnet-update.cc, absent from the patch set; stated from the nnet2
+ * contract): objf = sum_i log p[i, label_i]; deriv[i, label_i] = 1 / p[i, label_i],
+ * zero elsewhere.  Returns the objective. */
+double oraF_xent_objf_and_deriv(const float *post, int rows, int cols, int p_stride,
+                                const int *labels, float *deriv, int d_stride) {
+  double objf = 0.0;
+  for (int i = 0; i < rows; i++) {
+    for (int j = 0; j < cols; j++) deriv[(size_t)i * d_stride + j] = 0.0f;
+    float p = post[(size_t)i * p_stride + labels[i]];
+    objf += log((double)p);
+    deriv[(size_t)i * d_stride + labels[i]] = 1.0f / p;
+  }
+  return objf;
+}
+
+/* SoftmaxComponent::Backprop.  nnet2/nnet-component.cc:952-1000:
+ * in_deriv[i,:] = out[i,:] * (out_deriv[i,:] - dot(out[i,:], out_deriv[i,:])). */
+void oraF_softmax_backprop(const float *out_value, int rows, int cols, int ov_stride,
+                           const float *out_deriv, int od_stride, float *in_deriv,
+                           int id_stride) {
+  for (int i = 0; i < rows; i++) {
+    const float *y = out_value + (size_t)i * ov_stride;
+    const float *d = out_deriv + (size_t)i * od_stride;
+    float *o = in_deriv + (size_t)i * id_stride;
+    double dot = 0.0;
+    for (int j = 0; j < cols; j++) dot += (double)y[j] * d[j];
+    for (int j = 0; j < cols; j++) o[j] = y[j] * (d[j] - (float)dot);
+  }
+}
