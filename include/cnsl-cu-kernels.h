@@ -1,0 +1,288 @@
+/*
+ * include/cnsl-cu-kernels.h -- L0: the extern "C" kernel-launcher ABI of the
+ * B200-native CNN-layer hot path (libkaldicnn_b200.so).
+ *
+ * This header replaces the reference's src/cnslmat/cnsl-cu-kernels.h (itself
+ * styled after Kaldi's cu-kernels-ansi.h): plain C linkage, raw device
+ * pointers, MatrixDim {rows, cols, stride} by value, ints; launchers return
+ * void and errors surface through cudaGetLastError() in the caller, exactly as
+ * the reference's host code expects (cnslmat/conv2D.cc:108).
+ *
+ * Three groups:
+ *  (1) LEGACY launchers -- same names and parameter lists as
+ *      cnsl-cu-kernels.h:25-45, so the reference's own conv2D.cc links against
+ *      this library unchanged.  The Gr/Bl arguments are accepted and ignored
+ *      (the sm_100a kernels choose their own geometry); work is issued on the
+ *      stream set by kcnn_set_stream() (default: the legacy default stream).
+ *  (2) STREAM-ORDERED launchers cudaF_*_s -- what the new CuMatrixBase members
+ *      call: explicit cudaStream_t, each matrix's own stride (the reference
+ *      kernel reads out_deriv with out_value's pitch, cnsl-cu-kernels.cu:293).
+ *  (3) FUSED entry points -- implicit-GEMM convolution forward / input-gradient
+ *      / weight-gradient, the affine (fully connected) GEMMs, the fused SGD
+ *      update and the max-pool-with-index pair.  They replace SEQUENCES of
+ *      reference launches; each comment names the sequence.
+ *
+ * Only float is built: the reference instantiates BaseFloat = float only
+ * (cnslmat/conv2D.cc:81,96,138 hard-code CuMatrix<BaseFloat>), so its cudaD_*
+ * launchers are unreachable.
+ *
+ * All pointers are DEVICE pointers.  Nothing here allocates, synchronises or
+ * touches the host: every entry point is CUDA-graph capturable.
+ */
+#ifndef CNSL_CNSLMAT_CNSL_CU_KERNELS_H_
+#define CNSL_CNSLMAT_CNSL_CU_KERNELS_H_
+
+#include <cuda_runtime_api.h>
+#include "cu-matrixdim.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library state ------------------------------------------------------ */
+
+/* Stream used by the LEGACY launchers of group (1). */
+void kcnn_set_stream(cudaStream_t stream);
+cudaStream_t kcnn_get_stream(void);
+/* Number of kernels this library has launched since load / since the last
+ * reset (bench.py reports it as "gpu_launches"). */
+unsigned long long kcnn_launch_count(void);
+void kcnn_reset_launch_count(void);
+/* "sm_100a" build tag and the ABI revision of this header. */
+const char *kcnn_build_info(void);
+int kcnn_abi_version(void);
+
+/* Arithmetic used by the GEMM-shaped entry points of group (3). */
+enum {
+  KCNN_MATH_FP32_SIMT = 0,   /* FP32 FMA on the CUDA cores; 1e-5 class         */
+  KCNN_MATH_TF32_TC = 1      /* tcgen05.mma kind::tf32, FP32 accumulate in TMEM */
+};
+
+/* Max-pool window modes (the two bools of Maxpool_prop, cu-matrix.h:479). */
+enum { KCNN_POOL_PLAIN = 0, KCNN_POOL_OVERLAP = 1, KCNN_POOL_OVERLAP2D = 2 };
+
+/* ---- (1) legacy launchers: cnsl-cu-kernels.h:25-45 ------------------------ */
+
+void cudaF_span_row_to_convmat(dim3 Gr, dim3 Bl, const float *in, MatrixDim in_dim,
+                               float *span, MatrixDim span_dim, int in_height,
+                               int in_width, int in_channel, int kernel_height,
+                               int kernel_width, int row_offset);           /* :25 */
+void cudaF_convmat_to_out(dim3 Gr, dim3 Bl, const float *convMat, MatrixDim conv_dim,
+                          float *out, MatrixDim out_dim, int out_height,
+                          int out_width, int num_sample);                   /* :28 */
+void cudaF_add_mat_rep_vec(dim3 Gr, dim3 Bl, const float *vec, int rep, float *out,
+                           MatrixDim out_dim);                              /* :29 */
+void cudaF_flip_mat(dim3 Gr, dim3 Bl, const float *orig, MatrixDim orig_dim,
+                    int kernel_height, int kernel_width, int group, float *flip,
+                    MatrixDim flip_dim);                                    /* :30 */
+void cudaF_pad_zero(dim3 Gr, dim3 Bl, const float *orig, MatrixDim orig_dim,
+                    int orig_height, int orig_width, int kernel_height,
+                    int kernel_width, float *padmat, MatrixDim padmat_dim); /* :31 */
+void cudaF_tp_block(dim3 Gr, dim3 Bl, const float *in, MatrixDim in_dim, float *out,
+                    MatrixDim out_dim, int block_size);                     /* :32 */
+void cudaF_tp_inside_block(dim3 Gr, dim3 Bl, const float *in, MatrixDim in_dim,
+                           float *out, MatrixDim out_dim, int block_size);  /* :33 */
+void cudaF_mod_permute_row(dim3 Gr, dim3 Bl, const float *in, MatrixDim in_dim,
+                           float *out, MatrixDim out_dim, int block_size,
+                           int in_channel);                                 /* :34 */
+void cudaF_copy_rows_at(dim3 Gr, dim3 Bl, const float *src, MatrixDim src_dim,
+                        float *dest, MatrixDim dest_dim, int row_offset);   /* :35 */
+void cudaF_maxpool_prop(dim3 Gr, dim3 Bl, const float *src, MatrixDim src_dim,
+                        float *pool, MatrixDim pool_dim, int in_height_,
+                        int in_width_, int pool_height_dim_, int pool_width_dim_,
+                        int pool_channel_dim_);                             /* :36 */
+void cudaF_maxpool_backprop(dim3 Gr, dim3 Bl, const float *in_val, MatrixDim in_val_dim,
+                            const float *out_val, MatrixDim out_val_dim,
+                            const float *out_deriv, MatrixDim out_deriv_dim,
+                            float *dest, MatrixDim dest_dim, int in_height_,
+                            int in_width_, int pool_height_dim_, int pool_width_dim_,
+                            int pool_channel_dim_);                         /* :37 */
+void cudaF_maxpoolchannel_overlap_prop(dim3 Gr, dim3 Bl, const float *src,
+                                       MatrixDim src_dim, float *pool, MatrixDim pool_dim,
+                                       int in_height_, int in_width_, int pool_height_dim_,
+                                       int pool_width_dim_, int pool_channel_dim_); /* :39 */
+void cudaF_maxpoolchannel_overlap_backprop(dim3 Gr, dim3 Bl, const float *in_val,
+                                           MatrixDim in_val_dim, const float *out_val,
+                                           MatrixDim out_val_dim, const float *out_deriv,
+                                           MatrixDim out_deriv_dim, float *dest,
+                                           MatrixDim dest_dim, int in_height_, int in_width_,
+                                           int pool_height_dim_, int pool_width_dim_,
+                                           int pool_channel_dim_);          /* :40 */
+void cudaF_maxpoolchannel_overlap2D_prop(dim3 Gr, dim3 Bl, const float *src,
+                                         MatrixDim src_dim, float *pool, MatrixDim pool_dim,
+                                         int in_height_, int in_width_, int pool_height_dim_,
+                                         int pool_width_dim_, int pool_channel_dim_); /* :42 */
+void cudaF_maxpoolchannel_overlap2D_backprop(dim3 Gr, dim3 Bl, const float *in_val,
+                                             MatrixDim in_val_dim, const float *out_val,
+                                             MatrixDim out_val_dim, const float *out_deriv,
+                                             MatrixDim out_deriv_dim, float *dest,
+                                             MatrixDim dest_dim, int in_height_,
+                                             int in_width_, int pool_height_dim_,
+                                             int pool_width_dim_, int pool_channel_dim_); /* :43 */
+
+/* ---- (2) stream-ordered launchers --------------------------------------- */
+
+/* this[i,j] += vec[j / rep].  Replaces _add_mat_rep_vec (cnsl-cu-kernels.cu:61-75). */
+void cudaF_add_mat_rep_vec_s(cudaStream_t st, const float *vec, int rep, float *out,
+                             MatrixDim out_dim);
+/* flip[g*ks + r, c] = orig[c*ks + (ks-1-r), g].  _flip_mat (.cu:78-97).
+ * in_channel = flip_dim.cols. */
+void cudaF_flip_mat_s(cudaStream_t st, const float *orig, MatrixDim orig_dim,
+                      int kernel_height, int kernel_width, int group, float *flip,
+                      MatrixDim flip_dim);
+/* Zero border of kernel_height-1 / kernel_width-1 per side.  _pad_zero (.cu:100-134). */
+void cudaF_pad_zero_s(cudaStream_t st, const float *orig, MatrixDim orig_dim,
+                      int orig_height, int orig_width, int kernel_height,
+                      int kernel_width, float *padmat, MatrixDim padmat_dim);
+/* out[c, n*bs + p] = in[n, c*bs + p].  _tp_block (.cu:138-161). */
+void cudaF_tp_block_s(cudaStream_t st, const float *in, MatrixDim in_dim, float *out,
+                      MatrixDim out_dim, int block_size);
+/* out[n*bs + p, g] = in[n, g*bs + p].  _tp_inside_block (.cu:165-185). */
+void cudaF_tp_inside_block_s(cudaStream_t st, const float *in, MatrixDim in_dim,
+                             float *out, MatrixDim out_dim, int block_size);
+/* out[(i % C)*bs + i / C, :] = in[i, :].  _mod_permute_row (.cu:189-210). */
+void cudaF_mod_permute_row_s(cudaStream_t st, const float *in, MatrixDim in_dim,
+                             float *out, MatrixDim out_dim, int block_size,
+                             int in_channel);
+/* dest[i + row_offset, :] = src[i, :].  _copy_rows_at (.cu:214-228). */
+void cudaF_copy_rows_at_s(cudaStream_t st, const float *src, MatrixDim src_dim,
+                          float *dest, MatrixDim dest_dim, int row_offset);
+/* 3-D max pooling.  mode KCNN_POOL_PLAIN: _maxpool_prop (.cu:231-269);
+ * OVERLAP: .cu:310-356; OVERLAP2D: .cu:405-452.  -1e20 sentinel, strict '<',
+ * first maximum in c -> w -> h order wins (bit-exact incl. signed zero / NaN). */
+void cudaF_maxpool_prop_s(cudaStream_t st, const float *src, MatrixDim src_dim,
+                          float *pool, MatrixDim pool_dim, int in_height, int in_width,
+                          int pool_height_dim, int pool_width_dim, int pool_channel_dim,
+                          int mode);
+/* Reference-exact routing: dest = err at EVERY window element equal to the
+ * pooled value, other elements untouched.  _maxpool_backprop (.cu:271-308) and
+ * the overlap variants (.cu:358-403, 454-503; those accumulate -- done with
+ * atomics here, the reference kernels race).  zero_others != 0 additionally
+ * writes 0 to the non-maximal elements of each window (PLAIN mode only), which
+ * folds the caller's kSetZero pass (nnet0/nnet-component-nnet0.cc:889) into
+ * the same kernel. */
+void cudaF_maxpool_backprop_s(cudaStream_t st, const float *in_val, MatrixDim in_val_dim,
+                              const float *out_val, MatrixDim out_val_dim,
+                              const float *out_deriv, MatrixDim out_deriv_dim,
+                              float *dest, MatrixDim dest_dim, int in_height,
+                              int in_width, int pool_height_dim, int pool_width_dim,
+                              int pool_channel_dim, int mode, int zero_others);
+
+/* ---- (3) fused entry points ---------------------------------------------- */
+
+/* Max pooling that also records, per output, the window position
+ * (c*pw*ph + w*ph + h, one byte) of the first maximum; PLAIN mode, window
+ * <= 256 elements.  Same values as cudaF_maxpool_prop_s. */
+void cudaF_maxpool_prop_index(cudaStream_t st, const float *src, MatrixDim src_dim,
+                              float *pool, MatrixDim pool_dim, unsigned char *index,
+                              int index_stride, int in_height, int in_width,
+                              int pool_height_dim, int pool_width_dim,
+                              int pool_channel_dim);
+/* Exact-routing backward from the recorded index: dest = err at the recorded
+ * element, 0 at the other window elements (whole dest written; no input
+ * values read).  Equals the reference whenever a window has a unique maximum. */
+void cudaF_maxpool_backprop_index(cudaStream_t st, const unsigned char *index,
+                                  int index_stride, const float *out_deriv,
+                                  MatrixDim out_deriv_dim, float *dest, MatrixDim dest_dim,
+                                  int in_height, int in_width, int pool_height_dim,
+                                  int pool_width_dim, int pool_channel_dim);
+
+/* Convolution forward as ONE implicit GEMM:
+ *   out[n, g*OH*OW + ow*OH + oh] = bias[g] + sum_{c,kw,kh}
+ *        Xpad[n, c, ow+kw, oh+kh] * kernel[(c*KW + kw)*KH + kh, g]
+ * OH = H + 2*pad_h - KH + 1, OW likewise.  Replaces, for
+ * ConvolutionComponent::Propagate (nnet0/nnet-component-nnet0.cc:423-446):
+ * _pad_zero + [_span_row_to_convmat + SGEMM + _copy_rows_at]* + _convmat_to_out
+ * + _add_mat_rep_vec.  bias may be NULL.  concat == 0 writes the raw
+ * [(pos*N + n) x G] matrix of CuMatrixBase::Conv2D(..., concat=false)
+ * (cnslmat/conv2D.cc:199). */
+void cudaF_conv2d_fprop(cudaStream_t st, int math, const float *in, MatrixDim in_dim,
+                        const float *kernel, MatrixDim kernel_dim, const float *bias,
+                        float *out, MatrixDim out_dim, int in_height, int in_width,
+                        int in_channel, int pad_height, int pad_width, int kernel_height,
+                        int kernel_width, int group, int concat);
+/* Input gradient:
+ *   in_deriv[n, c, w, h] = sum_{g,kw,kh} out_deriv[n, g, w+pad_w-kw, h+pad_h-kh]
+ *                          * kernel[(c*KW + kw)*KH + kh, g]
+ * One kernel for both branches of ConvolutionComponent::Backprop (:499-540):
+ * replaces TpInsideBlock + FlipMat + transpose + TpBlock + PaddingZero + Conv2D
+ * + TpBlock, or PaddingZero + FlipMat + Conv2D. */
+void cudaF_conv2d_dgrad(cudaStream_t st, int math, const float *out_deriv,
+                        MatrixDim out_deriv_dim, const float *kernel, MatrixDim kernel_dim,
+                        float *in_deriv, MatrixDim in_deriv_dim, int in_height,
+                        int in_width, int in_channel, int pad_height, int pad_width,
+                        int kernel_height, int kernel_width, int group);
+/* Weight gradient (un-normalised), rows already in linear_params_ order:
+ *   kernel_grad[(c*KW + kw)*KH + kh, g] = sum_{n,ow,oh} Xpad[n,c,ow+kw,oh+kh]
+ *                                         * out_deriv[n, g, ow, oh]
+ *   bias_grad[g] = sum_{n,ow,oh} out_deriv[n, g, ow, oh]        (may be NULL)
+ * Replaces, in ConvolutionComponent::Update (:745-765, 775): PaddingZero +
+ * TpBlock + TpInsideBlock + Conv2D(concat=false) + ModPermuteRow + AddRowSumMat.
+ * workspace: device scratch of kcnn_conv2d_wgrad_workspace() bytes (split-K
+ * partial sums), may be NULL when that returns 0. */
+void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value,
+                        MatrixDim in_value_dim, const float *out_deriv,
+                        MatrixDim out_deriv_dim, float *kernel_grad,
+                        MatrixDim kernel_grad_dim, float *bias_grad, void *workspace,
+                        int in_height, int in_width, int in_channel, int pad_height,
+                        int pad_width, int kernel_height, int kernel_width, int group);
+size_t kcnn_conv2d_wgrad_workspace(int num_rows, int in_height, int in_width,
+                                   int in_channel, int pad_height, int pad_width,
+                                   int kernel_height, int kernel_width, int group);
+
+/* Fully connected layer (AffineComponent, nnet2/nnet-component.cc:1216-1258).
+ * W is [out_dim x in_dim].
+ *   fprop : out = 1 * bias^T + in * W^T          (CopyRowsFromVec + SGEMM, :1224-1227)
+ *   dgrad : in_deriv = out_deriv * W             (:1246-1247)
+ *   wgrad : w_grad = out_deriv^T * in_value, bias_grad = column sums of out_deriv
+ *           (un-normalised; the SGEMM of nnet0/nnet-component-nnet0.cc:1141 and
+ *           the AddRowSumMat of :1137) */
+void cudaF_affine_fprop(cudaStream_t st, int math, const float *in, MatrixDim in_dim,
+                        const float *w, MatrixDim w_dim, const float *bias, float *out,
+                        MatrixDim out_dim);
+void cudaF_affine_dgrad(cudaStream_t st, int math, const float *out_deriv,
+                        MatrixDim out_deriv_dim, const float *w, MatrixDim w_dim,
+                        float *in_deriv, MatrixDim in_deriv_dim);
+void cudaF_affine_wgrad(cudaStream_t st, int math, const float *in_value,
+                        MatrixDim in_value_dim, const float *out_deriv,
+                        MatrixDim out_deriv_dim, float *w_grad, MatrixDim w_grad_dim,
+                        float *bias_grad);
+
+/* Momentum / weight-decay SGD in ONE pass over the parameters:
+ *   prev = momentum*prev; prev += decay_alpha*params; prev += grad_alpha*grad;
+ *   params += prev
+ * with the reference's four roundings (Scale, AddMat, AddMat, AddMat of
+ * nnet0/nnet-component-nnet0.cc:769-772 and :1139-1142) kept in order. */
+void cudaF_sgd_momentum_update(cudaStream_t st, float *params, MatrixDim params_dim,
+                               float *prev_grad, MatrixDim prev_grad_dim,
+                               const float *grad, MatrixDim grad_dim, float momentum,
+                               float decay_alpha, float grad_alpha);
+/* vec[i] = alpha * grad[i] + vec[i]  (the bias AddRowSumMat tail, :775 / :1137). */
+void cudaF_vec_axpy(cudaStream_t st, float *vec, const float *grad, int dim, float alpha);
+
+/* ---- glue between hot-path layers --------------------------- */
+
+/* RectifiedLinearComponent (nnet2/nnet-component.cc:799-827). */
+void cudaF_relu_fprop(cudaStream_t st, const float *in, MatrixDim in_dim, float *out,
+                      MatrixDim out_dim);
+void cudaF_relu_bprop(cudaStream_t st, const float *out_value, MatrixDim out_value_dim,
+                      const float *out_deriv, MatrixDim out_deriv_dim, float *in_deriv,
+                      MatrixDim in_deriv_dim);
+/* SoftmaxComponent::Propagate (:930-950): row softmax + floor 1e-20. */
+void cudaF_softmax_fprop(cudaStream_t st, const float *in, MatrixDim in_dim, float *out,
+                         MatrixDim out_dim);
+/* SoftmaxComponent::Backprop (:952-1000). */
+void cudaF_softmax_bprop(cudaStream_t st, const float *out_value, MatrixDim out_value_dim,
+                         const float *out_deriv, MatrixDim out_deriv_dim, float *in_deriv,
+                         MatrixDim in_deriv_dim);
+/* Hard-label cross-entropy: deriv[i, label_i] = 1 / post[i, label_i], else 0;
+ * objf_accum[0] += sum_i log post[i, label_i] (double, device). */
+void cudaF_xent_deriv(cudaStream_t st, const float *post, MatrixDim post_dim,
+                      const int *labels, float *deriv, MatrixDim deriv_dim,
+                      double *objf_accum);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CNSL_CNSLMAT_CNSL_CU_KERNELS_H_ */

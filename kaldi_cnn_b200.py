@@ -1,0 +1,13 @@
+"""Import alias: the package directory is named ``kaldi-cnn_b200`` (hyphen, as the
+project is), which Python cannot import by name.  ``import kaldi_cnn_b200`` loads
+that directory as a regular package."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kaldi-cnn_b200")
+_spec = importlib.util.spec_from_file_location(
+    __name__, os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)
