@@ -30,8 +30,11 @@
 namespace kcnn {
 
 // Decoded GEMM index: element offset contribution + window coordinate.
+// Offsets are 32-bit element counts: the reference indexes with int32 everywhere
+// (cnsl-cu-kernels.cu:32 "index = Ir*in_dim.stride + ..."), so rows*stride < 2^31 is
+// already the contract; the launchers check it.
 struct Ctx {
-  long long off;
+  int off;
   int dw, dh;
 };
 
@@ -44,7 +47,7 @@ constexpr int kInvalidCoord = -(1 << 28);   // makes the window test fail
 //   plain matrix rows      nb = nc = 1
 struct Dec3 {
   FastDiv div_bc, div_c;       // by nb*nc and by nc
-  long long sa, sb, sc, off0;
+  int sa, sb, sc, off0;
   int wb, hc, w0, h0;
   int count;                   // number of valid indices
   __device__ __forceinline__ Ctx operator()(int idx) const {
@@ -53,7 +56,7 @@ struct Dec3 {
     uint32_t a, bc, b, c;
     div_bc.divmod((uint32_t)idx, a, bc);
     div_c.divmod(bc, b, c);
-    r.off = (long long)a * sa + (long long)b * sb + (long long)c * sc + off0;
+    r.off = (int)a * sa + (int)b * sb + (int)c * sc + off0;
     r.dw = (int)b * wb + w0;
     r.dh = (int)c * hc + h0;
     return r;
@@ -65,7 +68,7 @@ struct Dec3 {
 // along their contiguous axis.
 struct Dec3Inner {
   FastDiv div_a, div_c;
-  long long sa, sb, sc, off0;
+  int sa, sb, sc, off0;
   int wb, hc, w0, h0;
   int count;
   __device__ __forceinline__ Ctx operator()(int idx) const {
@@ -74,7 +77,7 @@ struct Dec3Inner {
     uint32_t t, a, b, c;
     div_a.divmod((uint32_t)idx, t, a);
     div_c.divmod(t, b, c);
-    r.off = (long long)a * sa + (long long)b * sb + (long long)c * sc + off0;
+    r.off = (int)a * sa + (int)b * sb + (int)c * sc + off0;
     r.dw = (int)b * wb + w0;
     r.dh = (int)c * hc + h0;
     return r;
@@ -86,7 +89,7 @@ inline Dec3 make_dec3(int na, int nb, int nc, long long sa, long long sb, long l
   Dec3 d;
   d.div_bc = FastDiv((uint32_t)(nb * nc));
   d.div_c = FastDiv((uint32_t)nc);
-  d.sa = sa; d.sb = sb; d.sc = sc; d.off0 = off0;
+  d.sa = (int)sa; d.sb = (int)sb; d.sc = (int)sc; d.off0 = (int)off0;
   d.wb = wb; d.hc = hc; d.w0 = w0; d.h0 = h0;
   d.count = na * nb * nc;
   return d;
@@ -101,7 +104,7 @@ inline Dec3Inner make_dec3_inner(int nb, int nc, int na, long long sa, long long
   Dec3Inner d;
   d.div_a = FastDiv((uint32_t)na);
   d.div_c = FastDiv((uint32_t)nc);
-  d.sa = sa; d.sb = sb; d.sc = sc; d.off0 = off0;
+  d.sa = (int)sa; d.sb = (int)sb; d.sc = (int)sc; d.off0 = (int)off0;
   d.wb = wb; d.hc = hc; d.w0 = w0; d.h0 = h0;
   d.count = na * nb * nc;
   return d;

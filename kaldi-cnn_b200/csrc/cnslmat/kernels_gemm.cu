@@ -1,0 +1,273 @@
+// kaldi-cnn_b200/csrc/cnslmat/kernels_gemm.cu
+//
+// Entry points of the GEMM-shaped part of the hot path: convolution forward /
+// input-gradient / weight-gradient and the three affine GEMMs.  Each builds the
+// operand decoders (gemm_operands.cuh) for its tensor roles and launches either
+// the tcgen05 TF32 kernel (gemm_tc.cuh, KCNN_MATH_TF32_TC) or the FP32 CUDA-core
+// kernel (gemm_simt.cuh, KCNN_MATH_FP32_SIMT).
+//
+// Index algebra (verified against the reference's CPU loops):
+//   activation row n : col = h + w*H + c*H*W                      [C][W][H]
+//   kernel           : row = kh + kw*KH + c*KH*KW, col = g
+//   fprop  Y[n,g,ow,oh] = b[g] + sum_{c,kw,kh} Xp[n,c,ow+kw,oh+kh] K[c,kw,kh,g]
+//   dgrad  dX[n,c,w,h]  = sum_{g,kw,kh} dY[n,g,w+pw-kw,h+ph-kh] K[c,kw,kh,g]
+//   wgrad  dK[c,kw,kh,g]= sum_{n,ow,oh} Xp[n,c,ow+kw,oh+kh] dY[n,g,ow,oh]
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace kcnn {
+
+using Op33 = Operand<Dec3, Dec3>;
+using Op3I = Operand<Dec3, Dec3Inner>;
+using Out33 = OutputMap<Dec3, Dec3>;
+
+static void check_int32(const MatrixDim &d, const char *what) {
+  if ((long long)d.rows * d.stride >= (1ll << 31)) {
+    fprintf(stderr, "kaldi-cnn_b200: %s has rows*stride >= 2^31 (%d x %d); the hot path indexes "
+            "with int32 like the reference\n", what, d.rows, d.stride);
+    abort();
+  }
+}
+
+static Op33 make_op(const float *base, const Dec3 &mn, const Dec3 &k, int wlim, int hlim) {
+  Op33 o; o.base = base; o.mn = mn; o.k = k; o.wlim = wlim; o.hlim = hlim; return o;
+}
+static Out33 make_out(float *base, const Dec3 &m, const Dec3 &n, const float *bias_n) {
+  Out33 o; o.base = base; o.m = m; o.n = n; o.bias_n = bias_n; o.bias_m = nullptr; return o;
+}
+
+// Column sums over rows and over the `inner` positions of each map:
+//   out[g] = sum_{n < rows} sum_{p < inner} m[n*stride + g*inner + p]
+// (db of the convolution; inner = 1 gives AddRowSumMat for the affine layer).
+__global__ void __launch_bounds__(256)
+colsum_maps_kernel(const float *__restrict__ m, int rows, int stride, int inner,
+                   float *__restrict__ out, FastDiv div_inner) {
+  __shared__ float scratch[8];
+  const int g = blockIdx.x;
+  const float *base = m + (size_t)g * inner;
+  float s = 0.0f;
+  const int total = rows * inner;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    uint32_t n, p;
+    div_inner.divmod((uint32_t)e, n, p);
+    s += __ldg(base + (size_t)n * stride + p);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < 8 ? scratch[threadIdx.x] : 0.0f;
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[g] = s;
+  }
+}
+
+// inner == 1: a block owns 32 adjacent columns, reads 128-byte row segments.
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const float *__restrict__ m, int rows, int cols, int stride,
+                   float *__restrict__ out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float s = 0.0f;
+  if (col < cols)
+    for (int r = ty; r < rows; r += 8) s += __ldg(m + (size_t)r * stride + col);
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < cols) {
+    float v = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v += part[i][tx];
+    out[col] = v;
+  }
+}
+
+static void launch_colsum(cudaStream_t st, const float *m, int rows, int stride, int maps,
+                          int inner, float *out) {
+  if (maps == 0) return;
+  if (inner == 1)
+    KCNN_LAUNCH(colsum_rows_kernel, ceil_div_u(maps, 32), 256, 0, st, m, rows, maps, stride, out);
+  else
+    KCNN_LAUNCH(colsum_maps_kernel, maps, 256, 0, st, m, rows, stride, inner, out,
+                FastDiv((uint32_t)inner));
+}
+
+static int pick_splits(int M, int N, int K) {
+  long long tiles = (long long)((M + SBM - 1) / SBM) * ((N + SBN - 1) / SBN);
+  long long want = (2 * kNumSMs + tiles - 1) / tiles;
+  long long max_by_k = K / (8 * SBK);
+  if (max_by_k < 1) max_by_k = 1;
+  if (want > max_by_k) want = max_by_k;
+  if (want > 64) want = 64;
+  return (int)(want < 1 ? 1 : want);
+}
+
+struct ConvGeom {
+  int N, H, W, C, ph, pw, KH, KW, G, OH, OW, P, ks;
+};
+
+static ConvGeom conv_geom(int N, int H, int W, int C, int ph, int pw, int KH, int KW, int G) {
+  ConvGeom q;
+  q.N = N; q.H = H; q.W = W; q.C = C; q.ph = ph; q.pw = pw; q.KH = KH; q.KW = KW; q.G = G;
+  q.OH = H + 2 * ph - KH + 1;
+  q.OW = W + 2 * pw - KW + 1;
+  q.P = q.OH * q.OW;
+  q.ks = KH * KW;
+  return q;
+}
+
+}  // namespace kcnn
+
+using namespace kcnn;
+
+extern "C" {
+
+void cudaF_conv2d_fprop(cudaStream_t st, int math, const float *in, MatrixDim id,
+                        const float *kernel, MatrixDim kd, const float *bias, float *out,
+                        MatrixDim od, int H, int W, int C, int ph, int pw, int KH, int KW, int G,
+                        int concat) {
+  ConvGeom q = conv_geom(id.rows, H, W, C, ph, pw, KH, KW, G);
+  if (q.N == 0 || q.P <= 0 || G == 0) return;
+  check_int32(id, "conv input"); check_int32(od, "conv output"); check_int32(kd, "conv kernel");
+  const int M = q.N * q.P, K = q.ks * C;
+  // A(m = (n, ow, oh), k = (c, kw, kh)) = Xpad[n, c, ow + kw, oh + kh]
+  Op33 a = make_op(in,
+      make_dec3(q.N, q.OW, q.OH, id.stride, H, 1, -pw * H - ph, 1, 1, -pw, -ph),
+      make_dec3(C, KW, KH, H * W, H, 1, 0, 1, 1, 0, 0), W, H);
+  // B(k, g) = kernel[k, g]
+  Op33 b = make_op(kernel, make_linear(G, 1), make_linear(K, kd.stride), 1, 1);
+  Out33 o = concat
+      // out[n, g*P + pos]                      (folds _convmat_to_out)
+      ? make_out(out, make_dec3(q.N, q.P, 1, od.stride, 1, 0, 0, 0, 0, 0, 0), make_linear(G, q.P), bias)
+      // out[pos*N + n, g]                      (concat = false, conv2D.cc:199)
+      : make_out(out, make_dec3(q.N, q.P, 1, od.stride, (long long)q.N * od.stride, 0, 0, 0, 0, 0, 0),
+                 make_linear(G, 1), bias);
+  if (math == KCNN_MATH_TF32_TC && tc_conv_fprop(st, in, id, kernel, kd, bias, out, od, q.N, H, W, C,
+                                                 ph, pw, KH, KW, G, concat))
+    return;
+  const bool a_fast_k = (q.OH == 1 && KH > 1);   // time-axis layers: the (kw, kh) run is contiguous
+  if (concat) {
+    if (a_fast_k) launch_gemm_simt<true, false, false>(st, a, b, o, M, G, K, 1, nullptr);
+    else          launch_gemm_simt<false, false, false>(st, a, b, o, M, G, K, 1, nullptr);
+  } else {
+    if (a_fast_k) launch_gemm_simt<true, false, true>(st, a, b, o, M, G, K, 1, nullptr);
+    else          launch_gemm_simt<false, false, true>(st, a, b, o, M, G, K, 1, nullptr);
+  }
+}
+
+void cudaF_conv2d_dgrad(cudaStream_t st, int math, const float *out_deriv, MatrixDim odd,
+                        const float *kernel, MatrixDim kd, float *in_deriv, MatrixDim idd, int H,
+                        int W, int C, int ph, int pw, int KH, int KW, int G) {
+  ConvGeom q = conv_geom(odd.rows, H, W, C, ph, pw, KH, KW, G);
+  if (q.N == 0 || C == 0) return;
+  check_int32(odd, "conv out_deriv"); check_int32(idd, "conv in_deriv"); check_int32(kd, "conv kernel");
+  const int M = q.N * H * W, K = q.ks * G;
+  if (math == KCNN_MATH_TF32_TC && tc_conv_dgrad(st, out_deriv, odd, kernel, kd, in_deriv, idd, q.N,
+                                                 H, W, C, ph, pw, KH, KW, G))
+    return;
+  // A(m = (n, w, h), k = (kw, kh, g)) = dY[n, g, w + pw - kw, h + ph - kh]
+  // (folds PaddingZero of out_deriv and the 180-degree rotation of FlipMat)
+  Op3I a; a.base = out_deriv;
+  a.mn = make_dec3(q.N, W, H, odd.stride, q.OH, 1, pw * q.OH + ph, 1, 1, pw, ph);
+  a.k = make_dec3_inner(KW, KH, G, q.P, -q.OH, -1, 0, -1, -1, 0, 0);
+  a.wlim = q.OW; a.hlim = q.OH;
+  // B(k = (kw, kh, g), c) = kernel[(c*KW + kw)*KH + kh, g]   (folds FlipMat's in/out swap)
+  Op3I b; b.base = kernel;
+  b.mn = make_linear(C, (long long)q.ks * kd.stride);
+  b.k = make_dec3_inner(KW, KH, G, 1, (long long)KH * kd.stride, kd.stride, 0, 0, 0, 0, 0);
+  b.wlim = 1; b.hlim = 1;
+  // dX[n, c*H*W + w*H + h]
+  Out33 o = make_out(in_deriv, make_dec3(q.N, H * W, 1, idd.stride, 1, 0, 0, 0, 0, 0, 0),
+                     make_linear(C, H * W), nullptr);
+  launch_gemm_simt<false, true, false>(st, a, b, o, M, C, K, 1, nullptr);
+}
+
+size_t kcnn_conv2d_wgrad_workspace(int num_rows, int H, int W, int C, int ph, int pw, int KH,
+                                   int KW, int G) {
+  ConvGeom q = conv_geom(num_rows, H, W, C, ph, pw, KH, KW, G);
+  int M = q.ks * C, K = q.N * q.P;
+  if (M <= 0 || G <= 0 || K <= 0) return 0;
+  size_t simt = (size_t)pick_splits(M, G, K) * M * G * sizeof(float);
+  size_t tc = tc_conv_wgrad_workspace(q.N, H, W, C, ph, pw, KH, KW, G);
+  return simt > tc ? simt : tc;
+}
+
+void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, MatrixDim ivd,
+                        const float *out_deriv, MatrixDim odd, float *kernel_grad, MatrixDim kgd,
+                        float *bias_grad, void *workspace, int H, int W, int C, int ph, int pw,
+                        int KH, int KW, int G) {
+  ConvGeom q = conv_geom(ivd.rows, H, W, C, ph, pw, KH, KW, G);
+  if (q.N == 0 || q.P <= 0 || G == 0 || C == 0) return;
+  check_int32(ivd, "conv in_value"); check_int32(odd, "conv out_deriv");
+  const int M = q.ks * C, K = q.N * q.P;
+  if (bias_grad) launch_colsum(st, out_deriv, q.N, odd.stride, G, q.P, bias_grad);
+  if (math == KCNN_MATH_TF32_TC && tc_conv_wgrad(st, in_value, ivd, out_deriv, odd, kernel_grad, kgd,
+                                                 workspace, q.N, H, W, C, ph, pw, KH, KW, G))
+    return;
+  // A(m = (c, kw, kh), k = (n, ow, oh)) = Xpad[n, c, ow + kw, oh + kh]
+  // (folds PaddingZero + TpBlock; row order (c, kw, kh) folds ModPermuteRow)
+  Op33 a = make_op(in_value,
+      make_dec3(C, KW, KH, H * W, H, 1, -pw * H - ph, 1, 1, -pw, -ph),
+      make_dec3(q.N, q.OW, q.OH, ivd.stride, H, 1, 0, 1, 1, 0, 0), W, H);
+  // B(k = (n, pos), g) = dY[n, g*P + pos]      (folds TpInsideBlock)
+  Op33 b = make_op(out_deriv, make_linear(G, q.P),
+                   make_dec3(q.N, q.P, 1, odd.stride, 1, 0, 0, 0, 0, 0, 0), 1, 1);
+  Out33 o = make_out(kernel_grad, make_linear(M, kgd.stride), make_linear(G, 1), nullptr);
+  int splits = pick_splits(M, G, K);
+  if (splits > 1 && workspace == nullptr) splits = 1;
+  const bool a_fast_k = !(q.OH == 1 && KH > 1);
+  const bool b_fast_k = q.P >= 4;
+  float *ws = static_cast<float *>(workspace);
+  if (a_fast_k && b_fast_k)       launch_gemm_simt<true, true, true>(st, a, b, o, M, G, K, splits, ws);
+  else if (a_fast_k && !b_fast_k) launch_gemm_simt<true, false, true>(st, a, b, o, M, G, K, splits, ws);
+  else if (!a_fast_k && b_fast_k) launch_gemm_simt<false, true, true>(st, a, b, o, M, G, K, splits, ws);
+  else                            launch_gemm_simt<false, false, true>(st, a, b, o, M, G, K, splits, ws);
+}
+
+void cudaF_affine_fprop(cudaStream_t st, int math, const float *in, MatrixDim id, const float *w,
+                        MatrixDim wd, const float *bias, float *out, MatrixDim od) {
+  const int M = id.rows, N = wd.rows, K = wd.cols;
+  if (M == 0 || N == 0) return;
+  check_int32(id, "affine input"); check_int32(od, "affine output"); check_int32(wd, "affine weights");
+  if (math == KCNN_MATH_TF32_TC && tc_affine_fprop(st, in, id, w, wd, bias, out, od)) return;
+  // out = 1 bias^T + in W^T : A(m, k) = in[m, k], B(k, n) = W[n, k]
+  Op33 a = make_op(in, make_linear(M, id.stride), make_linear(K, 1), 1, 1);
+  Op33 b = make_op(w, make_linear(N, wd.stride), make_linear(K, 1), 1, 1);
+  Out33 o = make_out(out, make_linear(M, od.stride), make_linear(N, 1), bias);
+  launch_gemm_simt<true, true, true>(st, a, b, o, M, N, K, 1, nullptr);
+}
+
+void cudaF_affine_dgrad(cudaStream_t st, int math, const float *out_deriv, MatrixDim odd,
+                        const float *w, MatrixDim wd, float *in_deriv, MatrixDim idd) {
+  const int M = odd.rows, N = wd.cols, K = wd.rows;
+  if (M == 0 || N == 0) return;
+  check_int32(odd, "affine out_deriv"); check_int32(idd, "affine in_deriv");
+  if (math == KCNN_MATH_TF32_TC && tc_affine_dgrad(st, out_deriv, odd, w, wd, in_deriv, idd)) return;
+  // in_deriv = out_deriv W : A(m, k) = dY[m, k], B(k, n) = W[k, n]
+  Op33 a = make_op(out_deriv, make_linear(M, odd.stride), make_linear(K, 1), 1, 1);
+  Op33 b = make_op(w, make_linear(N, 1), make_linear(K, wd.stride), 1, 1);
+  Out33 o = make_out(in_deriv, make_linear(M, idd.stride), make_linear(N, 1), nullptr);
+  launch_gemm_simt<true, false, true>(st, a, b, o, M, N, K, 1, nullptr);
+}
+
+void cudaF_affine_wgrad(cudaStream_t st, int math, const float *in_value, MatrixDim ivd,
+                        const float *out_deriv, MatrixDim odd, float *w_grad, MatrixDim wgd,
+                        float *bias_grad) {
+  const int M = odd.cols, N = ivd.cols, K = ivd.rows;
+  if (M == 0 || N == 0) return;
+  check_int32(ivd, "affine in_value"); check_int32(odd, "affine out_deriv");
+  if (bias_grad) launch_colsum(st, out_deriv, odd.rows, odd.stride, M, 1, bias_grad);
+  if (math == KCNN_MATH_TF32_TC && tc_affine_wgrad(st, in_value, ivd, out_deriv, odd, w_grad, wgd))
+    return;
+  // w_grad = out_deriv^T in_value : A(m, k) = dY[k, m], B(k, n) = X[k, n]
+  Op33 a = make_op(out_deriv, make_linear(M, 1), make_linear(K, odd.stride), 1, 1);
+  Op33 b = make_op(in_value, make_linear(N, 1), make_linear(K, ivd.stride), 1, 1);
+  Out33 o = make_out(w_grad, make_linear(M, wgd.stride), make_linear(N, 1), nullptr);
+  launch_gemm_simt<false, false, true>(st, a, b, o, M, N, K, 1, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// cudamatrix/cu-device.h -- shim: the CuDevice singleton.
+//
+// Kaldi's CuDevice selects the GPU, owns a caching allocator and accumulates a
+// per-function host-side profile (AccuProfile, printed by PrintProfile; used
+// after every launch in the reference, e.g. cnslmat/conv2D.cc:110).  This shim
+// keeps those entry points and adds the one thing the B200 build needs: the
+// CUDA stream every member launches on (default: the legacy default stream, as
+// in Kaldi; bench.py / the C API point it at the caller's stream so the whole
+// step is stream-ordered and CUDA-graph capturable).
+#ifndef KALDI_CUDAMATRIX_CU_DEVICE_H_
+#define KALDI_CUDAMATRIX_CU_DEVICE_H_
+
+#include <cuda_runtime_api.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "base/kaldi-common.h"
+
+namespace kaldi {
+
+class CuDevice {
+ public:
+  static CuDevice &Instantiate() { static CuDevice d; return d; }
+
+  /// "yes" / "no" / "optional" as in Kaldi.  "no" leaves the device disabled,
+  /// and every CuMatrix operation then fails loudly: this build has no CPU path.
+  void SelectGpuId(std::string use_gpu);
+  bool Enabled() const { return enabled_; }
+
+  void AccuProfile(const std::string &key, double time) {
+    if (profile_) profile_map_[key] += time;
+  }
+  void PrintProfile();
+  void EnableProfile(bool on) { profile_ = on; }
+
+  cudaStream_t Stream() const { return stream_; }
+  void SetStream(cudaStream_t s);
+
+  /// Caching allocator (device memory is reused across Resize calls so the
+  /// per-minibatch temporaries of the host code cost no cudaMalloc in steady state).
+  void *Malloc(size_t bytes);
+  void Free(void *ptr);
+  void ReleaseCache();
+  size_t BytesAllocated() const { return bytes_allocated_; }
+
+  /// Rows are pitched to a multiple of 16 bytes so 128-bit and TMA paths apply.
+  static int32 PitchInElements(int32 cols, size_t elem_size) {
+    int32 q = 16 / (int32)elem_size;
+    return ((cols + q - 1) / q) * q;
+  }
+
+  void RequireEnabled(const char *what) const {
+    if (!enabled_) KALDI_ERR << what << ": no CUDA device is selected and this is the GPU build "
+                             << "(no CPU fallback). Call CuDevice::Instantiate().SelectGpuId(\"yes\").";
+  }
+
+ private:
+  CuDevice() : enabled_(false), profile_(false), stream_(0), bytes_allocated_(0) {}
+  ~CuDevice() {}
+  bool enabled_, profile_;
+  cudaStream_t stream_;
+  std::map<std::string, double> profile_map_;
+  std::map<size_t, std::vector<void *> > free_;
+  std::map<void *, size_t> live_;
+  size_t bytes_allocated_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(CuDevice);
+};
+
+}  // namespace kaldi
+#endif
