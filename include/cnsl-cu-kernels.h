@@ -257,6 +257,12 @@ void cudaF_sgd_momentum_update(cudaStream_t st, float *params, MatrixDim params_
                                float *prev_grad, MatrixDim prev_grad_dim,
                                const float *grad, MatrixDim grad_dim, float momentum,
                                float decay_alpha, float grad_alpha);
+/* out[g] = sum over rows n and over the `inner` adjacent columns of map g of
+ * m[n, g*inner + p]; m has out_count*inner columns.  inner = 1 is the column-sum
+ * half of CuVectorBase::AddRowSumMat (:775, :1137); inner = OH*OW gives the
+ * convolution's bias gradient straight from out_deriv (no TpInsideBlock copy). */
+void cudaF_sum_rows_per_map(cudaStream_t st, const float *m, MatrixDim m_dim, int inner,
+                            float *out);
 /* vec[i] = alpha * grad[i] + vec[i]  (the bias AddRowSumMat tail, :775 / :1137). */
 void cudaF_vec_axpy(cudaStream_t st, float *vec, const float *grad, int dim, float alpha);
 

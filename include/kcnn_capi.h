@@ -1,0 +1,188 @@
+/*
+ * include/kcnn_capi.h -- C ABI over the L1 members and L2 components of
+ * libkaldicnn_b200.so, for hosts that are not Kaldi C++ (tests and bench.py bind it with
+ * ctypes; a cgo / JNI / N-API stub would bind the same symbols).
+ *
+ * A Kaldi C++ host does not need this header: it includes
+ * nnet0/nnet-component-nnet0.h and gets the components through nnet2's
+ * Component::NewComponentOfType (reference nnet2/nnet-component.cc:112-117), exactly as
+ * with the reference.  Every function here is a thin forwarder to that C++ interface;
+ * each comment names the reference interface it exposes.
+ *
+ * Conventions: matrices are float, row-major, (pointer, rows, cols, stride) with
+ * stride >= cols in elements -- Kaldi's MatrixDim.  Unless a name ends in _host all
+ * pointers are DEVICE pointers and calls are asynchronous on the stream set with
+ * kcnn_set_compute_stream().  Functions returning int return 0 on success and -1 on
+ * error (message: kcnn_last_error()); a Kaldi assertion or KALDI_ERR in the C++ layer
+ * is reported that way instead of aborting the host process.
+ */
+#ifndef KCNN_CAPI_H_
+#define KCNN_CAPI_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kcnn_component kcnn_component;   /* a kaldi::nnet2::Component*            */
+typedef struct kcnn_nnet kcnn_nnet;             /* Nnet + NnetMinibatchUpdater            */
+
+/* ---- device / library --------------------------------------------------------- */
+
+/* CuDevice::Instantiate().SelectGpuId(use_gpu): "yes" | "no" | "optional". */
+int kcnn_select_gpu(const char *use_gpu);
+/* Stream every member / component launches on (default: legacy default stream). */
+void kcnn_set_compute_stream(void *cuda_stream);
+/* KCNN_MATH_FP32_SIMT (0, default) or KCNN_MATH_TF32_TC (1): CuDevice::SetMathMode. */
+void kcnn_set_math_mode(int mode);
+int kcnn_get_math_mode(void);
+/* Seed of CuMatrix::SetRandn (parameter initialisation). */
+void kcnn_set_rand_seed(unsigned long long seed);
+const char *kcnn_last_error(void);
+/* CuDevice::PrintProfile / AccuProfile switch (reference cnslmat/conv2D.cc:110). */
+void kcnn_enable_profile(int on);
+void kcnn_print_profile(void);
+/* Bytes currently held by the caching device allocator. */
+size_t kcnn_device_bytes_allocated(void);
+
+/* ---- L1: CuMatrixBase members (reference cudamatrix/cu-matrix.h:451-482) --------- */
+/* 'this' is (a, a_rows, a_cols, a_stride).  Shape rules, resize rules and assertions
+ * are those of cnslmat/conv2D.cc; outputs declared CuMatrix<Real>* there must arrive
+ * with the final shape here (a foreign buffer cannot be resized). */
+
+int kcnn_mat_conv2d(const float *a, int a_rows, int a_cols, int a_stride,
+                    const float *kernel, int k_rows, int k_cols, int k_stride,
+                    int in_height, int in_width, int in_channel, int kernel_height,
+                    int kernel_width, int group,
+                    float *out, int o_rows, int o_cols, int o_stride, int concat);
+int kcnn_mat_add_mat_rep_vec(float *a, int a_rows, int a_cols, int a_stride,
+                             const float *vec, int vec_dim, int rep);
+int kcnn_mat_flip_mat(const float *a, int a_rows, int a_cols, int a_stride,
+                      int kernel_height, int kernel_width, int in_channel, int group,
+                      float *flip, int f_rows, int f_cols, int f_stride);
+int kcnn_mat_padding_zero(const float *a, int a_rows, int a_cols, int a_stride,
+                          int orig_height, int orig_width, int orig_channel,
+                          int kernel_height, int kernel_width,
+                          float *pad, int p_rows, int p_cols, int p_stride);
+int kcnn_mat_tp_block(const float *a, int a_rows, int a_cols, int a_stride,
+                      int in_channel, int block_size,
+                      float *out, int o_rows, int o_cols, int o_stride);
+int kcnn_mat_tp_inside_block(const float *a, int a_rows, int a_cols, int a_stride,
+                             int group, int block_size,
+                             float *out, int o_rows, int o_cols, int o_stride);
+int kcnn_mat_mod_permute_row(const float *a, int a_rows, int a_cols, int a_stride,
+                             int in_channel, int block_size,
+                             float *out, int o_rows, int o_cols, int o_stride);
+int kcnn_mat_maxpool_prop(const float *a, int a_rows, int a_cols, int a_stride,
+                          int in_height, int in_width, int pool_height_dim,
+                          int pool_width_dim, int pool_channel_dim, int overlap,
+                          int overlap2D, float *out, int o_rows, int o_cols, int o_stride);
+int kcnn_mat_maxpool_backprop(const float *a, int a_rows, int a_cols, int a_stride,
+                              const float *out_value, int ov_rows, int ov_cols, int ov_stride,
+                              const float *out_deriv, int od_rows, int od_cols, int od_stride,
+                              float *in_deriv, int id_rows, int id_cols, int id_stride,
+                              int in_height, int in_width, int pool_height_dim,
+                              int pool_width_dim, int pool_channel_dim, int overlap,
+                              int overlap2D);
+
+/* ---- L2: components (reference nnet2/nnet-component.h:157-269) -------------------- */
+
+/* Component::NewFromString: "ConvolutionComponent in-height=40 ..." (one nnet.config line). */
+kcnn_component *kcnn_component_new_from_string(const char *config_line);
+/* Component::ReadNew from a serialised component (binary != 0: Kaldi binary mode). */
+kcnn_component *kcnn_component_read(const char *data, size_t len, int binary);
+/* Component::Write into a malloc'ed buffer; release with kcnn_free(). */
+int kcnn_component_write(const kcnn_component *c, int binary, char **data, size_t *len);
+void kcnn_free(void *p);
+/* Component::Copy. */
+kcnn_component *kcnn_component_copy(const kcnn_component *c);
+void kcnn_component_delete(kcnn_component *c);
+const char *kcnn_component_type(const kcnn_component *c);       /* Component::Type()  */
+int kcnn_component_info(const kcnn_component *c, char *buf, size_t buf_len);   /* Info() */
+int kcnn_component_input_dim(const kcnn_component *c);
+int kcnn_component_output_dim(const kcnn_component *c);
+int kcnn_component_backprop_needs_input(const kcnn_component *c);
+int kcnn_component_backprop_needs_output(const kcnn_component *c);
+
+/* Component::Propagate(in_info, out_info, in, out) with ChunkInfo(dim, num_chunks, 0, 0). */
+int kcnn_component_propagate(const kcnn_component *c, int num_chunks,
+                             const float *in, int in_rows, int in_cols, int in_stride,
+                             float *out, int out_rows, int out_cols, int out_stride);
+/* Component::Backprop(in_info, out_info, in_value, out_value, out_deriv, to_update,
+ * in_deriv).  in_value / out_value may be NULL when BackpropNeedsInput / Output is false.
+ * to_update may be NULL (no update), c itself (ordinary SGD) or another component. */
+int kcnn_component_backprop(const kcnn_component *c, int num_chunks,
+                            const float *in_value, int iv_stride,
+                            const float *out_value, int ov_stride,
+                            const float *out_deriv, int od_rows, int od_stride,
+                            kcnn_component *to_update,
+                            float *in_deriv, int id_stride);
+
+/* Updatable components: parameter access.  which: 0 = linear_params_, 1 = bias_params_
+ * (rows = 1), 2 = prev_grad_.  Returns the device pointer and its shape. */
+int kcnn_component_params(kcnn_component *c, int which, float **data, int *rows, int *cols,
+                          int *stride);
+/* UpdatableComponent::{SetLearningRate, LearningRate}; Set{WeightDecay,Momentum}. */
+int kcnn_component_set_learning_rate(kcnn_component *c, float lr);
+float kcnn_component_learning_rate(const kcnn_component *c);
+int kcnn_component_set_weight_decay_momentum(kcnn_component *c, float weight_decay, float momentum);
+int kcnn_component_get_weight_decay_momentum(const kcnn_component *c, float *weight_decay, float *momentum);
+/* MaxpoolComponent::SetIndexRouting (B200 extension, see nnet-component-nnet0.h). */
+int kcnn_component_set_index_routing(kcnn_component *c, int on);
+
+/* Data-parallel split of the update (B200 extension): with deferred != 0 Backprop leaves
+ * the un-normalised gradient in the component's gradient buffers; after the caller has
+ * summed those over ranks, kcnn_component_apply_gradient(total_rows) performs the
+ * reference's update with lr / total_rows. */
+int kcnn_component_set_deferred_update(kcnn_component *c, int deferred);
+size_t kcnn_component_gradient_floats(const kcnn_component *c);
+int kcnn_component_set_gradient_storage(kcnn_component *c, float *base);
+/* which: 0 = weight gradient, 1 = bias gradient. */
+int kcnn_component_gradient(kcnn_component *c, int which, float **data, int *rows, int *cols,
+                            int *stride);
+int kcnn_component_apply_gradient(kcnn_component *c, int total_rows);
+
+/* ---- the callers of the path: a component sequence and one training step ---------- */
+
+/* nnet2 Nnet::Init from the text of an nnet.config (one component per line).
+ * skip_splice != 0 drops SpliceComponent lines (the input is then the spliced window). */
+kcnn_nnet *kcnn_nnet_new_from_config(const char *config_text, int skip_splice);
+kcnn_nnet *kcnn_nnet_read(const char *data, size_t len, int binary);
+int kcnn_nnet_write(const kcnn_nnet *n, int binary, char **data, size_t *len);
+void kcnn_nnet_delete(kcnn_nnet *n);
+int kcnn_nnet_num_components(const kcnn_nnet *n);
+kcnn_component *kcnn_nnet_component(kcnn_nnet *n, int index);   /* borrowed, do not delete */
+int kcnn_nnet_input_dim(const kcnn_nnet *n);
+int kcnn_nnet_output_dim(const kcnn_nnet *n);
+
+/* Forward through every component; feats is [rows x input_dim] on the device. */
+int kcnn_nnet_forward(kcnn_nnet *n, const float *feats, int rows, int stride);
+/* Cross-entropy derivative at the output for int32 device labels[rows]; the objective
+ * sum_i log p[i, label_i] accumulates on the device. */
+int kcnn_nnet_objf_and_deriv(kcnn_nnet *n, const int *labels);
+/* Backprop (with update unless deferred) through components last..first; last < 0 = top. */
+int kcnn_nnet_backward(kcnn_nnet *n, int last, int first);
+/* Output / activation access (device pointers, valid until the next forward). */
+int kcnn_nnet_activation(kcnn_nnet *n, int index, const float **data, int *rows, int *cols, int *stride);
+int kcnn_nnet_input_deriv(kcnn_nnet *n, const float **data, int *rows, int *cols, int *stride);
+/* Reads and clears the accumulated objective (synchronises the stream). */
+double kcnn_nnet_objf_and_reset(kcnn_nnet *n);
+/* Data-parallel: deferred updates + one gradient arena (top layer first). */
+int kcnn_nnet_set_deferred_update(kcnn_nnet *n, int deferred);
+size_t kcnn_nnet_gradient_floats(const kcnn_nnet *n);
+int kcnn_nnet_set_gradient_arena(kcnn_nnet *n, float *base);
+int kcnn_nnet_gradient_bucket(const kcnn_nnet *n, int component, size_t *offset, size_t *length);
+int kcnn_nnet_apply_gradients(kcnn_nnet *n, int total_rows);
+
+/* The whole step from HOST memory, the call a non-CUDA host makes: copies feats
+ * [rows x input_dim, packed] and labels[rows] to the device, runs forward, objective,
+ * backward + update, and returns the minibatch objective in *objf (synchronous). */
+int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const int *labels_host,
+                                   int rows, double *objf);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* KCNN_CAPI_H_ */

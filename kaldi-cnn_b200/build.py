@@ -21,7 +21,7 @@ LIB = os.path.join(LIBDIR, "libkaldicnn_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "-DHAVE_CUDA=1", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
           "-I" + os.path.join(CSRC, "cnslmat")]
 

@@ -78,6 +78,7 @@ _PROTOS = {
     "cudaF_affine_wgrad": [S, I, P, M, P, M, P, M, P],
     "cudaF_sgd_momentum_update": [S, P, M, P, M, P, M, F, F, F],
     "cudaF_vec_axpy": [S, P, P, I, F],
+    "cudaF_sum_rows_per_map": [S, P, M, I, P],
     "cudaF_relu_fprop": [S, P, M, P, M],
     "cudaF_relu_bprop": [S, P, M, P, M, P, M],
     "cudaF_softmax_fprop": [S, P, M, P, M],

@@ -228,6 +228,11 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   else                            launch_gemm_simt<false, false, true>(st, a, b, o, M, G, K, splits, ws);
 }
 
+void cudaF_sum_rows_per_map(cudaStream_t st, const float *m, MatrixDim md, int inner, float *out) {
+  if (inner <= 0 || md.cols == 0) return;
+  launch_colsum(st, m, md.rows, md.stride, md.cols / inner, inner, out);
+}
+
 void cudaF_affine_fprop(cudaStream_t st, int math, const float *in, MatrixDim id, const float *w,
                         MatrixDim wd, const float *bias, float *out, MatrixDim od) {
   const int M = id.rows, N = wd.rows, K = wd.cols;

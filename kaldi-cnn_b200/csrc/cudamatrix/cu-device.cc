@@ -6,6 +6,13 @@
 
 namespace kaldi {
 
+CuDevice::CuDevice()
+    : enabled_(false), profile_(false), math_mode_(KCNN_MATH_FP32_SIMT), rand_seed_(5489),
+      stream_(0), bytes_allocated_(0) {
+  const char *m = getenv("KCNN_MATH");
+  if (m && (std::string(m) == "tf32" || std::string(m) == "1")) math_mode_ = KCNN_MATH_TF32_TC;
+}
+
 void CuDevice::SelectGpuId(std::string use_gpu) {
   if (use_gpu == "no") { enabled_ = false; return; }
   int n = 0;

@@ -37,6 +37,16 @@ class CuDevice {
   cudaStream_t Stream() const { return stream_; }
   void SetStream(cudaStream_t s);
 
+  /// Arithmetic of the GEMM-shaped members (KCNN_MATH_FP32_SIMT = 0: FP32 FMA, the
+  /// accuracy class of the reference's SGEMM; KCNN_MATH_TF32_TC = 1: tcgen05 TF32).
+  /// Default FP32; the environment variable KCNN_MATH=tf32 or SetMathMode() selects TF32.
+  int MathMode() const { return math_mode_; }
+  void SetMathMode(int m) { math_mode_ = m; }
+
+  /// Seed of SetRandn() (host generator; parameters are initialised off the hot path).
+  void SetRandSeed(unsigned long long s) { rand_seed_ = s; }
+  unsigned long long NextRandSeed() { return rand_seed_++; }
+
   /// Caching allocator (device memory is reused across Resize calls so the
   /// per-minibatch temporaries of the host code cost no cudaMalloc in steady state).
   void *Malloc(size_t bytes);
@@ -56,9 +66,11 @@ class CuDevice {
   }
 
  private:
-  CuDevice() : enabled_(false), profile_(false), stream_(0), bytes_allocated_(0) {}
+  CuDevice();
   ~CuDevice() {}
   bool enabled_, profile_;
+  int math_mode_;
+  unsigned long long rand_seed_;
   cudaStream_t stream_;
   std::map<std::string, double> profile_map_;
   std::map<size_t, std::vector<void *> > free_;

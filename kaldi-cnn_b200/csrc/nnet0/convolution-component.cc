@@ -1,0 +1,486 @@
+// nnet0/convolution-component.cc -- ConvolutionComponent for the B200 build.
+// Follows reference src/nnet0/nnet-component-nnet0.cc:178-777 (cited per function).
+
+#include <sstream>
+
+#include "nnet0/nnet-component-nnet0.h"
+#include "util/common-utils.h"
+#include "cnsl-cu-kernels.h"
+
+namespace cnsl {
+namespace nnet0 {
+
+static inline cudaStream_t Str() { return CuDevice::Instantiate().Stream(); }
+static inline int Math() { return CuDevice::Instantiate().MathMode(); }
+
+ConvolutionComponent::ConvolutionComponent()     // defaults of reference .h:27
+    : is_gradient_(false), in_height_(0), in_width_(0), in_channel_(0), in_pad_height_(0),
+      in_pad_width_(0), kernel_height_(0), kernel_width_(0), stride_(1), group_(0), out_height_(0),
+      out_width_(0), weight_decay_(0.0002), momentum_(0.9), deferred_(false),
+      grad_external_(false), workspace_rows_(-1) {}
+
+// reference :178-195 (the copy constructor leaves prev_grad_ empty, App. C.3; here it
+// is sized and zeroed so that a copied component can be updated).
+ConvolutionComponent::ConvolutionComponent(const ConvolutionComponent &c)
+    : UpdatableComponent(c), linear_params_(c.linear_params_), bias_params_(c.bias_params_),
+      is_gradient_(c.is_gradient_), in_height_(c.in_height_), in_width_(c.in_width_),
+      in_channel_(c.in_channel_), in_pad_height_(c.in_pad_height_), in_pad_width_(c.in_pad_width_),
+      kernel_height_(c.kernel_height_), kernel_width_(c.kernel_width_), stride_(c.stride_),
+      group_(c.group_), out_height_(c.out_height_), out_width_(c.out_width_),
+      weight_decay_(c.weight_decay_), momentum_(c.momentum_), deferred_(false),
+      grad_external_(false), workspace_rows_(-1) {
+  prev_grad_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kSetZero);
+}
+
+// reference :199-229
+ConvolutionComponent::ConvolutionComponent(const CuMatrix<BaseFloat> &linear_params,
+                                           const CuVector<BaseFloat> &bias_params,
+                                           BaseFloat learning_rate, int32 in_height, int32 in_width,
+                                           int32 in_channels, int32 in_pad_height,
+                                           int32 in_pad_width, int32 kernel_height,
+                                           int32 kernel_width, int32 stride, int32 group,
+                                           int32 out_height, int32 out_width, BaseFloat weight_decay,
+                                           BaseFloat momentum)
+    : UpdatableComponent(learning_rate), linear_params_(linear_params), bias_params_(bias_params),
+      is_gradient_(false), in_height_(in_height), in_width_(in_width), in_channel_(in_channels),
+      in_pad_height_(in_pad_height), in_pad_width_(in_pad_width), kernel_height_(kernel_height),
+      kernel_width_(kernel_width), stride_(stride), group_(group), out_height_(out_height),
+      out_width_(out_width), weight_decay_(weight_decay), momentum_(momentum), deferred_(false),
+      grad_external_(false), workspace_rows_(-1) {
+  KALDI_ASSERT(linear_params.NumCols() == bias_params.Dim() && bias_params.Dim() != 0);
+  prev_grad_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kSetZero);
+}
+
+// reference :232-275
+void ConvolutionComponent::Init(BaseFloat learning_rate, int32 in_height, int32 in_width,
+                                int32 in_channels, int32 in_pad_height, int32 in_pad_width,
+                                int32 kernel_height, int32 kernel_width, int32 stride, int32 group,
+                                int32 out_height, int32 out_width, BaseFloat param_stddev,
+                                BaseFloat bias_stddev, BaseFloat weight_decay, BaseFloat momentum) {
+  in_height_ = in_height; in_width_ = in_width; in_channel_ = in_channels;
+  in_pad_height_ = in_pad_height; in_pad_width_ = in_pad_width;
+  kernel_height_ = kernel_height; kernel_width_ = kernel_width;
+  stride_ = stride; group_ = group;
+  out_height_ = out_height; out_width_ = out_width;
+  weight_decay_ = weight_decay; momentum_ = momentum;
+
+  KALDI_ASSERT(in_pad_height_ >= 0);
+  KALDI_ASSERT(in_pad_width_ >= 0);
+  KALDI_ASSERT(stride != 0);
+  KALDI_ASSERT(out_height_ == 1 + (in_height + (2 * in_pad_height) - kernel_height) / stride);
+  KALDI_ASSERT(out_width_ == 1 + (in_width + (2 * in_pad_width) - kernel_width) / stride);
+  // The reference parses "stride" but its Conv2D only implements stride 1
+  // (cnslmat/conv2D.cc:59-60); anything else silently mis-sizes the output there.
+  if (stride != 1)
+    KALDI_ERR << "ConvolutionComponent: stride=" << stride << " is not implemented (only stride 1)";
+
+  UpdatableComponent::Init(learning_rate);
+  linear_params_.Resize(KernelDim(), group);
+  bias_params_.Resize(group);
+  prev_grad_.Resize(KernelDim(), group);
+  KALDI_ASSERT(param_stddev >= 0.0);
+  linear_params_.SetRandn();
+  linear_params_.Scale(param_stddev);
+  prev_grad_.SetZero();
+  bias_params_.SetRandn();
+  bias_params_.Scale(bias_stddev);
+}
+
+// reference :277-321.  The matrix file holds [KernelDim()+1 x group]: weights, then bias.
+// (The reference sizes the bias as kernel_dim and reads a column, App. C.3 -- a defect
+// of an unused path; the bias here is the last ROW, one value per output map.)
+void ConvolutionComponent::Init(BaseFloat learning_rate, int32 in_height, int32 in_width,
+                                int32 in_channels, int32 in_pad_height, int32 in_pad_width,
+                                int32 kernel_height, int32 kernel_width, int32 stride, int32 group,
+                                int32 out_height, int32 out_width, BaseFloat weight_decay,
+                                BaseFloat momentum, std::string matrix_filename) {
+  in_height_ = in_height; in_width_ = in_width; in_channel_ = in_channels;
+  in_pad_height_ = in_pad_height; in_pad_width_ = in_pad_width;
+  kernel_height_ = kernel_height; kernel_width_ = kernel_width;
+  stride_ = stride; group_ = group;
+  out_height_ = out_height; out_width_ = out_width;
+  weight_decay_ = weight_decay; momentum_ = momentum;
+  if (stride != 1)
+    KALDI_ERR << "ConvolutionComponent: stride=" << stride << " is not implemented (only stride 1)";
+  UpdatableComponent::Init(learning_rate);
+  Matrix<BaseFloat> mat;
+  ReadKaldiObject(matrix_filename, &mat);
+  KALDI_ASSERT(mat.NumCols() >= 1);
+  int32 num_group = mat.NumCols(), kernel_dim = mat.NumRows() - 1;
+  KALDI_ASSERT(num_group == Group());
+  KALDI_ASSERT(kernel_dim == KernelDim());
+  Matrix<BaseFloat> w(kernel_dim, num_group);
+  Vector<BaseFloat> b(num_group);
+  for (int32 r = 0; r < kernel_dim; r++)
+    for (int32 c = 0; c < num_group; c++) w(r, c) = mat(r, c);
+  for (int32 c = 0; c < num_group; c++) b(c) = mat(kernel_dim, c);
+  linear_params_ = w;
+  bias_params_ = b;
+  prev_grad_.Resize(KernelDim(), group);
+  prev_grad_.SetZero();
+}
+
+// reference :323-385.  Key order and the quirk of App. C.2 are kept: "weight-decay" and
+// "momentum" are consumed AFTER Init, so the config values are swallowed but not
+// applied -- a freshly initialised conv layer runs with the constructor defaults
+// (0.0002 / 0.9) until SetWeightDecay / SetMomentum / Read change them.
+void ConvolutionComponent::InitFromString(std::string args) {
+  std::string orig_args(args);
+  bool ok = true;
+  BaseFloat learning_rate = learning_rate_;
+  BaseFloat weight_decay = weight_decay_, momentum = momentum_;
+  std::string matrix_filename;
+  int32 in_height = 0, in_width = 0, in_channel = 0, in_pad_height = 0, in_pad_width = 0,
+        kernel_height = 0, kernel_width = 0, stride = 1, group = 0, out_height = 0, out_width = 0;
+
+  ok = ok && ParseFromString("learning-rate", &args, &learning_rate);   // mandatory here
+  ok = ok && ParseFromString("in-height", &args, &in_height);
+  ok = ok && ParseFromString("in-width", &args, &in_width);
+  ok = ok && ParseFromString("in-channel", &args, &in_channel);
+  ParseFromString("in-pad-height", &args, &in_pad_height);
+  ParseFromString("in-pad-width", &args, &in_pad_width);
+  ok = ok && ParseFromString("kernel-height", &args, &kernel_height);
+  ok = ok && ParseFromString("kernel-width", &args, &kernel_width);
+  ok = ok && ParseFromString("stride", &args, &stride);
+  ok = ok && ParseFromString("group", &args, &group);
+  ok = ok && ParseFromString("out-height", &args, &out_height);
+  ok = ok && ParseFromString("out-width", &args, &out_width);
+  if (!ok) KALDI_ERR << "Bad initializer " << orig_args;
+  KALDI_ASSERT(stride != 0);
+  KALDI_ASSERT(out_height == 1 + (in_height + (2 * in_pad_height) - kernel_height) / stride &&
+               "out_height_ == 1 + (in_height + (2*in_pad_height) - kernel_height) / stride ");
+  KALDI_ASSERT(out_width == 1 + (in_width + (2 * in_pad_width) - kernel_width) / stride &&
+               "out_width == 1 + (in_width + (2*in_pad_width) - kernel_width) / stride");
+  KALDI_ASSERT(in_pad_height >= 0 && "in-pad-height should be positive");
+  KALDI_ASSERT(in_pad_width >= 0 && "in-pad-width should be positive");
+
+  if (ParseFromString("matrix", &args, &matrix_filename)) {
+    Init(learning_rate, in_height, in_width, in_channel, in_pad_height, in_pad_width, kernel_height,
+         kernel_width, stride, group, out_height, out_width, weight_decay, momentum, matrix_filename);
+  } else {
+    BaseFloat param_stddev = 1.0 / std::sqrt(kernel_height * kernel_width), bias_stddev = 1.0;
+    ParseFromString("param-stddev", &args, &param_stddev);
+    ParseFromString("bias-stddev", &args, &bias_stddev);
+    Init(learning_rate, in_height, in_width, in_channel, in_pad_height, in_pad_width, kernel_height,
+         kernel_width, stride, group, out_height, out_width, param_stddev, bias_stddev, weight_decay,
+         momentum);
+  }
+  ParseFromString("weight-decay", &args, &weight_decay);   // consumed, not applied (C.2)
+  ParseFromString("momentum", &args, &momentum);
+  if (!args.empty()) KALDI_ERR << "Could not process these elements in initializer: " << args;
+}
+
+// reference :387-421
+std::string ConvolutionComponent::Info() const {
+  std::stringstream stream;
+  BaseFloat linear_params_size = static_cast<BaseFloat>(linear_params_.NumRows()) *
+                                 static_cast<BaseFloat>(linear_params_.NumCols());
+  BaseFloat linear_stddev = std::sqrt(TraceMatMat(linear_params_, linear_params_, kTrans) / linear_params_size),
+            bias_stddev = std::sqrt(VecVec(bias_params_, bias_params_) / bias_params_.Dim());
+  stream << Type() << ", input-dim=" << InputDim() << " ( in-height=" << In_height()
+         << ", in-width=" << In_width() << ", in-channels=" << In_channels()
+         << "), output-dim=" << OutputDim() << " ( out-height=" << Out_height()
+         << ", out-width=" << Out_width() << ", group-num=" << Group()
+         << "), kernel-dim=" << KernelDim() << " ( kernel-height=" << Kernel_height()
+         << ", kernel-width=" << Kernel_width() << "), ( padding-height=" << in_pad_height_
+         << ", padding-width=" << in_pad_width_ << "), linear-params-stddev=" << linear_stddev
+         << ", bias-params-stddev=" << bias_stddev << ", learning-rate=" << LearningRate()
+         << ", weight-decay=" << weight_decay_ << ", momentum=" << momentum_;
+  return stream.str();
+}
+
+// reference :423-446: [PaddingZero] -> Conv2D -> AddMatRepVec, here ONE implicit GEMM
+// whose addressing supplies the zero border and whose epilogue adds the bias.
+void ConvolutionComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &,
+                                     const CuMatrixBase<BaseFloat> &in,
+                                     CuMatrixBase<BaseFloat> *out) const {
+  KALDI_ASSERT(in.NumCols() == InputDim() && out != NULL);
+  KALDI_ASSERT(in.NumRows() == in_info.NumChunks() || in_pad_height_ + in_pad_width_ == 0);
+  KALDI_ASSERT(out->NumRows() == in.NumRows() && out->NumCols() == OutputDim());
+  CuDevice::Instantiate().RequireEnabled("ConvolutionComponent::Propagate");
+  Timer tim;
+  cudaF_conv2d_fprop(Str(), Math(), in.Data(), in.Dim(), linear_params_.Data(), linear_params_.Dim(),
+                     bias_params_.Data(), out->Data(), out->Dim(), in_height_, in_width_, in_channel_,
+                     in_pad_height_, in_pad_width_, kernel_height_, kernel_width_, group_, 1);
+  CU_SAFE_CALL(cudaGetLastError());
+  CuDevice::Instantiate().AccuProfile(__func__, tim.Elapsed());
+}
+
+void ConvolutionComponent::Scale(BaseFloat scale) {      // reference :448-451
+  linear_params_.Scale(scale);
+  bias_params_.Scale(scale);
+}
+
+void ConvolutionComponent::Add(BaseFloat alpha, const UpdatableComponent &other_in) {   // :453-459
+  const ConvolutionComponent *other = dynamic_cast<const ConvolutionComponent *>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  linear_params_.AddMat(alpha, other->linear_params_);
+  bias_params_.AddVec(alpha, other->bias_params_);
+}
+
+// reference :461-544.  The reference picks between two data movements by comparing the
+// padded-kernel and padded-out_deriv sizes (:489-497); both evaluate the same sum
+//   dX[n,c,w,h] = sum_{g,kw,kh} dY[n,g,w+pw-kw,h+ph-kh] K[c,kw,kh,g]
+// which is one implicit GEMM here, so the branch disappears.  Then Update, as there.
+void ConvolutionComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
+                                    const CuMatrixBase<BaseFloat> &in_value,
+                                    const CuMatrixBase<BaseFloat> &,   // out_value
+                                    const CuMatrixBase<BaseFloat> &out_deriv,
+                                    Component *to_update_in, CuMatrix<BaseFloat> *in_deriv) const {
+  ConvolutionComponent *to_update = dynamic_cast<ConvolutionComponent *>(to_update_in);
+  KALDI_ASSERT(out_deriv.NumCols() == OutputDim());
+  CuDevice::Instantiate().RequireEnabled("ConvolutionComponent::Backprop");
+  if (in_deriv != NULL) {
+    if (in_deriv->NumRows() != out_deriv.NumRows() || in_deriv->NumCols() != InputDim())
+      in_deriv->Resize(out_deriv.NumRows(), InputDim(), kUndefined);
+    Timer tim;
+    cudaF_conv2d_dgrad(Str(), Math(), out_deriv.Data(), out_deriv.Dim(), linear_params_.Data(),
+                       linear_params_.Dim(), in_deriv->Data(), in_deriv->Dim(), in_height_, in_width_,
+                       in_channel_, in_pad_height_, in_pad_width_, kernel_height_, kernel_width_,
+                       group_);
+    CU_SAFE_CALL(cudaGetLastError());
+    CuDevice::Instantiate().AccuProfile(__func__, tim.Elapsed());
+  }
+  if (to_update != NULL) to_update->Update(in_value, out_deriv);
+}
+
+void ConvolutionComponent::SetZero(bool treat_as_gradient) {      // reference :546-554
+  if (treat_as_gradient) SetLearningRate(1.0);
+  linear_params_.SetZero();
+  bias_params_.SetZero();
+  if (treat_as_gradient) is_gradient_ = true;
+}
+
+// Serialisation: token order of reference :556-666, written from one table so Read and
+// Write cannot drift apart.
+void ConvolutionComponent::Read(std::istream &is, bool binary) {
+  const std::string beg = "<" + Type() + ">", end = "</" + Type() + ">";
+  ExpectOneOrTwoTokens(is, binary, beg, "<in_height>");
+  ReadBasicType(is, binary, &in_height_);
+  struct { const char *tok; int32 *field; } ints[] = {
+      {"<in_width>", &in_width_}, {"<in_channel>", &in_channel_},
+      {"<kernel_height>", &kernel_height_}, {"<kernel_width>", &kernel_width_},
+      {"<stride>", &stride_}, {"<padding_height>", &in_pad_height_},
+      {"<padding_width>", &in_pad_width_}, {"<group>", &group_},
+      {"<out_height>", &out_height_}, {"<out_width>", &out_width_}};
+  for (size_t i = 0; i < sizeof(ints) / sizeof(ints[0]); i++) {
+    ExpectToken(is, binary, ints[i].tok);
+    ReadBasicType(is, binary, ints[i].field);
+  }
+  ExpectToken(is, binary, "<LearningRate>");
+  ReadBasicType(is, binary, &learning_rate_);
+  ExpectToken(is, binary, "<WeightDecay>");
+  ReadBasicType(is, binary, &weight_decay_);
+  ExpectToken(is, binary, "<Momentum>");
+  ReadBasicType(is, binary, &momentum_);
+  ExpectToken(is, binary, "<LinearParams>");
+  linear_params_.Read(is, binary);
+  ExpectToken(is, binary, "<BiasParams>");
+  bias_params_.Read(is, binary);
+  ExpectToken(is, binary, "<PrevGrad>");
+  prev_grad_.Read(is, binary);
+  std::string tok;
+  ReadToken(is, binary, &tok);
+  if (tok == "<AvgInput>") {   // back-compatibility (:603-610): discard
+    CuVector<BaseFloat> avg_input;
+    avg_input.Read(is, binary);
+    BaseFloat avg_input_count;
+    ExpectToken(is, binary, "<AvgInputCount>");
+    ReadBasicType(is, binary, &avg_input_count);
+    ReadToken(is, binary, &tok);
+  }
+  if (tok == "<IsGradient>") {
+    ReadBasicType(is, binary, &is_gradient_);
+    ExpectToken(is, binary, end);
+  } else {
+    is_gradient_ = false;
+    KALDI_ASSERT(tok == end);
+  }
+  workspace_rows_ = -1;
+}
+
+void ConvolutionComponent::Write(std::ostream &os, bool binary) const {
+  const std::string beg = "<" + Type() + ">", end = "</" + Type() + ">";
+  WriteToken(os, binary, beg);
+  struct { const char *tok; int32 value; } ints[] = {
+      {"<in_height>", in_height_}, {"<in_width>", in_width_}, {"<in_channel>", in_channel_},
+      {"<kernel_height>", kernel_height_}, {"<kernel_width>", kernel_width_},
+      {"<stride>", stride_}, {"<padding_height>", in_pad_height_},
+      {"<padding_width>", in_pad_width_}, {"<group>", group_},
+      {"<out_height>", out_height_}, {"<out_width>", out_width_}};
+  for (size_t i = 0; i < sizeof(ints) / sizeof(ints[0]); i++) {
+    WriteToken(os, binary, ints[i].tok);
+    WriteBasicType(os, binary, ints[i].value);
+  }
+  WriteToken(os, binary, "<LearningRate>");
+  WriteBasicType(os, binary, learning_rate_);
+  WriteToken(os, binary, "<WeightDecay>");
+  WriteBasicType(os, binary, weight_decay_);
+  WriteToken(os, binary, "<Momentum>");
+  WriteBasicType(os, binary, momentum_);
+  WriteToken(os, binary, "<LinearParams>");
+  linear_params_.Write(os, binary);
+  WriteToken(os, binary, "<BiasParams>");
+  bias_params_.Write(os, binary);
+  WriteToken(os, binary, "<PrevGrad>");
+  prev_grad_.Write(os, binary);
+  WriteToken(os, binary, "<IsGradient>");
+  WriteBasicType(os, binary, is_gradient_);
+  WriteToken(os, binary, end);
+}
+
+BaseFloat ConvolutionComponent::DotProduct(const UpdatableComponent &other_in) const {   // :670-675
+  const ConvolutionComponent *other = dynamic_cast<const ConvolutionComponent *>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  return TraceMatMat(linear_params_, other->linear_params_, kTrans) +
+         VecVec(bias_params_, other->bias_params_);
+}
+
+Component *ConvolutionComponent::Copy() const {      // reference :679-705 (includes prev_grad_)
+  ConvolutionComponent *ans = new ConvolutionComponent();
+  ans->learning_rate_ = learning_rate_;
+  ans->linear_params_ = linear_params_;
+  ans->bias_params_ = bias_params_;
+  ans->is_gradient_ = is_gradient_;
+  ans->in_height_ = in_height_; ans->in_width_ = in_width_; ans->in_channel_ = in_channel_;
+  ans->kernel_height_ = kernel_height_; ans->kernel_width_ = kernel_width_;
+  ans->stride_ = stride_;
+  ans->in_pad_height_ = in_pad_height_; ans->in_pad_width_ = in_pad_width_;
+  ans->group_ = group_;
+  ans->out_height_ = out_height_; ans->out_width_ = out_width_;
+  ans->weight_decay_ = weight_decay_;
+  ans->momentum_ = momentum_;
+  ans->prev_grad_ = prev_grad_;
+  return ans;
+}
+
+void ConvolutionComponent::PerturbParams(BaseFloat stddev) {     // reference :706-714
+  CuMatrix<BaseFloat> temp_linear_params(linear_params_);
+  temp_linear_params.SetRandn();
+  linear_params_.AddMat(stddev, temp_linear_params);
+  CuVector<BaseFloat> temp_bias_params(bias_params_);
+  temp_bias_params.SetRandn();
+  bias_params_.AddVec(stddev, temp_bias_params);
+}
+
+// reference :716-736 use AffineComponent's shapes and are wrong for a convolution
+// (App. C.3, off the hot path); these versions use the convolution's own shapes.
+void ConvolutionComponent::SetParams(const VectorBase<BaseFloat> &bias,
+                                     const MatrixBase<BaseFloat> &linear) {
+  bias_params_ = bias;
+  linear_params_ = linear;
+  KALDI_ASSERT(bias_params_.Dim() == linear_params_.NumCols());
+}
+
+int32 ConvolutionComponent::GetParameterDim() const { return (KernelDim() + 1) * Group(); }
+
+void ConvolutionComponent::Vectorize(VectorBase<BaseFloat> *params) const {
+  KALDI_ASSERT(params->Dim() == GetParameterDim());
+  Matrix<BaseFloat> w(linear_params_.NumRows(), linear_params_.NumCols());
+  linear_params_.CopyToMat(&w);
+  Vector<BaseFloat> b(bias_params_.Dim());
+  bias_params_.CopyToVec(&b);
+  int32 k = 0;
+  for (int32 r = 0; r < w.NumRows(); r++)
+    for (int32 c = 0; c < w.NumCols(); c++) (*params)(k++) = w(r, c);
+  for (int32 i = 0; i < b.Dim(); i++) (*params)(k++) = b(i);
+}
+
+void ConvolutionComponent::UnVectorize(const VectorBase<BaseFloat> &params) {
+  KALDI_ASSERT(params.Dim() == GetParameterDim());
+  Matrix<BaseFloat> w(KernelDim(), Group());
+  Vector<BaseFloat> b(Group());
+  int32 k = 0;
+  for (int32 r = 0; r < w.NumRows(); r++)
+    for (int32 c = 0; c < w.NumCols(); c++) w(r, c) = params(k++);
+  for (int32 i = 0; i < b.Dim(); i++) b(i) = params(k++);
+  linear_params_ = w;
+  bias_params_ = b;
+}
+
+// ---- gradient buffers -------------------------------------------------------
+
+void ConvolutionComponent::EnsureGradBuffers() {
+  if (grad_external_) return;
+  if (w_grad_store_.NumRows() != KernelDim() || w_grad_store_.NumCols() != group_) {
+    w_grad_store_.Resize(KernelDim(), group_, kUndefined);
+    b_grad_store_.Resize(group_, kUndefined);
+  }
+  w_grad_.data = w_grad_store_.Data(); w_grad_.rows = KernelDim(); w_grad_.cols = group_;
+  w_grad_.stride = w_grad_store_.Stride();
+  b_grad_.data = b_grad_store_.Data(); b_grad_.rows = 1; b_grad_.cols = group_; b_grad_.stride = group_;
+}
+
+size_t ConvolutionComponent::GradientFloats() const {
+  size_t stride = CuDevice::PitchInElements(group_, sizeof(BaseFloat));
+  return stride * KernelDim() + stride;
+}
+
+void ConvolutionComponent::SetGradientStorage(float *base) {
+  if (base == NULL) { grad_external_ = false; return; }
+  int32 stride = CuDevice::PitchInElements(group_, sizeof(BaseFloat));
+  w_grad_.data = base; w_grad_.rows = KernelDim(); w_grad_.cols = group_; w_grad_.stride = stride;
+  b_grad_.data = base + (size_t)stride * KernelDim(); b_grad_.rows = 1; b_grad_.cols = group_;
+  b_grad_.stride = group_;
+  grad_external_ = true;
+}
+
+std::vector<UpdatableComponent::GradBuffer> ConvolutionComponent::GradientBuffers() {
+  EnsureGradBuffers();
+  std::vector<GradBuffer> v;
+  v.push_back(w_grad_);
+  v.push_back(b_grad_);
+  return v;
+}
+
+// Weight and bias gradient, reference :745-765 and the row sums of :775: one
+// reduction kernel (bias) + one implicit GEMM whose output rows are already in
+// linear_params_ order (no ModPermuteRow), reading in_value / out_deriv in place.
+void ConvolutionComponent::ComputeGradient(const CuMatrixBase<BaseFloat> &in_value,
+                                           const CuMatrixBase<BaseFloat> &out_deriv) {
+  KALDI_ASSERT(in_value.NumCols() == InputDim() && out_deriv.NumCols() == OutputDim() &&
+               in_value.NumRows() == out_deriv.NumRows());
+  EnsureGradBuffers();
+  const int32 rows = in_value.NumRows();
+  if (workspace_rows_ != rows) {
+    size_t bytes = kcnn_conv2d_wgrad_workspace(rows, in_height_, in_width_, in_channel_,
+                                               in_pad_height_, in_pad_width_, kernel_height_,
+                                               kernel_width_, group_);
+    workspace_.Resize((bytes + sizeof(BaseFloat) - 1) / sizeof(BaseFloat), kUndefined);
+    workspace_rows_ = rows;
+  }
+  ::MatrixDim gd = {w_grad_.rows, w_grad_.cols, w_grad_.stride};
+  Timer tim;
+  cudaF_conv2d_wgrad(Str(), Math(), in_value.Data(), in_value.Dim(), out_deriv.Data(),
+                     out_deriv.Dim(), w_grad_.data, gd, b_grad_.data,
+                     workspace_.Dim() ? workspace_.Data() : NULL, in_height_, in_width_, in_channel_,
+                     in_pad_height_, in_pad_width_, kernel_height_, kernel_width_, group_);
+  CU_SAFE_CALL(cudaGetLastError());
+  CuDevice::Instantiate().AccuProfile(__func__, tim.Elapsed());
+}
+
+// The SGD step of reference :767-775:
+//   lr = learning_rate_ / num_sample (BaseFloat division, widened to double)
+//   prev = momentum*prev ; prev += (-lr*wd) * W ; prev += lr * grad ; W += prev   (one fused pass)
+//   bias += lr * db                                                             (no momentum / decay)
+void ConvolutionComponent::ApplyGradient(int32 total_num_samples) {
+  EnsureGradBuffers();
+  KALDI_ASSERT(total_num_samples > 0);
+  double learning_rate = learning_rate_ / total_num_samples;
+  BaseFloat a_decay = -1 * learning_rate * weight_decay_, a_grad = learning_rate;
+  ::MatrixDim gd = {w_grad_.rows, w_grad_.cols, w_grad_.stride};
+  cudaF_sgd_momentum_update(Str(), linear_params_.Data(), linear_params_.Dim(), prev_grad_.Data(),
+                            prev_grad_.Dim(), w_grad_.data, gd, momentum_, a_decay, a_grad);
+  cudaF_vec_axpy(Str(), bias_params_.Data(), b_grad_.data, group_, a_grad);
+  CU_SAFE_CALL(cudaGetLastError());
+}
+
+// reference :738-777
+void ConvolutionComponent::Update(const CuMatrixBase<BaseFloat> &in_value,
+                                  const CuMatrixBase<BaseFloat> &out_deriv) {
+  ComputeGradient(in_value, out_deriv);
+  if (!deferred_) ApplyGradient(in_value.NumRows());
+}
+
+}  // namespace nnet0
+}  // namespace cnsl

@@ -1,0 +1,760 @@
+// nnet2/nnet-component.cc -- shim of the nnet2 Component machinery (see the header).
+// GPU only; every matrix operation is stream-ordered on CuDevice::Stream().
+
+#include <algorithm>
+#include <sstream>
+
+#include "nnet2/nnet-component.h"
+#include "nnet0/nnet-component-nnet0.h"
+#include "util/common-utils.h"
+#include "cnsl-cu-kernels.h"
+#include "kcnn_common.cuh"
+
+namespace kaldi {
+namespace nnet2 {
+
+static inline cudaStream_t Str() { return CuDevice::Instantiate().Stream(); }
+
+// ------------------------------------------------------------------ ChunkInfo --
+
+int32 ChunkInfo::GetIndex(int32 offset) const {
+  if (offsets_.empty()) {
+    KALDI_ASSERT((offset <= last_offset_) && (offset >= first_offset_));
+    return offset - first_offset_;
+  }
+  std::vector<int32>::const_iterator iter = std::lower_bound(offsets_.begin(), offsets_.end(), offset);
+  KALDI_ASSERT(iter != offsets_.end() && *iter == offset);
+  return static_cast<int32>(iter - offsets_.begin());
+}
+
+int32 ChunkInfo::GetOffset(int32 index) const {
+  if (offsets_.empty()) {
+    int32 offset = index + first_offset_;
+    KALDI_ASSERT((offset <= last_offset_) && (offset >= first_offset_));
+    return offset;
+  }
+  KALDI_ASSERT((index >= 0) && (index < static_cast<int32>(offsets_.size())));
+  return offsets_[index];
+}
+
+void ChunkInfo::Check() const {
+  KALDI_ASSERT((feat_dim_ > 0) && (num_chunks_ > 0));
+  if (!offsets_.empty()) {
+    KALDI_ASSERT((first_offset_ == offsets_.front()) && (last_offset_ == offsets_.back()));
+  } else {
+    KALDI_ASSERT((first_offset_ >= 0) && (last_offset_ >= first_offset_));
+  }
+  KALDI_ASSERT(NumRows() % num_chunks_ == 0);
+}
+
+void ChunkInfo::CheckSize(const CuMatrixBase<BaseFloat> &mat) const {
+  KALDI_ASSERT((mat.NumRows() == NumRows()) && (mat.NumCols() == NumCols()));
+}
+
+// ------------------------------------------------------------------ Component --
+
+// static
+Component *Component::NewComponentOfType(const std::string &component_type) {
+  Component *ans = NULL;
+  if (component_type == "SoftmaxComponent") {
+    ans = new SoftmaxComponent();
+  } else if (component_type == "RectifiedLinearComponent") {
+    ans = new RectifiedLinearComponent();
+  } else if (component_type == "AffineComponent") {
+    ans = new AffineComponent();
+  } else if (component_type == "DropoutComponent") {
+    ans = new DropoutComponent();
+  } else if (component_type == "ConvolutionComponent") {       // reference :112-113
+    ans = new cnsl::nnet0::ConvolutionComponent();
+  } else if (component_type == "MaxpoolComponent") {           // reference :114-115
+    ans = new cnsl::nnet0::MaxpoolComponent();
+  } else if (component_type == "FullyConnectedComponent") {    // reference :116-117
+    ans = new cnsl::nnet0::FullyConnectedComponent();
+  }
+  return ans;
+}
+
+// static
+Component *Component::ReadNew(std::istream &is, bool binary) {
+  std::string token;
+  ReadToken(is, binary, &token);   // e.g. "<SigmoidComponent>".
+  token.erase(0, 1);
+  token.erase(token.length() - 1);
+  Component *ans = NewComponentOfType(token);
+  if (!ans) KALDI_ERR << "Unknown component type " << token;
+  ans->Read(is, binary);
+  return ans;
+}
+
+// static
+Component *Component::NewFromString(const std::string &initializer_line) {
+  std::istringstream istr(initializer_line);
+  std::string component_type;
+  istr >> component_type >> std::ws;
+  std::string rest_of_line;
+  getline(istr, rest_of_line);
+  Component *ans = NewComponentOfType(component_type);
+  if (ans == NULL)
+    KALDI_ERR << "Bad initializer line (no such type of Component): " << initializer_line;
+  ans->InitFromString(rest_of_line);
+  return ans;
+}
+
+std::string Component::Info() const {
+  std::stringstream stream;
+  stream << Type() << ", input-dim=" << InputDim() << ", output-dim=" << OutputDim();
+  return stream.str();
+}
+
+std::string UpdatableComponent::Info() const {
+  std::stringstream stream;
+  stream << Type() << ", input-dim=" << InputDim() << ", output-dim=" << OutputDim()
+         << ", learning-rate=" << LearningRate();
+  return stream.str();
+}
+
+void ExpectOneOrTwoTokens(std::istream &is, bool binary, const std::string &token1,
+                          const std::string &token2) {
+  KALDI_ASSERT(token1 != token2);
+  std::string temp;
+  ReadToken(is, binary, &temp);
+  if (temp == token1) {
+    ExpectToken(is, binary, token2);
+  } else if (temp != token2) {
+    KALDI_ERR << "Expecting token " << token1 << " or " << token2 << " but got " << temp;
+  }
+}
+
+// One scan for all the ParseFromString overloads: finds "name=value", removes it from
+// *string, returns the value text.
+static bool TakeOption(const std::string &name, std::string *string, std::string *value) {
+  std::vector<std::string> pieces;
+  SplitStringToVector(*string, " \t", true, &pieces);
+  const std::string key = name + "=";
+  for (size_t i = 0; i < pieces.size(); i++) {
+    if (pieces[i].compare(0, key.length(), key) != 0) continue;
+    *value = pieces[i].substr(key.length());
+    std::string rest;
+    for (size_t j = 0; j < pieces.size(); j++) {
+      if (j == i) continue;
+      if (!rest.empty()) rest += " ";
+      rest += pieces[j];
+    }
+    *string = rest;
+    return true;
+  }
+  return false;
+}
+
+bool ParseFromString(const std::string &name, std::string *string, int32 *param) {
+  std::string v;
+  if (!TakeOption(name, string, &v)) return false;
+  if (!ConvertStringToInteger(v, param)) KALDI_ERR << "Bad option " << name << "=" << v;
+  return true;
+}
+bool ParseFromString(const std::string &name, std::string *string, bool *param) {
+  std::string v;
+  if (!TakeOption(name, string, &v)) return false;
+  if (v.empty()) KALDI_ERR << "Bad option " << name << "=" << v;
+  if (v[0] == 'f' || v[0] == 'F') *param = false;
+  else if (v[0] == 't' || v[0] == 'T') *param = true;
+  else KALDI_ERR << "Bad option " << name << "=" << v;
+  return true;
+}
+bool ParseFromString(const std::string &name, std::string *string, BaseFloat *param) {
+  std::string v;
+  if (!TakeOption(name, string, &v)) return false;
+  if (!ConvertStringToReal(v, param)) KALDI_ERR << "Bad option " << name << "=" << v;
+  return true;
+}
+bool ParseFromString(const std::string &name, std::string *string, std::string *param) {
+  return TakeOption(name, string, param);
+}
+bool ParseFromString(const std::string &name, std::string *string, std::vector<int32> *param) {
+  std::string v;
+  if (!TakeOption(name, string, &v)) return false;
+  if (!SplitStringToIntegers(v, ":", false, param)) KALDI_ERR << "Bad option " << name << "=" << v;
+  return true;
+}
+
+// --------------------------------------------------------- NonlinearComponent --
+
+namespace {
+// Column sums of y and of [y > 0] over the rows, added to the double accumulators.
+__global__ void __launch_bounds__(256)
+nonlin_stats_kernel(const float *__restrict__ y, ::MatrixDim d, double *value_sum,
+                    double *deriv_sum) {
+  __shared__ float pv[8][33], pd[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float sv = 0.0f, sd = 0.0f;
+  if (col < d.cols)
+    for (int r = ty; r < d.rows; r += 8) {
+      float v = __ldg(y + (size_t)r * d.stride + col);
+      sv += v;
+      sd += v > 0.0f ? 1.0f : 0.0f;
+    }
+  pv[ty][tx] = sv; pd[ty][tx] = sd;
+  __syncthreads();
+  if (ty == 0 && col < d.cols) {
+    float a = 0.0f, b = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a += pv[i][tx]; b += pd[i][tx]; }
+    value_sum[col] += (double)a;
+    if (deriv_sum) deriv_sum[col] += (double)b;
+  }
+}
+
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {     // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 32);
+}
+
+__global__ void __launch_bounds__(256)
+dropout_fprop_kernel(const float *__restrict__ in, ::MatrixDim id, float *__restrict__ out,
+                     ::MatrixDim od, float dp, float low, float high,
+                     const unsigned long long *seed_dev) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)od.rows * od.cols) return;
+  const unsigned long long seed = *seed_dev;
+  int i = (int)(t / od.cols), j = (int)(t % od.cols);
+  float u = (mix32(seed * 0x100000001B3ull + (uint64_t)t) >> 8) * (1.0f / 16777216.0f);
+  float scale = (u - dp > 0.0f) ? high : low;
+  out[(size_t)i * od.stride + j] = scale * __ldg(in + (size_t)i * id.stride + j);
+}
+
+__global__ void bump_seed_kernel(unsigned long long *seed_dev) { *seed_dev += 1; }
+
+// in_deriv = out_deriv .* out_value ./ in_value   (out_deriv where in_value == 0):
+// Kaldi's AddMatMatDivMat, reference nnet2/nnet-component.cc:3634-3636.
+__global__ void __launch_bounds__(256)
+dropout_bprop_kernel(const float *__restrict__ iv, ::MatrixDim ivd, const float *__restrict__ ov,
+                     ::MatrixDim ovd, const float *__restrict__ od, ::MatrixDim odd,
+                     float *__restrict__ id, ::MatrixDim idd) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)idd.rows * idd.cols) return;
+  int i = (int)(t / idd.cols), j = (int)(t % idd.cols);
+  float x = __ldg(iv + (size_t)i * ivd.stride + j), d = __ldg(od + (size_t)i * odd.stride + j);
+  id[(size_t)i * idd.stride + j] = x == 0.0f ? d : d * __ldg(ov + (size_t)i * ovd.stride + j) / x;
+}
+}  // namespace
+
+NonlinearComponent::NonlinearComponent(const NonlinearComponent &other)
+    : Component(), dim_(other.dim_), count_(other.count_), stats_(NULL), stats_dim_(0) {
+  other.GetStats(&value_sum_host_, &deriv_sum_host_);
+}
+
+NonlinearComponent::~NonlinearComponent() {
+  if (stats_) CuDevice::Instantiate().Free(stats_);
+}
+
+void NonlinearComponent::UpdateStats(const CuMatrixBase<BaseFloat> &out_value, bool relu_deriv) {
+  KALDI_ASSERT(out_value.NumCols() == InputDim());
+  if (stats_ == NULL || stats_dim_ != dim_) {
+    if (stats_) CuDevice::Instantiate().Free(stats_);
+    stats_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double) * 2 * dim_));
+    stats_dim_ = dim_;
+    std::vector<double> init(2 * dim_, 0.0);
+    for (int32 i = 0; i < dim_ && i < value_sum_host_.Dim(); i++) init[i] = value_sum_host_(i);
+    for (int32 i = 0; i < dim_ && i < deriv_sum_host_.Dim(); i++) init[dim_ + i] = deriv_sum_host_(i);
+    CU_SAFE_CALL(cudaMemcpyAsync(stats_, init.data(), sizeof(double) * 2 * dim_,
+                                 cudaMemcpyHostToDevice, Str()));
+    CU_SAFE_CALL(cudaStreamSynchronize(Str()));
+  }
+  count_ += out_value.NumRows();
+  if (out_value.NumRows() == 0) return;
+  KCNN_LAUNCH(nonlin_stats_kernel, kcnn::ceil_div_u(dim_, 32), 256, 0, Str(), out_value.Data(),
+              out_value.Dim(), stats_, relu_deriv ? stats_ + dim_ : (double *)NULL);
+}
+
+void NonlinearComponent::GetStats(Vector<double> *value_sum, Vector<double> *deriv_sum) const {
+  if (stats_ == NULL) {
+    *value_sum = value_sum_host_;
+    *deriv_sum = deriv_sum_host_;
+    return;
+  }
+  std::vector<double> h(2 * stats_dim_);
+  CU_SAFE_CALL(cudaMemcpyAsync(h.data(), stats_, sizeof(double) * 2 * stats_dim_,
+                               cudaMemcpyDeviceToHost, Str()));
+  CU_SAFE_CALL(cudaStreamSynchronize(Str()));
+  value_sum->Resize(stats_dim_);
+  deriv_sum->Resize(stats_dim_);
+  for (int32 i = 0; i < stats_dim_; i++) { (*value_sum)(i) = h[i]; (*deriv_sum)(i) = h[stats_dim_ + i]; }
+}
+
+void NonlinearComponent::Read(std::istream &is, bool binary) {
+  std::ostringstream ostr_beg, ostr_end;
+  ostr_beg << "<" << Type() << ">";
+  ostr_end << "</" << Type() << ">";
+  ExpectOneOrTwoTokens(is, binary, ostr_beg.str(), "<Dim>");
+  ReadBasicType(is, binary, &dim_);
+  ExpectToken(is, binary, "<ValueSum>");
+  value_sum_host_.Read(is, binary);
+  ExpectToken(is, binary, "<DerivSum>");
+  deriv_sum_host_.Read(is, binary);
+  ExpectToken(is, binary, "<Count>");
+  ReadBasicType(is, binary, &count_);
+  ExpectToken(is, binary, ostr_end.str());
+  if (stats_) { CuDevice::Instantiate().Free(stats_); stats_ = NULL; stats_dim_ = 0; }
+}
+
+void NonlinearComponent::Write(std::ostream &os, bool binary) const {
+  std::ostringstream ostr_beg, ostr_end;
+  ostr_beg << "<" << Type() << ">";
+  ostr_end << "</" << Type() << ">";
+  Vector<double> vs, ds;
+  GetStats(&vs, &ds);
+  WriteToken(os, binary, ostr_beg.str());
+  WriteToken(os, binary, "<Dim>");
+  WriteBasicType(os, binary, dim_);
+  WriteToken(os, binary, "<ValueSum>");
+  vs.Write(os, binary);
+  WriteToken(os, binary, "<DerivSum>");
+  ds.Write(os, binary);
+  WriteToken(os, binary, "<Count>");
+  WriteBasicType(os, binary, count_);
+  WriteToken(os, binary, ostr_end.str());
+}
+
+void NonlinearComponent::InitFromString(std::string args) {
+  std::string orig_args(args);
+  int32 dim;
+  bool ok = ParseFromString("dim", &args, &dim);
+  if (!ok || !args.empty() || dim <= 0)
+    KALDI_ERR << "Invalid initializer for layer of type " << Type() << ": \"" << orig_args << "\"";
+  Init(dim);
+}
+
+// out = max(in, 0)                                     reference :799-806
+void RectifiedLinearComponent::Propagate(const ChunkInfo &, const ChunkInfo &,
+                                         const CuMatrixBase<BaseFloat> &in,
+                                         CuMatrixBase<BaseFloat> *out) const {
+  KALDI_ASSERT(in.NumRows() == out->NumRows() && in.NumCols() == out->NumCols());
+  cudaF_relu_fprop(Str(), in.Data(), in.Dim(), out->Data(), out->Dim());
+}
+
+// in_deriv = out_deriv .* [out_value > 0], one pass     reference :808-827
+void RectifiedLinearComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
+                                        const CuMatrixBase<BaseFloat> &,
+                                        const CuMatrixBase<BaseFloat> &out_value,
+                                        const CuMatrixBase<BaseFloat> &out_deriv,
+                                        Component *to_update, CuMatrix<BaseFloat> *in_deriv) const {
+  in_deriv->Resize(out_deriv.NumRows(), out_deriv.NumCols(), kUndefined);
+  cudaF_relu_bprop(Str(), out_value.Data(), out_value.Dim(), out_deriv.Data(), out_deriv.Dim(),
+                   in_deriv->Data(), in_deriv->Dim());
+  if (to_update != NULL)
+    dynamic_cast<NonlinearComponent *>(to_update)->UpdateStats(out_value, true);
+}
+
+// reference :930-950
+void SoftmaxComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                                 const CuMatrixBase<BaseFloat> &in,
+                                 CuMatrixBase<BaseFloat> *out) const {
+  in_info.CheckSize(in);
+  out_info.CheckSize(*out);
+  KALDI_ASSERT(in_info.NumChunks() == out_info.NumChunks());
+  cudaF_softmax_fprop(Str(), in.Data(), in.Dim(), out->Data(), out->Dim());
+}
+
+// reference :952-1000
+void SoftmaxComponent::Backprop(const ChunkInfo &, const ChunkInfo &, const CuMatrixBase<BaseFloat> &,
+                                const CuMatrixBase<BaseFloat> &out_value,
+                                const CuMatrixBase<BaseFloat> &out_deriv, Component *to_update,
+                                CuMatrix<BaseFloat> *in_deriv) const {
+  in_deriv->Resize(out_deriv.NumRows(), out_deriv.NumCols(), kUndefined);
+  KALDI_ASSERT(out_value.NumRows() == out_deriv.NumRows() && out_value.NumCols() == out_deriv.NumCols());
+  cudaF_softmax_bprop(Str(), out_value.Data(), out_value.Dim(), out_deriv.Data(), out_deriv.Dim(),
+                      in_deriv->Data(), in_deriv->Dim());
+  if (to_update != NULL)
+    dynamic_cast<NonlinearComponent *>(to_update)->UpdateStats(out_value, false);
+}
+
+// ----------------------------------------------------------- DropoutComponent --
+
+void DropoutComponent::Init(int32 dim, BaseFloat dropout_proportion, BaseFloat dropout_scale) {
+  dim_ = dim;
+  dropout_proportion_ = dropout_proportion;
+  dropout_scale_ = dropout_scale;
+}
+
+void DropoutComponent::InitFromString(std::string args) {
+  std::string orig_args(args);
+  int32 dim;
+  BaseFloat dropout_proportion = 0.5, dropout_scale = 0.0;
+  bool ok = ParseFromString("dim", &args, &dim);
+  ParseFromString("dropout-proportion", &args, &dropout_proportion);
+  ParseFromString("dropout-scale", &args, &dropout_scale);
+  if (!ok || !args.empty() || dim <= 0)
+    KALDI_ERR << "Invalid initializer for layer of type DropoutComponent: \"" << orig_args << "\"";
+  Init(dim, dropout_proportion, dropout_scale);
+}
+
+void DropoutComponent::Read(std::istream &is, bool binary) {
+  ExpectOneOrTwoTokens(is, binary, "<DropoutComponent>", "<Dim>");
+  ReadBasicType(is, binary, &dim_);
+  ExpectToken(is, binary, "<DropoutScale>");
+  ReadBasicType(is, binary, &dropout_scale_);
+  ExpectToken(is, binary, "<DropoutProportion>");
+  ReadBasicType(is, binary, &dropout_proportion_);
+  ExpectToken(is, binary, "</DropoutComponent>");
+}
+
+void DropoutComponent::Write(std::ostream &os, bool binary) const {
+  WriteToken(os, binary, "<DropoutComponent>");
+  WriteToken(os, binary, "<Dim>");
+  WriteBasicType(os, binary, dim_);
+  WriteToken(os, binary, "<DropoutScale>");
+  WriteBasicType(os, binary, dropout_scale_);
+  WriteToken(os, binary, "<DropoutProportion>");
+  WriteBasicType(os, binary, dropout_proportion_);
+  WriteToken(os, binary, "</DropoutComponent>");
+}
+
+std::string DropoutComponent::Info() const {
+  std::stringstream stream;
+  stream << Type() << ", dim = " << dim_ << ", dropout-proportion = " << dropout_proportion_
+         << ", dropout-scale = " << dropout_scale_;
+  return stream.str();
+}
+
+DropoutComponent::~DropoutComponent() {
+  if (seed_dev_) CuDevice::Instantiate().Free(seed_dev_);
+}
+
+Component *DropoutComponent::Copy() const {
+  return new DropoutComponent(dim_, dropout_proportion_, dropout_scale_);
+}
+
+void DropoutComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                                 const CuMatrixBase<BaseFloat> &in,
+                                 CuMatrixBase<BaseFloat> *out) const {
+  in_info.CheckSize(in);
+  out_info.CheckSize(*out);
+  KALDI_ASSERT(in_info.NumChunks() == out_info.NumChunks());
+  KALDI_ASSERT(in.NumCols() == this->InputDim());
+  BaseFloat dp = dropout_proportion_;
+  KALDI_ASSERT(dp < 1.0 && dp >= 0.0);
+  KALDI_ASSERT(dropout_scale_ <= 1.0 && dropout_scale_ >= 0.0);
+  BaseFloat low_scale = dropout_scale_, high_scale = (1.0 - (dp * low_scale)) / (1.0 - dp);
+  long long total = (long long)out->NumRows() * out->NumCols();
+  if (total == 0) return;
+  // One fused pass (the reference draws uniforms, thresholds, scales and multiplies in
+  // five passes, :3600-3620).  The mask is a pure function of (seed, element); the seed
+  // lives on the device and is bumped by a one-thread kernel, so a replayed CUDA graph
+  // draws a fresh mask every step.
+  if (seed_dev_ == NULL) {
+    seed_dev_ = static_cast<unsigned long long *>(CuDevice::Instantiate().Malloc(sizeof(unsigned long long)));
+    unsigned long long s0 = CuDevice::Instantiate().NextRandSeed();
+    CU_SAFE_CALL(cudaMemcpyAsync(seed_dev_, &s0, sizeof(s0), cudaMemcpyHostToDevice, Str()));
+    CU_SAFE_CALL(cudaStreamSynchronize(Str()));
+  }
+  KCNN_LAUNCH(dropout_fprop_kernel, kcnn::ceil_div_u(total, 256), 256, 0, Str(), in.Data(), in.Dim(),
+              out->Data(), out->Dim(), dp, low_scale, high_scale, seed_dev_);
+  KCNN_LAUNCH(bump_seed_kernel, 1, 1, 0, Str(), seed_dev_);
+}
+
+void DropoutComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
+                                const CuMatrixBase<BaseFloat> &in_value,
+                                const CuMatrixBase<BaseFloat> &out_value,
+                                const CuMatrixBase<BaseFloat> &out_deriv, Component *,
+                                CuMatrix<BaseFloat> *in_deriv) const {
+  KALDI_ASSERT(in_value.NumRows() == out_value.NumRows() && in_value.NumCols() == out_value.NumCols());
+  in_deriv->Resize(out_deriv.NumRows(), out_deriv.NumCols(), kUndefined);
+  long long total = (long long)out_deriv.NumRows() * out_deriv.NumCols();
+  if (total == 0) return;
+  KCNN_LAUNCH(dropout_bprop_kernel, kcnn::ceil_div_u(total, 256), 256, 0, Str(), in_value.Data(),
+              in_value.Dim(), out_value.Data(), out_value.Dim(), out_deriv.Data(), out_deriv.Dim(),
+              in_deriv->Data(), in_deriv->Dim());
+}
+
+// ------------------------------------------------------------ AffineComponent --
+
+AffineComponent::AffineComponent(const AffineComponent &component)
+    : UpdatableComponent(component), linear_params_(component.linear_params_),
+      bias_params_(component.bias_params_), is_gradient_(component.is_gradient_),
+      deferred_(false), grad_external_(false) {}
+
+AffineComponent::AffineComponent(const CuMatrixBase<BaseFloat> &linear_params,
+                                 const CuVectorBase<BaseFloat> &bias_params, BaseFloat learning_rate)
+    : UpdatableComponent(learning_rate), linear_params_(linear_params), bias_params_(bias_params),
+      is_gradient_(false), deferred_(false), grad_external_(false) {
+  KALDI_ASSERT(linear_params.NumRows() == bias_params.Dim() && bias_params.Dim() != 0);
+}
+
+void AffineComponent::SetZero(bool treat_as_gradient) {
+  if (treat_as_gradient) SetLearningRate(1.0);
+  linear_params_.SetZero();
+  bias_params_.SetZero();
+  if (treat_as_gradient) is_gradient_ = true;
+}
+
+void AffineComponent::SetParams(const VectorBase<BaseFloat> &bias, const MatrixBase<BaseFloat> &linear) {
+  bias_params_ = bias;
+  linear_params_ = linear;
+  KALDI_ASSERT(bias_params_.Dim() == linear_params_.NumRows());
+}
+
+void AffineComponent::PerturbParams(BaseFloat stddev) {
+  CuMatrix<BaseFloat> temp_linear_params(linear_params_);
+  temp_linear_params.SetRandn();
+  linear_params_.AddMat(stddev, temp_linear_params);
+  CuVector<BaseFloat> temp_bias_params(bias_params_);
+  temp_bias_params.SetRandn();
+  bias_params_.AddVec(stddev, temp_bias_params);
+}
+
+std::string AffineComponent::Info() const {
+  std::stringstream stream;
+  BaseFloat linear_params_size = static_cast<BaseFloat>(linear_params_.NumRows()) *
+                                 static_cast<BaseFloat>(linear_params_.NumCols());
+  BaseFloat linear_stddev = std::sqrt(TraceMatMat(linear_params_, linear_params_, kTrans) / linear_params_size),
+            bias_stddev = std::sqrt(VecVec(bias_params_, bias_params_) / bias_params_.Dim());
+  stream << Type() << ", input-dim=" << InputDim() << ", output-dim=" << OutputDim()
+         << ", linear-params-stddev=" << linear_stddev << ", bias-params-stddev=" << bias_stddev
+         << ", learning-rate=" << LearningRate();
+  return stream.str();
+}
+
+Component *AffineComponent::Copy() const {
+  AffineComponent *ans = new AffineComponent();
+  ans->learning_rate_ = learning_rate_;
+  ans->linear_params_ = linear_params_;
+  ans->bias_params_ = bias_params_;
+  ans->is_gradient_ = is_gradient_;
+  return ans;
+}
+
+BaseFloat AffineComponent::DotProduct(const UpdatableComponent &other_in) const {
+  const AffineComponent *other = dynamic_cast<const AffineComponent *>(&other_in);
+  return TraceMatMat(linear_params_, other->linear_params_, kTrans) +
+         VecVec(bias_params_, other->bias_params_);
+}
+
+void AffineComponent::Init(BaseFloat learning_rate, int32 input_dim, int32 output_dim,
+                           BaseFloat param_stddev, BaseFloat bias_stddev) {
+  UpdatableComponent::Init(learning_rate);
+  linear_params_.Resize(output_dim, input_dim);
+  bias_params_.Resize(output_dim);
+  KALDI_ASSERT(output_dim > 0 && input_dim > 0 && param_stddev >= 0.0);
+  linear_params_.SetRandn();
+  linear_params_.Scale(param_stddev);
+  bias_params_.SetRandn();
+  bias_params_.Scale(bias_stddev);
+}
+
+void AffineComponent::Init(BaseFloat learning_rate, std::string matrix_filename) {
+  UpdatableComponent::Init(learning_rate);
+  CuMatrix<BaseFloat> mat;
+  ReadKaldiObject(matrix_filename, &mat);
+  KALDI_ASSERT(mat.NumCols() >= 2);
+  int32 input_dim = mat.NumCols() - 1, output_dim = mat.NumRows();
+  linear_params_.Resize(output_dim, input_dim);
+  bias_params_.Resize(output_dim);
+  linear_params_.CopyFromMat(mat.Range(0, output_dim, 0, input_dim));
+  bias_params_.CopyColFromMat(mat, input_dim);
+}
+
+void AffineComponent::InitFromString(std::string args) {
+  std::string orig_args(args);
+  bool ok = true;
+  BaseFloat learning_rate = learning_rate_;
+  std::string matrix_filename;
+  int32 input_dim = -1, output_dim = -1;
+  ParseFromString("learning-rate", &args, &learning_rate);
+  if (ParseFromString("matrix", &args, &matrix_filename)) {
+    Init(learning_rate, matrix_filename);
+    if (ParseFromString("input-dim", &args, &input_dim))
+      KALDI_ASSERT(input_dim == InputDim() && "input-dim mismatch vs. matrix.");
+    if (ParseFromString("output-dim", &args, &output_dim))
+      KALDI_ASSERT(output_dim == OutputDim() && "output-dim mismatch vs. matrix.");
+  } else {
+    ok = ok && ParseFromString("input-dim", &args, &input_dim);
+    ok = ok && ParseFromString("output-dim", &args, &output_dim);
+    BaseFloat param_stddev = 1.0 / std::sqrt(input_dim), bias_stddev = 1.0;
+    ParseFromString("param-stddev", &args, &param_stddev);
+    ParseFromString("bias-stddev", &args, &bias_stddev);
+    Init(learning_rate, input_dim, output_dim, param_stddev, bias_stddev);
+  }
+  if (!args.empty()) KALDI_ERR << "Could not process these elements in initializer: " << args;
+  if (!ok) KALDI_ERR << "Bad initializer " << orig_args;
+}
+
+// out = 1 bias^T + in W^T in ONE launch: the bias row copy (CopyRowsFromVec) is the
+// GEMM epilogue.  reference :1216-1228.
+void AffineComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                                const CuMatrixBase<BaseFloat> &in,
+                                CuMatrixBase<BaseFloat> *out) const {
+  in_info.CheckSize(in);
+  out_info.CheckSize(*out);
+  KALDI_ASSERT(in_info.NumChunks() == out_info.NumChunks());
+  KALDI_ASSERT(in.NumCols() == InputDim() && out->NumCols() == OutputDim());
+  CuDevice::Instantiate().RequireEnabled("AffineComponent::Propagate");
+  cudaF_affine_fprop(Str(), CuDevice::Instantiate().MathMode(), in.Data(), in.Dim(),
+                     linear_params_.Data(), linear_params_.Dim(), bias_params_.Data(), out->Data(),
+                     out->Dim());
+  CU_SAFE_CALL(cudaGetLastError());
+}
+
+void AffineComponent::EnsureGradBuffers() {
+  if (grad_external_) return;
+  if (w_grad_store_.NumRows() != linear_params_.NumRows() ||
+      w_grad_store_.NumCols() != linear_params_.NumCols()) {
+    w_grad_store_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kUndefined);
+    b_grad_store_.Resize(bias_params_.Dim(), kUndefined);
+  }
+  w_grad_.data = w_grad_store_.Data(); w_grad_.rows = w_grad_store_.NumRows();
+  w_grad_.cols = w_grad_store_.NumCols(); w_grad_.stride = w_grad_store_.Stride();
+  b_grad_.data = b_grad_store_.Data(); b_grad_.rows = 1;
+  b_grad_.cols = b_grad_store_.Dim(); b_grad_.stride = b_grad_store_.Dim();
+}
+
+size_t AffineComponent::GradientFloats() const {
+  size_t stride = CuDevice::PitchInElements(linear_params_.NumCols(), sizeof(BaseFloat));
+  return stride * linear_params_.NumRows() + CuDevice::PitchInElements(bias_params_.Dim(), sizeof(BaseFloat));
+}
+
+void AffineComponent::SetGradientStorage(float *base) {
+  if (base == NULL) { grad_external_ = false; return; }
+  int32 stride = CuDevice::PitchInElements(linear_params_.NumCols(), sizeof(BaseFloat));
+  w_grad_.data = base; w_grad_.rows = linear_params_.NumRows();
+  w_grad_.cols = linear_params_.NumCols(); w_grad_.stride = stride;
+  b_grad_.data = base + (size_t)stride * linear_params_.NumRows(); b_grad_.rows = 1;
+  b_grad_.cols = bias_params_.Dim(); b_grad_.stride = bias_params_.Dim();
+  grad_external_ = true;
+}
+
+std::vector<UpdatableComponent::GradBuffer> AffineComponent::GradientBuffers() {
+  EnsureGradBuffers();
+  std::vector<GradBuffer> v;
+  v.push_back(w_grad_);
+  v.push_back(b_grad_);
+  return v;
+}
+
+void AffineComponent::ComputeGradient(const CuMatrixBase<BaseFloat> &in_value,
+                                      const CuMatrixBase<BaseFloat> &out_deriv) {
+  EnsureGradBuffers();
+  ::MatrixDim gd = {w_grad_.rows, w_grad_.cols, w_grad_.stride};
+  cudaF_affine_wgrad(Str(), CuDevice::Instantiate().MathMode(), in_value.Data(), in_value.Dim(),
+                     out_deriv.Data(), out_deriv.Dim(), w_grad_.data, gd, b_grad_.data);
+  CU_SAFE_CALL(cudaGetLastError());
+}
+
+// Stock update (no momentum): bias += lr * colsum(out_deriv); W += lr * out_deriv^T in.
+// reference :1230-1235.
+void AffineComponent::UpdateSimple(const CuMatrixBase<BaseFloat> &in_value,
+                                   const CuMatrixBase<BaseFloat> &out_deriv) {
+  ComputeGradient(in_value, out_deriv);
+  cudaF_vec_axpy(Str(), bias_params_.Data(), b_grad_.data, bias_params_.Dim(), learning_rate_);
+  CuSubMatrix<BaseFloat> g(w_grad_.data, w_grad_.rows, w_grad_.cols, w_grad_.stride);
+  linear_params_.AddMat(learning_rate_, g, kNoTrans);
+}
+
+// reference :1237-1258
+void AffineComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
+                               const CuMatrixBase<BaseFloat> &in_value,
+                               const CuMatrixBase<BaseFloat> &,
+                               const CuMatrixBase<BaseFloat> &out_deriv, Component *to_update_in,
+                               CuMatrix<BaseFloat> *in_deriv) const {
+  AffineComponent *to_update = dynamic_cast<AffineComponent *>(to_update_in);
+  in_deriv->Resize(out_deriv.NumRows(), InputDim(), kUndefined);
+  KALDI_ASSERT(out_deriv.NumCols() == OutputDim());
+  // Propagate the derivative back to the input: in_deriv = out_deriv W (beta = 0).
+  cudaF_affine_dgrad(Str(), CuDevice::Instantiate().MathMode(), out_deriv.Data(), out_deriv.Dim(),
+                     linear_params_.Data(), linear_params_.Dim(), in_deriv->Data(), in_deriv->Dim());
+  CU_SAFE_CALL(cudaGetLastError());
+  if (to_update != NULL) {
+    // must come second, in case this == to_update_in
+    if (to_update->is_gradient_) to_update->UpdateSimple(in_value, out_deriv);
+    else to_update->Update(in_value, out_deriv);
+  }
+}
+
+void AffineComponent::Read(std::istream &is, bool binary) {
+  std::ostringstream ostr_beg, ostr_end;
+  ostr_beg << "<" << Type() << ">";
+  ostr_end << "</" << Type() << ">";
+  ExpectOneOrTwoTokens(is, binary, ostr_beg.str(), "<LearningRate>");
+  ReadBasicType(is, binary, &learning_rate_);
+  ExpectToken(is, binary, "<LinearParams>");
+  linear_params_.Read(is, binary);
+  ExpectToken(is, binary, "<BiasParams>");
+  bias_params_.Read(is, binary);
+  std::string tok;
+  ReadToken(is, binary, &tok);
+  if (tok == "<AvgInput>") {   // back-compatibility: discard
+    CuVector<BaseFloat> avg_input;
+    avg_input.Read(is, binary);
+    BaseFloat avg_input_count;
+    ExpectToken(is, binary, "<AvgInputCount>");
+    ReadBasicType(is, binary, &avg_input_count);
+    ReadToken(is, binary, &tok);
+  }
+  if (tok == "<IsGradient>") {
+    ReadBasicType(is, binary, &is_gradient_);
+    ExpectToken(is, binary, ostr_end.str());
+  } else {
+    is_gradient_ = false;
+    KALDI_ASSERT(tok == ostr_end.str());
+  }
+}
+
+void AffineComponent::Write(std::ostream &os, bool binary) const {
+  std::ostringstream ostr_beg, ostr_end;
+  ostr_beg << "<" << Type() << ">";
+  ostr_end << "</" << Type() << ">";
+  WriteToken(os, binary, ostr_beg.str());
+  WriteToken(os, binary, "<LearningRate>");
+  WriteBasicType(os, binary, learning_rate_);
+  WriteToken(os, binary, "<LinearParams>");
+  linear_params_.Write(os, binary);
+  WriteToken(os, binary, "<BiasParams>");
+  bias_params_.Write(os, binary);
+  WriteToken(os, binary, "<IsGradient>");
+  WriteBasicType(os, binary, is_gradient_);
+  WriteToken(os, binary, ostr_end.str());
+}
+
+void AffineComponent::Scale(BaseFloat scale) {
+  linear_params_.Scale(scale);
+  bias_params_.Scale(scale);
+}
+
+void AffineComponent::Add(BaseFloat alpha, const UpdatableComponent &other_in) {
+  const AffineComponent *other = dynamic_cast<const AffineComponent *>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  linear_params_.AddMat(alpha, other->linear_params_);
+  bias_params_.AddVec(alpha, other->bias_params_);
+}
+
+int32 AffineComponent::GetParameterDim() const { return (InputDim() + 1) * OutputDim(); }
+
+void AffineComponent::Vectorize(VectorBase<BaseFloat> *params) const {
+  KALDI_ASSERT(params->Dim() == GetParameterDim());
+  Matrix<BaseFloat> w(linear_params_.NumRows(), linear_params_.NumCols());
+  linear_params_.CopyToMat(&w);
+  Vector<BaseFloat> b(bias_params_.Dim());
+  bias_params_.CopyToVec(&b);
+  int32 k = 0;
+  for (int32 r = 0; r < w.NumRows(); r++)
+    for (int32 c = 0; c < w.NumCols(); c++) (*params)(k++) = w(r, c);
+  for (int32 i = 0; i < b.Dim(); i++) (*params)(k++) = b(i);
+}
+
+void AffineComponent::UnVectorize(const VectorBase<BaseFloat> &params) {
+  KALDI_ASSERT(params.Dim() == GetParameterDim());
+  Matrix<BaseFloat> w(linear_params_.NumRows(), linear_params_.NumCols());
+  Vector<BaseFloat> b(bias_params_.Dim());
+  int32 k = 0;
+  for (int32 r = 0; r < w.NumRows(); r++)
+    for (int32 c = 0; c < w.NumCols(); c++) w(r, c) = params(k++);
+  for (int32 i = 0; i < b.Dim(); i++) b(i) = params(k++);
+  linear_params_.CopyFromMat(w);
+  bias_params_.CopyFromVec(b);
+}
+
+}  // namespace nnet2
+}  // namespace kaldi

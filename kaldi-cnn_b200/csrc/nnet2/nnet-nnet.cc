@@ -1,0 +1,199 @@
+// nnet2/nnet-nnet.cc -- shim (see nnet-nnet.h).
+#include <sstream>
+
+#include "nnet2/nnet-nnet.h"
+#include "cnsl-cu-kernels.h"
+
+namespace kaldi {
+namespace nnet2 {
+
+static inline cudaStream_t Str() { return CuDevice::Instantiate().Stream(); }
+
+void Nnet::Destroy() {
+  for (size_t i = 0; i < components_.size(); i++) delete components_[i];
+  components_.clear();
+}
+
+void Nnet::Init(std::istream &is, bool skip_splice) {
+  Destroy();
+  std::string line;
+  while (std::getline(is, line)) {
+    size_t b = line.find_first_not_of(" \t\r\n");
+    if (b == std::string::npos || line[b] == '#') continue;
+    size_t e = line.find_last_not_of(" \t\r\n");
+    line = line.substr(b, e - b + 1);
+    if (skip_splice && line.compare(0, 15, "SpliceComponent") == 0) continue;
+    Component *c = Component::NewFromString(line);
+    c->SetIndex(components_.size());
+    components_.push_back(c);
+  }
+  Check();
+}
+
+void Nnet::Check() const {
+  for (size_t i = 0; i + 1 < components_.size(); i++) {
+    int32 output_dim = components_[i]->OutputDim(), next_input_dim = components_[i + 1]->InputDim();
+    if (output_dim != next_input_dim)
+      KALDI_ERR << "Dimension mismatch between output of component " << i << " ("
+                << components_[i]->Type() << ", " << output_dim << ") and input of the next ("
+                << components_[i + 1]->Type() << ", " << next_input_dim << ")";
+  }
+}
+
+void Nnet::Write(std::ostream &os, bool binary) const {
+  WriteToken(os, binary, "<Nnet>");
+  int32 num_components = components_.size();
+  WriteToken(os, binary, "<NumComponents>");
+  WriteBasicType(os, binary, num_components);
+  WriteToken(os, binary, "<Components>");
+  for (int32 c = 0; c < num_components; c++) {
+    components_[c]->Write(os, binary);
+    if (!binary) os << std::endl;
+  }
+  WriteToken(os, binary, "</Components>");
+  WriteToken(os, binary, "</Nnet>");
+}
+
+void Nnet::Read(std::istream &is, bool binary) {
+  Destroy();
+  ExpectToken(is, binary, "<Nnet>");
+  int32 num_components;
+  ExpectToken(is, binary, "<NumComponents>");
+  ReadBasicType(is, binary, &num_components);
+  ExpectToken(is, binary, "<Components>");
+  components_.resize(num_components, NULL);
+  for (int32 c = 0; c < num_components; c++) {
+    components_[c] = Component::ReadNew(is, binary);
+    components_[c]->SetIndex(c);
+  }
+  ExpectToken(is, binary, "</Components>");
+  ExpectToken(is, binary, "</Nnet>");
+  Check();
+}
+
+int32 Nnet::NumUpdatableComponents() const {
+  int32 ans = 0;
+  for (size_t i = 0; i < components_.size(); i++)
+    if (dynamic_cast<const UpdatableComponent *>(components_[i]) != NULL) ans++;
+  return ans;
+}
+
+std::string Nnet::Info() const {
+  std::ostringstream ostr;
+  ostr << "num-components " << NumComponents() << std::endl;
+  ostr << "num-updatable-components " << NumUpdatableComponents() << std::endl;
+  ostr << "input-dim " << InputDim() << std::endl;
+  ostr << "output-dim " << OutputDim() << std::endl;
+  for (int32 i = 0; i < NumComponents(); i++)
+    ostr << "component " << i << " : " << components_[i]->Info() << std::endl;
+  return ostr.str();
+}
+
+// ------------------------------------------------------- NnetMinibatchUpdater --
+
+NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
+    : nnet_(nnet), num_rows_(0), labels_(NULL), objf_dev_(NULL) {
+  objf_dev_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double)));
+  CU_SAFE_CALL(cudaMemsetAsync(objf_dev_, 0, sizeof(double), Str()));
+}
+
+NnetMinibatchUpdater::~NnetMinibatchUpdater() { CuDevice::Instantiate().Free(objf_dev_); }
+
+void NnetMinibatchUpdater::Forward(const CuMatrixBase<BaseFloat> &feats) {
+  const int32 L = nnet_->NumComponents();
+  KALDI_ASSERT(L > 0 && feats.NumCols() == nnet_->InputDim());
+  if (num_rows_ != feats.NumRows() || static_cast<int32>(forward_.size()) != L + 1) {
+    num_rows_ = feats.NumRows();
+    forward_.clear();
+    forward_.resize(L + 1);
+    info_.clear();
+    info_.push_back(ChunkInfo(nnet_->InputDim(), num_rows_, 0, 0));
+    for (int32 c = 0; c < L; c++) {
+      int32 dim = nnet_->GetComponent(c).OutputDim();
+      info_.push_back(ChunkInfo(dim, num_rows_, 0, 0));
+      forward_[c + 1].Resize(num_rows_, dim, kUndefined);
+    }
+  }
+  // the input is used in place (a borrowed view), not copied
+  forward_[0].Borrow(const_cast<BaseFloat *>(feats.Data()), feats.NumRows(), feats.NumCols(),
+                     feats.Stride());
+  for (int32 c = 0; c < L; c++)
+    nnet_->GetComponent(c).Propagate(info_[c], info_[c + 1], forward_[c],
+                                     static_cast<CuMatrixBase<BaseFloat> *>(&forward_[c + 1]));
+}
+
+void NnetMinibatchUpdater::ComputeObjfAndDeriv(const int32 *labels_dev) {
+  const CuMatrix<BaseFloat> &post = forward_.back();
+  deriv_a_.Resize(post.NumRows(), post.NumCols(), kUndefined);
+  cudaF_xent_deriv(Str(), post.Data(), post.Dim(), labels_dev, deriv_a_.Data(), deriv_a_.Dim(),
+                   objf_dev_);
+  CU_SAFE_CALL(cudaGetLastError());
+}
+
+void NnetMinibatchUpdater::Backward(int32 last, int32 first) {
+  const int32 L = nnet_->NumComponents();
+  if (last < 0) last = L - 1;
+  KALDI_ASSERT(first >= 0 && last < L && !forward_.empty());
+  // deriv_a_ holds d objf / d output-of-component[last]
+  for (int32 c = last; c >= first; c--) {
+    Component &comp = nnet_->GetComponent(c);
+    comp.Backprop(info_[c], info_[c + 1], forward_[c], forward_[c + 1], deriv_a_, &comp, &deriv_b_);
+    deriv_a_.Swap(&deriv_b_);
+  }
+}
+
+void NnetMinibatchUpdater::SetDeferredUpdate(bool on) {
+  for (int32 c = 0; c < nnet_->NumComponents(); c++) {
+    UpdatableComponent *u = dynamic_cast<UpdatableComponent *>(&nnet_->GetComponent(c));
+    if (u) u->SetDeferredUpdate(on);
+  }
+}
+
+void NnetMinibatchUpdater::ApplyGradients(int32 total_rows) {
+  for (int32 c = 0; c < nnet_->NumComponents(); c++) {
+    UpdatableComponent *u = dynamic_cast<UpdatableComponent *>(&nnet_->GetComponent(c));
+    if (u && u->DeferredUpdate()) u->ApplyGradient(total_rows);
+  }
+}
+
+size_t NnetMinibatchUpdater::GradientFloats() const {
+  size_t n = 0;
+  for (int32 c = 0; c < nnet_->NumComponents(); c++) {
+    const UpdatableComponent *u = dynamic_cast<const UpdatableComponent *>(&nnet_->GetComponent(c));
+    if (u) n += (u->GradientFloats() + 63) / 64 * 64;      // 256-byte aligned buckets
+  }
+  return n;
+}
+
+void NnetMinibatchUpdater::SetGradientArena(float *base) {
+  const int32 L = nnet_->NumComponents();
+  bucket_off_.assign(L, 0);
+  bucket_len_.assign(L, 0);
+  size_t off = 0;
+  for (int32 c = L - 1; c >= 0; c--) {     // top layer first: the order backward produces them
+    UpdatableComponent *u = dynamic_cast<UpdatableComponent *>(&nnet_->GetComponent(c));
+    if (!u) continue;
+    size_t len = (u->GradientFloats() + 63) / 64 * 64;
+    bucket_off_[c] = off;
+    bucket_len_[c] = len;
+    u->SetGradientStorage(base ? base + off : NULL);
+    off += len;
+  }
+}
+
+void NnetMinibatchUpdater::GradientBucket(int32 c, size_t *offset, size_t *length) const {
+  KALDI_ASSERT(c >= 0 && c < static_cast<int32>(bucket_off_.size()));
+  *offset = bucket_off_[c];
+  *length = bucket_len_[c];
+}
+
+double NnetMinibatchUpdater::GetObjfAndReset() {
+  double v = 0;
+  CU_SAFE_CALL(cudaMemcpyAsync(&v, objf_dev_, sizeof(double), cudaMemcpyDeviceToHost, Str()));
+  CU_SAFE_CALL(cudaMemsetAsync(objf_dev_, 0, sizeof(double), Str()));
+  CU_SAFE_CALL(cudaStreamSynchronize(Str()));
+  return v;
+}
+
+}  // namespace nnet2
+}  // namespace kaldi

@@ -1,0 +1,87 @@
+// nnet2/nnet-nnet.h -- shim: a minimal nnet2::Nnet (sequence of Components) and the
+// minibatch step that nnet2's NnetUpdater performs (upstream nnet-update.cc, absent from
+// the patch set): Propagate through every component, cross-entropy
+// objective + derivative at the output, Backprop in reverse with to_update == the
+// component itself, so the parameter update happens inside Backprop.
+// These are the CALLERS of the hot path, kept just big enough to drive it.
+#ifndef KALDI_NNET2_NNET_NNET_H_
+#define KALDI_NNET2_NNET_NNET_H_
+
+#include <string>
+#include <vector>
+
+#include "nnet2/nnet-component.h"
+
+namespace kaldi {
+namespace nnet2 {
+
+class Nnet {
+ public:
+  Nnet() {}
+  ~Nnet() { Destroy(); }
+  /// One component per config line ("Type key=value ..."), as nnet-init does.
+  /// SpliceComponent lines are skipped when skip_splice is set: the benchmark feeds
+  /// already-spliced [N x 40*21] windows.
+  void Init(std::istream &is, bool skip_splice = false);
+  void Read(std::istream &is, bool binary);
+  void Write(std::ostream &os, bool binary) const;
+  int32 NumComponents() const { return static_cast<int32>(components_.size()); }
+  const Component &GetComponent(int32 c) const { return *components_[c]; }
+  Component &GetComponent(int32 c) { return *components_[c]; }
+  int32 InputDim() const { return components_.empty() ? 0 : components_.front()->InputDim(); }
+  int32 OutputDim() const { return components_.empty() ? 0 : components_.back()->OutputDim(); }
+  void Append(Component *c) { components_.push_back(c); }
+  int32 NumUpdatableComponents() const;
+  std::string Info() const;
+  void Check() const;
+ private:
+  void Destroy();
+  std::vector<Component *> components_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(Nnet);
+};
+
+/// Forward / backward over one minibatch with persistent activation buffers (sized on
+/// the first call for a given number of rows; no allocation afterwards).
+class NnetMinibatchUpdater {
+ public:
+  explicit NnetMinibatchUpdater(Nnet *nnet);
+  ~NnetMinibatchUpdater();
+  /// feats: device [num_rows x InputDim()].  Runs Propagate through all components.
+  void Forward(const CuMatrixBase<BaseFloat> &feats);
+  /// labels: device int32 [num_rows].  Writes the cross-entropy derivative at the output
+  /// and accumulates sum_i log p[i, label_i] into the device objective.
+  void ComputeObjfAndDeriv(const int32 *labels_dev);
+  /// Backprop through components [first, last] in reverse order (last defaults to the
+  /// top).  Splitting the range lets a data-parallel caller start all-reducing the
+  /// gradients of the upper layers while the lower layers are still running.
+  void Backward(int32 last = -1, int32 first = 0);
+  /// ApplyGradient(total_rows) on every updatable component (deferred-update mode).
+  void ApplyGradients(int32 total_rows);
+  /// Total floats of gradient storage; SetGradientArena places every component's
+  /// gradient buffers in one contiguous arena (one bucket per component, top first).
+  size_t GradientFloats() const;
+  void SetGradientArena(float *base);
+  /// Offset (floats) of component c's bucket inside the arena and its length.
+  void GradientBucket(int32 c, size_t *offset, size_t *length) const;
+  void SetDeferredUpdate(bool on);
+  const CuMatrix<BaseFloat> &Output() const { return forward_.back(); }
+  const CuMatrix<BaseFloat> &Activation(int32 i) const { return forward_[i]; }
+  const CuMatrix<BaseFloat> &InputDeriv() const { return deriv_a_; }
+  double *ObjfDevice() { return objf_dev_; }
+  double GetObjfAndReset();      // synchronises
+  int32 NumRows() const { return num_rows_; }
+ private:
+  Nnet *nnet_;
+  int32 num_rows_;
+  std::vector<CuMatrix<BaseFloat> > forward_;   // [0] = copy-free view of the input
+  std::vector<ChunkInfo> info_;
+  CuMatrix<BaseFloat> deriv_a_, deriv_b_;
+  const int32 *labels_;
+  double *objf_dev_;
+  std::vector<size_t> bucket_off_, bucket_len_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(NnetMinibatchUpdater);
+};
+
+}  // namespace nnet2
+}  // namespace kaldi
+#endif
