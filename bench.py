@@ -1,0 +1,489 @@
+#!/usr/bin/env python
+"""bench.py -- CNN training throughput (frames/sec) of the kaldi-cnn hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one training minibatch through the hot path: Propagate through every
+component of the model, cross-entropy objective + derivative, Backprop in reverse with the
+parameter update inside Backprop (momentum / weight-decay SGD), exactly the loop nnet2's
+NnetUpdater runs.  One frame = one minibatch row.
+
+Workload (config.workload): BASELINE.json configs[1] -- the reference's time-axis deep CNN
+(egs/exp/nnet/nnet.config: 40 mel x 21 frames, 6 conv + pool + 3 FC + softmax 3454) with an
+intermap max-pool after conv1 (pool-channel-dim=2, the egs/local/nnet0/run_conv.sh shape),
+per-GPU minibatch 512 (the recipes' GPU minibatch, egs/local/nnet0/run_nnet.sh:19-20), synthetic
+N(0,1) filterbank windows, random-init weights.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel of the step, timed live with CUDA events
+  cpu_baseline  the reference's CPU path (oracle/_ref when built, else the oracle port)
+                timed on this box's host cores on a bounded sample
+  kernels       per-kernel rooflines named by BASELINE's metric (conv tensor pipe, maxpool HBM GB/s)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2-intermap": ("nnet_c2_intermap.config",
+                    "C2 time-axis deep CNN with intermap pooling: egs/exp/nnet/nnet.config + "
+                    "MaxpoolComponent pool-channel-dim=2 after conv1 (40x21x1 input, 6 conv, 2 maxpool, 3 FC, "
+                    "softmax 3454)"),
+    "c2": ("nnet_c2.config",
+           "C2: egs/exp/nnet/nnet.config verbatim (40x21x1 input, 6 conv, time max-pool, 3 FC, softmax 3454)"),
+}
+
+
+def load_config(name):
+    path = os.path.join(ROOT, "kaldi-cnn_b200", "configs", WORKLOADS[name][0])
+    return open(path).read()
+
+
+def model_flops_per_frame(cfg_text):
+    """Algorithmic training FLOPs per frame: 3 x forward GEMM FLOPs (fprop, dgrad, wgrad) of the
+    conv and FC layers."""
+    from oracle.cpu_nnet import parse_config
+    macs = 0
+    for kind, kv in parse_config(cfg_text):
+        if kind == "ConvolutionComponent":
+            g = lambda k, d=0: int(kv.get(k, d))
+            oh = g("in-height") + 2 * g("in-pad-height") - g("kernel-height") + 1
+            ow = g("in-width") + 2 * g("in-pad-width") - g("kernel-width") + 1
+            macs += oh * ow * g("group") * g("kernel-height") * g("kernel-width") * g("in-channel")
+        elif kind == "FullyConnectedComponent":
+            macs += int(kv["input-dim"]) * int(kv["output-dim"])
+    return 2 * macs * 3
+
+
+def param_count(cfg_text):
+    from oracle.cpu_nnet import parse_config
+    n = 0
+    for kind, kv in parse_config(cfg_text):
+        if kind == "ConvolutionComponent":
+            n += (int(kv["kernel-height"]) * int(kv["kernel-width"]) * int(kv["in-channel"]) + 1) * int(kv["group"])
+        elif kind == "FullyConnectedComponent":
+            n += (int(kv["input-dim"]) + 1) * int(kv["output-dim"])
+    return n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------ CPU arm --
+
+def cpu_backend():
+    """('reference', module) when oracle/_ref is built, else ('port', oracle)."""
+    try:
+        from oracle import ref
+        if ref.available():
+            return "reference", ref
+    except Exception:
+        pass
+    from oracle import oracle
+    oracle.build()
+    return "port", oracle
+
+
+def cpu_train_frames_per_sec(cfg_text, rows, steps, warmup, threads):
+    import numpy as np
+    from oracle.cpu_nnet import CpuNnet
+    kind, backend = cpu_backend()
+    if hasattr(backend, "set_num_threads"):
+        backend.set_num_threads(threads)
+    net = CpuNnet(cfg_text, seed=42, backend=backend)
+    rng = np.random.default_rng(1234)
+    x = rng.standard_normal((rows, net.input_dim)).astype(np.float32)
+    nout = [L for L in net.layers if L["kind"] == "SoftmaxComponent"][-1]["dim"]
+    labels = rng.integers(0, nout, size=rows).astype(np.int64)
+    for _ in range(warmup):
+        net.train_step(x, labels)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        net.train_step(x, labels)
+    dt = time.perf_counter() - t0
+    used = threads if (kind == "reference" and hasattr(backend, "set_num_threads")) else 1
+    return rows * steps / dt, dt / steps, kind, used
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = load_config(args.workload)
+    cores = os.cpu_count() or 1
+    rows = args.cpu_rows
+    fps, sec, kind, used = cpu_train_frames_per_sec(cfg, rows, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": "train_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][1], "per_gpu_batch": args.batch,
+                   "cpu_sample_rows_per_step": rows},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": used, "kind": kind,
+                         "sample": "%d training steps of %d rows of the same model on the host CPU" % (args.steps, rows)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm --
+
+def event_time_ms(fn, iters, flush=None):
+    import torch
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        times.append(a.elapsed_time(b))
+    times.sort()
+    return times[len(times) // 2], sum(times) / len(times)
+
+
+def kernel_rooflines(args, pk, math):
+    """Live CUDA-event timings of the kernels BASELINE's metric names, at the model's shapes:
+    the dominant GEMM of the step, a conv fprop, and max-pool forward / backward."""
+    import torch
+    from kaldi_cnn_b200 import capi
+    from kaldi_cnn_b200.capi import mdim, ptr, stream
+    L = capi.lib()
+    N = args.batch
+    out = []
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    tf32_peak = pk["bf16_tflops"] / 2.0
+    simt_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    peak = tf32_peak if math == 1 else simt_peak
+    peak_note = ("measured bf16 dense / 2 (TF32 runs at half the bf16 rate)" if math == 1
+                 else "nominal FP32 FMA: 148 SM x 128 lanes x 2 x 1.965 GHz")
+
+    def gemm_entry(name, fn, flops):
+        med, _ = event_time_ms(fn, 20, flush)
+        out.append({"kernel": name, "bound": "tensor", "achieved": flops / (med * 1e-3) / 1e12, "peak": peak,
+                    "unit": "TFLOP/s", "frac": flops / (med * 1e-3) / 1e12 / peak, "ms": med,
+                    "peak_source": pk["source"] + ": " + peak_note, "traffic": None})
+
+    # FC2 (4096 x 4096): the largest GEMMs of the step
+    x = torch.randn(N, 4096, device="cuda")
+    w = torch.randn(4096, 4096, device="cuda") * 0.01
+    b = torch.zeros(4096, device="cuda")
+    y = torch.empty(N, 4096, device="cuda")
+    g = torch.empty(4096, 4096, device="cuda")
+    bg = torch.empty(4096, device="cuda")
+    fl = 2.0 * N * 4096 * 4096
+    gemm_entry("affine_fprop FC2 [%dx4096]x[4096x4096]^T" % N,
+               lambda: L.cudaF_affine_fprop(stream(), math, ptr(x), mdim(x), ptr(w), mdim(w), ptr(b), ptr(y), mdim(y)), fl)
+    gemm_entry("affine_dgrad FC2", lambda: L.cudaF_affine_dgrad(stream(), math, ptr(y), mdim(y), ptr(w), mdim(w), ptr(x), mdim(x)), fl)
+    gemm_entry("affine_wgrad FC2", lambda: L.cudaF_affine_wgrad(stream(), math, ptr(x), mdim(x), ptr(y), mdim(y), ptr(g), mdim(g), ptr(bg)), fl)
+    # conv4 of nnet.config: 1x14x256 -> k1x3 -> 256 maps
+    H, W, C, KH, KW, G = 1, 14, 256, 1, 3, 256
+    xi = torch.randn(N, H * W * C, device="cuda")
+    k = torch.randn(KH * KW * C, G, device="cuda") * 0.01
+    bb = torch.zeros(G, device="cuda")
+    yo = torch.empty(N, 12 * G, device="cuda")
+    fl = 2.0 * N * 12 * G * KH * KW * C
+    gemm_entry("conv2d_fprop conv4 (M,N,K)=(%d,256,768)" % (N * 12),
+               lambda: L.cudaF_conv2d_fprop(stream(), math, ptr(xi), mdim(xi), ptr(k), mdim(k), ptr(bb), ptr(yo), mdim(yo),
+                                            H, W, C, 0, 0, KH, KW, G, 1), fl)
+    # max pooling at the C4 sweep shape 1x8x2000 pool 1x2x10 and at the model's time pool
+    for (name, H, W, C, ph, pw, pc, rows) in (("1x8x2000 pool 1x2x10", 1, 8, 2000, 1, 2, 10, 8192),
+                                              ("1x16x2000 pool 1x2x1", 1, 16, 2000, 1, 2, 1, 8192),
+                                              ("1x12x256 pool 1x2x1 (model)", 1, 12, 256, 1, 2, 1, N)):
+        ind, outd = H * W * C, (H // ph) * (W // pw) * (C // pc)
+        xi = torch.randn(rows, ind, device="cuda")
+        yo = torch.empty(rows, outd, device="cuda")
+        dy = torch.randn(rows, outd, device="cuda")
+        dx = torch.empty(rows, ind, device="cuda")
+        med, _ = event_time_ms(lambda: L.cudaF_maxpool_prop_s(stream(), ptr(xi), mdim(xi), ptr(yo), mdim(yo), H, W, ph, pw, pc, 0),
+                               20, flush)
+        byts = 4.0 * rows * (ind + outd)
+        out.append({"kernel": "maxpool_prop " + name + " N=%d" % rows, "bound": "hbm", "achieved": byts / (med * 1e-3) / 1e9,
+                    "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": byts / (med * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": med,
+                    "peak_source": pk["source"], "traffic": None})
+        med, _ = event_time_ms(lambda: L.cudaF_maxpool_backprop_s(stream(), ptr(xi), mdim(xi), ptr(yo), mdim(yo), ptr(dy), mdim(dy),
+                                                                  ptr(dx), mdim(dx), H, W, ph, pw, pc, 0, 1), 20, flush)
+        byts = 4.0 * rows * (2 * ind + 2 * outd)
+        out.append({"kernel": "maxpool_backprop(exact, zero-fill fused) " + name + " N=%d" % rows, "bound": "hbm",
+                    "achieved": byts / (med * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": byts / (med * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": med, "peak_source": pk["source"],
+                    "traffic": None})
+    return out
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from kaldi_cnn_b200 import components as kc
+    from kaldi_cnn_b200 import capi
+
+    math = 1 if args.math == "tf32" else 0
+    kc.set_math_mode(math)
+    kc.set_rand_seed(42)
+    cfg = load_config(args.workload)
+    net = kc.Nnet.from_config(cfg, skip_splice=True)
+    N, dim, nout = args.batch, net.input_dim, net.output_dim
+    L = capi.lib()
+    pk = peaks()
+
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+    feats = torch.randn(N, dim, device="cuda", generator=gen)
+    labels = torch.randint(0, nout, (N,), device="cuda", generator=gen, dtype=torch.int32)
+    stream = torch.cuda.Stream()
+    arena = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            arena = net.enable_data_parallel()
+    ncomp = net.num_components
+    updatable = [c for c in range(ncomp) if L.kcnn_component_gradient_floats(net.component(c).h) > 0]
+
+    def step():
+        net.forward(feats)
+        net.objf_and_deriv(labels)
+        if world == 1:
+            net.backward()
+            return
+        # data parallel: backward top-down, all-reduce each layer's gradient bucket as soon as
+        # its Backprop has been issued (overlaps the rest of the backward), then apply.
+        works, hi = [], ncomp - 1
+        for c in reversed(updatable):
+            net.backward(hi, c)
+            off, ln = net.gradient_bucket(c)
+            works.append(dist.all_reduce(arena[off:off + ln], async_op=True))
+            hi = c - 1
+        if hi >= 0:
+            net.backward(hi, 0)
+        for w in works:
+            w.wait()
+        net.apply_gradients(N * world)
+
+    with torch.cuda.stream(stream):
+        kc.use_current_stream()
+        for _ in range(max(args.warmup, 3)):
+            step()
+        stream.synchronize()
+        L.kcnn_reset_launch_count()
+        step()
+        stream.synchronize()
+        launches_per_step = int(L.kcnn_launch_count())
+        graph = None
+        if args.graph and world == 1:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    step()
+            except Exception as e:           # capture is an optimisation, never a requirement
+                sys.stderr.write("bench.py: CUDA graph capture unavailable (%s); running eagerly\n" % e)
+                graph = None
+                torch.cuda.synchronize()
+        run = (lambda: graph.replay()) if graph is not None else step
+        for _ in range(3):
+            run()
+        stream.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            run()
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        objf = net.objf_and_reset()
+
+        # ---- end to end through the C-ABI with HOST buffers (pinned), copies in the timed region
+        e2e = None
+        if world == 1:
+            hx = torch.randn(N, dim).pin_memory()
+            hl = torch.randint(0, nout, (N,), dtype=torch.int32).pin_memory()
+            hx_np, hl_np = hx.numpy(), hl.numpy()
+            for _ in range(3):
+                net.train_minibatch_host(hx_np, hl_np)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                net.train_minibatch_host(hx_np, hl_np)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e = {"value": N * args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": N * dim * 4 + N * 4,
+                   "d2h_bytes_per_step": 8, "ms_per_step": dt / args.steps * 1e3,
+                   "api": "kcnn_nnet_train_minibatch_host (include/kcnn_capi.h), pinned host buffers"}
+        else:
+            # per-rank host->device copy + step + objective read, max over ranks
+            hx = torch.randn(N, dim).pin_memory()
+            hl = torch.randint(0, nout, (N,), dtype=torch.int32).pin_memory()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                feats.copy_(hx, non_blocking=True)
+                labels.copy_(hl, non_blocking=True)
+                step()
+                net.objf_and_reset()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            e2e = {"value": N * world * args.steps / float(dt.item()), "unit": "frames/s",
+                   "h2d_bytes_per_step": N * dim * 4 + N * 4, "d2h_bytes_per_step": 8,
+                   "api": "kcnn_nnet_forward/backward + NCCL all-reduce, pinned host buffers per rank"}
+
+        kernels = kernel_rooflines(args, pk, math) if (rank == 0 and not args.no_kernels) else []
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    frames = N * world * args.steps
+    value = frames / (ms * 1e-3)
+    flops_frame = model_flops_per_frame(cfg)
+    step_tflops = flops_frame * N / (ms / args.steps * 1e-3) / 1e12
+    cpu = None
+    if not args.no_cpu:
+        try:
+            fps, sec, kind, used = cpu_train_frames_per_sec(cfg, args.cpu_rows, 2, 1, os.cpu_count() or 1)
+            cpu = {"value": fps, "unit": "frames/s", "cores": used, "kind": kind,
+                   "sample": "2 training steps of %d rows of the same model (after 1 warm-up) on the host CPU" % args.cpu_rows}
+        except Exception as e:
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    dominant = None
+    for kr in kernels:
+        if kr["kernel"].startswith("affine_wgrad"):
+            dominant = dict(kr)
+    line = {
+        "metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32" if math == 1 else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][1], "per_gpu_batch": N, "global_batch": N * world,
+                   "parallelism": "dp%d" % world if world > 1 else "single",
+                   "params": param_count(cfg), "train_mflop_per_frame": flops_frame / 1e6,
+                   "l2": "working set (weights + momentum + gradients = %.0f MB) exceeds the 126 MB L2"
+                         % (param_count(cfg) * 12 / 1e6),
+                   "cuda_graph": graph is not None,
+                   "math": "KCNN_MATH_TF32_TC" if math == 1 else "KCNN_MATH_FP32_SIMT"},
+        "step_tflops": step_tflops,
+        "objf_per_frame_last": objf / max(N * (args.steps + 3 + 1), 1),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": dominant, "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2-intermap", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=512, help="minibatch rows per GPU")
+    ap.add_argument("--math", default=os.environ.get("KCNN_BENCH_MATH", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--cpu-rows", type=int, default=64, help="rows per step of the bounded CPU sample")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

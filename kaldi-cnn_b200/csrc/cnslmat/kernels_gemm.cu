@@ -106,6 +106,25 @@ static int pick_splits(int M, int N, int K) {
   return (int)(want < 1 ? 1 : want);
 }
 
+// One problem, two kernels: tcgen05 TF32 or FP32 CUDA cores.  `ws` must hold
+// gemm_workspace_bytes(M, N, K) bytes when that is non-zero (split-K partials).
+template <bool kAFastK, bool kBFastK, bool kEpiFastN, class OpA, class OpB, class Out>
+static void launch_gemm(cudaStream_t st, int math, const OpA &a, const OpB &b, const Out &o, int M,
+                        int N, int K, bool allow_split, float *ws) {
+  if (math == KCNN_MATH_TF32_TC) {
+    tc::launch_gemm_tc<kAFastK, kBFastK, kEpiFastN>(st, a, b, o, M, N, K, allow_split ? ws : nullptr);
+  } else {
+    int splits = (allow_split && ws) ? pick_splits(M, N, K) : 1;
+    launch_gemm_simt<kAFastK, kBFastK, kEpiFastN>(st, a, b, o, M, N, K, splits, ws);
+  }
+}
+
+static size_t gemm_workspace_bytes(int M, int N, int K) {
+  size_t simt = (size_t)pick_splits(M, N, K) * M * N * sizeof(float);
+  size_t tcb = tc::workspace_bytes(M, N, K);
+  return simt > tcb ? simt : tcb;
+}
+
 struct ConvGeom {
   int N, H, W, C, ph, pw, KH, KW, G, OH, OW, P, ks;
 };
@@ -146,16 +165,13 @@ void cudaF_conv2d_fprop(cudaStream_t st, int math, const float *in, MatrixDim id
       // out[pos*N + n, g]                      (concat = false, conv2D.cc:199)
       : make_out(out, make_dec3(q.N, q.P, 1, od.stride, (long long)q.N * od.stride, 0, 0, 0, 0, 0, 0),
                  make_linear(G, 1), bias);
-  if (math == KCNN_MATH_TF32_TC && tc_conv_fprop(st, in, id, kernel, kd, bias, out, od, q.N, H, W, C,
-                                                 ph, pw, KH, KW, G, concat))
-    return;
   const bool a_fast_k = (q.OH == 1 && KH > 1);   // time-axis layers: the (kw, kh) run is contiguous
   if (concat) {
-    if (a_fast_k) launch_gemm_simt<true, false, false>(st, a, b, o, M, G, K, 1, nullptr);
-    else          launch_gemm_simt<false, false, false>(st, a, b, o, M, G, K, 1, nullptr);
+    if (a_fast_k) launch_gemm<true, false, false>(st, math, a, b, o, M, G, K, false, nullptr);
+    else          launch_gemm<false, false, false>(st, math, a, b, o, M, G, K, false, nullptr);
   } else {
-    if (a_fast_k) launch_gemm_simt<true, false, true>(st, a, b, o, M, G, K, 1, nullptr);
-    else          launch_gemm_simt<false, false, true>(st, a, b, o, M, G, K, 1, nullptr);
+    if (a_fast_k) launch_gemm<true, false, true>(st, math, a, b, o, M, G, K, false, nullptr);
+    else          launch_gemm<false, false, true>(st, math, a, b, o, M, G, K, false, nullptr);
   }
 }
 
@@ -165,10 +181,28 @@ void cudaF_conv2d_dgrad(cudaStream_t st, int math, const float *out_deriv, Matri
   ConvGeom q = conv_geom(odd.rows, H, W, C, ph, pw, KH, KW, G);
   if (q.N == 0 || C == 0) return;
   check_int32(odd, "conv out_deriv"); check_int32(idd, "conv in_deriv"); check_int32(kd, "conv kernel");
-  const int M = q.N * H * W, K = q.ks * G;
-  if (math == KCNN_MATH_TF32_TC && tc_conv_dgrad(st, out_deriv, odd, kernel, kd, in_deriv, idd, q.N,
-                                                 H, W, C, ph, pw, KH, KW, G))
+  if (q.OH == 1) {
+    // Full-height kernel (every layer of egs/exp/nnet/nnet.config): out_deriv has one row
+    // of positions, so kh is fixed by h (kh = h + ph) and moves from the reduction into the
+    // GEMM's N axis:  dX[(n, w), (c, h)] = sum_{kw, g} dY[n, g, w + pw - kw] K[c, kw, h + ph, g].
+    // (The reference's "no-flip" branch exploits the same structure with four copies,
+    // nnet0/nnet-component-nnet0.cc:499-528.)  N = C*H instead of C: conv1 (C = 1, H = 40)
+    // becomes a 40-wide GEMM instead of a 1-wide one.
+    const int M = q.N * W, Ng = C * H, K = KW * G;
+    Op3I a; a.base = out_deriv;
+    a.mn = make_dec3(q.N, W, 1, odd.stride, 1, 0, pw, 1, 0, pw, 0);
+    a.k = make_dec3_inner(KW, 1, G, q.OW, -1, 0, 0, -1, 0, 0, 0);
+    a.wlim = q.OW; a.hlim = 1;
+    Op3I b; b.base = kernel;
+    b.mn = make_dec3(C, H, 1, (long long)q.ks * kd.stride, kd.stride, 0, (long long)ph * kd.stride, 0, 0, 0, 0);
+    b.k = make_dec3_inner(KW, 1, G, 1, (long long)KH * kd.stride, 0, 0, 0, 0, 0, 0);
+    b.wlim = 1; b.hlim = 1;
+    Out33 o = make_out(in_deriv, make_dec3(q.N, W, 1, idd.stride, H, 0, 0, 0, 0, 0, 0),
+                       make_dec3(C, H, 1, H * W, 1, 0, 0, 0, 0, 0, 0), nullptr);
+    launch_gemm<false, true, true>(st, math, a, b, o, M, Ng, K, false, nullptr);
     return;
+  }
+  const int M = q.N * H * W, K = q.ks * G;
   // A(m = (n, w, h), k = (kw, kh, g)) = dY[n, g, w + pw - kw, h + ph - kh]
   // (folds PaddingZero of out_deriv and the 180-degree rotation of FlipMat)
   Op3I a; a.base = out_deriv;
@@ -183,7 +217,7 @@ void cudaF_conv2d_dgrad(cudaStream_t st, int math, const float *out_deriv, Matri
   // dX[n, c*H*W + w*H + h]
   Out33 o = make_out(in_deriv, make_dec3(q.N, H * W, 1, idd.stride, 1, 0, 0, 0, 0, 0, 0),
                      make_linear(C, H * W), nullptr);
-  launch_gemm_simt<false, true, false>(st, a, b, o, M, C, K, 1, nullptr);
+  launch_gemm<false, true, false>(st, math, a, b, o, M, C, K, false, nullptr);
 }
 
 size_t kcnn_conv2d_wgrad_workspace(int num_rows, int H, int W, int C, int ph, int pw, int KH,
@@ -191,9 +225,7 @@ size_t kcnn_conv2d_wgrad_workspace(int num_rows, int H, int W, int C, int ph, in
   ConvGeom q = conv_geom(num_rows, H, W, C, ph, pw, KH, KW, G);
   int M = q.ks * C, K = q.N * q.P;
   if (M <= 0 || G <= 0 || K <= 0) return 0;
-  size_t simt = (size_t)pick_splits(M, G, K) * M * G * sizeof(float);
-  size_t tc = tc_conv_wgrad_workspace(q.N, H, W, C, ph, pw, KH, KW, G);
-  return simt > tc ? simt : tc;
+  return gemm_workspace_bytes(M, G, K);
 }
 
 void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, MatrixDim ivd,
@@ -205,9 +237,6 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   check_int32(ivd, "conv in_value"); check_int32(odd, "conv out_deriv");
   const int M = q.ks * C, K = q.N * q.P;
   if (bias_grad) launch_colsum(st, out_deriv, q.N, odd.stride, G, q.P, bias_grad);
-  if (math == KCNN_MATH_TF32_TC && tc_conv_wgrad(st, in_value, ivd, out_deriv, odd, kernel_grad, kgd,
-                                                 workspace, q.N, H, W, C, ph, pw, KH, KW, G))
-    return;
   // A(m = (c, kw, kh), k = (n, ow, oh)) = Xpad[n, c, ow + kw, oh + kh]
   // (folds PaddingZero + TpBlock; row order (c, kw, kh) folds ModPermuteRow)
   Op33 a = make_op(in_value,
@@ -217,15 +246,13 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   Op33 b = make_op(out_deriv, make_linear(G, q.P),
                    make_dec3(q.N, q.P, 1, odd.stride, 1, 0, 0, 0, 0, 0, 0), 1, 1);
   Out33 o = make_out(kernel_grad, make_linear(M, kgd.stride), make_linear(G, 1), nullptr);
-  int splits = pick_splits(M, G, K);
-  if (splits > 1 && workspace == nullptr) splits = 1;
   const bool a_fast_k = !(q.OH == 1 && KH > 1);
   const bool b_fast_k = q.P >= 4;
   float *ws = static_cast<float *>(workspace);
-  if (a_fast_k && b_fast_k)       launch_gemm_simt<true, true, true>(st, a, b, o, M, G, K, splits, ws);
-  else if (a_fast_k && !b_fast_k) launch_gemm_simt<true, false, true>(st, a, b, o, M, G, K, splits, ws);
-  else if (!a_fast_k && b_fast_k) launch_gemm_simt<false, true, true>(st, a, b, o, M, G, K, splits, ws);
-  else                            launch_gemm_simt<false, false, true>(st, a, b, o, M, G, K, splits, ws);
+  if (a_fast_k && b_fast_k)       launch_gemm<true, true, true>(st, math, a, b, o, M, G, K, true, ws);
+  else if (a_fast_k && !b_fast_k) launch_gemm<true, false, true>(st, math, a, b, o, M, G, K, true, ws);
+  else if (!a_fast_k && b_fast_k) launch_gemm<false, true, true>(st, math, a, b, o, M, G, K, true, ws);
+  else                            launch_gemm<false, false, true>(st, math, a, b, o, M, G, K, true, ws);
 }
 
 void cudaF_sum_rows_per_map(cudaStream_t st, const float *m, MatrixDim md, int inner, float *out) {
@@ -238,12 +265,11 @@ void cudaF_affine_fprop(cudaStream_t st, int math, const float *in, MatrixDim id
   const int M = id.rows, N = wd.rows, K = wd.cols;
   if (M == 0 || N == 0) return;
   check_int32(id, "affine input"); check_int32(od, "affine output"); check_int32(wd, "affine weights");
-  if (math == KCNN_MATH_TF32_TC && tc_affine_fprop(st, in, id, w, wd, bias, out, od)) return;
   // out = 1 bias^T + in W^T : A(m, k) = in[m, k], B(k, n) = W[n, k]
   Op33 a = make_op(in, make_linear(M, id.stride), make_linear(K, 1), 1, 1);
   Op33 b = make_op(w, make_linear(N, wd.stride), make_linear(K, 1), 1, 1);
   Out33 o = make_out(out, make_linear(M, od.stride), make_linear(N, 1), bias);
-  launch_gemm_simt<true, true, true>(st, a, b, o, M, N, K, 1, nullptr);
+  launch_gemm<true, true, true>(st, math, a, b, o, M, N, K, false, nullptr);
 }
 
 void cudaF_affine_dgrad(cudaStream_t st, int math, const float *out_deriv, MatrixDim odd,
@@ -251,12 +277,11 @@ void cudaF_affine_dgrad(cudaStream_t st, int math, const float *out_deriv, Matri
   const int M = odd.rows, N = wd.cols, K = wd.rows;
   if (M == 0 || N == 0) return;
   check_int32(odd, "affine out_deriv"); check_int32(idd, "affine in_deriv");
-  if (math == KCNN_MATH_TF32_TC && tc_affine_dgrad(st, out_deriv, odd, w, wd, in_deriv, idd)) return;
   // in_deriv = out_deriv W : A(m, k) = dY[m, k], B(k, n) = W[k, n]
   Op33 a = make_op(out_deriv, make_linear(M, odd.stride), make_linear(K, 1), 1, 1);
   Op33 b = make_op(w, make_linear(N, 1), make_linear(K, wd.stride), 1, 1);
   Out33 o = make_out(in_deriv, make_linear(M, idd.stride), make_linear(N, 1), nullptr);
-  launch_gemm_simt<true, false, true>(st, a, b, o, M, N, K, 1, nullptr);
+  launch_gemm<true, false, true>(st, math, a, b, o, M, N, K, false, nullptr);
 }
 
 void cudaF_affine_wgrad(cudaStream_t st, int math, const float *in_value, MatrixDim ivd,
@@ -266,13 +291,11 @@ void cudaF_affine_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   if (M == 0 || N == 0) return;
   check_int32(ivd, "affine in_value"); check_int32(odd, "affine out_deriv");
   if (bias_grad) launch_colsum(st, out_deriv, odd.rows, odd.stride, M, 1, bias_grad);
-  if (math == KCNN_MATH_TF32_TC && tc_affine_wgrad(st, in_value, ivd, out_deriv, odd, w_grad, wgd))
-    return;
   // w_grad = out_deriv^T in_value : A(m, k) = dY[k, m], B(k, n) = X[k, n]
   Op33 a = make_op(out_deriv, make_linear(M, 1), make_linear(K, odd.stride), 1, 1);
   Op33 b = make_op(in_value, make_linear(N, 1), make_linear(K, ivd.stride), 1, 1);
   Out33 o = make_out(w_grad, make_linear(M, wgd.stride), make_linear(N, 1), nullptr);
-  launch_gemm_simt<false, false, true>(st, a, b, o, M, N, K, 1, nullptr);
+  launch_gemm<false, false, true>(st, math, a, b, o, M, N, K, false, nullptr);
 }
 
 }  // extern "C"
