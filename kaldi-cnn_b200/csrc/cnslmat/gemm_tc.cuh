@@ -38,6 +38,7 @@ namespace kcnn {
 namespace tc {
 
 constexpr int BM = 128, BK = 32, STAGES = 4;
+constexpr int PREFETCH = 2;          // K-blocks of loads in flight ahead of the one being stored
 constexpr int PRODUCER_WARPS = 8, PRODUCER_THREADS = PRODUCER_WARPS * 32;
 constexpr int THREADS = PRODUCER_THREADS + 32;
 constexpr int A_STAGE_BYTES = BM * BK * 4;
@@ -142,14 +143,16 @@ struct Smem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
 
-// Gathers a ROWS x 32 slice (rows row0.., K range k0..k0+31) into one swizzled stage.
-// kFastK:  thread owns the 16-byte K-chunk (t & 7) of rows (t >> 3) + 32 i
+// One thread's share of a ROWS x 32 operand slice: ROWS / 32 rows x one 16-byte K-chunk.
+// kFastK:  thread owns K-chunk (t & 7) of rows (t >> 3) + 32 i
 // !kFastK: warp w owns K-chunk w of rows lane + 32 i (consecutive lanes -> consecutive rows)
+// load_slice only ISSUES the global loads (into registers); store_slice rounds to TF32 and
+// writes the swizzled stage.  Keeping them apart lets the producer keep several K-blocks
+// of loads in flight (see the prefetch ring in the kernel).
 template <int ROWS, bool kFastK, class Op>
-__device__ __forceinline__ void produce_slice(const Op &op, const Ctx (&rows)[ROWS / 32], int k0,
-                                              int k_end, uint32_t stage_addr, int t) {
+__device__ __forceinline__ void load_slice(const Op &op, const Ctx (&rows)[ROWS / 32], int k0, int k_end,
+                                           int t, float4 (&v)[ROWS / 32]) {
   const int chunk = kFastK ? (t & 7) : (t >> 5);
-  const int rbase = kFastK ? (t >> 3) : (t & 31);
   Ctx ck[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -160,10 +163,9 @@ __device__ __forceinline__ void produce_slice(const Op &op, const Ctx (&rows)[RO
                       ck[3].off == ck[0].off + 3 && ck[3].dw != kInvalidCoord;
 #pragma unroll
   for (int i = 0; i < ROWS / 32; i++) {
-    const int r = rbase + 32 * i;
     const Ctx &cr = rows[i];
-    float4 v;
-    bool done = false;
+    bool vec = false;
+    const float *p = op.base + cr.off + ck[0].off;
     if (contig) {
       // all four taps inside the window?  (dw / dh of the K-neighbours may differ)
       bool ok = true;
@@ -171,21 +173,29 @@ __device__ __forceinline__ void produce_slice(const Op &op, const Ctx (&rows)[RO
       for (int j = 0; j < 4; j++)
         ok = ok && (unsigned)(cr.dw + ck[j].dw) < (unsigned)op.wlim &&
              (unsigned)(cr.dh + ck[j].dh) < (unsigned)op.hlim;
-      const float *p = op.base + cr.off + ck[0].off;
-      if (ok && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
-        v = __ldg(reinterpret_cast<const float4 *>(p));
-        done = true;
-      }
+      vec = ok && (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
     }
-    if (!done) {
-      v.x = op.load(cr, ck[0]);
-      v.y = op.load(cr, ck[1]);
-      v.z = op.load(cr, ck[2]);
-      v.w = op.load(cr, ck[3]);
+    if (vec) {
+      v[i] = __ldg(reinterpret_cast<const float4 *>(p));
+    } else {
+      v[i].x = op.load(cr, ck[0]);
+      v[i].y = op.load(cr, ck[1]);
+      v[i].z = op.load(cr, ck[2]);
+      v[i].w = op.load(cr, ck[3]);
     }
+  }
+}
+
+template <int ROWS, bool kFastK>
+__device__ __forceinline__ void store_slice(const float4 (&v)[ROWS / 32], uint32_t stage_addr, int t) {
+  const int chunk = kFastK ? (t & 7) : (t >> 5);
+  const int rbase = kFastK ? (t >> 3) : (t & 31);
+#pragma unroll
+  for (int i = 0; i < ROWS / 32; i++) {
+    const int r = rbase + 32 * i;
     uint32_t dst = stage_addr + r * 128 + ((chunk ^ (r & 7)) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(to_tf32(v.x)),
-                 "r"(to_tf32(v.y)), "r"(to_tf32(v.z)), "r"(to_tf32(v.w))
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(to_tf32(v[i].x)),
+                 "r"(to_tf32(v[i].y)), "r"(to_tf32(v[i].z)), "r"(to_tf32(v[i].w))
                  : "memory");
   }
 }
@@ -237,17 +247,36 @@ gemm_tc_kernel(const TcGemm<OpA, OpB, Out> g) {
 #pragma unroll
     for (int i = 0; i < BN / 32; i++)
       b_rows[i] = g.b.mn(n0 + (kBFastK ? (t >> 3) : (t & 31)) + 32 * i);
-    for (int kb = 0; kb < num_kb; kb++) {
-      const int s = kb % STAGES;
-      if (kb >= STAGES) mbar_wait(empty_bar(s), ((kb / STAGES) - 1) & 1);
-      const uint32_t a_addr = smem_base + s * S::STAGE_BYTES;
-      const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-      const int k0 = k_begin + kb * BK;
-      produce_slice<BM, kAFastK>(g.a, a_rows, k0, k_end, a_addr, t);
-      produce_slice<BN, kBFastK>(g.b, b_rows, k0, k_end, b_addr, t);
-      fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(s));
+    // Prefetch ring: the loads of K-block kb + PREFETCH are issued before the stores of
+    // K-block kb, so PREFETCH + 1 K-blocks (32 KB each per CTA) are in flight per SM.
+    float4 fa[PREFETCH + 1][BM / 32], fb[PREFETCH + 1][BN / 32];
+#pragma unroll
+    for (int u = 0; u < PREFETCH; u++)
+      if (u < num_kb) {
+        load_slice<BM, kAFastK>(g.a, a_rows, k_begin + u * BK, k_end, t, fa[u]);
+        load_slice<BN, kBFastK>(g.b, b_rows, k_begin + u * BK, k_end, t, fb[u]);
+      }
+    for (int kb0 = 0; kb0 < num_kb; kb0 += PREFETCH + 1) {
+#pragma unroll
+      for (int u = 0; u < PREFETCH + 1; u++) {
+        const int kb = kb0 + u;
+        if (kb < num_kb) {
+          constexpr int R = PREFETCH + 1;
+          const int nxt = kb + PREFETCH;
+          if (nxt < num_kb) {
+            load_slice<BM, kAFastK>(g.a, a_rows, k_begin + nxt * BK, k_end, t, fa[(u + PREFETCH) % R]);
+            load_slice<BN, kBFastK>(g.b, b_rows, k_begin + nxt * BK, k_end, t, fb[(u + PREFETCH) % R]);
+          }
+          const int s = kb % STAGES;
+          if (kb >= STAGES) mbar_wait(empty_bar(s), ((kb / STAGES) - 1) & 1);
+          const uint32_t a_addr = smem_base + s * S::STAGE_BYTES;
+          store_slice<BM, kAFastK>(fa[u], a_addr, t);
+          store_slice<BN, kBFastK>(fb[u], a_addr + A_STAGE_BYTES, t);
+          fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(s));
+        }
+      }
     }
   } else {
     // --------------------------------------------------------------- MMA issuer --
