@@ -10,9 +10,9 @@
 //
 // Both operand majors are supported without a transpose pass:
 //   K-major   matrix is [MN rows][K cols]  -> one box {32 k, rows} per stage
-//   MN-major  matrix is [K rows][MN cols]  -> MN/32 boxes {32 mn, 32 k} per stage;
-//             the UMMA descriptor uses the MN-major canonical layout
-//             ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, LBO = 4096, SBO = 1024
+//   MN-major  matrix is [K rows][MN cols]  -> MN/32 boxes {32 mn, 32 k} per stage,
+//             TMA swizzle 128B_ATOM_32B; the UMMA descriptor uses the MN-major
+//             SWIZZLE_128B_BASE32B canonical layout (4-k-row atoms, LBO = 4096, SBO = 512)
 // so  fprop  Y = X W^T      is (A K-major,  B K-major)
 //     dgrad  dX = dY W      is (A K-major,  B MN-major)
 //     wgrad  dW = dY^T X    is (A MN-major, B MN-major)
@@ -115,15 +115,17 @@ __device__ __forceinline__ uint64_t desc_k_major(uint32_t addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// MN-major SWIZZLE_128B: atoms of 8 k-rows x 128 bytes (32 mn); MN atoms LBO apart,
-// 8-k groups SBO apart.
+// MN-major, 32-bit elements: the only layout the tensor core transposes is
+// SWIZZLE_128B_BASE32B (layout type 1; 32-byte chunks XOR-ed with the row index mod 4,
+// TMA's SWIZZLE_128B_ATOM_32B): atoms of 4 k-rows x 128 bytes (32 mn); MN atoms LBO
+// apart, 4-k groups SBO = 512 bytes apart (one MMA = 8 k = two groups).
 __device__ __forceinline__ uint64_t desc_mn_major(uint32_t addr) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)(ATOM_BYTES >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 
@@ -365,7 +367,7 @@ inline bool matrix_tma_ok(const Matrix &m) {
 }
 
 // 2-D tensor map over `m` with a {32 cols, box_rows} box, 128-byte swizzle.
-inline bool encode_2d(CUtensorMap *map, const Matrix &m, int box_rows) {
+inline bool encode_2d(CUtensorMap *map, const Matrix &m, int box_rows, bool mn_major) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)m.cols, (cuuint64_t)m.rows};
@@ -373,7 +375,8 @@ inline bool encode_2d(CUtensorMap *map, const Matrix &m, int box_rows) {
   cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, (CUtensorMapDataType)tma_data_type(), 2, const_cast<float *>(m.base), gdim, gstr, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -423,8 +426,8 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
   if (M <= 0 || N <= 0 || K <= 0) return false;
   if (!matrix_tma_ok(a) || !matrix_tma_ok(b)) return false;
   CUtensorMap ma, mb;
-  if (!encode_2d(&ma, a, kAMn ? BK : BM)) return false;
-  if (!encode_2d(&mb, b, kBMn ? BK : 128)) return false;
+  if (!encode_2d(&ma, a, kAMn ? BK : BM, kAMn)) return false;
+  if (!encode_2d(&mb, b, kBMn ? BK : 128, kBMn)) return false;
   Params p;
   p.M = M; p.N = N; p.K = K;
   p.out = out; p.ldo = ldo; p.bias_n = epi.bias_n; p.workspace = nullptr;

@@ -18,8 +18,69 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 namespace kcnn {
+
+namespace tma {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library links
+// the static CUDA runtime only, libcuda.so is whatever the process already has.
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      fprintf(stderr, "kaldi-cnn_b200: cuTensorMapEncodeTiled unavailable; TMA GEMMs disabled\n");
+  }
+  return fn;
+}
+
+// TFLOAT32: the TMA unit converts FP32 -> TF32 while it copies, so the tensor core sees
+// rounded operands like the software producer's cvt.rna (KCNN_TMA_DTYPE=f32 copies raw bits,
+// which the tensor core truncates).
+int tma_data_type() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_TMA_DTYPE");
+    v = (e && e[0] == 'f') ? (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (int)CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  }
+  return v;
+}
+
+static bool enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_TMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Grow-only scratch for split-K partials.  Grown with cudaMalloc, so the first call of a
+// shape must happen outside stream capture (warm-up steps do that).
+float *splitk_workspace(size_t bytes) {
+  static float *buf = nullptr;
+  static size_t cap = 0;
+  if (bytes > cap) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(g_legacy_stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return nullptr;
+    if (buf) { cudaDeviceSynchronize(); cudaFree(buf); }
+    size_t want = bytes + bytes / 4;
+    if (cudaMalloc(&buf, want) != cudaSuccess) { buf = nullptr; cap = 0; return nullptr; }
+    cap = want;
+  }
+  return buf;
+}
+
+}  // namespace tma
 
 using Op33 = Operand<Dec3, Dec3>;
 using Op3I = Operand<Dec3, Dec3Inner>;
@@ -266,6 +327,12 @@ void cudaF_affine_fprop(cudaStream_t st, int math, const float *in, MatrixDim id
   if (M == 0 || N == 0) return;
   check_int32(id, "affine input"); check_int32(od, "affine output"); check_int32(wd, "affine weights");
   // out = 1 bias^T + in W^T : A(m, k) = in[m, k], B(k, n) = W[n, k]
+  if (math == KCNN_MATH_TF32_TC && tma::enabled()) {
+    tma::Epilogue epi; epi.bias_n = bias;
+    if (tma::gemm<false, false>(st, tma::Matrix{in, M, K, id.stride}, tma::Matrix{w, N, K, wd.stride}, M, N, K,
+                                out, od.stride, epi, true))
+      return;
+  }
   Op33 a = make_op(in, make_linear(M, id.stride), make_linear(K, 1), 1, 1);
   Op33 b = make_op(w, make_linear(N, wd.stride), make_linear(K, 1), 1, 1);
   Out33 o = make_out(out, make_linear(M, od.stride), make_linear(N, 1), bias);
@@ -278,6 +345,12 @@ void cudaF_affine_dgrad(cudaStream_t st, int math, const float *out_deriv, Matri
   if (M == 0 || N == 0) return;
   check_int32(odd, "affine out_deriv"); check_int32(idd, "affine in_deriv");
   // in_deriv = out_deriv W : A(m, k) = dY[m, k], B(k, n) = W[k, n]
+  if (math == KCNN_MATH_TF32_TC && tma::enabled()) {
+    tma::Epilogue epi;
+    if (tma::gemm<false, true>(st, tma::Matrix{out_deriv, M, K, odd.stride}, tma::Matrix{w, K, N, wd.stride}, M, N, K,
+                               in_deriv, idd.stride, epi, true))
+      return;
+  }
   Op33 a = make_op(out_deriv, make_linear(M, odd.stride), make_linear(K, 1), 1, 1);
   Op33 b = make_op(w, make_linear(N, 1), make_linear(K, wd.stride), 1, 1);
   Out33 o = make_out(in_deriv, make_linear(M, idd.stride), make_linear(N, 1), nullptr);
@@ -292,6 +365,12 @@ void cudaF_affine_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   check_int32(ivd, "affine in_value"); check_int32(odd, "affine out_deriv");
   if (bias_grad) launch_colsum(st, out_deriv, odd.rows, odd.stride, M, 1, bias_grad);
   // w_grad = out_deriv^T in_value : A(m, k) = dY[k, m], B(k, n) = X[k, n]
+  if (math == KCNN_MATH_TF32_TC && tma::enabled()) {
+    tma::Epilogue epi;
+    if (tma::gemm<true, true>(st, tma::Matrix{out_deriv, K, M, odd.stride}, tma::Matrix{in_value, K, N, ivd.stride},
+                              M, N, K, w_grad, wgd.stride, epi, true))
+      return;
+  }
   Op33 a = make_op(out_deriv, make_linear(M, 1), make_linear(K, odd.stride), 1, 1);
   Op33 b = make_op(in_value, make_linear(N, 1), make_linear(K, ivd.stride), 1, 1);
   Out33 o = make_out(w_grad, make_linear(M, wgd.stride), make_linear(N, 1), nullptr);

@@ -16,21 +16,34 @@ def rel(got, ref):
     return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
 
 
-def affine(N, din, dout, math):
+def pitched(a):
+    """CuMatrix-like device copy: row pitch rounded up to 4 floats (16 bytes)."""
+    r, c = a.shape
+    ld = (c + 3) // 4 * 4
+    buf = torch.full((r, ld), float("nan"), device="cuda")
+    v = buf[:, :c]
+    v.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+    return v
+
+
+def affine(N, din, dout, math, relu=False):
     x = rng.standard_normal((N, din)).astype(np.float32)
+    if relu:
+        x = np.maximum(x, 0)
     w = (rng.standard_normal((dout, din)) * 0.05).astype(np.float32)
     b = rng.standard_normal(dout).astype(np.float32)
     dy = rng.standard_normal((N, dout)).astype(np.float32)
-    xd, wd, bd, dyd = (torch.from_numpy(a).cuda() for a in (x, w, b, dy))
-    y = torch.full((N, dout), float("nan"), device="cuda")
+    xd, wd, dyd = (pitched(a) for a in (x, w, dy))
+    bd = torch.from_numpy(b).cuda()
+    y = pitched(np.full((N, dout), np.nan, dtype=np.float32))
     L.cudaF_affine_fprop(stream(), math, ptr(xd), mdim(xd), ptr(wd), mdim(wd), ptr(bd), ptr(y), mdim(y))
     torch.cuda.synchronize()
     e1 = rel(y.cpu().numpy(), x.astype(np.float64) @ w.T.astype(np.float64) + b)
-    dx = torch.full((N, din), float("nan"), device="cuda")
+    dx = pitched(np.full((N, din), np.nan, dtype=np.float32))
     L.cudaF_affine_dgrad(stream(), math, ptr(dyd), mdim(dyd), ptr(wd), mdim(wd), ptr(dx), mdim(dx))
     torch.cuda.synchronize()
     e2 = rel(dx.cpu().numpy(), dy.astype(np.float64) @ w.astype(np.float64))
-    g = torch.full((dout, din), float("nan"), device="cuda")
+    g = pitched(np.full((dout, din), np.nan, dtype=np.float32))
     bg = torch.full((dout,), float("nan"), device="cuda")
     L.cudaF_affine_wgrad(stream(), math, ptr(xd), mdim(xd), ptr(dyd), mdim(dyd), ptr(g), mdim(g), ptr(bg))
     torch.cuda.synchronize()
@@ -39,8 +52,10 @@ def affine(N, din, dout, math):
 
 
 if "--ncu" not in sys.argv and "--perf" not in sys.argv:
-    for shape in [(128, 32, 128), (128, 64, 128), (256, 256, 1024), (33, 70, 130), (1, 1, 1), (512, 1024, 4096)]:
+    for shape in [(128, 32, 128), (128, 64, 128), (256, 256, 1024), (33, 70, 130), (1, 1, 1), (512, 1024, 4096),
+                  (512, 4096, 3454), (100, 1056, 1024), (37, 8, 4), (512, 4096, 4096)]:
         affine(*shape, 1)
+    affine(512, 4096, 4096, 1, relu=True)
     affine(256, 256, 1024, 0)
 
 
@@ -61,7 +76,7 @@ def perf(N=512):
     for math in (1,):
         for (din, dout) in ((1024, 4096), (4096, 4096), (4096, 3454)):
             x = torch.randn(N, din, device="cuda"); w = torch.randn(dout, din, device="cuda") * 0.01
-            b = torch.zeros(dout, device="cuda"); y = torch.empty(N, dout, device="cuda")
+            b = torch.zeros(dout, device="cuda"); y = pitched(np.zeros((N, dout), dtype=np.float32))
             g = torch.empty(dout, din, device="cuda"); bg = torch.empty(dout, device="cuda")
             fl = 2.0 * N * din * dout
             t1 = timeit(lambda: L.cudaF_affine_fprop(stream(), math, ptr(x), mdim(x), ptr(w), mdim(w), ptr(b), ptr(y), mdim(y)))
