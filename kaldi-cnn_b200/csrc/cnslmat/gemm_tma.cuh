@@ -1,32 +1,41 @@
 // kaldi-cnn_b200/csrc/cnslmat/gemm_tma.cuh
 //
-// TMA-fed TF32 GEMM on tcgen05 / TMEM for operands that ARE plain pitched row-major
-// matrices: the three GEMMs of the affine layer (nnet2/nnet-component.cc:1216-1258,
-// nnet0/nnet-component-nnet0.cc:1133-1143) and, through the channels-last staging of
-// conv_tma.cuh, the convolutions.  Unlike gemm_tc.cuh no thread ever touches an
-// operand element: one lane issues cp.async.bulk.tensor (TMA) boxes that land in
-// shared memory already in the SWIZZLE_128B layout the UMMA descriptors describe,
-// one lane issues tcgen05.mma, four warps drain the accumulator.
+// TMA-fed TF32 GEMM pipeline on tcgen05 / TMEM, and the "problems" that ride on it.
+// Unlike gemm_tc.cuh no thread ever touches an operand element: one lane issues
+// cp.async.bulk.tensor (TMA) boxes that land in shared memory already in the swizzled
+// layout the UMMA descriptors describe, one lane issues tcgen05.mma, four warps drain
+// the accumulator through a padded shared-memory staging tile into coalesced stores.
 //
-// Both operand majors are supported without a transpose pass:
-//   K-major   matrix is [MN rows][K cols]  -> one box {32 k, rows} per stage
-//   MN-major  matrix is [K rows][MN cols]  -> MN/32 boxes {32 mn, 32 k} per stage,
-//             TMA swizzle 128B_ATOM_32B; the UMMA descriptor uses the MN-major
-//             SWIZZLE_128B_BASE32B canonical layout (4-k-row atoms, LBO = 4096, SBO = 512)
-// so  fprop  Y = X W^T      is (A K-major,  B K-major)
-//     dgrad  dX = dY W      is (A K-major,  B MN-major)
-//     wgrad  dW = dY^T X    is (A MN-major, B MN-major)
+// Tensor maps are encoded with data type TFLOAT32: the TMA unit rounds FP32 to TF32
+// while it copies (measured: 3e-4 max-norm error against FP64 vs 7.5e-4 when the raw
+// FP32 bits are truncated by the tensor core), so no rounding pass is needed.
 //
-// CTA = 128 x BN tile (BN = 128), 6 warps, 2 CTAs per SM (3 x 32 KB stages each) so
-// one CTA's epilogue overlaps the other's main loop:
-//   warp 0   TMA producer (one lane), full/empty mbarrier ring
-//   warp 1   TMEM allocator + MMA issuer (one lane), tcgen05.commit frees the stages
-//   warps 2-5 epilogue: tcgen05.ld 32x32b -> padded smem staging (the idle stages) ->
-//            512-byte coalesced row segments to HBM, with bias, split-K partials, or
-//            the fused momentum / weight-decay SGD update (wgrad of the FC layer).
-// K / M / N tails are zero-filled by TMA (out-of-bounds box elements), never read.
+// Operand majors, both straight from row-major matrices (no transpose pass):
+//   K-major   [MN rows][K cols]  one box {32 k, rows}, SWIZZLE_128B
+//   MN-major  [K rows][MN cols]  MN/32 boxes {32 mn, 32 k}, TMA SWIZZLE_128B_ATOM_32B;
+//             the only layout the tensor core transposes for 32-bit elements is
+//             SWIZZLE_128B_BASE32B (4-k-row atoms): LBO = 4096 (next MN atom),
+//             SBO = 512 (next 4 k rows)
 //
-// Eligibility (host side): 16-byte aligned base and row pitch for every operand
+// Pipeline (one kernel template, parameterised by a Problem):
+//   CTA = 128 x 128 output tile, 6 warps, 2 CTAs per SM (3 x 32 KB stages each) so one
+//   CTA's epilogue overlaps the other's main loop
+//   warp 0    TMA producer (one lane), full / empty mbarrier ring
+//   warp 1    TMEM allocator + MMA issuer (one lane), tcgen05.commit frees the stages
+//   warps 2-5 epilogue: tcgen05.ld 32x32b -> staging [128][132] (the idle stages) ->
+//             Problem::store (row segments, transposed [map][pos] runs, split-K partials,
+//             or the fused momentum / weight-decay SGD update)
+// M / N / K tails and the zero padding of the convolutions are TMA out-of-bounds
+// zero fill, never memory traffic.
+//
+// Problems:
+//   DenseProb    the three GEMMs of the affine layer (nnet2/nnet-component.cc:1216-1258,
+//                nnet0/nnet-component-nnet0.cc:1133-1143)
+//   ConvRowsProb convolution forward and input-gradient over a channels-last staging
+//                copy (conv_tma.cuh)
+//   ConvWgradProb convolution weight-gradient (conv_tma.cuh)
+//
+// Eligibility (host side): 16-byte aligned base and pitches for every operand
 // (cuTensorMapEncodeTiled); anything else takes the software-producer kernel.
 
 #ifndef KCNN_GEMM_TMA_CUH_
@@ -48,42 +57,18 @@ using tc::tmem_ld32;
 using tc::umma_commit;
 using tc::umma_tf32;
 
-constexpr int BM = 128, BK = 32;
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 4;
+constexpr int B_STAGE_BYTES = BN * BK * 4;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ATOM_BYTES = BK * 128;          // one MN-major box: 32 k-rows x 128 bytes
-
-template <int BN, int STAGES>
-struct Smem {
-  static constexpr int B_STAGE_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGING_PITCH = BN + 4;                    // floats; conflict-free v4 stores
-  static constexpr int STAGING_BYTES = 128 * STAGING_PITCH * 4;
-  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int DATA_BYTES = RING_BYTES > STAGING_BYTES ? RING_BYTES : STAGING_BYTES;
-  static constexpr int BAR_OFFSET = DATA_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
-};
-
-// What the epilogue does with the accumulator tile.
-enum EpiMode {
-  EPI_STORE = 0,      // out = acc (+ bias_n)
-  EPI_PARTIAL = 1,    // workspace[z] = acc           (split-K)
-  EPI_SGD = 2,        // prev = m prev - lr wd W + lr acc ; W += prev   (out = W, aux = prev)
-};
-
-struct Params {
-  int M, N, K;
-  int k_chunk;             // K range per blockIdx.z (multiple of BK)
-  float *out;              // row-major [M][ldo]
-  int ldo;
-  const float *bias_n;     // per column, or nullptr
-  float *workspace;        // [splits][M][N] partials
-  float *aux;              // EPI_SGD: prev_grad, same shape / pitch as out
-  float *grad_out;         // EPI_SGD: optional copy of the raw gradient (nullptr = none)
-  int ldg;
-  float lr, lr_wd, momentum;
-};
+constexpr int PITCH = BN + 4;                 // staging row pitch (floats): conflict-free v4 stores
+constexpr int STAGING_BYTES = 128 * PITCH * 4;
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+constexpr int DATA_BYTES = RING_BYTES > STAGING_BYTES ? RING_BYTES : STAGING_BYTES;
+constexpr int BAR_OFFSET = DATA_BYTES;
+constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -115,10 +100,8 @@ __device__ __forceinline__ uint64_t desc_k_major(uint32_t addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// MN-major, 32-bit elements: the only layout the tensor core transposes is
-// SWIZZLE_128B_BASE32B (layout type 1; 32-byte chunks XOR-ed with the row index mod 4,
-// TMA's SWIZZLE_128B_ATOM_32B): atoms of 4 k-rows x 128 bytes (32 mn); MN atoms LBO
-// apart, 4-k groups SBO = 512 bytes apart (one MMA = 8 k = two groups).
+// MN-major SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 k-rows x 128 bytes (32 mn);
+// MN atoms LBO apart, 4-k groups SBO = 512 bytes apart (one MMA = 8 k = two groups).
 __device__ __forceinline__ uint64_t desc_mn_major(uint32_t addr) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
@@ -134,25 +117,29 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN, int STAGES, bool kAMn, bool kBMn, int kEpi>
+// Problem interface:
+//   static constexpr bool kAMn, kBMn
+//   void kb_range(int &begin, int &end) const          K-blocks of this CTA
+//   uint32_t tx_bytes() const                           bytes one stage's TMA boxes deliver
+//   void load(kb, a_addr, b_addr, bar, &map_a, &map_b)  issue the boxes of K-block kb
+//   void store(const float *stage, int tid) const       128 epilogue threads, stage[128][PITCH]
+template <class Prob>
 __global__ void __launch_bounds__(THREADS, 2)
-gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const Params p) {
-  using S = Smem<BN, STAGES>;
+tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const Prob prob) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + S::BAR_OFFSET;
+  const uint32_t bar_base = smem_base + BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8 * s; };
   auto empty_bar = [&](int s) { return bar_base + 8 * (STAGES + s); };
   const uint32_t accum_bar = bar_base + 8 * (2 * STAGES);
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem_gen + S::BAR_OFFSET + 8 * (2 * STAGES + 1));
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem_gen + BAR_OFFSET + 8 * (2 * STAGES + 1));
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int k_begin = blockIdx.z * p.k_chunk;
-  const int k_end = min(p.K, k_begin + p.k_chunk);
-  const int num_kb = (k_end - k_begin + BK - 1) / BK;
+  int kb_begin, kb_end;
+  prob.kb_range(kb_begin, kb_end);
+  const int num_kb = kb_end - kb_begin;
 
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -178,47 +165,35 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer --
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(empty_bar(s), ((kb / STAGES) - 1) & 1);
-        const uint32_t a_addr = smem_base + s * S::STAGE_BYTES;
-        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-        const int k0 = k_begin + kb * BK;
-        mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
-        if (kAMn) {
-#pragma unroll
-          for (int i = 0; i < BM / 32; i++) tma_load_2d(a_addr + i * ATOM_BYTES, &map_a, m0 + 32 * i, k0, full_bar(s));
-        } else {
-          tma_load_2d(a_addr, &map_a, k0, m0, full_bar(s));
-        }
-        if (kBMn) {
-#pragma unroll
-          for (int i = 0; i < BN / 32; i++) tma_load_2d(b_addr + i * ATOM_BYTES, &map_b, n0 + 32 * i, k0, full_bar(s));
-        } else {
-          tma_load_2d(b_addr, &map_b, k0, n0, full_bar(s));
-        }
+      const uint32_t tx = prob.tx_bytes();
+      for (int i = 0; i < num_kb; i++) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait(empty_bar(s), ((i / STAGES) - 1) & 1);
+        const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), tx);
+        prob.load(kb_begin + i, a_addr, a_addr + A_STAGE_BYTES, full_bar(s), &map_a, &map_b);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer --
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, kAMn, kBMn);
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        mbar_wait(full_bar(s), (kb / STAGES) & 1);
+      constexpr uint32_t idesc = make_idesc(BM, BN, Prob::kAMn, Prob::kBMn);
+      for (int i = 0; i < num_kb; i++) {
+        const int s = i % STAGES;
+        mbar_wait(full_bar(s), (i / STAGES) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * S::STAGE_BYTES;
+        const uint32_t a_addr = smem_base + s * STAGE_BYTES;
         const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-        const uint64_t adesc = kAMn ? desc_mn_major(a_addr) : desc_k_major(a_addr);
-        const uint64_t bdesc = kBMn ? desc_mn_major(b_addr) : desc_k_major(b_addr);
+        const uint64_t adesc = Prob::kAMn ? desc_mn_major(a_addr) : desc_k_major(a_addr);
+        const uint64_t bdesc = Prob::kBMn ? desc_mn_major(b_addr) : desc_k_major(b_addr);
 #pragma unroll
         for (int k = 0; k < BK / 8; k++) {
-          // one MMA = 8 TF32 of K: +32 bytes along a K-major row, +1024 bytes (one 8-row
-          // group) in an MN-major atom; start-address field is in 16-byte units
-          const uint64_t ad = adesc + (kAMn ? 64 * k : 2 * k);
-          const uint64_t bd = bdesc + (kBMn ? 64 * k : 2 * k);
-          umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          // one MMA = 8 TF32 of K: +32 bytes along a K-major row, +1024 bytes (two 4-row
+          // groups) in an MN-major atom; the start-address field is in 16-byte units
+          const uint64_t ad = adesc + (Prob::kAMn ? 64 * k : 2 * k);
+          const uint64_t bd = bdesc + (Prob::kBMn ? 64 * k : 2 * k);
+          umma_tf32(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));
       }
@@ -228,12 +203,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else {
     // ----------------------------------------------------------------- epilogue --
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-    float *stage = reinterpret_cast<float *>(smem_gen) + q * 32 * S::STAGING_PITCH;
+    float *stage = reinterpret_cast<float *>(smem_gen);
     if (num_kb > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
-    // TMEM -> registers -> padded staging: lane = row, 32 columns per tcgen05.ld
+    // TMEM -> registers -> padded staging: lane = tile row, 32 columns per tcgen05.ld
 #pragma unroll 1
     for (int j0 = 0; j0 < BN; j0 += 32) {
       uint32_t v[32];
@@ -243,78 +218,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = 0u;
       }
-      float *dst = stage + lane * S::STAGING_PITCH + j0;
+      float *dst = stage + (q * 32 + lane) * PITCH + j0;
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    __syncwarp();
-    // staging -> HBM: one 512-byte row segment per warp instruction (lane = 4 columns)
-    static_assert(BN == 128, "epilogue readback assumes 128 columns = 32 lanes x float4");
-    const int n = n0 + 4 * lane;
-    const bool n_full = n + 3 < p.N;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (kEpi == EPI_STORE && p.bias_n) {
-      if (n < p.N) bias4.x = __ldg(p.bias_n + n);
-      if (n + 1 < p.N) bias4.y = __ldg(p.bias_n + n + 1);
-      if (n + 2 < p.N) bias4.z = __ldg(p.bias_n + n + 2);
-      if (n + 3 < p.N) bias4.w = __ldg(p.bias_n + n + 3);
-    }
-    float *obase;
-    int ld;
-    if (kEpi == EPI_PARTIAL) {
-      obase = p.workspace + (size_t)blockIdx.z * p.M * p.N;
-      ld = p.N;
-    } else {
-      obase = p.out;
-      ld = p.ldo;
-    }
-    const bool vec_ok = n_full && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15u) == 0);
-#pragma unroll 4
-    for (int r = 0; r < 32; r++) {
-      const int m = m0 + q * 32 + r;
-      if (m >= p.M) break;
-      float4 a = *reinterpret_cast<const float4 *>(stage + r * S::STAGING_PITCH + 4 * lane);
-      float *orow = obase + (size_t)m * ld + n;
-      if (kEpi == EPI_SGD) {
-        // nnet0/nnet-component-nnet0.cc:1138-1142: prev = m prev - lr wd W + lr grad ; W += prev
-        float *prow = p.aux + (size_t)m * ld + n;
-        if (vec_ok) {
-          float4 w = *reinterpret_cast<const float4 *>(orow);
-          float4 pv = *reinterpret_cast<const float4 *>(prow);
-          if (p.grad_out && ((p.ldg & 3) == 0))
-            *reinterpret_cast<float4 *>(p.grad_out + (size_t)m * p.ldg + n) = a;
-          pv.x = p.momentum * pv.x - p.lr_wd * w.x + p.lr * a.x;
-          pv.y = p.momentum * pv.y - p.lr_wd * w.y + p.lr * a.y;
-          pv.z = p.momentum * pv.z - p.lr_wd * w.z + p.lr * a.z;
-          pv.w = p.momentum * pv.w - p.lr_wd * w.w + p.lr * a.w;
-          w.x += pv.x; w.y += pv.y; w.z += pv.z; w.w += pv.w;
-          *reinterpret_cast<float4 *>(prow) = pv;
-          *reinterpret_cast<float4 *>(orow) = w;
-        } else {
-          const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (n + j < p.N) {
-              float w = orow[j];
-              float pv = p.momentum * prow[j] - p.lr_wd * w + p.lr * av[j];
-              prow[j] = pv;
-              orow[j] = w + pv;
-              if (p.grad_out) p.grad_out[(size_t)m * p.ldg + n + j] = av[j];
-            }
-        }
-      } else {
-        a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-        if (vec_ok) {
-          *reinterpret_cast<float4 *>(orow) = a;
-        } else {
-          if (n < p.N) orow[0] = a.x;
-          if (n + 1 < p.N) orow[1] = a.y;
-          if (n + 2 < p.N) orow[2] = a.z;
-          if (n + 3 < p.N) orow[3] = a.w;
-        }
-      }
-    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    prob.store(stage, t - 64);
   }
 
   tc_fence_before();
@@ -326,11 +236,140 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-// out[m][n] = sum_z ws[z][m][n] (+ bias_n[n])
+// ------------------------------------------------------------------ DenseProb --
+
+// What the epilogue does with the accumulator tile.
+enum EpiMode {
+  EPI_STORE = 0,      // out = acc (+ bias_n)
+  EPI_PARTIAL = 1,    // workspace[z] = acc           (split-K)
+  EPI_SGD = 2,        // prev = m prev - lr wd W + lr acc ; W += prev   (out = W, aux = prev)
+};
+
+struct SgdCoef {
+  float lr, lr_wd, momentum;
+};
+
+// Row-major 128-column segment store shared by the dense and the weight-gradient
+// problems: tid -> (row group, 4 columns); each warp instruction writes one 512-byte
+// row segment.  row_of(m) maps a tile row to the output row.
+template <int kEpi, class RowMap>
+__device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, int n0, int M, int N,
+                                           float *obase, int ld, const float *bias_n, float *aux,
+                                           const SgdCoef &sgd, RowMap row_of) {
+  const int wl = tid >> 5, lane = tid & 31;
+  const int n = n0 + 4 * lane;
+  const bool vec_ok = (n + 3 < N) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15u) == 0);
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kEpi == EPI_STORE && bias_n) {
+    if (n < N) bias4.x = __ldg(bias_n + n);
+    if (n + 1 < N) bias4.y = __ldg(bias_n + n + 1);
+    if (n + 2 < N) bias4.z = __ldg(bias_n + n + 2);
+    if (n + 3 < N) bias4.w = __ldg(bias_n + n + 3);
+  }
+#pragma unroll 4
+  for (int r = 0; r < 32; r++) {
+    const int mt = wl * 32 + r;
+    if (m0 + mt >= M) break;
+    float4 a = *reinterpret_cast<const float4 *>(stage + mt * PITCH + 4 * lane);
+    const size_t roff = (size_t)row_of(m0 + mt) * ld + n;
+    float *orow = obase + roff;
+    if (kEpi == EPI_SGD) {
+      // nnet0/nnet-component-nnet0.cc:767-773, 1138-1142:
+      //   prev = momentum prev - lr wd W + lr grad ;  W += prev
+      float *prow = aux + roff;
+      if (vec_ok) {
+        float4 w = *reinterpret_cast<const float4 *>(orow);
+        float4 pv = *reinterpret_cast<const float4 *>(prow);
+        pv.x = sgd.momentum * pv.x; pv.x += -sgd.lr_wd * w.x; pv.x += sgd.lr * a.x;
+        pv.y = sgd.momentum * pv.y; pv.y += -sgd.lr_wd * w.y; pv.y += sgd.lr * a.y;
+        pv.z = sgd.momentum * pv.z; pv.z += -sgd.lr_wd * w.z; pv.z += sgd.lr * a.z;
+        pv.w = sgd.momentum * pv.w; pv.w += -sgd.lr_wd * w.w; pv.w += sgd.lr * a.w;
+        w.x += pv.x; w.y += pv.y; w.z += pv.z; w.w += pv.w;
+        *reinterpret_cast<float4 *>(prow) = pv;
+        *reinterpret_cast<float4 *>(orow) = w;
+      } else {
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (n + j < N) {
+            float w = orow[j];
+            float pv = sgd.momentum * prow[j];
+            pv += -sgd.lr_wd * w;
+            pv += sgd.lr * av[j];
+            prow[j] = pv;
+            orow[j] = w + pv;
+          }
+      }
+    } else {
+      a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+      if (vec_ok) {
+        *reinterpret_cast<float4 *>(orow) = a;
+      } else {
+        if (n < N) orow[0] = a.x;
+        if (n + 1 < N) orow[1] = a.y;
+        if (n + 2 < N) orow[2] = a.z;
+        if (n + 3 < N) orow[3] = a.w;
+      }
+    }
+  }
+}
+
+struct IdentityRow {
+  __device__ __forceinline__ int operator()(int m) const { return m; }
+};
+
+template <bool kAMn_, bool kBMn_, int kEpi>
+struct DenseProb {
+  static constexpr bool kAMn = kAMn_, kBMn = kBMn_;
+  int M, N, K;
+  int kb_per_split;
+  float *out;              // row-major [M][ldo]
+  int ldo;
+  const float *bias_n;     // per column, or nullptr
+  float *workspace;        // [splits][M][N] partials
+  float *aux;              // EPI_SGD: prev_grad, same shape / pitch as out
+  SgdCoef sgd;
+
+  __device__ __forceinline__ void kb_range(int &b, int &e) const {
+    const int total = (K + BK - 1) / BK;
+    b = blockIdx.z * kb_per_split;
+    e = min(total, b + kb_per_split);
+    if (e < b) e = b;
+  }
+  __device__ __forceinline__ uint32_t tx_bytes() const { return STAGE_BYTES; }
+  __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
+                                       const CUtensorMap *ma, const CUtensorMap *mb) const {
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, k0 = kb * BK;
+    if (kAMn) {
+#pragma unroll
+      for (int i = 0; i < BM / 32; i++) tma_load_2d(a_addr + i * ATOM_BYTES, ma, m0 + 32 * i, k0, bar);
+    } else {
+      tma_load_2d(a_addr, ma, k0, m0, bar);
+    }
+    if (kBMn) {
+#pragma unroll
+      for (int i = 0; i < BN / 32; i++) tma_load_2d(b_addr + i * ATOM_BYTES, mb, n0 + 32 * i, k0, bar);
+    } else {
+      tma_load_2d(b_addr, mb, k0, n0, bar);
+    }
+  }
+  __device__ __forceinline__ void store(const float *stage, int tid) const {
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (kEpi == EPI_PARTIAL)
+      store_rows<EPI_STORE>(stage, tid, m0, n0, M, N, workspace + (size_t)blockIdx.z * M * N, N, nullptr,
+                            nullptr, sgd, IdentityRow());
+    else
+      store_rows<kEpi>(stage, tid, m0, n0, M, N, out, ldo, bias_n, aux, sgd, IdentityRow());
+  }
+};
+
+// out[row_of(m)][n] = sum_z ws[z][m][n] (+ bias_n[n]), or the SGD update with that sum as the
+// gradient.  N % 4 == 0, 16-byte aligned rows (checked by the launchers).
+template <int kEpi, class RowMap>
 __global__ void __launch_bounds__(256)
-splitk_reduce_rows_kernel(const float *__restrict__ ws, int splits, int M, int N, float *__restrict__ out,
-                          int ldo, const float *__restrict__ bias_n) {
-  const long long total4 = ((long long)M * N) >> 2;         // N % 4 == 0 is checked by the launcher
+splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, float *__restrict__ out, int ldo,
+                     const float *__restrict__ bias_n, float *__restrict__ aux, SgdCoef sgd, RowMap row_of) {
+  const long long total4 = ((long long)M * N) >> 2;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const long long e = i << 2;
@@ -340,10 +379,23 @@ splitk_reduce_rows_kernel(const float *__restrict__ ws, int splits, int M, int N
     float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (size_t)z * M * N + e));
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-  if (bias_n) {
-    s.x += __ldg(bias_n + n); s.y += __ldg(bias_n + n + 1); s.z += __ldg(bias_n + n + 2); s.w += __ldg(bias_n + n + 3);
+  const size_t off = (size_t)row_of(m) * ldo + n;
+  if (kEpi == EPI_SGD) {
+    float4 w = *reinterpret_cast<const float4 *>(out + off);
+    float4 pv = *reinterpret_cast<const float4 *>(aux + off);
+    pv.x = sgd.momentum * pv.x; pv.x += -sgd.lr_wd * w.x; pv.x += sgd.lr * s.x;
+    pv.y = sgd.momentum * pv.y; pv.y += -sgd.lr_wd * w.y; pv.y += sgd.lr * s.y;
+    pv.z = sgd.momentum * pv.z; pv.z += -sgd.lr_wd * w.z; pv.z += sgd.lr * s.z;
+    pv.w = sgd.momentum * pv.w; pv.w += -sgd.lr_wd * w.w; pv.w += sgd.lr * s.w;
+    w.x += pv.x; w.y += pv.y; w.z += pv.z; w.w += pv.w;
+    *reinterpret_cast<float4 *>(aux + off) = pv;
+    *reinterpret_cast<float4 *>(out + off) = w;
+  } else {
+    if (bias_n) {
+      s.x += __ldg(bias_n + n); s.y += __ldg(bias_n + n + 1); s.z += __ldg(bias_n + n + 2); s.w += __ldg(bias_n + n + 3);
+    }
+    *reinterpret_cast<float4 *>(out + off) = s;
   }
-  *reinterpret_cast<float4 *>(out + (size_t)m * ldo + n) = s;
 }
 
 // ------------------------------------------------------------------- host side --
@@ -355,6 +407,37 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 EncodeTiledFn encode_tiled_fn();         // kernels_gemm.cu (driver entry point, resolved once)
 int tma_data_type();                     // CU_TENSOR_MAP_DATA_TYPE_* used for the operands
+bool enabled();                          // KCNN_TMA=0 disables the TMA paths
+
+// Grow-only device scratch, one buffer per slot (kernels_gemm.cu).  Returns nullptr when it
+// would have to grow while the stream is being captured; callers then take another path.
+enum ScratchSlot { SCRATCH_SPLITK = 0, SCRATCH_XCL = 1, SCRATCH_DYCL = 2, SCRATCH_BIAS = 3, SCRATCH_SLOTS = 4 };
+float *scratch(int slot, size_t bytes);
+
+// Tensor map of rank 2 or 3 over FP32 data; dims[0] is the contiguous axis, strides_bytes[i]
+// is the pitch of dims[i + 1].  mn_major picks the 32-byte-atom swizzle.
+inline bool encode_map(CUtensorMap *map, const float *base, int rank, const unsigned long long *dims,
+                       const unsigned long long *strides_bytes, const unsigned *box, bool mn_major) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  if (!host_aligned16(base)) return false;
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; i++) {
+    if (dims[i] == 0 || box[i] == 0 || box[i] > 256) return false;
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; i++) {
+    if (strides_bytes[i] % 16 != 0 || strides_bytes[i] == 0) return false;
+    gstr[i] = strides_bytes[i];
+  }
+  CUresult r = fn(map, (CUtensorMapDataType)tma_data_type(), (cuuint32_t)rank, const_cast<float *>(base), gdim,
+                  gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 
 // A pitched row-major matrix as a GEMM operand.
 struct Matrix {
@@ -362,58 +445,40 @@ struct Matrix {
   int rows, cols, ld;
 };
 
-inline bool matrix_tma_ok(const Matrix &m) {
-  return host_aligned16(m.base) && (m.ld & 3) == 0 && m.rows > 0 && m.cols > 0;
-}
-
-// 2-D tensor map over `m` with a {32 cols, box_rows} box, 128-byte swizzle.
+// 2-D tensor map over `m` with a {32 cols, box_rows} box.
 inline bool encode_2d(CUtensorMap *map, const Matrix &m, int box_rows, bool mn_major) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)m.cols, (cuuint64_t)m.rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)m.ld * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, (CUtensorMapDataType)tma_data_type(), 2, const_cast<float *>(m.base), gdim, gstr, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  if (m.rows <= 0 || m.cols <= 0) return false;
+  unsigned long long dims[2] = {(unsigned long long)m.cols, (unsigned long long)m.rows};
+  unsigned long long str[1] = {(unsigned long long)m.ld * 4};
+  unsigned box[2] = {32, (unsigned)box_rows};
+  return encode_map(map, m.base, 2, dims, str, box, mn_major);
 }
 
 struct Epilogue {
   int mode = EPI_STORE;
   const float *bias_n = nullptr;
   float *aux = nullptr;          // EPI_SGD: prev_grad
-  float *grad_out = nullptr;
-  int ldg = 0;
-  float lr = 0.f, lr_wd = 0.f, momentum = 0.f;
+  SgdCoef sgd = {0.f, 0.f, 0.f};
 };
 
-float *splitk_workspace(size_t bytes);   // kernels_gemm.cu: grow-only device scratch
-
-inline int pick_splits(int M, int N, int K) {
-  long long tiles = (long long)((M + BM - 1) / BM) * ((N + 127) / 128);
+inline int pick_splits(long long tiles, int num_kb) {
   if (tiles >= 100) return 1;
   long long want = (2 * kNumSMs) / tiles;
-  long long max_by_k = K / (BK * 8);
+  long long max_by_k = num_kb / 8;            // at least 8 K-blocks per split
   if (want > max_by_k) want = max_by_k;
   if (want > 16) want = 16;
   return (int)(want < 1 ? 1 : want);
 }
 
-template <bool kAMn, bool kBMn, int kEpi>
-void launch_cfg(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Params &p, int splits) {
-  constexpr int BN = 128, STAGES = 3;
-  using S = Smem<BN, STAGES>;
-  auto kernel = gemm_tma_kernel<BN, STAGES, kAMn, kBMn, kEpi>;
-  static bool attr_set = false;
+template <class Prob>
+void launch_prob(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 grid) {
+  auto kernel = tma_gemm_kernel<Prob>;
+  static bool attr_set = false;          // one flag per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     attr_set = true;
   }
-  dim3 grid(ceil_div_u(p.M, BM), ceil_div_u(p.N, BN), splits);
-  kernel<<<grid, THREADS, S::TOTAL, st>>>(ma, mb, p);
+  kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(ma, mb, p);
   count_launch();
 }
 
@@ -424,34 +489,42 @@ template <bool kAMn, bool kBMn>
 bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K, float *out, int ldo,
           const Epilogue &epi, bool allow_split) {
   if (M <= 0 || N <= 0 || K <= 0) return false;
-  if (!matrix_tma_ok(a) || !matrix_tma_ok(b)) return false;
   CUtensorMap ma, mb;
   if (!encode_2d(&ma, a, kAMn ? BK : BM, kAMn)) return false;
-  if (!encode_2d(&mb, b, kBMn ? BK : 128, kBMn)) return false;
-  Params p;
-  p.M = M; p.N = N; p.K = K;
-  p.out = out; p.ldo = ldo; p.bias_n = epi.bias_n; p.workspace = nullptr;
-  p.aux = epi.aux; p.grad_out = epi.grad_out; p.ldg = epi.ldg;
-  p.lr = epi.lr; p.lr_wd = epi.lr_wd; p.momentum = epi.momentum;
+  if (!encode_2d(&mb, b, kBMn ? BK : BN, kBMn)) return false;
+  const int num_kb = (K + BK - 1) / BK;
+  const bool out_vec = (N & 3) == 0 && (ldo & 3) == 0 && host_aligned16(out);
   int splits = 1;
-  if (allow_split && epi.mode == EPI_STORE && (N & 3) == 0 && (ldo & 3) == 0 && host_aligned16(out))
-    splits = pick_splits(M, N, K);
-  int chunk = (K + splits - 1) / splits;
-  chunk = ((chunk + BK - 1) / BK) * BK;
-  splits = (K + chunk - 1) / chunk;
-  p.k_chunk = chunk;
+  if (allow_split && out_vec)
+    splits = pick_splits((long long)ceil_div_u(M, BM) * ceil_div_u(N, BN), num_kb);
+  int per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + per - 1) / per;
+  float *ws = nullptr;
   if (splits > 1) {
-    p.workspace = splitk_workspace((size_t)splits * M * N * sizeof(float));
-    if (!p.workspace) { splits = 1; p.k_chunk = ((K + BK - 1) / BK) * BK; }
+    ws = scratch(SCRATCH_SPLITK, (size_t)splits * M * N * sizeof(float));
+    if (!ws) { splits = 1; per = num_kb; }
   }
+  dim3 grid(ceil_div_u(M, BM), ceil_div_u(N, BN), splits);
+  auto fill = [&](auto &p) {
+    p.M = M; p.N = N; p.K = K; p.kb_per_split = per;
+    p.out = out; p.ldo = ldo; p.bias_n = epi.bias_n; p.workspace = ws; p.aux = epi.aux; p.sgd = epi.sgd;
+  };
   if (splits > 1) {
-    launch_cfg<kAMn, kBMn, EPI_PARTIAL>(st, ma, mb, p, splits);
-    KCNN_LAUNCH(splitk_reduce_rows_kernel, ceil_div_u(((long long)M * N) >> 2, 256), 256, 0, st, p.workspace,
-                splits, M, N, out, ldo, epi.bias_n);
+    DenseProb<kAMn, kBMn, EPI_PARTIAL> p; fill(p);
+    launch_prob(st, ma, mb, p, grid);
+    const unsigned blocks = ceil_div_u(((long long)M * N) >> 2, 256);
+    if (epi.mode == EPI_SGD)
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
+                  nullptr, epi.aux, epi.sgd, IdentityRow());
+    else
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
+                  epi.bias_n, nullptr, epi.sgd, IdentityRow());
   } else if (epi.mode == EPI_SGD) {
-    launch_cfg<kAMn, kBMn, EPI_SGD>(st, ma, mb, p, 1);
+    DenseProb<kAMn, kBMn, EPI_SGD> p; fill(p);
+    launch_prob(st, ma, mb, p, grid);
   } else {
-    launch_cfg<kAMn, kBMn, EPI_STORE>(st, ma, mb, p, 1);
+    DenseProb<kAMn, kBMn, EPI_STORE> p; fill(p);
+    launch_prob(st, ma, mb, p, grid);
   }
   return true;
 }

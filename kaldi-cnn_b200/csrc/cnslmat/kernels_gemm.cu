@@ -18,7 +18,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
-#include "gemm_tma.cuh"
+#include "conv_tma.cuh"
 
 namespace kcnn {
 
@@ -54,7 +54,7 @@ int tma_data_type() {
   return v;
 }
 
-static bool enabled() {
+bool enabled() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("KCNN_TMA");
@@ -63,21 +63,23 @@ static bool enabled() {
   return v == 1;
 }
 
-// Grow-only scratch for split-K partials.  Grown with cudaMalloc, so the first call of a
-// shape must happen outside stream capture (warm-up steps do that).
-float *splitk_workspace(size_t bytes) {
-  static float *buf = nullptr;
-  static size_t cap = 0;
-  if (bytes > cap) {
+// Grow-only device scratch, one buffer per slot.  Grown with cudaMalloc, so the first call
+// of a shape must happen outside stream capture (warm-up steps do that); outgrown buffers
+// are kept alive because CUDA graphs captured earlier still point at them.
+float *scratch(int slot, size_t bytes) {
+  static float *buf[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  static size_t cap[SCRATCH_SLOTS] = {0, 0, 0, 0};
+  if (bytes > cap[slot]) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(g_legacy_stream, &cs);
     if (cs != cudaStreamCaptureStatusNone) return nullptr;
-    if (buf) { cudaDeviceSynchronize(); cudaFree(buf); }
-    size_t want = bytes + bytes / 4;
-    if (cudaMalloc(&buf, want) != cudaSuccess) { buf = nullptr; cap = 0; return nullptr; }
-    cap = want;
+    size_t want = bytes > 2 * cap[slot] ? bytes : 2 * cap[slot];
+    float *p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    buf[slot] = p;
+    cap[slot] = want;
   }
-  return buf;
+  return buf[slot];
 }
 
 }  // namespace tma
@@ -214,6 +216,10 @@ void cudaF_conv2d_fprop(cudaStream_t st, int math, const float *in, MatrixDim id
   if (q.N == 0 || q.P <= 0 || G == 0) return;
   check_int32(id, "conv input"); check_int32(od, "conv output"); check_int32(kd, "conv kernel");
   const int M = q.N * q.P, K = q.ks * C;
+  if (math == KCNN_MATH_TF32_TC && concat && H == 1 && KH == 1 && ph == 0) {
+    tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
+    if (tma::conv_fprop(st, cs, in, id.stride, kernel, kd.stride, bias, out, od.stride)) return;
+  }
   // A(m = (n, ow, oh), k = (c, kw, kh)) = Xpad[n, c, ow + kw, oh + kh]
   Op33 a = make_op(in,
       make_dec3(q.N, q.OW, q.OH, id.stride, H, 1, -pw * H - ph, 1, 1, -pw, -ph),
@@ -242,6 +248,10 @@ void cudaF_conv2d_dgrad(cudaStream_t st, int math, const float *out_deriv, Matri
   ConvGeom q = conv_geom(odd.rows, H, W, C, ph, pw, KH, KW, G);
   if (q.N == 0 || C == 0) return;
   check_int32(odd, "conv out_deriv"); check_int32(idd, "conv in_deriv"); check_int32(kd, "conv kernel");
+  if (math == KCNN_MATH_TF32_TC && H == 1 && KH == 1 && ph == 0) {
+    tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
+    if (tma::conv_dgrad(st, cs, out_deriv, odd.stride, kernel, kd.stride, in_deriv, idd.stride)) return;
+  }
   if (q.OH == 1) {
     // Full-height kernel (every layer of egs/exp/nnet/nnet.config): out_deriv has one row
     // of positions, so kh is fixed by h (kh = h + ph) and moves from the reduction into the
@@ -297,6 +307,16 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   if (q.N == 0 || q.P <= 0 || G == 0 || C == 0) return;
   check_int32(ivd, "conv in_value"); check_int32(odd, "conv out_deriv");
   const int M = q.ks * C, K = q.N * q.P;
+  if (math == KCNN_MATH_TF32_TC && H == 1 && KH == 1 && ph == 0) {
+    tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
+    float *bpart = nullptr;
+    int brows = 0;
+    if (tma::conv_wgrad(st, cs, in_value, ivd.stride, out_deriv, odd.stride, kernel_grad, kgd.stride, nullptr,
+                        nullptr, bias_grad ? &bpart : nullptr, &brows)) {
+      if (bias_grad) launch_colsum(st, bpart, brows, G, G, 1, bias_grad);
+      return;
+    }
+  }
   if (bias_grad) launch_colsum(st, out_deriv, q.N, odd.stride, G, q.P, bias_grad);
   // A(m = (c, kw, kh), k = (n, ow, oh)) = Xpad[n, c, ow + kw, oh + kh]
   // (folds PaddingZero + TpBlock; row order (c, kw, kh) folds ModPermuteRow)

@@ -24,6 +24,8 @@ CONVS = [
     ("conv2", 64, 1, 18, 128, 0, 0, 1, 3, 128),
     ("conv4", 32, 1, 14, 256, 0, 0, 1, 3, 256),
     ("conv6", 64, 1, 4, 512, 0, 0, 1, 3, 512),
+    ("t_pad", 33, 1, 10, 64, 0, 1, 1, 3, 96),       # time-axis + zero padding, sample / map tile tails
+    ("t_wide", 20, 1, 18, 32, 0, 2, 1, 5, 160),
     ("pad2d", 9, 6, 7, 5, 1, 1, 3, 3, 10),
     ("padw", 7, 5, 9, 4, 0, 2, 5, 4, 6),
     ("ragged", 5, 3, 5, 7, 0, 0, 2, 2, 3),
