@@ -317,25 +317,20 @@ def run_ours(args):
     ncomp = net.num_components
     updatable = [c for c in range(ncomp) if L.kcnn_component_gradient_floats(net.component(c).h) > 0]
 
+    dp_step = None
+    if world > 1:
+        from kaldi_cnn_b200.dp import DataParallelStep
+        dp_step = DataParallelStep(net, arena, updatable, dist, world)
+
     def step():
-        net.forward(feats)
-        net.objf_and_deriv(labels)
         if world == 1:
+            net.forward(feats)
+            net.objf_and_deriv(labels)
             net.backward()
-            return
-        # data parallel: backward top-down, all-reduce each layer's gradient bucket as soon as
-        # its Backprop has been issued (overlaps the rest of the backward), then apply.
-        works, hi = [], ncomp - 1
-        for c in reversed(updatable):
-            net.backward(hi, c)
-            off, ln = net.gradient_bucket(c)
-            works.append(dist.all_reduce(arena[off:off + ln], async_op=True))
-            hi = c - 1
-        if hi >= 0:
-            net.backward(hi, 0)
-        for w in works:
-            w.wait()
-        net.apply_gradients(N * world)
+        else:
+            # data parallel: backward top-down, all-reduce each layer's gradient bucket as soon as
+            # its Backprop has been issued (overlaps the rest of the backward), then apply.
+            dp_step(feats, labels, N * world)
 
     with torch.cuda.stream(stream):
         kc.use_current_stream()

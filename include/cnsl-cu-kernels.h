@@ -248,6 +248,34 @@ void cudaF_affine_wgrad(cudaStream_t st, int math, const float *in_value,
                         MatrixDim out_deriv_dim, float *w_grad, MatrixDim w_grad_dim,
                         float *bias_grad);
 
+/* Fused backward of one layer in the single-GPU (apply-immediately) case and for the
+ * data-parallel (gradient-only) case.  Both return 1 when the fused TMA / tcgen05 path
+ * ran and 0 when the shape or alignment is not eligible -- the caller then uses the
+ * separate dgrad / wgrad / update entry points above (same results).
+ *
+ * cudaF_conv2d_backward: ConvolutionComponent::Backprop + Update
+ * (nnet0/nnet-component-nnet0.cc:461-544, 738-777) from one channels-last staging copy
+ * of out_deriv and one of in_value: in_deriv (skipped when NULL), then
+ *   apply != 0:  prev = momentum*prev + a_decay*K + a_grad*dK ; K += prev ;
+ *                bias += a_grad * db       (kernel_grad / bias_grad unused)
+ *   apply == 0:  kernel_grad = dK ; bias_grad = db
+ * cudaF_affine_wgrad_sgd: FullyConnectedComponent::UpdateSimple (:1133-1143) with the
+ * update applied in the weight-gradient GEMM's epilogue; the gradient is never stored. */
+int cudaF_conv2d_backward(cudaStream_t st, int math, const float *in_value,
+                          MatrixDim in_value_dim, const float *out_deriv,
+                          MatrixDim out_deriv_dim, float *kernel, MatrixDim kernel_dim,
+                          float *in_deriv, MatrixDim in_deriv_dim, float *kernel_grad,
+                          MatrixDim kernel_grad_dim, float *bias_grad, float *prev_grad,
+                          MatrixDim prev_grad_dim, float *bias, int apply, float momentum,
+                          float decay_alpha, float grad_alpha, int in_height, int in_width,
+                          int in_channel, int pad_height, int pad_width, int kernel_height,
+                          int kernel_width, int group);
+int cudaF_affine_wgrad_sgd(cudaStream_t st, int math, const float *in_value,
+                           MatrixDim in_value_dim, const float *out_deriv,
+                           MatrixDim out_deriv_dim, float *w, MatrixDim w_dim,
+                           float *prev_grad, MatrixDim prev_grad_dim, float *bias,
+                           float momentum, float decay_alpha, float grad_alpha);
+
 /* Momentum / weight-decay SGD in ONE pass over the parameters:
  *   prev = momentum*prev; prev += decay_alpha*params; prev += grad_alpha*grad;
  *   params += prev

@@ -76,6 +76,9 @@ _PROTOS = {
     "cudaF_affine_fprop": [S, I, P, M, P, M, P, P, M],
     "cudaF_affine_dgrad": [S, I, P, M, P, M, P, M],
     "cudaF_affine_wgrad": [S, I, P, M, P, M, P, M, P],
+    "cudaF_conv2d_backward": [S, I, P, M, P, M, P, M, P, M, P, M, P, P, M, P, I, F, F, F,
+                              I, I, I, I, I, I, I, I],
+    "cudaF_affine_wgrad_sgd": [S, I, P, M, P, M, P, M, P, M, P, F, F, F],
     "cudaF_sgd_momentum_update": [S, P, M, P, M, P, M, F, F, F],
     "cudaF_vec_axpy": [S, P, P, I, F],
     "cudaF_sum_rows_per_map": [S, P, M, I, P],
@@ -91,6 +94,8 @@ _RESTYPES = {
     "kcnn_build_info": ctypes.c_char_p,
     "kcnn_abi_version": c_int,
     "kcnn_conv2d_wgrad_workspace": c_size_t,
+    "cudaF_conv2d_backward": c_int,
+    "cudaF_affine_wgrad_sgd": c_int,
 }
 
 _lib = None

@@ -38,76 +38,103 @@ namespace tma {
 // ------------------------------------------------------------- channels-last pack --
 
 // in: [N][ld] rows holding [C][R] (R fastest)  ->  out: [N][R][C] (C fastest), dense.
-// One CTA moves kSamples samples through shared memory (row pitch R|1: conflict-free both
-// ways).  With kColSum it also writes partial[blockIdx.x][c] = sum over its samples and r
-// (the bias gradient's first stage, reference nnet0/nnet-component-nnet0.cc:775).
+// CTA (bx, by) moves channels [by*64, by*64+64) of samples [bx*spc, bx*spc+spc) through
+// shared memory in one pass (row pitch R|1: conflict-free both ways); reads are the
+// contiguous 64*R-float run of each sample, writes are 256-byte channel runs.  With kColSum
+// it also writes partial[bx][c] = sum over its samples and r of in[n][c][r] -- the first stage
+// of the bias gradient (reference nnet0/nnet-component-nnet0.cc:775), deterministic.
+constexpr int kPackCh = 64;
+constexpr int kPackMaxSamples = 4;
+constexpr int kPackSmemBudget = 44 * 1024;
+
 template <bool kColSum>
 __global__ void __launch_bounds__(256)
 pack_channels_last_kernel(const float *__restrict__ in, int ld, int N, int C, int R, float *__restrict__ out,
-                          float *__restrict__ partial, int samples_per_cta, FastDiv div_r, FastDiv div_c) {
+                          float *__restrict__ partial, int spc, FastDiv div_r, FastDiv div_ch) {
   extern __shared__ float tile[];
   const int rp = R | 1;
-  const int per = C * R;
-  const int n_begin = blockIdx.x * samples_per_cta;
-  const int n_end = min(N, n_begin + samples_per_cta);
-  float *colacc = tile + C * rp;                // kColSum: per-channel sums over this CTA's samples
-  if (kColSum)
-    for (int c = threadIdx.x; c < C; c += 256) colacc[c] = 0.f;     // channel c stays with one thread
-  for (int n = n_begin; n < n_end; n++) {
-    const float *src = in + (size_t)n * ld;
+  const int c0 = blockIdx.y * kPackCh;
+  const int ch = min(kPackCh, C - c0);
+  const int n_begin = blockIdx.x * spc;
+  const int ns = min(spc, N - n_begin);
+  const int per = ch * R;                       // elements per sample in this CTA
+  const int sample_tile = kPackCh * rp;
+  for (int s = 0; s < ns; s++) {
+    const float *src = in + (size_t)(n_begin + s) * ld + (size_t)c0 * R;
+    float *ts = tile + s * sample_tile;
     for (int i = threadIdx.x; i < per; i += 256) {
       uint32_t c, r;
       div_r.divmod((uint32_t)i, c, r);
-      tile[c * rp + r] = __ldg(src + i);
+      ts[c * rp + r] = __ldg(src + i);
     }
-    __syncthreads();
-    float *dst = out + (size_t)n * per;
-    for (int i = threadIdx.x; i < per; i += 256) {
-      uint32_t r, c;
-      div_c.divmod((uint32_t)i, r, c);
-      dst[i] = tile[c * rp + r];
-    }
-    if (kColSum) {
-      for (int c = threadIdx.x; c < C; c += 256) {
-        float s = 0.f;
-        for (int r = 0; r < R; r++) s += tile[c * rp + r];
-        colacc[c] += s;
-      }
-    }
-    __syncthreads();
   }
-  if (kColSum) {
-    float *prow = partial + (size_t)blockIdx.x * C;
-    for (int c = threadIdx.x; c < C; c += 256) prow[c] = colacc[c];
+  __syncthreads();
+  for (int s = 0; s < ns; s++) {
+    float *dst = out + (size_t)(n_begin + s) * R * C + c0;
+    const float *ts = tile + s * sample_tile;
+    for (int i = threadIdx.x; i < R * kPackCh; i += 256) {
+      uint32_t r, c;
+      div_ch.divmod((uint32_t)i, r, c);
+      if ((int)c < ch) dst[(size_t)r * C + c] = ts[c * rp + r];
+    }
+  }
+  if (kColSum && (int)threadIdx.x < ch) {
+    float acc = 0.f;
+    for (int s = 0; s < ns; s++) {
+      const float *tc = tile + s * sample_tile + threadIdx.x * rp;
+      for (int r = 0; r < R; r++) acc += tc[r];
+    }
+    partial[(size_t)blockIdx.x * C + c0 + threadIdx.x] = acc;
   }
 }
 
-constexpr int kPackSamples = 4;
-constexpr int kPackMaxSmem = 96 * 1024;
+inline int pack_samples_per_cta(int R) {
+  int spc = kPackSmemBudget / (kPackCh * (R | 1) * (int)sizeof(float));
+  if (spc > kPackMaxSamples) spc = kPackMaxSamples;
+  return spc;                                   // 0: R too large for the pack kernel
+}
 
-inline size_t pack_smem_bytes(int C, int R) { return (size_t)C * ((R | 1) + 1) * sizeof(float); }
+// Rows of partial sums the pack writes for `N` samples with `R` positions.
+inline int pack_partial_rows(int N, int R) {
+  int spc = pack_samples_per_cta(R);
+  return spc > 0 ? (N + spc - 1) / spc : 0;
+}
 
-// Returns the number of partial rows written when colsum_partial != nullptr.
-inline int launch_pack(cudaStream_t st, const float *in, int ld, int N, int C, int R, float *out,
-                       float *colsum_partial) {
-  const size_t smem = pack_smem_bytes(C, R);
-  const int ctas = (N + kPackSamples - 1) / kPackSamples;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(pack_channels_last_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackMaxSmem);
-    cudaFuncSetAttribute(pack_channels_last_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackMaxSmem);
-    attr_set = true;
-  }
+inline void launch_pack(cudaStream_t st, const float *in, int ld, int N, int C, int R, float *out,
+                        float *colsum_partial) {
+  const int spc = pack_samples_per_cta(R);
+  const size_t smem = (size_t)spc * kPackCh * (R | 1) * sizeof(float);
+  dim3 grid((N + spc - 1) / spc, (C + kPackCh - 1) / kPackCh);
   if (colsum_partial)
-    KCNN_LAUNCH(pack_channels_last_kernel<true>, ctas, 256, smem, st, in, ld, N, C, R, out, colsum_partial,
-                kPackSamples, FastDiv((uint32_t)R), FastDiv((uint32_t)C));
+    KCNN_LAUNCH(pack_channels_last_kernel<true>, grid, 256, smem, st, in, ld, N, C, R, out, colsum_partial, spc,
+                FastDiv((uint32_t)R), FastDiv((uint32_t)kPackCh));
   else
-    KCNN_LAUNCH(pack_channels_last_kernel<false>, ctas, 256, smem, st, in, ld, N, C, R, out, nullptr,
-                kPackSamples, FastDiv((uint32_t)R), FastDiv((uint32_t)C));
-  return ctas;
+    KCNN_LAUNCH(pack_channels_last_kernel<false>, grid, 256, smem, st, in, ld, N, C, R, out, nullptr, spc,
+                FastDiv((uint32_t)R), FastDiv((uint32_t)kPackCh));
 }
 
 // ------------------------------------------------------- fprop / dgrad problem --
+
+// stage[(s*R + pos)][map] -> out[n0 + s][(col0 + map) * R + pos]: per sample ONE contiguous run of
+// maps * R floats (the reference's [map][pos] layout), written 512 bytes per warp instruction.
+__device__ __forceinline__ void store_maps_transposed(const float *stage, int tid, int n0, int nb, int R,
+                                                      int col0, int maps, int num_samples, float *out, int ldo,
+                                                      const float *bias, const FastDiv &div_r) {
+  const int total = maps * R;
+  for (int s = 0; s < nb; s++) {
+    const int n = n0 + s;
+    if (n >= num_samples) break;
+    float *orow = out + (size_t)n * ldo + (size_t)col0 * R;
+    const float *srow = stage + s * R * PITCH;
+    for (int idx = tid; idx < total; idx += 128) {
+      uint32_t g, pos;
+      div_r.divmod((uint32_t)idx, g, pos);
+      float v = srow[pos * PITCH + g];
+      if (bias) v += __ldg(bias + col0 + g);
+      orow[idx] = v;
+    }
+  }
+}
 
 // Rows of the GEMM are (sample, position) with R positions per sample and NB = 128 / R
 // samples per tile; the K-blocks walk taps t (outer) x 32-wide slices of the reduced
@@ -143,22 +170,90 @@ struct ConvRowsProb {
       tma_load_3d(b_addr, mb, i0, (int)t, col0, bar);
     }
   }
-  // stage[(s*R + pos)][map] -> out[n0 + s][(col0 + map) * R + pos]: per sample one contiguous run
+  __device__ __forceinline__ void prefetch(int) const {}
   __device__ __forceinline__ void store(const float *stage, int tid) const {
-    const int n0 = blockIdx.x * nb, col0 = blockIdx.y * BN;
-    const int maps = min(BN, out_maps - col0);
-    const int total = maps * R;
+    const int col0 = blockIdx.y * BN;
+    store_maps_transposed(stage, tid, blockIdx.x * nb, nb, R, col0, min(BN, out_maps - col0), num_samples, out,
+                          ldo, bias, div_r);
+  }
+};
+
+// ------------------------------------------- full-height kernels (KH = H, OH = 1) --
+//
+// conv1 of nnet.config (40 x 21 x 1, kernel 40 x 4) and C1a: the (kw, kh) window of output
+// column ow is the CONTIGUOUS run X[n, c*H*W + ow*H ... + KW*H), so the im2col matrix is a
+// 4-D tensor map over the input itself -- dims (j < KW*KH, ow [pitch H], c [pitch H*W],
+// n [row pitch]) with overlapping rows -- and the forward pass needs no staging copy at all.
+// (No zero padding on this path: the window position is folded into the address.)
+
+// fprop: A box {32 j, OW, 1, NB} at (j0, 0, c, n0) K-major; B = kernel rows c*ks + j, MN-major.
+struct ConvFullFpropProb {
+  static constexpr bool kAMn = false, kBMn = true;
+  int num_samples, OW, nb, ks, j_blocks, G;
+  float *out;
+  int ldo;
+  const float *bias;
+  FastDiv div_jb, div_ow;
+
+  int total_kb;            // C * j_blocks
+  __device__ __forceinline__ void kb_range(int &b, int &e) const { b = 0; e = total_kb; }
+  __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)(nb * OW * 128 + B_STAGE_BYTES); }
+  __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
+                                       const CUtensorMap *ma, const CUtensorMap *mb) const {
+    uint32_t c, jb;
+    div_jb.divmod((uint32_t)kb, c, jb);
+    const int j0 = (int)jb * 32;
+    const int n0 = blockIdx.x * nb, g0 = blockIdx.y * BN;
+    tma_load_4d(a_addr, ma, j0, 0, (int)c, n0, bar);
+#pragma unroll
+    for (int i = 0; i < BN / 32; i++) tma_load_2d(b_addr + i * ATOM_BYTES, mb, g0 + 32 * i, (int)c * ks + j0, bar);
+  }
+  __device__ __forceinline__ void prefetch(int) const {}
+  __device__ __forceinline__ void store(const float *stage, int tid) const {
+    const int g0 = blockIdx.y * BN;
+    store_maps_transposed(stage, tid, blockIdx.x * nb, nb, OW, g0, min(BN, G - g0), num_samples, out, ldo, bias,
+                          div_ow);
+  }
+};
+
+// dgrad: dX[(n,w),(c,h)] = sum_{kw,g} dYcl[n, w-kw, g] K[c*ks + kw*KH + h, g]  (kh = h is fixed by
+// the row of the image, so it moves from the reduction into the GEMM's N axis).
+// A box {32 g, W, NB} of dYcl at (g0, -kw, n0); B box {32 g, KH, NBC channels} of the kernel
+// viewed as (g, r < ks, c) at (g0, kw*KH, c0), K-major.  The tile rows (s, w) x columns
+// (cb, h) ARE the reference layout [c][w][h]: each (sample, channel) is one contiguous run.
+struct ConvFullDgradProb {
+  static constexpr bool kAMn = false, kBMn = false;
+  int num_samples, W, H, C, nb, nbc, g_blocks, total_kb;
+  float *out;
+  int ldo;
+  FastDiv div_gb, div_h;
+
+  __device__ __forceinline__ void kb_range(int &b, int &e) const { b = 0; e = total_kb; }
+  __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)((nb * W + nbc * H) * 128); }
+  __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
+                                       const CUtensorMap *ma, const CUtensorMap *mb) const {
+    uint32_t kw, gb;
+    div_gb.divmod((uint32_t)kb, kw, gb);
+    const int g0 = (int)gb * 32;
+    tma_load_3d(a_addr, ma, g0, -(int)kw, blockIdx.x * nb, bar);
+    tma_load_3d(b_addr, mb, g0, (int)kw * H, blockIdx.y * nbc, bar);
+  }
+  __device__ __forceinline__ void prefetch(int) const {}
+  __device__ __forceinline__ void store(const float *stage, int tid) const {
+    const int n0 = blockIdx.x * nb, c0 = blockIdx.y * nbc;
+    const int chans = min(nbc, C - c0);
+    const int hw = H * W;
     for (int s = 0; s < nb; s++) {
       const int n = n0 + s;
       if (n >= num_samples) break;
-      float *orow = out + (size_t)n * ldo + (size_t)col0 * R;
-      const float *srow = stage + s * R * PITCH;
-      for (int idx = tid; idx < total; idx += 128) {
-        uint32_t g, pos;
-        div_r.divmod((uint32_t)idx, g, pos);
-        float v = srow[pos * PITCH + g];
-        if (bias) v += __ldg(bias + col0 + g);
-        orow[idx] = v;
+      for (int cb = 0; cb < chans; cb++) {
+        float *orow = out + (size_t)n * ldo + (size_t)(c0 + cb) * hw;
+        const float *sbase = stage + s * W * PITCH + cb * H;
+        for (int idx = tid; idx < hw; idx += 128) {
+          uint32_t w, h;
+          div_h.divmod((uint32_t)idx, w, h);
+          orow[idx] = sbase[w * PITCH + h];
+        }
       }
     }
   }
@@ -177,10 +272,12 @@ struct KernelRow {
   }
 };
 
-template <int kEpi>
+// kFull: full-height kernels, A straight from the input through the 4-D window map, rows m in
+// kernel order c*ks + j (ks % 32 == 0); div_c then divides by ks.
+template <int kEpi, bool kFull = false>
 struct ConvWgradProb {
   static constexpr bool kAMn = true, kBMn = true;
-  int C, KW, G, M;         // M = KW * C, rows m = kw * C + c
+  int C, KW, G, M;         // M = KW * C, rows m = kw * C + c   (kFull: M = C * ks, kernel order)
   int pw;
   int n_blocks;            // ceil(N / 32): K-blocks per output position
   int total_kb;            // OW * n_blocks
@@ -206,18 +303,31 @@ struct ConvWgradProb {
     const int m0 = blockIdx.x * BM, g0 = blockIdx.y * BN;
 #pragma unroll
     for (int i = 0; i < BM / 32; i++) {
-      uint32_t kw, c;
-      div_c.divmod((uint32_t)(m0 + 32 * i), kw, c);
-      tma_load_3d(a_addr + i * ATOM_BYTES, ma, (int)c, (int)ow + (int)kw - pw, n0, bar);
+      uint32_t q, r;
+      div_c.divmod((uint32_t)(m0 + 32 * i), q, r);
+      if (kFull) tma_load_4d(a_addr + i * ATOM_BYTES, ma, (int)r, (int)ow, (int)q, n0, bar);      // (j, ow, c, n)
+      else       tma_load_3d(a_addr + i * ATOM_BYTES, ma, (int)r, (int)ow + (int)q - pw, n0, bar); // (c, w, n)
     }
 #pragma unroll
     for (int i = 0; i < BN / 32; i++) tma_load_3d(b_addr + i * ATOM_BYTES, mb, g0 + 32 * i, (int)ow, n0, bar);
+  }
+  __device__ __forceinline__ void prefetch(int tid) const {
+    if (kEpi == EPI_SGD) {
+      if (kFull) {
+        prefetch_tile_l2(tid, blockIdx.x * BM, blockIdx.y * BN, M, G, out, aux, ldo, IdentityRow());
+      } else {
+        KernelRow rm; rm.div_c = div_c; rm.KW = KW;
+        prefetch_tile_l2(tid, blockIdx.x * BM, blockIdx.y * BN, M, G, out, aux, ldo, rm);
+      }
+    }
   }
   __device__ __forceinline__ void store(const float *stage, int tid) const {
     const int m0 = blockIdx.x * BM, g0 = blockIdx.y * BN;
     if (kEpi == EPI_PARTIAL) {
       store_rows<EPI_STORE>(stage, tid, m0, g0, M, G, workspace + (size_t)blockIdx.z * M * G, G, nullptr,
                             nullptr, sgd, IdentityRow());
+    } else if (kFull) {
+      store_rows<kEpi>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, IdentityRow());
     } else {
       KernelRow rm; rm.div_c = div_c; rm.KW = KW;
       store_rows<kEpi>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, rm);
@@ -238,8 +348,7 @@ inline bool conv_tma_shape_ok(const ConvShape &q) {
   if (q.N <= 0 || q.OW <= 0 || q.OW > 128 || q.W > 128) return false;
   if (q.C < 32 || (q.C & 31) != 0) return false;          // 32-channel K slices / M atoms
   if (q.G < 32 || (q.G & 3) != 0) return false;
-  if (pack_smem_bytes(q.C, q.W) > (size_t)kPackMaxSmem || pack_smem_bytes(q.G, q.OW) > (size_t)kPackMaxSmem)
-    return false;
+  if (pack_samples_per_cta(q.W) < 1 || pack_samples_per_cta(q.OW) < 1) return false;
   return true;
 }
 
@@ -280,82 +389,224 @@ inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int
   return true;
 }
 
-inline bool conv_dgrad(cudaStream_t st, const ConvShape &q, const float *out_deriv, int ld_od,
-                       const float *kernel, int ld_k, float *in_deriv, int ld_id) {
-  if (!conv_tma_shape_ok(q)) return false;
-  float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float));
-  if (!dycl) return false;
-  const int nb = 128 / q.W;
-  CUtensorMap ma, mb;
-  if (!encode_act_map(&ma, dycl, q.N, q.OW, q.G, (unsigned)q.W, (unsigned)nb, false)) return false;
-  if (!encode_kernel_map(&mb, kernel, ld_k, q.C, q.KW, q.G, 128, false)) return false;
-  launch_pack(st, out_deriv, ld_od, q.N, q.G, q.OW, dycl, nullptr);
-  ConvRowsProb<false> p;
-  p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
-  p.a_w0 = q.pw; p.a_wstep = -1; p.out_maps = q.C; p.out = in_deriv; p.ldo = ld_id; p.bias = nullptr;
-  p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.W);
-  launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
-  return true;
-}
+// Everything ConvolutionComponent::Backprop needs (reference nnet0/nnet-component-nnet0.cc:
+// 461-544 + 738-777) from ONE channels-last copy of out_deriv and one of in_value:
+//   in_deriv (optional)            dgrad GEMM
+//   kernel gradient                wgrad GEMM, split-K
+//   bias gradient                  column sums, first stage inside the out_deriv pack
+// With sgd != nullptr the weight step  prev = m prev + a_decay K + a_grad dK ; K += prev  runs in
+// the wgrad epilogue / split-K reduction on (kernel, prev) and the gradient is never
+// written; otherwise kernel_grad receives dK.  The bias partial sums are returned for the
+// caller's final column-sum stage.
+struct ConvBackward {
+  const float *in_value; int ld_iv;
+  const float *out_deriv; int ld_od;
+  float *kernel; int ld_k;                // weights (read by dgrad; updated in place when sgd)
+  float *in_deriv; int ld_id;             // nullptr: skip dgrad
+  float *kernel_grad; int ld_kg;          // !sgd: receives dK;  nullptr: skip wgrad
+  float *prev; int ld_p;                  // sgd: momentum state, same shape / pitch as kernel
+  const SgdCoef *sgd;
+  bool want_bias;
+  float *bias_partial; int bias_rows;     // out
+};
 
-// Weight gradient into kernel_grad (sgd == nullptr) or, with sgd, straight into the
-// update prev = m prev - lr wd K + lr dK ; K += prev (kernel_grad = K, prev = aux).
-// bias_partial (optional): [ceil(N / kPackSamples)][G] first-stage column sums of dY; the
-// number of rows is returned through bias_rows.
-inline bool conv_wgrad(cudaStream_t st, const ConvShape &q, const float *in_value, int ld_iv,
-                       const float *out_deriv, int ld_od, float *kernel_grad, int ld_kg, float *prev,
-                       const SgdCoef *sgd, float **bias_partial, int *bias_rows) {
+inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) {
   if (!conv_tma_shape_ok(q)) return false;
-  if ((ld_kg & 3) != 0 || !host_aligned16(kernel_grad) || (prev && !host_aligned16(prev))) return false;
-  float *xcl = scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
+  const bool do_dgrad = b.in_deriv != nullptr;
+  const bool do_wgrad = b.sgd != nullptr || b.kernel_grad != nullptr;
+  float *wout = b.sgd ? b.kernel : b.kernel_grad;
+  const int ld_w = b.sgd ? b.ld_k : b.ld_kg;
+  if (do_wgrad) {
+    if ((ld_w & 3) != 0 || !host_aligned16(wout)) return false;
+    if (b.sgd && (b.ld_p != b.ld_k || !host_aligned16(b.prev))) return false;
+  }
   float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float));
-  const int pack_ctas = (q.N + kPackSamples - 1) / kPackSamples;
-  float *bpart = bias_partial ? scratch(SCRATCH_BIAS, (size_t)pack_ctas * q.G * sizeof(float)) : nullptr;
-  if (!xcl || !dycl || (bias_partial && !bpart)) return false;
+  float *xcl = do_wgrad ? scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float)) : nullptr;
+  const int prow = pack_partial_rows(q.N, q.OW);
+  float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float)) : nullptr;
+  if (!dycl || (do_wgrad && !xcl) || (b.want_bias && !bpart)) return false;
+
   const int M = q.KW * q.C;
   const int n_blocks = (q.N + 31) / 32;
   const int total_kb = q.OW * n_blocks;
-  const long long tiles = (long long)ceil_div_u(M, BM) * ceil_div_u(q.G, BN);
-  int splits = pick_splits(tiles, total_kb);
-  int per = (total_kb + splits - 1) / splits;
-  splits = (total_kb + per - 1) / per;
+  int splits = 1, per = total_kb;
   float *ws = nullptr;
-  if (splits > 1) {
-    ws = scratch(SCRATCH_SPLITK, (size_t)splits * M * q.G * sizeof(float));
-    if (!ws) return false;
+  CUtensorMap wa, wb, da, db;
+  if (do_wgrad) {
+    splits = pick_splits((long long)ceil_div_u(M, BM) * ceil_div_u(q.G, BN), total_kb);
+    per = (total_kb + splits - 1) / splits;
+    splits = (total_kb + per - 1) / per;
+    if (splits > 1) {
+      ws = scratch(SCRATCH_SPLITK, (size_t)splits * M * q.G * sizeof(float));
+      if (!ws) return false;
+    }
+    if (!encode_act_map(&wa, xcl, q.N, q.W, q.C, 1, 32, true)) return false;
+    if (!encode_act_map(&wb, dycl, q.N, q.OW, q.G, 1, 32, true)) return false;
   }
-  CUtensorMap ma, mb;
-  if (!encode_act_map(&ma, xcl, q.N, q.W, q.C, 1, 32, true)) return false;
-  if (!encode_act_map(&mb, dycl, q.N, q.OW, q.G, 1, 32, true)) return false;
-  launch_pack(st, in_value, ld_iv, q.N, q.C, q.W, xcl, nullptr);
-  launch_pack(st, out_deriv, ld_od, q.N, q.G, q.OW, dycl, bpart);
-  if (bias_partial) { *bias_partial = bpart; *bias_rows = pack_ctas; }
+  const int nb = 128 / q.W;
+  if (do_dgrad) {
+    if (!encode_act_map(&da, dycl, q.N, q.OW, q.G, (unsigned)q.W, (unsigned)nb, false)) return false;
+    if (!encode_kernel_map(&db, b.kernel, b.ld_k, q.C, q.KW, q.G, 128, false)) return false;
+  }
+  // ---- nothing can fail past this point
+  launch_pack(st, b.out_deriv, b.ld_od, q.N, q.G, q.OW, dycl, bpart);
+  b.bias_partial = bpart; b.bias_rows = prow;
+  if (do_dgrad) {
+    ConvRowsProb<false> p;
+    p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
+    p.a_w0 = q.pw; p.a_wstep = -1; p.out_maps = q.C; p.out = b.in_deriv; p.ldo = b.ld_id; p.bias = nullptr;
+    p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.W);
+    launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
+  }
+  if (!do_wgrad) return true;
+  launch_pack(st, b.in_value, b.ld_iv, q.N, q.C, q.W, xcl, nullptr);
   dim3 grid(ceil_div_u(M, BM), ceil_div_u(q.G, BN), splits);
   SgdCoef none = {0.f, 0.f, 0.f};
   auto fill = [&](auto &p) {
     p.C = q.C; p.KW = q.KW; p.G = q.G; p.M = M; p.pw = q.pw; p.n_blocks = n_blocks; p.total_kb = total_kb;
-    p.kb_per_split = per; p.out = kernel_grad; p.ldo = ld_kg; p.workspace = ws; p.aux = prev;
-    p.sgd = sgd ? *sgd : none;
+    p.kb_per_split = per; p.out = wout; p.ldo = ld_w; p.workspace = ws; p.aux = b.prev;
+    p.sgd = b.sgd ? *b.sgd : none;
     p.div_nb = FastDiv((uint32_t)n_blocks); p.div_c = FastDiv((uint32_t)q.C);
   };
   KernelRow rm;
   rm.div_c = FastDiv((uint32_t)q.C); rm.KW = q.KW;
   if (splits > 1) {
     ConvWgradProb<EPI_PARTIAL> p; fill(p);
-    launch_prob(st, ma, mb, p, grid);
+    launch_prob(st, wa, wb, p, grid);
     const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
-    if (sgd)
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, KernelRow>), blocks, 256, 0,
-                  st, ws, splits, M, q.G, kernel_grad, ld_kg, nullptr, prev, *sgd, rm);
+    if (b.sgd)
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, KernelRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout, ld_w,
+                  nullptr, b.prev, *b.sgd, rm);
     else
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, KernelRow>), blocks, 256, 0,
-                  st, ws, splits, M, q.G, kernel_grad, ld_kg, nullptr, nullptr, none, rm);
-  } else if (sgd) {
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, KernelRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout, ld_w,
+                  nullptr, nullptr, none, rm);
+  } else if (b.sgd) {
     ConvWgradProb<EPI_SGD> p; fill(p);
-    launch_prob(st, ma, mb, p, grid);
+    launch_prob(st, wa, wb, p, grid);
   } else {
     ConvWgradProb<EPI_STORE> p; fill(p);
-    launch_prob(st, ma, mb, p, grid);
+    launch_prob(st, wa, wb, p, grid);
+  }
+  return true;
+}
+
+// ---- full-height kernels (KH = H, no padding): conv1 of nnet.config, C1a -----------------
+
+struct ConvFullShape {
+  int N, H, W, C, KW, G, OW;      // kernel_height = in_height, pads = 0
+};
+
+inline bool conv_full_shape_ok(const ConvFullShape &q) {
+  if (!enabled()) return false;
+  if (q.N <= 0 || q.OW <= 0 || q.OW > 128 || q.W > 128 || q.H > 128) return false;
+  if ((q.H & 3) != 0 || q.G < 32) return false;
+  return true;
+}
+
+// (j < KW*H, ow [pitch H], c [pitch H*W], n [row pitch]) over the input matrix itself
+inline bool encode_window_map(CUtensorMap *map, const float *in, int ld, const ConvFullShape &q, unsigned box_ow,
+                              unsigned box_n, bool mn_major) {
+  unsigned long long dims[4] = {(unsigned long long)q.KW * q.H, (unsigned long long)q.OW, (unsigned long long)q.C,
+                                (unsigned long long)q.N};
+  unsigned long long str[3] = {(unsigned long long)q.H * 4, (unsigned long long)q.H * q.W * 4,
+                               (unsigned long long)ld * 4};
+  unsigned box[4] = {32, box_ow, 1, box_n};
+  return encode_map(map, in, 4, dims, str, box, mn_major);
+}
+
+inline bool conv_full_fprop(cudaStream_t st, const ConvFullShape &q, const float *in, int ld_in,
+                            const float *kernel, int ld_k, const float *bias, float *out, int ldo) {
+  if (!conv_full_shape_ok(q)) return false;
+  const int ks = q.KW * q.H, nb = 128 / q.OW;
+  CUtensorMap ma, mb;
+  if (!encode_window_map(&ma, in, ld_in, q, (unsigned)q.OW, (unsigned)nb, false)) return false;
+  if (!encode_2d(&mb, Matrix{kernel, q.C * ks, q.G, ld_k}, 32, true)) return false;
+  ConvFullFpropProb p;
+  p.num_samples = q.N; p.OW = q.OW; p.nb = nb; p.ks = ks; p.j_blocks = (ks + 31) / 32; p.G = q.G;
+  p.total_kb = q.C * p.j_blocks; p.out = out; p.ldo = ldo; p.bias = bias;
+  p.div_jb = FastDiv((uint32_t)p.j_blocks); p.div_ow = FastDiv((uint32_t)q.OW);
+  launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1));
+  return true;
+}
+
+// Same contract as conv_backward(); in_value must be TMA-addressable (16-byte aligned rows).
+inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBackward &b) {
+  if (!conv_full_shape_ok(q)) return false;
+  if (pack_samples_per_cta(q.OW) < 1) return false;
+  const int ks = q.KW * q.H;
+  const bool do_dgrad = b.in_deriv != nullptr;
+  const bool do_wgrad = b.sgd != nullptr || b.kernel_grad != nullptr;
+  float *wout = b.sgd ? b.kernel : b.kernel_grad;
+  const int ld_w = b.sgd ? b.ld_k : b.ld_kg;
+  if (do_wgrad) {
+    if ((ks & 31) != 0) return false;                       // M atoms must not straddle channels
+    if ((ld_w & 3) != 0 || !host_aligned16(wout)) return false;
+    if (b.sgd && (b.ld_p != b.ld_k || !host_aligned16(b.prev))) return false;
+  }
+  float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float));
+  const int prow = pack_partial_rows(q.N, q.OW);
+  float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float)) : nullptr;
+  if (!dycl || (b.want_bias && !bpart)) return false;
+  const int M = q.C * ks;
+  const int n_blocks = (q.N + 31) / 32;
+  const int total_kb = q.OW * n_blocks;
+  int splits = 1, per = total_kb;
+  float *ws = nullptr;
+  CUtensorMap wa, wb, da, db;
+  if (do_wgrad) {
+    splits = pick_splits((long long)ceil_div_u(M, BM) * ceil_div_u(q.G, BN), total_kb);
+    per = (total_kb + splits - 1) / splits;
+    splits = (total_kb + per - 1) / per;
+    if (splits > 1) {
+      ws = scratch(SCRATCH_SPLITK, (size_t)splits * M * q.G * sizeof(float));
+      if (!ws) return false;
+    }
+    if (!encode_window_map(&wa, b.in_value, b.ld_iv, q, 1, 32, true)) return false;
+    if (!encode_act_map(&wb, dycl, q.N, q.OW, q.G, 1, 32, true)) return false;
+  }
+  const int nb = 128 / q.W, nbc = 128 / q.H;
+  if (do_dgrad) {
+    if (!encode_act_map(&da, dycl, q.N, q.OW, q.G, (unsigned)q.W, (unsigned)nb, false)) return false;
+    unsigned long long dims[3] = {(unsigned long long)q.G, (unsigned long long)ks, (unsigned long long)q.C};
+    unsigned long long str[2] = {(unsigned long long)b.ld_k * 4, (unsigned long long)b.ld_k * 4 * ks};
+    unsigned box[3] = {32, (unsigned)q.H, (unsigned)nbc};
+    if (!encode_map(&db, b.kernel, 3, dims, str, box, false)) return false;
+  }
+  // ---- nothing can fail past this point
+  launch_pack(st, b.out_deriv, b.ld_od, q.N, q.G, q.OW, dycl, bpart);
+  b.bias_partial = bpart; b.bias_rows = prow;
+  if (do_dgrad) {
+    ConvFullDgradProb p;
+    p.num_samples = q.N; p.W = q.W; p.H = q.H; p.C = q.C; p.nb = nb; p.nbc = nbc;
+    p.g_blocks = (q.G + 31) / 32; p.total_kb = q.KW * p.g_blocks; p.out = b.in_deriv; p.ldo = b.ld_id;
+    p.div_gb = FastDiv((uint32_t)p.g_blocks); p.div_h = FastDiv((uint32_t)q.H);
+    launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, nbc), 1));
+  }
+  if (!do_wgrad) return true;
+  dim3 grid(ceil_div_u(M, BM), ceil_div_u(q.G, BN), splits);
+  SgdCoef none = {0.f, 0.f, 0.f};
+  auto fill = [&](auto &p) {
+    p.C = q.C; p.KW = q.KW; p.G = q.G; p.M = M; p.pw = 0; p.n_blocks = n_blocks; p.total_kb = total_kb;
+    p.kb_per_split = per; p.out = wout; p.ldo = ld_w; p.workspace = ws; p.aux = b.prev;
+    p.sgd = b.sgd ? *b.sgd : none;
+    p.div_nb = FastDiv((uint32_t)n_blocks); p.div_c = FastDiv((uint32_t)ks);
+  };
+  if (splits > 1) {
+    ConvWgradProb<EPI_PARTIAL, true> p; fill(p);
+    launch_prob(st, wa, wb, p, grid);
+    const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
+    if (b.sgd)
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout, ld_w,
+                  nullptr, b.prev, *b.sgd, IdentityRow());
+    else
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout,
+                  ld_w, nullptr, nullptr, none, IdentityRow());
+  } else if (b.sgd) {
+    ConvWgradProb<EPI_SGD, true> p; fill(p);
+    launch_prob(st, wa, wb, p, grid);
+  } else {
+    ConvWgradProb<EPI_STORE, true> p; fill(p);
+    launch_prob(st, wa, wb, p, grid);
   }
   return true;
 }

@@ -86,6 +86,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -122,6 +129,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
 //   void kb_range(int &begin, int &end) const          K-blocks of this CTA
 //   uint32_t tx_bytes() const                           bytes one stage's TMA boxes deliver
 //   void load(kb, a_addr, b_addr, bar, &map_a, &map_b)  issue the boxes of K-block kb
+//   void prefetch(int tid) const                        epilogue threads, before the accumulator is ready
 //   void store(const float *stage, int tid) const       128 epilogue threads, stage[128][PITCH]
 template <class Prob>
 __global__ void __launch_bounds__(THREADS, 2)
@@ -204,6 +212,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ----------------------------------------------------------------- epilogue --
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     float *stage = reinterpret_cast<float *>(smem_gen);
+    prob.prefetch(t - 64);
     if (num_kb > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
@@ -245,9 +254,17 @@ enum EpiMode {
   EPI_SGD = 2,        // prev = m prev - lr wd W + lr acc ; W += prev   (out = W, aux = prev)
 };
 
+// prev = momentum*prev ; prev += a_decay*W ; prev += a_grad*grad ; W += prev  -- the four
+// roundings of the reference's Scale / AddMat / AddMat / AddMat, as sgd_momentum_kernel.
 struct SgdCoef {
-  float lr, lr_wd, momentum;
+  float momentum, a_decay, a_grad;
 };
+__device__ __forceinline__ void sgd_apply(float &w, float &p, float g, const SgdCoef &c) {
+  p = p * c.momentum;
+  p = fmaf(c.a_decay, w, p);
+  p = fmaf(c.a_grad, g, p);
+  w = w + p;
+}
 
 // Row-major 128-column segment store shared by the dense and the weight-gradient
 // problems: tid -> (row group, 4 columns); each warp instruction writes one 512-byte
@@ -266,6 +283,38 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
     if (n + 2 < N) bias4.z = __ldg(bias_n + n + 2);
     if (n + 3 < N) bias4.w = __ldg(bias_n + n + 3);
   }
+  if (kEpi == EPI_SGD && vec_ok) {
+    // nnet0/nnet-component-nnet0.cc:767-773, 1138-1142 on the tile: W and prev_grad rows are
+    // read in batches of 8 rows (16 independent 128-bit loads per thread in flight; the lines
+    // were L2-prefetched by Problem::prefetch while the main loop ran), updated, written back.
+    constexpr int RB = 8;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += RB) {
+      float4 w[RB], pv[RB];
+      size_t roff[RB];
+#pragma unroll
+      for (int i = 0; i < RB; i++) {
+        const int mt = wl * 32 + r0 + i;
+        const bool ok = m0 + mt < M;
+        roff[i] = (size_t)row_of(ok ? m0 + mt : m0) * ld + n;
+        if (ok) {
+          w[i] = *reinterpret_cast<const float4 *>(obase + roff[i]);
+          pv[i] = *reinterpret_cast<const float4 *>(aux + roff[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RB; i++) {
+        const int mt = wl * 32 + r0 + i;
+        if (m0 + mt >= M) break;
+        const float4 a = *reinterpret_cast<const float4 *>(stage + mt * PITCH + 4 * lane);
+        sgd_apply(w[i].x, pv[i].x, a.x, sgd); sgd_apply(w[i].y, pv[i].y, a.y, sgd);
+        sgd_apply(w[i].z, pv[i].z, a.z, sgd); sgd_apply(w[i].w, pv[i].w, a.w, sgd);
+        *reinterpret_cast<float4 *>(aux + roff[i]) = pv[i];
+        *reinterpret_cast<float4 *>(obase + roff[i]) = w[i];
+      }
+    }
+    return;
+  }
 #pragma unroll 4
   for (int r = 0; r < 32; r++) {
     const int mt = wl * 32 + r;
@@ -274,32 +323,16 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
     const size_t roff = (size_t)row_of(m0 + mt) * ld + n;
     float *orow = obase + roff;
     if (kEpi == EPI_SGD) {
-      // nnet0/nnet-component-nnet0.cc:767-773, 1138-1142:
-      //   prev = momentum prev - lr wd W + lr grad ;  W += prev
       float *prow = aux + roff;
-      if (vec_ok) {
-        float4 w = *reinterpret_cast<const float4 *>(orow);
-        float4 pv = *reinterpret_cast<const float4 *>(prow);
-        pv.x = sgd.momentum * pv.x; pv.x += -sgd.lr_wd * w.x; pv.x += sgd.lr * a.x;
-        pv.y = sgd.momentum * pv.y; pv.y += -sgd.lr_wd * w.y; pv.y += sgd.lr * a.y;
-        pv.z = sgd.momentum * pv.z; pv.z += -sgd.lr_wd * w.z; pv.z += sgd.lr * a.z;
-        pv.w = sgd.momentum * pv.w; pv.w += -sgd.lr_wd * w.w; pv.w += sgd.lr * a.w;
-        w.x += pv.x; w.y += pv.y; w.z += pv.z; w.w += pv.w;
-        *reinterpret_cast<float4 *>(prow) = pv;
-        *reinterpret_cast<float4 *>(orow) = w;
-      } else {
-        const float av[4] = {a.x, a.y, a.z, a.w};
+      const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (n + j < N) {
-            float w = orow[j];
-            float pv = sgd.momentum * prow[j];
-            pv += -sgd.lr_wd * w;
-            pv += sgd.lr * av[j];
-            prow[j] = pv;
-            orow[j] = w + pv;
-          }
-      }
+      for (int j = 0; j < 4; j++)
+        if (n + j < N) {
+          float w = orow[j], pv = prow[j];
+          sgd_apply(w, pv, av[j], sgd);
+          prow[j] = pv;
+          orow[j] = w;
+        }
     } else {
       a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
       if (vec_ok) {
@@ -310,6 +343,23 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
         if (n + 2 < N) orow[2] = a.z;
         if (n + 3 < N) orow[3] = a.w;
       }
+    }
+  }
+}
+
+// L2 prefetch of the 128 x 128 tiles of two row-major matrices the epilogue will read
+// (EPI_SGD: W and prev_grad), issued by the 128 epilogue threads before the main loop ends.
+template <class RowMap>
+__device__ __forceinline__ void prefetch_tile_l2(int tid, int m0, int n0, int M, int N, const float *a,
+                                                 const float *b, int ld, RowMap row_of) {
+  // 128 rows x 4 lines of 128 bytes per matrix; thread -> (row, line) pairs
+  for (int i = tid; i < 128 * 4; i += 128) {
+    const int r = i >> 2, line = i & 3;
+    const int m = m0 + r, n = n0 + line * 32;
+    if (m < M && n < N) {
+      const size_t off = (size_t)row_of(m) * ld + n;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a + off));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(b + off));
     }
   }
 }
@@ -353,6 +403,10 @@ struct DenseProb {
       tma_load_2d(b_addr, mb, k0, n0, bar);
     }
   }
+  __device__ __forceinline__ void prefetch(int tid) const {
+    if (kEpi == EPI_SGD)
+      prefetch_tile_l2(tid, blockIdx.x * BM, blockIdx.y * BN, M, N, out, aux, ldo, IdentityRow());
+  }
   __device__ __forceinline__ void store(const float *stage, int tid) const {
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     if (kEpi == EPI_PARTIAL)
@@ -383,11 +437,8 @@ splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, flo
   if (kEpi == EPI_SGD) {
     float4 w = *reinterpret_cast<const float4 *>(out + off);
     float4 pv = *reinterpret_cast<const float4 *>(aux + off);
-    pv.x = sgd.momentum * pv.x; pv.x += -sgd.lr_wd * w.x; pv.x += sgd.lr * s.x;
-    pv.y = sgd.momentum * pv.y; pv.y += -sgd.lr_wd * w.y; pv.y += sgd.lr * s.y;
-    pv.z = sgd.momentum * pv.z; pv.z += -sgd.lr_wd * w.z; pv.z += sgd.lr * s.z;
-    pv.w = sgd.momentum * pv.w; pv.w += -sgd.lr_wd * w.w; pv.w += sgd.lr * s.w;
-    w.x += pv.x; w.y += pv.y; w.z += pv.z; w.w += pv.w;
+    sgd_apply(w.x, pv.x, s.x, sgd); sgd_apply(w.y, pv.y, s.y, sgd);
+    sgd_apply(w.z, pv.z, s.z, sgd); sgd_apply(w.w, pv.w, s.w, sgd);
     *reinterpret_cast<float4 *>(aux + off) = pv;
     *reinterpret_cast<float4 *>(out + off) = w;
   } else {
@@ -414,15 +465,15 @@ bool enabled();                          // KCNN_TMA=0 disables the TMA paths
 enum ScratchSlot { SCRATCH_SPLITK = 0, SCRATCH_XCL = 1, SCRATCH_DYCL = 2, SCRATCH_BIAS = 3, SCRATCH_SLOTS = 4 };
 float *scratch(int slot, size_t bytes);
 
-// Tensor map of rank 2 or 3 over FP32 data; dims[0] is the contiguous axis, strides_bytes[i]
+// Tensor map of rank 2 to 4 over FP32 data; dims[0] is the contiguous axis, strides_bytes[i]
 // is the pitch of dims[i + 1].  mn_major picks the 32-byte-atom swizzle.
 inline bool encode_map(CUtensorMap *map, const float *base, int rank, const unsigned long long *dims,
                        const unsigned long long *strides_bytes, const unsigned *box, bool mn_major) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   if (!host_aligned16(base)) return false;
-  cuuint64_t gdim[3], gstr[2];
-  cuuint32_t bx[3], estr[3] = {1, 1, 1};
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], estr[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; i++) {
     if (dims[i] == 0 || box[i] == 0 || box[i] > 256) return false;
     gdim[i] = dims[i];

@@ -129,31 +129,42 @@ colsum_maps_kernel(const float *__restrict__ m, int rows, int stride, int inner,
   }
 }
 
-// inner == 1: a block owns 32 adjacent columns, reads 128-byte row segments.
-__global__ void __launch_bounds__(256)
+// inner == 1: a block owns 32 adjacent columns and reads 128-byte row segments with 32
+// row-threads, four independent accumulators each.  out[c] = alpha * sum (+ out[c] if accumulate).
+__global__ void __launch_bounds__(1024)
 colsum_rows_kernel(const float *__restrict__ m, int rows, int cols, int stride,
-                   float *__restrict__ out) {
-  __shared__ float part[8][33];
+                   float *__restrict__ out, float alpha, int accumulate) {
+  __shared__ float part[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
-  float s = 0.0f;
-  if (col < cols)
-    for (int r = ty; r < rows; r += 8) s += __ldg(m + (size_t)r * stride + col);
-  part[ty][tx] = s;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  if (col < cols) {
+    const float *p = m + col;
+    int r = ty;
+    for (; r + 96 < rows; r += 128) {
+      s0 += __ldg(p + (size_t)r * stride);
+      s1 += __ldg(p + (size_t)(r + 32) * stride);
+      s2 += __ldg(p + (size_t)(r + 64) * stride);
+      s3 += __ldg(p + (size_t)(r + 96) * stride);
+    }
+    for (; r < rows; r += 32) s0 += __ldg(p + (size_t)r * stride);
+  }
+  part[ty][tx] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (ty == 0 && col < cols) {
     float v = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) v += part[i][tx];
-    out[col] = v;
+    for (int i = 0; i < 32; i++) v += part[i][tx];
+    out[col] = accumulate ? fmaf(alpha, v, out[col]) : alpha * v;
   }
 }
 
 static void launch_colsum(cudaStream_t st, const float *m, int rows, int stride, int maps,
-                          int inner, float *out) {
+                          int inner, float *out, float alpha = 1.0f, int accumulate = 0) {
   if (maps == 0) return;
   if (inner == 1)
-    KCNN_LAUNCH(colsum_rows_kernel, ceil_div_u(maps, 32), 256, 0, st, m, rows, maps, stride, out);
+    KCNN_LAUNCH(colsum_rows_kernel, ceil_div_u(maps, 32), 1024, 0, st, m, rows, maps, stride, out, alpha,
+                accumulate);
   else
     KCNN_LAUNCH(colsum_maps_kernel, maps, 256, 0, st, m, rows, stride, inner, out,
                 FastDiv((uint32_t)inner));
@@ -220,6 +231,10 @@ void cudaF_conv2d_fprop(cudaStream_t st, int math, const float *in, MatrixDim id
     tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
     if (tma::conv_fprop(st, cs, in, id.stride, kernel, kd.stride, bias, out, od.stride)) return;
   }
+  if (math == KCNN_MATH_TF32_TC && concat && KH == H && H > 1 && ph == 0 && pw == 0) {
+    tma::ConvFullShape fs = {q.N, H, W, C, KW, G, q.OW};
+    if (tma::conv_full_fprop(st, fs, in, id.stride, kernel, kd.stride, bias, out, od.stride)) return;
+  }
   // A(m = (n, ow, oh), k = (c, kw, kh)) = Xpad[n, c, ow + kw, oh + kh]
   Op33 a = make_op(in,
       make_dec3(q.N, q.OW, q.OH, id.stride, H, 1, -pw * H - ph, 1, 1, -pw, -ph),
@@ -250,7 +265,17 @@ void cudaF_conv2d_dgrad(cudaStream_t st, int math, const float *out_deriv, Matri
   check_int32(odd, "conv out_deriv"); check_int32(idd, "conv in_deriv"); check_int32(kd, "conv kernel");
   if (math == KCNN_MATH_TF32_TC && H == 1 && KH == 1 && ph == 0) {
     tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
-    if (tma::conv_dgrad(st, cs, out_deriv, odd.stride, kernel, kd.stride, in_deriv, idd.stride)) return;
+    tma::ConvBackward b = {};
+    b.out_deriv = out_deriv; b.ld_od = odd.stride; b.kernel = const_cast<float *>(kernel); b.ld_k = kd.stride;
+    b.in_deriv = in_deriv; b.ld_id = idd.stride;
+    if (tma::conv_backward(st, cs, b)) return;
+  }
+  if (math == KCNN_MATH_TF32_TC && KH == H && H > 1 && ph == 0 && pw == 0) {
+    tma::ConvFullShape fs = {q.N, H, W, C, KW, G, q.OW};
+    tma::ConvBackward b = {};
+    b.out_deriv = out_deriv; b.ld_od = odd.stride; b.kernel = const_cast<float *>(kernel); b.ld_k = kd.stride;
+    b.in_deriv = in_deriv; b.ld_id = idd.stride;
+    if (tma::conv_full_backward(st, fs, b)) return;
   }
   if (q.OH == 1) {
     // Full-height kernel (every layer of egs/exp/nnet/nnet.config): out_deriv has one row
@@ -309,11 +334,21 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   const int M = q.ks * C, K = q.N * q.P;
   if (math == KCNN_MATH_TF32_TC && H == 1 && KH == 1 && ph == 0) {
     tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
-    float *bpart = nullptr;
-    int brows = 0;
-    if (tma::conv_wgrad(st, cs, in_value, ivd.stride, out_deriv, odd.stride, kernel_grad, kgd.stride, nullptr,
-                        nullptr, bias_grad ? &bpart : nullptr, &brows)) {
-      if (bias_grad) launch_colsum(st, bpart, brows, G, G, 1, bias_grad);
+    tma::ConvBackward b = {};
+    b.in_value = in_value; b.ld_iv = ivd.stride; b.out_deriv = out_deriv; b.ld_od = odd.stride;
+    b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride; b.want_bias = bias_grad != nullptr;
+    if (tma::conv_backward(st, cs, b)) {
+      if (bias_grad) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
+      return;
+    }
+  }
+  if (math == KCNN_MATH_TF32_TC && KH == H && H > 1 && ph == 0 && pw == 0) {
+    tma::ConvFullShape fs = {q.N, H, W, C, KW, G, q.OW};
+    tma::ConvBackward b = {};
+    b.in_value = in_value; b.ld_iv = ivd.stride; b.out_deriv = out_deriv; b.ld_od = odd.stride;
+    b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride; b.want_bias = bias_grad != nullptr;
+    if (tma::conv_full_backward(st, fs, b)) {
+      if (bias_grad) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
       return;
     }
   }
@@ -334,6 +369,55 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   else if (a_fast_k && !b_fast_k) launch_gemm<true, false, true>(st, math, a, b, o, M, G, K, true, ws);
   else if (!a_fast_k && b_fast_k) launch_gemm<false, true, true>(st, math, a, b, o, M, G, K, true, ws);
   else                            launch_gemm<false, false, true>(st, math, a, b, o, M, G, K, true, ws);
+}
+
+int cudaF_conv2d_backward(cudaStream_t st, int math, const float *in_value, MatrixDim ivd,
+                          const float *out_deriv, MatrixDim odd, float *kernel, MatrixDim kd,
+                          float *in_deriv, MatrixDim idd, float *kernel_grad, MatrixDim kgd,
+                          float *bias_grad, float *prev_grad, MatrixDim pd, float *bias, int apply,
+                          float momentum, float a_decay, float a_grad, int H, int W, int C, int ph,
+                          int pw, int KH, int KW, int G) {
+  ConvGeom q = conv_geom(odd.rows, H, W, C, ph, pw, KH, KW, G);
+  if (q.N == 0 || q.P <= 0 || G == 0 || C == 0) return 0;
+  if (math != KCNN_MATH_TF32_TC) return 0;
+  const bool time_axis = H == 1 && KH == 1 && ph == 0;
+  const bool full_height = KH == H && H > 1 && ph == 0 && pw == 0;
+  if (!time_axis && !full_height) return 0;
+  tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
+  tma::ConvFullShape fs = {q.N, H, W, C, KW, G, q.OW};
+  tma::SgdCoef coef = {momentum, a_decay, a_grad};
+  tma::ConvBackward b = {};
+  b.in_value = in_value; b.ld_iv = ivd.stride; b.out_deriv = out_deriv; b.ld_od = odd.stride;
+  b.kernel = kernel; b.ld_k = kd.stride; b.in_deriv = in_deriv; b.ld_id = idd.stride;
+  b.want_bias = true;
+  if (apply) {
+    b.prev = prev_grad; b.ld_p = pd.stride; b.sgd = &coef;
+  } else {
+    b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride;
+  }
+  if (!(time_axis ? tma::conv_backward(st, cs, b) : tma::conv_full_backward(st, fs, b))) return 0;
+  if (apply) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias, a_grad, 1);   // bias += lr * db
+  else       launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
+  return 1;
+}
+
+int cudaF_affine_wgrad_sgd(cudaStream_t st, int math, const float *in_value, MatrixDim ivd,
+                           const float *out_deriv, MatrixDim odd, float *w, MatrixDim wd,
+                           float *prev_grad, MatrixDim pd, float *bias, float momentum,
+                           float a_decay, float a_grad) {
+  const int M = odd.cols, N = ivd.cols, K = ivd.rows;
+  if (M == 0 || N == 0 || K == 0) return 0;
+  if (!(math == KCNN_MATH_TF32_TC && tma::enabled())) return 0;
+  if (pd.stride != wd.stride || !host_aligned16(prev_grad) || !host_aligned16(w) || (wd.stride & 3)) return 0;
+  tma::Epilogue epi;
+  epi.mode = tma::EPI_SGD; epi.aux = prev_grad;
+  epi.sgd.momentum = momentum; epi.sgd.a_decay = a_decay; epi.sgd.a_grad = a_grad;
+  // bias first: it reads out_deriv only, and nothing below touches the bias
+  if (!tma::gemm<true, true>(st, tma::Matrix{out_deriv, K, M, odd.stride}, tma::Matrix{in_value, K, N, ivd.stride},
+                             M, N, K, w, wd.stride, epi, true))
+    return 0;
+  launch_colsum(st, out_deriv, odd.rows, odd.stride, M, 1, bias, a_grad, 1);
+  return 1;
 }
 
 void cudaF_sum_rows_per_map(cudaStream_t st, const float *m, MatrixDim md, int inner, float *out) {

@@ -230,9 +230,36 @@ void ConvolutionComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
   ConvolutionComponent *to_update = dynamic_cast<ConvolutionComponent *>(to_update_in);
   KALDI_ASSERT(out_deriv.NumCols() == OutputDim());
   CuDevice::Instantiate().RequireEnabled("ConvolutionComponent::Backprop");
+  if (in_deriv != NULL &&
+      (in_deriv->NumRows() != out_deriv.NumRows() || in_deriv->NumCols() != InputDim()))
+    in_deriv->Resize(out_deriv.NumRows(), InputDim(), kUndefined);
+  if (to_update == this && out_deriv.NumRows() > 0) {
+    // Ordinary SGD (to_update is the component itself): input gradient, weight gradient,
+    // bias gradient and -- unless the update is deferred for the data-parallel all-reduce --
+    // the momentum / weight-decay step, from one staging copy of out_deriv and in_value.
+    ConvolutionComponent *self = to_update;
+    self->EnsureGradBuffers();
+    const bool apply = !deferred_;
+    double learning_rate = learning_rate_ / out_deriv.NumRows();
+    BaseFloat a_decay = -1 * learning_rate * weight_decay_, a_grad = learning_rate;
+    ::MatrixDim gd = {self->w_grad_.rows, self->w_grad_.cols, self->w_grad_.stride};
+    ::MatrixDim idd = {0, 0, 0};
+    if (in_deriv != NULL) idd = in_deriv->Dim();
+    Timer tim;
+    int done = cudaF_conv2d_backward(
+        Str(), Math(), in_value.Data(), in_value.Dim(), out_deriv.Data(), out_deriv.Dim(),
+        self->linear_params_.Data(), self->linear_params_.Dim(),
+        in_deriv != NULL ? in_deriv->Data() : NULL, idd, self->w_grad_.data, gd, self->b_grad_.data,
+        self->prev_grad_.Data(), self->prev_grad_.Dim(), self->bias_params_.Data(), apply ? 1 : 0,
+        momentum_, a_decay, a_grad, in_height_, in_width_, in_channel_, in_pad_height_, in_pad_width_,
+        kernel_height_, kernel_width_, group_);
+    if (done) {
+      CU_SAFE_CALL(cudaGetLastError());
+      CuDevice::Instantiate().AccuProfile(__func__, tim.Elapsed());
+      return;
+    }
+  }
   if (in_deriv != NULL) {
-    if (in_deriv->NumRows() != out_deriv.NumRows() || in_deriv->NumCols() != InputDim())
-      in_deriv->Resize(out_deriv.NumRows(), InputDim(), kUndefined);
     Timer tim;
     cudaF_conv2d_dgrad(Str(), Math(), out_deriv.Data(), out_deriv.Dim(), linear_params_.Data(),
                        linear_params_.Dim(), in_deriv->Data(), in_deriv->Dim(), in_height_, in_width_,

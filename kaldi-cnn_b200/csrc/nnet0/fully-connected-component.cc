@@ -12,6 +12,7 @@ namespace cnsl {
 namespace nnet0 {
 
 static inline cudaStream_t Str() { return CuDevice::Instantiate().Stream(); }
+static inline int Math() { return CuDevice::Instantiate().MathMode(); }
 
 // reference :980-999 (no <IsGradient> in this component's stream)
 void FullyConnectedComponent::Read(std::istream &is, bool binary) {
@@ -166,6 +167,21 @@ void FullyConnectedComponent::ApplyGradient(int32 total_num_samples) {
 // reference :1133-1150
 void FullyConnectedComponent::UpdateSimple(const CuMatrixBase<BaseFloat> &in_value,
                                            const CuMatrixBase<BaseFloat> &out_deriv) {
+  if (!deferred_ && in_value.NumRows() > 0) {
+    // Single-GPU step: the update runs in the epilogue of the weight-gradient GEMM, the
+    // gradient matrix is never written (16 instead of 24 bytes of HBM traffic per weight).
+    double learning_rate = learning_rate_ / in_value.NumRows();
+    BaseFloat a_decay = -1 * learning_rate * weight_decay_, a_grad = learning_rate;
+    if (prev_grad_.NumRows() != linear_params_.NumRows() || prev_grad_.NumCols() != linear_params_.NumCols())
+      prev_grad_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kSetZero);
+    if (cudaF_affine_wgrad_sgd(Str(), Math(), in_value.Data(), in_value.Dim(), out_deriv.Data(),
+                               out_deriv.Dim(), linear_params_.Data(), linear_params_.Dim(),
+                               prev_grad_.Data(), prev_grad_.Dim(), bias_params_.Data(), momentum_,
+                               a_decay, a_grad)) {
+      CU_SAFE_CALL(cudaGetLastError());
+      return;
+    }
+  }
   ComputeGradient(in_value, out_deriv);
   if (!deferred_) ApplyGradient(in_value.NumRows());
 }

@@ -181,25 +181,33 @@ bool ParseFromString(const std::string &name, std::string *string, std::vector<i
 
 namespace {
 // Column sums of y and of [y > 0] over the rows, added to the double accumulators.
-__global__ void __launch_bounds__(256)
+// A block owns 32 adjacent columns: 32 row-threads x 128-byte row segments.
+__global__ void __launch_bounds__(1024)
 nonlin_stats_kernel(const float *__restrict__ y, ::MatrixDim d, double *value_sum,
                     double *deriv_sum) {
-  __shared__ float pv[8][33], pd[8][33];
+  __shared__ float pv[32][33], pd[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
-  float sv = 0.0f, sd = 0.0f;
-  if (col < d.cols)
-    for (int r = ty; r < d.rows; r += 8) {
-      float v = __ldg(y + (size_t)r * d.stride + col);
-      sv += v;
-      sd += v > 0.0f ? 1.0f : 0.0f;
+  float sv0 = 0.0f, sv1 = 0.0f, sd0 = 0.0f, sd1 = 0.0f;
+  if (col < d.cols) {
+    const float *p = y + col;
+    int r = ty;
+    for (; r + 32 < d.rows; r += 64) {
+      float a = __ldg(p + (size_t)r * d.stride), b = __ldg(p + (size_t)(r + 32) * d.stride);
+      sv0 += a; sd0 += a > 0.0f ? 1.0f : 0.0f;
+      sv1 += b; sd1 += b > 0.0f ? 1.0f : 0.0f;
     }
-  pv[ty][tx] = sv; pd[ty][tx] = sd;
+    for (; r < d.rows; r += 32) {
+      float a = __ldg(p + (size_t)r * d.stride);
+      sv0 += a; sd0 += a > 0.0f ? 1.0f : 0.0f;
+    }
+  }
+  pv[ty][tx] = sv0 + sv1; pd[ty][tx] = sd0 + sd1;
   __syncthreads();
   if (ty == 0 && col < d.cols) {
     float a = 0.0f, b = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { a += pv[i][tx]; b += pd[i][tx]; }
+    for (int i = 0; i < 32; i++) { a += pv[i][tx]; b += pd[i][tx]; }
     value_sum[col] += (double)a;
     if (deriv_sum) deriv_sum[col] += (double)b;
   }
@@ -266,7 +274,7 @@ void NonlinearComponent::UpdateStats(const CuMatrixBase<BaseFloat> &out_value, b
   }
   count_ += out_value.NumRows();
   if (out_value.NumRows() == 0) return;
-  KCNN_LAUNCH(nonlin_stats_kernel, kcnn::ceil_div_u(dim_, 32), 256, 0, Str(), out_value.Data(),
+  KCNN_LAUNCH(nonlin_stats_kernel, kcnn::ceil_div_u(dim_, 32), 1024, 0, Str(), out_value.Data(),
               out_value.Dim(), stats_, relu_deriv ? stats_ + dim_ : (double *)NULL);
 }
 

@@ -1,0 +1,57 @@
+"""Data-parallel training step over minibatch rows.
+
+Replaces the reference's file-based multi-job averaging (nnet-am-average once per iteration,
+egs/steps/nnet0/train_conv_dropout.sh:323-341) by a per-step gradient all-reduce:
+
+  * rank r owns rows [r*N/P, (r+1)*N/P) of the global minibatch (`shard_rows`)
+  * every updatable component runs Backprop with the update DEFERRED and leaves its
+    un-normalised dW, db in one bucket of a gradient arena
+  * buckets are all-reduced (sum) top layer first, each as soon as its layer's backward has
+    been issued, so the transfer overlaps the rest of the backward
+  * every rank then applies the identical momentum / weight-decay step with
+    lr = learning_rate / N_global (the reference normalises by the minibatch rows,
+    nnet0/nnet-component-nnet0.cc:767, 1136) -- P ranks x N/P rows reproduce the 1-rank N-row
+    step up to floating-point summation order.
+
+Host logic only: `net` is anything with the Nnet interface of components.py (the CUDA model on
+a GPU box, an oracle-backed model in the world-size-2 gloo test).
+"""
+
+
+def shard_rows(num_rows, rank, world):
+    """[begin, end) of the global minibatch rows rank `rank` of `world` processes."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world %r/%r" % (rank, world))
+    base, rem = divmod(num_rows, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def bucket_order(updatable):
+    """Components in the order their gradients become available (top layer first)."""
+    return sorted(updatable, reverse=True)
+
+
+class DataParallelStep:
+    def __init__(self, net, arena, updatable, dist=None, world=1):
+        self.net, self.arena, self.dist, self.world = net, arena, dist, world
+        self.updatable = bucket_order(updatable)
+        if world > 1 and dist is None:
+            raise ValueError("world > 1 needs a torch.distributed module / process group")
+
+    def __call__(self, feats, labels, rows_global):
+        net = self.net
+        net.forward(feats)
+        net.objf_and_deriv(labels)
+        works, hi = [], net.num_components - 1
+        for c in self.updatable:
+            net.backward(hi, c)                       # layers hi .. c, update deferred
+            off, ln = net.gradient_bucket(c)
+            if self.world > 1 and ln > 0:
+                works.append(self.dist.all_reduce(self.arena[off:off + ln], async_op=True))
+            hi = c - 1
+        if hi >= 0:
+            net.backward(hi, 0)
+        for w in works:
+            w.wait()
+        net.apply_gradients(rows_global)

@@ -1,0 +1,161 @@
+"""Data-parallel host logic (kaldi-cnn_b200/dp.py) on CPU: two gloo ranks, each with half of
+the minibatch, must reproduce the single-process step.  The compute behind the Nnet
+interface is the CPU oracle here (the CUDA model implements the same interface on a GPU box;
+tests/test_gpu_components.py covers that side)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import kaldi_cnn_b200  # noqa: E402,F401
+from kaldi_cnn_b200.dp import DataParallelStep, shard_rows  # noqa: E402
+
+H, W, C, KH, KW, G = 1, 10, 8, 1, 3, 12
+OW = W - KW + 1
+DIN, DOUT = G * OW, 9
+LR, WD, MOM = 0.02, 0.0002, 0.9
+
+
+class OracleNet:
+    """conv -> relu -> fc -> softmax with the Nnet interface DataParallelStep drives."""
+    num_components = 4
+
+    def __init__(self, seed=3):
+        from oracle import oracle
+        self.o = oracle
+        rng = np.random.default_rng(seed)
+        self.k = (rng.standard_normal((KH * KW * C, G)) * 0.1).astype(np.float32)
+        self.kb = rng.standard_normal(G).astype(np.float32)
+        self.kp = np.zeros_like(self.k)
+        self.w = (rng.standard_normal((DOUT, DIN)) * 0.1).astype(np.float32)
+        self.wb = np.full(DOUT, 0.1, np.float32)
+        self.wp = np.zeros_like(self.w)
+        sizes = [self.k.size + G, 0, self.w.size + DOUT, 0]
+        self.off = np.concatenate([[0], np.cumsum(sizes)])
+        self.arena = torch.zeros(int(self.off[-1]), dtype=torch.float32)
+        self.objf = 0.0
+
+    def forward(self, x):
+        o = self.o
+        self.a0 = x
+        self.a1 = o.conv_propagate(x, self.k, self.kb, H, W, C, 0, 0, KH, KW, G)
+        self.a2 = np.maximum(self.a1, 0)
+        self.a3 = o.fc_propagate(self.a2, self.w, self.wb)
+        self.a4 = o.softmax_propagate(self.a3)
+
+    def objf_and_deriv(self, labels):
+        n = self.a4.shape[0]
+        self.objf += float(np.log(self.a4[np.arange(n), labels]).sum())
+        d = np.zeros_like(self.a4)
+        d[np.arange(n), labels] = 1.0 / self.a4[np.arange(n), labels]
+        self.d = d
+
+    def gradient_bucket(self, c):
+        return int(self.off[c]), int(self.off[c + 1] - self.off[c])
+
+    def _put(self, c, wgrad, bgrad):
+        off, _ = self.gradient_bucket(c)
+        flat = np.concatenate([wgrad.ravel(), bgrad.ravel()]).astype(np.float32)
+        self.arena[off:off + flat.size] = torch.from_numpy(flat)
+
+    def backward(self, last, first):
+        o = self.o
+        for c in range(last, first - 1, -1):
+            d = self.d
+            if c == 3:
+                self.d = o.softmax_backprop(self.a4, d)
+            elif c == 2:
+                self._put(2, d.T.astype(np.float64) @ self.a2.astype(np.float64), d.sum(0))
+                self.d = o.fc_backprop(d, self.w)
+            elif c == 1:
+                self.d = np.where(self.a2 > 0, d, 0).astype(np.float32)
+            else:
+                _, _, _, g, bg = o.conv_update(self.a0, d, self.k, self.kb, self.kp, H, W, C, 0, 0, KH, KW, G,
+                                               LR, WD, MOM, apply=False)
+                self._put(0, g, bg)
+                self.d = o.conv_backprop(d, self.k, H, W, C, 0, 0, KH, KW, G)
+
+    def apply_gradients(self, rows):
+        lr = np.float32(LR) / np.float32(rows)
+        a = self.arena.numpy()
+        for c, (w, b, p) in ((0, (self.k, self.kb, self.kp)), (2, (self.w, self.wb, self.wp))):
+            off, _ = self.gradient_bucket(c)
+            g = a[off:off + w.size].reshape(w.shape)
+            bg = a[off + w.size:off + w.size + b.size]
+            p *= np.float32(MOM)
+            p += np.float32(-lr * WD) * w
+            p += lr * g
+            w += p
+            b += lr * bg
+
+
+def _data(n, seed=11):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((n, H * W * C)).astype(np.float32), rng.integers(0, DOUT, n)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_global, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x, y = _data(n_global)
+        b, e = shard_rows(n_global, rank, world)
+        net = OracleNet()
+        step = DataParallelStep(net, net.arena, [0, 2], dist, world)
+        for _ in range(2):
+            step(x[b:e], y[b:e], n_global)
+        out[rank] = (net.k.copy(), net.kb.copy(), net.w.copy(), net.wb.copy(), net.kp.copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_rows_partitions_exactly():
+    for n in (1, 7, 256, 513):
+        for world in (1, 2, 3, 8):
+            spans = [shard_rows(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_rows(4, 2, 2)
+
+
+def test_world_size_2_gloo_matches_single_process():
+    n = 12
+    x, y = _data(n)
+    ref = OracleNet()
+    single = DataParallelStep(ref, ref.arena, [0, 2], None, 1)
+    for _ in range(2):
+        single(x, y, n)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
+    for rank in (0, 1):
+        for got, want in zip(out[rank], (ref.k, ref.kb, ref.w, ref.wb, ref.kp)):
+            assert np.abs(got - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
+    for a, b in zip(out[0], out[1]):                  # replicas stay bit-identical
+        assert np.array_equal(a, b)
+
+
+def test_world_gt_1_needs_a_process_group():
+    net = OracleNet()
+    with pytest.raises(ValueError):
+        DataParallelStep(net, net.arena, [0, 2], None, 2)
