@@ -156,25 +156,27 @@ struct ConvRowsProb {
 
   __device__ __forceinline__ void kb_range(int &b, int &e) const { b = 0; e = taps * inner_blocks; }
   __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)(nb * R * 128 + B_STAGE_BYTES); }
+  template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
-                                       const CUtensorMap *ma, const CUtensorMap *mb) const {
+                                       const CUtensorMap *ma, const CUtensorMap *mb, int mt, int nt) const {
     uint32_t t, ib;
     div_inner.divmod((uint32_t)kb, t, ib);
     const int i0 = (int)ib * 32;
-    const int n0 = blockIdx.x * nb, col0 = blockIdx.y * BN;
-    tma_load_3d(a_addr, ma, i0, a_w0 + a_wstep * (int)t, n0, bar);
+    const int n0 = mt * nb, col0 = nt * BN;
+    tma_load_3d<kPair>(a_addr, ma, i0, a_w0 + a_wstep * (int)t, n0, bar);
     if (kBMn) {
 #pragma unroll
-      for (int i = 0; i < BN / 32; i++) tma_load_3d(b_addr + i * ATOM_BYTES, mb, col0 + 32 * i, (int)t, i0, bar);
+      for (int i = 0; i < BN / 32; i++) tma_load_3d<kPair>(b_addr + i * ATOM_BYTES, mb, col0 + 32 * i, (int)t, i0, bar);
     } else {
-      tma_load_3d(b_addr, mb, i0, (int)t, col0, bar);
+      tma_load_3d<kPair>(b_addr, mb, i0, (int)t, col0, bar);
     }
   }
-  __device__ __forceinline__ void prefetch(int) const {}
-  __device__ __forceinline__ void store(const float *stage, int tid) const {
-    const int col0 = blockIdx.y * BN;
-    store_maps_transposed(stage, tid, blockIdx.x * nb, nb, R, col0, min(BN, out_maps - col0), num_samples, out,
-                          ldo, bias, div_r);
+  __device__ __forceinline__ void prefetch(int, int, int) const {}
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+    const int col0 = nt * BN;
+    if (col0 >= out_maps) return;
+    store_maps_transposed(stage, tid, mt * nb, nb, R, col0, min(BN, out_maps - col0), num_samples, out, ldo, bias,
+                          div_r);
   }
 };
 
@@ -198,21 +200,22 @@ struct ConvFullFpropProb {
   int total_kb;            // C * j_blocks
   __device__ __forceinline__ void kb_range(int &b, int &e) const { b = 0; e = total_kb; }
   __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)(nb * OW * 128 + B_STAGE_BYTES); }
+  template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
-                                       const CUtensorMap *ma, const CUtensorMap *mb) const {
+                                       const CUtensorMap *ma, const CUtensorMap *mb, int mt, int nt) const {
     uint32_t c, jb;
     div_jb.divmod((uint32_t)kb, c, jb);
     const int j0 = (int)jb * 32;
-    const int n0 = blockIdx.x * nb, g0 = blockIdx.y * BN;
-    tma_load_4d(a_addr, ma, j0, 0, (int)c, n0, bar);
+    const int n0 = mt * nb, g0 = nt * BN;
+    tma_load_4d<kPair>(a_addr, ma, j0, 0, (int)c, n0, bar);
 #pragma unroll
-    for (int i = 0; i < BN / 32; i++) tma_load_2d(b_addr + i * ATOM_BYTES, mb, g0 + 32 * i, (int)c * ks + j0, bar);
+    for (int i = 0; i < BN / 32; i++) tma_load_2d<kPair>(b_addr + i * ATOM_BYTES, mb, g0 + 32 * i, (int)c * ks + j0, bar);
   }
-  __device__ __forceinline__ void prefetch(int) const {}
-  __device__ __forceinline__ void store(const float *stage, int tid) const {
-    const int g0 = blockIdx.y * BN;
-    store_maps_transposed(stage, tid, blockIdx.x * nb, nb, OW, g0, min(BN, G - g0), num_samples, out, ldo, bias,
-                          div_ow);
+  __device__ __forceinline__ void prefetch(int, int, int) const {}
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+    const int g0 = nt * BN;
+    if (g0 >= G) return;
+    store_maps_transposed(stage, tid, mt * nb, nb, OW, g0, min(BN, G - g0), num_samples, out, ldo, bias, div_ow);
   }
 };
 
@@ -230,17 +233,18 @@ struct ConvFullDgradProb {
 
   __device__ __forceinline__ void kb_range(int &b, int &e) const { b = 0; e = total_kb; }
   __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)((nb * W + nbc * H) * 128); }
+  template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
-                                       const CUtensorMap *ma, const CUtensorMap *mb) const {
+                                       const CUtensorMap *ma, const CUtensorMap *mb, int mt, int nt) const {
     uint32_t kw, gb;
     div_gb.divmod((uint32_t)kb, kw, gb);
     const int g0 = (int)gb * 32;
-    tma_load_3d(a_addr, ma, g0, -(int)kw, blockIdx.x * nb, bar);
-    tma_load_3d(b_addr, mb, g0, (int)kw * H, blockIdx.y * nbc, bar);
+    tma_load_3d<kPair>(a_addr, ma, g0, -(int)kw, mt * nb, bar);
+    tma_load_3d<kPair>(b_addr, mb, g0, (int)kw * H, nt * nbc, bar);
   }
-  __device__ __forceinline__ void prefetch(int) const {}
-  __device__ __forceinline__ void store(const float *stage, int tid) const {
-    const int n0 = blockIdx.x * nb, c0 = blockIdx.y * nbc;
+  __device__ __forceinline__ void prefetch(int, int, int) const {}
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+    const int n0 = mt * nb, c0 = nt * nbc;
     const int chans = min(nbc, C - c0);
     const int hw = H * W;
     for (int s = 0; s < nb; s++) {
@@ -295,34 +299,35 @@ struct ConvWgradProb {
     if (e < b) e = b;
   }
   __device__ __forceinline__ uint32_t tx_bytes() const { return STAGE_BYTES; }
+  template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
-                                       const CUtensorMap *ma, const CUtensorMap *mb) const {
+                                       const CUtensorMap *ma, const CUtensorMap *mb, int mt, int nt) const {
     uint32_t ow, nblk;
     div_nb.divmod((uint32_t)kb, ow, nblk);
     const int n0 = (int)nblk * 32;
-    const int m0 = blockIdx.x * BM, g0 = blockIdx.y * BN;
+    const int m0 = mt * BM, g0 = nt * BN;
 #pragma unroll
     for (int i = 0; i < BM / 32; i++) {
       uint32_t q, r;
       div_c.divmod((uint32_t)(m0 + 32 * i), q, r);
-      if (kFull) tma_load_4d(a_addr + i * ATOM_BYTES, ma, (int)r, (int)ow, (int)q, n0, bar);      // (j, ow, c, n)
-      else       tma_load_3d(a_addr + i * ATOM_BYTES, ma, (int)r, (int)ow + (int)q - pw, n0, bar); // (c, w, n)
+      if (kFull) tma_load_4d<kPair>(a_addr + i * ATOM_BYTES, ma, (int)r, (int)ow, (int)q, n0, bar);      // (j, ow, c, n)
+      else       tma_load_3d<kPair>(a_addr + i * ATOM_BYTES, ma, (int)r, (int)ow + (int)q - pw, n0, bar); // (c, w, n)
     }
 #pragma unroll
-    for (int i = 0; i < BN / 32; i++) tma_load_3d(b_addr + i * ATOM_BYTES, mb, g0 + 32 * i, (int)ow, n0, bar);
+    for (int i = 0; i < BN / 32; i++) tma_load_3d<kPair>(b_addr + i * ATOM_BYTES, mb, g0 + 32 * i, (int)ow, n0, bar);
   }
-  __device__ __forceinline__ void prefetch(int tid) const {
+  __device__ __forceinline__ void prefetch(int tid, int mt, int nt) const {
     if (kEpi == EPI_SGD) {
       if (kFull) {
-        prefetch_tile_l2(tid, blockIdx.x * BM, blockIdx.y * BN, M, G, out, aux, ldo, IdentityRow());
+        prefetch_tile_l2(tid, mt * BM, nt * BN, M, G, out, aux, ldo, IdentityRow());
       } else {
         KernelRow rm; rm.div_c = div_c; rm.KW = KW;
-        prefetch_tile_l2(tid, blockIdx.x * BM, blockIdx.y * BN, M, G, out, aux, ldo, rm);
+        prefetch_tile_l2(tid, mt * BM, nt * BN, M, G, out, aux, ldo, rm);
       }
     }
   }
-  __device__ __forceinline__ void store(const float *stage, int tid) const {
-    const int m0 = blockIdx.x * BM, g0 = blockIdx.y * BN;
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+    const int m0 = mt * BM, g0 = nt * BN;
     if (kEpi == EPI_PARTIAL) {
       store_rows<EPI_STORE>(stage, tid, m0, g0, M, G, workspace + (size_t)blockIdx.z * M * G, G, nullptr,
                             nullptr, sgd, IdentityRow());

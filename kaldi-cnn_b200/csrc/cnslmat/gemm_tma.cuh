@@ -57,7 +57,7 @@ using tc::tmem_ld32;
 using tc::umma_commit;
 using tc::umma_tf32;
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 4;
 constexpr int B_STAGE_BYTES = BN * BK * 4;
@@ -65,34 +65,43 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ATOM_BYTES = BK * 128;          // one MN-major box: 32 k-rows x 128 bytes
 constexpr int PITCH = BN + 4;                 // staging row pitch (floats): conflict-free v4 stores
 constexpr int STAGING_BYTES = 128 * PITCH * 4;
-constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-constexpr int DATA_BYTES = RING_BYTES > STAGING_BYTES ? RING_BYTES : STAGING_BYTES;
-constexpr int BAR_OFFSET = DATA_BYTES;
-constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+// kStages = 3: 2 CTAs per SM (6 stages in flight per SM, one CTA's epilogue under the other's
+// main loop) for grids of more than one wave; kStages = 6: 1 CTA per SM with the same bytes
+// in flight, for grids that leave at most one CTA per SM anyway (M = 512 FC layers, the
+// convolutions) -- with 3 stages those are latency-bound (measured 330 vs 600 TFLOP/s).
+template <int kStages>
+struct Ring {
+  static constexpr int RING_BYTES = kStages * STAGE_BYTES;
+  static constexpr int DATA_BYTES = RING_BYTES > STAGING_BYTES ? RING_BYTES : STAGING_BYTES;
+  static constexpr int BAR_OFFSET = DATA_BYTES;
+  static constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * kStages + 1) * 8 + 16 + 1024;
+};
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
-}
+// kPair: cta_group::2 form -- the box lands in THIS CTA's shared memory, the bytes are
+// credited to the mbarrier of the pair's leader CTA (`bar` is then a shared::cluster address).
+#define KCNN_TMA_LOAD(NAME, DIMS, COORD_FMT, COORD_ARGS, COORD_OPS, BAR_IDX)                                   \
+  template <bool kPair>                                                                                       \
+  __device__ __forceinline__ void NAME(uint32_t dst, const CUtensorMap *map, COORD_ARGS, uint32_t bar) {      \
+    if (kPair)                                                                                                \
+      asm volatile("cp.async.bulk.tensor." DIMS ".cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes " \
+                   "[%0], [%1, " COORD_FMT "], [%" BAR_IDX "];" ::"r"(dst), "l"(map), COORD_OPS, "r"(bar)      \
+                   : "memory");                                                                               \
+    else                                                                                                      \
+      asm volatile("cp.async.bulk.tensor." DIMS ".shared::cluster.global.mbarrier::complete_tx::bytes "       \
+                   "[%0], [%1, " COORD_FMT "], [%" BAR_IDX "];" ::"r"(dst), "l"(map), COORD_OPS, "r"(bar)      \
+                   : "memory");                                                                               \
+  }
+#define KCNN_COMMA ,
+KCNN_TMA_LOAD(tma_load_2d, "2d", "{%2, %3}", int c0 KCNN_COMMA int c1, "r"(c0) KCNN_COMMA "r"(c1), "4")
+KCNN_TMA_LOAD(tma_load_3d, "3d", "{%2, %3, %4}", int c0 KCNN_COMMA int c1 KCNN_COMMA int c2,
+              "r"(c0) KCNN_COMMA "r"(c1) KCNN_COMMA "r"(c2), "5")
+KCNN_TMA_LOAD(tma_load_4d, "4d", "{%2, %3, %4, %5}", int c0 KCNN_COMMA int c1 KCNN_COMMA int c2 KCNN_COMMA int c3,
+              "r"(c0) KCNN_COMMA "r"(c1) KCNN_COMMA "r"(c2) KCNN_COMMA "r"(c3), "6")
+#undef KCNN_COMMA
+#undef KCNN_TMA_LOAD
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -124,17 +133,64 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// Problem interface:
+// Problem interface (mt / nt: 128-row / 128-column tile indices):
 //   static constexpr bool kAMn, kBMn
-//   void kb_range(int &begin, int &end) const          K-blocks of this CTA
-//   uint32_t tx_bytes() const                           bytes one stage's TMA boxes deliver
-//   void load(kb, a_addr, b_addr, bar, &map_a, &map_b)  issue the boxes of K-block kb
-//   void prefetch(int tid) const                        epilogue threads, before the accumulator is ready
-//   void store(const float *stage, int tid) const       128 epilogue threads, stage[128][PITCH]
-template <class Prob>
-__global__ void __launch_bounds__(THREADS, 2)
+//   void kb_range(int &begin, int &end) const                    K-blocks of this CTA
+//   uint32_t tx_bytes() const                                     bytes one CTA's boxes of a stage deliver
+//   void load<kPair>(kb, a_addr, b_addr, bar, &map_a, &map_b, mt, nt)   A rows of tile mt, B rows of tile nt
+//   void prefetch(tid, mt, nt) const                              epilogue threads, before the accumulator is ready
+//   void store(stage, tid, mt, nt) const                          128 epilogue threads, stage[128][PITCH]
+//
+// kPair = false: one CTA computes the 128 x 128 tile (blockIdx.x, blockIdx.y).
+// kPair = true:  a cluster of two CTAs (one TPC) computes a 256 x 256 tile with
+//   tcgen05.mma.cta_group::2 (M = 256, N = 256): CTA r stages A rows of tile 2*pair + r
+//   (= blockIdx.x) and the B rows of column tile 2*blockIdx.y + r -- 32 KB per K-block per
+//   SM for twice the FLOPs per SM, which is what lifts these TF32 GEMMs off the ~40 B/clk
+//   per-SM L2 -> shared-memory ingress limit (profiles/).  The leader CTA issues the MMAs
+//   for both; its tcgen05.commit multicasts the stage release and the "accumulator ready"
+//   signal to both CTAs; each CTA drains its own 128 lanes x 256 columns of TMEM.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+template <class Prob, bool kPair, int STAGES>
+__global__ void __launch_bounds__(THREADS, STAGES <= 3 ? 2 : 1)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const Prob prob) {
+  constexpr int kCols = kPair ? 2 * BN : BN;        // TMEM columns = accumulator columns per CTA
+  constexpr int BAR_OFFSET = Ring<STAGES>::BAR_OFFSET;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -145,28 +201,38 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem_gen + BAR_OFFSET + 8 * (2 * STAGES + 1));
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int mt = blockIdx.x;
+  const int nt_load = kPair ? 2 * (int)blockIdx.y + (int)rank : (int)blockIdx.y;
   int kb_begin, kb_end;
   prob.kb_range(kb_begin, kb_end);
   const int num_kb = kb_end - kb_begin;
 
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_ptr_smem)), "r"((uint32_t)kCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_ptr_smem)), "r"((uint32_t)kCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (t == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), kPair ? 2 : 1);      // pair: one arrive.expect_tx per CTA's producer
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -178,15 +244,17 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int s = i % STAGES;
         if (i >= STAGES) mbar_wait(empty_bar(s), ((i / STAGES) - 1) & 1);
         const uint32_t a_addr = smem_base + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), tx);
-        prob.load(kb_begin + i, a_addr, a_addr + A_STAGE_BYTES, full_bar(s), &map_a, &map_b);
+        // the full barrier that counts: this CTA's, or the pair leader's
+        const uint32_t fb = kPair ? map_to_cta(full_bar(s), 0) : full_bar(s);
+        if (kPair) mbar_expect_tx_cluster(fb, tx); else mbar_expect_tx(fb, tx);
+        prob.template load<kPair>(kb_begin + i, a_addr, a_addr + A_STAGE_BYTES, fb, &map_a, &map_b, mt, nt_load);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer --
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, Prob::kAMn, Prob::kBMn);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(kPair ? 2 * BM : BM, kCols, Prob::kAMn, Prob::kBMn);
       for (int i = 0; i < num_kb; i++) {
         const int s = i % STAGES;
         mbar_wait(full_bar(s), (i / STAGES) & 1);
@@ -201,47 +269,58 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           // groups) in an MN-major atom; the start-address field is in 16-byte units
           const uint64_t ad = adesc + (Prob::kAMn ? 64 * k : 2 * k);
           const uint64_t bd = bdesc + (Prob::kBMn ? 64 * k : 2 * k);
-          umma_tf32(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          if (kPair) umma_tf32_pair(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          else       umma_tf32(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
         }
-        umma_commit(empty_bar(s));
+        if (kPair) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
       }
-      umma_commit(accum_bar);
+      if (kPair) umma_commit_pair(accum_bar); else umma_commit(accum_bar);
     }
     __syncwarp();
   } else {
     // ----------------------------------------------------------------- epilogue --
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     float *stage = reinterpret_cast<float *>(smem_gen);
-    prob.prefetch(t - 64);
+    const int tid = t - 64;
+#pragma unroll
+    for (int h = 0; h < kCols / BN; h++) prob.prefetch(tid, mt, kPair ? 2 * (int)blockIdx.y + h : (int)blockIdx.y);
     if (num_kb > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
-    // TMEM -> registers -> padded staging: lane = tile row, 32 columns per tcgen05.ld
 #pragma unroll 1
-    for (int j0 = 0; j0 < BN; j0 += 32) {
-      uint32_t v[32];
-      if (num_kb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j0, v);
-      } else {
+    for (int h = 0; h < kCols / BN; h++) {
+      // TMEM -> registers -> padded staging: lane = tile row, 32 columns per tcgen05.ld
+#pragma unroll 1
+      for (int j0 = 0; j0 < BN; j0 += 32) {
+        uint32_t v[32];
+        if (num_kb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + j0), v);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = 0u;
+          for (int j = 0; j < 32; j++) v[j] = 0u;
+        }
+        float *dst = stage + (q * 32 + lane) * PITCH + j0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-      float *dst = stage + (q * 32 + lane) * PITCH + j0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      prob.store(stage, tid, mt, kPair ? 2 * (int)blockIdx.y + h : (int)blockIdx.y);
+      if (h + 1 < kCols / BN) asm volatile("bar.sync 1, 128;" ::: "memory");     // staging is reused
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    prob.store(stage, t - 64);
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
-                 : "memory");
+    if (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kCols)
+                   : "memory");
   }
 }
 
@@ -387,28 +466,28 @@ struct DenseProb {
     if (e < b) e = b;
   }
   __device__ __forceinline__ uint32_t tx_bytes() const { return STAGE_BYTES; }
+  template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
-                                       const CUtensorMap *ma, const CUtensorMap *mb) const {
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, k0 = kb * BK;
+                                       const CUtensorMap *ma, const CUtensorMap *mb, int mt, int nt) const {
+    const int m0 = mt * BM, n0 = nt * BN, k0 = kb * BK;
     if (kAMn) {
 #pragma unroll
-      for (int i = 0; i < BM / 32; i++) tma_load_2d(a_addr + i * ATOM_BYTES, ma, m0 + 32 * i, k0, bar);
+      for (int i = 0; i < BM / 32; i++) tma_load_2d<kPair>(a_addr + i * ATOM_BYTES, ma, m0 + 32 * i, k0, bar);
     } else {
-      tma_load_2d(a_addr, ma, k0, m0, bar);
+      tma_load_2d<kPair>(a_addr, ma, k0, m0, bar);
     }
     if (kBMn) {
 #pragma unroll
-      for (int i = 0; i < BN / 32; i++) tma_load_2d(b_addr + i * ATOM_BYTES, mb, n0 + 32 * i, k0, bar);
+      for (int i = 0; i < BN / 32; i++) tma_load_2d<kPair>(b_addr + i * ATOM_BYTES, mb, n0 + 32 * i, k0, bar);
     } else {
-      tma_load_2d(b_addr, mb, k0, n0, bar);
+      tma_load_2d<kPair>(b_addr, mb, k0, n0, bar);
     }
   }
-  __device__ __forceinline__ void prefetch(int tid) const {
-    if (kEpi == EPI_SGD)
-      prefetch_tile_l2(tid, blockIdx.x * BM, blockIdx.y * BN, M, N, out, aux, ldo, IdentityRow());
+  __device__ __forceinline__ void prefetch(int tid, int mt, int nt) const {
+    if (kEpi == EPI_SGD) prefetch_tile_l2(tid, mt * BM, nt * BN, M, N, out, aux, ldo, IdentityRow());
   }
-  __device__ __forceinline__ void store(const float *stage, int tid) const {
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+    const int m0 = mt * BM, n0 = nt * BN;
     if (kEpi == EPI_PARTIAL)
       store_rows<EPI_STORE>(stage, tid, m0, n0, M, N, workspace + (size_t)blockIdx.z * M * N, N, nullptr,
                             nullptr, sgd, IdentityRow());
@@ -459,6 +538,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn encode_tiled_fn();         // kernels_gemm.cu (driver entry point, resolved once)
 int tma_data_type();                     // CU_TENSOR_MAP_DATA_TYPE_* used for the operands
 bool enabled();                          // KCNN_TMA=0 disables the TMA paths
+bool pair_enabled();                     // KCNN_TMA_PAIR=1 opts in to the 2-CTA (cta_group::2) tiles
+bool deep_ring_enabled();                // KCNN_TMA_DEEP=0 keeps 3 stages for one-wave grids
 
 // Grow-only device scratch, one buffer per slot (kernels_gemm.cu).  Returns nullptr when it
 // would have to grow while the stream is being captured; callers then take another path.
@@ -521,17 +602,48 @@ inline int pick_splits(long long tiles, int num_kb) {
   return (int)(want < 1 ? 1 : want);
 }
 
-template <class Prob>
-void launch_prob(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 grid) {
-  auto kernel = tma_gemm_kernel<Prob>;
+
+
+// grid = (128-row tiles, 128-column tiles, splits).  pair: 2-CTA clusters along x, 256-column
+// tiles along y (grid.x rounded up to even, grid.y halved).
+template <class Prob, bool kPair, int kStages>
+void launch_variant(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 grid) {
+  auto kernel = tma_gemm_kernel<Prob, kPair, kStages>;
+  constexpr int smem = Ring<kStages>::SMEM_TOTAL;
   static bool attr_set = false;          // one flag per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
-  kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(ma, mb, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kPair ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, ma, mb, p);
   count_launch();
 }
+
+// grid = (128-row tiles, 128-column tiles, splits).  pair: 2-CTA clusters along x, 256-column
+// tiles along y (grid.x rounded up to even, grid.y halved).
+template <class Prob>
+void launch_prob(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 grid,
+                 bool pair = false) {
+  if (pair) {
+    launch_variant<Prob, true, 3>(st, ma, mb, p, dim3((grid.x + 1) & ~1u, (grid.y + 1) / 2, grid.z));
+  } else if ((long long)grid.x * grid.y * grid.z <= kNumSMs && deep_ring_enabled()) {
+    launch_variant<Prob, false, 6>(st, ma, mb, p, grid);
+  } else {
+    launch_variant<Prob, false, 3>(st, ma, mb, p, grid);
+  }
+}
+
+// Pair tiles pay when both extents fill a 256 x 256 tile reasonably.
+inline bool use_pair(int M, int N) { return pair_enabled() && M >= 256 && N >= 192; }
 
 // D[M x N] (row-major, pitch ldo) = A B^T with A logical [M x K], B logical [N x K].
 // a / b are the matrices as stored: K-major -> [MN][K], MN-major -> [K][MN].
@@ -545,9 +657,13 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
   if (!encode_2d(&mb, b, kBMn ? BK : BN, kBMn)) return false;
   const int num_kb = (K + BK - 1) / BK;
   const bool out_vec = (N & 3) == 0 && (ldo & 3) == 0 && host_aligned16(out);
+  const bool pair = use_pair(M, N);
   int splits = 1;
-  if (allow_split && out_vec)
-    splits = pick_splits((long long)ceil_div_u(M, BM) * ceil_div_u(N, BN), num_kb);
+  if (allow_split && out_vec) {
+    long long ctas = pair ? (long long)(2 * ceil_div_u(M, 2 * BM)) * ceil_div_u(N, 2 * BN)
+                          : (long long)ceil_div_u(M, BM) * ceil_div_u(N, BN);
+    splits = pick_splits(ctas, num_kb);
+  }
   int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;
   float *ws = nullptr;
@@ -562,7 +678,7 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
   };
   if (splits > 1) {
     DenseProb<kAMn, kBMn, EPI_PARTIAL> p; fill(p);
-    launch_prob(st, ma, mb, p, grid);
+    launch_prob(st, ma, mb, p, grid, pair);
     const unsigned blocks = ceil_div_u(((long long)M * N) >> 2, 256);
     if (epi.mode == EPI_SGD)
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
@@ -572,10 +688,10 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
                   epi.bias_n, nullptr, epi.sgd, IdentityRow());
   } else if (epi.mode == EPI_SGD) {
     DenseProb<kAMn, kBMn, EPI_SGD> p; fill(p);
-    launch_prob(st, ma, mb, p, grid);
+    launch_prob(st, ma, mb, p, grid, pair);
   } else {
     DenseProb<kAMn, kBMn, EPI_STORE> p; fill(p);
-    launch_prob(st, ma, mb, p, grid);
+    launch_prob(st, ma, mb, p, grid, pair);
   }
   return true;
 }

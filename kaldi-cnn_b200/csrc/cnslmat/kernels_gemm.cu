@@ -63,6 +63,26 @@ bool enabled() {
   return v == 1;
 }
 
+bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // Validated (same results) but measured SLOWER than the single-CTA tiles on this part
+    // (4096^3: 472 vs 599 TFLOP/s, profiles/), so it is opt-in.
+    const char *e = getenv("KCNN_TMA_PAIR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+bool deep_ring_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_TMA_DEEP");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // Grow-only device scratch, one buffer per slot.  Grown with cudaMalloc, so the first call
 // of a shape must happen outside stream capture (warm-up steps do that); outgrown buffers
 // are kept alive because CUDA graphs captured earlier still point at them.

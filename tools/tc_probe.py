@@ -133,3 +133,26 @@ def ncu_target(N=512):
 
 if "--ncu" in sys.argv:
     ncu_target()
+
+
+def big(N=4096):
+    """Main-loop-dominated GEMMs (K = 4096 per tile) to compare tile variants."""
+    math = 1
+    din = dout = 4096
+    x = torch.randn(N, din, device="cuda"); w = torch.randn(dout, din, device="cuda") * 0.01
+    b = torch.zeros(dout, device="cuda"); y = torch.empty(N, dout, device="cuda")
+    g = torch.empty(dout, din, device="cuda"); bg = torch.empty(dout, device="cuda")
+    fl = 2.0 * N * din * dout
+    t1 = timeit(lambda: L.cudaF_affine_fprop(stream(), math, ptr(x), mdim(x), ptr(w), mdim(w), ptr(b), ptr(y), mdim(y)))
+    t2 = timeit(lambda: L.cudaF_affine_dgrad(stream(), math, ptr(y), mdim(y), ptr(w), mdim(w), ptr(x), mdim(x)))
+    t3 = timeit(lambda: L.cudaF_affine_wgrad(stream(), math, ptr(x), mdim(x), ptr(y), mdim(y), ptr(g), mdim(g), ptr(bg)))
+    print("GEMM %d^3 pair=%s: KK %.1f us (%.0f TF/s)  K,MN %.1f us (%.0f)  MN,MN %.1f us (%.0f)" % (
+        N, os.environ.get("KCNN_TMA_PAIR", "1"), t1 * 1e3, fl / t1 / 1e9, t2 * 1e3, fl / t2 / 1e9, t3 * 1e3, fl / t3 / 1e9), flush=True)
+    a = torch.randn(4096, 4096, device="cuda"); bb = torch.randn(4096, 4096, device="cuda")
+    torch.backends.cuda.matmul.allow_tf32 = True
+    t4 = timeit(lambda: torch.matmul(a, bb))
+    print("cuBLAS TF32 4096^3: %.1f us (%.0f TF/s)" % (t4 * 1e3, 2 * 4096.0 ** 3 / t4 / 1e9), flush=True)
+
+
+if "--big" in sys.argv:
+    big()
