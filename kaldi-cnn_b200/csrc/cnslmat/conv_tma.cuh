@@ -154,7 +154,7 @@ struct ConvRowsProb {
   const float *bias;       // per map or nullptr
   FastDiv div_inner, div_r;
 
-  __device__ __forceinline__ void kb_range(int &b, int &e) const { b = 0; e = taps * inner_blocks; }
+  __device__ __forceinline__ void kb_range(int, int &b, int &e) const { b = 0; e = taps * inner_blocks; }
   __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)(nb * R * 128 + B_STAGE_BYTES); }
   template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
@@ -172,7 +172,8 @@ struct ConvRowsProb {
     }
   }
   __device__ __forceinline__ void prefetch(int, int, int) const {}
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+  template <int kRows>
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
     const int col0 = nt * BN;
     if (col0 >= out_maps) return;
     store_maps_transposed(stage, tid, mt * nb, nb, R, col0, min(BN, out_maps - col0), num_samples, out, ldo, bias,
@@ -198,7 +199,7 @@ struct ConvFullFpropProb {
   FastDiv div_jb, div_ow;
 
   int total_kb;            // C * j_blocks
-  __device__ __forceinline__ void kb_range(int &b, int &e) const { b = 0; e = total_kb; }
+  __device__ __forceinline__ void kb_range(int, int &b, int &e) const { b = 0; e = total_kb; }
   __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)(nb * OW * 128 + B_STAGE_BYTES); }
   template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
@@ -212,7 +213,8 @@ struct ConvFullFpropProb {
     for (int i = 0; i < BN / 32; i++) tma_load_2d<kPair>(b_addr + i * ATOM_BYTES, mb, g0 + 32 * i, (int)c * ks + j0, bar);
   }
   __device__ __forceinline__ void prefetch(int, int, int) const {}
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+  template <int kRows>
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
     const int g0 = nt * BN;
     if (g0 >= G) return;
     store_maps_transposed(stage, tid, mt * nb, nb, OW, g0, min(BN, G - g0), num_samples, out, ldo, bias, div_ow);
@@ -231,7 +233,7 @@ struct ConvFullDgradProb {
   int ldo;
   FastDiv div_gb, div_h;
 
-  __device__ __forceinline__ void kb_range(int &b, int &e) const { b = 0; e = total_kb; }
+  __device__ __forceinline__ void kb_range(int, int &b, int &e) const { b = 0; e = total_kb; }
   __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)((nb * W + nbc * H) * 128); }
   template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
@@ -243,7 +245,8 @@ struct ConvFullDgradProb {
     tma_load_3d<kPair>(b_addr, mb, g0, (int)kw * H, nt * nbc, bar);
   }
   __device__ __forceinline__ void prefetch(int, int, int) const {}
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+  template <int kRows>
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
     const int n0 = mt * nb, c0 = nt * nbc;
     const int chans = min(nbc, C - c0);
     const int hw = H * W;
@@ -293,8 +296,8 @@ struct ConvWgradProb {
   SgdCoef sgd;
   FastDiv div_nb, div_c;
 
-  __device__ __forceinline__ void kb_range(int &b, int &e) const {
-    b = blockIdx.z * kb_per_split;
+  __device__ __forceinline__ void kb_range(int z, int &b, int &e) const {
+    b = z * kb_per_split;
     e = min(total_kb, b + kb_per_split);
     if (e < b) e = b;
   }
@@ -326,16 +329,17 @@ struct ConvWgradProb {
       }
     }
   }
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+  template <int kRows>
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
     const int m0 = mt * BM, g0 = nt * BN;
     if (kEpi == EPI_PARTIAL) {
-      store_rows<EPI_STORE>(stage, tid, m0, g0, M, G, workspace + (size_t)blockIdx.z * M * G, G, nullptr,
-                            nullptr, sgd, IdentityRow());
+      store_rows<EPI_STORE, kRows>(stage, tid, m0, g0, M, G, workspace + (size_t)z * M * G, G, nullptr, nullptr,
+                                   sgd, IdentityRow());
     } else if (kFull) {
-      store_rows<kEpi>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, IdentityRow());
+      store_rows<kEpi, kRows>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, IdentityRow());
     } else {
       KernelRow rm; rm.div_c = div_c; rm.KW = KW;
-      store_rows<kEpi>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, rm);
+      store_rows<kEpi, kRows>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, rm);
     }
   }
 };

@@ -135,11 +135,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
 
 // Problem interface (mt / nt: 128-row / 128-column tile indices):
 //   static constexpr bool kAMn, kBMn
-//   void kb_range(int &begin, int &end) const                    K-blocks of this CTA
+//   void kb_range(int z, int &begin, int &end) const             K-blocks of split z
 //   uint32_t tx_bytes() const                                     bytes one CTA's boxes of a stage deliver
 //   void load<kPair>(kb, a_addr, b_addr, bar, &map_a, &map_b, mt, nt)   A rows of tile mt, B rows of tile nt
 //   void prefetch(tid, mt, nt) const                              epilogue threads, before the accumulator is ready
-//   void store(stage, tid, mt, nt) const                          128 epilogue threads, stage[128][PITCH]
+//   void store<kRows>(stage, tid, mt, nt, z) const                128 epilogue threads, stage[128][PITCH];
+//                                                                 kRows = rows of global loads kept in flight
 //
 // kPair = false: one CTA computes the 128 x 128 tile (blockIdx.x, blockIdx.y).
 // kPair = true:  a cluster of two CTAs (one TPC) computes a 256 x 256 tile with
@@ -186,7 +187,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 
 template <class Prob, bool kPair, int STAGES>
-__global__ void __launch_bounds__(THREADS, STAGES <= 3 ? 2 : 1)
+__global__ void __launch_bounds__(THREADS, STAGES <= 2 ? 3 : (STAGES <= 3 ? 2 : 1))
 tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const Prob prob) {
   constexpr int kCols = kPair ? 2 * BN : BN;        // TMEM columns = accumulator columns per CTA
@@ -205,7 +206,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int mt = blockIdx.x;
   const int nt_load = kPair ? 2 * (int)blockIdx.y + (int)rank : (int)blockIdx.y;
   int kb_begin, kb_end;
-  prob.kb_range(kb_begin, kb_end);
+  prob.kb_range((int)blockIdx.z, kb_begin, kb_end);
   const int num_kb = kb_end - kb_begin;
 
   if (warp == 1) {
@@ -306,7 +307,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      prob.store(stage, tid, mt, kPair ? 2 * (int)blockIdx.y + h : (int)blockIdx.y);
+      prob.template store<8>(stage, tid, mt, kPair ? 2 * (int)blockIdx.y + h : (int)blockIdx.y, (int)blockIdx.z);
       if (h + 1 < kCols / BN) asm volatile("bar.sync 1, 128;" ::: "memory");     // staging is reused
     }
   }
@@ -321,6 +322,164 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kCols)
                    : "memory");
+  }
+}
+
+// ---- persistent variant ------------------------------------------------------------------
+// For grids of several waves (the weight gradients: 1024 tiles x 16 K-blocks for FC2): one
+// CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (tile row fastest, so CTAs
+// running together share B tiles in L2).  The 4-stage operand ring runs straight across tile
+// boundaries, the accumulator is double-buffered in TMEM (2 x 128 columns) and the staging
+// tile has its own shared memory, so the epilogue of tile i -- TMEM drain, then the HBM-heavy
+// fused SGD read-modify-write of the W / prev_grad tile -- overlaps the main loop of tile
+// i + 1 inside the SAME CTA instead of relying on a second resident CTA.
+constexpr int PSTAGES = 4;
+struct PRing {
+  static constexpr int RING_BYTES = PSTAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFFSET = RING_BYTES;
+  static constexpr int BAR_OFFSET = RING_BYTES + STAGING_BYTES;
+  static constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * PSTAGES + 4) * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <class Prob>
+__global__ void __launch_bounds__(THREADS, 1)
+tma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                           const Prob prob, int tiles_m, int tiles_n, int splits) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + PRing::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8 * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8 * (PSTAGES + s); };
+  auto acc_full = [&](int b) { return bar_base + 8 * (2 * PSTAGES + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8 * (2 * PSTAGES + 2 + b); };
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem_gen + PRing::BAR_OFFSET + 8 * (2 * PSTAGES + 4));
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int total_tiles = tiles_m * tiles_n * splits;
+  auto decode = [&](int tile, int &mt, int &nt, int &z) {
+    mt = tile % tiles_m;
+    const int r = tile / tiles_m;
+    nt = r % tiles_n;
+    z = r / tiles_n;
+  };
+
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr_smem)), "r"((uint32_t)(2 * BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (t == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < PSTAGES; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer --
+    if (lane == 0) {
+      const uint32_t tx = prob.tx_bytes();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt, nt, z, kb_begin, kb_end;
+        decode(tile, mt, nt, z);
+        prob.kb_range(z, kb_begin, kb_end);
+        for (int kb = kb_begin; kb < kb_end; kb++, it++) {
+          const int s = it % PSTAGES;
+          if (it >= PSTAGES) mbar_wait(empty_bar(s), ((it / PSTAGES) - 1) & 1);
+          const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), tx);
+          prob.template load<false>(kb, a_addr, a_addr + A_STAGE_BYTES, full_bar(s), &map_a, &map_b, mt, nt);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // --------------------------------------------------------------- MMA issuer --
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, Prob::kAMn, Prob::kBMn);
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+        int mt, nt, z, kb_begin, kb_end;
+        decode(tile, mt, nt, z);
+        prob.kb_range(z, kb_begin, kb_end);
+        const int buf = tcount & 1, use = tcount >> 1;
+        if (use > 0) mbar_wait(acc_empty(buf), (use - 1) & 1);       // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int i = 0; i < kb_end - kb_begin; i++, it++) {
+          const int s = it % PSTAGES;
+          mbar_wait(full_bar(s), (it / PSTAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint64_t adesc = Prob::kAMn ? desc_mn_major(a_addr) : desc_k_major(a_addr);
+          const uint64_t bdesc = Prob::kBMn ? desc_mn_major(b_addr) : desc_k_major(b_addr);
+#pragma unroll
+          for (int k = 0; k < BK / 8; k++) {
+            const uint64_t ad = adesc + (Prob::kAMn ? 64 * k : 2 * k);
+            const uint64_t bd = bdesc + (Prob::kBMn ? 64 * k : 2 * k);
+            umma_tf32(tmem_d, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(acc_full(buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ----------------------------------------------------------------- epilogue --
+    const int q = warp & 3;
+    float *stage = reinterpret_cast<float *>(smem_gen + PRing::STAGING_OFFSET);
+    const int tid = t - 64;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+      int mt, nt, z;
+      decode(tile, mt, nt, z);
+      const int buf = tcount & 1, use = tcount >> 1;
+      prob.prefetch(tid, mt, nt);
+      mbar_wait(acc_full(buf), use & 1);
+      tc_fence_after();
+      asm volatile("bar.sync 1, 128;" ::: "memory");              // previous tile's staging fully consumed
+#pragma unroll 1
+      for (int j0 = 0; j0 < BN; j0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + j0), v);
+        float *dst = stage + (q * 32 + lane) * PITCH + j0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      tc_fence_before();
+      mbar_arrive_local(acc_empty(buf));                           // TMEM buffer may be overwritten
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      prob.template store<16>(stage, tid, mt, nt, z);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                 : "memory");
   }
 }
 
@@ -348,7 +507,7 @@ __device__ __forceinline__ void sgd_apply(float &w, float &p, float g, const Sgd
 // Row-major 128-column segment store shared by the dense and the weight-gradient
 // problems: tid -> (row group, 4 columns); each warp instruction writes one 512-byte
 // row segment.  row_of(m) maps a tile row to the output row.
-template <int kEpi, class RowMap>
+template <int kEpi, int kRows, class RowMap>
 __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, int n0, int M, int N,
                                            float *obase, int ld, const float *bias_n, float *aux,
                                            const SgdCoef &sgd, RowMap row_of) {
@@ -364,9 +523,9 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
   }
   if (kEpi == EPI_SGD && vec_ok) {
     // nnet0/nnet-component-nnet0.cc:767-773, 1138-1142 on the tile: W and prev_grad rows are
-    // read in batches of 8 rows (16 independent 128-bit loads per thread in flight; the lines
-    // were L2-prefetched by Problem::prefetch while the main loop ran), updated, written back.
-    constexpr int RB = 8;
+    // read in batches of kRows rows (2 kRows independent 128-bit loads per thread in flight; the
+    // lines were L2-prefetched by Problem::prefetch while the main loop ran), updated, written back.
+    constexpr int RB = kRows;
 #pragma unroll 1
     for (int r0 = 0; r0 < 32; r0 += RB) {
       float4 w[RB], pv[RB];
@@ -459,9 +618,9 @@ struct DenseProb {
   float *aux;              // EPI_SGD: prev_grad, same shape / pitch as out
   SgdCoef sgd;
 
-  __device__ __forceinline__ void kb_range(int &b, int &e) const {
+  __device__ __forceinline__ void kb_range(int z, int &b, int &e) const {
     const int total = (K + BK - 1) / BK;
-    b = blockIdx.z * kb_per_split;
+    b = z * kb_per_split;
     e = min(total, b + kb_per_split);
     if (e < b) e = b;
   }
@@ -486,13 +645,14 @@ struct DenseProb {
   __device__ __forceinline__ void prefetch(int tid, int mt, int nt) const {
     if (kEpi == EPI_SGD) prefetch_tile_l2(tid, mt * BM, nt * BN, M, N, out, aux, ldo, IdentityRow());
   }
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt) const {
+  template <int kRows>
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
     const int m0 = mt * BM, n0 = nt * BN;
     if (kEpi == EPI_PARTIAL)
-      store_rows<EPI_STORE>(stage, tid, m0, n0, M, N, workspace + (size_t)blockIdx.z * M * N, N, nullptr,
-                            nullptr, sgd, IdentityRow());
+      store_rows<EPI_STORE, kRows>(stage, tid, m0, n0, M, N, workspace + (size_t)z * M * N, N, nullptr, nullptr,
+                                   sgd, IdentityRow());
     else
-      store_rows<kEpi>(stage, tid, m0, n0, M, N, out, ldo, bias_n, aux, sgd, IdentityRow());
+      store_rows<kEpi, kRows>(stage, tid, m0, n0, M, N, out, ldo, bias_n, aux, sgd, IdentityRow());
   }
 };
 
@@ -540,6 +700,7 @@ int tma_data_type();                     // CU_TENSOR_MAP_DATA_TYPE_* used for t
 bool enabled();                          // KCNN_TMA=0 disables the TMA paths
 bool pair_enabled();                     // KCNN_TMA_PAIR=1 opts in to the 2-CTA (cta_group::2) tiles
 bool deep_ring_enabled();                // KCNN_TMA_DEEP=0 keeps 3 stages for one-wave grids
+bool persistent_enabled();               // KCNN_TMA_PERSIST=0 keeps multi-wave grids on one tile per CTA
 
 // Grow-only device scratch, one buffer per slot (kernels_gemm.cu).  Returns nullptr when it
 // would have to grow while the stream is being captured; callers then take another path.
@@ -604,8 +765,7 @@ inline int pick_splits(long long tiles, int num_kb) {
 
 
 
-// grid = (128-row tiles, 128-column tiles, splits).  pair: 2-CTA clusters along x, 256-column
-// tiles along y (grid.x rounded up to even, grid.y halved).
+// One tile per CTA; kPair launches 2-CTA clusters.
 template <class Prob, bool kPair, int kStages>
 void launch_variant(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 grid) {
   auto kernel = tma_gemm_kernel<Prob, kPair, kStages>;
@@ -628,6 +788,20 @@ void launch_variant(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &m
   count_launch();
 }
 
+template <class Prob>
+void launch_persistent(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 tiles) {
+  auto kernel = tma_gemm_persistent_kernel<Prob>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PRing::SMEM_TOTAL);
+    attr_set = true;
+  }
+  long long total = (long long)tiles.x * tiles.y * tiles.z;
+  unsigned ctas = (unsigned)(total < kNumSMs ? total : kNumSMs);
+  kernel<<<ctas, THREADS, PRing::SMEM_TOTAL, st>>>(ma, mb, p, (int)tiles.x, (int)tiles.y, (int)tiles.z);
+  count_launch();
+}
+
 // grid = (128-row tiles, 128-column tiles, splits).  pair: 2-CTA clusters along x, 256-column
 // tiles along y (grid.x rounded up to even, grid.y halved).
 template <class Prob>
@@ -637,6 +811,8 @@ void launch_prob(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, 
     launch_variant<Prob, true, 3>(st, ma, mb, p, dim3((grid.x + 1) & ~1u, (grid.y + 1) / 2, grid.z));
   } else if ((long long)grid.x * grid.y * grid.z <= kNumSMs && deep_ring_enabled()) {
     launch_variant<Prob, false, 6>(st, ma, mb, p, grid);
+  } else if ((long long)grid.x * grid.y * grid.z > kNumSMs + kNumSMs / 2 && persistent_enabled()) {
+    launch_persistent<Prob>(st, ma, mb, p, grid);
   } else {
     launch_variant<Prob, false, 3>(st, ma, mb, p, grid);
   }

@@ -74,6 +74,15 @@ bool pair_enabled() {
   return v == 1;
 }
 
+bool persistent_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_TMA_PERSIST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool deep_ring_enabled() {
   static int v = -1;
   if (v < 0) {

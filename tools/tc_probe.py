@@ -82,6 +82,9 @@ def perf(N=512):
             t1 = timeit(lambda: L.cudaF_affine_fprop(stream(), math, ptr(x), mdim(x), ptr(w), mdim(w), ptr(b), ptr(y), mdim(y)))
             t2 = timeit(lambda: L.cudaF_affine_dgrad(stream(), math, ptr(y), mdim(y), ptr(w), mdim(w), ptr(x), mdim(x)))
             t3 = timeit(lambda: L.cudaF_affine_wgrad(stream(), math, ptr(x), mdim(x), ptr(y), mdim(y), ptr(g), mdim(g), ptr(bg)))
+            pv = torch.zeros(dout, din, device="cuda")
+            t4 = timeit(lambda: L.cudaF_affine_wgrad_sgd(stream(), math, ptr(x), mdim(x), ptr(y), mdim(y), ptr(w), mdim(w), ptr(pv), mdim(pv), ptr(b), 0.9, -1e-9, 1e-9))
+            print("   fused wgrad+sgd %.1f us" % (t4 * 1e3))
             print("FC %d->%d N=%d math=%d: fprop %.1f us (%.0f TF/s)  dgrad %.1f us (%.0f)  wgrad %.1f us (%.0f)" % (
                 din, dout, N, math, t1 * 1e3, fl / t1 / 1e9, t2 * 1e3, fl / t2 / 1e9, t3 * 1e3, fl / t3 / 1e9), flush=True)
         convs = [(40, 21, 1, 40, 4, 128), (1, 18, 64, 1, 3, 128), (1, 16, 128, 1, 3, 256), (1, 14, 256, 1, 3, 256),
