@@ -213,6 +213,44 @@ nonlin_stats_kernel(const float *__restrict__ y, ::MatrixDim d, double *value_su
   }
 }
 
+// RectifiedLinearComponent::Backprop and the statistics of NonlinearComponent::UpdateStats
+// (reference nnet2/nnet-component.cc:337-363, 813-827) in ONE pass over out_value:
+// in_deriv = out_deriv * [y > 0], value_sum += colsum(y), deriv_sum += colsum([y > 0]).
+__global__ void __launch_bounds__(1024)
+relu_bprop_stats_kernel(const float *__restrict__ y, ::MatrixDim yd, const float *__restrict__ od,
+                        int od_stride, float *__restrict__ id, int id_stride, double *value_sum,
+                        double *deriv_sum) {
+  __shared__ float pv[32][33], pd[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float sv0 = 0.0f, sv1 = 0.0f, sd0 = 0.0f, sd1 = 0.0f;
+  if (col < yd.cols) {
+    int r = ty;
+    for (; r + 32 < yd.rows; r += 64) {
+      const float a = __ldg(y + (size_t)r * yd.stride + col), b = __ldg(y + (size_t)(r + 32) * yd.stride + col);
+      const float da = __ldg(od + (size_t)r * od_stride + col), db = __ldg(od + (size_t)(r + 32) * od_stride + col);
+      id[(size_t)r * id_stride + col] = a > 0.0f ? da : 0.0f;
+      id[(size_t)(r + 32) * id_stride + col] = b > 0.0f ? db : 0.0f;
+      sv0 += a; sd0 += a > 0.0f ? 1.0f : 0.0f;
+      sv1 += b; sd1 += b > 0.0f ? 1.0f : 0.0f;
+    }
+    for (; r < yd.rows; r += 32) {
+      const float a = __ldg(y + (size_t)r * yd.stride + col);
+      id[(size_t)r * id_stride + col] = a > 0.0f ? __ldg(od + (size_t)r * od_stride + col) : 0.0f;
+      sv0 += a; sd0 += a > 0.0f ? 1.0f : 0.0f;
+    }
+  }
+  pv[ty][tx] = sv0 + sv1; pd[ty][tx] = sd0 + sd1;
+  __syncthreads();
+  if (ty == 0 && col < yd.cols) {
+    float a = 0.0f, b = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) { a += pv[i][tx]; b += pd[i][tx]; }
+    value_sum[col] += (double)a;
+    deriv_sum[col] += (double)b;
+  }
+}
+
 __device__ __forceinline__ uint32_t mix32(uint64_t x) {     // splitmix64 finaliser
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -221,32 +259,69 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {     // splitmix64 finali
   return (uint32_t)(x >> 32);
 }
 
+// The mask is a pure function of (seed, element index i*cols + j).  Each thread owns up to four
+// adjacent columns of one row (128-bit accesses when kVec4).
+template <bool kVec4>
 __global__ void __launch_bounds__(256)
 dropout_fprop_kernel(const float *__restrict__ in, ::MatrixDim id, float *__restrict__ out,
                      ::MatrixDim od, float dp, float low, float high,
-                     const unsigned long long *seed_dev) {
+                     const unsigned long long *seed_dev, kcnn::FastDiv div_units) {
+  const int units = kVec4 ? od.cols / 4 : od.cols;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)od.rows * od.cols) return;
-  const unsigned long long seed = *seed_dev;
-  int i = (int)(t / od.cols), j = (int)(t % od.cols);
-  float u = (mix32(seed * 0x100000001B3ull + (uint64_t)t) >> 8) * (1.0f / 16777216.0f);
-  float scale = (u - dp > 0.0f) ? high : low;
-  out[(size_t)i * od.stride + j] = scale * __ldg(in + (size_t)i * id.stride + j);
+  if (t >= (long long)od.rows * units) return;
+  uint32_t i, u;
+  div_units.divmod((uint32_t)t, i, u);
+  const unsigned long long base = *seed_dev * 0x100000001B3ull + (unsigned long long)i * od.cols;
+  if (kVec4) {
+    const int j = 4 * (int)u;
+    float4 v = __ldg(reinterpret_cast<const float4 *>(in + (size_t)i * id.stride) + u);
+    float *e = &v.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float r = (mix32(base + (unsigned long long)(j + k)) >> 8) * (1.0f / 16777216.0f);
+      e[k] *= (r - dp > 0.0f) ? high : low;
+    }
+    reinterpret_cast<float4 *>(out + (size_t)i * od.stride)[u] = v;
+  } else {
+    float r = (mix32(base + u) >> 8) * (1.0f / 16777216.0f);
+    out[(size_t)i * od.stride + u] = ((r - dp > 0.0f) ? high : low) * __ldg(in + (size_t)i * id.stride + u);
+  }
 }
 
 __global__ void bump_seed_kernel(unsigned long long *seed_dev) { *seed_dev += 1; }
 
 // in_deriv = out_deriv .* out_value ./ in_value   (out_deriv where in_value == 0):
 // Kaldi's AddMatMatDivMat, reference nnet2/nnet-component.cc:3634-3636.
+template <bool kVec4>
 __global__ void __launch_bounds__(256)
-dropout_bprop_kernel(const float *__restrict__ iv, ::MatrixDim ivd, const float *__restrict__ ov,
-                     ::MatrixDim ovd, const float *__restrict__ od, ::MatrixDim odd,
-                     float *__restrict__ id, ::MatrixDim idd) {
+dropout_bprop_kernel(const float *__restrict__ iv, int iv_stride, const float *__restrict__ ov,
+                     int ov_stride, const float *__restrict__ od, int od_stride,
+                     float *__restrict__ id, ::MatrixDim idd, kcnn::FastDiv div_units) {
+  const int units = kVec4 ? idd.cols / 4 : idd.cols;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)idd.rows * idd.cols) return;
-  int i = (int)(t / idd.cols), j = (int)(t % idd.cols);
-  float x = __ldg(iv + (size_t)i * ivd.stride + j), d = __ldg(od + (size_t)i * odd.stride + j);
-  id[(size_t)i * idd.stride + j] = x == 0.0f ? d : d * __ldg(ov + (size_t)i * ovd.stride + j) / x;
+  if (t >= (long long)idd.rows * units) return;
+  uint32_t i, u;
+  div_units.divmod((uint32_t)t, i, u);
+  if (kVec4) {
+    const float4 x = __ldg(reinterpret_cast<const float4 *>(iv + (size_t)i * iv_stride) + u);
+    const float4 y = __ldg(reinterpret_cast<const float4 *>(ov + (size_t)i * ov_stride) + u);
+    float4 d = __ldg(reinterpret_cast<const float4 *>(od + (size_t)i * od_stride) + u);
+    d.x = x.x == 0.0f ? d.x : d.x * y.x / x.x;
+    d.y = x.y == 0.0f ? d.y : d.y * y.y / x.y;
+    d.z = x.z == 0.0f ? d.z : d.z * y.z / x.z;
+    d.w = x.w == 0.0f ? d.w : d.w * y.w / x.w;
+    reinterpret_cast<float4 *>(id + (size_t)i * idd.stride)[u] = d;
+  } else {
+    float x = __ldg(iv + (size_t)i * iv_stride + u), d = __ldg(od + (size_t)i * od_stride + u);
+    id[(size_t)i * idd.stride + u] = x == 0.0f ? d : d * __ldg(ov + (size_t)i * ov_stride + u) / x;
+  }
+}
+
+inline bool rows_vec4(int cols, std::initializer_list<int> strides, std::initializer_list<const void *> ptrs) {
+  if (cols & 3) return false;
+  for (int st : strides) if (st & 3) return false;
+  for (const void *p : ptrs) if (reinterpret_cast<uintptr_t>(p) & 15u) return false;
+  return true;
 }
 }  // namespace
 
@@ -259,8 +334,7 @@ NonlinearComponent::~NonlinearComponent() {
   if (stats_) CuDevice::Instantiate().Free(stats_);
 }
 
-void NonlinearComponent::UpdateStats(const CuMatrixBase<BaseFloat> &out_value, bool relu_deriv) {
-  KALDI_ASSERT(out_value.NumCols() == InputDim());
+void NonlinearComponent::EnsureStats() {
   if (stats_ == NULL || stats_dim_ != dim_) {
     if (stats_) CuDevice::Instantiate().Free(stats_);
     stats_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double) * 2 * dim_));
@@ -272,10 +346,26 @@ void NonlinearComponent::UpdateStats(const CuMatrixBase<BaseFloat> &out_value, b
                                  cudaMemcpyHostToDevice, Str()));
     CU_SAFE_CALL(cudaStreamSynchronize(Str()));
   }
+}
+
+void NonlinearComponent::UpdateStats(const CuMatrixBase<BaseFloat> &out_value, bool relu_deriv) {
+  KALDI_ASSERT(out_value.NumCols() == InputDim());
+  EnsureStats();
   count_ += out_value.NumRows();
   if (out_value.NumRows() == 0) return;
   KCNN_LAUNCH(nonlin_stats_kernel, kcnn::ceil_div_u(dim_, 32), 1024, 0, Str(), out_value.Data(),
               out_value.Dim(), stats_, relu_deriv ? stats_ + dim_ : (double *)NULL);
+}
+
+void NonlinearComponent::BackpropReluWithStats(const CuMatrixBase<BaseFloat> &out_value,
+                                               const CuMatrixBase<BaseFloat> &out_deriv,
+                                               CuMatrix<BaseFloat> *in_deriv) {
+  KALDI_ASSERT(out_value.NumCols() == InputDim());
+  EnsureStats();
+  count_ += out_value.NumRows();
+  KCNN_LAUNCH(relu_bprop_stats_kernel, kcnn::ceil_div_u(dim_, 32), 1024, 0, Str(), out_value.Data(),
+              out_value.Dim(), out_deriv.Data(), out_deriv.Stride(), in_deriv->Data(), in_deriv->Stride(),
+              stats_, stats_ + dim_);
 }
 
 void NonlinearComponent::GetStats(Vector<double> *value_sum, Vector<double> *deriv_sum) const {
@@ -351,10 +441,12 @@ void RectifiedLinearComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
                                         const CuMatrixBase<BaseFloat> &out_deriv,
                                         Component *to_update, CuMatrix<BaseFloat> *in_deriv) const {
   in_deriv->Resize(out_deriv.NumRows(), out_deriv.NumCols(), kUndefined);
+  if (to_update != NULL && out_value.NumRows() > 0) {
+    dynamic_cast<NonlinearComponent *>(to_update)->BackpropReluWithStats(out_value, out_deriv, in_deriv);
+    return;
+  }
   cudaF_relu_bprop(Str(), out_value.Data(), out_value.Dim(), out_deriv.Data(), out_deriv.Dim(),
                    in_deriv->Data(), in_deriv->Dim());
-  if (to_update != NULL)
-    dynamic_cast<NonlinearComponent *>(to_update)->UpdateStats(out_value, true);
 }
 
 // reference :930-950
@@ -459,8 +551,15 @@ void DropoutComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &out_
     CU_SAFE_CALL(cudaMemcpyAsync(seed_dev_, &s0, sizeof(s0), cudaMemcpyHostToDevice, Str()));
     CU_SAFE_CALL(cudaStreamSynchronize(Str()));
   }
-  KCNN_LAUNCH(dropout_fprop_kernel, kcnn::ceil_div_u(total, 256), 256, 0, Str(), in.Data(), in.Dim(),
-              out->Data(), out->Dim(), dp, low_scale, high_scale, seed_dev_);
+  const bool v4 = rows_vec4(out->NumCols(), {in.Stride(), out->Stride()}, {in.Data(), out->Data()});
+  const int units = v4 ? out->NumCols() / 4 : out->NumCols();
+  const unsigned grid = kcnn::ceil_div_u((long long)out->NumRows() * units, 256);
+  if (v4)
+    KCNN_LAUNCH(dropout_fprop_kernel<true>, grid, 256, 0, Str(), in.Data(), in.Dim(), out->Data(), out->Dim(),
+                dp, low_scale, high_scale, seed_dev_, kcnn::FastDiv((uint32_t)units));
+  else
+    KCNN_LAUNCH(dropout_fprop_kernel<false>, grid, 256, 0, Str(), in.Data(), in.Dim(), out->Data(), out->Dim(),
+                dp, low_scale, high_scale, seed_dev_, kcnn::FastDiv((uint32_t)units));
   KCNN_LAUNCH(bump_seed_kernel, 1, 1, 0, Str(), seed_dev_);
 }
 
@@ -473,9 +572,19 @@ void DropoutComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
   in_deriv->Resize(out_deriv.NumRows(), out_deriv.NumCols(), kUndefined);
   long long total = (long long)out_deriv.NumRows() * out_deriv.NumCols();
   if (total == 0) return;
-  KCNN_LAUNCH(dropout_bprop_kernel, kcnn::ceil_div_u(total, 256), 256, 0, Str(), in_value.Data(),
-              in_value.Dim(), out_value.Data(), out_value.Dim(), out_deriv.Data(), out_deriv.Dim(),
-              in_deriv->Data(), in_deriv->Dim());
+  const bool v4 = rows_vec4(in_deriv->NumCols(),
+                            {in_value.Stride(), out_value.Stride(), out_deriv.Stride(), in_deriv->Stride()},
+                            {in_value.Data(), out_value.Data(), out_deriv.Data(), in_deriv->Data()});
+  const int units = v4 ? in_deriv->NumCols() / 4 : in_deriv->NumCols();
+  const unsigned grid = kcnn::ceil_div_u((long long)in_deriv->NumRows() * units, 256);
+  if (v4)
+    KCNN_LAUNCH(dropout_bprop_kernel<true>, grid, 256, 0, Str(), in_value.Data(), in_value.Stride(),
+                out_value.Data(), out_value.Stride(), out_deriv.Data(), out_deriv.Stride(), in_deriv->Data(),
+                in_deriv->Dim(), kcnn::FastDiv((uint32_t)units));
+  else
+    KCNN_LAUNCH(dropout_bprop_kernel<false>, grid, 256, 0, Str(), in_value.Data(), in_value.Stride(),
+                out_value.Data(), out_value.Stride(), out_deriv.Data(), out_deriv.Stride(), in_deriv->Data(),
+                in_deriv->Dim(), kcnn::FastDiv((uint32_t)units));
 }
 
 // ------------------------------------------------------------ AffineComponent --

@@ -175,6 +175,10 @@ class NonlinearComponent : public Component {
   friend class SoftmaxComponent;
   /// Adds column sums of out_value (and, for ReLU, of the 0/1 derivative) to the stats.
   void UpdateStats(const CuMatrixBase<BaseFloat> &out_value, bool relu_deriv);
+  /// in_deriv = out_deriv * [out_value > 0] and the UpdateStats sums, one kernel.
+  void BackpropReluWithStats(const CuMatrixBase<BaseFloat> &out_value, const CuMatrixBase<BaseFloat> &out_deriv,
+                             CuMatrix<BaseFloat> *in_deriv);
+  void EnsureStats();
   const NonlinearComponent &operator=(const NonlinearComponent &other);  // Disallow.
   int32 dim_;
   double count_;
