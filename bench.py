@@ -153,8 +153,9 @@ def cpu_train_frames_per_sec(cfg_text, rows, steps, warmup, threads):
     import numpy as np
     from oracle.cpu_nnet import CpuNnet
     kind, backend = cpu_backend()
+    used = 1
     if hasattr(backend, "set_num_threads"):
-        backend.set_num_threads(threads)
+        used = backend.set_num_threads(threads) or 1
     net = CpuNnet(cfg_text, seed=42, backend=backend)
     rng = np.random.default_rng(1234)
     x = rng.standard_normal((rows, net.input_dim)).astype(np.float32)
@@ -166,7 +167,6 @@ def cpu_train_frames_per_sec(cfg_text, rows, steps, warmup, threads):
     for _ in range(steps):
         net.train_step(x, labels)
     dt = time.perf_counter() - t0
-    used = threads if (kind == "reference" and hasattr(backend, "set_num_threads")) else 1
     return rows * steps / dt, dt / steps, kind, used
 
 

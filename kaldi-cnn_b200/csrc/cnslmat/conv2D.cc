@@ -168,6 +168,7 @@ namespace {
 __global__ void mod_permute_channels_kernel(float *comp, ::MatrixDim cd, float *container,
                                             ::MatrixDim kd, int comp_idx, int num_component, int hw,
                                             bool to_container) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)cd.rows * cd.cols) return;
   int i = (int)(t / cd.cols), j = (int)(t % cd.cols);

@@ -51,6 +51,7 @@ template <bool kColSum>
 __global__ void __launch_bounds__(256)
 pack_channels_last_kernel(const float *__restrict__ in, int ld, int N, int C, int R, float *__restrict__ out,
                           float *__restrict__ partial, int spc, FastDiv div_r, FastDiv div_ch) {
+  kcnn::pdl_prologue();
   extern __shared__ float tile[];
   const int rp = R | 1;
   const int c0 = blockIdx.y * kPackCh;

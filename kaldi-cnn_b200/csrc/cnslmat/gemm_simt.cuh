@@ -37,6 +37,7 @@ struct SimtGemm {
 template <class G, class OpA, class OpB, class Out, bool kAFastK, bool kBFastK, bool kEpiFastN>
 __global__ void __launch_bounds__(STHREADS)
 gemm_simt_kernel(const SimtGemm<OpA, OpB, Out, kAFastK, kBFastK, kEpiFastN> g) {
+  kcnn::pdl_prologue();
   __shared__ float As[2][SBK][SPITCH];
   __shared__ float Bs[2][SBK][SPITCH];
 
@@ -181,6 +182,7 @@ template <class Out>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, Out out,
                      FastDiv div_n) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)M * N) return;
   uint32_t m, n;

@@ -203,6 +203,7 @@ __device__ __forceinline__ void store_slice(const float4 (&v)[ROWS / 32], uint32
 template <int BN, bool kAFastK, bool kBFastK, bool kEpiFastN, class OpA, class OpB, class Out>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const TcGemm<OpA, OpB, Out> g) {
+  kcnn::pdl_prologue();
   using S = Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -383,6 +384,7 @@ gemm_tc_kernel(const TcGemm<OpA, OpB, Out> g) {
 template <class Out>
 __global__ void __launch_bounds__(256)
 tc_splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, Out out, FastDiv div_n) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)M * N) return;
   uint32_t m, n;
@@ -432,8 +434,7 @@ void launch_bn(cudaStream_t st, const OpA &a, const OpB &b, const Out &out, int 
     attr_set = true;
   }
   dim3 grid(ceil_div_u(M, BM), ceil_div_u(N, BN), splits);
-  kernel<<<grid, THREADS, S::TOTAL, st>>>(g);
-  count_launch();
+  launch_kernel(kernel, grid, dim3(THREADS), (size_t)S::TOTAL, st, 1u, g);
   if (splits > 1)
     KCNN_LAUNCH(tc_splitk_reduce_kernel<Out>, ceil_div_u((long long)M * N, 256), 256, 0, st, workspace,
                 splits, M, N, out, FastDiv((uint32_t)N));

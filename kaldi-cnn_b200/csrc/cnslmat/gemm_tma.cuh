@@ -190,6 +190,7 @@ template <class Prob, bool kPair, int STAGES>
 __global__ void __launch_bounds__(THREADS, STAGES <= 2 ? 3 : (STAGES <= 3 ? 2 : 1))
 tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const Prob prob) {
+  kcnn::pdl_trigger();
   constexpr int kCols = kPair ? 2 * BN : BN;        // TMEM columns = accumulator columns per CTA
   constexpr int BAR_OFFSET = Ring<STAGES>::BAR_OFFSET;
   extern __shared__ uint8_t smem_raw[];
@@ -236,6 +237,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  kcnn::pdl_wait();                 // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer --
@@ -349,6 +351,7 @@ template <class Prob>
 __global__ void __launch_bounds__(THREADS, 1)
 tma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                            const Prob prob, int tiles_m, int tiles_n, int splits) {
+  kcnn::pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -391,6 +394,7 @@ tma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  kcnn::pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer --
@@ -662,6 +666,7 @@ template <int kEpi, class RowMap>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, float *__restrict__ out, int ldo,
                      const float *__restrict__ bias_n, float *__restrict__ aux, SgdCoef sgd, RowMap row_of) {
+  kcnn::pdl_prologue();
   const long long total4 = ((long long)M * N) >> 2;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
@@ -775,17 +780,7 @@ void launch_variant(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &m
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = kPair ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, ma, mb, p);
-  count_launch();
+  launch_kernel(kernel, grid, dim3(THREADS), (size_t)smem, st, kPair ? 2u : 1u, ma, mb, p);
 }
 
 template <class Prob>
@@ -798,8 +793,8 @@ void launch_persistent(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap
   }
   long long total = (long long)tiles.x * tiles.y * tiles.z;
   unsigned ctas = (unsigned)(total < kNumSMs ? total : kNumSMs);
-  kernel<<<ctas, THREADS, PRing::SMEM_TOTAL, st>>>(ma, mb, p, (int)tiles.x, (int)tiles.y, (int)tiles.z);
-  count_launch();
+  launch_kernel(kernel, dim3(ctas), dim3(THREADS), (size_t)PRing::SMEM_TOTAL, st, 1u, ma, mb, p, (int)tiles.x,
+                (int)tiles.y, (int)tiles.z);
 }
 
 // grid = (128-row tiles, 128-column tiles, splits).  pair: 2-CTA clusters along x, 256-column

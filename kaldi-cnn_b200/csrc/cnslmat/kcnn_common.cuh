@@ -21,11 +21,64 @@ extern cudaStream_t g_legacy_stream;
 
 inline void count_launch() { ++g_launch_count; }
 
-#define KCNN_LAUNCH(kernel, grid, block, smem, stream, ...)        \
-  do {                                                             \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
-    ::kcnn::count_launch();                                        \
-  } while (0)
+// Programmatic dependent launch (PDL): every kernel of the library starts with
+// pdl_prologue() -- "let the NEXT kernel of the stream be scheduled as soon as all my CTAs
+// have started; wait until the PREVIOUS kernel has completed and flushed" -- and is launched
+// with the programmatic-stream-serialization attribute, so the launch latency and the
+// prologue of kernel i+1 (barrier init, TMEM allocation, tensor-map fetch) hide under the
+// tail of kernel i instead of adding ~90 serial gaps to a training step.  Without the
+// attribute (the default; KCNN_PDL=1 turns it on) both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+// The two halves separately, for kernels whose set-up (barrier init, TMEM allocation) may
+// run before the previous kernel has finished: trigger first, wait right before the first
+// access to memory another kernel may have written.
+__device__ __forceinline__ void pdl_trigger() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+bool pdl_enabled();      // kcnn_lib.cu: KCNN_PDL=1 turns the launch attribute on
+
+template <class... KArgs, class... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          unsigned cluster_x, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    n++;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  count_launch();
+}
+
+#define KCNN_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ::kcnn::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), 1u, __VA_ARGS__)
 
 inline unsigned int ceil_div_u(long long a, long long b) {
   return (unsigned int)((a + b - 1) / b);

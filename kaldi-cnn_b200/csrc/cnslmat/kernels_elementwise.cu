@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256)
 sgd_momentum_kernel(float *__restrict__ w, int w_stride, float *__restrict__ p, int p_stride,
                     const float *__restrict__ g, int g_stride, int rows, int cols, float momentum,
                     float a_decay, float a_grad, FastDiv div_units) {
+  kcnn::pdl_prologue();
   const int units = kVec4 ? cols / 4 : cols;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * units) return;
@@ -52,6 +53,7 @@ sgd_momentum_kernel(float *__restrict__ w, int w_stride, float *__restrict__ p, 
 
 __global__ void __launch_bounds__(256)
 vec_axpy_kernel(float *__restrict__ v, const float *__restrict__ g, int dim, float alpha) {
+  kcnn::pdl_prologue();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < dim) v[t] = fmaf(alpha, __ldg(g + t), v[t]);
 }
@@ -60,6 +62,7 @@ template <bool kVec4>
 __global__ void __launch_bounds__(256)
 relu_fprop_kernel(const float *__restrict__ in, int in_stride, float *__restrict__ out,
                   int out_stride, int rows, int cols, FastDiv div_units) {
+  kcnn::pdl_prologue();
   const int units = kVec4 ? cols / 4 : cols;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * units) return;
@@ -81,6 +84,7 @@ __global__ void __launch_bounds__(256)
 relu_bprop_kernel(const float *__restrict__ ov, int ov_stride, const float *__restrict__ od,
                   int od_stride, float *__restrict__ id, int id_stride, int rows, int cols,
                   FastDiv div_units) {
+  kcnn::pdl_prologue();
   const int units = kVec4 ? cols / 4 : cols;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * units) return;
@@ -120,6 +124,7 @@ __device__ __forceinline__ float block_reduce(float v, float *scratch, bool is_m
 __global__ void __launch_bounds__(256)
 softmax_fprop_kernel(const float *__restrict__ in, int in_stride, float *__restrict__ out,
                      int out_stride, int cols) {
+  kcnn::pdl_prologue();
   __shared__ float scratch[32];
   const float *x = in + (size_t)blockIdx.x * in_stride;
   float *y = out + (size_t)blockIdx.x * out_stride;
@@ -144,6 +149,7 @@ softmax_fprop_kernel(const float *__restrict__ in, int in_stride, float *__restr
 __global__ void __launch_bounds__(256)
 softmax_bprop_kernel(const float *__restrict__ ov, int ov_stride, const float *__restrict__ od,
                      int od_stride, float *__restrict__ id, int id_stride, int cols) {
+  kcnn::pdl_prologue();
   __shared__ float scratch[32];
   const float *y = ov + (size_t)blockIdx.x * ov_stride;
   const float *d = od + (size_t)blockIdx.x * od_stride;
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(256)
 xent_deriv_kernel(const float *__restrict__ post, int post_stride, const int *__restrict__ labels,
                   float *__restrict__ deriv, int deriv_stride, int rows, int cols,
                   double *objf_accum, FastDiv div_cols) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * cols) return;
   uint32_t i, j;

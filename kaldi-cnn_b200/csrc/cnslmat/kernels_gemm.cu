@@ -138,6 +138,7 @@ static Out33 make_out(float *base, const Dec3 &m, const Dec3 &n, const float *bi
 __global__ void __launch_bounds__(256)
 colsum_maps_kernel(const float *__restrict__ m, int rows, int stride, int inner,
                    float *__restrict__ out, FastDiv div_inner) {
+  kcnn::pdl_prologue();
   __shared__ float scratch[8];
   const int g = blockIdx.x;
   const float *base = m + (size_t)g * inner;
@@ -163,6 +164,7 @@ colsum_maps_kernel(const float *__restrict__ m, int rows, int stride, int inner,
 __global__ void __launch_bounds__(1024)
 colsum_rows_kernel(const float *__restrict__ m, int rows, int cols, int stride,
                    float *__restrict__ out, float alpha, int accumulate) {
+  kcnn::pdl_prologue();
   __shared__ float part[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;

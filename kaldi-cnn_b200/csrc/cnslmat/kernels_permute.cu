@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256)
 swap_outer_direct(const float *__restrict__ in, float *__restrict__ out, int A, int B, int L,
                   long long sa_in, long long sb_in, long long sb_out, long long sa_out,
                   FastDiv div_L, FastDiv div_A, int ab_limit) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)A * B * L) return;
   // order threads by OUTPUT address: (b, a, x)
@@ -49,6 +50,7 @@ swap_outer_direct(const float *__restrict__ in, float *__restrict__ out, int A, 
 __global__ void __launch_bounds__(256)
 swap_outer_tiled(const float *__restrict__ in, float *__restrict__ out, int A, int B, int L,
                  int KB, long long sa_in, long long sb_out) {
+  kcnn::pdl_prologue();
   extern __shared__ float tile[];
   const int a0 = blockIdx.x * 32, b0 = blockIdx.y * KB;
   const int na = min(32, A - a0), nb = min(KB, B - b0);
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(256)
 swap_inner_tiled(const float *__restrict__ in, float *__restrict__ out, int R, int Q,
                  long long base_in, long long sz_in, long long sr_in, long long sz_out,
                  long long sq_out) {
+  kcnn::pdl_prologue();
   __shared__ float tile[32][33];
   const int z = blockIdx.z;
   const int q0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(256)
 pad_zero_kernel(const float *__restrict__ orig, int orig_stride, float *__restrict__ pad,
                 int pad_stride, int rows, int pad_cols, int H, int W, int KH, int KW, int PH,
                 FastDiv div_cols, FastDiv div_ps, FastDiv div_ph) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * pad_cols) return;
   uint32_t i, j, c, p, J, I;
@@ -129,6 +133,7 @@ template <bool kVec4>
 __global__ void __launch_bounds__(256)
 add_mat_rep_vec_kernel(const float *__restrict__ vec, float *__restrict__ out, int rows,
                        int cols, int stride, FastDiv div_units, FastDiv div_rep) {
+  kcnn::pdl_prologue();
   const int units = kVec4 ? cols / 4 : cols;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * units) return;
@@ -151,6 +156,7 @@ add_mat_rep_vec_kernel(const float *__restrict__ vec, float *__restrict__ out, i
 __global__ void __launch_bounds__(256)
 copy_rows_at_kernel(const float *__restrict__ src, int src_stride, float *__restrict__ dest,
                     int dest_stride, int rows, int cols, int row_offset, FastDiv div_cols) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * cols) return;
   uint32_t i, j;
@@ -165,6 +171,7 @@ span_row_to_convmat_kernel(const float *__restrict__ in, int in_rows, int in_str
                            int span_stride, int H, int W, int KH, int KW, int row_offset,
                            FastDiv div_cols, FastDiv div_rows, FastDiv div_ks, FastDiv div_kh,
                            FastDiv div_q) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)span_rows * span_cols) return;
   uint32_t i, j, I, Ir, J, Jr, kw, kh, ow, oh;

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256)
 maxpool_prop_scalar(const float *__restrict__ src, int src_stride, float *__restrict__ pool,
                     int pool_stride, unsigned char *__restrict__ index, int index_stride,
                     int rows, PoolGeom g, FastDiv div_cols) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * g.out_cols) return;
   uint32_t i, j;
@@ -92,6 +93,7 @@ maxpool_prop_time_vec4(const float *__restrict__ src, int src_stride, float *__r
                        int pool_stride, unsigned char *__restrict__ index, int index_stride,
                        int rows, int W, int pc, int quads_per_row, FastDiv div_quads,
                        FastDiv div_owq) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * quads_per_row) return;
   uint32_t i, q, oc, owq;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(256)
 maxpool_prop_overlap(const float *__restrict__ src, int src_stride, float *__restrict__ pool,
                      int pool_stride, int rows, int out_cols, int HW, int pc, int o2, int i2,
                      FastDiv div_cols, FastDiv div_hw, FastDiv div_o2) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * out_cols) return;
   uint32_t i, j, oc, pos;
@@ -168,6 +171,7 @@ maxpool_backprop_scalar(const float *__restrict__ in_val, int in_stride,
                         const float *__restrict__ out_deriv, int od_stride,
                         float *__restrict__ dest, int dest_stride, int rows, PoolGeom g,
                         FastDiv div_cols) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * g.out_cols) return;
   uint32_t i, j, oc, pos, ow, oh;
@@ -198,6 +202,7 @@ maxpool_backprop_time_vec4(const float *__restrict__ in_val, int in_stride,
                            const float *__restrict__ out_deriv, int od_stride,
                            float *__restrict__ dest, int dest_stride, int rows, int W, int pc,
                            int quads_per_row, FastDiv div_quads, FastDiv div_owq) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * quads_per_row) return;
   uint32_t i, q, oc, owq;
@@ -240,6 +245,7 @@ maxpool_backprop_overlap(const float *__restrict__ in_val, int in_stride,
                          float *__restrict__ dest, int dest_stride, int rows, int in_cols,
                          int HW, int pc, int OC, int o2, int i2, FastDiv div_cols,
                          FastDiv div_hw, FastDiv div_i2) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * in_cols) return;
   uint32_t i, col, c, pos;
@@ -277,6 +283,7 @@ maxpool_backprop_index_scalar(const unsigned char *__restrict__ index, int index
                               const float *__restrict__ out_deriv, int od_stride,
                               float *__restrict__ dest, int dest_stride, int rows, PoolGeom g,
                               FastDiv div_cols) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * g.out_cols) return;
   uint32_t i, j, oc, pos, ow, oh;
@@ -300,6 +307,7 @@ maxpool_backprop_index_time_vec4(const unsigned char *__restrict__ index, int in
                                  const float *__restrict__ out_deriv, int od_stride,
                                  float *__restrict__ dest, int dest_stride, int rows, int W,
                                  int pc, int quads_per_row, FastDiv div_quads, FastDiv div_owq) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)rows * quads_per_row) return;
   uint32_t i, q, oc, owq;

@@ -9,6 +9,7 @@ using kcnn::ceil_div_u;
 
 template <class F>
 __global__ void __launch_bounds__(256) map_mat_kernel(MatrixDim d, FastDiv div_cols, F f) {
+  kcnn::pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)d.rows * d.cols) return;
   uint32_t i, j;
@@ -25,6 +26,7 @@ static void map_mat(cudaStream_t st, MatrixDim d, F f) {
 
 template <class F>
 __global__ void __launch_bounds__(256) map_vec_kernel(int dim, F f) {
+  kcnn::pdl_prologue();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < dim) f(t);
 }

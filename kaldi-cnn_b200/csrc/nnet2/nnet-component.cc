@@ -185,6 +185,7 @@ namespace {
 __global__ void __launch_bounds__(1024)
 nonlin_stats_kernel(const float *__restrict__ y, ::MatrixDim d, double *value_sum,
                     double *deriv_sum) {
+  kcnn::pdl_prologue();
   __shared__ float pv[32][33], pd[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -216,38 +217,57 @@ nonlin_stats_kernel(const float *__restrict__ y, ::MatrixDim d, double *value_su
 // RectifiedLinearComponent::Backprop and the statistics of NonlinearComponent::UpdateStats
 // (reference nnet2/nnet-component.cc:337-363, 813-827) in ONE pass over out_value:
 // in_deriv = out_deriv * [y > 0], value_sum += colsum(y), deriv_sum += colsum([y > 0]).
-__global__ void __launch_bounds__(1024)
+// CTA = 128 columns (32 lanes x float4) x 64 rows (8 row-threads x 8 rows, all loads
+// independent); per-CTA column sums go to the double accumulators with atomics (sums of a
+// few hundred floats in double: order does not change the result in practice).
+constexpr int kReluRowsPerCta = 64;
+__global__ void __launch_bounds__(256)
 relu_bprop_stats_kernel(const float *__restrict__ y, ::MatrixDim yd, const float *__restrict__ od,
                         int od_stride, float *__restrict__ id, int id_stride, double *value_sum,
                         double *deriv_sum) {
-  __shared__ float pv[32][33], pd[32][33];
+  kcnn::pdl_prologue();
+  __shared__ float4 pv[8][33], pd[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + tx;
-  float sv0 = 0.0f, sv1 = 0.0f, sd0 = 0.0f, sd1 = 0.0f;
+  const int col = (blockIdx.x * 32 + tx) * 4;
+  const int r0 = blockIdx.y * kReluRowsPerCta;
+  float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), sd = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < yd.cols) {
-    int r = ty;
-    for (; r + 32 < yd.rows; r += 64) {
-      const float a = __ldg(y + (size_t)r * yd.stride + col), b = __ldg(y + (size_t)(r + 32) * yd.stride + col);
-      const float da = __ldg(od + (size_t)r * od_stride + col), db = __ldg(od + (size_t)(r + 32) * od_stride + col);
-      id[(size_t)r * id_stride + col] = a > 0.0f ? da : 0.0f;
-      id[(size_t)(r + 32) * id_stride + col] = b > 0.0f ? db : 0.0f;
-      sv0 += a; sd0 += a > 0.0f ? 1.0f : 0.0f;
-      sv1 += b; sd1 += b > 0.0f ? 1.0f : 0.0f;
+    float4 a[8], d[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int r = r0 + ty + 8 * k;
+      if (r < yd.rows) {
+        a[k] = __ldg(reinterpret_cast<const float4 *>(y + (size_t)r * yd.stride + col));
+        d[k] = __ldg(reinterpret_cast<const float4 *>(od + (size_t)r * od_stride + col));
+      }
     }
-    for (; r < yd.rows; r += 32) {
-      const float a = __ldg(y + (size_t)r * yd.stride + col);
-      id[(size_t)r * id_stride + col] = a > 0.0f ? __ldg(od + (size_t)r * od_stride + col) : 0.0f;
-      sv0 += a; sd0 += a > 0.0f ? 1.0f : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int r = r0 + ty + 8 * k;
+      if (r < yd.rows) {
+        float4 o;
+        o.x = a[k].x > 0.0f ? d[k].x : 0.0f; o.y = a[k].y > 0.0f ? d[k].y : 0.0f;
+        o.z = a[k].z > 0.0f ? d[k].z : 0.0f; o.w = a[k].w > 0.0f ? d[k].w : 0.0f;
+        *reinterpret_cast<float4 *>(id + (size_t)r * id_stride + col) = o;
+        sv.x += a[k].x; sv.y += a[k].y; sv.z += a[k].z; sv.w += a[k].w;
+        sd.x += a[k].x > 0.0f ? 1.0f : 0.0f; sd.y += a[k].y > 0.0f ? 1.0f : 0.0f;
+        sd.z += a[k].z > 0.0f ? 1.0f : 0.0f; sd.w += a[k].w > 0.0f ? 1.0f : 0.0f;
+      }
     }
   }
-  pv[ty][tx] = sv0 + sv1; pd[ty][tx] = sd0 + sd1;
+  pv[ty][tx] = sv; pd[ty][tx] = sd;
   __syncthreads();
   if (ty == 0 && col < yd.cols) {
-    float a = 0.0f, b = 0.0f;
+    float4 v = pv[0][tx], w = pd[0][tx];
 #pragma unroll
-    for (int i = 0; i < 32; i++) { a += pv[i][tx]; b += pd[i][tx]; }
-    value_sum[col] += (double)a;
-    deriv_sum[col] += (double)b;
+    for (int i = 1; i < 8; i++) {
+      v.x += pv[i][tx].x; v.y += pv[i][tx].y; v.z += pv[i][tx].z; v.w += pv[i][tx].w;
+      w.x += pd[i][tx].x; w.y += pd[i][tx].y; w.z += pd[i][tx].z; w.w += pd[i][tx].w;
+    }
+    atomicAdd(value_sum + col, (double)v.x); atomicAdd(value_sum + col + 1, (double)v.y);
+    atomicAdd(value_sum + col + 2, (double)v.z); atomicAdd(value_sum + col + 3, (double)v.w);
+    atomicAdd(deriv_sum + col, (double)w.x); atomicAdd(deriv_sum + col + 1, (double)w.y);
+    atomicAdd(deriv_sum + col + 2, (double)w.z); atomicAdd(deriv_sum + col + 3, (double)w.w);
   }
 }
 
@@ -266,6 +286,7 @@ __global__ void __launch_bounds__(256)
 dropout_fprop_kernel(const float *__restrict__ in, ::MatrixDim id, float *__restrict__ out,
                      ::MatrixDim od, float dp, float low, float high,
                      const unsigned long long *seed_dev, kcnn::FastDiv div_units) {
+  kcnn::pdl_prologue();
   const int units = kVec4 ? od.cols / 4 : od.cols;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)od.rows * units) return;
@@ -288,7 +309,8 @@ dropout_fprop_kernel(const float *__restrict__ in, ::MatrixDim id, float *__rest
   }
 }
 
-__global__ void bump_seed_kernel(unsigned long long *seed_dev) { *seed_dev += 1; }
+__global__ void bump_seed_kernel(unsigned long long *seed_dev) {
+  kcnn::pdl_prologue(); *seed_dev += 1; }
 
 // in_deriv = out_deriv .* out_value ./ in_value   (out_deriv where in_value == 0):
 // Kaldi's AddMatMatDivMat, reference nnet2/nnet-component.cc:3634-3636.
@@ -297,6 +319,7 @@ __global__ void __launch_bounds__(256)
 dropout_bprop_kernel(const float *__restrict__ iv, int iv_stride, const float *__restrict__ ov,
                      int ov_stride, const float *__restrict__ od, int od_stride,
                      float *__restrict__ id, ::MatrixDim idd, kcnn::FastDiv div_units) {
+  kcnn::pdl_prologue();
   const int units = kVec4 ? idd.cols / 4 : idd.cols;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)idd.rows * units) return;
@@ -361,11 +384,20 @@ void NonlinearComponent::BackpropReluWithStats(const CuMatrixBase<BaseFloat> &ou
                                                const CuMatrixBase<BaseFloat> &out_deriv,
                                                CuMatrix<BaseFloat> *in_deriv) {
   KALDI_ASSERT(out_value.NumCols() == InputDim());
+  const bool v4 = (dim_ & 3) == 0 && (out_value.Stride() & 3) == 0 && (out_deriv.Stride() & 3) == 0 &&
+                  (in_deriv->Stride() & 3) == 0 && ((uintptr_t)out_value.Data() & 15) == 0 &&
+                  ((uintptr_t)out_deriv.Data() & 15) == 0 && ((uintptr_t)in_deriv->Data() & 15) == 0;
+  if (!v4) {                                          // unaligned views: the two separate kernels
+    cudaF_relu_bprop(Str(), out_value.Data(), out_value.Dim(), out_deriv.Data(), out_deriv.Dim(),
+                     in_deriv->Data(), in_deriv->Dim());
+    UpdateStats(out_value, true);
+    return;
+  }
   EnsureStats();
   count_ += out_value.NumRows();
-  KCNN_LAUNCH(relu_bprop_stats_kernel, kcnn::ceil_div_u(dim_, 32), 1024, 0, Str(), out_value.Data(),
-              out_value.Dim(), out_deriv.Data(), out_deriv.Stride(), in_deriv->Data(), in_deriv->Stride(),
-              stats_, stats_ + dim_);
+  dim3 grid(kcnn::ceil_div_u(dim_, 128), kcnn::ceil_div_u(out_value.NumRows(), kReluRowsPerCta));
+  KCNN_LAUNCH(relu_bprop_stats_kernel, grid, 256, 0, Str(), out_value.Data(), out_value.Dim(),
+              out_deriv.Data(), out_deriv.Stride(), in_deriv->Data(), in_deriv->Stride(), stats_, stats_ + dim_);
 }
 
 void NonlinearComponent::GetStats(Vector<double> *value_sum, Vector<double> *deriv_sum) const {

@@ -11,6 +11,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define ORA_CAT(a, b) a##b
 
@@ -94,4 +97,16 @@ void oraF_softmax_backprop(const float *out_value, int rows, int cols, int ov_st
     for (int j = 0; j < cols; j++) dot += (double)y[j] * d[j];
     for (int j = 0; j < cols; j++) o[j] = y[j] * (d[j] - (float)dot);
   }
+}
+
+/* Host threads the GEMMs may use (bench.py's CPU legs set it to the box's core count;
+ * tests leave it alone).  Returns the number in effect; 1 when built without OpenMP. */
+int ora_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
 }

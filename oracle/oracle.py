@@ -25,10 +25,19 @@ def build(force=False):
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
-    cmd = ["gcc", "-O3", "-mavx2", "-mfma", "-fPIC", "-shared", "-std=c11",
+    cmd = ["gcc", "-O3", "-mavx2", "-mfma", "-fopenmp", "-fPIC", "-shared", "-std=c11",
            "-Wall", "-Wno-maybe-uninitialized", "-o", _LIB_PATH, src[0], "-lm"]
-    subprocess.run(cmd, check=True, cwd=_HERE)
+    if subprocess.run(cmd, cwd=_HERE, capture_output=True).returncode != 0:
+        cmd.remove("-fopenmp")                      # no libgomp: single-threaded build
+        subprocess.run(cmd, check=True, cwd=_HERE)
     return _LIB_PATH
+
+
+def set_num_threads(n):
+    """Host threads for the oracle's GEMMs; returns the number in effect."""
+    L = lib()
+    L.ora_set_num_threads.restype = ctypes.c_int
+    return int(L.ora_set_num_threads(int(n)))
 
 
 def lib():

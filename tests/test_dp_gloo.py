@@ -121,7 +121,7 @@ def _worker(rank, world, port, n_global, out):
         step = DataParallelStep(net, net.arena, [0, 2], dist, world)
         for _ in range(2):
             step(x[b:e], y[b:e], n_global)
-        out[rank] = (net.k.copy(), net.kb.copy(), net.w.copy(), net.wb.copy(), net.kp.copy())
+        np.savez(os.path.join(out, "rank%d.npz" % rank), k=net.k, kb=net.kb, w=net.w, wb=net.wb, kp=net.kp)
     finally:
         dist.destroy_process_group()
 
@@ -138,21 +138,20 @@ def test_shard_rows_partitions_exactly():
         shard_rows(4, 2, 2)
 
 
-def test_world_size_2_gloo_matches_single_process():
+def test_world_size_2_gloo_matches_single_process(tmp_path):
     n = 12
     x, y = _data(n)
     ref = OracleNet()
     single = DataParallelStep(ref, ref.arena, [0, 2], None, 1)
     for _ in range(2):
         single(x, y, n)
-    mgr = mp.Manager()
-    out = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
-    for rank in (0, 1):
-        for got, want in zip(out[rank], (ref.k, ref.kb, ref.w, ref.wb, ref.kp)):
-            assert np.abs(got - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
-    for a, b in zip(out[0], out[1]):                  # replicas stay bit-identical
-        assert np.array_equal(a, b)
+    mp.spawn(_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in (0, 1)]
+    want = dict(k=ref.k, kb=ref.kb, w=ref.w, wb=ref.wb, kp=ref.kp)
+    for name, w in want.items():
+        for r in (0, 1):
+            assert np.abs(got[r][name] - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), (name, r)
+        assert np.array_equal(got[0][name], got[1][name])          # replicas stay bit-identical
 
 
 def test_world_gt_1_needs_a_process_group():

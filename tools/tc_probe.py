@@ -115,10 +115,13 @@ def ncu_target(N=512):
     x = torch.randn(N, din, device="cuda"); w = torch.randn(dout, din, device="cuda") * 0.01
     b = torch.zeros(dout, device="cuda"); y = torch.empty(N, dout, device="cuda")
     g = torch.empty(dout, din, device="cuda"); bg = torch.empty(dout, device="cuda")
+    pv = torch.zeros(dout, din, device="cuda")
     for _ in range(2):
         L.cudaF_affine_fprop(stream(), math, ptr(x), mdim(x), ptr(w), mdim(w), ptr(b), ptr(y), mdim(y))
         L.cudaF_affine_dgrad(stream(), math, ptr(y), mdim(y), ptr(w), mdim(w), ptr(x), mdim(x))
         L.cudaF_affine_wgrad(stream(), math, ptr(x), mdim(x), ptr(y), mdim(y), ptr(g), mdim(g), ptr(bg))
+        L.cudaF_affine_wgrad_sgd(stream(), math, ptr(x), mdim(x), ptr(y), mdim(y), ptr(w), mdim(w), ptr(pv), mdim(pv),
+                                 ptr(b), 0.9, -1e-9, 1e-9)
     H, W, C, KH, KW, G = 1, 14, 256, 1, 3, 256
     OW = W - KW + 1
     xi = torch.randn(N, W * C, device="cuda"); k = torch.randn(KW * C, G, device="cuda") * 0.01
