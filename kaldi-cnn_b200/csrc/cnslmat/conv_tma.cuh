@@ -47,7 +47,7 @@ constexpr int kPackCh = 64;
 constexpr int kPackMaxSamples = 4;
 constexpr int kPackSmemBudget = 44 * 1024;
 
-template <bool kColSum>
+template <bool kColSum, bool kVec4>
 __global__ void __launch_bounds__(256)
 pack_channels_last_kernel(const float *__restrict__ in, int ld, int N, int C, int R, float *__restrict__ out,
                           float *__restrict__ partial, int spc, FastDiv div_r, FastDiv div_ch) {
@@ -60,23 +60,52 @@ pack_channels_last_kernel(const float *__restrict__ in, int ld, int N, int C, in
   const int ns = min(spc, N - n_begin);
   const int per = ch * R;                       // elements per sample in this CTA
   const int sample_tile = kPackCh * rp;
-  for (int s = 0; s < ns; s++) {
-    const float *src = in + (size_t)(n_begin + s) * ld + (size_t)c0 * R;
-    float *ts = tile + s * sample_tile;
-    for (int i = threadIdx.x; i < per; i += 256) {
-      uint32_t c, r;
-      div_r.divmod((uint32_t)i, c, r);
-      ts[c * rp + r] = __ldg(src + i);
+  if (kVec4) {
+    // 128-bit global accesses both ways (host checked: ch == 64, 16-byte aligned rows)
+    const int per4 = per >> 2;
+    for (int s = 0; s < ns; s++) {
+      const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)(n_begin + s) * ld + (size_t)c0 * R);
+      float *ts = tile + s * sample_tile;
+      for (int i4 = threadIdx.x; i4 < per4; i4 += 256) {
+        const float4 v = __ldg(src + i4);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          uint32_t c, r;
+          div_r.divmod((uint32_t)(4 * i4 + k), c, r);
+          ts[c * rp + r] = e[k];
+        }
+      }
     }
-  }
-  __syncthreads();
-  for (int s = 0; s < ns; s++) {
-    float *dst = out + (size_t)(n_begin + s) * R * C + c0;
-    const float *ts = tile + s * sample_tile;
-    for (int i = threadIdx.x; i < R * kPackCh; i += 256) {
-      uint32_t r, c;
-      div_ch.divmod((uint32_t)i, r, c);
-      if ((int)c < ch) dst[(size_t)r * C + c] = ts[c * rp + r];
+    __syncthreads();
+    for (int s = 0; s < ns; s++) {
+      float *dst = out + (size_t)(n_begin + s) * R * C + c0;
+      const float *ts = tile + s * sample_tile;
+      for (int i4 = threadIdx.x; i4 < R * (kPackCh / 4); i4 += 256) {
+        const int r = i4 >> 4, c = (i4 & 15) << 2;           // 16 float4 per position
+        const float *t4 = ts + c * rp + r;
+        *reinterpret_cast<float4 *>(dst + (size_t)r * C + c) = make_float4(t4[0], t4[rp], t4[2 * rp], t4[3 * rp]);
+      }
+    }
+  } else {
+    for (int s = 0; s < ns; s++) {
+      const float *src = in + (size_t)(n_begin + s) * ld + (size_t)c0 * R;
+      float *ts = tile + s * sample_tile;
+      for (int i = threadIdx.x; i < per; i += 256) {
+        uint32_t c, r;
+        div_r.divmod((uint32_t)i, c, r);
+        ts[c * rp + r] = __ldg(src + i);
+      }
+    }
+    __syncthreads();
+    for (int s = 0; s < ns; s++) {
+      float *dst = out + (size_t)(n_begin + s) * R * C + c0;
+      const float *ts = tile + s * sample_tile;
+      for (int i = threadIdx.x; i < R * kPackCh; i += 256) {
+        uint32_t r, c;
+        div_ch.divmod((uint32_t)i, r, c);
+        if ((int)c < ch) dst[(size_t)r * C + c] = ts[c * rp + r];
+      }
     }
   }
   if (kColSum && (int)threadIdx.x < ch) {
@@ -106,12 +135,19 @@ inline void launch_pack(cudaStream_t st, const float *in, int ld, int N, int C, 
   const int spc = pack_samples_per_cta(R);
   const size_t smem = (size_t)spc * kPackCh * (R | 1) * sizeof(float);
   dim3 grid((N + spc - 1) / spc, (C + kPackCh - 1) / kPackCh);
-  if (colsum_partial)
-    KCNN_LAUNCH(pack_channels_last_kernel<true>, grid, 256, smem, st, in, ld, N, C, R, out, colsum_partial, spc,
-                FastDiv((uint32_t)R), FastDiv((uint32_t)kPackCh));
-  else
-    KCNN_LAUNCH(pack_channels_last_kernel<false>, grid, 256, smem, st, in, ld, N, C, R, out, nullptr, spc,
-                FastDiv((uint32_t)R), FastDiv((uint32_t)kPackCh));
+  const bool v4 = (C % kPackCh) == 0 && (ld & 3) == 0 && host_aligned16(in) && host_aligned16(out);
+  const FastDiv dr((uint32_t)R), dc((uint32_t)kPackCh);
+  if (colsum_partial) {
+    if (v4) KCNN_LAUNCH((pack_channels_last_kernel<true, true>), grid, 256, smem, st, in, ld, N, C, R, out,
+                        colsum_partial, spc, dr, dc);
+    else    KCNN_LAUNCH((pack_channels_last_kernel<true, false>), grid, 256, smem, st, in, ld, N, C, R, out,
+                        colsum_partial, spc, dr, dc);
+  } else {
+    if (v4) KCNN_LAUNCH((pack_channels_last_kernel<false, true>), grid, 256, smem, st, in, ld, N, C, R, out,
+                        nullptr, spc, dr, dc);
+    else    KCNN_LAUNCH((pack_channels_last_kernel<false, false>), grid, 256, smem, st, in, ld, N, C, R, out,
+                        nullptr, spc, dr, dc);
+  }
 }
 
 // ------------------------------------------------------- fprop / dgrad problem --
