@@ -349,7 +349,7 @@ def run_ours(args):
     dp_step = None
     if world > 1:
         from kaldi_cnn_b200.dp import DataParallelStep
-        dp_step = DataParallelStep(net, arena, updatable, dist, world)
+        dp_step = DataParallelStep(net, arena, updatable, dist, world, skip_reduce=args.dp_skip_reduce)
 
     def step():
         if world == 1:
@@ -371,7 +371,9 @@ def run_ours(args):
         stream.synchronize()
         launches_per_step = int(L.kcnn_launch_count())
         graph = None
-        if args.graph and world == 1:
+        if args.graph and (world == 1 or os.environ.get("KCNN_BENCH_DP_GRAPH", "1") != "0"):
+            # world > 1: NCCL all-reduces are captured into the same graph (one replay per step
+            # on every rank); falls back to eager launches if the capture is refused.
             try:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream):
@@ -445,8 +447,7 @@ def run_ours(args):
 
     if rank != 0:
         if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
+            finish_distributed(dist)
         return
 
     frames = N * world * args.steps
@@ -480,6 +481,7 @@ def run_ours(args):
                    "l2": "working set (weights + momentum + gradients = %.0f MB) exceeds the 126 MB L2"
                          % (param_count(cfg) * 12 / 1e6),
                    "cuda_graph": graph is not None,
+                   **({"INVALID": "all-reduces skipped (--dp-skip-reduce diagnosis run)"} if args.dp_skip_reduce else {}),
                    "math": "KCNN_MATH_TF32_TC" if math == 1 else "KCNN_MATH_FP32_SIMT"},
         "step_tflops": step_tflops,
         "objf_per_frame_last": objf / max(N * (args.steps + 3 + 1), 1),
@@ -489,8 +491,19 @@ def run_ours(args):
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        finish_distributed(dist)
+
+
+def finish_distributed(dist):
+    """Leave a multi-rank run without tearing NCCL down: destroying the process group while a
+    captured graph still references its communicator can hang at exit (seen with 2 ranks)."""
+    import torch
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():
@@ -506,6 +519,8 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--dp-skip-reduce", action="store_true",
+                    help="diagnosis only: run the data-parallel step without its all-reduces (invalid as a result)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -291,3 +291,8 @@ class Nnet:
 
     def apply_gradients(self, total_rows):
         _check(_lib().kcnn_nnet_apply_gradients(self.h, int(total_rows)))
+
+    def apply_component_gradient(self, component, total_rows):
+        """The deferred SGD step of ONE updatable component (dp.py pipelines these under the
+        all-reduces of the layers below)."""
+        self.component(component).apply_gradient(total_rows)

@@ -33,8 +33,11 @@ def bucket_order(updatable):
 
 
 class DataParallelStep:
-    def __init__(self, net, arena, updatable, dist=None, world=1):
+    def __init__(self, net, arena, updatable, dist=None, world=1, skip_reduce=False):
+        """skip_reduce: diagnosis only (bench.py --dp-skip-reduce): the deferred-update step without
+        the all-reduces, to separate their cost from the cost of splitting Update."""
         self.net, self.arena, self.dist, self.world = net, arena, dist, world
+        self.skip_reduce = skip_reduce
         self.updatable = bucket_order(updatable)
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs a torch.distributed module / process group")
@@ -47,11 +50,16 @@ class DataParallelStep:
         for c in self.updatable:
             net.backward(hi, c)                       # layers hi .. c, update deferred
             off, ln = net.gradient_bucket(c)
-            if self.world > 1 and ln > 0:
+            if self.world > 1 and not self.skip_reduce:
                 works.append(self.dist.all_reduce(self.arena[off:off + ln], async_op=True))
             hi = c - 1
         if hi >= 0:
             net.backward(hi, 0)
-        for w in works:
+        if not works:
+            net.apply_gradients(rows_global)
+            return
+        # Pipelined apply: the reductions complete in issue order, so layer c's SGD step runs as
+        # soon as ITS bucket has arrived, under the reductions of the layers below it.
+        for c, w in zip(self.updatable, works):
             w.wait()
-        net.apply_gradients(rows_global)
+            net.apply_component_gradient(c, rows_global)

@@ -85,9 +85,15 @@ class OracleNet:
                 self.d = o.conv_backprop(d, self.k, H, W, C, 0, 0, KH, KW, G)
 
     def apply_gradients(self, rows):
+        for c in (0, 2):
+            self.apply_component_gradient(c, rows)
+
+    def apply_component_gradient(self, comp, rows):
         lr = np.float32(LR) / np.float32(rows)
         a = self.arena.numpy()
         for c, (w, b, p) in ((0, (self.k, self.kb, self.kp)), (2, (self.w, self.wb, self.wp))):
+            if c != comp:
+                continue
             off, _ = self.gradient_bucket(c)
             g = a[off:off + w.size].reshape(w.shape)
             bg = a[off + w.size:off + w.size + b.size]
