@@ -348,8 +348,13 @@ def run_ours(args):
 
     dp_step = None
     if world > 1:
-        from kaldi_cnn_b200.dp import DataParallelStep
-        dp_step = DataParallelStep(net, arena, updatable, dist, world, skip_reduce=args.dp_skip_reduce)
+        # Data parallel: software-pipelined step (dp.py) -- backward of batch t with the per-layer
+        # all-reduces, then forward of batch t+1, the FC stack's update sitting between the
+        # convolution forward and the FC forward so its all-reduce hides under both.
+        from kaldi_cnn_b200.dp import PipelinedDataParallelStep, late_components
+        small_group = dist.new_group(ranks=list(range(world)))
+        dp_step = PipelinedDataParallelStep(net, arena, updatable, dist, world, late_components(net, updatable),
+                                            small_group, skip_reduce=args.dp_skip_reduce)
 
     def step():
         if world == 1:
@@ -357,12 +362,12 @@ def run_ours(args):
             net.objf_and_deriv(labels)
             net.backward()
         else:
-            # data parallel: backward top-down, all-reduce each layer's gradient bucket as soon as
-            # its Backprop has been issued (overlaps the rest of the backward), then apply.
-            dp_step(feats, labels, N * world)
+            dp_step.rotate(feats, labels, N * world)
 
     with torch.cuda.stream(stream):
         kc.use_current_stream()
+        if dp_step is not None:
+            dp_step.prime(feats, labels)
         for _ in range(max(args.warmup, 3)):
             step()
         stream.synchronize()
@@ -477,6 +482,8 @@ def run_ours(args):
         "dtype": "tf32" if math == 1 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][1], "per_gpu_batch": N, "global_batch": N * world,
                    "parallelism": "dp%d" % world if world > 1 else "single",
+                   **({"dp_schedule": "pipelined: backward(t) + all-reduce + update + forward(t+1) per step"}
+                      if world > 1 else {}),
                    "params": param_count(cfg), "train_mflop_per_frame": flops_frame / 1e6,
                    "l2": "working set (weights + momentum + gradients = %.0f MB) exceeds the 126 MB L2"
                          % (param_count(cfg) * 12 / 1e6),

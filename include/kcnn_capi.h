@@ -158,6 +158,10 @@ int kcnn_nnet_output_dim(const kcnn_nnet *n);
 
 /* Forward through every component; feats is [rows x input_dim] on the device. */
 int kcnn_nnet_forward(kcnn_nnet *n, const float *feats, int rows, int stride);
+/* Propagate through components [first, last] only (first == 0 binds feats as the input; the
+ * activations below first must come from an earlier call on the same batch). */
+int kcnn_nnet_forward_range(kcnn_nnet *n, const float *feats, int rows, int stride, int first,
+                            int last);
 /* Cross-entropy derivative at the output for int32 device labels[rows]; the objective
  * sum_i log p[i, label_i] accumulates on the device. */
 int kcnn_nnet_objf_and_deriv(kcnn_nnet *n, const int *labels);

@@ -62,6 +62,7 @@ PROTOS = {
     "kcnn_nnet_input_dim": ([H], c_int),
     "kcnn_nnet_output_dim": ([H], c_int),
     "kcnn_nnet_forward": ([H, P, I, I], c_int),
+    "kcnn_nnet_forward_range": ([H, P, I, I, I, I], c_int),
     "kcnn_nnet_objf_and_deriv": ([H, P], c_int),
     "kcnn_nnet_backward": ([H, I, I], c_int),
     "kcnn_nnet_activation": ([H, I, PP, PI, PI, PI], c_int),

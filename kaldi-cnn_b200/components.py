@@ -237,6 +237,13 @@ class Nnet:
         d = capi.mdim(feats)
         _check(_lib().kcnn_nnet_forward(self.h, ctypes.c_void_p(feats.data_ptr()), d.rows, d.stride))
 
+    def forward_range(self, feats, first, last):
+        """Propagate through components [first, last] (first == 0 binds feats as the input)."""
+        use_current_stream()
+        d = capi.mdim(feats)
+        _check(_lib().kcnn_nnet_forward_range(self.h, ctypes.c_void_p(feats.data_ptr()), d.rows, d.stride,
+                                              int(first), int(last)))
+
     def objf_and_deriv(self, labels):
         _check(_lib().kcnn_nnet_objf_and_deriv(self.h, ctypes.c_void_p(labels.data_ptr())))
 

@@ -433,6 +433,15 @@ int kcnn_nnet_forward(kcnn_nnet *n, const float *feats, int rows, int stride) {
   KCNN_CATCH(-1)
 }
 
+int kcnn_nnet_forward_range(kcnn_nnet *n, const float *feats, int rows, int stride, int first, int last) {
+  KCNN_TRY
+  View F(feats, rows, N(n)->nnet.InputDim(), stride);
+  if (first < 0 || last >= N(n)->nnet.NumComponents()) KALDI_ERR << "bad component range";
+  N(n)->U().ForwardRange(F, first, last);
+  return 0;
+  KCNN_CATCH(-1)
+}
+
 int kcnn_nnet_objf_and_deriv(kcnn_nnet *n, const int *labels) {
   KCNN_TRY
   N(n)->U().ComputeObjfAndDeriv(labels);

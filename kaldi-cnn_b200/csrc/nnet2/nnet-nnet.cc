@@ -100,8 +100,13 @@ NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
 NnetMinibatchUpdater::~NnetMinibatchUpdater() { CuDevice::Instantiate().Free(objf_dev_); }
 
 void NnetMinibatchUpdater::Forward(const CuMatrixBase<BaseFloat> &feats) {
+  ForwardRange(feats, 0, nnet_->NumComponents() - 1);
+}
+
+void NnetMinibatchUpdater::ForwardRange(const CuMatrixBase<BaseFloat> &feats, int32 first, int32 last) {
   const int32 L = nnet_->NumComponents();
   KALDI_ASSERT(L > 0 && feats.NumCols() == nnet_->InputDim());
+  KALDI_ASSERT(first >= 0 && last < L);
   if (num_rows_ != feats.NumRows() || static_cast<int32>(forward_.size()) != L + 1) {
     num_rows_ = feats.NumRows();
     forward_.clear();
@@ -115,9 +120,10 @@ void NnetMinibatchUpdater::Forward(const CuMatrixBase<BaseFloat> &feats) {
     }
   }
   // the input is used in place (a borrowed view), not copied
-  forward_[0].Borrow(const_cast<BaseFloat *>(feats.Data()), feats.NumRows(), feats.NumCols(),
-                     feats.Stride());
-  for (int32 c = 0; c < L; c++)
+  if (first == 0)
+    forward_[0].Borrow(const_cast<BaseFloat *>(feats.Data()), feats.NumRows(), feats.NumCols(),
+                       feats.Stride());
+  for (int32 c = first; c <= last; c++)
     nnet_->GetComponent(c).Propagate(info_[c], info_[c + 1], forward_[c],
                                      static_cast<CuMatrixBase<BaseFloat> *>(&forward_[c + 1]));
 }

@@ -48,6 +48,11 @@ class NnetMinibatchUpdater {
   ~NnetMinibatchUpdater();
   /// feats: device [num_rows x InputDim()].  Runs Propagate through all components.
   void Forward(const CuMatrixBase<BaseFloat> &feats);
+  /// Propagate through components [first, last] only.  first == 0 binds `feats` as the input;
+  /// otherwise the activations below `first` must come from an earlier call on the same batch.
+  /// (Lets the data-parallel step run the layers whose weights are up to date while the
+  /// gradients of the others are still being all-reduced.)
+  void ForwardRange(const CuMatrixBase<BaseFloat> &feats, int32 first, int32 last);
   /// labels: device int32 [num_rows].  Writes the cross-entropy derivative at the output
   /// and accumulates sum_i log p[i, label_i] into the device objective.
   void ComputeObjfAndDeriv(const int32 *labels_dev);

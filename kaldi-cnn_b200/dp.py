@@ -32,6 +32,19 @@ def bucket_order(updatable):
     return sorted(updatable, reverse=True)
 
 
+def late_components(net, updatable, min_floats=1 << 20):
+    """Index of the first updatable component (in network order) from which on every updatable
+    component has a gradient bucket of at least `min_floats` -- the fully connected stack, 96 % of
+    the gradient bytes of the reference model -- or None."""
+    late = None
+    for c in sorted(updatable, reverse=True):
+        if net.gradient_bucket(c)[1] >= min_floats:
+            late = c
+        else:
+            break
+    return late
+
+
 class DataParallelStep:
     def __init__(self, net, arena, updatable, dist=None, world=1, skip_reduce=False):
         """skip_reduce: diagnosis only (bench.py --dp-skip-reduce): the deferred-update step without
@@ -63,3 +76,87 @@ class DataParallelStep:
         for c, w in zip(self.updatable, works):
             w.wait()
             net.apply_component_gradient(c, rows_global)
+
+
+class PipelinedDataParallelStep:
+    """The same step, software-pipelined across the batch boundary so that the big all-reduces
+    get the whole convolution backward AND the next batch's convolution forward to hide under:
+
+        prime(x0, y0):      forward(x0), objective / derivative
+        rotate(x1, y1, N):  backward(batch 0) with the all-reduces issued as each layer finishes
+                            small buckets (convolutions): wait, apply         [second communicator]
+                            forward(x1) through the layers BELOW the first late component
+                            late buckets (FC stack): wait, apply
+                            forward(x1) through the rest, objective / derivative of batch 1
+
+    Every weight is updated before the first forward pass that reads it, so the numbers are
+    those of the plain step; one rotate() is exactly one backward + update + forward.  The
+    small buckets go through their own communicator (`dist_small_group`): NCCL runs the
+    collectives of one communicator in issue order, and the convolution gradients -- produced
+    last -- must not queue behind 140 MB of FC gradients."""
+
+    def __init__(self, net, arena, updatable, dist, world, late_from, small_group=None, skip_reduce=False):
+        if world > 1 and dist is None:
+            raise ValueError("world > 1 needs a torch.distributed module / process group")
+        self.net, self.arena, self.dist, self.world = net, arena, dist, world
+        self.updatable = bucket_order(updatable)
+        self.late_from = late_from if late_from is not None else net.num_components
+        self.small_group = small_group
+        self.skip_reduce = skip_reduce
+        self.primed = False
+
+    def prime(self, feats, labels):
+        self.net.forward(feats)
+        self.net.objf_and_deriv(labels)
+        self.primed = True
+
+    def _reduce(self, c):
+        off, ln = self.net.gradient_bucket(c)
+        if self.world <= 1 or self.skip_reduce:
+            return None
+        group = self.small_group if c < self.late_from else None
+        return self.dist.all_reduce(self.arena[off:off + ln], group=group, async_op=True)
+
+    def rotate(self, feats_next, labels_next, rows_global):
+        if not self.primed:
+            raise RuntimeError("prime() the pipeline with the first batch")
+        net = self.net
+        works, hi = [], net.num_components - 1
+        for c in self.updatable:
+            net.backward(hi, c)
+            works.append((c, self._reduce(c)))
+            hi = c - 1
+        if hi >= 0:
+            net.backward(hi, 0)
+        for c, w in works:                            # convolutions: small, own communicator
+            if c < self.late_from:
+                if w is not None:
+                    w.wait()
+                net.apply_component_gradient(c, rows_global)
+        split = min(self.late_from, net.num_components)
+        if split > 0:
+            net.forward_range(feats_next, 0, split - 1)
+        for c, w in works:                            # FC stack, in issue order
+            if c >= self.late_from:
+                if w is not None:
+                    w.wait()
+                net.apply_component_gradient(c, rows_global)
+        if split < net.num_components:
+            net.forward_range(feats_next, split, net.num_components - 1)
+        net.objf_and_deriv(labels_next)
+
+    def finish(self, rows_global):
+        """Backward + update of the batch still in the pipeline (no further forward)."""
+        net = self.net
+        works, hi = [], net.num_components - 1
+        for c in self.updatable:
+            net.backward(hi, c)
+            works.append((c, self._reduce(c)))
+            hi = c - 1
+        if hi >= 0:
+            net.backward(hi, 0)
+        for c, w in works:
+            if w is not None:
+                w.wait()
+            net.apply_component_gradient(c, rows_global)
+        self.primed = False

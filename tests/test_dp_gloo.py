@@ -17,7 +17,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 import kaldi_cnn_b200  # noqa: E402,F401
-from kaldi_cnn_b200.dp import DataParallelStep, shard_rows  # noqa: E402
+from kaldi_cnn_b200.dp import (DataParallelStep, PipelinedDataParallelStep, late_components,  # noqa: E402
+                               shard_rows)
 
 H, W, C, KH, KW, G = 1, 10, 8, 1, 3, 12
 OW = W - KW + 1
@@ -45,12 +46,20 @@ class OracleNet:
         self.objf = 0.0
 
     def forward(self, x):
+        self.forward_range(x, 0, 3)
+
+    def forward_range(self, x, first, last):
         o = self.o
-        self.a0 = x
-        self.a1 = o.conv_propagate(x, self.k, self.kb, H, W, C, 0, 0, KH, KW, G)
-        self.a2 = np.maximum(self.a1, 0)
-        self.a3 = o.fc_propagate(self.a2, self.w, self.wb)
-        self.a4 = o.softmax_propagate(self.a3)
+        for c in range(first, last + 1):
+            if c == 0:
+                self.a0 = x
+                self.a1 = o.conv_propagate(x, self.k, self.kb, H, W, C, 0, 0, KH, KW, G)
+            elif c == 1:
+                self.a2 = np.maximum(self.a1, 0)
+            elif c == 2:
+                self.a3 = o.fc_propagate(self.a2, self.w, self.wb)
+            else:
+                self.a4 = o.softmax_propagate(self.a3)
 
     def objf_and_deriv(self, labels):
         n = self.a4.shape[0]
@@ -117,6 +126,24 @@ def _free_port():
     return port
 
 
+def _pipelined_worker(rank, world, port, n_global, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        small = dist.new_group(ranks=list(range(world)))
+        b, e = shard_rows(n_global, rank, world)
+        net = OracleNet()
+        step = PipelinedDataParallelStep(net, net.arena, [0, 2], dist, world, late_from=2, small_group=small)
+        batches = [_data(n_global, seed=11 + i) for i in range(3)]
+        step.prime(batches[0][0][b:e], batches[0][1][b:e])
+        for x, y in batches[1:]:
+            step.rotate(x[b:e], y[b:e], n_global)
+        step.finish(n_global)
+        np.savez(os.path.join(out, "prank%d.npz" % rank), k=net.k, kb=net.kb, w=net.w, wb=net.wb, kp=net.kp)
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, n_global, out):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -164,3 +191,28 @@ def test_world_gt_1_needs_a_process_group():
     net = OracleNet()
     with pytest.raises(ValueError):
         DataParallelStep(net, net.arena, [0, 2], None, 2)
+
+
+def test_late_components_picks_the_big_buckets():
+    net = OracleNet()
+    assert late_components(net, [0, 2], min_floats=DIN * DOUT) == 2
+    assert late_components(net, [0, 2], min_floats=1) == 0
+    assert late_components(net, [0, 2], min_floats=10 ** 9) is None
+
+
+def test_pipelined_step_matches_plain_step_world_2(tmp_path):
+    """Three batches through the software-pipelined step on two gloo ranks == three plain
+    single-process steps (every weight is updated before the forward pass that reads it)."""
+    n = 12
+    ref = OracleNet()
+    single = DataParallelStep(ref, ref.arena, [0, 2], None, 1)
+    for i in range(3):
+        x, y = _data(n, seed=11 + i)
+        single(x, y, n)
+    mp.spawn(_pipelined_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(os.path.join(str(tmp_path), "prank%d.npz" % r)) for r in (0, 1)]
+    want = dict(k=ref.k, kb=ref.kb, w=ref.w, wb=ref.wb, kp=ref.kp)
+    for name, w in want.items():
+        for r in (0, 1):
+            assert np.abs(got[r][name] - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), (name, r)
+        assert np.array_equal(got[0][name], got[1][name])
