@@ -305,14 +305,15 @@ struct ConvFullDgradProb {
 
 // --------------------------------------------------------------- wgrad problem --
 
-// GEMM row m = kw * C + c  ->  kernel-matrix row c * KW + kw (folds ModPermuteRow)
+// GEMM row m = kw * Cp + c (Cp = C rounded up to 32, so a 32-row operand atom never straddles
+// two taps)  ->  kernel-matrix row c * KW + kw (folds ModPermuteRow); rows c >= C are padding.
 struct KernelRow {
-  FastDiv div_c;
-  int KW;
+  FastDiv div_c;        // by Cp
+  int KW, C;
   __device__ __forceinline__ int operator()(int m) const {
     uint32_t kw, c;
     div_c.divmod((uint32_t)m, kw, c);
-    return (int)c * KW + (int)kw;
+    return (int)c < C ? (int)c * KW + (int)kw : -1;
   }
 };
 
@@ -321,7 +322,7 @@ struct KernelRow {
 template <int kEpi, bool kFull = false>
 struct ConvWgradProb {
   static constexpr bool kAMn = true, kBMn = true;
-  int C, KW, G, M;         // M = KW * C, rows m = kw * C + c   (kFull: M = C * ks, kernel order)
+  int C, KW, G, M;         // M = KW * Cp, rows m = kw * Cp + c   (kFull: M = C * ks, kernel order)
   int pw;
   int n_blocks;            // ceil(N / 32): K-blocks per output position
   int total_kb;            // OW * n_blocks
@@ -361,7 +362,7 @@ struct ConvWgradProb {
       if (kFull) {
         prefetch_tile_l2(tid, mt * BM, nt * BN, M, G, out, aux, ldo, IdentityRow());
       } else {
-        KernelRow rm; rm.div_c = div_c; rm.KW = KW;
+        KernelRow rm; rm.div_c = div_c; rm.KW = KW; rm.C = C;
         prefetch_tile_l2(tid, mt * BM, nt * BN, M, G, out, aux, ldo, rm);
       }
     }
@@ -375,7 +376,7 @@ struct ConvWgradProb {
     } else if (kFull) {
       store_rows<kEpi, kRows>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, IdentityRow());
     } else {
-      KernelRow rm; rm.div_c = div_c; rm.KW = KW;
+      KernelRow rm; rm.div_c = div_c; rm.KW = KW; rm.C = C;
       store_rows<kEpi, kRows>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, rm);
     }
   }
@@ -392,7 +393,7 @@ struct ConvShape {
 inline bool conv_tma_shape_ok(const ConvShape &q) {
   if (!enabled()) return false;
   if (q.N <= 0 || q.OW <= 0 || q.OW > 128 || q.W > 128) return false;
-  if (q.C < 32 || (q.C & 31) != 0) return false;          // 32-channel K slices / M atoms
+  if (q.C < 8 || (q.C & 3) != 0) return false;            // 16-byte pitch of the channels-last copy
   if (q.G < 32 || (q.G & 3) != 0) return false;
   if (pack_samples_per_cta(q.W) < 1 || pack_samples_per_cta(q.OW) < 1) return false;
   return true;
@@ -431,7 +432,7 @@ inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int
   p.num_samples = q.N; p.R = q.OW; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.C + 31) / 32;
   p.a_w0 = -q.pw; p.a_wstep = 1; p.out_maps = q.G; p.out = out; p.ldo = ldo; p.bias = bias;
   p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.OW);
-  launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1));
+  launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1), p.taps * p.inner_blocks);
   return true;
 }
 
@@ -472,7 +473,8 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
   float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float)) : nullptr;
   if (!dycl || (do_wgrad && !xcl) || (b.want_bias && !bpart)) return false;
 
-  const int M = q.KW * q.C;
+  const int Cp = (q.C + 31) & ~31;
+  const int M = q.KW * Cp;
   const int n_blocks = (q.N + 31) / 32;
   const int total_kb = q.OW * n_blocks;
   int splits = 1, per = total_kb;
@@ -502,7 +504,7 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
     p.a_w0 = q.pw; p.a_wstep = -1; p.out_maps = q.C; p.out = b.in_deriv; p.ldo = b.ld_id; p.bias = nullptr;
     p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.W);
-    launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
+    launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1), p.taps * p.inner_blocks);
   }
   if (!do_wgrad) return true;
   launch_pack(st, b.in_value, b.ld_iv, q.N, q.C, q.W, xcl, nullptr);
@@ -512,13 +514,13 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     p.C = q.C; p.KW = q.KW; p.G = q.G; p.M = M; p.pw = q.pw; p.n_blocks = n_blocks; p.total_kb = total_kb;
     p.kb_per_split = per; p.out = wout; p.ldo = ld_w; p.workspace = ws; p.aux = b.prev;
     p.sgd = b.sgd ? *b.sgd : none;
-    p.div_nb = FastDiv((uint32_t)n_blocks); p.div_c = FastDiv((uint32_t)q.C);
+    p.div_nb = FastDiv((uint32_t)n_blocks); p.div_c = FastDiv((uint32_t)Cp);
   };
   KernelRow rm;
-  rm.div_c = FastDiv((uint32_t)q.C); rm.KW = q.KW;
+  rm.div_c = FastDiv((uint32_t)Cp); rm.KW = q.KW; rm.C = q.C;
   if (splits > 1) {
     ConvWgradProb<EPI_PARTIAL> p; fill(p);
-    launch_prob(st, wa, wb, p, grid);
+    launch_prob(st, wa, wb, p, grid, per);
     const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
     if (b.sgd)
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, KernelRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout, ld_w,
@@ -528,10 +530,10 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
                   nullptr, nullptr, none, rm);
   } else if (b.sgd) {
     ConvWgradProb<EPI_SGD> p; fill(p);
-    launch_prob(st, wa, wb, p, grid);
+    launch_prob(st, wa, wb, p, grid, per);
   } else {
     ConvWgradProb<EPI_STORE> p; fill(p);
-    launch_prob(st, wa, wb, p, grid);
+    launch_prob(st, wa, wb, p, grid, per);
   }
   return true;
 }
@@ -571,7 +573,7 @@ inline bool conv_full_fprop(cudaStream_t st, const ConvFullShape &q, const float
   p.num_samples = q.N; p.OW = q.OW; p.nb = nb; p.ks = ks; p.j_blocks = (ks + 31) / 32; p.G = q.G;
   p.total_kb = q.C * p.j_blocks; p.out = out; p.ldo = ldo; p.bias = bias;
   p.div_jb = FastDiv((uint32_t)p.j_blocks); p.div_ow = FastDiv((uint32_t)q.OW);
-  launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1));
+  launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1), p.total_kb);
   return true;
 }
 
@@ -626,7 +628,7 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
     p.num_samples = q.N; p.W = q.W; p.H = q.H; p.C = q.C; p.nb = nb; p.nbc = nbc;
     p.g_blocks = (q.G + 31) / 32; p.total_kb = q.KW * p.g_blocks; p.out = b.in_deriv; p.ldo = b.ld_id;
     p.div_gb = FastDiv((uint32_t)p.g_blocks); p.div_h = FastDiv((uint32_t)q.H);
-    launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, nbc), 1));
+    launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, nbc), 1), p.total_kb);
   }
   if (!do_wgrad) return true;
   dim3 grid(ceil_div_u(M, BM), ceil_div_u(q.G, BN), splits);
@@ -639,7 +641,7 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
   };
   if (splits > 1) {
     ConvWgradProb<EPI_PARTIAL, true> p; fill(p);
-    launch_prob(st, wa, wb, p, grid);
+    launch_prob(st, wa, wb, p, grid, per);
     const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
     if (b.sgd)
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout, ld_w,
@@ -649,10 +651,10 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
                   ld_w, nullptr, nullptr, none, IdentityRow());
   } else if (b.sgd) {
     ConvWgradProb<EPI_SGD, true> p; fill(p);
-    launch_prob(st, wa, wb, p, grid);
+    launch_prob(st, wa, wb, p, grid, per);
   } else {
     ConvWgradProb<EPI_STORE, true> p; fill(p);
-    launch_prob(st, wa, wb, p, grid);
+    launch_prob(st, wa, wb, p, grid, per);
   }
   return true;
 }

@@ -510,7 +510,8 @@ __device__ __forceinline__ void sgd_apply(float &w, float &p, float g, const Sgd
 
 // Row-major 128-column segment store shared by the dense and the weight-gradient
 // problems: tid -> (row group, 4 columns); each warp instruction writes one 512-byte
-// row segment.  row_of(m) maps a tile row to the output row.
+// row segment.  row_of(m) maps a tile row to the output row; a negative result marks a padding
+// row of the GEMM that has no output row (skipped).
 template <int kEpi, int kRows, class RowMap>
 __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, int n0, int M, int N,
                                            float *obase, int ld, const float *bias_n, float *aux,
@@ -534,12 +535,14 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
     for (int r0 = 0; r0 < 32; r0 += RB) {
       float4 w[RB], pv[RB];
       size_t roff[RB];
+      bool okr[RB];
 #pragma unroll
       for (int i = 0; i < RB; i++) {
         const int mt = wl * 32 + r0 + i;
-        const bool ok = m0 + mt < M;
-        roff[i] = (size_t)row_of(ok ? m0 + mt : m0) * ld + n;
-        if (ok) {
+        const int row = m0 + mt < M ? row_of(m0 + mt) : -1;
+        okr[i] = row >= 0;
+        roff[i] = (size_t)(okr[i] ? row : 0) * ld + n;
+        if (okr[i]) {
           w[i] = *reinterpret_cast<const float4 *>(obase + roff[i]);
           pv[i] = *reinterpret_cast<const float4 *>(aux + roff[i]);
         }
@@ -547,7 +550,7 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
 #pragma unroll
       for (int i = 0; i < RB; i++) {
         const int mt = wl * 32 + r0 + i;
-        if (m0 + mt >= M) break;
+        if (!okr[i]) continue;
         const float4 a = *reinterpret_cast<const float4 *>(stage + mt * PITCH + 4 * lane);
         sgd_apply(w[i].x, pv[i].x, a.x, sgd); sgd_apply(w[i].y, pv[i].y, a.y, sgd);
         sgd_apply(w[i].z, pv[i].z, a.z, sgd); sgd_apply(w[i].w, pv[i].w, a.w, sgd);
@@ -561,8 +564,10 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
   for (int r = 0; r < 32; r++) {
     const int mt = wl * 32 + r;
     if (m0 + mt >= M) break;
+    const int row = row_of(m0 + mt);
+    if (row < 0) continue;
     float4 a = *reinterpret_cast<const float4 *>(stage + mt * PITCH + 4 * lane);
-    const size_t roff = (size_t)row_of(m0 + mt) * ld + n;
+    const size_t roff = (size_t)row * ld + n;
     float *orow = obase + roff;
     if (kEpi == EPI_SGD) {
       float *prow = aux + roff;
@@ -598,8 +603,9 @@ __device__ __forceinline__ void prefetch_tile_l2(int tid, int m0, int n0, int M,
   for (int i = tid; i < 128 * 4; i += 128) {
     const int r = i >> 2, line = i & 3;
     const int m = m0 + r, n = n0 + line * 32;
-    if (m < M && n < N) {
-      const size_t off = (size_t)row_of(m) * ld + n;
+    const int row = m < M ? row_of(m) : -1;
+    if (row >= 0 && n < N) {
+      const size_t off = (size_t)row * ld + n;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a + off));
       asm volatile("prefetch.global.L2 [%0];" ::"l"(b + off));
     }
@@ -677,7 +683,9 @@ splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, flo
     float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (size_t)z * M * N + e));
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-  const size_t off = (size_t)row_of(m) * ldo + n;
+  const int row = row_of(m);
+  if (row < 0) return;
+  const size_t off = (size_t)row * ldo + n;
   if (kEpi == EPI_SGD) {
     float4 w = *reinterpret_cast<const float4 *>(out + off);
     float4 pv = *reinterpret_cast<const float4 *>(aux + off);
@@ -801,12 +809,16 @@ void launch_persistent(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap
 // tiles along y (grid.x rounded up to even, grid.y halved).
 template <class Prob>
 void launch_prob(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 grid,
-                 bool pair = false) {
+                 int kb_per_tile, bool pair = false) {
   if (pair) {
     launch_variant<Prob, true, 3>(st, ma, mb, p, dim3((grid.x + 1) & ~1u, (grid.y + 1) / 2, grid.z));
   } else if ((long long)grid.x * grid.y * grid.z <= kNumSMs && deep_ring_enabled()) {
     launch_variant<Prob, false, 6>(st, ma, mb, p, grid);
-  } else if ((long long)grid.x * grid.y * grid.z > kNumSMs + kNumSMs / 2 && persistent_enabled()) {
+  } else if ((long long)grid.x * grid.y * grid.z > kNumSMs + kNumSMs / 2 && kb_per_tile <= 64 &&
+             persistent_enabled()) {
+    // many SHORT tiles (weight gradients): the epilogue is a large share of a tile, overlap it.
+    // Long-K tiles keep one tile per CTA, 2 CTAs per SM: 6 stages in flight per SM beat the
+    // persistent kernel's 4 (4096^3: 599 vs 488 TFLOP/s).
     launch_persistent<Prob>(st, ma, mb, p, grid);
   } else {
     launch_variant<Prob, false, 3>(st, ma, mb, p, grid);
@@ -849,7 +861,7 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
   };
   if (splits > 1) {
     DenseProb<kAMn, kBMn, EPI_PARTIAL> p; fill(p);
-    launch_prob(st, ma, mb, p, grid, pair);
+    launch_prob(st, ma, mb, p, grid, per, pair);
     const unsigned blocks = ceil_div_u(((long long)M * N) >> 2, 256);
     if (epi.mode == EPI_SGD)
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
@@ -859,10 +871,10 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
                   epi.bias_n, nullptr, epi.sgd, IdentityRow());
   } else if (epi.mode == EPI_SGD) {
     DenseProb<kAMn, kBMn, EPI_SGD> p; fill(p);
-    launch_prob(st, ma, mb, p, grid, pair);
+    launch_prob(st, ma, mb, p, grid, per, pair);
   } else {
     DenseProb<kAMn, kBMn, EPI_STORE> p; fill(p);
-    launch_prob(st, ma, mb, p, grid, pair);
+    launch_prob(st, ma, mb, p, grid, per, pair);
   }
   return true;
 }

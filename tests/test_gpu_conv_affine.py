@@ -26,6 +26,8 @@ CONVS = [
     ("conv6", 64, 1, 4, 512, 0, 0, 1, 3, 512),
     ("t_pad", 33, 1, 10, 64, 0, 1, 1, 3, 96),       # time-axis + zero padding, sample / map tile tails
     ("t_wide", 20, 1, 18, 32, 0, 2, 1, 5, 160),
+    ("t_c40", 17, 1, 12, 40, 0, 0, 1, 3, 64),        # channel count not a multiple of 32 (padded M atoms)
+    ("t_c200", 8, 1, 8, 200, 0, 0, 1, 5, 200),
     ("pad2d", 9, 6, 7, 5, 1, 1, 3, 3, 10),
     ("padw", 7, 5, 9, 4, 0, 2, 5, 4, 6),
     ("ragged", 5, 3, 5, 7, 0, 0, 2, 2, 3),
