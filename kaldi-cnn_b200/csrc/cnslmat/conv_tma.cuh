@@ -176,9 +176,15 @@ __device__ __forceinline__ void store_maps_transposed(const float *stage, int ti
 // Rows of the GEMM are (sample, position) with R positions per sample and NB = 128 / R
 // samples per tile; the K-blocks walk taps t (outer) x 32-wide slices of the reduced
 // channel axis (inner).  kBMn: fprop (B = kernel as [k rows][g]) ; !kBMn: dgrad (B rows c).
-template <bool kBMn_>
+// kPartial: split-K -- blockIdx.z owns K-blocks [z*kb_per_split, ...) and writes its tile
+// rows to workspace[z][(n*R + pos)][map]; conv_rows_reduce_kernel sums the splits into the
+// reference layout.  Used when the tile grid alone would leave most SMs idle (conv5 / conv6 of
+// nnet.config: 32 - 64 tiles with 24 - 48 K-blocks each).
+template <bool kBMn_, bool kPartial = false>
 struct ConvRowsProb {
   static constexpr bool kAMn = false, kBMn = kBMn_;
+  int kb_per_split;        // kPartial
+  float *workspace;        // kPartial: [splits][num_samples * R][out_maps]
   int num_samples;         // N
   int R;                   // positions per sample in the OUTPUT (OW for fprop, W for dgrad)
   int nb;                  // samples per tile
@@ -191,7 +197,16 @@ struct ConvRowsProb {
   const float *bias;       // per map or nullptr
   FastDiv div_inner, div_r;
 
-  __device__ __forceinline__ void kb_range(int, int &b, int &e) const { b = 0; e = taps * inner_blocks; }
+  __device__ __forceinline__ void kb_range(int z, int &b, int &e) const {
+    const int total = taps * inner_blocks;
+    if (kPartial) {
+      b = z * kb_per_split;
+      e = min(total, b + kb_per_split);
+      if (e < b) e = b;
+    } else {
+      b = 0; e = total;
+    }
+  }
   __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)(nb * R * 128 + B_STAGE_BYTES); }
   template <bool kPair>
   __device__ __forceinline__ void load(int kb, uint32_t a_addr, uint32_t b_addr, uint32_t bar,
@@ -213,10 +228,75 @@ struct ConvRowsProb {
   __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
     const int col0 = nt * BN;
     if (col0 >= out_maps) return;
-    store_maps_transposed(stage, tid, mt * nb, nb, R, col0, min(BN, out_maps - col0), num_samples, out, ldo, bias,
-                          div_r);
+    if (kPartial) {
+      const int M = num_samples * R, m0 = mt * nb * R;
+      SgdCoef none = {0.f, 0.f, 0.f};
+      store_rows<EPI_STORE, kRows>(stage, tid, m0, col0, min(M, m0 + nb * R), out_maps,
+                                   workspace + (size_t)z * M * out_maps, out_maps, nullptr, nullptr, none,
+                                   IdentityRow());
+    } else {
+      store_maps_transposed(stage, tid, mt * nb, nb, R, col0, min(BN, out_maps - col0), num_samples, out, ldo,
+                            bias, div_r);
+    }
   }
 };
+
+// out[n][g*R + pos] = sum_z ws[z][(n*R + pos)][g] (+ bias[g]); one thread per (row m, 4 maps).
+__global__ void __launch_bounds__(256)
+conv_rows_reduce_kernel(const float *__restrict__ ws, int splits, int M, int maps, int R, float *__restrict__ out,
+                        int ldo, const float *__restrict__ bias, FastDiv div_g4, FastDiv div_r) {
+  kcnn::pdl_prologue();
+  const int g4n = maps >> 2;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)M * g4n) return;
+  uint32_t m, g4, n, pos;
+  div_g4.divmod((uint32_t)t, m, g4);
+  div_r.divmod(m, n, pos);
+  const int g = (int)g4 << 2;
+  const size_t e = (size_t)m * maps + g;
+  float4 s = __ldg(reinterpret_cast<const float4 *>(ws + e));
+  for (int z = 1; z < splits; z++) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (size_t)z * M * maps + e));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  if (bias) { s.x += __ldg(bias + g); s.y += __ldg(bias + g + 1); s.z += __ldg(bias + g + 2); s.w += __ldg(bias + g + 3); }
+  float *o = out + (size_t)n * ldo + (size_t)g * R + pos;
+  o[0] = s.x; o[R] = s.y; o[2 * R] = s.z; o[3 * R] = s.w;
+}
+
+// Split count for a fprop / dgrad tile grid (1 = no split).
+inline int conv_rows_splits(long long tiles, int num_kb, int maps) {
+  if ((maps & 3) != 0 || tiles > kNumSMs / 2 || num_kb < 16) return 1;
+  long long want = kNumSMs / tiles;
+  if (want > num_kb / 8) want = num_kb / 8;
+  if (want > 8) want = 8;
+  return (int)(want < 1 ? 1 : want);
+}
+
+// Launches one fprop / dgrad problem, split over K when that fills the machine.
+template <bool kBMn>
+inline bool launch_conv_rows(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, ConvRowsProb<kBMn> p,
+                             dim3 grid) {
+  const int num_kb = p.taps * p.inner_blocks;
+  int splits = conv_rows_splits((long long)grid.x * grid.y, num_kb, p.out_maps);
+  int per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + per - 1) / per;
+  const int M = p.num_samples * p.R;
+  float *ws = splits > 1 ? scratch(SCRATCH_SPLITK, (size_t)splits * M * p.out_maps * sizeof(float)) : nullptr;
+  if (splits <= 1 || !ws) {
+    p.kb_per_split = num_kb; p.workspace = nullptr;
+    launch_prob(st, ma, mb, p, grid, num_kb);
+    return true;
+  }
+  ConvRowsProb<kBMn, true> q;
+  q.num_samples = p.num_samples; q.R = p.R; q.nb = p.nb; q.taps = p.taps; q.inner_blocks = p.inner_blocks;
+  q.a_w0 = p.a_w0; q.a_wstep = p.a_wstep; q.out_maps = p.out_maps; q.out = p.out; q.ldo = p.ldo; q.bias = p.bias;
+  q.div_inner = p.div_inner; q.div_r = p.div_r; q.kb_per_split = per; q.workspace = ws;
+  launch_prob(st, ma, mb, q, dim3(grid.x, grid.y, splits), per);
+  KCNN_LAUNCH(conv_rows_reduce_kernel, ceil_div_u((long long)M * (p.out_maps >> 2), 256), 256, 0, st, ws, splits, M,
+              p.out_maps, p.R, p.out, p.ldo, p.bias, FastDiv((uint32_t)(p.out_maps >> 2)), FastDiv((uint32_t)p.R));
+  return true;
+}
 
 // ------------------------------------------- full-height kernels (KH = H, OH = 1) --
 //
@@ -432,7 +512,7 @@ inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int
   p.num_samples = q.N; p.R = q.OW; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.C + 31) / 32;
   p.a_w0 = -q.pw; p.a_wstep = 1; p.out_maps = q.G; p.out = out; p.ldo = ldo; p.bias = bias;
   p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.OW);
-  launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1), p.taps * p.inner_blocks);
+  launch_conv_rows(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1));
   return true;
 }
 
@@ -504,7 +584,7 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
     p.a_w0 = q.pw; p.a_wstep = -1; p.out_maps = q.C; p.out = b.in_deriv; p.ldo = b.ld_id; p.bias = nullptr;
     p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.W);
-    launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1), p.taps * p.inner_blocks);
+    launch_conv_rows(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
   }
   if (!do_wgrad) return true;
   launch_pack(st, b.in_value, b.ld_iv, q.N, q.C, q.W, xcl, nullptr);
