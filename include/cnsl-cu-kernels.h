@@ -259,6 +259,7 @@ void cudaF_affine_wgrad(cudaStream_t st, int math, const float *in_value,
  *   apply != 0:  prev = momentum*prev + a_decay*K + a_grad*dK ; K += prev ;
  *                bias += a_grad * db       (kernel_grad / bias_grad unused)
  *   apply == 0:  kernel_grad = dK ; bias_grad = db
+ * staged_input: NULL, or the staging copy cudaF_conv2d_fprop_staged left for this in_value.
  * cudaF_affine_wgrad_sgd: FullyConnectedComponent::UpdateSimple (:1133-1143) with the
  * update applied in the weight-gradient GEMM's epilogue; the gradient is never stored. */
 int cudaF_conv2d_backward(cudaStream_t st, int math, const float *in_value,
@@ -267,9 +268,21 @@ int cudaF_conv2d_backward(cudaStream_t st, int math, const float *in_value,
                           float *in_deriv, MatrixDim in_deriv_dim, float *kernel_grad,
                           MatrixDim kernel_grad_dim, float *bias_grad, float *prev_grad,
                           MatrixDim prev_grad_dim, float *bias, int apply, float momentum,
-                          float decay_alpha, float grad_alpha, int in_height, int in_width,
-                          int in_channel, int pad_height, int pad_width, int kernel_height,
-                          int kernel_width, int group);
+                          float decay_alpha, float grad_alpha, const float *staged_input,
+                          int in_height, int in_width, int in_channel, int pad_height,
+                          int pad_width, int kernel_height, int kernel_width, int group);
+/* Forward pass that also LEAVES the channels-last staging copy of `in` in caller-owned memory
+ * (kcnn_conv2d_staging_floats() floats, 16-byte aligned; 0 = this shape has no staging copy),
+ * so that cudaF_conv2d_backward(..., staged_input = staging, ...) for the SAME in_value skips
+ * its own pack.  Returns 1 when the copy WAS written (tensor-core TMA path taken), else 0. */
+size_t kcnn_conv2d_staging_floats(int num_rows, int in_height, int in_width, int in_channel,
+                                  int pad_height, int pad_width, int kernel_height,
+                                  int kernel_width, int group);
+int cudaF_conv2d_fprop_staged(cudaStream_t st, int math, const float *in, MatrixDim in_dim,
+                               const float *kernel, MatrixDim kernel_dim, const float *bias,
+                               float *out, MatrixDim out_dim, int in_height, int in_width,
+                               int in_channel, int pad_height, int pad_width, int kernel_height,
+                               int kernel_width, int group, int concat, float *staging);
 int cudaF_affine_wgrad_sgd(cudaStream_t st, int math, const float *in_value,
                            MatrixDim in_value_dim, const float *out_deriv,
                            MatrixDim out_deriv_dim, float *w, MatrixDim w_dim,

@@ -76,8 +76,10 @@ _PROTOS = {
     "cudaF_affine_fprop": [S, I, P, M, P, M, P, P, M],
     "cudaF_affine_dgrad": [S, I, P, M, P, M, P, M],
     "cudaF_affine_wgrad": [S, I, P, M, P, M, P, M, P],
-    "cudaF_conv2d_backward": [S, I, P, M, P, M, P, M, P, M, P, M, P, P, M, P, I, F, F, F,
+    "cudaF_conv2d_backward": [S, I, P, M, P, M, P, M, P, M, P, M, P, P, M, P, I, F, F, F, P,
                               I, I, I, I, I, I, I, I],
+    "cudaF_conv2d_fprop_staged": [S, I, P, M, P, M, P, P, M, I, I, I, I, I, I, I, I, I, P],
+    "kcnn_conv2d_staging_floats": [I, I, I, I, I, I, I, I, I],
     "cudaF_affine_wgrad_sgd": [S, I, P, M, P, M, P, M, P, M, P, F, F, F],
     "cudaF_sgd_momentum_update": [S, P, M, P, M, P, M, F, F, F],
     "cudaF_vec_axpy": [S, P, P, I, F],
@@ -95,6 +97,8 @@ _RESTYPES = {
     "kcnn_abi_version": c_int,
     "kcnn_conv2d_wgrad_workspace": c_size_t,
     "cudaF_conv2d_backward": c_int,
+    "kcnn_conv2d_staging_floats": c_size_t,
+    "cudaF_conv2d_fprop_staged": c_int,
     "cudaF_affine_wgrad_sgd": c_int,
 }
 

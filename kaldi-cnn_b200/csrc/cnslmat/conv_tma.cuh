@@ -498,11 +498,13 @@ inline bool encode_act_map(CUtensorMap *map, const float *act, int N, int R, int
   return encode_map(map, act, 3, dims, str, box, mn_major);
 }
 
+// staging (optional): caller-owned [N*W*C] floats that receive the channels-last copy of `in`
+// and stay valid after the call, so the matching Backprop can skip its own pack of in_value.
 inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int ld_in, const float *kernel,
-                       int ld_k, const float *bias, float *out, int ldo) {
+                       int ld_k, const float *bias, float *out, int ldo, float *staging = nullptr) {
   if (!conv_tma_shape_ok(q)) return false;
-  float *xcl = scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
-  if (!xcl) return false;
+  float *xcl = staging ? staging : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
+  if (!xcl || !host_aligned16(xcl)) return false;
   const int nb = 128 / q.OW;
   CUtensorMap ma, mb;
   if (!encode_act_map(&ma, xcl, q.N, q.W, q.C, (unsigned)q.OW, (unsigned)nb, false)) return false;
@@ -533,8 +535,12 @@ struct ConvBackward {
   float *kernel_grad; int ld_kg;          // !sgd: receives dK;  nullptr: skip wgrad
   float *prev; int ld_p;                  // sgd: momentum state, same shape / pitch as kernel
   const SgdCoef *sgd;
+  const float *staged_x;                  // optional: channels-last copy of in_value left by conv_fprop
   bool want_bias;
-  float *bias_partial; int bias_rows;     // out
+  float *bias_dst;                        // optional: where the bias column sums go, so that the
+  float bias_alpha; int bias_accumulate;  //   split-K reduction launch can finish them too
+  float *bias_partial; int bias_rows;     // out: partial sums (bias_done == false: caller reduces)
+  bool bias_done;                         // out
 };
 
 inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) {
@@ -548,7 +554,10 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     if (b.sgd && (b.ld_p != b.ld_k || !host_aligned16(b.prev))) return false;
   }
   float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float));
-  float *xcl = do_wgrad ? scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float)) : nullptr;
+  const bool have_x = b.staged_x != nullptr && host_aligned16(b.staged_x);
+  float *xcl = !do_wgrad ? nullptr
+               : have_x ? const_cast<float *>(b.staged_x)
+                        : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
   const int prow = pack_partial_rows(q.N, q.OW);
   float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float)) : nullptr;
   if (!dycl || (do_wgrad && !xcl) || (b.want_bias && !bpart)) return false;
@@ -578,7 +587,7 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
   }
   // ---- nothing can fail past this point
   launch_pack(st, b.out_deriv, b.ld_od, q.N, q.G, q.OW, dycl, bpart);
-  b.bias_partial = bpart; b.bias_rows = prow;
+  b.bias_partial = bpart; b.bias_rows = prow; b.bias_done = false;
   if (do_dgrad) {
     ConvRowsProb<false> p;
     p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
@@ -587,7 +596,7 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     launch_conv_rows(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
   }
   if (!do_wgrad) return true;
-  launch_pack(st, b.in_value, b.ld_iv, q.N, q.C, q.W, xcl, nullptr);
+  if (!have_x) launch_pack(st, b.in_value, b.ld_iv, q.N, q.C, q.W, xcl, nullptr);
   dim3 grid(ceil_div_u(M, BM), ceil_div_u(q.G, BN), splits);
   SgdCoef none = {0.f, 0.f, 0.f};
   auto fill = [&](auto &p) {
@@ -602,12 +611,19 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     ConvWgradProb<EPI_PARTIAL> p; fill(p);
     launch_prob(st, wa, wb, p, grid, per);
     const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
+    ColSumTail tail = {nullptr, 0, 0, nullptr, 0.f, 0};
+    unsigned tail_blocks = 0;
+    if (b.want_bias && b.bias_dst) {
+      tail = ColSumTail{bpart, prow, q.G, b.bias_dst, b.bias_alpha, b.bias_accumulate};
+      tail_blocks = ceil_div_u(q.G, 256);
+      b.bias_done = true;
+    }
     if (b.sgd)
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, KernelRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout, ld_w,
-                  nullptr, b.prev, *b.sgd, rm);
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, KernelRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
+                  wout, ld_w, nullptr, b.prev, *b.sgd, rm, tail, blocks);
     else
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, KernelRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout, ld_w,
-                  nullptr, nullptr, none, rm);
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, KernelRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
+                  wout, ld_w, nullptr, nullptr, none, rm, tail, blocks);
   } else if (b.sgd) {
     ConvWgradProb<EPI_SGD> p; fill(p);
     launch_prob(st, wa, wb, p, grid, per);
@@ -702,7 +718,7 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
   }
   // ---- nothing can fail past this point
   launch_pack(st, b.out_deriv, b.ld_od, q.N, q.G, q.OW, dycl, bpart);
-  b.bias_partial = bpart; b.bias_rows = prow;
+  b.bias_partial = bpart; b.bias_rows = prow; b.bias_done = false;
   if (do_dgrad) {
     ConvFullDgradProb p;
     p.num_samples = q.N; p.W = q.W; p.H = q.H; p.C = q.C; p.nb = nb; p.nbc = nbc;
@@ -723,12 +739,19 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
     ConvWgradProb<EPI_PARTIAL, true> p; fill(p);
     launch_prob(st, wa, wb, p, grid, per);
     const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
+    ColSumTail tail = {nullptr, 0, 0, nullptr, 0.f, 0};
+    unsigned tail_blocks = 0;
+    if (b.want_bias && b.bias_dst) {
+      tail = ColSumTail{bpart, prow, q.G, b.bias_dst, b.bias_alpha, b.bias_accumulate};
+      tail_blocks = ceil_div_u(q.G, 256);
+      b.bias_done = true;
+    }
     if (b.sgd)
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout, ld_w,
-                  nullptr, b.prev, *b.sgd, IdentityRow());
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
+                  wout, ld_w, nullptr, b.prev, *b.sgd, IdentityRow(), tail, blocks);
     else
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks, 256, 0, st, ws, splits, M, q.G, wout,
-                  ld_w, nullptr, nullptr, none, IdentityRow());
+      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M,
+                  q.G, wout, ld_w, nullptr, nullptr, none, IdentityRow(), tail, blocks);
   } else if (b.sgd) {
     ConvWgradProb<EPI_SGD, true> p; fill(p);
     launch_prob(st, wa, wb, p, grid, per);

@@ -666,13 +666,33 @@ struct DenseProb {
   }
 };
 
+// Optional tail of the split-K reduction: the last stage of a per-column sum (the convolution's
+// bias gradient from the pack kernel's partial rows), run by extra blocks of the same launch:
+//   dst[c] = alpha * sum_r partial[r][c]  (+ dst[c] when accumulate)
+struct ColSumTail {
+  const float *partial;   // [rows][cols], nullptr = no tail
+  int rows, cols;
+  float *dst;
+  float alpha;
+  int accumulate;
+};
+
 // out[row_of(m)][n] = sum_z ws[z][m][n] (+ bias_n[n]), or the SGD update with that sum as the
 // gradient.  N % 4 == 0, 16-byte aligned rows (checked by the launchers).
 template <int kEpi, class RowMap>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, float *__restrict__ out, int ldo,
-                     const float *__restrict__ bias_n, float *__restrict__ aux, SgdCoef sgd, RowMap row_of) {
+                     const float *__restrict__ bias_n, float *__restrict__ aux, SgdCoef sgd, RowMap row_of,
+                     ColSumTail tail, unsigned main_blocks) {
   kcnn::pdl_prologue();
+  if (blockIdx.x >= main_blocks) {
+    const int c = (int)(blockIdx.x - main_blocks) * blockDim.x + threadIdx.x;
+    if (tail.partial == nullptr || c >= tail.cols) return;
+    float s = 0.0f;
+    for (int r = 0; r < tail.rows; r++) s += __ldg(tail.partial + (size_t)r * tail.cols + c);
+    tail.dst[c] = tail.accumulate ? fmaf(tail.alpha, s, tail.dst[c]) : tail.alpha * s;
+    return;
+  }
   const long long total4 = ((long long)M * N) >> 2;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
@@ -865,10 +885,10 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
     const unsigned blocks = ceil_div_u(((long long)M * N) >> 2, 256);
     if (epi.mode == EPI_SGD)
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
-                  nullptr, epi.aux, epi.sgd, IdentityRow());
+                  nullptr, epi.aux, epi.sgd, IdentityRow(), ColSumTail{nullptr, 0, 0, nullptr, 0.f, 0}, blocks);
     else
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
-                  epi.bias_n, nullptr, epi.sgd, IdentityRow());
+                  epi.bias_n, nullptr, epi.sgd, IdentityRow(), ColSumTail{nullptr, 0, 0, nullptr, 0.f, 0}, blocks);
   } else if (epi.mode == EPI_SGD) {
     DenseProb<kAMn, kBMn, EPI_SGD> p; fill(p);
     launch_prob(st, ma, mb, p, grid, per, pair);

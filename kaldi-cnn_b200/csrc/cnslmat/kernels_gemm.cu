@@ -250,21 +250,39 @@ using namespace kcnn;
 
 extern "C" {
 
+size_t kcnn_conv2d_staging_floats(int num_rows, int H, int W, int C, int ph, int pw, int KH, int KW, int G) {
+  ConvGeom q = conv_geom(num_rows, H, W, C, ph, pw, KH, KW, G);
+  if (!(H == 1 && KH == 1 && ph == 0) || q.P <= 0) return 0;
+  tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
+  return tma::conv_tma_shape_ok(cs) ? (size_t)q.N * W * C : 0;
+}
+
 void cudaF_conv2d_fprop(cudaStream_t st, int math, const float *in, MatrixDim id,
                         const float *kernel, MatrixDim kd, const float *bias, float *out,
                         MatrixDim od, int H, int W, int C, int ph, int pw, int KH, int KW, int G,
                         int concat) {
+  (void)cudaF_conv2d_fprop_staged(st, math, in, id, kernel, kd, bias, out, od, H, W, C, ph, pw, KH, KW, G,
+                                  concat, nullptr);
+}
+
+int cudaF_conv2d_fprop_staged(cudaStream_t st, int math, const float *in, MatrixDim id,
+                               const float *kernel, MatrixDim kd, const float *bias, float *out,
+                               MatrixDim od, int H, int W, int C, int ph, int pw, int KH, int KW, int G,
+                               int concat, float *staging) {
   ConvGeom q = conv_geom(id.rows, H, W, C, ph, pw, KH, KW, G);
-  if (q.N == 0 || q.P <= 0 || G == 0) return;
+  if (q.N == 0 || q.P <= 0 || G == 0) return 0;
   check_int32(id, "conv input"); check_int32(od, "conv output"); check_int32(kd, "conv kernel");
   const int M = q.N * q.P, K = q.ks * C;
   if (math == KCNN_MATH_TF32_TC && concat && H == 1 && KH == 1 && ph == 0) {
     tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
-    if (tma::conv_fprop(st, cs, in, id.stride, kernel, kd.stride, bias, out, od.stride)) return;
+    if (tma::conv_fprop(st, cs, in, id.stride, kernel, kd.stride, bias, out, od.stride, staging))
+      return staging != nullptr ? 1 : 0;
   }
+  // (any other path does not fill `staging`: the caller must only trust it when
+  //  kcnn_conv2d_staging_floats() was non-zero AND the math mode is the tensor-core one.)
   if (math == KCNN_MATH_TF32_TC && concat && KH == H && H > 1 && ph == 0 && pw == 0) {
     tma::ConvFullShape fs = {q.N, H, W, C, KW, G, q.OW};
-    if (tma::conv_full_fprop(st, fs, in, id.stride, kernel, kd.stride, bias, out, od.stride)) return;
+    if (tma::conv_full_fprop(st, fs, in, id.stride, kernel, kd.stride, bias, out, od.stride)) return 0;
   }
   // A(m = (n, ow, oh), k = (c, kw, kh)) = Xpad[n, c, ow + kw, oh + kh]
   Op33 a = make_op(in,
@@ -286,6 +304,7 @@ void cudaF_conv2d_fprop(cudaStream_t st, int math, const float *in, MatrixDim id
     if (a_fast_k) launch_gemm<true, false, true>(st, math, a, b, o, M, G, K, false, nullptr);
     else          launch_gemm<false, false, true>(st, math, a, b, o, M, G, K, false, nullptr);
   }
+  return 0;
 }
 
 void cudaF_conv2d_dgrad(cudaStream_t st, int math, const float *out_deriv, MatrixDim odd,
@@ -368,8 +387,9 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
     tma::ConvBackward b = {};
     b.in_value = in_value; b.ld_iv = ivd.stride; b.out_deriv = out_deriv; b.ld_od = odd.stride;
     b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride; b.want_bias = bias_grad != nullptr;
+    b.bias_dst = bias_grad; b.bias_alpha = 1.0f; b.bias_accumulate = 0;
     if (tma::conv_backward(st, cs, b)) {
-      if (bias_grad) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
+      if (bias_grad && !b.bias_done) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
       return;
     }
   }
@@ -378,8 +398,9 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
     tma::ConvBackward b = {};
     b.in_value = in_value; b.ld_iv = ivd.stride; b.out_deriv = out_deriv; b.ld_od = odd.stride;
     b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride; b.want_bias = bias_grad != nullptr;
+    b.bias_dst = bias_grad; b.bias_alpha = 1.0f; b.bias_accumulate = 0;
     if (tma::conv_full_backward(st, fs, b)) {
-      if (bias_grad) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
+      if (bias_grad && !b.bias_done) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
       return;
     }
   }
@@ -406,8 +427,8 @@ int cudaF_conv2d_backward(cudaStream_t st, int math, const float *in_value, Matr
                           const float *out_deriv, MatrixDim odd, float *kernel, MatrixDim kd,
                           float *in_deriv, MatrixDim idd, float *kernel_grad, MatrixDim kgd,
                           float *bias_grad, float *prev_grad, MatrixDim pd, float *bias, int apply,
-                          float momentum, float a_decay, float a_grad, int H, int W, int C, int ph,
-                          int pw, int KH, int KW, int G) {
+                          float momentum, float a_decay, float a_grad, const float *staged_input, int H,
+                          int W, int C, int ph, int pw, int KH, int KW, int G) {
   ConvGeom q = conv_geom(odd.rows, H, W, C, ph, pw, KH, KW, G);
   if (q.N == 0 || q.P <= 0 || G == 0 || C == 0) return 0;
   if (math != KCNN_MATH_TF32_TC) return 0;
@@ -421,14 +442,19 @@ int cudaF_conv2d_backward(cudaStream_t st, int math, const float *in_value, Matr
   b.in_value = in_value; b.ld_iv = ivd.stride; b.out_deriv = out_deriv; b.ld_od = odd.stride;
   b.kernel = kernel; b.ld_k = kd.stride; b.in_deriv = in_deriv; b.ld_id = idd.stride;
   b.want_bias = true;
+  b.staged_x = time_axis ? staged_input : nullptr;
   if (apply) {
     b.prev = prev_grad; b.ld_p = pd.stride; b.sgd = &coef;
+    b.bias_dst = bias; b.bias_alpha = a_grad; b.bias_accumulate = 1;        // bias += lr * db
   } else {
     b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride;
+    b.bias_dst = bias_grad; b.bias_alpha = 1.0f; b.bias_accumulate = 0;
   }
   if (!(time_axis ? tma::conv_backward(st, cs, b) : tma::conv_full_backward(st, fs, b))) return 0;
-  if (apply) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias, a_grad, 1);   // bias += lr * db
-  else       launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
+  if (!b.bias_done) {
+    if (apply) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias, a_grad, 1);
+    else       launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
+  }
   return 1;
 }
 

@@ -17,7 +17,7 @@ ConvolutionComponent::ConvolutionComponent()     // defaults of reference .h:27
     : is_gradient_(false), in_height_(0), in_width_(0), in_channel_(0), in_pad_height_(0),
       in_pad_width_(0), kernel_height_(0), kernel_width_(0), stride_(1), group_(0), out_height_(0),
       out_width_(0), weight_decay_(0.0002), momentum_(0.9), deferred_(false),
-      grad_external_(false), workspace_rows_(-1) {}
+      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0) {}
 
 // reference :178-195 (the copy constructor leaves prev_grad_ empty, App. C.3; here it
 // is sized and zeroed so that a copied component can be updated).
@@ -28,7 +28,7 @@ ConvolutionComponent::ConvolutionComponent(const ConvolutionComponent &c)
       kernel_height_(c.kernel_height_), kernel_width_(c.kernel_width_), stride_(c.stride_),
       group_(c.group_), out_height_(c.out_height_), out_width_(c.out_width_),
       weight_decay_(c.weight_decay_), momentum_(c.momentum_), deferred_(false),
-      grad_external_(false), workspace_rows_(-1) {
+      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0) {
   prev_grad_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kSetZero);
 }
 
@@ -46,7 +46,7 @@ ConvolutionComponent::ConvolutionComponent(const CuMatrix<BaseFloat> &linear_par
       in_pad_height_(in_pad_height), in_pad_width_(in_pad_width), kernel_height_(kernel_height),
       kernel_width_(kernel_width), stride_(stride), group_(group), out_height_(out_height),
       out_width_(out_width), weight_decay_(weight_decay), momentum_(momentum), deferred_(false),
-      grad_external_(false), workspace_rows_(-1) {
+      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0) {
   KALDI_ASSERT(linear_params.NumCols() == bias_params.Dim() && bias_params.Dim() != 0);
   prev_grad_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kSetZero);
 }
@@ -199,9 +199,27 @@ void ConvolutionComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &
   KALDI_ASSERT(out->NumRows() == in.NumRows() && out->NumCols() == OutputDim());
   CuDevice::Instantiate().RequireEnabled("ConvolutionComponent::Propagate");
   Timer tim;
-  cudaF_conv2d_fprop(Str(), Math(), in.Data(), in.Dim(), linear_params_.Data(), linear_params_.Dim(),
-                     bias_params_.Data(), out->Data(), out->Dim(), in_height_, in_width_, in_channel_,
-                     in_pad_height_, in_pad_width_, kernel_height_, kernel_width_, group_, 1);
+  // The channels-last staging copy of `in` that the TMA path makes anyway is kept in a
+  // per-component buffer: Backprop of the same in_value (the nnet2 contract: in_value IS the
+  // matrix that was propagated) then does not pack it a second time.
+  BaseFloat *staging = NULL;
+  staged_src_ = NULL;
+  if (Math() == KCNN_MATH_TF32_TC) {
+    size_t floats = kcnn_conv2d_staging_floats(in.NumRows(), in_height_, in_width_, in_channel_,
+                                               in_pad_height_, in_pad_width_, kernel_height_,
+                                               kernel_width_, group_);
+    if (floats > 0) {
+      if (static_cast<size_t>(staged_in_.Dim()) != floats) staged_in_.Resize(floats, kUndefined);
+      staging = staged_in_.Data();
+    }
+  }
+  int staged = cudaF_conv2d_fprop_staged(Str(), Math(), in.Data(), in.Dim(), linear_params_.Data(),
+                                         linear_params_.Dim(), bias_params_.Data(), out->Data(),
+                                         out->Dim(), in_height_, in_width_, in_channel_, in_pad_height_,
+                                         in_pad_width_, kernel_height_, kernel_width_, group_, 1, staging);
+  if (staged) {
+    staged_src_ = in.Data(); staged_rows_ = in.NumRows(); staged_stride_ = in.Stride();
+  }
   CU_SAFE_CALL(cudaGetLastError());
   CuDevice::Instantiate().AccuProfile(__func__, tim.Elapsed());
 }
@@ -245,14 +263,18 @@ void ConvolutionComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
     ::MatrixDim gd = {self->w_grad_.rows, self->w_grad_.cols, self->w_grad_.stride};
     ::MatrixDim idd = {0, 0, 0};
     if (in_deriv != NULL) idd = in_deriv->Dim();
+    const BaseFloat *staged = NULL;
+    if (staged_src_ != NULL && staged_src_ == in_value.Data() && staged_rows_ == in_value.NumRows() &&
+        staged_stride_ == in_value.Stride() && Math() == KCNN_MATH_TF32_TC)
+      staged = staged_in_.Data();
     Timer tim;
     int done = cudaF_conv2d_backward(
         Str(), Math(), in_value.Data(), in_value.Dim(), out_deriv.Data(), out_deriv.Dim(),
         self->linear_params_.Data(), self->linear_params_.Dim(),
         in_deriv != NULL ? in_deriv->Data() : NULL, idd, self->w_grad_.data, gd, self->b_grad_.data,
         self->prev_grad_.Data(), self->prev_grad_.Dim(), self->bias_params_.Data(), apply ? 1 : 0,
-        momentum_, a_decay, a_grad, in_height_, in_width_, in_channel_, in_pad_height_, in_pad_width_,
-        kernel_height_, kernel_width_, group_);
+        momentum_, a_decay, a_grad, staged, in_height_, in_width_, in_channel_, in_pad_height_,
+        in_pad_width_, kernel_height_, kernel_width_, group_);
     if (done) {
       CU_SAFE_CALL(cudaGetLastError());
       CuDevice::Instantiate().AccuProfile(__func__, tim.Elapsed());

@@ -141,6 +141,10 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   CuMatrix<BaseFloat> w_grad_store_;
   CuVector<BaseFloat> b_grad_store_;
   GradBuffer w_grad_, b_grad_;
+  // channels-last staging copy of the last propagated input (see Propagate)
+  mutable CuVector<BaseFloat> staged_in_;
+  mutable const BaseFloat *staged_src_;
+  mutable int32 staged_rows_, staged_stride_;
   CuVector<BaseFloat> workspace_;     // split-K partials of the weight-gradient GEMM
   int32 workspace_rows_;
 };
