@@ -17,7 +17,8 @@ ConvolutionComponent::ConvolutionComponent()     // defaults of reference .h:27
     : is_gradient_(false), in_height_(0), in_width_(0), in_channel_(0), in_pad_height_(0),
       in_pad_width_(0), kernel_height_(0), kernel_width_(0), stride_(1), group_(0), out_height_(0),
       out_width_(0), weight_decay_(0.0002), momentum_(0.9), deferred_(false),
-      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0) {}
+      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0),
+      input_persists_(false) {}
 
 // reference :178-195 (the copy constructor leaves prev_grad_ empty, App. C.3; here it
 // is sized and zeroed so that a copied component can be updated).
@@ -28,7 +29,8 @@ ConvolutionComponent::ConvolutionComponent(const ConvolutionComponent &c)
       kernel_height_(c.kernel_height_), kernel_width_(c.kernel_width_), stride_(c.stride_),
       group_(c.group_), out_height_(c.out_height_), out_width_(c.out_width_),
       weight_decay_(c.weight_decay_), momentum_(c.momentum_), deferred_(false),
-      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0) {
+      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0),
+      input_persists_(false) {
   prev_grad_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kSetZero);
 }
 
@@ -46,7 +48,8 @@ ConvolutionComponent::ConvolutionComponent(const CuMatrix<BaseFloat> &linear_par
       in_pad_height_(in_pad_height), in_pad_width_(in_pad_width), kernel_height_(kernel_height),
       kernel_width_(kernel_width), stride_(stride), group_(group), out_height_(out_height),
       out_width_(out_width), weight_decay_(weight_decay), momentum_(momentum), deferred_(false),
-      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0) {
+      grad_external_(false), workspace_rows_(-1), staged_src_(NULL), staged_rows_(0), staged_stride_(0),
+      input_persists_(false) {
   KALDI_ASSERT(linear_params.NumCols() == bias_params.Dim() && bias_params.Dim() != 0);
   prev_grad_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kSetZero);
 }
@@ -199,12 +202,12 @@ void ConvolutionComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &
   KALDI_ASSERT(out->NumRows() == in.NumRows() && out->NumCols() == OutputDim());
   CuDevice::Instantiate().RequireEnabled("ConvolutionComponent::Propagate");
   Timer tim;
-  // The channels-last staging copy of `in` that the TMA path makes anyway is kept in a
-  // per-component buffer: Backprop of the same in_value (the nnet2 contract: in_value IS the
-  // matrix that was propagated) then does not pack it a second time.
+  // When the caller has promised that in_value persists until Backprop (SetInputPersists), the
+  // channels-last staging copy of `in` that the TMA path makes anyway is kept in a
+  // per-component buffer, and Backprop does not pack in_value a second time.
   BaseFloat *staging = NULL;
   staged_src_ = NULL;
-  if (Math() == KCNN_MATH_TF32_TC) {
+  if (input_persists_ && Math() == KCNN_MATH_TF32_TC) {
     size_t floats = kcnn_conv2d_staging_floats(in.NumRows(), in_height_, in_width_, in_channel_,
                                                in_pad_height_, in_pad_width_, kernel_height_,
                                                kernel_width_, group_);
@@ -264,7 +267,7 @@ void ConvolutionComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
     ::MatrixDim idd = {0, 0, 0};
     if (in_deriv != NULL) idd = in_deriv->Dim();
     const BaseFloat *staged = NULL;
-    if (staged_src_ != NULL && staged_src_ == in_value.Data() && staged_rows_ == in_value.NumRows() &&
+    if (input_persists_ && staged_src_ != NULL && staged_src_ == in_value.Data() && staged_rows_ == in_value.NumRows() &&
         staged_stride_ == in_value.Stride() && Math() == KCNN_MATH_TF32_TC)
       staged = staged_in_.Data();
     Timer tim;

@@ -111,6 +111,11 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   virtual void ApplyGradient(int32 total_num_samples);
   virtual size_t GradientFloats() const;
   virtual void SetGradientStorage(float *base);
+  /// Opt-in for a caller that OWNS the activation buffers (NnetMinibatchUpdater) and so can
+  /// promise that the matrix given to Backprop as in_value is, unmodified, the one last
+  /// propagated: Backprop then reuses Propagate's channels-last staging copy instead of
+  /// packing in_value again.  Off by default: a bare Component makes no such assumption.
+  virtual void SetInputPersists(bool on) { input_persists_ = on; staged_src_ = NULL; }
 
  protected:
   virtual void Update(const CuMatrixBase<BaseFloat> &in_value,
@@ -145,6 +150,7 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   mutable CuVector<BaseFloat> staged_in_;
   mutable const BaseFloat *staged_src_;
   mutable int32 staged_rows_, staged_stride_;
+  bool input_persists_;
   CuVector<BaseFloat> workspace_;     // split-K partials of the weight-gradient GEMM
   int32 workspace_rows_;
 };

@@ -144,6 +144,9 @@ class UpdatableComponent : public Component {
   /// Place the gradient buffers in caller-provided storage (one flat all-reduce bucket).
   virtual size_t GradientFloats() const { return 0; }
   virtual void SetGradientStorage(float * /*base*/) {}
+  /// The caller owns the activation buffers and promises that Backprop's in_value is the
+  /// unmodified matrix last given to Propagate (lets a component keep per-input scratch).
+  virtual void SetInputPersists(bool) {}
 
  protected:
   BaseFloat learning_rate_;

@@ -95,9 +95,20 @@ NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
     : nnet_(nnet), num_rows_(0), labels_(NULL), objf_dev_(NULL) {
   objf_dev_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double)));
   CU_SAFE_CALL(cudaMemsetAsync(objf_dev_, 0, sizeof(double), Str()));
+  SetInputPersists(true);    // forward_[c] is ours and untouched between Forward and Backward
 }
 
-NnetMinibatchUpdater::~NnetMinibatchUpdater() { CuDevice::Instantiate().Free(objf_dev_); }
+NnetMinibatchUpdater::~NnetMinibatchUpdater() {
+  SetInputPersists(false);
+  CuDevice::Instantiate().Free(objf_dev_);
+}
+
+void NnetMinibatchUpdater::SetInputPersists(bool on) {
+  for (int32 c = 0; c < nnet_->NumComponents(); c++) {
+    UpdatableComponent *u = dynamic_cast<UpdatableComponent *>(&nnet_->GetComponent(c));
+    if (u) u->SetInputPersists(on);
+  }
+}
 
 void NnetMinibatchUpdater::Forward(const CuMatrixBase<BaseFloat> &feats) {
   ForwardRange(feats, 0, nnet_->NumComponents() - 1);

@@ -76,6 +76,7 @@ class NnetMinibatchUpdater {
   double GetObjfAndReset();      // synchronises
   int32 NumRows() const { return num_rows_; }
  private:
+  void SetInputPersists(bool on);
   Nnet *nnet_;
   int32 num_rows_;
   std::vector<CuMatrix<BaseFloat> > forward_;   // [0] = copy-free view of the input

@@ -26,8 +26,11 @@ C1B = ("ConvolutionComponent in-height=40 in-width=11 in-channel=3 kernel-height
        "group=64 out-height=33 out-width=9 learning-rate=0.02 param-stddev=0.01 bias-stddev=0.5")
 CPAD = ("ConvolutionComponent in-height=6 in-width=7 in-channel=5 in-pad-height=1 in-pad-width=2 kernel-height=3 "
         "kernel-width=4 stride=1 group=10 out-height=6 out-width=8 learning-rate=0.05 param-stddev=0.1 bias-stddev=0.5")
+CTIME = ("ConvolutionComponent in-height=1 in-width=14 in-channel=64 kernel-height=1 kernel-width=3 stride=1 "
+         "group=128 out-height=1 out-width=12 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5")
 CONV_LINES = {"C1a": (C1A, (40, 11, 3, 0, 0, 40, 4, 128), 256), "C1b": (C1B, (40, 11, 3, 0, 0, 8, 3, 64), 32),
-              "pad": (CPAD, (6, 7, 5, 1, 2, 3, 4, 10), 9)}
+              "pad": (CPAD, (6, 7, 5, 1, 2, 3, 4, 10), 9),
+              "time": (CTIME, (1, 14, 64, 0, 0, 1, 3, 128), 70)}     # nnet.config-style layer: TMA path + staging
 
 
 def _get(t):
@@ -70,6 +73,37 @@ def test_convolution_component_two_training_steps(ora, name, math):
         assert rel_err(_get(comp.params(2)), prev_r) <= TOL[math] * 4
         assert np.abs(_get(comp.params(1))[0] - bias_r).max() <= 1e-5 * max(np.abs(bias_r - bias).max(), 1e-30) * 4
         lin, bias, prev = _get(comp.params(0)), _get(comp.params(1))[0], _get(comp.params(2))
+    kc.set_math_mode(0)
+
+
+def test_backprop_with_another_in_value_does_not_reuse_the_staging_copy(ora):
+    """A bare Component must not assume Backprop's in_value is what was last propagated (the two
+    device buffers here may even share an address through the caching allocator): the
+    channels-last staging copy is reused only under NnetMinibatchUpdater (SetInputPersists)."""
+    kc.set_math_mode(1)
+    kc.set_rand_seed(7)
+    comp = kc.Component.from_string(CTIME)
+    H, W, C, ph, pw, KH, KW, G = CONV_LINES["time"][1]
+    N = 40
+    rng = np.random.default_rng(9)
+    x1 = rng.standard_normal((N, W * C)).astype(np.float32)
+    x2 = rng.standard_normal((N, W * C)).astype(np.float32)
+    dy = rng.standard_normal((N, 12 * G)).astype(np.float32)
+    lin, bias, prev = _get(comp.params(0)), _get(comp.params(1))[0], _get(comp.params(2))
+    wd, mom = comp.weight_decay_momentum()
+    comp.propagate(dev(x1))
+    comp.backprop(dev(x2), None, dev(dy), update=True)
+    lin_r = ora.conv_update(x2, dy, lin, bias, prev, H, W, C, ph, pw, KH, KW, G, 0.02, wd, mom, dtype=np.float64)[0]
+    scale = max(np.abs(lin_r - lin).max(), 1e-30)
+    assert np.abs(_get(comp.params(0)) - lin_r).max() <= 1e-3 * scale * 4
+    # same tensor propagated and back-propagated:
+    xd = dev(x1)
+    comp.propagate(xd)
+    lin = _get(comp.params(0)); prev = _get(comp.params(2)); bias = _get(comp.params(1))[0]
+    comp.backprop(xd, None, dev(dy), update=True)
+    lin_r = ora.conv_update(x1, dy, lin, bias, prev, H, W, C, ph, pw, KH, KW, G, 0.02, wd, mom, dtype=np.float64)[0]
+    scale = max(np.abs(lin_r - lin).max(), 1e-30)
+    assert np.abs(_get(comp.params(0)) - lin_r).max() <= 1e-3 * scale * 4
     kc.set_math_mode(0)
 
 
