@@ -184,6 +184,14 @@ int kcnn_nnet_apply_gradients(kcnn_nnet *n, int total_rows);
  * backward + update, and returns the minibatch objective in *objf (synchronous). */
 int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const int *labels_host,
                                    int rows, double *objf);
+/* The same step on DEVICE buffers, asynchronous on the compute stream (read the objective
+ * with kcnn_nnet_objf_and_reset).  Both calls go through NnetMinibatchUpdater::TrainStep: on a
+ * non-default compute stream the ~85 launches of a step are recorded into a CUDA graph on the
+ * second call with the same buffers / configuration and replayed from then on
+ * (KCNN_NNET_GRAPH=0 keeps every step eager). */
+int kcnn_nnet_train_step(kcnn_nnet *n, const float *feats, int rows, int stride, const int *labels);
+/* 1 when the most recent train step of this network was a graph replay, else 0. */
+int kcnn_nnet_last_step_replayed(const kcnn_nnet *n);
 
 #ifdef __cplusplus
 }

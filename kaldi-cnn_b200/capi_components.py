@@ -74,6 +74,8 @@ PROTOS = {
     "kcnn_nnet_gradient_bucket": ([H, I, PS, PS], c_int),
     "kcnn_nnet_apply_gradients": ([H, I], c_int),
     "kcnn_nnet_train_minibatch_host": ([H, P, P, I, ctypes.POINTER(ctypes.c_double)], c_int),
+    "kcnn_nnet_train_step": ([H, P, I, I, P], c_int),
+    "kcnn_nnet_last_step_replayed": ([H], c_int),
 }
 
 

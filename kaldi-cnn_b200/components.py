@@ -279,6 +279,18 @@ class Nnet:
             feats_np.shape[0], ctypes.byref(objf)))
         return objf.value
 
+    def train_step_graph(self, feats, labels):
+        """The same step through NnetMinibatchUpdater::TrainStep: recorded into a CUDA graph by the
+        library on the second call with the same buffers, replayed afterwards."""
+        use_current_stream()
+        d = capi.mdim(feats)
+        _check(_lib().kcnn_nnet_train_step(self.h, ctypes.c_void_p(feats.data_ptr()), d.rows, d.stride,
+                                           ctypes.c_void_p(labels.data_ptr())))
+
+    @property
+    def last_step_replayed(self):
+        return bool(_lib().kcnn_nnet_last_step_replayed(self.h))
+
     # ---- data parallel -----------------------------------------------------------
     def enable_data_parallel(self):
         """Deferred updates + one flat gradient arena (a torch tensor, so torch.distributed

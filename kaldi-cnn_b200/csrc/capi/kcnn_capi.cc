@@ -528,13 +528,25 @@ int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const 
                                  sizeof(float) * dim, sizeof(float) * dim, rows, cudaMemcpyHostToDevice, st));
   CU_SAFE_CALL(cudaMemcpyAsync(h->host_labels_dev, labels_host, sizeof(int32) * rows,
                                cudaMemcpyHostToDevice, st));
-  h->U().Forward(h->host_feats);
-  h->U().ComputeObjfAndDeriv(h->host_labels_dev);
-  h->U().Backward();
+  h->U().TrainStep(h->host_feats, h->host_labels_dev);
   double v = h->U().GetObjfAndReset();
   if (objf) *objf = v;
   return 0;
   KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_train_step(kcnn_nnet *n, const float *feats, int rows, int stride, const int *labels) {
+  KCNN_TRY
+  NnetHandle *h = N(n);
+  View F(feats, rows, h->nnet.InputDim(), stride);
+  h->U().TrainStep(F, labels);
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_last_step_replayed(const kcnn_nnet *n) {
+  const NnetHandle *h = N(n);
+  return (h->updater != NULL && h->updater->LastStepReplayed()) ? 1 : 0;
 }
 
 }  // extern "C"

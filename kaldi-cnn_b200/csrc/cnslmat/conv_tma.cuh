@@ -588,6 +588,12 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
   // ---- nothing can fail past this point
   launch_pack(st, b.out_deriv, b.ld_od, q.N, q.G, q.OW, dycl, bpart);
   b.bias_partial = bpart; b.bias_rows = prow; b.bias_done = false;
+  // The input-gradient GEMM and the weight-gradient GEMM both read the staging copy just made
+  // and each fills well under half of the SMs: they run as two branches.  The kernel matrix is
+  // WRITTEN by the momentum step (the split-K reduction, or the EPI_SGD epilogue when there is
+  // no split), which therefore stays behind the join: dgrad must see the old weights.
+  ForkJoin fj(st, do_dgrad && do_wgrad && (splits > 1 || !b.sgd));
+  cudaStream_t wst = fj.active() ? fj.side() : st;
   if (do_dgrad) {
     ConvRowsProb<false> p;
     p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
@@ -596,7 +602,7 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     launch_conv_rows(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
   }
   if (!do_wgrad) return true;
-  if (!have_x) launch_pack(st, b.in_value, b.ld_iv, q.N, q.C, q.W, xcl, nullptr);
+  if (!have_x) launch_pack(wst, b.in_value, b.ld_iv, q.N, q.C, q.W, xcl, nullptr);
   dim3 grid(ceil_div_u(M, BM), ceil_div_u(q.G, BN), splits);
   SgdCoef none = {0.f, 0.f, 0.f};
   auto fill = [&](auto &p) {
@@ -609,7 +615,8 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
   rm.div_c = FastDiv((uint32_t)Cp); rm.KW = q.KW; rm.C = q.C;
   if (splits > 1) {
     ConvWgradProb<EPI_PARTIAL> p; fill(p);
-    launch_prob(st, wa, wb, p, grid, per);
+    launch_prob(wst, wa, wb, p, grid, per);
+    fj.join();
     const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
     ColSumTail tail = {nullptr, 0, 0, nullptr, 0.f, 0};
     unsigned tail_blocks = 0;
@@ -629,7 +636,7 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     launch_prob(st, wa, wb, p, grid, per);
   } else {
     ConvWgradProb<EPI_STORE> p; fill(p);
-    launch_prob(st, wa, wb, p, grid, per);
+    launch_prob(wst, wa, wb, p, grid, per);
   }
   return true;
 }
@@ -719,6 +726,8 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
   // ---- nothing can fail past this point
   launch_pack(st, b.out_deriv, b.ld_od, q.N, q.G, q.OW, dycl, bpart);
   b.bias_partial = bpart; b.bias_rows = prow; b.bias_done = false;
+  ForkJoin fj(st, do_dgrad && do_wgrad && (splits > 1 || !b.sgd));      // see conv_backward()
+  cudaStream_t wst = fj.active() ? fj.side() : st;
   if (do_dgrad) {
     ConvFullDgradProb p;
     p.num_samples = q.N; p.W = q.W; p.H = q.H; p.C = q.C; p.nb = nb; p.nbc = nbc;
@@ -737,7 +746,8 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
   };
   if (splits > 1) {
     ConvWgradProb<EPI_PARTIAL, true> p; fill(p);
-    launch_prob(st, wa, wb, p, grid, per);
+    launch_prob(wst, wa, wb, p, grid, per);
+    fj.join();
     const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
     ColSumTail tail = {nullptr, 0, 0, nullptr, 0.f, 0};
     unsigned tail_blocks = 0;
@@ -757,7 +767,7 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
     launch_prob(st, wa, wb, p, grid, per);
   } else {
     ConvWgradProb<EPI_STORE, true> p; fill(p);
-    launch_prob(st, wa, wb, p, grid, per);
+    launch_prob(wst, wa, wb, p, grid, per);
   }
   return true;
 }

@@ -51,6 +51,24 @@ __device__ __forceinline__ void pdl_wait() {
 
 bool pdl_enabled();      // kcnn_lib.cu: KCNN_PDL=1 turns the launch attribute on
 
+// Fork / join of independent launches inside one library call (e.g. the input-gradient and
+// the weight-gradient GEMM of a convolution: small grids that leave most SMs idle when run
+// back to back).  The work between fork() and join() on side() runs concurrently with the
+// caller's stream and is ordered before everything the caller enqueues after join(); both
+// are event waits, so the pair is captured into CUDA graphs as two parallel branches.
+// KCNN_SIDE_STREAM=0 disables it (active() is then false and callers stay on one stream).
+class ForkJoin {
+ public:
+  explicit ForkJoin(cudaStream_t main, bool want);
+  bool active() const { return side_ != nullptr; }
+  cudaStream_t side() const { return side_; }
+  void join();                       // idempotent
+  ~ForkJoin() { join(); }
+ private:
+  cudaStream_t main_, side_;
+  cudaEvent_t join_ev_;
+};
+
 template <class... KArgs, class... Args>
 inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                           unsigned cluster_x, Args &&...args) {

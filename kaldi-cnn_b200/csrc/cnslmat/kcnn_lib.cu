@@ -19,6 +19,56 @@ bool pdl_enabled() {
   }
   return v == 1;
 }
+
+namespace {
+struct SideState { cudaStream_t stream; cudaEvent_t fork, join; bool tried; };
+SideState g_side = {nullptr, nullptr, nullptr, false};
+
+SideState *side_state(cudaStream_t main) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char *e = getenv("KCNN_SIDE_STREAM");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  if (!g_side.tried) {
+    // created on first use, never while the caller's stream is being captured (the warm-up
+    // steps that precede any capture get here first)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    g_side.tried = true;
+    if (cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      g_side.stream = nullptr;
+    }
+  }
+  return g_side.stream ? &g_side : nullptr;
+}
+}  // namespace
+
+ForkJoin::ForkJoin(cudaStream_t main, bool want) : main_(main), side_(nullptr), join_ev_(nullptr) {
+  if (!want) return;
+  SideState *s = side_state(main);
+  if (!s) return;
+  if (cudaEventRecord(s->fork, main) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  side_ = s->stream;
+  join_ev_ = s->join;
+}
+
+void ForkJoin::join() {
+  if (!side_) return;
+  cudaEventRecord(join_ev_, side_);
+  cudaStreamWaitEvent(main_, join_ev_, 0);
+  side_ = nullptr;
+}
 }  // namespace kcnn
 
 extern "C" {

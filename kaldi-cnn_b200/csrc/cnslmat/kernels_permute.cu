@@ -24,48 +24,120 @@
 
 #include "kcnn_common.cuh"
 
+#include <type_traits>
+
 namespace kcnn {
 
 // ---------------------------------------------------------------- swap_outer --
 // in  address: a*sa_in  + b*sb_in  + x
 // out address: b*sb_out + a*sa_out + x          x in [0, L)
+// One thread moves kIlp units (float or float4) that are a whole grid apart: the loads are all
+// issued before the first store, so a thread keeps kIlp requests in flight (one 4-byte load per
+// thread caps a 2048-thread SM at ~8 KB in flight, i.e. ~1.5 TB/s by Little's law).
+constexpr int kIlp = 4;
+template <int VEC>
 __global__ void __launch_bounds__(256)
-swap_outer_direct(const float *__restrict__ in, float *__restrict__ out, int A, int B, int L,
+swap_outer_direct(const float *__restrict__ in, float *__restrict__ out, int A, int B, int units,
                   long long sa_in, long long sb_in, long long sb_out, long long sa_out,
-                  FastDiv div_L, FastDiv div_A, int ab_limit) {
+                  FastDiv div_units, FastDiv div_A, int ab_limit, long long total) {
   kcnn::pdl_prologue();
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)A * B * L) return;
-  // order threads by OUTPUT address: (b, a, x)
-  uint32_t ba, x, b, a;
-  div_L.divmod((uint32_t)t, ba, x);
-  div_A.divmod(ba, b, a);
-  if ((long long)a * B + b >= ab_limit) return;      // ragged last block of rows
-  out[b * sb_out + a * sa_out + x] = __ldg(in + a * sa_in + b * sb_in + x);
+  typedef typename std::conditional<VEC == 4, float4, float>::type T;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  T v[kIlp];
+  long long dst[kIlp];
+#pragma unroll
+  for (int k = 0; k < kIlp; k++) {
+    const long long t = t0 + k * step;
+    dst[k] = -1;
+    if (t >= total) continue;
+    // order threads by OUTPUT address: (b, a, x)
+    uint32_t ba, x, b, a;
+    div_units.divmod((uint32_t)t, ba, x);
+    div_A.divmod(ba, b, a);
+    if ((long long)a * B + b >= ab_limit) continue;    // ragged last block of rows
+    dst[k] = b * sb_out + a * sa_out + (long long)x * VEC;
+    v[k] = __ldg(reinterpret_cast<const T *>(in + a * sa_in + b * sb_in + (long long)x * VEC));
+  }
+#pragma unroll
+  for (int k = 0; k < kIlp; k++)
+    if (dst[k] >= 0) *reinterpret_cast<T *>(out + dst[k]) = v[k];
 }
 
-// Short runs (L < 32) with sb_in == L and sa_out == L (TpBlock): a block takes 32
-// values of a and KB whole values of b, so it reads 32 spans of KB*L contiguous
-// floats and writes KB spans of 32*L contiguous floats.
+static void launch_swap_outer_direct(cudaStream_t st, const float *in, float *out, int A, int B, int L,
+                                     long long sa_in, long long sb_in, long long sb_out, long long sa_out,
+                                     int ab_limit) {
+  const bool v4 = (L % 4 == 0) && (sa_in % 4 == 0) && (sb_in % 4 == 0) && (sb_out % 4 == 0) && (sa_out % 4 == 0) &&
+                  host_aligned16(in) && host_aligned16(out);
+  const int units = v4 ? L / 4 : L;
+  const long long total = (long long)A * B * units;
+  if (total == 0) return;
+  const unsigned grid = ceil_div_u(total, 256 * kIlp);
+  if (v4)
+    KCNN_LAUNCH(swap_outer_direct<4>, grid, 256, 0, st, in, out, A, B, units, sa_in, sb_in, sb_out, sa_out,
+                FastDiv((uint32_t)units), FastDiv((uint32_t)A), ab_limit, total);
+  else
+    KCNN_LAUNCH(swap_outer_direct<1>, grid, 256, 0, st, in, out, A, B, units, sa_in, sb_in, sb_out, sa_out,
+                FastDiv((uint32_t)units), FastDiv((uint32_t)A), ab_limit, total);
+}
+
+// Short runs (L < 32) with sb_in == L and sa_out == L (TpBlock): a block takes 32 values of a
+// and KB whole values of b (KB*L ~ 128 floats), so it reads 32 spans of KB*L contiguous floats
+// and writes KB spans of 32*L contiguous floats.
 __global__ void __launch_bounds__(256)
 swap_outer_tiled(const float *__restrict__ in, float *__restrict__ out, int A, int B, int L,
-                 int KB, long long sa_in, long long sb_out) {
+                 int KB, long long sa_in, long long sb_out, FastDiv div_span, FastDiv div_run, FastDiv div_L) {
   kcnn::pdl_prologue();
   extern __shared__ float tile[];
   const int a0 = blockIdx.x * 32, b0 = blockIdx.y * KB;
   const int na = min(32, A - a0), nb = min(KB, B - b0);
-  const int span = nb * L;                 // contiguous input floats per a
-  const int pitch = (KB * L) | 1;          // odd pitch: conflict-free column reads
-  for (int e = threadIdx.x; e < na * span; e += blockDim.x) {
-    int al = e / span, k = e - al * span;
-    tile[al * pitch + k] = __ldg(in + (long long)(a0 + al) * sa_in + (long long)b0 * L + k);
+  const int span = KB * L;                 // contiguous input floats per a (nb*L of them valid)
+  const int pitch = span | 1;              // odd pitch: conflict-free column reads
+  const float *src = in + (long long)a0 * sa_in + (long long)b0 * L;
+#pragma unroll 4
+  for (int e = threadIdx.x; e < 32 * span; e += 256) {
+    uint32_t al, k;
+    div_span.divmod((uint32_t)e, al, k);
+    if ((int)al < na && (int)k < nb * L) tile[al * pitch + k] = __ldg(src + (long long)al * sa_in + k);
   }
   __syncthreads();
-  const int run = na * L;                  // contiguous output floats per b
-  for (int e = threadIdx.x; e < nb * run; e += blockDim.x) {
-    int bl = e / run, r = e - bl * run;
-    int al = r / L, x = r - al * L;
-    out[(long long)(b0 + bl) * sb_out + (long long)a0 * L + r] = tile[al * pitch + bl * L + x];
+  const int run = 32 * L;                  // contiguous output floats per b (na*L of them valid)
+  float *dst = out + (long long)b0 * sb_out + (long long)a0 * L;
+#pragma unroll 4
+  for (int e = threadIdx.x; e < KB * run; e += 256) {
+    uint32_t bl, r, al, x;
+    div_run.divmod((uint32_t)e, bl, r);
+    div_L.divmod(r, al, x);
+    if ((int)bl < nb && (int)al < na) dst[(long long)bl * sb_out + r] = tile[al * pitch + bl * L + x];
+  }
+}
+
+// Small-Q transpose (TpInsideBlock with a short block: Q = block_size): one CTA moves the whole
+// [R][Q] block of one batch entry through shared memory -- the read is one contiguous run when
+// sr_in == Q, the write Q runs of R floats.  The 32 x 32 tiles below would use Q / 32 of each
+// warp on the read side.
+__global__ void __launch_bounds__(256)
+swap_inner_smallq(const float *__restrict__ in, float *__restrict__ out, int R, int Q, long long base_in,
+                  long long sz_in, long long sr_in, long long sz_out, long long sq_out, FastDiv div_Q,
+                  FastDiv div_R) {
+  kcnn::pdl_prologue();
+  extern __shared__ float tile[];
+  const int pitch = Q | 1;
+  const float *src = in + base_in + (long long)blockIdx.x * sz_in;
+  float *dst = out + (long long)blockIdx.x * sz_out;
+  const int total = R * Q;
+#pragma unroll 4
+  for (int e = threadIdx.x; e < total; e += 256) {
+    uint32_t r, q;
+    div_Q.divmod((uint32_t)e, r, q);
+    tile[r * pitch + q] = __ldg(src + (long long)r * sr_in + q);
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int e = threadIdx.x; e < total; e += 256) {
+    uint32_t q, r;
+    div_R.divmod((uint32_t)e, q, r);
+    dst[(long long)q * sq_out + r] = tile[r * pitch + q];
   }
 }
 
@@ -100,6 +172,11 @@ static void launch_swap_inner(cudaStream_t st, const float *in, float *out, int 
                               long long base_in, long long sz_in, long long sr_in,
                               long long sz_out, long long sq_out) {
   if (Z == 0 || R == 0 || Q == 0) return;
+  if (Q < 32 && (long long)R * (Q | 1) <= 12288) {
+    KCNN_LAUNCH(swap_inner_smallq, (unsigned)Z, 256, (size_t)R * (Q | 1) * sizeof(float), st, in, out, R, Q, base_in,
+                sz_in, sr_in, sz_out, sq_out, FastDiv((uint32_t)Q), FastDiv((uint32_t)R));
+    return;
+  }
   // gridDim.z is limited to 65535: walk the batch in slabs.
   for (int z0 = 0; z0 < Z; z0 += 65535) {
     int nz = Z - z0 < 65535 ? Z - z0 : 65535;
@@ -116,17 +193,29 @@ pad_zero_kernel(const float *__restrict__ orig, int orig_stride, float *__restri
                 int pad_stride, int rows, int pad_cols, int H, int W, int KH, int KW, int PH,
                 FastDiv div_cols, FastDiv div_ps, FastDiv div_ph) {
   kcnn::pdl_prologue();
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)rows * pad_cols) return;
-  uint32_t i, j, c, p, J, I;
-  div_cols.divmod((uint32_t)t, i, j);
-  div_ps.divmod(j, c, p);
-  div_ph.divmod(p, J, I);
-  int m = (int)I - (KH - 1), n = (int)J - (KW - 1);
-  float v = 0.0f;
-  if (m >= 0 && m < H && n >= 0 && n < W)
-    v = __ldg(orig + (size_t)i * orig_stride + (size_t)c * (H * W) + n * H + m);
-  pad[(size_t)i * pad_stride + j] = v;
+  const long long total = (long long)rows * pad_cols;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  float v[kIlp];
+  long long dst[kIlp];
+#pragma unroll
+  for (int k = 0; k < kIlp; k++) {                   // kIlp independent loads in flight per thread
+    const long long t = t0 + k * step;
+    dst[k] = -1;
+    v[k] = 0.0f;
+    if (t >= total) continue;
+    uint32_t i, j, c, p, J, I;
+    div_cols.divmod((uint32_t)t, i, j);
+    div_ps.divmod(j, c, p);
+    div_ph.divmod(p, J, I);
+    int m = (int)I - (KH - 1), n = (int)J - (KW - 1);
+    if (m >= 0 && m < H && n >= 0 && n < W)
+      v[k] = __ldg(orig + (size_t)i * orig_stride + (size_t)c * (H * W) + n * H + m);
+    dst[k] = (long long)i * pad_stride + j;
+  }
+#pragma unroll
+  for (int k = 0; k < kIlp; k++)
+    if (dst[k] >= 0) pad[dst[k]] = v[k];
 }
 
 template <bool kVec4>
@@ -219,7 +308,7 @@ void cudaF_pad_zero_s(cudaStream_t st, const float *orig, MatrixDim od, int H, i
                       int KW, float *pad, MatrixDim pd) {
   if (pd.rows == 0 || pd.cols == 0) return;
   int PH = H + 2 * (KH - 1), PW = W + 2 * (KW - 1);
-  unsigned int grid = ceil_div_u((long long)pd.rows * pd.cols, 256);
+  unsigned int grid = ceil_div_u((long long)pd.rows * pd.cols, 256 * kIlp);
   KCNN_LAUNCH(pad_zero_kernel, grid, 256, 0, st, orig, od.stride, pad, pd.stride, pd.rows,
               pd.cols, H, W, KH, KW, PH, FastDiv((uint32_t)pd.cols), FastDiv((uint32_t)(PH * PW)),
               FastDiv((uint32_t)PH));
@@ -230,26 +319,17 @@ void cudaF_tp_block_s(cudaStream_t st, const float *in, MatrixDim id, float *out
   // out[c, n*bs + p] = in[n, c*bs + p]   a = n, b = c, x = p
   int A = id.rows, B = od.rows, L = bs;
   if (A == 0 || B == 0 || L == 0) return;
-  if (L >= 32) {
-    unsigned int grid = ceil_div_u((long long)A * B * L, 256);
-    KCNN_LAUNCH(swap_outer_direct, grid, 256, 0, st, in, out, A, B, L, (long long)id.stride,
-                (long long)bs, (long long)od.stride, (long long)bs, FastDiv((uint32_t)L),
-                FastDiv((uint32_t)A), A * B);
-  } else {
-    int KB = 32 / L; if (KB < 1) KB = 1;
-    int pitch = (KB * L) | 1;
-    dim3 grid(ceil_div_u(A, 32), ceil_div_u(B, KB));
-    // gridDim.y <= 65535
-    if (grid.y > 65535) {
-      unsigned int g1 = ceil_div_u((long long)A * B * L, 256);
-      KCNN_LAUNCH(swap_outer_direct, g1, 256, 0, st, in, out, A, B, L, (long long)id.stride,
-                  (long long)bs, (long long)od.stride, (long long)bs, FastDiv((uint32_t)L),
-                  FastDiv((uint32_t)A), A * B);
-    } else {
-      KCNN_LAUNCH(swap_outer_tiled, grid, 256, 32 * pitch * sizeof(float), st, in, out, A, B, L,
-                  KB, (long long)id.stride, (long long)od.stride);
-    }
+  int KB = 128 / L; if (KB < 1) KB = 1;
+  dim3 grid(ceil_div_u(A, 32), ceil_div_u(B, KB));
+  if (L >= 32 || grid.y > 65535) {            // long runs: direct coalesced copy
+    launch_swap_outer_direct(st, in, out, A, B, L, (long long)id.stride, (long long)bs, (long long)od.stride,
+                             (long long)bs, A * B);
+    return;
   }
+  const int span = KB * L, pitch = span | 1;
+  KCNN_LAUNCH(swap_outer_tiled, grid, 256, 32 * pitch * sizeof(float), st, in, out, A, B, L, KB,
+              (long long)id.stride, (long long)od.stride, FastDiv((uint32_t)span), FastDiv((uint32_t)(32 * L)),
+              FastDiv((uint32_t)L));
 }
 
 void cudaF_tp_inside_block_s(cudaStream_t st, const float *in, MatrixDim id, float *out,
@@ -266,10 +346,8 @@ void cudaF_mod_permute_row_s(cudaStream_t st, const float *in, MatrixDim id, flo
   // (the reference walks i < rows with c = i % C, pos = i / C; rows need not be bs*C)
   int B = C, A = (id.rows + C - 1) / C, L = id.cols;
   if (id.rows == 0 || L == 0) return;
-  unsigned int grid = ceil_div_u((long long)A * B * L, 256);
-  KCNN_LAUNCH(swap_outer_direct, grid, 256, 0, st, in, out, A, B, L, (long long)C * id.stride,
-              (long long)id.stride, (long long)bs * od.stride, (long long)od.stride,
-              FastDiv((uint32_t)L), FastDiv((uint32_t)A), id.rows);
+  launch_swap_outer_direct(st, in, out, A, B, L, (long long)C * id.stride, (long long)id.stride,
+                           (long long)bs * od.stride, (long long)od.stride, id.rows);
 }
 
 void cudaF_copy_rows_at_s(cudaStream_t st, const float *src, MatrixDim sd, float *dest,

@@ -26,8 +26,18 @@
 //    (nnet0/nnet-component-nnet0.cc:889) into the same sweep.
 //  * Index mode: forward records the window position of the first maximum in
 //    one byte; backward routes from it without reading the activations.
+//  * Intermap pooling (pool_channel_dim > 1) and 2-D planes take the STAGED path: the
+//    channel stride H*W makes a warp of the direct kernels touch 32 different 128-byte
+//    lines per load, so they are bound by L1 wavefronts (measured 38-75 % of the HBM
+//    peak), not by HBM.  A pooled channel's window slab (pc*H*W floats) is contiguous in
+//    the row, so the staged kernels move whole slabs with 1-D TMA bulk copies
+//    (cp.async.bulk global -> shared, mbarrier complete_tx; backward also shared ->
+//    global), 4 stages x 24 KB per CTA, 2 persistent CTAs per SM, and do the strided
+//    window walk in shared memory.  Scan order, strict '<' and the sentinel are the same.
 
 #include "kcnn_common.cuh"
+
+#include <stdlib.h>
 
 namespace kcnn {
 
@@ -330,6 +340,276 @@ maxpool_backprop_index_time_vec4(const unsigned char *__restrict__ index, int in
   }
 }
 
+// ------------------------------------------------------------- staged path --
+
+namespace staged {
+
+constexpr int kStageFloats = 6144;          // 24 KB
+constexpr int kStages = 4;
+constexpr int kThreads = 1024;         // x 2 CTAs per SM: full occupancy for the shared-memory window walk
+constexpr int kSmemBytes = kStages * kStageFloats * 4 + kStages * 8 + 128;
+
+struct Geom {
+  int H, W, ph, pw, pc, OH, OW;
+  int HW, L, OHW;            // plane, slab = pc*HW floats, outputs per slab
+  int OC;                    // slabs (pooled channels) per row
+  int S;                     // slabs per chunk
+  int chunks_per_row;
+  FastDiv div_cpr, div_ohw, div_oh;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "POOL_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra POOL_WAIT_DONE;\n\t"
+      "bra POOL_WAIT_LOOP;\n\t"
+      "POOL_WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// kBackward = false: pool[j] = max over the window (optional arg-max byte).
+// kBackward = true : the staged slab is rewritten in place -- err where the element equals the
+//                    pooled value, 0 elsewhere (cnsl-cu-kernels.cu:302-303 + the caller's
+//                    kSetZero) -- and goes back to dest with a bulk store.
+// VW >= 1: H == 1 and pw == VW, the window row is one 32 / 64 / 128-bit shared-memory access;
+// VW == 0: any plane, scalar walk c -> w -> h; PH > 0 fixes pool_height_dim at compile time so
+// the innermost loop unrolls (the walk is instruction-bound, not bandwidth-bound).
+template <bool kBackward, bool kIndex, int VW, int PH>
+__global__ void __launch_bounds__(kThreads)
+maxpool_staged_kernel(const float *__restrict__ src, int src_stride, float *__restrict__ pool, int pool_stride,
+                      const float *__restrict__ out_deriv, int od_stride, float *__restrict__ dest,
+                      int dest_stride, unsigned char *__restrict__ index, int index_stride, int rows, Geom g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *stage_f = reinterpret_cast<float *>(smem_raw);
+  const uint32_t stage_u = smem_u32(smem_raw);
+  const uint32_t bar_u = stage_u + kStages * kStageFloats * 4;
+  const int tid = threadIdx.x;
+  const int nchunks = rows * g.chunks_per_row;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(bar_u + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  kcnn::pdl_prologue();
+
+  auto issue = [&](int k) {                       // thread 0: fetch the k-th chunk of this CTA
+    const long long chunk = (long long)blockIdx.x + (long long)k * gridDim.x;
+    if (chunk >= nchunks) return;
+    uint32_t i, cr;
+    g.div_cpr.divmod((uint32_t)chunk, i, cr);
+    const int s0 = cr * g.S, ns = min(g.S, g.OC - s0);
+    const uint32_t bytes = (uint32_t)ns * g.L * 4u;
+    const int st = k % kStages;
+    mbar_expect_tx(bar_u + 8 * st, bytes);
+    bulk_load(stage_u + st * kStageFloats * 4, src + (size_t)i * src_stride + (size_t)s0 * g.L, bytes,
+              bar_u + 8 * st);
+  };
+  constexpr int kPrefetch = kBackward ? kStages - 1 : kStages;
+  if (tid == 0)
+    for (int k = 0; k < kPrefetch; k++) issue(k);
+
+  for (int k = 0;; k++) {
+    const long long chunk = (long long)blockIdx.x + (long long)k * gridDim.x;
+    if (chunk >= nchunks) break;
+    uint32_t i, cr;
+    g.div_cpr.divmod((uint32_t)chunk, i, cr);
+    const int s0 = cr * g.S, ns = min(g.S, g.OC - s0);
+    const int st = k % kStages;
+    float *sm = stage_f + st * kStageFloats;
+    mbar_wait(bar_u + 8 * st, (uint32_t)(k / kStages) & 1u);
+
+    const int nout = ns * g.OHW;
+    const size_t j0 = (size_t)s0 * g.OHW;
+    for (int lo = tid; lo < nout; lo += kThreads) {
+      uint32_t ocl, pos, ow, oh;
+      g.div_ohw.divmod((uint32_t)lo, ocl, pos);
+      g.div_oh.divmod(pos, ow, oh);
+      float *p = sm + ocl * g.L + ow * g.pw * g.H + oh * g.ph;
+      if (!kBackward) {
+        float val = -1e20f;
+        int best = 0;
+        if (VW == 0) {
+          const int ph = PH > 0 ? PH : g.ph;
+          int kk = 0;
+          for (int c = 0; c < g.pc; c++)
+            for (int w = 0; w < g.pw; w++) {
+              const float *r = p + c * g.HW + w * g.H;
+#pragma unroll
+              for (int h = 0; h < ph; h++, kk++) {
+                const float e = r[h];
+                if (val < e) { val = e; if (kIndex) best = kk; }
+              }
+            }
+        } else {
+#pragma unroll 4
+          for (int c = 0; c < g.pc; c++) {
+            float e[VW > 0 ? VW : 1];
+            if (VW == 1) {
+              e[0] = p[c * g.HW];
+            } else if (VW == 2) {
+              const float2 v = *reinterpret_cast<const float2 *>(p + c * g.HW);
+              e[0] = v.x; e[1 % (VW > 0 ? VW : 1)] = v.y;
+            } else {
+              const float4 v = *reinterpret_cast<const float4 *>(p + c * g.HW);
+              e[0] = v.x; e[1 % (VW > 0 ? VW : 1)] = v.y; e[2 % (VW > 0 ? VW : 1)] = v.z; e[3 % (VW > 0 ? VW : 1)] = v.w;
+            }
+#pragma unroll
+            for (int w = 0; w < (VW > 0 ? VW : 1); w++)
+              if (val < e[w]) { val = e[w]; if (kIndex) best = c * VW + w; }
+          }
+        }
+        pool[(size_t)i * pool_stride + j0 + lo] = val;
+        if (kIndex) index[(size_t)i * index_stride + j0 + lo] = (unsigned char)best;
+      } else {
+        const float ov = __ldg(pool + (size_t)i * pool_stride + j0 + lo);
+        const float err = __ldg(out_deriv + (size_t)i * od_stride + j0 + lo);
+        if (VW == 0) {
+          const int ph = PH > 0 ? PH : g.ph;
+          for (int c = 0; c < g.pc; c++)
+            for (int w = 0; w < g.pw; w++) {
+              float *q = p + c * g.HW + w * g.H;
+#pragma unroll
+              for (int h = 0; h < ph; h++) q[h] = (ov == q[h]) ? err : 0.0f;
+            }
+        } else if (VW == 1) {
+#pragma unroll 4
+          for (int c = 0; c < g.pc; c++) {
+            float *q = p + c * g.HW;
+            *q = (ov == *q) ? err : 0.0f;
+          }
+        } else if (VW == 2) {
+#pragma unroll 4
+          for (int c = 0; c < g.pc; c++) {
+            float2 *q = reinterpret_cast<float2 *>(p + c * g.HW);
+            float2 v = *q;
+            v.x = (ov == v.x) ? err : 0.0f; v.y = (ov == v.y) ? err : 0.0f;
+            *q = v;
+          }
+        } else {
+#pragma unroll 4
+          for (int c = 0; c < g.pc; c++) {
+            float4 *q = reinterpret_cast<float4 *>(p + c * g.HW);
+            float4 v = *q;
+            v.x = (ov == v.x) ? err : 0.0f; v.y = (ov == v.y) ? err : 0.0f;
+            v.z = (ov == v.z) ? err : 0.0f; v.w = (ov == v.w) ? err : 0.0f;
+            *q = v;
+          }
+        }
+      }
+    }
+    if (kBackward) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic stores -> bulk-store reads
+      __syncthreads();
+      if (tid == 0) {
+        bulk_store(dest + (size_t)i * dest_stride + (size_t)s0 * g.L, stage_u + st * kStageFloats * 4,
+                   (uint32_t)ns * g.L * 4u);
+        // the stage of chunk k-1 is free once ITS store has read it: all but the newest group
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        issue(k + kStages - 1);
+      }
+    } else {
+      __syncthreads();                                                 // everyone is done reading the stage
+      if (tid == 0) issue(k + kStages);
+    }
+  }
+  if (kBackward && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// Chunking of a row of OC slabs of L floats: every chunk starts and ends on a 16-byte boundary.
+static bool make_geom(Geom *g, int H, int W, int ph, int pw, int pc, int in_cols, int out_cols) {
+  if (H <= 0 || W <= 0 || ph <= 0 || pw <= 0 || pc <= 0) return false;
+  g->H = H; g->W = W; g->ph = ph; g->pw = pw; g->pc = pc;
+  g->OH = H / ph; g->OW = W / pw;
+  g->HW = H * W; g->OHW = g->OH * g->OW;
+  if (g->OHW <= 0) return false;
+  const long long L = (long long)pc * g->HW;
+  if (L > kStageFloats) return false;
+  g->L = (int)L;
+  if (out_cols % g->OHW != 0) return false;
+  g->OC = out_cols / g->OHW;
+  if (g->OC <= 0 || (long long)g->OC * L > in_cols) return false;
+  if (((long long)g->OC * L) % 4 != 0) return false;              // the last chunk ends on 16 bytes
+  const int m = (L % 4 == 0) ? 1 : (L % 2 == 0 ? 2 : 4);          // S*L % 4 == 0
+  int S = (int)(kStageFloats / L) / m * m;
+  if (S <= 0) return false;
+  if (S >= g->OC) S = g->OC;
+  g->S = S;
+  g->chunks_per_row = (g->OC + S - 1) / S;
+  g->div_cpr = FastDiv((uint32_t)g->chunks_per_row);
+  g->div_ohw = FastDiv((uint32_t)g->OHW);
+  g->div_oh = FastDiv((uint32_t)g->OH);
+  return true;
+}
+
+static bool enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_POOL_STAGED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <bool kBackward, bool kIndex, int VW, int PH>
+static void launch_one(cudaStream_t st, const float *src, int src_stride, float *pool, int pool_stride,
+                       const float *out_deriv, int od_stride, float *dest, int dest_stride, unsigned char *index,
+                       int index_stride, int rows, const Geom &g) {
+  auto kern = maxpool_staged_kernel<kBackward, kIndex, VW, PH>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    attr_set = true;
+  }
+  const long long nchunks = (long long)rows * g.chunks_per_row;
+  const unsigned grid = (unsigned)(nchunks < 2 * kNumSMs ? nchunks : 2 * kNumSMs);
+  KCNN_LAUNCH(kern, grid, kThreads, kSmemBytes, st, src, src_stride, pool, pool_stride, out_deriv, od_stride, dest,
+              dest_stride, index, index_stride, rows, g);
+}
+
+template <bool kBackward, bool kIndex>
+static void launch(cudaStream_t st, const float *src, int src_stride, float *pool, int pool_stride,
+                   const float *out_deriv, int od_stride, float *dest, int dest_stride, unsigned char *index,
+                   int index_stride, int rows, const Geom &g) {
+  const int vw = (g.H == 1 && g.ph == 1 && (g.pw == 1 || g.pw == 2 || g.pw == 4) && g.W % g.pw == 0) ? g.pw : 0;
+#define KCNN_POOL_STAGED(VW_, PH_)                                                                            \
+  launch_one<kBackward, kIndex, VW_, PH_>(st, src, src_stride, pool, pool_stride, out_deriv, od_stride, dest, \
+                                          dest_stride, index, index_stride, rows, g)
+  if (vw == 4) KCNN_POOL_STAGED(4, 0);
+  else if (vw == 2) KCNN_POOL_STAGED(2, 0);
+  else if (vw == 1) KCNN_POOL_STAGED(1, 0);
+  else if (g.ph == 1) KCNN_POOL_STAGED(0, 1);
+  else if (g.ph == 2) KCNN_POOL_STAGED(0, 2);
+  else if (g.ph == 3) KCNN_POOL_STAGED(0, 3);
+  else if (g.ph == 4) KCNN_POOL_STAGED(0, 4);
+  else KCNN_POOL_STAGED(0, 0);
+#undef KCNN_POOL_STAGED
+}
+
+}  // namespace staged
+
 // ---------------------------------------------------------------- host side --
 
 static bool time_vec_ok(int H, int W, int ph, int pw, const void *a, int sa, const void *b,
@@ -349,6 +629,17 @@ static void launch_prop_plain(cudaStream_t st, const float *src, MatrixDim sd, f
   if (pd.rows == 0 || pd.cols == 0) return;
   bool vec = time_vec_ok(H, W, ph, pw, src, sd.stride, pool, pd.stride) &&
              (!kIndex || (index_stride % 4 == 0 && host_aligned16(index)));
+  bool vec_first = vec && (pc == 1 || !staged::enabled());       // contiguous windows: already at the HBM peak
+  if (!vec_first) {
+    staged::Geom sg;
+    if (staged::enabled() && sd.stride % 4 == 0 && host_aligned16(src) &&
+        (long long)pd.rows * sd.stride < (1ll << 31) &&
+        staged::make_geom(&sg, H, W, ph, pw, pc, sd.cols, pd.cols)) {
+      staged::launch<false, kIndex>(st, src, sd.stride, pool, pd.stride, nullptr, 0, nullptr, 0, index,
+                                    index_stride, pd.rows, sg);
+      return;
+    }
+  }
   if (vec) {
     int OW = W / pw, quads = pd.cols / 4, owq = OW / 4;
     long long total = (long long)pd.rows * quads;
@@ -413,6 +704,19 @@ void cudaF_maxpool_backprop_s(cudaStream_t st, const float *in_val, MatrixDim id
     bool vec = zero_others && time_vec_ok(H, W, ph, pw, in_val, id.stride, dest, dd.stride) &&
                ovd.stride % 4 == 0 && odd.stride % 4 == 0 && host_aligned16(out_val) &&
                host_aligned16(out_deriv);
+    if (zero_others && !(vec && pc == 1) && staged::enabled()) {
+      // every element of dest must lie in exactly one window: the slab is stored back whole
+      staged::Geom sg;
+      if (W % pw == 0 && H % ph == 0 && id.stride % 4 == 0 && dd.stride % 4 == 0 && host_aligned16(in_val) &&
+          host_aligned16(dest) && (long long)id.rows * id.stride < (1ll << 31) &&
+          (long long)dd.rows * dd.stride < (1ll << 31) &&
+          staged::make_geom(&sg, H, W, ph, pw, pc, id.cols, odd.cols) &&
+          (long long)sg.OC * sg.L == dd.cols && dd.cols == id.cols) {
+        staged::launch<true, false>(st, in_val, id.stride, const_cast<float *>(out_val), ovd.stride, out_deriv,
+                                    odd.stride, dest, dd.stride, nullptr, 0, odd.rows, sg);
+        return;
+      }
+    }
     if (vec) {
       int OW = W / pw, quads = odd.cols / 4, owq = OW / 4;
       long long total = (long long)odd.rows * quads;

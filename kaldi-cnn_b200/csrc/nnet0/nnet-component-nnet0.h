@@ -116,6 +116,15 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   /// propagated: Backprop then reuses Propagate's channels-last staging copy instead of
   /// packing in_value again.  Off by default: a bare Component makes no such assumption.
   virtual void SetInputPersists(bool on) { input_persists_ = on; staged_src_ = NULL; }
+  virtual uint64 StepSignature() const {
+    uint64 h = HashValue(learning_rate_, 13);
+    h = HashValue(weight_decay_, h); h = HashValue(momentum_, h);
+    h = HashValue(linear_params_.Data(), h); h = HashValue(bias_params_.Data(), h);
+    h = HashValue(prev_grad_.Data(), h); h = HashValue(deferred_, h);
+    h = HashValue(w_grad_.data, h); h = HashValue(b_grad_.data, h);
+    h = HashValue(input_persists_, h);
+    return HashValue(is_gradient_, h);
+  }
 
  protected:
   virtual void Update(const CuMatrixBase<BaseFloat> &in_value,
@@ -252,6 +261,11 @@ class FullyConnectedComponent : public nnet2::AffineComponent {
   virtual void UpdateSimple(const CuMatrixBase<BaseFloat> &in_value,
                             const CuMatrixBase<BaseFloat> &out_deriv);
   virtual void ApplyGradient(int32 total_num_samples);
+  virtual uint64 StepSignature() const {
+    uint64 h = nnet2::AffineComponent::StepSignature();
+    h = HashValue(weight_decay_, h); h = HashValue(momentum_, h);
+    return HashValue(prev_grad_.Data(), h);
+  }
 
  protected:
   KALDI_DISALLOW_COPY_AND_ASSIGN(FullyConnectedComponent);

@@ -97,6 +97,18 @@ class Component {
   virtual bool BackpropNeedsInput() const { return true; }
   virtual bool BackpropNeedsOutput() const { return true; }
 
+  /// B200 extension: a hash of everything a captured CUDA graph of this component's
+  /// Propagate / Backprop bakes in besides the activation buffers -- parameter addresses,
+  /// learning rate, momentum, ... (NnetMinibatchUpdater::TrainStep re-captures its graph
+  /// when the sum over the components changes).
+  virtual uint64 StepSignature() const { return 0; }
+  static uint64 HashBytes(const void *p, size_t n, uint64 h = 1469598103934665603ull) {
+    const unsigned char *b = static_cast<const unsigned char *>(p);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+  }
+  template <class T> static uint64 HashValue(const T &v, uint64 h) { return HashBytes(&v, sizeof(T), h); }
+
   static Component *ReadNew(std::istream &is, bool binary);
   virtual Component *Copy() const = 0;
   static Component *NewFromString(const std::string &initializer_line);
@@ -170,6 +182,8 @@ class NonlinearComponent : public Component {
   virtual void Read(std::istream &is, bool binary);
   virtual void Write(std::ostream &os, bool binary) const;
   double Count() const { return count_; }
+  /// Frames a replayed CUDA graph of Backprop has accumulated into the statistics.
+  void AddToCount(double frames) { count_ += frames; }
   /// Host copies of the diagnostics.
   void GetStats(Vector<double> *value_sum, Vector<double> *deriv_sum) const;
 
@@ -247,6 +261,9 @@ class DropoutComponent : public Component {
   virtual void Write(std::ostream &os, bool binary) const;
   virtual std::string Type() const { return "DropoutComponent"; }
   void SetDropoutScale(BaseFloat scale) { dropout_scale_ = scale; }
+  virtual uint64 StepSignature() const {
+    return HashValue(seed_dev_, HashValue(dropout_scale_, HashValue(dropout_proportion_, 7)));
+  }
   virtual bool BackpropNeedsInput() const { return true; }
   virtual bool BackpropNeedsOutput() const { return true; }
   virtual Component *Copy() const;
@@ -312,6 +329,13 @@ class AffineComponent : public UpdatableComponent {
   virtual std::vector<GradBuffer> GradientBuffers();
   virtual size_t GradientFloats() const;
   virtual void SetGradientStorage(float *base);
+  virtual uint64 StepSignature() const {
+    uint64 h = HashValue(learning_rate_, 11);
+    h = HashValue(linear_params_.Data(), h); h = HashValue(bias_params_.Data(), h);
+    h = HashValue(linear_params_.Stride(), h); h = HashValue(deferred_, h);
+    h = HashValue(w_grad_.data, h); h = HashValue(b_grad_.data, h);
+    return HashValue(is_gradient_, h);
+  }
 
  protected:
   virtual void Update(const CuMatrixBase<BaseFloat> &in_value,

@@ -1,5 +1,8 @@
 // nnet2/nnet-nnet.cc -- shim (see nnet-nnet.h).
+#include <stdlib.h>
 #include <sstream>
+
+#include <cuda_runtime_api.h>
 
 #include "nnet2/nnet-nnet.h"
 #include "cnsl-cu-kernels.h"
@@ -91,14 +94,25 @@ std::string Nnet::Info() const {
 
 // ------------------------------------------------------- NnetMinibatchUpdater --
 
+struct NnetMinibatchUpdater::GraphState {
+  cudaGraphExec_t exec;
+  uint64 key;
+  std::vector<double> count_delta;      // NonlinearComponent::count_ added by one step (host state)
+  bool failed;                          // a capture was refused: stay eager for this key
+  GraphState() : exec(NULL), key(0), failed(false) {}
+};
+
 NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
-    : nnet_(nnet), num_rows_(0), labels_(NULL), objf_dev_(NULL) {
+    : graph_(new GraphState), seen_key_(0), last_replayed_(false),
+      nnet_(nnet), num_rows_(0), labels_(NULL), objf_dev_(NULL) {
   objf_dev_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double)));
   CU_SAFE_CALL(cudaMemsetAsync(objf_dev_, 0, sizeof(double), Str()));
   SetInputPersists(true);    // forward_[c] is ours and untouched between Forward and Backward
 }
 
 NnetMinibatchUpdater::~NnetMinibatchUpdater() {
+  DropGraph();
+  delete graph_;
   SetInputPersists(false);
   CuDevice::Instantiate().Free(objf_dev_);
 }
@@ -157,6 +171,110 @@ void NnetMinibatchUpdater::Backward(int32 last, int32 first) {
     comp.Backprop(info_[c], info_[c + 1], forward_[c], forward_[c + 1], deriv_a_, &comp, &deriv_b_);
     deriv_a_.Swap(&deriv_b_);
   }
+}
+
+// ------------------------------------------------------------- graph step --
+
+static bool GraphsEnabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_NNET_GRAPH");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+void NnetMinibatchUpdater::DropGraph() {
+  if (graph_->exec) cudaGraphExecDestroy(graph_->exec);
+  graph_->exec = NULL;
+  graph_->key = 0;
+  graph_->failed = false;
+}
+
+uint64 NnetMinibatchUpdater::StepKey(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) const {
+  uint64 h = Component::HashValue(feats.Data(), 17);
+  h = Component::HashValue(feats.NumRows(), h);
+  h = Component::HashValue(feats.NumCols(), h);
+  h = Component::HashValue(feats.Stride(), h);
+  h = Component::HashValue(labels_dev, h);
+  h = Component::HashValue(Str(), h);
+  h = Component::HashValue(CuDevice::Instantiate().MathMode(), h);
+  for (int32 c = 0; c < nnet_->NumComponents(); c++)
+    h = Component::HashValue(nnet_->GetComponent(c).StepSignature(), h);
+  return h | 1;      // never 0
+}
+
+void NnetMinibatchUpdater::EagerStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) {
+  Forward(feats);
+  ComputeObjfAndDeriv(labels_dev);
+  Backward();
+}
+
+void NnetMinibatchUpdater::TrainStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) {
+  last_replayed_ = false;
+  cudaStream_t st = Str();
+  const bool capturable = GraphsEnabled() && st != 0 && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (!capturable) { EagerStep(feats, labels_dev); return; }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) { EagerStep(feats, labels_dev); return; }   // caller's own capture
+  const uint64 key = StepKey(feats, labels_dev);
+  const int32 L = nnet_->NumComponents();
+  if (graph_->exec != NULL && graph_->key == key) {
+    CU_SAFE_CALL(cudaGraphLaunch(graph_->exec, st));
+    for (int32 c = 0; c < L; c++) {
+      NonlinearComponent *nl = dynamic_cast<NonlinearComponent *>(&nnet_->GetComponent(c));
+      if (nl && graph_->count_delta[c] != 0.0) nl->AddToCount(graph_->count_delta[c]);
+    }
+    last_replayed_ = true;
+    return;
+  }
+  if (graph_->key != key) DropGraph();
+  if (seen_key_ != key || graph_->failed) {          // first step of this configuration: eager
+    EagerStep(feats, labels_dev);
+    seen_key_ = key;
+    return;
+  }
+  // Second step: record it.  Host-side effects of a step (the frame counts of the
+  // nonlinearity statistics) happen once here and are re-applied after every replay.
+  std::vector<double> before(L, 0.0);
+  for (int32 c = 0; c < L; c++) {
+    const NonlinearComponent *nl = dynamic_cast<const NonlinearComponent *>(&nnet_->GetComponent(c));
+    if (nl) before[c] = nl->Count();
+  }
+  cudaGraph_t g = NULL;
+  bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+  if (ok) {
+    try {
+      EagerStep(feats, labels_dev);
+    } catch (...) {
+      ok = false;
+    }
+    if (cudaStreamEndCapture(st, &g) != cudaSuccess || g == NULL) ok = false;
+  }
+  cudaGraphExec_t exec = NULL;
+  if (ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) ok = false;
+  if (g) cudaGraphDestroy(g);
+  if (!ok) {
+    cudaGetLastError();                               // clear the sticky capture error
+    for (int32 c = 0; c < L; c++) {                   // the aborted recording did not run
+      NonlinearComponent *nl = dynamic_cast<NonlinearComponent *>(&nnet_->GetComponent(c));
+      if (nl) nl->AddToCount(before[c] - nl->Count());
+    }
+    graph_->failed = true;
+    graph_->key = key;
+    EagerStep(feats, labels_dev);
+    return;
+  }
+  graph_->exec = exec;
+  graph_->key = key;
+  graph_->count_delta.assign(L, 0.0);
+  for (int32 c = 0; c < L; c++) {
+    const NonlinearComponent *nl = dynamic_cast<const NonlinearComponent *>(&nnet_->GetComponent(c));
+    if (nl) graph_->count_delta[c] = nl->Count() - before[c];
+  }
+  CU_SAFE_CALL(cudaGraphLaunch(exec, st));            // the recording itself executed nothing
+  last_replayed_ = true;
 }
 
 void NnetMinibatchUpdater::SetDeferredUpdate(bool on) {

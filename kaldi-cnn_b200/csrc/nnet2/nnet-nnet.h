@@ -60,6 +60,17 @@ class NnetMinibatchUpdater {
   /// top).  Splitting the range lets a data-parallel caller start all-reducing the
   /// gradients of the upper layers while the lower layers are still running.
   void Backward(int32 last = -1, int32 first = 0);
+  /// One whole training step on device buffers: Forward(feats), ComputeObjfAndDeriv(labels),
+  /// Backward() -- what NnetUpdater does per minibatch.  The first call for a given (feats,
+  /// labels, configuration) runs the ~85 launches eagerly (buffers and scratch get sized); the
+  /// second captures them into a CUDA graph; from then on a step is ONE cudaGraphLaunch.  The
+  /// graph is dropped and re-captured when the buffers or any component's StepSignature()
+  /// (parameter addresses, learning rate, momentum, ...) change.  Needs a non-default compute
+  /// stream (the legacy default stream cannot be captured): otherwise, or with
+  /// KCNN_NNET_GRAPH=0, every step runs eagerly.
+  void TrainStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev);
+  /// True when the last TrainStep was a graph replay.
+  bool LastStepReplayed() const { return last_replayed_; }
   /// ApplyGradient(total_rows) on every updatable component (deferred-update mode).
   void ApplyGradients(int32 total_rows);
   /// Total floats of gradient storage; SetGradientArena places every component's
@@ -77,6 +88,13 @@ class NnetMinibatchUpdater {
   int32 NumRows() const { return num_rows_; }
  private:
   void SetInputPersists(bool on);
+  void EagerStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev);
+  void DropGraph();
+  uint64 StepKey(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) const;
+  struct GraphState;                 // cudaGraphExec_t + the host-side effects of one step
+  GraphState *graph_;
+  uint64 seen_key_;                  // key of the last eager step (capture needs one warm step)
+  bool last_replayed_;
   Nnet *nnet_;
   int32 num_rows_;
   std::vector<CuMatrix<BaseFloat> > forward_;   // [0] = copy-free view of the input
