@@ -283,6 +283,20 @@ int cudaF_conv2d_fprop_staged(cudaStream_t st, int math, const float *in, Matrix
                                float *out, MatrixDim out_dim, int in_height, int in_width,
                                int in_channel, int pad_height, int pad_width, int kernel_height,
                                int kernel_width, int group, int concat, float *staging);
+/* The same forward pass with an activation fused into its epilogue (KCNN_ACT_RELU:
+ * RectifiedLinearComponent::Propagate, upstream nnet2/nnet-component.cc:799-811, out = x > 0 ? x : 0
+ * applied to the biased output before it is stored: `out` then holds what the ReLU component
+ * would have produced and the pre-activation is never written).  staging as above. */
+#define KCNN_ACT_NONE 0
+#define KCNN_ACT_RELU 1
+int cudaF_conv2d_fprop_act(cudaStream_t st, int math, const float *in, MatrixDim in_dim,
+                           const float *kernel, MatrixDim kernel_dim, const float *bias, float *out,
+                           MatrixDim out_dim, int in_height, int in_width, int in_channel,
+                           int pad_height, int pad_width, int kernel_height, int kernel_width,
+                           int group, int concat, float *staging, int act);
+void cudaF_affine_fprop_act(cudaStream_t st, int math, const float *in, MatrixDim in_dim,
+                            const float *w, MatrixDim w_dim, const float *bias, float *out,
+                            MatrixDim out_dim, int act);
 int cudaF_affine_wgrad_sgd(cudaStream_t st, int math, const float *in_value,
                            MatrixDim in_value_dim, const float *out_deriv,
                            MatrixDim out_deriv_dim, float *w, MatrixDim w_dim,

@@ -190,6 +190,10 @@ int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const 
  * second call with the same buffers / configuration and replayed from then on
  * (KCNN_NNET_GRAPH=0 keeps every step eager). */
 int kcnn_nnet_train_step(kcnn_nnet *n, const float *feats, int rows, int stride, const int *labels);
+/* Fusion of adjacent components in the forward pass ([Convolution | FullyConnected] + ReLU as
+ * one launch); default on.  With fusion the pre-activation kcnn_nnet_activation(c + 1) of a
+ * fused pair is not filled. */
+int kcnn_nnet_set_fusion(kcnn_nnet *n, int on);
 /* 1 when the most recent train step of this network was a graph replay, else 0. */
 int kcnn_nnet_last_step_replayed(const kcnn_nnet *n);
 

@@ -79,6 +79,8 @@ _PROTOS = {
     "cudaF_conv2d_backward": [S, I, P, M, P, M, P, M, P, M, P, M, P, P, M, P, I, F, F, F, P,
                               I, I, I, I, I, I, I, I],
     "cudaF_conv2d_fprop_staged": [S, I, P, M, P, M, P, P, M, I, I, I, I, I, I, I, I, I, P],
+    "cudaF_conv2d_fprop_act": [S, I, P, M, P, M, P, P, M, I, I, I, I, I, I, I, I, I, P, I],
+    "cudaF_affine_fprop_act": [S, I, P, M, P, M, P, P, M, I],
     "kcnn_conv2d_staging_floats": [I, I, I, I, I, I, I, I, I],
     "cudaF_affine_wgrad_sgd": [S, I, P, M, P, M, P, M, P, M, P, F, F, F],
     "cudaF_sgd_momentum_update": [S, P, M, P, M, P, M, F, F, F],
@@ -99,6 +101,7 @@ _RESTYPES = {
     "cudaF_conv2d_backward": c_int,
     "kcnn_conv2d_staging_floats": c_size_t,
     "cudaF_conv2d_fprop_staged": c_int,
+    "cudaF_conv2d_fprop_act": c_int,
     "cudaF_affine_wgrad_sgd": c_int,
 }
 

@@ -287,6 +287,10 @@ class Nnet:
         _check(_lib().kcnn_nnet_train_step(self.h, ctypes.c_void_p(feats.data_ptr()), d.rows, d.stride,
                                            ctypes.c_void_p(labels.data_ptr())))
 
+    def set_fusion(self, on):
+        """[Convolution | FullyConnected] + ReLU as one launch in the forward pass (default on)."""
+        _check(_lib().kcnn_nnet_set_fusion(self.h, int(bool(on))))
+
     @property
     def last_step_replayed(self):
         return bool(_lib().kcnn_nnet_last_step_replayed(self.h))

@@ -544,6 +544,13 @@ int kcnn_nnet_train_step(kcnn_nnet *n, const float *feats, int rows, int stride,
   KCNN_CATCH(-1)
 }
 
+int kcnn_nnet_set_fusion(kcnn_nnet *n, int on) {
+  KCNN_TRY
+  N(n)->U().SetFusion(on != 0);
+  return 0;
+  KCNN_CATCH(-1)
+}
+
 int kcnn_nnet_last_step_replayed(const kcnn_nnet *n) {
   const NnetHandle *h = N(n);
   return (h->updater != NULL && h->updater->LastStepReplayed()) ? 1 : 0;

@@ -156,7 +156,7 @@ inline void launch_pack(cudaStream_t st, const float *in, int ld, int N, int C, 
 // maps * R floats (the reference's [map][pos] layout), written 512 bytes per warp instruction.
 __device__ __forceinline__ void store_maps_transposed(const float *stage, int tid, int n0, int nb, int R,
                                                       int col0, int maps, int num_samples, float *out, int ldo,
-                                                      const float *bias, const FastDiv &div_r) {
+                                                      const float *bias, const FastDiv &div_r, bool relu = false) {
   const int total = maps * R;
   for (int s = 0; s < nb; s++) {
     const int n = n0 + s;
@@ -168,6 +168,7 @@ __device__ __forceinline__ void store_maps_transposed(const float *stage, int ti
       div_r.divmod((uint32_t)idx, g, pos);
       float v = srow[pos * PITCH + g];
       if (bias) v += __ldg(bias + col0 + g);
+      if (relu) v = v > 0.0f ? v : 0.0f;
       orow[idx] = v;
     }
   }
@@ -195,6 +196,7 @@ struct ConvRowsProb {
   float *out;              // [N][ldo], sample rows hold [map][R]
   int ldo;
   const float *bias;       // per map or nullptr
+  int relu;                // rectify after the bias (RectifiedLinearComponent fused)
   FastDiv div_inner, div_r;
 
   __device__ __forceinline__ void kb_range(int z, int &b, int &e) const {
@@ -236,7 +238,7 @@ struct ConvRowsProb {
                                    IdentityRow());
     } else {
       store_maps_transposed(stage, tid, mt * nb, nb, R, col0, min(BN, out_maps - col0), num_samples, out, ldo,
-                            bias, div_r);
+                            bias, div_r, relu != 0);
     }
   }
 };
@@ -244,7 +246,7 @@ struct ConvRowsProb {
 // out[n][g*R + pos] = sum_z ws[z][(n*R + pos)][g] (+ bias[g]); one thread per (row m, 4 maps).
 __global__ void __launch_bounds__(256)
 conv_rows_reduce_kernel(const float *__restrict__ ws, int splits, int M, int maps, int R, float *__restrict__ out,
-                        int ldo, const float *__restrict__ bias, FastDiv div_g4, FastDiv div_r) {
+                        int ldo, const float *__restrict__ bias, FastDiv div_g4, FastDiv div_r, int relu) {
   kcnn::pdl_prologue();
   const int g4n = maps >> 2;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,6 +262,10 @@ conv_rows_reduce_kernel(const float *__restrict__ ws, int splits, int M, int map
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   if (bias) { s.x += __ldg(bias + g); s.y += __ldg(bias + g + 1); s.z += __ldg(bias + g + 2); s.w += __ldg(bias + g + 3); }
+  if (relu) {
+    s.x = s.x > 0.0f ? s.x : 0.0f; s.y = s.y > 0.0f ? s.y : 0.0f;
+    s.z = s.z > 0.0f ? s.z : 0.0f; s.w = s.w > 0.0f ? s.w : 0.0f;
+  }
   float *o = out + (size_t)n * ldo + (size_t)g * R + pos;
   o[0] = s.x; o[R] = s.y; o[2 * R] = s.z; o[3 * R] = s.w;
 }
@@ -291,10 +297,12 @@ inline bool launch_conv_rows(cudaStream_t st, const CUtensorMap &ma, const CUten
   ConvRowsProb<kBMn, true> q;
   q.num_samples = p.num_samples; q.R = p.R; q.nb = p.nb; q.taps = p.taps; q.inner_blocks = p.inner_blocks;
   q.a_w0 = p.a_w0; q.a_wstep = p.a_wstep; q.out_maps = p.out_maps; q.out = p.out; q.ldo = p.ldo; q.bias = p.bias;
+  q.relu = p.relu;
   q.div_inner = p.div_inner; q.div_r = p.div_r; q.kb_per_split = per; q.workspace = ws;
   launch_prob(st, ma, mb, q, dim3(grid.x, grid.y, splits), per);
   KCNN_LAUNCH(conv_rows_reduce_kernel, ceil_div_u((long long)M * (p.out_maps >> 2), 256), 256, 0, st, ws, splits, M,
-              p.out_maps, p.R, p.out, p.ldo, p.bias, FastDiv((uint32_t)(p.out_maps >> 2)), FastDiv((uint32_t)p.R));
+              p.out_maps, p.R, p.out, p.ldo, p.bias, FastDiv((uint32_t)(p.out_maps >> 2)), FastDiv((uint32_t)p.R),
+              p.relu);
   return true;
 }
 
@@ -313,6 +321,7 @@ struct ConvFullFpropProb {
   float *out;
   int ldo;
   const float *bias;
+  int relu;
   FastDiv div_jb, div_ow;
 
   int total_kb;            // C * j_blocks
@@ -334,7 +343,8 @@ struct ConvFullFpropProb {
   __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
     const int g0 = nt * BN;
     if (g0 >= G) return;
-    store_maps_transposed(stage, tid, mt * nb, nb, OW, g0, min(BN, G - g0), num_samples, out, ldo, bias, div_ow);
+    store_maps_transposed(stage, tid, mt * nb, nb, OW, g0, min(BN, G - g0), num_samples, out, ldo, bias, div_ow,
+                          relu != 0);
   }
 };
 
@@ -501,7 +511,8 @@ inline bool encode_act_map(CUtensorMap *map, const float *act, int N, int R, int
 // staging (optional): caller-owned [N*W*C] floats that receive the channels-last copy of `in`
 // and stay valid after the call, so the matching Backprop can skip its own pack of in_value.
 inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int ld_in, const float *kernel,
-                       int ld_k, const float *bias, float *out, int ldo, float *staging = nullptr) {
+                       int ld_k, const float *bias, float *out, int ldo, float *staging = nullptr,
+                       bool relu = false) {
   if (!conv_tma_shape_ok(q)) return false;
   float *xcl = staging ? staging : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
   if (!xcl || !host_aligned16(xcl)) return false;
@@ -512,7 +523,7 @@ inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int
   launch_pack(st, in, ld_in, q.N, q.C, q.W, xcl, nullptr);
   ConvRowsProb<true> p;
   p.num_samples = q.N; p.R = q.OW; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.C + 31) / 32;
-  p.a_w0 = -q.pw; p.a_wstep = 1; p.out_maps = q.G; p.out = out; p.ldo = ldo; p.bias = bias;
+  p.a_w0 = -q.pw; p.a_wstep = 1; p.out_maps = q.G; p.out = out; p.ldo = ldo; p.bias = bias; p.relu = relu ? 1 : 0;
   p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.OW);
   launch_conv_rows(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1));
   return true;
@@ -597,7 +608,7 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
   if (do_dgrad) {
     ConvRowsProb<false> p;
     p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
-    p.a_w0 = q.pw; p.a_wstep = -1; p.out_maps = q.C; p.out = b.in_deriv; p.ldo = b.ld_id; p.bias = nullptr;
+    p.a_w0 = q.pw; p.a_wstep = -1; p.out_maps = q.C; p.out = b.in_deriv; p.ldo = b.ld_id; p.bias = nullptr; p.relu = 0;
     p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.W);
     launch_conv_rows(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
   }
@@ -627,10 +638,10 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     }
     if (b.sgd)
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, KernelRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
-                  wout, ld_w, nullptr, b.prev, *b.sgd, rm, tail, blocks);
+                  wout, ld_w, nullptr, b.prev, *b.sgd, rm, tail, blocks, 0);
     else
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, KernelRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
-                  wout, ld_w, nullptr, nullptr, none, rm, tail, blocks);
+                  wout, ld_w, nullptr, nullptr, none, rm, tail, blocks, 0);
   } else if (b.sgd) {
     ConvWgradProb<EPI_SGD> p; fill(p);
     launch_prob(st, wa, wb, p, grid, per);
@@ -666,7 +677,8 @@ inline bool encode_window_map(CUtensorMap *map, const float *in, int ld, const C
 }
 
 inline bool conv_full_fprop(cudaStream_t st, const ConvFullShape &q, const float *in, int ld_in,
-                            const float *kernel, int ld_k, const float *bias, float *out, int ldo) {
+                            const float *kernel, int ld_k, const float *bias, float *out, int ldo,
+                            bool relu = false) {
   if (!conv_full_shape_ok(q)) return false;
   const int ks = q.KW * q.H, nb = 128 / q.OW;
   CUtensorMap ma, mb;
@@ -674,7 +686,7 @@ inline bool conv_full_fprop(cudaStream_t st, const ConvFullShape &q, const float
   if (!encode_2d(&mb, Matrix{kernel, q.C * ks, q.G, ld_k}, 32, true)) return false;
   ConvFullFpropProb p;
   p.num_samples = q.N; p.OW = q.OW; p.nb = nb; p.ks = ks; p.j_blocks = (ks + 31) / 32; p.G = q.G;
-  p.total_kb = q.C * p.j_blocks; p.out = out; p.ldo = ldo; p.bias = bias;
+  p.total_kb = q.C * p.j_blocks; p.out = out; p.ldo = ldo; p.bias = bias; p.relu = relu ? 1 : 0;
   p.div_jb = FastDiv((uint32_t)p.j_blocks); p.div_ow = FastDiv((uint32_t)q.OW);
   launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1), p.total_kb);
   return true;
@@ -758,10 +770,10 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
     }
     if (b.sgd)
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
-                  wout, ld_w, nullptr, b.prev, *b.sgd, IdentityRow(), tail, blocks);
+                  wout, ld_w, nullptr, b.prev, *b.sgd, IdentityRow(), tail, blocks, 0);
     else
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M,
-                  q.G, wout, ld_w, nullptr, nullptr, none, IdentityRow(), tail, blocks);
+                  q.G, wout, ld_w, nullptr, nullptr, none, IdentityRow(), tail, blocks, 0);
   } else if (b.sgd) {
     ConvWgradProb<EPI_SGD, true> p; fill(p);
     launch_prob(st, wa, wb, p, grid, per);

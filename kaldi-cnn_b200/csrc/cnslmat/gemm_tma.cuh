@@ -515,7 +515,7 @@ __device__ __forceinline__ void sgd_apply(float &w, float &p, float g, const Sgd
 template <int kEpi, int kRows, class RowMap>
 __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, int n0, int M, int N,
                                            float *obase, int ld, const float *bias_n, float *aux,
-                                           const SgdCoef &sgd, RowMap row_of) {
+                                           const SgdCoef &sgd, RowMap row_of, bool relu = false) {
   const int wl = tid >> 5, lane = tid & 31;
   const int n = n0 + 4 * lane;
   const bool vec_ok = (n + 3 < N) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15u) == 0);
@@ -582,6 +582,10 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
         }
     } else {
       a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+      if (relu) {       // RectifiedLinearComponent::Propagate fused: x > 0 ? x : 0
+        a.x = a.x > 0.0f ? a.x : 0.0f; a.y = a.y > 0.0f ? a.y : 0.0f;
+        a.z = a.z > 0.0f ? a.z : 0.0f; a.w = a.w > 0.0f ? a.w : 0.0f;
+      }
       if (vec_ok) {
         *reinterpret_cast<float4 *>(orow) = a;
       } else {
@@ -627,6 +631,7 @@ struct DenseProb {
   float *workspace;        // [splits][M][N] partials
   float *aux;              // EPI_SGD: prev_grad, same shape / pitch as out
   SgdCoef sgd;
+  int relu;                // EPI_STORE: max(., 0) after the bias
 
   __device__ __forceinline__ void kb_range(int z, int &b, int &e) const {
     const int total = (K + BK - 1) / BK;
@@ -662,7 +667,7 @@ struct DenseProb {
       store_rows<EPI_STORE, kRows>(stage, tid, m0, n0, M, N, workspace + (size_t)z * M * N, N, nullptr, nullptr,
                                    sgd, IdentityRow());
     else
-      store_rows<kEpi, kRows>(stage, tid, m0, n0, M, N, out, ldo, bias_n, aux, sgd, IdentityRow());
+      store_rows<kEpi, kRows>(stage, tid, m0, n0, M, N, out, ldo, bias_n, aux, sgd, IdentityRow(), relu != 0);
   }
 };
 
@@ -683,7 +688,7 @@ template <int kEpi, class RowMap>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, float *__restrict__ out, int ldo,
                      const float *__restrict__ bias_n, float *__restrict__ aux, SgdCoef sgd, RowMap row_of,
-                     ColSumTail tail, unsigned main_blocks) {
+                     ColSumTail tail, unsigned main_blocks, int relu) {
   kcnn::pdl_prologue();
   if (blockIdx.x >= main_blocks) {
     const int c = (int)(blockIdx.x - main_blocks) * blockDim.x + threadIdx.x;
@@ -716,6 +721,10 @@ splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, flo
   } else {
     if (bias_n) {
       s.x += __ldg(bias_n + n); s.y += __ldg(bias_n + n + 1); s.z += __ldg(bias_n + n + 2); s.w += __ldg(bias_n + n + 3);
+    }
+    if (relu) {
+      s.x = s.x > 0.0f ? s.x : 0.0f; s.y = s.y > 0.0f ? s.y : 0.0f;
+      s.z = s.z > 0.0f ? s.z : 0.0f; s.w = s.w > 0.0f ? s.w : 0.0f;
     }
     *reinterpret_cast<float4 *>(out + off) = s;
   }
@@ -785,6 +794,7 @@ struct Epilogue {
   const float *bias_n = nullptr;
   float *aux = nullptr;          // EPI_SGD: prev_grad
   SgdCoef sgd = {0.f, 0.f, 0.f};
+  int relu = 0;                  // EPI_STORE: rectify after the bias
 };
 
 inline int pick_splits(long long tiles, int num_kb) {
@@ -878,6 +888,7 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
   auto fill = [&](auto &p) {
     p.M = M; p.N = N; p.K = K; p.kb_per_split = per;
     p.out = out; p.ldo = ldo; p.bias_n = epi.bias_n; p.workspace = ws; p.aux = epi.aux; p.sgd = epi.sgd;
+    p.relu = epi.relu;
   };
   if (splits > 1) {
     DenseProb<kAMn, kBMn, EPI_PARTIAL> p; fill(p);
@@ -885,10 +896,11 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
     const unsigned blocks = ceil_div_u(((long long)M * N) >> 2, 256);
     if (epi.mode == EPI_SGD)
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
-                  nullptr, epi.aux, epi.sgd, IdentityRow(), ColSumTail{nullptr, 0, 0, nullptr, 0.f, 0}, blocks);
+                  nullptr, epi.aux, epi.sgd, IdentityRow(), ColSumTail{nullptr, 0, 0, nullptr, 0.f, 0}, blocks, 0);
     else
       KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
-                  epi.bias_n, nullptr, epi.sgd, IdentityRow(), ColSumTail{nullptr, 0, 0, nullptr, 0.f, 0}, blocks);
+                  epi.bias_n, nullptr, epi.sgd, IdentityRow(), ColSumTail{nullptr, 0, 0, nullptr, 0.f, 0}, blocks,
+                  epi.relu);
   } else if (epi.mode == EPI_SGD) {
     DenseProb<kAMn, kBMn, EPI_SGD> p; fill(p);
     launch_prob(st, ma, mb, p, grid, per, pair);

@@ -261,29 +261,43 @@ void cudaF_conv2d_fprop(cudaStream_t st, int math, const float *in, MatrixDim id
                         const float *kernel, MatrixDim kd, const float *bias, float *out,
                         MatrixDim od, int H, int W, int C, int ph, int pw, int KH, int KW, int G,
                         int concat) {
-  (void)cudaF_conv2d_fprop_staged(st, math, in, id, kernel, kd, bias, out, od, H, W, C, ph, pw, KH, KW, G,
-                                  concat, nullptr);
+  (void)cudaF_conv2d_fprop_act(st, math, in, id, kernel, kd, bias, out, od, H, W, C, ph, pw, KH, KW, G,
+                               concat, nullptr, KCNN_ACT_NONE);
 }
 
 int cudaF_conv2d_fprop_staged(cudaStream_t st, int math, const float *in, MatrixDim id,
                                const float *kernel, MatrixDim kd, const float *bias, float *out,
                                MatrixDim od, int H, int W, int C, int ph, int pw, int KH, int KW, int G,
                                int concat, float *staging) {
+  return cudaF_conv2d_fprop_act(st, math, in, id, kernel, kd, bias, out, od, H, W, C, ph, pw, KH, KW, G, concat,
+                                staging, KCNN_ACT_NONE);
+}
+
+int cudaF_conv2d_fprop_act(cudaStream_t st, int math, const float *in, MatrixDim id,
+                            const float *kernel, MatrixDim kd, const float *bias, float *out,
+                            MatrixDim od, int H, int W, int C, int ph, int pw, int KH, int KW, int G,
+                            int concat, float *staging, int act) {
   ConvGeom q = conv_geom(id.rows, H, W, C, ph, pw, KH, KW, G);
   if (q.N == 0 || q.P <= 0 || G == 0) return 0;
   check_int32(id, "conv input"); check_int32(od, "conv output"); check_int32(kd, "conv kernel");
   const int M = q.N * q.P, K = q.ks * C;
+  const bool relu = act == KCNN_ACT_RELU;
   if (math == KCNN_MATH_TF32_TC && concat && H == 1 && KH == 1 && ph == 0) {
     tma::ConvShape cs = {q.N, W, C, pw, KW, G, q.OW};
-    if (tma::conv_fprop(st, cs, in, id.stride, kernel, kd.stride, bias, out, od.stride, staging))
+    if (tma::conv_fprop(st, cs, in, id.stride, kernel, kd.stride, bias, out, od.stride, staging, relu))
       return staging != nullptr ? 1 : 0;
   }
   // (any other path does not fill `staging`: the caller must only trust it when
   //  kcnn_conv2d_staging_floats() was non-zero AND the math mode is the tensor-core one.)
   if (math == KCNN_MATH_TF32_TC && concat && KH == H && H > 1 && ph == 0 && pw == 0) {
     tma::ConvFullShape fs = {q.N, H, W, C, KW, G, q.OW};
-    if (tma::conv_full_fprop(st, fs, in, id.stride, kernel, kd.stride, bias, out, od.stride)) return 0;
+    if (tma::conv_full_fprop(st, fs, in, id.stride, kernel, kd.stride, bias, out, od.stride, relu)) return 0;
   }
+  // the generic kernels below have no activation in their epilogue: one in-place pass after them
+  struct ReluAfter {
+    cudaStream_t st; float *out; MatrixDim od; bool on;
+    ~ReluAfter() { if (on) cudaF_relu_fprop(st, out, od, out, od); }
+  } relu_after = {st, out, od, relu};
   // A(m = (n, ow, oh), k = (c, kw, kh)) = Xpad[n, c, ow + kw, oh + kh]
   Op33 a = make_op(in,
       make_dec3(q.N, q.OW, q.OH, id.stride, H, 1, -pw * H - ph, 1, 1, -pw, -ph),
@@ -484,12 +498,17 @@ void cudaF_sum_rows_per_map(cudaStream_t st, const float *m, MatrixDim md, int i
 
 void cudaF_affine_fprop(cudaStream_t st, int math, const float *in, MatrixDim id, const float *w,
                         MatrixDim wd, const float *bias, float *out, MatrixDim od) {
+  cudaF_affine_fprop_act(st, math, in, id, w, wd, bias, out, od, KCNN_ACT_NONE);
+}
+
+void cudaF_affine_fprop_act(cudaStream_t st, int math, const float *in, MatrixDim id, const float *w,
+                            MatrixDim wd, const float *bias, float *out, MatrixDim od, int act) {
   const int M = id.rows, N = wd.rows, K = wd.cols;
   if (M == 0 || N == 0) return;
   check_int32(id, "affine input"); check_int32(od, "affine output"); check_int32(wd, "affine weights");
   // out = 1 bias^T + in W^T : A(m, k) = in[m, k], B(k, n) = W[n, k]
   if (math == KCNN_MATH_TF32_TC && tma::enabled()) {
-    tma::Epilogue epi; epi.bias_n = bias;
+    tma::Epilogue epi; epi.bias_n = bias; epi.relu = act == KCNN_ACT_RELU ? 1 : 0;
     if (tma::gemm<false, false>(st, tma::Matrix{in, M, K, id.stride}, tma::Matrix{w, N, K, wd.stride}, M, N, K,
                                 out, od.stride, epi, true))
       return;
@@ -498,6 +517,7 @@ void cudaF_affine_fprop(cudaStream_t st, int math, const float *in, MatrixDim id
   Op33 b = make_op(w, make_linear(N, wd.stride), make_linear(K, 1), 1, 1);
   Out33 o = make_out(out, make_linear(M, od.stride), make_linear(N, 1), bias);
   launch_gemm<true, true, true>(st, math, a, b, o, M, N, K, false, nullptr);
+  if (act == KCNN_ACT_RELU) cudaF_relu_fprop(st, out, od, out, od);      // generic kernels: separate pass
 }
 
 void cudaF_affine_dgrad(cudaStream_t st, int math, const float *out_deriv, MatrixDim odd,

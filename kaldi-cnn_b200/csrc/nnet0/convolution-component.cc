@@ -197,6 +197,20 @@ std::string ConvolutionComponent::Info() const {
 void ConvolutionComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &,
                                      const CuMatrixBase<BaseFloat> &in,
                                      CuMatrixBase<BaseFloat> *out) const {
+  PropagateAct(in_info, in, out, KCNN_ACT_NONE);
+}
+
+// Fusion hook: the ReLU that follows every convolution of egs/exp/nnet/nnet.config applied in
+// the GEMM epilogue (one launch and one pass over the activation less per layer).
+bool ConvolutionComponent::PropagateRelu(const ChunkInfo &in_info, const ChunkInfo &,
+                                         const CuMatrixBase<BaseFloat> &in,
+                                         CuMatrixBase<BaseFloat> *out) const {
+  PropagateAct(in_info, in, out, KCNN_ACT_RELU);
+  return true;
+}
+
+void ConvolutionComponent::PropagateAct(const ChunkInfo &in_info, const CuMatrixBase<BaseFloat> &in,
+                                        CuMatrixBase<BaseFloat> *out, int act) const {
   KALDI_ASSERT(in.NumCols() == InputDim() && out != NULL);
   KALDI_ASSERT(in.NumRows() == in_info.NumChunks() || in_pad_height_ + in_pad_width_ == 0);
   KALDI_ASSERT(out->NumRows() == in.NumRows() && out->NumCols() == OutputDim());
@@ -216,10 +230,10 @@ void ConvolutionComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &
       staging = staged_in_.Data();
     }
   }
-  int staged = cudaF_conv2d_fprop_staged(Str(), Math(), in.Data(), in.Dim(), linear_params_.Data(),
-                                         linear_params_.Dim(), bias_params_.Data(), out->Data(),
-                                         out->Dim(), in_height_, in_width_, in_channel_, in_pad_height_,
-                                         in_pad_width_, kernel_height_, kernel_width_, group_, 1, staging);
+  int staged = cudaF_conv2d_fprop_act(Str(), Math(), in.Data(), in.Dim(), linear_params_.Data(),
+                                      linear_params_.Dim(), bias_params_.Data(), out->Data(),
+                                      out->Dim(), in_height_, in_width_, in_channel_, in_pad_height_,
+                                      in_pad_width_, kernel_height_, kernel_width_, group_, 1, staging, act);
   if (staged) {
     staged_src_ = in.Data(); staged_rows_ = in.NumRows(); staged_stride_ = in.Stride();
   }

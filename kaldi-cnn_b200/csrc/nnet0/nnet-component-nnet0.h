@@ -78,6 +78,8 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   using Component::Propagate;   // to avoid name hiding
   virtual void Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
                          const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) const;
+  virtual bool PropagateRelu(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                             const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) const;
   virtual void Scale(BaseFloat scale);
   virtual void Add(BaseFloat alpha, const UpdatableComponent &other);
   virtual void Backprop(const ChunkInfo &in_info, const ChunkInfo &out_info,
@@ -132,6 +134,8 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   void ComputeGradient(const CuMatrixBase<BaseFloat> &in_value,
                        const CuMatrixBase<BaseFloat> &out_deriv);
   void EnsureGradBuffers();
+  void PropagateAct(const ChunkInfo &in_info, const CuMatrixBase<BaseFloat> &in,
+                    CuMatrixBase<BaseFloat> *out, int act) const;
 
   const ConvolutionComponent &operator=(const ConvolutionComponent &other);   // Disallow.
 

@@ -733,18 +733,31 @@ void AffineComponent::InitFromString(std::string args) {
 
 // out = 1 bias^T + in W^T in ONE launch: the bias row copy (CopyRowsFromVec) is the
 // GEMM epilogue.  reference :1216-1228.
-void AffineComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
-                                const CuMatrixBase<BaseFloat> &in,
-                                CuMatrixBase<BaseFloat> *out) const {
+void AffineComponent::PropagateAct(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                                   const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out,
+                                   int act) const {
   in_info.CheckSize(in);
   out_info.CheckSize(*out);
   KALDI_ASSERT(in_info.NumChunks() == out_info.NumChunks());
   KALDI_ASSERT(in.NumCols() == InputDim() && out->NumCols() == OutputDim());
   CuDevice::Instantiate().RequireEnabled("AffineComponent::Propagate");
-  cudaF_affine_fprop(Str(), CuDevice::Instantiate().MathMode(), in.Data(), in.Dim(),
-                     linear_params_.Data(), linear_params_.Dim(), bias_params_.Data(), out->Data(),
-                     out->Dim());
+  cudaF_affine_fprop_act(Str(), CuDevice::Instantiate().MathMode(), in.Data(), in.Dim(),
+                         linear_params_.Data(), linear_params_.Dim(), bias_params_.Data(), out->Data(),
+                         out->Dim(), act);
   CU_SAFE_CALL(cudaGetLastError());
+}
+
+void AffineComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                                const CuMatrixBase<BaseFloat> &in,
+                                CuMatrixBase<BaseFloat> *out) const {
+  PropagateAct(in_info, out_info, in, out, KCNN_ACT_NONE);
+}
+
+bool AffineComponent::PropagateRelu(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                                    const CuMatrixBase<BaseFloat> &in,
+                                    CuMatrixBase<BaseFloat> *out) const {
+  PropagateAct(in_info, out_info, in, out, KCNN_ACT_RELU);
+  return true;
 }
 
 void AffineComponent::EnsureGradBuffers() {

@@ -97,6 +97,17 @@ class Component {
   virtual bool BackpropNeedsInput() const { return true; }
   virtual bool BackpropNeedsOutput() const { return true; }
 
+  /// B200 extension (fusion hook): this component's Propagate followed by
+  /// RectifiedLinearComponent::Propagate as ONE launch -- `out` receives max(Propagate(in), 0),
+  /// the pre-activation is never stored.  Returns false when the component has no such path;
+  /// the caller then runs the two components one after the other.  Only valid for a caller
+  /// that will not look at the pre-activation again (this component's BackpropNeedsOutput()
+  /// is false and the ReLU's BackpropNeedsInput() is false: NnetMinibatchUpdater checks both).
+  virtual bool PropagateRelu(const ChunkInfo & /*in_info*/, const ChunkInfo & /*out_info*/,
+                             const CuMatrixBase<BaseFloat> & /*in*/, CuMatrixBase<BaseFloat> * /*out*/) const {
+    return false;
+  }
+
   /// B200 extension: a hash of everything a captured CUDA graph of this component's
   /// Propagate / Backprop bakes in besides the activation buffers -- parameter addresses,
   /// learning rate, momentum, ... (NnetMinibatchUpdater::TrainStep re-captures its graph
@@ -303,6 +314,8 @@ class AffineComponent : public UpdatableComponent {
   using Component::Propagate;
   virtual void Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
                          const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) const;
+  virtual bool PropagateRelu(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                             const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) const;
   virtual void Scale(BaseFloat scale);
   virtual void Add(BaseFloat alpha, const UpdatableComponent &other);
   virtual void Backprop(const ChunkInfo &in_info, const ChunkInfo &out_info,
@@ -348,6 +361,8 @@ class AffineComponent : public UpdatableComponent {
   void ComputeGradient(const CuMatrixBase<BaseFloat> &in_value,
                        const CuMatrixBase<BaseFloat> &out_deriv);
   void EnsureGradBuffers();
+  void PropagateAct(const ChunkInfo &in_info, const ChunkInfo &out_info, const CuMatrixBase<BaseFloat> &in,
+                    CuMatrixBase<BaseFloat> *out, int act) const;
 
   const AffineComponent &operator=(const AffineComponent &other);  // Disallow.
   CuMatrix<BaseFloat> linear_params_;

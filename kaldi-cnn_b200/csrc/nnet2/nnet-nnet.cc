@@ -103,10 +103,12 @@ struct NnetMinibatchUpdater::GraphState {
 };
 
 NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
-    : graph_(new GraphState), seen_key_(0), last_replayed_(false),
+    : graph_(new GraphState), seen_key_(0), last_replayed_(false), fuse_(true),
       nnet_(nnet), num_rows_(0), labels_(NULL), objf_dev_(NULL) {
   objf_dev_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double)));
   CU_SAFE_CALL(cudaMemsetAsync(objf_dev_, 0, sizeof(double), Str()));
+  const char *fe = getenv("KCNN_NNET_FUSE");
+  if (fe && fe[0] == '0') fuse_ = false;
   SetInputPersists(true);    // forward_[c] is ours and untouched between Forward and Backward
 }
 
@@ -148,9 +150,21 @@ void NnetMinibatchUpdater::ForwardRange(const CuMatrixBase<BaseFloat> &feats, in
   if (first == 0)
     forward_[0].Borrow(const_cast<BaseFloat *>(feats.Data()), feats.NumRows(), feats.NumCols(),
                        feats.Stride());
-  for (int32 c = first; c <= last; c++)
-    nnet_->GetComponent(c).Propagate(info_[c], info_[c + 1], forward_[c],
-                                     static_cast<CuMatrixBase<BaseFloat> *>(&forward_[c + 1]));
+  for (int32 c = first; c <= last; c++) {
+    const Component &comp = nnet_->GetComponent(c);
+    if (fuse_ && c + 1 <= last && !comp.BackpropNeedsOutput()) {
+      const RectifiedLinearComponent *relu =
+          dynamic_cast<const RectifiedLinearComponent *>(&nnet_->GetComponent(c + 1));
+      if (relu != NULL && !relu->BackpropNeedsInput() &&
+          comp.PropagateRelu(info_[c], info_[c + 2], forward_[c],
+                             static_cast<CuMatrixBase<BaseFloat> *>(&forward_[c + 2]))) {
+        c++;                       // forward_[c + 1] (the pre-activation) is not needed by anyone
+        continue;
+      }
+    }
+    comp.Propagate(info_[c], info_[c + 1], forward_[c],
+                   static_cast<CuMatrixBase<BaseFloat> *>(&forward_[c + 1]));
+  }
 }
 
 void NnetMinibatchUpdater::ComputeObjfAndDeriv(const int32 *labels_dev) {
@@ -199,6 +213,7 @@ uint64 NnetMinibatchUpdater::StepKey(const CuMatrixBase<BaseFloat> &feats, const
   h = Component::HashValue(labels_dev, h);
   h = Component::HashValue(Str(), h);
   h = Component::HashValue(CuDevice::Instantiate().MathMode(), h);
+  h = Component::HashValue(fuse_, h);
   for (int32 c = 0; c < nnet_->NumComponents(); c++)
     h = Component::HashValue(nnet_->GetComponent(c).StepSignature(), h);
   return h | 1;      // never 0

@@ -69,6 +69,11 @@ class NnetMinibatchUpdater {
   /// stream (the legacy default stream cannot be captured): otherwise, or with
   /// KCNN_NNET_GRAPH=0, every step runs eagerly.
   void TrainStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev);
+  /// Fusion of adjacent components inside Forward (default on; KCNN_NNET_FUSE=0 turns it off):
+  /// [Convolution | FullyConnected | Affine] + RectifiedLinear run as one launch through
+  /// Component::PropagateRelu.  The skipped pre-activation Activation(c + 1) is then NOT filled.
+  void SetFusion(bool on) { fuse_ = on; }
+  bool Fusion() const { return fuse_; }
   /// True when the last TrainStep was a graph replay.
   bool LastStepReplayed() const { return last_replayed_; }
   /// ApplyGradient(total_rows) on every updatable component (deferred-update mode).
@@ -95,6 +100,7 @@ class NnetMinibatchUpdater {
   GraphState *graph_;
   uint64 seen_key_;                  // key of the last eager step (capture needs one warm step)
   bool last_replayed_;
+  bool fuse_;
   Nnet *nnet_;
   int32 num_rows_;
   std::vector<CuMatrix<BaseFloat> > forward_;   // [0] = copy-free view of the input

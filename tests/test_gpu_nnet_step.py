@@ -102,3 +102,35 @@ def test_legacy_default_stream_runs_eagerly():
     lab = rng.integers(0, net.output_dim, 32).astype(np.int32)
     vals = [net.train_minibatch_host(x, lab) for _ in range(4)]
     assert all(np.isfinite(v) for v in vals) and vals[3] > vals[0]        # the objective improves on a fixed batch
+
+
+@pytest.mark.parametrize("math", [0, 1], ids=["fp32", "tf32"])
+def test_fused_relu_epilogue_equals_separate_relu_component(math):
+    """[Convolution | FullyConnected] + RectifiedLinear as ONE launch (Component::PropagateRelu:
+    the ReLU of upstream nnet2/nnet-component.cc:799-811 applied in the GEMM epilogue) gives
+    bit-identical activations, parameters and statistics to the two components run separately."""
+    kc.set_math_mode(math)
+    N = 64
+    nets = []
+    for fuse in (True, False):
+        kc.set_rand_seed(21)
+        net = kc.Nnet.from_config(CFG)
+        net.set_fusion(fuse)
+        nets.append(net)
+    a, b = nets
+    rng = np.random.default_rng(8)
+    kc.use_current_stream()
+    for step in range(3):
+        x = torch.from_numpy(rng.standard_normal((N, a.input_dim)).astype(np.float32)).cuda()
+        lab = torch.from_numpy(rng.integers(0, a.output_dim, N).astype(np.int32)).cuda()
+        for net in nets:
+            if step == 0:
+                kc.set_rand_seed(5)
+            net.train_step(x, lab)
+        assert a.objf_and_reset() == b.objf_and_reset()
+        for i in (2, 5, 10):          # ReLU outputs after conv1, conv2, fc1
+            assert torch.equal(a.activation(i), b.activation(i)), i
+    for pa, pb in zip(_params(a), _params(b)):
+        assert torch.equal(pa, pb)
+    assert _counts(a) == _counts(b)
+    kc.set_math_mode(0)
