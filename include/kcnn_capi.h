@@ -184,6 +184,17 @@ int kcnn_nnet_apply_gradients(kcnn_nnet *n, int total_rows);
  * backward + update, and returns the minibatch objective in *objf (synchronous). */
 int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const int *labels_host,
                                    int rows, double *objf);
+/* Pipelined form of the call above for a host that streams minibatches: the caller's buffers
+ * are copied to pinned staging memory (they may be reused as soon as the call returns), the
+ * host-to-device copy of this batch runs on a copy stream while the PREVIOUS batch is still
+ * computing, the step is enqueued behind it, and the call returns without waiting for the
+ * GPU.  The objective accumulates on the device and is also copied back to the host after
+ * every step: kcnn_nnet_running_objf() returns the accumulated value as of the newest step
+ * that has completed (never blocks); kcnn_nnet_objf_and_reset() waits for everything enqueued
+ * and returns the total, as in Kaldi's periodic objective report. */
+int kcnn_nnet_train_minibatch_host_async(kcnn_nnet *n, const float *feats_host, const int *labels_host,
+                                         int rows);
+double kcnn_nnet_running_objf(kcnn_nnet *n);
 /* The same step on DEVICE buffers, asynchronous on the compute stream (read the objective
  * with kcnn_nnet_objf_and_reset).  Both calls go through NnetMinibatchUpdater::TrainStep: on a
  * non-default compute stream the ~85 launches of a step are recorded into a CUDA graph on the

@@ -75,6 +75,8 @@ PROTOS = {
     "kcnn_nnet_apply_gradients": ([H, I], c_int),
     "kcnn_nnet_train_minibatch_host": ([H, P, P, I, ctypes.POINTER(ctypes.c_double)], c_int),
     "kcnn_nnet_train_step": ([H, P, I, I, P], c_int),
+    "kcnn_nnet_train_minibatch_host_async": ([H, P, P, I], c_int),
+    "kcnn_nnet_running_objf": ([H], ctypes.c_double),
     "kcnn_nnet_last_step_replayed": ([H], c_int),
     "kcnn_nnet_set_fusion": ([H, I], c_int),
 }

@@ -279,6 +279,18 @@ class Nnet:
             feats_np.shape[0], ctypes.byref(objf)))
         return objf.value
 
+    def train_minibatch_host_async(self, feats_np, labels_np):
+        """Pipelined host step: stages the buffers, enqueues copy + step, returns without waiting.
+        Read the objective with objf_and_reset() (waits) or running_objf (does not)."""
+        use_current_stream()
+        _check(_lib().kcnn_nnet_train_minibatch_host_async(
+            self.h, feats_np.ctypes.data_as(ctypes.c_void_p), labels_np.ctypes.data_as(ctypes.c_void_p),
+            feats_np.shape[0]))
+
+    @property
+    def running_objf(self):
+        return _lib().kcnn_nnet_running_objf(self.h)
+
     def train_step_graph(self, feats, labels):
         """The same step through NnetMinibatchUpdater::TrainStep: recorded into a CUDA graph by the
         library on the second call with the same buffers, replayed afterwards."""

@@ -3,6 +3,7 @@
 // assertions / KALDI_ERR raised underneath are caught and reported through
 // kcnn_last_error() so a foreign host is not aborted.
 
+#include <string.h>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -45,8 +46,52 @@ struct NnetHandle {
   CuMatrix<BaseFloat> host_feats;      // staging for kcnn_nnet_train_minibatch_host
   int32 *host_labels_dev;
   int32 host_labels_rows;
+  // kcnn_nnet_train_minibatch_host_async: two slots of (pinned host, device) buffers, a copy
+  // stream, and events -- batch k+1 is staged and copied while batch k computes.
+  struct Pipe {
+    float *pin_feats[2]; int32 *pin_labels[2]; double *pin_objf;
+    CuMatrix<BaseFloat> dev_feats[2]; int32 *dev_labels[2];
+    cudaStream_t copy_stream; cudaEvent_t copied[2], done[2];
+    int rows, dim; unsigned long long step;
+    Pipe() : pin_objf(NULL), copy_stream(NULL), rows(0), dim(0), step(0) {
+      for (int i = 0; i < 2; i++) { pin_feats[i] = NULL; pin_labels[i] = NULL; dev_labels[i] = NULL; copied[i] = NULL; done[i] = NULL; }
+    }
+    void Release() {
+      if (copy_stream) cudaStreamSynchronize(copy_stream);
+      for (int i = 0; i < 2; i++) {
+        if (pin_feats[i]) cudaFreeHost(pin_feats[i]);
+        if (pin_labels[i]) cudaFreeHost(pin_labels[i]);
+        if (dev_labels[i]) CuDevice::Instantiate().Free(dev_labels[i]);
+        if (copied[i]) cudaEventDestroy(copied[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+        pin_feats[i] = NULL; pin_labels[i] = NULL; dev_labels[i] = NULL; copied[i] = NULL; done[i] = NULL;
+        dev_feats[i].Resize(0, 0);
+      }
+      if (pin_objf) cudaFreeHost(pin_objf);
+      if (copy_stream) cudaStreamDestroy(copy_stream);
+      pin_objf = NULL; copy_stream = NULL; rows = 0; dim = 0;
+    }
+    void Ensure(int r, int d) {
+      if (r == rows && d == dim && copy_stream != NULL) return;
+      Release();
+      CU_SAFE_CALL(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_objf), 2 * sizeof(double)));
+      pin_objf[0] = pin_objf[1] = 0.0;
+      for (int i = 0; i < 2; i++) {
+        CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_feats[i]), sizeof(float) * (size_t)r * d));
+        CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_labels[i]), sizeof(int32) * (size_t)r));
+        dev_feats[i].Resize(r, d, kUndefined);
+        dev_labels[i] = static_cast<int32 *>(CuDevice::Instantiate().Malloc(sizeof(int32) * (size_t)r));
+        CU_SAFE_CALL(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        CU_SAFE_CALL(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+      }
+      rows = r; dim = d;
+    }
+  } pipe;
   NnetHandle() : updater(NULL), host_labels_dev(NULL), host_labels_rows(0) {}
   ~NnetHandle() {
+    if (CuDevice::Instantiate().Enabled()) cudaStreamSynchronize(CuDevice::Instantiate().Stream());
+    pipe.Release();
     delete updater;
     if (host_labels_dev) CuDevice::Instantiate().Free(host_labels_dev);
   }
@@ -533,6 +578,50 @@ int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const 
   if (objf) *objf = v;
   return 0;
   KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_train_minibatch_host_async(kcnn_nnet *n, const float *feats_host, const int *labels_host,
+                                         int rows) {
+  KCNN_TRY
+  NnetHandle *h = N(n);
+  const int dim = h->nnet.InputDim();
+  cudaStream_t st = CuDevice::Instantiate().Stream();
+  NnetHandle::Pipe &p = h->pipe;
+  p.Ensure(rows, dim);
+  const int s = (int)(p.step & 1ull);
+  // the pinned slot is free once ITS previous copy (two calls ago) has run; then the caller's
+  // buffers are staged and belong to the caller again as soon as this call returns
+  CU_SAFE_CALL(cudaEventSynchronize(p.copied[s]));
+  memcpy(p.pin_feats[s], feats_host, sizeof(float) * (size_t)rows * dim);
+  memcpy(p.pin_labels[s], labels_host, sizeof(int32) * (size_t)rows);
+  // the device slot is free once the step that read it (two calls ago) has finished
+  CU_SAFE_CALL(cudaStreamWaitEvent(p.copy_stream, p.done[s], 0));
+  CU_SAFE_CALL(cudaMemcpy2DAsync(p.dev_feats[s].Data(), sizeof(float) * p.dev_feats[s].Stride(), p.pin_feats[s],
+                                 sizeof(float) * dim, sizeof(float) * dim, rows, cudaMemcpyHostToDevice,
+                                 p.copy_stream));
+  CU_SAFE_CALL(cudaMemcpyAsync(p.dev_labels[s], p.pin_labels[s], sizeof(int32) * rows, cudaMemcpyHostToDevice,
+                               p.copy_stream));
+  CU_SAFE_CALL(cudaEventRecord(p.copied[s], p.copy_stream));
+  CU_SAFE_CALL(cudaStreamWaitEvent(st, p.copied[s], 0));
+  h->U().TrainStep(p.dev_feats[s], p.dev_labels[s]);
+  // the running objective comes back to the host after every step, without a synchronisation
+  CU_SAFE_CALL(cudaMemcpyAsync(p.pin_objf + s, h->U().ObjfDevice(), sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU_SAFE_CALL(cudaEventRecord(p.done[s], st));
+  p.step++;
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+double kcnn_nnet_running_objf(kcnn_nnet *n) {
+  NnetHandle::Pipe &p = N(n)->pipe;
+  if (p.copy_stream == NULL || p.step == 0) return 0.0;
+  // newest step whose objective has already landed in host memory (no waiting)
+  for (unsigned long long back = 1; back <= 2 && back <= p.step; back++) {
+    const int s = (int)((p.step - back) & 1ull);
+    if (cudaEventQuery(p.done[s]) == cudaSuccess) return p.pin_objf[s];
+  }
+  cudaGetLastError();
+  return 0.0;
 }
 
 int kcnn_nnet_train_step(kcnn_nnet *n, const float *feats, int rows, int stride, const int *labels) {

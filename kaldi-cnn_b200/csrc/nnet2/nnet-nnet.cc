@@ -95,15 +95,19 @@ std::string Nnet::Info() const {
 // ------------------------------------------------------- NnetMinibatchUpdater --
 
 struct NnetMinibatchUpdater::GraphState {
-  cudaGraphExec_t exec;
-  uint64 key;
-  std::vector<double> count_delta;      // NonlinearComponent::count_ added by one step (host state)
-  bool failed;                          // a capture was refused: stay eager for this key
-  GraphState() : exec(NULL), key(0), failed(false) {}
+  struct Entry {
+    cudaGraphExec_t exec;                 // NULL: recording was refused, stay eager for this key
+    uint64 key;
+    std::vector<double> count_delta;      // NonlinearComponent::count_ added by one step (host state)
+  };
+  std::vector<Entry> entries;             // a few (input buffer, labels) pairs: double-buffered callers
+  std::vector<uint64> seen;               // keys that have run eagerly once (recording needs a warm step)
+  uint64 config;                          // signature of everything but the buffers
+  GraphState() : config(0) {}
 };
 
 NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
-    : graph_(new GraphState), seen_key_(0), last_replayed_(false), fuse_(true),
+    : graph_(new GraphState), last_replayed_(false), fuse_(true),
       nnet_(nnet), num_rows_(0), labels_(NULL), objf_dev_(NULL) {
   objf_dev_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double)));
   CU_SAFE_CALL(cudaMemsetAsync(objf_dev_, 0, sizeof(double), Str()));
@@ -199,23 +203,28 @@ static bool GraphsEnabled() {
 }
 
 void NnetMinibatchUpdater::DropGraph() {
-  if (graph_->exec) cudaGraphExecDestroy(graph_->exec);
-  graph_->exec = NULL;
-  graph_->key = 0;
-  graph_->failed = false;
+  for (size_t i = 0; i < graph_->entries.size(); i++)
+    if (graph_->entries[i].exec) cudaGraphExecDestroy(graph_->entries[i].exec);
+  graph_->entries.clear();
+  graph_->seen.clear();
 }
 
-uint64 NnetMinibatchUpdater::StepKey(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) const {
-  uint64 h = Component::HashValue(feats.Data(), 17);
-  h = Component::HashValue(feats.NumRows(), h);
-  h = Component::HashValue(feats.NumCols(), h);
-  h = Component::HashValue(feats.Stride(), h);
-  h = Component::HashValue(labels_dev, h);
-  h = Component::HashValue(Str(), h);
+// Everything a recorded step bakes in besides the input / label buffers.
+uint64 NnetMinibatchUpdater::ConfigKey() const {
+  uint64 h = Component::HashValue(Str(), 17);
   h = Component::HashValue(CuDevice::Instantiate().MathMode(), h);
   h = Component::HashValue(fuse_, h);
   for (int32 c = 0; c < nnet_->NumComponents(); c++)
     h = Component::HashValue(nnet_->GetComponent(c).StepSignature(), h);
+  return h | 1;
+}
+
+uint64 NnetMinibatchUpdater::StepKey(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) const {
+  uint64 h = Component::HashValue(feats.Data(), 19);
+  h = Component::HashValue(feats.NumRows(), h);
+  h = Component::HashValue(feats.NumCols(), h);
+  h = Component::HashValue(feats.Stride(), h);
+  h = Component::HashValue(labels_dev, h);
   return h | 1;      // never 0
 }
 
@@ -233,21 +242,35 @@ void NnetMinibatchUpdater::TrainStep(const CuMatrixBase<BaseFloat> &feats, const
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cs);
   if (cs != cudaStreamCaptureStatusNone) { EagerStep(feats, labels_dev); return; }   // caller's own capture
+  const uint64 config = ConfigKey();
+  if (config != graph_->config) {       // learning rate, parameter storage, stream, ... changed
+    DropGraph();
+    graph_->config = config;
+  }
   const uint64 key = StepKey(feats, labels_dev);
   const int32 L = nnet_->NumComponents();
-  if (graph_->exec != NULL && graph_->key == key) {
-    CU_SAFE_CALL(cudaGraphLaunch(graph_->exec, st));
+  for (size_t i = 0; i < graph_->entries.size(); i++) {
+    GraphState::Entry &e = graph_->entries[i];
+    if (e.key != key) continue;
+    if (e.exec == NULL) { EagerStep(feats, labels_dev); return; }
+    CU_SAFE_CALL(cudaGraphLaunch(e.exec, st));
     for (int32 c = 0; c < L; c++) {
       NonlinearComponent *nl = dynamic_cast<NonlinearComponent *>(&nnet_->GetComponent(c));
-      if (nl && graph_->count_delta[c] != 0.0) nl->AddToCount(graph_->count_delta[c]);
+      if (nl && e.count_delta[c] != 0.0) nl->AddToCount(e.count_delta[c]);
     }
     last_replayed_ = true;
     return;
   }
-  if (graph_->key != key) DropGraph();
-  if (seen_key_ != key || graph_->failed) {          // first step of this configuration: eager
+  bool seen = false;
+  for (size_t i = 0; i < graph_->seen.size(); i++) seen = seen || graph_->seen[i] == key;
+  if (!seen) {                           // first step with these buffers: eager (sizes every scratch buffer)
     EagerStep(feats, labels_dev);
-    seen_key_ = key;
+    if (ConfigKey() != config) {         // the step itself allocated state (e.g. a dropout seed)
+      DropGraph();
+      graph_->config = ConfigKey();
+    }
+    if (graph_->seen.size() >= 8) graph_->seen.erase(graph_->seen.begin());
+    graph_->seen.push_back(key);
     return;
   }
   // Second step: record it.  Host-side effects of a step (the frame counts of the
@@ -268,26 +291,31 @@ void NnetMinibatchUpdater::TrainStep(const CuMatrixBase<BaseFloat> &feats, const
     if (cudaStreamEndCapture(st, &g) != cudaSuccess || g == NULL) ok = false;
   }
   cudaGraphExec_t exec = NULL;
-  if (ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) ok = false;
+  if (ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { ok = false; exec = NULL; }
   if (g) cudaGraphDestroy(g);
+  if (graph_->entries.size() >= 4) {                  // oldest out
+    if (graph_->entries[0].exec) cudaGraphExecDestroy(graph_->entries[0].exec);
+    graph_->entries.erase(graph_->entries.begin());
+  }
+  GraphState::Entry e;
+  e.exec = exec;
+  e.key = key;
+  e.count_delta.assign(L, 0.0);
   if (!ok) {
     cudaGetLastError();                               // clear the sticky capture error
     for (int32 c = 0; c < L; c++) {                   // the aborted recording did not run
       NonlinearComponent *nl = dynamic_cast<NonlinearComponent *>(&nnet_->GetComponent(c));
       if (nl) nl->AddToCount(before[c] - nl->Count());
     }
-    graph_->failed = true;
-    graph_->key = key;
+    graph_->entries.push_back(e);                     // exec == NULL: eager from now on
     EagerStep(feats, labels_dev);
     return;
   }
-  graph_->exec = exec;
-  graph_->key = key;
-  graph_->count_delta.assign(L, 0.0);
   for (int32 c = 0; c < L; c++) {
     const NonlinearComponent *nl = dynamic_cast<const NonlinearComponent *>(&nnet_->GetComponent(c));
-    if (nl) graph_->count_delta[c] = nl->Count() - before[c];
+    if (nl) e.count_delta[c] = nl->Count() - before[c];
   }
+  graph_->entries.push_back(e);
   CU_SAFE_CALL(cudaGraphLaunch(exec, st));            // the recording itself executed nothing
   last_replayed_ = true;
 }

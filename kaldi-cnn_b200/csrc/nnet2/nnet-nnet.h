@@ -96,9 +96,9 @@ class NnetMinibatchUpdater {
   void EagerStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev);
   void DropGraph();
   uint64 StepKey(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) const;
-  struct GraphState;                 // cudaGraphExec_t + the host-side effects of one step
+  uint64 ConfigKey() const;
+  struct GraphState;                 // recorded steps + the host-side effects of one step
   GraphState *graph_;
-  uint64 seen_key_;                  // key of the last eager step (capture needs one warm step)
   bool last_replayed_;
   bool fuse_;
   Nnet *nnet_;

@@ -71,7 +71,7 @@ def test_graph_replayed_steps_equal_eager_steps(math):
             hx.copy_(torch.from_numpy(x)); hl.copy_(torch.from_numpy(lab))
             if step == 0:
                 kc.set_rand_seed(77)              # DropoutComponent draws its seed at the first Propagate
-            objf_a = a.train_minibatch_host(hx.numpy(), hl.numpy())       # eager x2, record, replay, eager x2, record
+            objf_a = a.train_minibatch_host(hx.numpy(), hl.numpy())       # eager, record, replay x2, eager, record, ...
             replayed.append(a.last_step_replayed)
             xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
             if step == 0:
@@ -82,9 +82,8 @@ def test_graph_replayed_steps_equal_eager_steps(math):
         stream.synchronize()
     for pa, pb in zip(_params(a), _params(b)):
         assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-8), float((pa - pb).abs().max())
-    # the first step changes the signature (the dropout seed gets allocated), so: eager, eager,
-    # record + launch, replay; learning-rate change; eager, record + launch, replay, replay
-    assert replayed == [False, False, True, True, False, True, True, True], replayed
+    # eager, record + launch, replay, replay; learning-rate change: eager, record + launch, replay x2
+    assert replayed == [False, True, True, True, False, True, True, True], replayed
     ca, cb = _counts(a), _counts(b)
     assert ca == cb and len(ca) >= 5 and all(c == 8 * N for c in ca[:4]), (ca, cb)
     kc.set_math_mode(0)
@@ -134,3 +133,40 @@ def test_fused_relu_epilogue_equals_separate_relu_component(math):
         assert torch.equal(pa, pb)
     assert _counts(a) == _counts(b)
     kc.set_math_mode(0)
+
+
+def test_pipelined_host_steps_equal_synchronous_steps():
+    """kcnn_nnet_train_minibatch_host_async (double-buffered staging, copy stream, one recorded
+    graph per device slot) trains exactly like the synchronous call, and the caller may overwrite
+    its buffers right after each call."""
+    kc.set_math_mode(1)
+    N, steps = 64, 9
+    nets = []
+    for _ in range(2):
+        kc.set_rand_seed(31)
+        nets.append(kc.Nnet.from_config(CFG))
+    a, b = nets
+    rng = np.random.default_rng(12)
+    xs = [rng.standard_normal((N, a.input_dim)).astype(np.float32) for _ in range(steps)]
+    ls = [rng.integers(0, a.output_dim, N).astype(np.int32) for _ in range(steps)]
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        kc.use_current_stream()
+        buf_x, buf_l = np.empty_like(xs[0]), np.empty_like(ls[0])
+        kc.set_rand_seed(9)
+        for k in range(steps):
+            buf_x[...] = xs[k]; buf_l[...] = ls[k]
+            a.train_minibatch_host_async(buf_x, buf_l)
+            buf_x.fill(np.nan)                       # the staged copy must already be independent of it
+        total_a = a.objf_and_reset()
+        assert a.last_step_replayed
+        kc.set_rand_seed(9)
+        total_b = sum(b.train_minibatch_host(xs[k], ls[k]) for k in range(steps))
+        stream.synchronize()
+    assert np.isfinite(total_a) and abs(total_a - total_b) <= 1e-6 * abs(total_b), (total_a, total_b)
+    for pa, pb in zip(_params(a), _params(b)):
+        assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-8), float((pa - pb).abs().max())
+    assert _counts(a) == _counts(b)
+    assert np.isfinite(a.running_objf)
+    kc.set_math_mode(0)
+    kc.use_current_stream()
