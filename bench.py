@@ -150,9 +150,15 @@ def cpu_backend():
 
 
 def cpu_train_frames_per_sec(cfg_text, rows, steps, warmup, threads):
+    """The CPU arm: the op-for-op port of the reference's CPU path (oracle/), its GEMMs through a
+    threaded OpenBLAS as in a Kaldi BLAS build, everything else the reference's own
+    scalar loops.  Returns (frames/s, s/step, kind, threads, description of the back end)."""
     import numpy as np
     from oracle.cpu_nnet import CpuNnet
     kind, backend = cpu_backend()
+    blas = None
+    if hasattr(backend, "use_blas"):
+        blas = backend.use_blas(True)
     used = 1
     if hasattr(backend, "set_num_threads"):
         used = backend.set_num_threads(threads) or 1
@@ -167,7 +173,9 @@ def cpu_train_frames_per_sec(cfg_text, rows, steps, warmup, threads):
     for _ in range(steps):
         net.train_step(x, labels)
     dt = time.perf_counter() - t0
-    return rows * steps / dt, dt / steps, kind, used
+    how = ("GEMMs: OpenBLAS (%s, %d threads); other loops: OpenMP port of the reference's CPU branches"
+           % (os.path.basename(blas), used)) if blas else "GEMMs and loops: OpenMP C port (no BLAS found)"
+    return rows * steps / dt, dt / steps, kind, used, how
 
 
 def run_reference_arm(args):
@@ -176,8 +184,8 @@ def run_reference_arm(args):
         return
     cfg = load_config(args.workload)
     cores = os.cpu_count() or 1
-    rows = args.cpu_rows
-    fps, sec, kind, used = cpu_train_frames_per_sec(cfg, rows, args.steps, args.warmup, cores)
+    rows = args.cpu_rows or (args.batch if args.steps + args.warmup <= 64 else 128)
+    fps, sec, kind, used, how = cpu_train_frames_per_sec(cfg, rows, args.steps, args.warmup, cores)
     line = {
         "impl": "reference", "metric": "train_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -185,7 +193,8 @@ def run_reference_arm(args):
         "config": {"workload": WORKLOADS[args.workload][1], "per_gpu_batch": args.batch,
                    "cpu_sample_rows_per_step": rows},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": used, "kind": kind,
-                         "sample": "%d training steps of %d rows of the same model on the host CPU" % (args.steps, rows)},
+                         "sample": "%d training steps of %d rows of the same model on the host CPU; %s"
+                                   % (args.steps, rows, how)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -479,9 +488,11 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu:
         try:
-            fps, sec, kind, used = cpu_train_frames_per_sec(cfg, args.cpu_rows, 2, 1, os.cpu_count() or 1)
+            cpu_rows = args.cpu_rows or args.batch
+            fps, sec, kind, used, how = cpu_train_frames_per_sec(cfg, cpu_rows, 2, 1, os.cpu_count() or 1)
             cpu = {"value": fps, "unit": "frames/s", "cores": used, "kind": kind,
-                   "sample": "2 training steps of %d rows of the same model (after 1 warm-up) on the host CPU" % args.cpu_rows}
+                   "sample": "2 training steps of %d rows of the same model (after 1 warm-up) on the host CPU; %s"
+                             % (cpu_rows, how)}
         except Exception as e:
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     dominant = None
@@ -539,7 +550,10 @@ def main():
     ap.add_argument("--workload", default="c2-intermap", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=512, help="minibatch rows per GPU")
     ap.add_argument("--math", default=os.environ.get("KCNN_BENCH_MATH", "tf32"), choices=["tf32", "fp32"])
-    ap.add_argument("--cpu-rows", type=int, default=64, help="rows per step of the bounded CPU sample")
+    ap.add_argument("--cpu-rows", type=int, default=0,
+                    help="rows per step of the CPU legs; 0 = the workload's own minibatch (--batch) when the run is "
+                         "short enough (<= 64 steps incl. warm-up), else 128 (the reference's CPU minibatch, "
+                         "egs/local/nnet0/run_nnet.sh:25-27)")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")

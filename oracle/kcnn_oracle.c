@@ -15,19 +15,65 @@
 #include <omp.h>
 #endif
 
+#include <dlfcn.h>
+
 #define ORA_CAT(a, b) a##b
+
+/* Optional BLAS back end for ORA(gemm): the reference's CPU build does its GEMMs in the BLAS
+ * Kaldi links (AddMatMat -> cblas_sgemm, cnslmat/conv2D.cc:139, nnet2/nnet-component.cc:1227,
+ * 1247, nnet0/nnet-component-nnet0.cc:1141), so the CPU BASELINE legs of bench.py route them
+ * through the OpenBLAS that numpy bundles (ILP64 build, symbols scipy_cblas_?gemm64_), loaded
+ * at run time with dlopen.  Parity tests keep the plain loops (deterministic summation order). */
+typedef void (*ora_sgemm_fn)(int, int, int, long long, long long, long long, float, const float *, long long,
+                             const float *, long long, float, float *, long long);
+typedef void (*ora_dgemm_fn)(int, int, int, long long, long long, long long, double, const double *, long long,
+                             const double *, long long, double, double *, long long);
+static ora_sgemm_fn g_sgemm = NULL;
+static ora_dgemm_fn g_dgemm = NULL;
+static void (*g_blas_set_threads)(int) = NULL;
+
+static int ora_blas_gemm_f(int tA, int tB, int m, int n, int k, float alpha, const float *A, int lda,
+                           const float *B, int ldb, float beta, float *C, int ldc) {
+  if (!g_sgemm) return 0;
+  g_sgemm(101, tA ? 112 : 111, tB ? 112 : 111, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  return 1;
+}
+static int ora_blas_gemm_d(int tA, int tB, int m, int n, int k, double alpha, const double *A, int lda,
+                           const double *B, int ldb, double beta, double *C, int ldc) {
+  if (!g_dgemm) return 0;
+  g_dgemm(101, tA ? 112 : 111, tB ? 112 : 111, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  return 1;
+}
 
 #define REAL float
 #define ORA(name) ORA_CAT(oraF_, name)
+#define ORA_BLAS_GEMM ora_blas_gemm_f
 #include "kcnn_oracle_impl.h"
 #undef REAL
 #undef ORA
+#undef ORA_BLAS_GEMM
 
 #define REAL double
 #define ORA(name) ORA_CAT(oraD_, name)
+#define ORA_BLAS_GEMM ora_blas_gemm_d
 #include "kcnn_oracle_impl.h"
 #undef REAL
 #undef ORA
+#undef ORA_BLAS_GEMM
+
+/* path: an ILP64 OpenBLAS (numpy.libs/libscipy_openblas64_*.so); NULL or "" switches back to
+ * the plain loops.  Returns 1 when the BLAS is in use. */
+int ora_use_blas(const char *path) {
+  g_sgemm = NULL; g_dgemm = NULL; g_blas_set_threads = NULL;
+  if (!path || !path[0]) return 0;
+  void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return 0;
+  g_sgemm = (ora_sgemm_fn)dlsym(h, "scipy_cblas_sgemm64_");
+  g_dgemm = (ora_dgemm_fn)dlsym(h, "scipy_cblas_dgemm64_");
+  g_blas_set_threads = (void (*)(int))dlsym(h, "scipy_openblas_set_num_threads64_");
+  if (!g_sgemm || !g_dgemm) { g_sgemm = NULL; g_dgemm = NULL; return 0; }
+  return 1;
+}
 
 /* ---- glue between the hot-path layers, float only ---------- */
 
@@ -102,6 +148,7 @@ void oraF_softmax_backprop(const float *out_value, int rows, int cols, int ov_st
 /* Host threads the GEMMs may use (bench.py's CPU legs set it to the box's core count;
  * tests leave it alone).  Returns the number in effect; 1 when built without OpenMP. */
 int ora_set_num_threads(int n) {
+  if (n > 0 && g_blas_set_threads) g_blas_set_threads(n);
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);
   return omp_get_max_threads();

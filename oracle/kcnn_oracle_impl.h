@@ -36,6 +36,7 @@
 void ORA(gemm)(int transA, int transB, int m, int n, int k, REAL alpha,
                const REAL *A, int lda, const REAL *B, int ldb, REAL beta,
                REAL *C, int ldc) {
+  if (ORA_BLAS_GEMM(transA, transB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)) return;
   for (int i = 0; i < m; i++) {
     REAL *c = C + (size_t)i * ldc;
     if (beta == (REAL)0) {

@@ -25,12 +25,29 @@ def build(force=False):
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
-    cmd = ["gcc", "-O3", "-mavx2", "-mfma", "-fopenmp", "-fPIC", "-shared", "-std=c11",
-           "-Wall", "-Wno-maybe-uninitialized", "-o", _LIB_PATH, src[0], "-lm"]
+    cmd = ["gcc", "-O3", "-mavx2", "-mfma", "-fopenmp", "-fPIC", "-shared", "-std=gnu11",
+           "-Wall", "-Wno-maybe-uninitialized", "-o", _LIB_PATH, src[0], "-lm", "-ldl"]
     if subprocess.run(cmd, cwd=_HERE, capture_output=True).returncode != 0:
         cmd.remove("-fopenmp")                      # no libgomp: single-threaded build
         subprocess.run(cmd, check=True, cwd=_HERE)
     return _LIB_PATH
+
+
+def use_blas(on=True):
+    """Route the oracle's GEMMs through the OpenBLAS numpy bundles (the reference's CPU build
+    does them in Kaldi's BLAS).  CPU-baseline legs only; returns the library path or None."""
+    import glob
+    L = lib()
+    L.ora_use_blas.restype = ctypes.c_int
+    L.ora_use_blas.argtypes = [ctypes.c_char_p]
+    if not on:
+        L.ora_use_blas(None)
+        return None
+    cands = glob.glob(os.path.join(os.path.dirname(np.__file__), "..", "numpy.libs", "libscipy_openblas64_*.so"))
+    for c in sorted(cands):
+        if L.ora_use_blas(os.path.abspath(c).encode()) == 1:
+            return os.path.abspath(c)
+    return None
 
 
 def set_num_threads(n):
