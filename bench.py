@@ -349,9 +349,20 @@ def run_ours(args):
     labels = torch.randint(0, nout, (N,), device="cuda", generator=gen, dtype=torch.int32)
     stream = torch.cuda.Stream()
     arena = None
+    peer = None
     if world > 1:
         with torch.cuda.stream(stream):
-            arena = net.enable_data_parallel()
+            if args.dp_reduce == "p2p":
+                # gradient arena in NVLink peer memory, reduced by the library's own kernel
+                try:
+                    from kaldi_cnn_b200.dp import PeerMemoryAllReduce
+                    peer = PeerMemoryAllReduce(L, dist, net.gradient_floats())
+                    arena = net.enable_data_parallel(peer.arena)
+                except Exception as e:
+                    sys.stderr.write("bench.py: peer-memory all-reduce unavailable (%r); using NCCL\n" % (e,))
+                    peer = None
+            if peer is None:
+                arena = net.enable_data_parallel()
     ncomp = net.num_components
     updatable = [c for c in range(ncomp) if L.kcnn_component_gradient_floats(net.component(c).h) > 0]
 
@@ -363,7 +374,7 @@ def run_ours(args):
         from kaldi_cnn_b200.dp import PipelinedDataParallelStep, late_components
         small_group = dist.new_group(ranks=list(range(world)))
         dp_step = PipelinedDataParallelStep(net, arena, updatable, dist, world, late_components(net, updatable),
-                                            small_group, skip_reduce=args.dp_skip_reduce)
+                                            small_group, skip_reduce=args.dp_skip_reduce, peer=peer)
 
     def step():
         if world == 1:
@@ -420,6 +431,11 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         objf = net.objf_and_reset()
+        # a fingerprint of the trained parameters right after the timed steps: two runs that did the
+        # same arithmetic (e.g. --dp-reduce p2p vs nccl at 2 GPUs) print the same number
+        param_checksum = 0.0
+        for c in updatable:
+            param_checksum += float(net.component(c).params(0).double().abs().sum().item())
 
         # ---- end to end through the C-ABI with HOST buffers (pinned), copies in the timed region
         e2e = None
@@ -510,8 +526,9 @@ def run_ours(args):
         "dtype": "tf32" if math == 1 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][1], "per_gpu_batch": N, "global_batch": N * world,
                    "parallelism": "dp%d" % world if world > 1 else "single",
-                   **({"dp_schedule": "pipelined: backward(t) + all-reduce + update + forward(t+1) per step"}
-                      if world > 1 else {}),
+                   **({"dp_schedule": "pipelined: backward(t) + all-reduce + update + forward(t+1) per step",
+                       "dp_reduce": ("kcnn_p2p_allreduce_f32 (NVLink peer memory, two-shot)" if peer is not None
+                                     else "NCCL all-reduce")} if world > 1 else {}),
                    "params": param_count(cfg), "train_mflop_per_frame": flops_frame / 1e6,
                    "l2": "working set (weights + momentum + gradients = %.0f MB) exceeds the 126 MB L2"
                          % (param_count(cfg) * 12 / 1e6),
@@ -520,6 +537,7 @@ def run_ours(args):
                    "math": "KCNN_MATH_TF32_TC" if math == 1 else "KCNN_MATH_FP32_SIMT"},
         "step_tflops": step_tflops,
         "objf_per_frame_last": objf / max(N * (args.steps + 3 + 1), 1),
+        "param_checksum": param_checksum,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": dominant, "kernels": kernels, "cpu_baseline": cpu,
@@ -557,6 +575,9 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--dp-reduce", default=os.environ.get("KCNN_BENCH_DP_REDUCE", "p2p"), choices=["p2p", "nccl"],
+                    help="gradient all-reduce of the data-parallel step: the library's NVLink peer-memory kernel "
+                         "(kcnn_p2p_allreduce_f32) or NCCL")
     ap.add_argument("--dp-skip-reduce", action="store_true",
                     help="diagnosis only: run the data-parallel step without its all-reduces (invalid as a result)")
     args = ap.parse_args()

@@ -208,6 +208,23 @@ int kcnn_nnet_set_fusion(kcnn_nnet *n, int on);
 /* 1 when the most recent train step of this network was a graph replay, else 0. */
 int kcnn_nnet_last_step_replayed(const kcnn_nnet *n);
 
+/* ---- gradient all-reduce over NVLink peer memory (kernels_p2p.cu) ---------------------------
+ * Replaces the reference's file-based nnet-am-average (egs/steps/nnet0/train_conv_dropout.sh:
+ * 323-341) for the data-parallel step.  Every rank owns one SYMMETRIC allocation of the same
+ * size (e.g. torch.distributed._symmetric_memory, cudaIpc, cuMem fabric handles): the gradient
+ * arena (kcnn_nnet_set_gradient_arena) followed by kcnn_p2p_flag_floats() zero-initialised
+ * floats of flags.  peer_bases[p] is the address of rank p's allocation as mapped into THIS
+ * process.  kcnn_p2p_allreduce_f32 sums floats [offset, offset + count) of all ranks' arenas
+ * in place on every rank (two-shot: reduce own slice from peer loads, store the sum to every
+ * peer), enqueued on `stream`; all ranks must enqueue the same sequence of calls per channel
+ * (channel 0 / 1: two independent flag sets, for two streams).  Offsets and counts in floats,
+ * multiples of 4.  Returns 0, or -1 on bad arguments. */
+size_t kcnn_p2p_flag_floats(void);
+int kcnn_p2p_allreduce_f32(void *stream, const unsigned long long *peer_bases, int rank, int world,
+                           size_t offset_floats, size_t count_floats, size_t flag_offset_floats, int channel);
+/* 1 when a barrier of this rank gave up waiting for a peer (synchronises the device). */
+int kcnn_p2p_error(const float *local_base, size_t flag_offset_floats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -308,14 +308,23 @@ class Nnet:
         return bool(_lib().kcnn_nnet_last_step_replayed(self.h))
 
     # ---- data parallel -----------------------------------------------------------
-    def enable_data_parallel(self):
+    def gradient_floats(self):
+        return int(_lib().kcnn_nnet_gradient_floats(self.h))
+
+    def enable_data_parallel(self, arena=None):
         """Deferred updates + one flat gradient arena (a torch tensor, so torch.distributed
-        can all-reduce it); returns the arena."""
+        can all-reduce it); returns the arena.  arena: caller-provided storage of at least
+        gradient_floats() floats (e.g. NVLink peer memory, dp.PeerMemoryAllReduce.arena)."""
         import torch
         L = _lib()
         _check(L.kcnn_nnet_set_deferred_update(self.h, 1))
         n = L.kcnn_nnet_gradient_floats(self.h)
-        self._arena = torch.zeros(n, dtype=torch.float32, device="cuda")
+        if arena is not None:
+            if arena.numel() < n or arena.dtype != torch.float32 or not arena.is_cuda:
+                raise ValueError("arena must be a CUDA float32 tensor of >= %d elements" % n)
+            self._arena = arena
+        else:
+            self._arena = torch.zeros(n, dtype=torch.float32, device="cuda")
         _check(L.kcnn_nnet_set_gradient_arena(self.h, ctypes.c_void_p(self._arena.data_ptr())))
         return self._arena
 

@@ -288,7 +288,7 @@ inline bool launch_conv_rows(cudaStream_t st, const CUtensorMap &ma, const CUten
   int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;
   const int M = p.num_samples * p.R;
-  float *ws = splits > 1 ? scratch(SCRATCH_SPLITK, (size_t)splits * M * p.out_maps * sizeof(float)) : nullptr;
+  float *ws = splits > 1 ? scratch(SCRATCH_SPLITK_ROWS, (size_t)splits * M * p.out_maps * sizeof(float)) : nullptr;
   if (splits <= 1 || !ws) {
     p.kb_per_split = num_kb; p.workspace = nullptr;
     launch_prob(st, ma, mb, p, grid, num_kb);

@@ -746,7 +746,11 @@ bool persistent_enabled();               // KCNN_TMA_PERSIST=0 keeps multi-wave 
 
 // Grow-only device scratch, one buffer per slot (kernels_gemm.cu).  Returns nullptr when it
 // would have to grow while the stream is being captured; callers then take another path.
-enum ScratchSlot { SCRATCH_SPLITK = 0, SCRATCH_XCL = 1, SCRATCH_DYCL = 2, SCRATCH_BIAS = 3, SCRATCH_SLOTS = 4 };
+// SCRATCH_SPLITK_ROWS: partials of the convolution fprop / dgrad split; its own slot because
+// inside a convolution's Backprop the dgrad GEMM runs CONCURRENTLY with the weight-gradient GEMM
+// (kcnn::ForkJoin), whose partials live in SCRATCH_SPLITK.
+enum ScratchSlot { SCRATCH_SPLITK = 0, SCRATCH_XCL = 1, SCRATCH_DYCL = 2, SCRATCH_BIAS = 3, SCRATCH_SPLITK_ROWS = 4,
+                   SCRATCH_SLOTS = 5 };
 float *scratch(int slot, size_t bytes);
 
 // Tensor map of rank 2 to 4 over FP32 data; dims[0] is the contiguous axis, strides_bytes[i]

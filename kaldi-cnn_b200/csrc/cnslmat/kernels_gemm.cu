@@ -96,8 +96,8 @@ bool deep_ring_enabled() {
 // of a shape must happen outside stream capture (warm-up steps do that); outgrown buffers
 // are kept alive because CUDA graphs captured earlier still point at them.
 float *scratch(int slot, size_t bytes) {
-  static float *buf[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-  static size_t cap[SCRATCH_SLOTS] = {0, 0, 0, 0};
+  static float *buf[SCRATCH_SLOTS] = {};
+  static size_t cap[SCRATCH_SLOTS] = {};
   if (bytes > cap[slot]) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(g_legacy_stream, &cs);

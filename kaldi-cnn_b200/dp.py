@@ -16,6 +16,7 @@ egs/steps/nnet0/train_conv_dropout.sh:323-341) by a per-step gradient all-reduce
 Host logic only: `net` is anything with the Nnet interface of components.py (the CUDA model on
 a GPU box, an oracle-backed model in the world-size-2 gloo test).
 """
+import os
 
 
 def shard_rows(num_rows, rank, world):
@@ -43,6 +44,81 @@ def late_components(net, updatable, min_floats=1 << 20):
         else:
             break
     return late
+
+
+class _Done:
+    """What dist.all_reduce(async_op=True) returns, for the peer-memory path: wait() makes the
+    CURRENT stream wait for the reduction (an event wait, capturable into a CUDA graph)."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        import torch
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class PeerMemoryAllReduce:
+    """Gradient arena in NVLink peer memory + the library's own all-reduce kernel
+    (csrc/cnslmat/kernels_p2p.cu, kcnn_p2p_allreduce_f32): two-shot, 128-bit peer loads and
+    stores, device-side flags -- no NCCL on the data path.  The arena is one symmetric
+    allocation (torch.distributed._symmetric_memory: cuMem handles exchanged through the
+    process group) of `floats` gradient floats followed by the flag words.
+
+    all_reduce(offset, length, channel) enqueues the reduction of arena[offset:offset+length]
+    on the channel's own stream behind everything the current stream has enqueued so far and
+    returns a handle whose wait() orders the current stream behind it -- the contract of
+    dist.all_reduce(async_op=True).  Two channels = two independent streams / flag sets (small
+    convolution buckets must not queue behind 140 MB of FC gradients)."""
+
+    def __init__(self, lib, dist, floats):
+        import ctypes
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        self.lib, self.dist = lib, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        flag = int(lib.kcnn_p2p_flag_floats())
+        self.floats = (int(floats) + 63) // 64 * 64
+        self.flag_off = self.floats
+        group = dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass                                   # newer torch: not needed
+        self.buf = symm.empty(self.floats + flag, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(ptrs) == self.world and ptrs[self.rank] == self.buf.data_ptr()
+        self.bases = (ctypes.c_ulonglong * self.world)(*ptrs)
+        self.arena = self.buf[:self.floats]
+        prio = int(os.environ.get("KCNN_P2P_STREAM_PRIORITY", "-1"))      # reductions first: they are short CTAs
+        self.streams = [torch.cuda.Stream(priority=prio), torch.cuda.Stream(priority=prio)]
+
+    def all_reduce(self, offset, length, channel=0):
+        import ctypes
+        import torch
+        if length % 4 or offset % 4:
+            raise ValueError("offset / length must be multiples of 4 floats")
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        st = self.streams[channel]
+        st.wait_event(ready)
+        rc = self.lib.kcnn_p2p_allreduce_f32(ctypes.c_void_p(st.cuda_stream), self.bases, self.rank, self.world,
+                                             int(offset), int(length), int(self.flag_off), int(channel))
+        if rc != 0:
+            raise RuntimeError("kcnn_p2p_allreduce_f32 rejected its arguments")
+        done = torch.cuda.Event()
+        done.record(st)
+        return _Done(done)
+
+    def failed(self):
+        """True when a barrier gave up waiting for a peer (synchronises)."""
+        import ctypes
+        return bool(self.lib.kcnn_p2p_error(ctypes.c_void_p(self.buf.data_ptr()), int(self.flag_off)))
 
 
 class DataParallelStep:
@@ -95,9 +171,13 @@ class PipelinedDataParallelStep:
     collectives of one communicator in issue order, and the convolution gradients -- produced
     last -- must not queue behind 140 MB of FC gradients."""
 
-    def __init__(self, net, arena, updatable, dist, world, late_from, small_group=None, skip_reduce=False):
+    def __init__(self, net, arena, updatable, dist, world, late_from, small_group=None, skip_reduce=False,
+                 peer=None):
+        """peer: a PeerMemoryAllReduce whose .arena IS `arena` -- the reductions then run on the
+        library's own NVLink kernel instead of NCCL."""
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs a torch.distributed module / process group")
+        self.peer = peer
         self.net, self.arena, self.dist, self.world = net, arena, dist, world
         self.updatable = bucket_order(updatable)
         self.late_from = late_from if late_from is not None else net.num_components
@@ -114,6 +194,17 @@ class PipelinedDataParallelStep:
         off, ln = self.net.gradient_bucket(c)
         if self.world <= 1 or self.skip_reduce:
             return None
+        dbg = os.environ.get("KCNN_DP_DEBUG", "")          # timing diagnosis only (results are then wrong)
+        if (dbg == "fc_only" and c < self.late_from) or (dbg == "conv_only" and c >= self.late_from):
+            return None
+        if dbg == "nowait":
+            self._reduce_impl(c, off, ln)
+            return None
+        return self._reduce_impl(c, off, ln)
+
+    def _reduce_impl(self, c, off, ln):
+        if self.peer is not None:
+            return self.peer.all_reduce(off, ln, channel=1 if c < self.late_from else 0)
         group = self.small_group if c < self.late_from else None
         return self.dist.all_reduce(self.arena[off:off + ln], group=group, async_op=True)
 

@@ -28,7 +28,12 @@ CPAD = ("ConvolutionComponent in-height=6 in-width=7 in-channel=5 in-pad-height=
         "kernel-width=4 stride=1 group=10 out-height=6 out-width=8 learning-rate=0.05 param-stddev=0.1 bias-stddev=0.5")
 CTIME = ("ConvolutionComponent in-height=1 in-width=14 in-channel=64 kernel-height=1 kernel-width=3 stride=1 "
          "group=128 out-height=1 out-width=12 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5")
+C5 = ("ConvolutionComponent in-height=1 in-width=6 in-channel=256 kernel-height=1 kernel-width=3 stride=1 "
+      "group=512 out-height=1 out-width=4 learning-rate=0.02 param-stddev=0.02 bias-stddev=0.5")
 CONV_LINES = {"C1a": (C1A, (40, 11, 3, 0, 0, 40, 4, 128), 256), "C1b": (C1B, (40, 11, 3, 0, 0, 8, 3, 64), 32),
+              # conv5 of nnet.config at N = 128: the input-gradient GEMM AND the weight-gradient GEMM are both
+              # split over K, and they run as two concurrent branches (separate split-K scratch!)
+              "conv5": (C5, (1, 6, 256, 0, 0, 1, 3, 512), 128),
               "pad": (CPAD, (6, 7, 5, 1, 2, 3, 4, 10), 9),
               "time": (CTIME, (1, 14, 64, 0, 0, 1, 3, 128), 70)}     # nnet.config-style layer: TMA path + staging
 
@@ -73,6 +78,33 @@ def test_convolution_component_two_training_steps(ora, name, math):
         assert rel_err(_get(comp.params(2)), prev_r) <= TOL[math] * 4
         assert np.abs(_get(comp.params(1))[0] - bias_r).max() <= 1e-5 * max(np.abs(bias_r - bias).max(), 1e-30) * 4
         lin, bias, prev = _get(comp.params(0)), _get(comp.params(1))[0], _get(comp.params(2))
+    kc.set_math_mode(0)
+
+
+@pytest.mark.parametrize("name", ["conv5", "time", "C1a"])
+def test_convolution_deferred_gradient(ora, name):
+    """Data-parallel mode (update deferred): Backprop leaves the un-normalised dK, db of
+    nnet0/nnet-component-nnet0.cc:763, 775 in the gradient buffers and the right in_deriv."""
+    line, (H, W, C, ph, pw, KH, KW, G), N = CONV_LINES[name]
+    kc.set_math_mode(1)
+    kc.set_rand_seed(42)
+    comp = kc.Component.from_string(line)
+    comp.set_deferred_update(True)
+    OH, OW = H + 2 * ph - KH + 1, W + 2 * pw - KW + 1
+    lin, bias, prev = _get(comp.params(0)), _get(comp.params(1))[0], _get(comp.params(2))
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((N, H * W * C)).astype(np.float32)
+    dy = rng.standard_normal((N, OH * OW * G)).astype(np.float32)
+    xd, dyd = dev(x, 4, 0), dev(dy, 0, 0)
+    comp.propagate(xd)
+    dx = comp.backprop(xd, None, dyd, update=True)
+    dx_ref = ora.conv_backprop(dy, lin, H, W, C, ph, pw, KH, KW, G, dtype=np.float64)
+    assert rel_err(_get(dx), dx_ref) <= 1e-3
+    g_r, bg_r = ora.conv_update(x, dy, lin, bias, prev, H, W, C, ph, pw, KH, KW, G, 0.02, 0.0002, 0.9,
+                                dtype=np.float64)[3:5]
+    assert rel_err(_get(comp.gradient(0)), g_r) <= 1e-3
+    assert rel_err(_get(comp.gradient(1))[0], bg_r) <= 1e-5 * 8
+    assert np.array_equal(_get(comp.params(0)), lin)          # nothing applied yet
     kc.set_math_mode(0)
 
 
