@@ -352,15 +352,26 @@ def run_ours(args):
     peer = None
     if world > 1:
         with torch.cuda.stream(stream):
-            if args.dp_reduce == "p2p":
+            # auto: the in-switch (multimem) kernel from 4 GPUs up -- measured at 8 GPUs: 1.06 ms / step vs
+            # 1.15 two-shot vs 1.23 NCCL -- and the two-shot kernel at 2 (1.00 vs 1.06 vs 1.05)
+            modes = {"auto": ["nvls", "p2p"] if world > 2 else ["p2p"], "nvls": ["nvls"], "p2p": ["p2p"],
+                     "nccl": []}[args.dp_reduce]
+            for mode in modes:
                 # gradient arena in NVLink peer memory, reduced by the library's own kernel
                 try:
                     from kaldi_cnn_b200.dp import PeerMemoryAllReduce
-                    peer = PeerMemoryAllReduce(L, dist, net.gradient_floats())
-                    arena = net.enable_data_parallel(peer.arena)
+                    peer = PeerMemoryAllReduce(L, dist, net.gradient_floats(), multicast=mode == "nvls")
                 except Exception as e:
-                    sys.stderr.write("bench.py: peer-memory all-reduce unavailable (%r); using NCCL\n" % (e,))
+                    sys.stderr.write("bench.py: peer-memory all-reduce (%s) unavailable (%r)\n" % (mode, e))
                     peer = None
+                # all ranks take the same path: one rank without peer memory sends everyone on
+                agree = torch.tensor([1 if peer is not None else 0], device="cuda")
+                dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+                if int(agree.item()) == 1:
+                    break
+                peer = None
+            if peer is not None:
+                arena = net.enable_data_parallel(peer.arena)
             if peer is None:
                 arena = net.enable_data_parallel()
     ncomp = net.num_components
@@ -488,7 +499,10 @@ def run_ours(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             e2e = {"value": N * world * args.steps / float(dt.item()), "unit": "frames/s",
                    "h2d_bytes_per_step": N * dim * 4 + N * 4, "d2h_bytes_per_step": 8,
-                   "api": "kcnn_nnet_forward/backward + NCCL all-reduce, pinned host buffers per rank"}
+                   "api": "kcnn_nnet_forward/backward + %s, pinned host buffers per rank, objective read "
+                          "back every step" % ("NCCL all-reduce" if peer is None else
+                                               "kcnn_p2p_allreduce_multicast_f32" if peer.multicast_base else
+                                               "kcnn_p2p_allreduce_f32")}
 
         kernels = kernel_rooflines(args, pk, math) if (rank == 0 and not args.no_kernels) else []
 
@@ -527,8 +541,10 @@ def run_ours(args):
         "config": {"workload": WORKLOADS[args.workload][1], "per_gpu_batch": N, "global_batch": N * world,
                    "parallelism": "dp%d" % world if world > 1 else "single",
                    **({"dp_schedule": "pipelined: backward(t) + all-reduce + update + forward(t+1) per step",
-                       "dp_reduce": ("kcnn_p2p_allreduce_f32 (NVLink peer memory, two-shot)" if peer is not None
-                                     else "NCCL all-reduce")} if world > 1 else {}),
+                       "dp_reduce": ("NCCL all-reduce" if peer is None else
+                                     "kcnn_p2p_allreduce_multicast_f32 (NVSwitch in-switch reduction, multimem)"
+                                     if peer.multicast_base else
+                                     "kcnn_p2p_allreduce_f32 (NVLink peer memory, two-shot)")} if world > 1 else {}),
                    "params": param_count(cfg), "train_mflop_per_frame": flops_frame / 1e6,
                    "l2": "working set (weights + momentum + gradients = %.0f MB) exceeds the 126 MB L2"
                          % (param_count(cfg) * 12 / 1e6),
@@ -575,9 +591,10 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
-    ap.add_argument("--dp-reduce", default=os.environ.get("KCNN_BENCH_DP_REDUCE", "p2p"), choices=["p2p", "nccl"],
+    ap.add_argument("--dp-reduce", default=os.environ.get("KCNN_BENCH_DP_REDUCE", "auto"),
+                    choices=["auto", "p2p", "nvls", "nccl"],
                     help="gradient all-reduce of the data-parallel step: the library's NVLink peer-memory kernel "
-                         "(kcnn_p2p_allreduce_f32) or NCCL")
+                         "(kcnn_p2p_allreduce_f32: two-shot), its in-switch variant (nvls: multimem) or NCCL")
     ap.add_argument("--dp-skip-reduce", action="store_true",
                     help="diagnosis only: run the data-parallel step without its all-reduces (invalid as a result)")
     args = ap.parse_args()

@@ -222,6 +222,13 @@ int kcnn_nnet_last_step_replayed(const kcnn_nnet *n);
 size_t kcnn_p2p_flag_floats(void);
 int kcnn_p2p_allreduce_f32(void *stream, const unsigned long long *peer_bases, int rank, int world,
                            size_t offset_floats, size_t count_floats, size_t flag_offset_floats, int channel);
+/* The same reduction done INSIDE the NVSwitch (NVLS): multicast_base is the multicast mapping of
+ * the symmetric allocation (torch symmetric memory: handle.multicast_ptr; cuMulticast*); the
+ * kernel pulls the sum of its slice with multimem.ld_reduce and broadcasts it with multimem.st.
+ * The flags still go through peer_bases.  Returns -1 when multicast_base is 0. */
+int kcnn_p2p_allreduce_multicast_f32(void *stream, const unsigned long long *peer_bases,
+                                     unsigned long long multicast_base, int rank, int world, size_t offset_floats,
+                                     size_t count_floats, size_t flag_offset_floats, int channel);
 /* 1 when a barrier of this rank gave up waiting for a peer (synchronises the device). */
 int kcnn_p2p_error(const float *local_base, size_t flag_offset_floats);
 

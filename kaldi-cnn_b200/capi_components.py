@@ -81,6 +81,7 @@ PROTOS = {
     "kcnn_nnet_set_fusion": ([H, I], c_int),
     "kcnn_p2p_flag_floats": ([], c_size_t),
     "kcnn_p2p_allreduce_f32": ([P, P, I, I, c_size_t, c_size_t, c_size_t, I], c_int),
+    "kcnn_p2p_allreduce_multicast_f32": ([P, P, ctypes.c_ulonglong, I, I, c_size_t, c_size_t, c_size_t, I], c_int),
     "kcnn_p2p_error": ([P, c_size_t], c_int),
 }
 

@@ -82,8 +82,24 @@ __device__ __forceinline__ void cross_barrier(const Peers &pr, size_t flag_off, 
   __syncthreads();
 }
 
+// In-switch reduction (NVLS): one 128-bit multimem.ld_reduce on the MULTICAST address of an
+// element makes the NVSwitch fetch it from every rank's replica and return the sum; multimem.st
+// writes a value to every replica.  Per GPU the links then carry (1 + 1/world) x the bucket in
+// each direction instead of 2 (world-1)/world x for the two-shot above, and the SMs do no adds.
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float *mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float *mc, const float4 &v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// mc: multicast mapping of the same symmetric allocation (nullptr: two-shot over unicast peers)
 __global__ void __launch_bounds__(kThreads)
-p2p_allreduce_kernel(Peers pr, int rank, int world, size_t off, size_t n4, size_t flag_off) {
+p2p_allreduce_kernel(Peers pr, float *mc, int rank, int world, size_t off, size_t n4, size_t flag_off) {
   const int b = blockIdx.x, G = gridDim.x, t = threadIdx.x;
   __shared__ uint32_t s_epoch;
   uint32_t *my_flags = reinterpret_cast<uint32_t *>(pr.buf[rank] + flag_off);
@@ -98,6 +114,22 @@ p2p_allreduce_kernel(Peers pr, int rank, int world, size_t off, size_t n4, size_
   const size_t hi = lo + per < n4 ? lo + per : n4;
   const size_t step = (size_t)G * kThreads;
   constexpr int U = 4;                                   // independent 128-bit loads per peer in flight
+  if (mc != nullptr) {
+    float *m = mc + off;
+    for (size_t i0 = lo + (size_t)b * kThreads + t; i0 < hi; i0 += U * step) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + u * step;
+        if (i < hi) v[u] = multimem_ld_reduce_f4(m + 4 * i);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + u * step;
+        if (i < hi) multimem_st_f4(m + 4 * i, v[u]);
+      }
+    }
+  } else
   for (size_t i0 = lo + (size_t)b * kThreads + t; i0 < hi; i0 += U * step) {
     float4 acc[U];
 #pragma unroll
@@ -140,8 +172,8 @@ extern "C" {
 
 size_t kcnn_p2p_flag_floats(void) { return (size_t)p2p::kChannelWords * 2; }   // two channels
 
-int kcnn_p2p_allreduce_f32(void *stream, const unsigned long long *peer_bases, int rank, int world,
-                           size_t offset_floats, size_t count_floats, size_t flag_offset_floats, int channel) {
+static int p2p_launch(void *stream, const unsigned long long *peer_bases, unsigned long long mc_base, int rank,
+                      int world, size_t offset_floats, size_t count_floats, size_t flag_offset_floats, int channel) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (world < 1 || world > p2p::kMaxRanks || rank < 0 || rank >= world) return -1;
   if (channel < 0 || channel > 1) return -1;
@@ -162,9 +194,23 @@ int kcnn_p2p_allreduce_f32(void *stream, const unsigned long long *peer_bases, i
   size_t want = (per + p2p::kThreads * 4 - 1) / (p2p::kThreads * 4);       // one pass of 4 units per thread
   if (want < 1) want = 1;
   const unsigned grid = (unsigned)(want < (size_t)max_ctas ? want : (size_t)max_ctas);
-  KCNN_LAUNCH(p2p::p2p_allreduce_kernel, grid, p2p::kThreads, 0, st, pr, rank, world, offset_floats, n4,
+  KCNN_LAUNCH(p2p::p2p_allreduce_kernel, grid, p2p::kThreads, 0, st, pr,
+              reinterpret_cast<float *>(static_cast<uintptr_t>(mc_base)), rank, world, offset_floats, n4,
               flag_offset_floats + (size_t)channel * p2p::kChannelWords);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int kcnn_p2p_allreduce_f32(void *stream, const unsigned long long *peer_bases, int rank, int world,
+                           size_t offset_floats, size_t count_floats, size_t flag_offset_floats, int channel) {
+  return p2p_launch(stream, peer_bases, 0ull, rank, world, offset_floats, count_floats, flag_offset_floats, channel);
+}
+
+int kcnn_p2p_allreduce_multicast_f32(void *stream, const unsigned long long *peer_bases,
+                                     unsigned long long multicast_base, int rank, int world, size_t offset_floats,
+                                     size_t count_floats, size_t flag_offset_floats, int channel) {
+  if (multicast_base == 0ull) return -1;
+  return p2p_launch(stream, peer_bases, multicast_base, rank, world, offset_floats, count_floats,
+                    flag_offset_floats, channel);
 }
 
 /* 1 when a barrier of this rank gave up waiting for a peer (the arena contents are then undefined). */

@@ -71,7 +71,10 @@ class PeerMemoryAllReduce:
     dist.all_reduce(async_op=True).  Two channels = two independent streams / flag sets (small
     convolution buckets must not queue behind 140 MB of FC gradients)."""
 
-    def __init__(self, lib, dist, floats):
+    def __init__(self, lib, dist, floats, multicast=False):
+        """multicast: reduce inside the NVSwitch (kcnn_p2p_allreduce_multicast_f32, multimem.ld_reduce /
+        multimem.st on the allocation's multicast mapping); raises RuntimeError when the
+        platform gives the allocation no multicast address."""
         import ctypes
         import torch
         import torch.distributed._symmetric_memory as symm
@@ -94,6 +97,11 @@ class PeerMemoryAllReduce:
         assert len(ptrs) == self.world and ptrs[self.rank] == self.buf.data_ptr()
         self.bases = (ctypes.c_ulonglong * self.world)(*ptrs)
         self.arena = self.buf[:self.floats]
+        self.multicast_base = 0
+        if multicast:
+            self.multicast_base = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+            if self.multicast_base == 0:
+                raise RuntimeError("symmetric memory has no multicast mapping on this platform")
         prio = int(os.environ.get("KCNN_P2P_STREAM_PRIORITY", "-1"))      # reductions first: they are short CTAs
         self.streams = [torch.cuda.Stream(priority=prio), torch.cuda.Stream(priority=prio)]
 
@@ -107,8 +115,13 @@ class PeerMemoryAllReduce:
         ready.record(cur)
         st = self.streams[channel]
         st.wait_event(ready)
-        rc = self.lib.kcnn_p2p_allreduce_f32(ctypes.c_void_p(st.cuda_stream), self.bases, self.rank, self.world,
-                                             int(offset), int(length), int(self.flag_off), int(channel))
+        if self.multicast_base:
+            rc = self.lib.kcnn_p2p_allreduce_multicast_f32(
+                ctypes.c_void_p(st.cuda_stream), self.bases, ctypes.c_ulonglong(self.multicast_base), self.rank,
+                self.world, int(offset), int(length), int(self.flag_off), int(channel))
+        else:
+            rc = self.lib.kcnn_p2p_allreduce_f32(ctypes.c_void_p(st.cuda_stream), self.bases, self.rank, self.world,
+                                                 int(offset), int(length), int(self.flag_off), int(channel))
         if rc != 0:
             raise RuntimeError("kcnn_p2p_allreduce_f32 rejected its arguments")
         done = torch.cuda.Event()

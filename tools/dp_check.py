@@ -52,7 +52,8 @@ def main():
         rng = np.random.default_rng(3)
         kc.set_rand_seed(7)
         net = kc.Nnet.from_config(CFG, skip_splice=True)
-        peer = PeerMemoryAllReduce(L, dist, net.gradient_floats()) if mode == "p2p" else None
+        peer = (PeerMemoryAllReduce(L, dist, net.gradient_floats(), multicast=mode == "nvls")
+                if mode in ("p2p", "nvls") else None)
         arena = net.enable_data_parallel(peer.arena if peer else None)
         updatable = [c for c in range(net.num_components) if L.kcnn_component_gradient_floats(net.component(c).h) > 0]
         plain = DataParallelStep(net, arena, updatable, dist, world)

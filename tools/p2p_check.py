@@ -27,7 +27,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = capi.lib()
     floats = 36_700_160                       # ~ the C2 model's gradient arena (146.8 MB)
-    peer = PeerMemoryAllReduce(L, dist, floats)
+    mode = os.environ.get("KCNN_P2P_CHECK_MODE", "p2p")        # p2p (two-shot) | nvls (in-switch, multimem)
+    peer = PeerMemoryAllReduce(L, dist, floats, multicast=mode == "nvls")
     g = torch.Generator(device="cuda"); g.manual_seed(100 + rank)
     ok = True
     cases = [(0, 64), (64, 4096), (4160, 20608 // 4 * 4), (1 << 20, 4 << 20), (0, peer.floats), (128, 786944 // 4 * 4)]
@@ -41,7 +42,7 @@ def main():
             peer.all_reduce(off, ln, channel=ch & 1).wait()
             torch.cuda.synchronize(); dist.barrier()
             got = peer.arena
-            same_in = torch.equal(got[off:off + ln], ref[off:off + ln]) if world == 2 else \
+            same_in = torch.equal(got[off:off + ln], ref[off:off + ln]) if world == 2 and mode == "p2p" else \
                 torch.allclose(got[off:off + ln], ref[off:off + ln], rtol=1e-6, atol=1e-6)
             same_out = torch.equal(got[:off], before[:off]) and torch.equal(got[off + ln:], before[off + ln:])
             if not (same_in and same_out):
@@ -75,9 +76,9 @@ def main():
     t_small_nccl = timeit(lambda: dist.all_reduce(small))
     err = peer.failed()
     if rank == 0:
-        print("p2p_check world=%d ok=%s barrier_error=%s | %.1f MB: p2p %.3f ms (%.0f GB/s algbw)  nccl %.3f ms (%.0f GB/s) | "
-              "197 KB bucket: p2p %.1f us  nccl %.1f us" % (
-                  world, ok, err, n * 4 / 1e6, t_p2p, n * 4 / t_p2p / 1e6, t_nccl, n * 4 / t_nccl / 1e6,
+        print("p2p_check world=%d mode=%s ok=%s barrier_error=%s | %.1f MB: kcnn %.3f ms (%.0f GB/s algbw)  nccl %.3f ms (%.0f GB/s) | "
+              "197 KB bucket: kcnn %.1f us  nccl %.1f us" % (
+                  world, mode, ok, err, n * 4 / 1e6, t_p2p, n * 4 / t_p2p / 1e6, t_nccl, n * 4 / t_nccl / 1e6,
                   t_small_p2p * 1e3, t_small_nccl * 1e3), flush=True)
     dist.barrier()
     dist.destroy_process_group()
