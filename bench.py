@@ -339,7 +339,12 @@ def run_ours(args):
     kc.set_rand_seed(42)
     cfg = load_config(args.workload)
     net = kc.Nnet.from_config(cfg, skip_splice=True)
+    if args.global_batch:                       # strong scaling: the global minibatch is fixed
+        if args.global_batch % world:
+            raise SystemExit("bench.py: --global-batch must be a multiple of the number of GPUs")
+        args.batch = args.global_batch // world
     N, dim, nout = args.batch, net.input_dim, net.output_dim
+    averaging = world > 1 and args.dp_mode == "average"
     L = capi.lib()
     pk = peaks()
 
@@ -350,7 +355,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     arena = None
     peer = None
-    if world > 1:
+    if world > 1 and not averaging:
         with torch.cuda.stream(stream):
             # auto: the in-switch (multimem) kernel from 4 GPUs up -- measured at 8 GPUs: 1.06 ms / step vs
             # 1.15 two-shot vs 1.23 NCCL -- and the two-shot kernel at 2 (1.00 vs 1.06 vs 1.05)
@@ -378,7 +383,15 @@ def run_ours(args):
     updatable = [c for c in range(ncomp) if L.kcnn_component_gradient_floats(net.component(c).h) > 0]
 
     dp_step = None
-    if world > 1:
+    post_step = lambda: None                      # noqa: E731
+    if averaging:
+        # Comparison row of SURVEY 8d C5: the reference's recipe trains independent jobs and averages their
+        # models (nnet-am-average, egs/steps/nnet0/train_conv_dropout.sh:323-341).  Here: ordinary local
+        # steps on every rank, parameters averaged in memory every --average-every steps.
+        from kaldi_cnn_b200.dp import ParameterAveraging
+        tensors = [net.component(c).params(k) for c in updatable for k in (0, 1)]
+        post_step = ParameterAveraging(tensors, dist, world, args.average_every).after_step
+    elif world > 1:
         # Data parallel: software-pipelined step (dp.py) -- backward of batch t with the per-layer
         # all-reduces, then forward of batch t+1, the FC stack's update sitting between the
         # convolution forward and the FC forward so its all-reduce hides under both.
@@ -388,7 +401,7 @@ def run_ours(args):
                                             small_group, skip_reduce=args.dp_skip_reduce, peer=peer)
 
     def step():
-        if world == 1:
+        if dp_step is None:
             net.forward(feats)
             net.objf_and_deriv(labels)
             net.backward()
@@ -432,6 +445,7 @@ def run_ours(args):
         e0.record(stream)
         for _ in range(args.steps):
             run()
+            post_step()
         e1.record(stream)
         e1.synchronize()
         torch.cuda.synchronize()
@@ -492,15 +506,16 @@ def run_ours(args):
             for _ in range(args.steps):
                 feats.copy_(hx, non_blocking=True)
                 labels.copy_(hl, non_blocking=True)
-                step()
+                run()                            # the recorded rotation reads feats / labels in place
+                post_step()
                 net.objf_and_reset()
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             e2e = {"value": N * world * args.steps / float(dt.item()), "unit": "frames/s",
                    "h2d_bytes_per_step": N * dim * 4 + N * 4, "d2h_bytes_per_step": 8,
-                   "api": "kcnn_nnet_forward/backward + %s, pinned host buffers per rank, objective read "
-                          "back every step" % ("NCCL all-reduce" if peer is None else
+                   "api": "kcnn_nnet_forward/backward + %s (one recorded CUDA graph per rotation), pinned host "
+                          "buffers per rank, objective read back every step" % ("NCCL all-reduce" if peer is None else
                                                "kcnn_p2p_allreduce_multicast_f32" if peer.multicast_base else
                                                "kcnn_p2p_allreduce_f32")}
 
@@ -536,11 +551,15 @@ def run_ours(args):
     line = {
         "metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
         "dtype": "tf32" if math == 1 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][1], "per_gpu_batch": N, "global_batch": N * world,
                    "parallelism": "dp%d" % world if world > 1 else "single",
-                   **({"dp_schedule": "pipelined: backward(t) + all-reduce + update + forward(t+1) per step",
+                   **({"dp_schedule": "BASELINE (comparison row, not synchronous SGD): independent local steps, "
+                                      "parameters averaged every %d steps (nnet-am-average emulation)"
+                                      % args.average_every, "dp_reduce": "NCCL all-reduce of the parameters"}
+                      if averaging else
+                      {"dp_schedule": "pipelined: backward(t) + all-reduce + update + forward(t+1) per step",
                        "dp_reduce": ("NCCL all-reduce" if peer is None else
                                      "kcnn_p2p_allreduce_multicast_f32 (NVSwitch in-switch reduction, multimem)"
                                      if peer.multicast_base else
@@ -595,6 +614,13 @@ def main():
                     choices=["auto", "p2p", "nvls", "nccl"],
                     help="gradient all-reduce of the data-parallel step: the library's NVLink peer-memory kernel "
                          "(kcnn_p2p_allreduce_f32: two-shot), its in-switch variant (nvls: multimem) or NCCL")
+    ap.add_argument("--dp-mode", default="sync", choices=["sync", "average"],
+                    help="sync: gradient all-reduce every step (the product). average: the comparison row of SURVEY 8d "
+                         "C5 -- local steps + parameter averaging every --average-every steps (nnet-am-average style)")
+    ap.add_argument("--average-every", type=int, default=8)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: fix the GLOBAL minibatch (rows per GPU = global / GPUs); 0 = weak scaling, "
+                         "--batch rows per GPU")
     ap.add_argument("--dp-skip-reduce", action="store_true",
                     help="diagnosis only: run the data-parallel step without its all-reduces (invalid as a result)")
     args = ap.parse_args()

@@ -134,6 +134,41 @@ class PeerMemoryAllReduce:
         return bool(self.lib.kcnn_p2p_error(ctypes.c_void_p(self.buf.data_ptr()), int(self.flag_off)))
 
 
+class ParameterAveraging:
+    """The baseline the gradient all-reduce replaces, for the comparison row of SURVEY 8d C5: the
+    reference's recipe runs independent training jobs and averages their models through the
+    filesystem (nnet-am-average, egs/steps/nnet0/train_conv_dropout.sh:323-341).  Emulated in
+    memory: every rank takes ordinary local steps; after every `every`-th step the given parameter
+    tensors (linear_params_ and bias_params_, what Nnet::Scale / AddNnet touch) are replaced by
+    their mean over the ranks.  Momentum (prev_grad_) stays local, as in the recipe."""
+
+    def __init__(self, tensors, dist, world, every):
+        if every < 1:
+            raise ValueError("every must be >= 1")
+        if world > 1 and dist is None:
+            raise ValueError("world > 1 needs a torch.distributed module / process group")
+        self.tensors, self.dist, self.world, self.every = list(tensors), dist, world, every
+        self.steps = 0
+
+    def after_step(self):
+        """Call once per local training step; True when this call averaged."""
+        self.steps += 1
+        if self.steps % self.every:
+            return False
+        self.average()
+        return True
+
+    def average(self):
+        if self.world <= 1:
+            return
+        for t in self.tensors:
+            flat = t if t.is_contiguous() else t.contiguous()      # pitched matrices: reduce a packed copy
+            self.dist.all_reduce(flat)
+            flat.mul_(1.0 / self.world)
+            if flat is not t:
+                t.copy_(flat)
+
+
 class DataParallelStep:
     def __init__(self, net, arena, updatable, dist=None, world=1, skip_reduce=False):
         """skip_reduce: diagnosis only (bench.py --dp-skip-reduce): the deferred-update step without

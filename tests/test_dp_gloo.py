@@ -216,3 +216,47 @@ def test_pipelined_step_matches_plain_step_world_2(tmp_path):
         for r in (0, 1):
             assert np.abs(got[r][name] - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), (name, r)
         assert np.array_equal(got[0][name], got[1][name])
+
+
+def _averaging_worker(rank, world, port, out):
+    from kaldi_cnn_b200.dp import ParameterAveraging
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = torch.arange(12, dtype=torch.float32).reshape(3, 4) * (rank + 1)
+        pitched = torch.zeros(3, 8)
+        b = pitched[:, :5]                                   # a pitched matrix view: not contiguous
+        b.fill_(float(rank))
+        avg = ParameterAveraging([w, b], dist, world, every=2)
+        flags = []
+        for _ in range(4):
+            w += 1.0                                          # the "local step"
+            flags.append(avg.after_step())
+        np.savez(os.path.join(out, "arank%d.npz" % rank), w=w.numpy(), b=pitched.numpy(), flags=np.array(flags))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_parameter_averaging_baseline_world_2(tmp_path):
+    """The comparison row of SURVEY 8d C5 (nnet-am-average emulation): local steps, mean of the
+    parameters every `every` steps, pitched views handled, padding untouched."""
+    mp.spawn(_averaging_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(os.path.join(str(tmp_path), "arank%d.npz" % r)) for r in (0, 1)]
+    base = np.arange(12, dtype=np.float32).reshape(3, 4)
+    # step 1, 2: +2 on each rank, then mean of (base + 2, 2 base + 2) = 1.5 base + 2; steps 3, 4 likewise
+    want = 1.5 * base + 4.0
+    for r in (0, 1):
+        assert list(got[r]["flags"]) == [False, True, False, True]
+        assert np.allclose(got[r]["w"], want)
+        assert np.allclose(got[r]["b"][:, :5], 0.5) and np.all(got[r]["b"][:, 5:] == 0.0)
+    assert np.array_equal(got[0]["w"], got[1]["w"])
+
+
+def test_parameter_averaging_argument_checks():
+    from kaldi_cnn_b200.dp import ParameterAveraging
+    with pytest.raises(ValueError):
+        ParameterAveraging([], None, 2, 1)
+    with pytest.raises(ValueError):
+        ParameterAveraging([], None, 1, 0)
+    one = ParameterAveraging([torch.ones(3)], None, 1, 1)
+    assert one.after_step() is True                          # world 1: nothing to exchange
