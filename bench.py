@@ -464,7 +464,9 @@ def run_ours(args):
 
         # ---- end to end through the C-ABI with HOST buffers (pinned), copies in the timed region
         e2e = None
-        if world == 1:
+        if args.no_e2e:
+            pass                                 # launch-list captures under ncu only
+        elif world == 1:
             hx = torch.randn(N, dim).pin_memory()
             hl = torch.randint(0, nout, (N,), dtype=torch.int32).pin_memory()
             hx_np, hl_np = hx.numpy(), hl.numpy()
@@ -610,6 +612,7 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu launch-list captures only)")
     ap.add_argument("--dp-reduce", default=os.environ.get("KCNN_BENCH_DP_REDUCE", "auto"),
                     choices=["auto", "p2p", "nvls", "nccl"],
                     help="gradient all-reduce of the data-parallel step: the library's NVLink peer-memory kernel "

@@ -633,7 +633,7 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
     unsigned tail_blocks = 0;
     if (b.want_bias && b.bias_dst) {
       tail = ColSumTail{bpart, prow, q.G, b.bias_dst, b.bias_alpha, b.bias_accumulate};
-      tail_blocks = ceil_div_u(q.G, 256);
+      tail_blocks = colsum_tail_blocks(q.G);
       b.bias_done = true;
     }
     if (b.sgd)
@@ -765,7 +765,7 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
     unsigned tail_blocks = 0;
     if (b.want_bias && b.bias_dst) {
       tail = ColSumTail{bpart, prow, q.G, b.bias_dst, b.bias_alpha, b.bias_accumulate};
-      tail_blocks = ceil_div_u(q.G, 256);
+      tail_blocks = colsum_tail_blocks(q.G);
       b.bias_done = true;
     }
     if (b.sgd)

@@ -121,6 +121,12 @@ __device__ __forceinline__ float block_reduce(float v, float *scratch, bool is_m
 
 // One block per row: max, exp-sum, normalise, floor at 1e-20
 // (SoftmaxComponent::Propagate, nnet2/nnet-component.cc:930-950).
+// kInRegs: rows of up to 256 x kSoftmaxRegs columns are read ONCE and stay in registers between
+// the three passes (all loads of a thread in flight together instead of three dependent sweeps
+// over global memory); the arithmetic and its order are those of the generic form, so the two
+// give identical bits.  Launched with 256 threads.
+constexpr int kSoftmaxRegs = 16;
+template <bool kInRegs>
 __global__ void __launch_bounds__(256)
 softmax_fprop_kernel(const float *__restrict__ in, int in_stride, float *__restrict__ out,
                      int out_stride, int cols) {
@@ -128,6 +134,38 @@ softmax_fprop_kernel(const float *__restrict__ in, int in_stride, float *__restr
   __shared__ float scratch[32];
   const float *x = in + (size_t)blockIdx.x * in_stride;
   float *y = out + (size_t)blockIdx.x * out_stride;
+  if (kInRegs) {
+    float v[kSoftmaxRegs];
+#pragma unroll
+    for (int k = 0; k < kSoftmaxRegs; k++) {
+      const int j = (int)threadIdx.x + k * 256;
+      v[k] = j < cols ? __ldg(x + j) : -INFINITY;
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kSoftmaxRegs; k++) m = fmaxf(m, v[k]);
+    m = block_reduce(m, scratch, true);
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSoftmaxRegs; k++) {
+      const int j = (int)threadIdx.x + k * 256;
+      if (j < cols) {
+        v[k] = expf(v[k] - m);
+        s += v[k];
+      }
+    }
+    s = block_reduce(s, scratch, false);
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int k = 0; k < kSoftmaxRegs; k++) {
+      const int j = (int)threadIdx.x + k * 256;
+      if (j < cols) {
+        const float r = v[k] * inv;
+        y[j] = r < 1e-20f ? 1e-20f : r;
+      }
+    }
+    return;
+  }
   float m = -INFINITY;
   for (int j = threadIdx.x; j < cols; j += blockDim.x) m = fmaxf(m, __ldg(x + j));
   m = block_reduce(m, scratch, true);
@@ -145,7 +183,8 @@ softmax_fprop_kernel(const float *__restrict__ in, int in_stride, float *__restr
   }
 }
 
-// in_deriv = y * (d - dot(y, d))   (SoftmaxComponent::Backprop, :952-1000)
+// in_deriv = y * (d - dot(y, d))   (SoftmaxComponent::Backprop, :952-1000); kInRegs as above.
+template <bool kInRegs>
 __global__ void __launch_bounds__(256)
 softmax_bprop_kernel(const float *__restrict__ ov, int ov_stride, const float *__restrict__ od,
                      int od_stride, float *__restrict__ id, int id_stride, int cols) {
@@ -154,6 +193,28 @@ softmax_bprop_kernel(const float *__restrict__ ov, int ov_stride, const float *_
   const float *y = ov + (size_t)blockIdx.x * ov_stride;
   const float *d = od + (size_t)blockIdx.x * od_stride;
   float *o = id + (size_t)blockIdx.x * id_stride;
+  if (kInRegs) {
+    float yv[kSoftmaxRegs], dv[kSoftmaxRegs];
+#pragma unroll
+    for (int k = 0; k < kSoftmaxRegs; k++) {
+      const int j = (int)threadIdx.x + k * 256;
+      yv[k] = j < cols ? __ldg(y + j) : 0.0f;
+      dv[k] = j < cols ? __ldg(d + j) : 0.0f;
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSoftmaxRegs; k++) {
+      const int j = (int)threadIdx.x + k * 256;
+      if (j < cols) s = fmaf(yv[k], dv[k], s);
+    }
+    s = block_reduce(s, scratch, false);
+#pragma unroll
+    for (int k = 0; k < kSoftmaxRegs; k++) {
+      const int j = (int)threadIdx.x + k * 256;
+      if (j < cols) o[j] = yv[k] * (dv[k] - s);
+    }
+    return;
+  }
   float s = 0.0f;
   for (int j = threadIdx.x; j < cols; j += blockDim.x) s = fmaf(__ldg(y + j), __ldg(d + j), s);
   s = block_reduce(s, scratch, false);
@@ -245,14 +306,21 @@ void cudaF_relu_bprop(cudaStream_t st, const float *ov, MatrixDim ovd, const flo
 void cudaF_softmax_fprop(cudaStream_t st, const float *in, MatrixDim id, float *out,
                          MatrixDim od) {
   if (od.rows == 0 || od.cols == 0) return;
-  KCNN_LAUNCH(softmax_fprop_kernel, od.rows, 256, 0, st, in, id.stride, out, od.stride, od.cols);
+  if (od.cols <= 256 * kSoftmaxRegs)
+    KCNN_LAUNCH(softmax_fprop_kernel<true>, od.rows, 256, 0, st, in, id.stride, out, od.stride, od.cols);
+  else
+    KCNN_LAUNCH(softmax_fprop_kernel<false>, od.rows, 256, 0, st, in, id.stride, out, od.stride, od.cols);
 }
 
 void cudaF_softmax_bprop(cudaStream_t st, const float *ov, MatrixDim ovd, const float *od,
                          MatrixDim odd, float *id, MatrixDim idd) {
   if (idd.rows == 0 || idd.cols == 0) return;
-  KCNN_LAUNCH(softmax_bprop_kernel, idd.rows, 256, 0, st, ov, ovd.stride, od, odd.stride, id,
-              idd.stride, idd.cols);
+  if (idd.cols <= 256 * kSoftmaxRegs)
+    KCNN_LAUNCH(softmax_bprop_kernel<true>, idd.rows, 256, 0, st, ov, ovd.stride, od, odd.stride, id,
+                idd.stride, idd.cols);
+  else
+    KCNN_LAUNCH(softmax_bprop_kernel<false>, idd.rows, 256, 0, st, ov, ovd.stride, od, odd.stride, id,
+                idd.stride, idd.cols);
 }
 
 void cudaF_xent_deriv(cudaStream_t st, const float *post, MatrixDim pd, const int *labels,
