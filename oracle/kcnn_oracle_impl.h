@@ -8,14 +8,23 @@
  * bench.py's cpu_baseline / --impl reference legs may call it.  The product
  * (kaldi-cnn_b200/) never links or loads it.
  *
- * Parity status: PARITY UNPINNED against reference outputs.  The reference is a
- * patch on Kaldi r4510 and cannot be compiled in this image (no Kaldi tree, no
- * BLAS headers), and it ships no golden vectors or known-answer
- * tests, so there is no oracle/_ref.  What pins this restatement
- * instead: the independent NumPy / einsum formulation of the same index
- * algebra (oracle/oracle_np.py, tests/test_oracle_einsum.py, <= 1e-12 in FP64,
- * both Backprop branches) and the committed fixtures generated from it
- * (tests/golden/, tests/test_golden.py).
+ * Parity status.
+ *   PINNED against outputs of the reference itself for the L0 rows of SURVEY 8(a)
+ *   (a2 AddMatRepVec, a3 FlipMat, a4 PaddingZero, a5 TpBlock, a6 TpInsideBlock,
+ *   a7 ModPermuteRow, a8 Maxpool_prop, a9 Maxpool_backprop): oracle/Makefile compiles
+ *   the reference's own CUDA kernels (src/cnslmat/cnsl-cu-kernels.cu, unmodified, from
+ *   /root/reference) into oracle/_ref/libcnsl_ref_kernels.so, and
+ *   tests/test_gpu_reference_kernels.py runs them on the GPU box: reference kernel ==
+ *   this oracle == the product, bit for bit.
+ *   PARITY UNPINNED for the rows that cross the SGEMM boundary (a1 Conv2D, a10-a12
+ *   ConvolutionComponent, a14 FullyConnectedComponent): that part of the reference is a
+ *   patch on Kaldi r4510 and cannot be compiled in this image (no Kaldi tree, no BLAS
+ *   headers), and it ships no golden vectors or known-answer tests
+ *   (SURVEY 4).  What pins the restatement there: the independent NumPy / einsum
+ *   formulation of the same index algebra (oracle/oracle_np.py,
+ *   tests/test_oracle_einsum.py, <= 1e-12 in FP64, both Backprop branches), the
+ *   reference's finite-difference method in FP64, and the committed fixtures
+ *   (tests/golden/, tests/test_golden.py).
  *
  * Every function cites the reference lines it follows
  * (paths relative to /root/reference/src).
