@@ -149,22 +149,13 @@ def c1_gpu(lines, N, math):
 
 
 def c1_cpu(lines, N, threads):
-    from oracle import oracle
-    from oracle.cpu_nnet import CpuNnet
-    used = oracle.set_num_threads(threads)
+    """C1 on the host cores, through bench.py's cpu_baseline leg (the one place outside tests/ that
+    runs the CPU port under oracle/)."""
+    import bench
     cfg = "\n".join(lines) + "\nSoftmaxComponent dim=1024\n"
-    net = CpuNnet(cfg, seed=42)
-    rng = np.random.default_rng(1)
-    x = rng.standard_normal((N, net.input_dim)).astype(np.float32)
-    lab = rng.integers(0, 1024, N)
-    net.train_step(x, lab)
-    t0 = time.perf_counter()
-    reps = 2
-    for _ in range(reps):
-        net.train_step(x, lab)
-    dt = (time.perf_counter() - t0) / reps
-    return {"ms_per_step": dt * 1e3, "frames_per_sec": N / dt, "cores": used, "kind": "port",
-            "note": "oracle step incl. a softmax / cross-entropy tail the GPU timing does not have"}
+    fps, sec, kind, used, how = bench.cpu_train_frames_per_sec(cfg, N, 2, 1, threads)
+    return {"ms_per_step": sec * 1e3, "frames_per_sec": fps, "cores": used, "kind": kind,
+            "note": "CPU port step incl. a softmax / cross-entropy tail the GPU timing does not have; " + how}
 
 
 def main():
