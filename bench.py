@@ -462,6 +462,11 @@ def run_ours(args):
         for c in updatable:
             param_checksum += float(net.component(c).params(0).double().abs().sum().item())
 
+        if peer is not None and peer.failed():
+            # a device-side barrier of the peer-memory reduction gave up waiting for a rank: the
+            # gradients of that step were incomplete -- no number is better than a wrong one
+            raise SystemExit("bench.py: rank %d: peer-memory all-reduce barrier timed out; result invalid" % rank)
+
         # ---- end to end through the C-ABI with HOST buffers (pinned), copies in the timed region
         e2e = None
         if args.no_e2e:
