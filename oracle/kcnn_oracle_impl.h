@@ -16,15 +16,19 @@
  *   /root/reference) into oracle/_ref/libcnsl_ref_kernels.so, and
  *   tests/test_gpu_reference_kernels.py runs them on the GPU box: reference kernel ==
  *   this oracle == the product, bit for bit.
- *   PARITY UNPINNED for the rows that cross the SGEMM boundary (a1 Conv2D, a10-a12
- *   ConvolutionComponent, a14 FullyConnectedComponent): that part of the reference is a
- *   patch on Kaldi r4510 and cannot be compiled in this image (no Kaldi tree, no BLAS
- *   headers), and it ships no golden vectors or known-answer tests
- *   (SURVEY 4).  What pins the restatement there: the independent NumPy / einsum
- *   formulation of the same index algebra (oracle/oracle_np.py,
- *   tests/test_oracle_einsum.py, <= 1e-12 in FP64, both Backprop branches), the
- *   reference's finite-difference method in FP64, and the committed fixtures
- *   (tests/golden/, tests/test_golden.py).
+ *   PINNED for the forward convolution (a1 Conv2D + a2 = a10 ConvolutionComponent::Propagate)
+ *   against the reference's GPU path rebuilt from its own kernels (span_row_to_convmat,
+ *   convmat_to_out, add_mat_rep_vec from oracle/_ref) and the cuBLAS SGEMM Kaldi's AddMatMat
+ *   calls: tests/ref_conv_check.py, test_reference_conv2d_chain (<= 1e-5).
+ *   PARITY UNPINNED for a11 / a12 (ConvolutionComponent Backprop / Update) and a14
+ *   (FullyConnectedComponent): the host code that chains the kernels there is a patch on
+ *   Kaldi r4510 and cannot be compiled in this image (no Kaldi tree, no BLAS headers;
+ *   SURVEY 8c), and it ships no golden vectors or known-answer tests.  What
+ *   pins the restatement there: the independent NumPy / einsum formulation of the same
+ *   index algebra (oracle/oracle_np.py, tests/test_oracle_einsum.py, <= 1e-12 in FP64,
+ *   both Backprop branches), the reference's finite-difference method in FP64 (gradients
+ *   against the pinned forward pass), and the committed fixtures (tests/golden/,
+ *   tests/test_golden.py).
  *
  * Every function cites the reference lines it follows
  * (paths relative to /root/reference/src).

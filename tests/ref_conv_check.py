@@ -16,6 +16,7 @@ the CPU oracle, and timed: this chain is "the reference recompiled for sm_100a",
 baseline the fused TMA / tcgen05 path replaces.
 """
 import ctypes
+import json
 import os
 import sys
 
@@ -67,44 +68,66 @@ def timed(fn, iters=20):
     return a.elapsed_time(b) / iters
 
 
-def main():
+def load_reference():
     if not os.path.exists(REF_SO):
-        raise SystemExit("build oracle/_ref first: make -C oracle ref (needs /root/reference)")
-    torch.backends.cuda.matmul.allow_tf32 = False
-    L = capi.lib()
+        return None
     R = ctypes.CDLL(REF_SO)
     for name, args in capi._PROTOS.items():
         if name.startswith("cudaF_") and hasattr(R, name) and args and args[0] is Dim3:
             getattr(R, name).argtypes = args
             getattr(R, name).restype = None
+    return R
+
+
+def check(cases, timing=False, oracle_dtype=np.float64):
+    """[(name, err reference-vs-oracle, err product FP32-vs-reference, err product TF32-vs-reference,
+    timings or None)], errors max-norm relative."""
+    L = capi.lib()
+    R = load_reference()
+    if R is None:
+        raise RuntimeError("build oracle/_ref first: make -C oracle ref (needs /root/reference)")
     from oracle import oracle as ora
     ora.build()
-    ok = True
-    for name, N, H, W, C, KH, KW, G in CASES:
-        rng = np.random.default_rng(1234)
-        x = rng.standard_normal((N, H * W * C)).astype(np.float32)
-        k = (rng.standard_normal((KH * KW * C, G)) * 0.05).astype(np.float32)
-        bias = rng.standard_normal(G).astype(np.float32)
-        xd, kd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(k).cuda(), torch.from_numpy(bias).cuda()
-        OH, OW = H - KH + 1, W - KW + 1
-        ref = reference_conv_propagate(R, xd, kd, bd, H, W, C, KH, KW, G)
-        torch.cuda.synchronize()
-        want = ora.conv_propagate(x, k, bias, H, W, C, 0, 0, KH, KW, G, dtype=np.float64)
-        scale = float(np.abs(want).max())
-        e_ref = float(np.abs(ref.cpu().numpy() - want).max()) / scale
-        line = "%-6s reference(GPU kernels + cuBLAS) vs oracle(f64) %.2e" % (name, e_ref)
-        ok = ok and e_ref <= 1e-5
-        for math, tol in ((0, 1e-5), (1, 1e-3)):
-            out = torch.empty(N, OH * OW * G, device="cuda")
-            call = lambda: L.cudaF_conv2d_fprop(stream(), math, ptr(xd), mdim(xd), ptr(kd), mdim(kd), ptr(bd),  # noqa: E731
-                                                ptr(out), mdim(out), H, W, C, 0, 0, KH, KW, G, 1)
-            call()
+    tf32_was = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False          # Kaldi's AddMatMat is cublasSgemm: plain FP32
+    rows = []
+    try:
+        for name, N, H, W, C, KH, KW, G in cases:
+            rng = np.random.default_rng(1234)
+            x = rng.standard_normal((N, H * W * C)).astype(np.float32)
+            k = (rng.standard_normal((KH * KW * C, G)) * 0.05).astype(np.float32)
+            bias = rng.standard_normal(G).astype(np.float32)
+            xd, kd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(k).cuda(), torch.from_numpy(bias).cuda()
+            OH, OW = H - KH + 1, W - KW + 1
+            ref = reference_conv_propagate(R, xd, kd, bd, H, W, C, KH, KW, G)
             torch.cuda.synchronize()
-            e = float((out - ref).abs().max()) / scale
-            ok = ok and e <= tol
-            line += " | product math=%d vs reference %.2e (%.1f us)" % (math, e, timed(call) * 1e3)
-        t_ref = timed(lambda: reference_conv_propagate(R, xd, kd, bd, H, W, C, KH, KW, G))
-        print(line + " | reference chain %.1f us" % (t_ref * 1e3), flush=True)
+            want = ora.conv_propagate(x, k, bias, H, W, C, 0, 0, KH, KW, G, dtype=oracle_dtype)
+            scale = float(np.abs(want).max())
+            e_ref = float(np.abs(ref.cpu().numpy().astype(np.float64) - want).max()) / scale
+            errs, times = [], {}
+            for math in (0, 1):
+                out = torch.empty(N, OH * OW * G, device="cuda")
+                call = lambda: L.cudaF_conv2d_fprop(stream(), math, ptr(xd), mdim(xd), ptr(kd), mdim(kd), ptr(bd),  # noqa: E731
+                                                    ptr(out), mdim(out), H, W, C, 0, 0, KH, KW, G, 1)
+                call()
+                torch.cuda.synchronize()
+                errs.append(float((out - ref).abs().max()) / scale)
+                if timing:
+                    times["product_math%d_us" % math] = timed(call) * 1e3
+            if timing:
+                times["reference_chain_us"] = timed(lambda: reference_conv_propagate(R, xd, kd, bd, H, W, C, KH, KW, G)) * 1e3
+            rows.append((name, e_ref, errs[0], errs[1], times if timing else None))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
+    return rows
+
+
+def main():
+    ok = True
+    for name, e_ref, e0, e1, times in check(CASES, timing=True):
+        ok = ok and e_ref <= 1e-5 and e0 <= 1e-5 and e1 <= 1e-3
+        print("%-6s reference(GPU kernels + cuBLAS) vs oracle(f64) %.2e | product FP32 vs reference %.2e | "
+              "product TF32 vs reference %.2e | %s" % (name, e_ref, e0, e1, json.dumps(times)), flush=True)
     print("ref_conv_check", "ok" if ok else "FAILED")
     sys.exit(0 if ok else 1)
 

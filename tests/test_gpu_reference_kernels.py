@@ -224,3 +224,17 @@ def test_reference_add_mat_rep_vec(ora, N, G, rep):
     r, o = both("cudaF_add_mat_rep_vec", dev_empty(N, G * rep), run)
     assert_bit_exact(r, want, "reference kernel vs oracle: add_mat_rep_vec")
     assert_bit_exact(o, r, "product vs reference kernel: add_mat_rep_vec")
+
+
+def test_reference_conv2d_chain(ora):
+    """Rows a1 / a10 (forward): the reference's GPU Conv2D rebuilt from ITS kernels -- span_row_to_convmat,
+    cuBLAS SGEMM (Kaldi's AddMatMat), convmat_to_out, AddMatRepVec (conv2D.cc:60-185,
+    nnet0/nnet-component-nnet0.cc:423-446) -- against the oracle and the product's fused
+    cudaF_conv2d_fprop in both math modes."""
+    ref_lib()
+    from tests.ref_conv_check import check
+    cases = [("C1a", 32, 40, 11, 3, 40, 4, 128), ("time", 16, 1, 14, 64, 1, 3, 128), ("2d", 8, 12, 9, 3, 5, 3, 64)]
+    for name, e_ref, e_fp32, e_tf32, _ in check(cases):
+        assert e_ref <= 1e-5, ("reference chain vs oracle", name, e_ref)
+        assert e_fp32 <= 1e-5, ("product FP32 vs reference chain", name, e_fp32)
+        assert e_tf32 <= 1e-3, ("product TF32 vs reference chain", name, e_tf32)
