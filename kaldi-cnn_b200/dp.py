@@ -242,12 +242,6 @@ class PipelinedDataParallelStep:
         off, ln = self.net.gradient_bucket(c)
         if self.world <= 1 or self.skip_reduce:
             return None
-        dbg = os.environ.get("KCNN_DP_DEBUG", "")          # timing diagnosis only (results are then wrong)
-        if (dbg == "fc_only" and c < self.late_from) or (dbg == "conv_only" and c >= self.late_from):
-            return None
-        if dbg == "nowait":
-            self._reduce_impl(c, off, ln)
-            return None
         return self._reduce_impl(c, off, ln)
 
     def _reduce_impl(self, c, off, ln):
