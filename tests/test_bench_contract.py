@@ -45,3 +45,24 @@ def test_product_arm_has_no_cpu_path():
     r = _run("--steps", "1", "--warmup", "0", "--no-cpu", "--no-kernels")
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_step_roofline_matches_the_committed_launch_list():
+    """tools/step_roofline.py's launch plan of the C2 step (76 launches) lines up with the committed
+    ncu launch list it documents, kernel family by kernel family."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "step_roofline.py")], capture_output=True,
+                       text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-1000:]
+    rows = [l for l in r.stdout.splitlines() if l.startswith("| ") and l.split("|")[1].strip().isdigit()]
+    assert len(rows) == 76
+    for l in rows:
+        cells = [c.strip() for c in l.split("|")]
+        label, kernel, bound = cells[2], cells[3], cells[6]
+        if bound == "tensor":
+            assert "tma_gemm" in kernel, l
+        if label.startswith("pack"):
+            assert "pack_channels_last" in kernel, l
+        if label.startswith("maxpool"):
+            assert "maxpool" in kernel, l
+        if "ReLU bwd" in label:
+            assert "relu_bprop" in kernel, l
