@@ -57,6 +57,28 @@ def reference_conv_propagate(R, x, kern, bias, H, W, C, KH, KW, G):
     return out
 
 
+def out_shape(op, rows, *a):
+    """Shape of the matrix each L0 member produces from a [rows x .] input (conv2D.cc asserts /
+    Resize calls); shared by RefOps (allocation) and the CPU flow test (checked against the oracle)."""
+    if op == "tp_block":                    # (C, bs):            [rows x C*bs] -> [C x rows*bs]
+        C, bs = a
+        return C, rows * bs
+    if op == "tp_inside_block":             # (G, bs):            [rows x G*bs] -> [rows*bs x G]
+        G, bs = a
+        return rows * bs, G
+    if op == "flip_mat":                    # (KH, KW, C, G):     [KH*KW*C x G] -> [KH*KW*G x C]
+        KH, KW, C, G = a
+        return KH * KW * G, C
+    if op == "pad_zero":                    # (H, W, C, KH, KW):  pads KH-1 / KW-1 per side
+        H, W, C, KH, KW = a
+        return rows, (H + 2 * (KH - 1)) * (W + 2 * (KW - 1)) * C
+    if op == "conv2d":                      # (H, W, C, KH, KW, G, concat)
+        H, W, C, KH, KW, G, concat = a
+        OH, OW = H - KH + 1, W - KW + 1
+        return (rows, OH * OW * G) if concat else (OH * OW * rows, G)
+    raise ValueError(op)
+
+
 class RefOps:
     """The reference's L0 kernels as matrix -> matrix functions on CUDA tensors (fresh contiguous
     outputs), with the launch shapes of conv2D.cc (16 x 16 threads over the output)."""
@@ -64,26 +86,30 @@ class RefOps:
     def __init__(self, R):
         self.R = R
 
+    @staticmethod
+    def _new(op, x, *a):
+        return torch.empty(*out_shape(op, x.shape[0], *a), device="cuda")
+
     def tp_block(self, x, C, bs):                       # conv2D.cc:348-386   out[c, n*bs+p] = x[n, c*bs+p]
-        out = torch.empty(C, x.shape[0] * bs, device="cuda")
+        out = self._new("tp_block", x, C, bs)
         g, b = grid(*out.shape)
         self.R.cudaF_tp_block(g, b, ptr(x), mdim(x), ptr(out), mdim(out), bs)
         return out
 
     def tp_inside_block(self, x, G, bs):                # :388-426            out[n*bs+p, g] = x[n, g*bs+p]
-        out = torch.empty(x.shape[0] * bs, G, device="cuda")
+        out = self._new("tp_inside_block", x, G, bs)
         g, b = grid(*out.shape)
         self.R.cudaF_tp_inside_block(g, b, ptr(x), mdim(x), ptr(out), mdim(out), bs)
         return out
 
     def flip_mat(self, k, KH, KW, C, G):                # :244-287            [KH*KW*C x G] -> [KH*KW*G x C]
-        out = torch.empty(KH * KW * G, C, device="cuda")
+        out = self._new("flip_mat", k, KH, KW, C, G)
         g, b = grid(*out.shape)
         self.R.cudaF_flip_mat(g, b, ptr(k), mdim(k), KH, KW, G, ptr(out), mdim(out))
         return out
 
     def pad_zero(self, x, H, W, C, KH, KW):             # :289-344            pads KH-1 / KW-1 per side
-        out = torch.empty(x.shape[0], (H + 2 * (KH - 1)) * (W + 2 * (KW - 1)) * C, device="cuda")
+        out = self._new("pad_zero", x, H, W, C, KH, KW)
         g, b = grid(*out.shape)
         self.R.cudaF_pad_zero(g, b, ptr(x), mdim(x), H, W, KH, KW, ptr(out), mdim(out))
         return out
@@ -103,7 +129,7 @@ class RefOps:
         conv = torch.mm(span, kern)
         if not concat:
             return conv
-        out = torch.empty(n, OH * OW * G, device="cuda")
+        out = self._new("conv2d", x, H, W, C, KH, KW, G, True)
         g, b = grid(*conv.shape)
         self.R.cudaF_convmat_to_out(g, b, ptr(conv), mdim(conv), ptr(out), mdim(out), OH, OW, n)
         return out

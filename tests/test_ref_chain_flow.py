@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.ref_conv_check import reference_conv_backprop, reference_conv_gradient
+from tests.ref_conv_check import out_shape, reference_conv_backprop, reference_conv_gradient
 
 
 class CpuOps:
@@ -20,23 +20,36 @@ class CpuOps:
     def _n(t):
         return np.ascontiguousarray(t.numpy())
 
+    def _chk(self, op, x, got, *a):
+        """The shape RefOps would allocate on the GPU for this call == what the oracle produced, and the
+        input is as wide as the member's assert demands (conv2D.cc:55-57, 247, 292, 353, 393)."""
+        assert tuple(got.shape) == tuple(out_shape(op, x.shape[0], *a)), (op, got.shape, a)
+        return torch.from_numpy(got)
+
     def tp_block(self, x, C, bs):
-        return torch.from_numpy(self.o.tp_block(self._n(x), C, bs))
+        assert x.shape[1] == C * bs
+        return self._chk("tp_block", x, self.o.tp_block(self._n(x), C, bs), C, bs)
 
     def tp_inside_block(self, x, G, bs):
-        return torch.from_numpy(self.o.tp_inside_block(self._n(x), G, bs))
+        assert x.shape[1] == G * bs
+        return self._chk("tp_inside_block", x, self.o.tp_inside_block(self._n(x), G, bs), G, bs)
 
     def flip_mat(self, k, KH, KW, C, G):
-        return torch.from_numpy(self.o.flip_mat(self._n(k), KH, KW, C, G))
+        assert tuple(k.shape) == (KH * KW * C, G)
+        return self._chk("flip_mat", k, self.o.flip_mat(self._n(k), KH, KW, C, G), KH, KW, C, G)
 
     def pad_zero(self, x, H, W, C, KH, KW):
-        return torch.from_numpy(self.o.pad_zero(self._n(x), H, W, C, KH, KW))
+        assert x.shape[1] == H * W * C
+        return self._chk("pad_zero", x, self.o.pad_zero(self._n(x), H, W, C, KH, KW), H, W, C, KH, KW)
 
     def mod_permute_row(self, x, C, bs):
+        assert x.shape[0] == C * bs
         return torch.from_numpy(self.o.mod_permute_row(self._n(x), C, bs))
 
     def conv2d(self, x, kern, H, W, C, KH, KW, G, concat):
-        return torch.from_numpy(self.o.conv2d(self._n(x), self._n(kern), H, W, C, KH, KW, G, concat=concat))
+        assert x.shape[1] == H * W * C and tuple(kern.shape) == (KH * KW * C, G)
+        return self._chk("conv2d", x, self.o.conv2d(self._n(x), self._n(kern), H, W, C, KH, KW, G, concat=concat),
+                         H, W, C, KH, KW, G, concat)
 
 
 # (N, H, W, C, ph, pw, KH, KW, G)
