@@ -260,3 +260,57 @@ def test_parameter_averaging_argument_checks():
         ParameterAveraging([], None, 1, 0)
     one = ParameterAveraging([torch.ones(3)], None, 1, 1)
     assert one.after_step() is True                          # world 1: nothing to exchange
+
+
+class _FakePeer:
+    """Stands in for dp.PeerMemoryAllReduce on CPU: same interface (arena, all_reduce(offset, length,
+    channel) -> handle with wait()), the reduction done by gloo on the arena slice."""
+
+    def __init__(self, arena):
+        self.arena = arena
+        self.calls = []
+
+    def all_reduce(self, offset, length, channel=0):
+        self.calls.append((int(offset), int(length), int(channel)))
+        return dist.all_reduce(self.arena[offset:offset + length], async_op=True)
+
+
+def _peer_worker(rank, world, port, n_global, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, e = shard_rows(n_global, rank, world)
+        net = OracleNet()
+        peer = _FakePeer(net.arena)
+        step = PipelinedDataParallelStep(net, net.arena, [0, 2], dist, world, late_from=2, peer=peer)
+        batches = [_data(n_global, seed=11 + i) for i in range(3)]
+        step.prime(batches[0][0][b:e], batches[0][1][b:e])
+        for x, y in batches[1:]:
+            step.rotate(x[b:e], y[b:e], n_global)
+        step.finish(n_global)
+        np.savez(os.path.join(out, "qrank%d.npz" % rank), k=net.k, kb=net.kb, w=net.w, wb=net.wb, kp=net.kp,
+                 calls=np.array(peer.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipelined_step_through_the_peer_memory_interface_world_2(tmp_path):
+    """The host glue of the NVLink path (PipelinedDataParallelStep(peer=...)): buckets are reduced
+    through peer.all_reduce(offset, length, channel) -- FC buckets on channel 0, convolution buckets
+    on channel 1 -- and the result is the plain step's."""
+    n = 12
+    ref = OracleNet()
+    single = DataParallelStep(ref, ref.arena, [0, 2], None, 1)
+    for i in range(3):
+        x, y = _data(n, seed=11 + i)
+        single(x, y, n)
+    mp.spawn(_peer_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(os.path.join(str(tmp_path), "qrank%d.npz" % r)) for r in (0, 1)]
+    for name, w in dict(k=ref.k, kb=ref.kb, w=ref.w, wb=ref.wb, kp=ref.kp).items():
+        for r in (0, 1):
+            assert np.abs(got[r][name] - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), (name, r)
+        assert np.array_equal(got[0][name], got[1][name])
+    fc_off, fc_len = ref.gradient_bucket(2)
+    cv_off, cv_len = ref.gradient_bucket(0)
+    calls = [tuple(c) for c in got[0]["calls"]]
+    assert calls == [(fc_off, fc_len, 0), (cv_off, cv_len, 1)] * 3          # issue order: top layer first, every batch
