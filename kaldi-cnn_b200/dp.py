@@ -60,8 +60,9 @@ class _Done:
 
 class PeerMemoryAllReduce:
     """Gradient arena in NVLink peer memory + the library's own all-reduce kernel
-    (csrc/cnslmat/kernels_p2p.cu, kcnn_p2p_allreduce_f32): two-shot, 128-bit peer loads and
-    stores, device-side flags -- no NCCL on the data path.  The arena is one symmetric
+    (csrc/cnslmat/kernels_p2p.cu): kcnn_p2p_allreduce_f32 -- two-shot, 128-bit peer loads and
+    stores -- or, with multicast=True, kcnn_p2p_allreduce_multicast_f32 -- the sum formed inside the
+    NVSwitch (multimem.ld_reduce / multimem.st); device-side flags, no NCCL on the data path.  The arena is one symmetric
     allocation (torch.distributed._symmetric_memory: cuMem handles exchanged through the
     process group) of `floats` gradient floats followed by the flag words.
 
