@@ -30,3 +30,36 @@ def test_reference_backprop_and_gradient_chains(ora):
         assert w_ref <= 1e-5, ("wgrad: reference chain vs oracle", name, w_ref)
         assert w_fp32 <= 1e-5, ("wgrad: product FP32 vs reference chain", name, w_fp32)
         assert w_tf32 <= 1e-3, ("wgrad: product TF32 vs reference chain", name, w_tf32)
+
+
+# (N, H, W, C, pc, mode): the overlap shapes of tests/test_gpu_l0_pool_permute.py; mode 1 = overlap
+# (stride-1 pooling across channels), 2 = overlap2D (channels as a 2-D map) -- SURVEY 8f-4
+OVERLAPS = [(16, 1, 8, 12, 3, 1), (8, 2, 3, 9, 4, 1), (16, 1, 8, 16, 2, 2), (8, 2, 2, 25, 3, 2)]
+
+
+@pytest.mark.parametrize("shape", OVERLAPS)
+def test_reference_overlap_maxpool_forward(ora, shape):
+    """Maxpool_prop with overlap / overlap2D (conv2D.cc:485-489, cnsl-cu-kernels.cu:310-350, 405-450): the
+    reference's forward kernels next to the oracle and the product, bit for bit.  (The reference's
+    overlap BACKWARD kernels race -- .cu:396-397, 497-498 -- and are not a usable checker.)"""
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built")
+    import numpy as np
+    import torch
+    from tests.gpu_util import dev, dev_empty, host, assert_bit_exact, mdim, ptr
+    from tests.test_gpu_reference_kernels import both
+    N, H, W, C, pc, mode = shape
+    x = np.maximum(np.random.default_rng(13).standard_normal((N, H * W * C)), 0).astype(np.float32)
+    y_ora = ora.maxpool_prop(x, H, W, 1, 1, pc, mode=mode)
+    xd = dev(x, 3, 0)
+    name = "cudaF_maxpoolchannel_overlap_prop" if mode == 1 else "cudaF_maxpoolchannel_overlap2D_prop"
+
+    def fwd(fn, gr, bl):
+        yd = dev_empty(N, y_ora.shape[1], 3, 0)
+        fn(gr, bl, ptr(xd), mdim(xd), ptr(yd), mdim(yd), H, W, 1, 1, pc)
+        torch.cuda.synchronize()
+        return host(yd)
+
+    y_ref, y_ours = both(name, dev_empty(N, y_ora.shape[1]), fwd)
+    assert_bit_exact(y_ref, y_ora, "reference kernel vs oracle: " + name)
+    assert_bit_exact(y_ours, y_ref, "product vs reference kernel: " + name)
