@@ -63,3 +63,44 @@ def test_reference_overlap_maxpool_forward(ora, shape):
     y_ref, y_ours = both(name, dev_empty(N, y_ora.shape[1]), fwd)
     assert_bit_exact(y_ref, y_ora, "reference kernel vs oracle: " + name)
     assert_bit_exact(y_ours, y_ref, "product vs reference kernel: " + name)
+
+
+def test_reference_padded_propagate_chain(ora):
+    """ConvolutionComponent::Propagate with in-pad-height / in-pad-width (nnet0/nnet-component-nnet0.cc:
+    430-435): PaddingZero(pad + 1) then Conv2D on the padded tensor, from the reference's kernels,
+    against the oracle and the product's fused forward (padding as TMA / index arithmetic)."""
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built")
+    import numpy as np
+    import torch
+    from kaldi_cnn_b200 import capi
+    from kaldi_cnn_b200.capi import mdim, ptr, stream
+    from tests.ref_conv_check import RefOps, load_reference, reference_conv_propagate
+    L = capi.lib()
+    R = load_reference()
+    ops = RefOps(R)
+    was = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for (N, H, W, C, ph, pw, KH, KW, G) in [(9, 6, 7, 5, 1, 2, 3, 4, 10), (16, 1, 14, 64, 0, 1, 1, 3, 128)]:
+            rng = np.random.default_rng(21)
+            x = rng.standard_normal((N, H * W * C)).astype(np.float32)
+            k = (rng.standard_normal((KH * KW * C, G)) * 0.05).astype(np.float32)
+            b = rng.standard_normal(G).astype(np.float32)
+            xd, kd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(k).cuda(), torch.from_numpy(b).cuda()
+            Hp, Wp = H + 2 * ph, W + 2 * pw
+            OH, OW = Hp - KH + 1, Wp - KW + 1
+            padded = ops.pad_zero(xd, H, W, C, ph + 1, pw + 1)
+            ref = reference_conv_propagate(R, padded, kd, bd, Hp, Wp, C, KH, KW, G)
+            torch.cuda.synchronize()
+            want = ora.conv_propagate(x, k, b, H, W, C, ph, pw, KH, KW, G, dtype=np.float64)
+            scale = float(np.abs(want).max())
+            assert float(np.abs(ref.cpu().numpy() - want).max()) / scale <= 1e-5
+            for math, tol in ((0, 1e-5), (1, 1e-3)):
+                out = torch.empty(N, OH * OW * G, device="cuda")
+                L.cudaF_conv2d_fprop(stream(), math, ptr(xd), mdim(xd), ptr(kd), mdim(kd), ptr(bd), ptr(out), mdim(out),
+                                     H, W, C, ph, pw, KH, KW, G, 1)
+                torch.cuda.synchronize()
+                assert float((out - ref).abs().max()) / scale <= tol, (math, N, H, W, C, ph, pw)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = was
