@@ -219,7 +219,8 @@ void cudaF_conv2d_dgrad(cudaStream_t st, int math, const float *out_deriv,
  * Replaces, in ConvolutionComponent::Update (:745-765, 775): PaddingZero +
  * TpBlock + TpInsideBlock + Conv2D(concat=false) + ModPermuteRow + AddRowSumMat.
  * workspace: device scratch of kcnn_conv2d_wgrad_workspace() bytes (split-K
- * partial sums), may be NULL when that returns 0. */
+ * partial sums of the generic kernels; the TMA path reduces its K-splits inside
+ * the kernel, through distributed shared memory), may be NULL when that returns 0. */
 void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value,
                         MatrixDim in_value_dim, const float *out_deriv,
                         MatrixDim out_deriv_dim, float *kernel_grad,
@@ -341,6 +342,123 @@ void cudaF_softmax_bprop(cudaStream_t st, const float *out_value, MatrixDim out_
 void cudaF_xent_deriv(cudaStream_t st, const float *post, MatrixDim post_dim,
                       const int *labels, float *deriv, MatrixDim deriv_dim,
                       double *objf_accum);
+
+/* ---- (4) the fused training step: channels-last activations ----------------------------
+ *
+ * Entry points of NnetMinibatchUpdater's fused step (csrc/nnet2/nnet-fused.cc).  Between the
+ * time-axis layers (in_height = kernel_height = 1) activations and derivatives are kept
+ * channels-last -- dense [N][W][C] floats, C fastest, 16-byte aligned -- which is the layout the
+ * convolution tensor maps read, so that what ConvolutionComponent::Propagate / Backprop / Update
+ * (nnet0/nnet-component-nnet0.cc:423-446, 461-544, 738-777) do with 5-9 permute / pad copies per
+ * layer, and round 1 did with one staging pack per operand, is tile addressing only.  All
+ * tensor-core (TF32) only; every function returns 1 when it launched and 0 when the shape or an
+ * alignment is not eligible (nothing launched: the caller falls back to the component path). */
+
+/* 1 when the shape is one the channels-last entry points below accept (channel counts that are
+ * multiples of 4, at least 8 input channels and 32 maps, widths up to 128; full-height: in_height a
+ * multiple of 4 and kernel_width * in_height a multiple of 32). */
+int kcnn_conv_time_shape_ok(int N, int W, int C, int pad_width, int kernel_width, int group);
+int kcnn_conv_full_shape_ok(int N, int in_height, int in_width, int in_channel, int kernel_width, int group);
+/* out[n][c*W + w] = in[n][w][c]: a channels-last activation copied back to the reference layout. */
+void cudaF_cl_to_ref(cudaStream_t st, const float *in, int N, int W, int C, float *out, int ldo);
+
+/* Forward of a time-axis layer.  x: [N][W][C].  out_cl != 0: out is [N][OW][G] (the next time-axis
+ * layer's input); else out is the reference matrix, rows [G][OW] with pitch ldo (what a following
+ * affine layer reads).  bias (may be NULL) and, with relu != 0, max(., 0) in the epilogue. */
+int cudaF_conv_time_fprop_cl(cudaStream_t st, const float *x, int N, int W, int C, int pad_width,
+                             int kernel_width, int group, const float *kernel, MatrixDim kernel_dim,
+                             const float *bias, float *out, int out_cl, int ldo, int relu);
+/* dx[N][W][C] = input gradient of dy[N][OW][G]; mask (may be NULL, [N][W][C]): dx = mask > 0 ? dx : 0,
+ * the backward pass of the ReLU that produced this layer's input. */
+int cudaF_conv_time_dgrad_cl(cudaStream_t st, const float *dy, int N, int W, int C, int pad_width,
+                             int kernel_width, int group, const float *kernel, MatrixDim kernel_dim,
+                             float *dx, const float *mask);
+/* Weight gradient from x[N][W][C] and dy[N][OW][G], K-splits reduced inside the kernel.
+ * apply != 0: the momentum / weight-decay step on (w = linear_params_, prev_grad) in the epilogue
+ * (nnet0/nnet-component-nnet0.cc:767-773), the gradient is never stored; else w receives dK. */
+int cudaF_conv_time_wgrad_cl(cudaStream_t st, const float *x, const float *dy, int N, int W, int C,
+                             int pad_width, int kernel_width, int group, float *w, MatrixDim w_dim,
+                             float *prev_grad, MatrixDim prev_grad_dim, int apply, float momentum,
+                             float decay_alpha, float grad_alpha);
+/* Full-height first layer (kernel_height = in_height, no padding): input in the reference layout,
+ * output / out_deriv channels-last [N][OW][G]. */
+int cudaF_conv_full_fprop_cl(cudaStream_t st, const float *in, MatrixDim in_dim, int in_height,
+                             int in_width, int in_channel, int kernel_width, int group,
+                             const float *kernel, MatrixDim kernel_dim, const float *bias, float *out,
+                             int relu);
+int cudaF_conv_full_dgrad_cl(cudaStream_t st, const float *dy, int num_rows, int in_height, int in_width,
+                             int in_channel, int kernel_width, int group, const float *kernel,
+                             MatrixDim kernel_dim, float *in_deriv, MatrixDim in_deriv_dim);
+int cudaF_conv_full_wgrad_cl(cudaStream_t st, const float *in, MatrixDim in_dim, const float *dy,
+                             int in_height, int in_width, int in_channel, int kernel_width, int group,
+                             float *w, MatrixDim w_dim, float *prev_grad, MatrixDim prev_grad_dim,
+                             int apply, float momentum, float decay_alpha, float grad_alpha);
+
+/* Affine forward with the two element-wise components that follow it in nnet.config in its epilogue:
+ * out = relu ? max(in W^T + b, 0) : in W^T + b; drop_out (may be NULL) = out .* scale, scale = low with
+ * probability dp else high, drawn from *seed_dev exactly as DropoutComponent::Propagate draws it
+ * (upstream nnet2/nnet-component.cc:3592-3620; the seed is advanced by cudaF_softmax_xent /
+ * cudaF_bump_seeds once the forward pass is over). */
+int cudaF_affine_fprop_fused(cudaStream_t st, const float *in, MatrixDim in_dim, const float *w,
+                             MatrixDim w_dim, const float *bias, float *out, MatrixDim out_dim, int relu,
+                             float *drop_out, MatrixDim drop_dim, float dp, float low, float high,
+                             const unsigned long long *seed_dev);
+/* Affine input gradient with the backward pass of the element-wise components that PRECEDE the layer:
+ *   relu_out only:        in_deriv = relu_out > 0 ? dY W : 0                       (:813-827)
+ *   relu_out + drop_out:  in_deriv = relu_out > 0 ? (dY W) * drop_out / relu_out : 0 (:3634-3636 then ReLU)
+ * perm_r > 0: the input of this layer is a time-axis activation with perm_r positions per map and
+ * in_deriv is written channels-last: logical column g*perm_r + pos goes to pos*(cols/perm_r) + g
+ * (in_deriv is then dense, in_deriv_dim.stride = cols).  The masks are indexed like the logical matrix. */
+int cudaF_affine_dgrad_fused(cudaStream_t st, const float *out_deriv, MatrixDim out_deriv_dim,
+                             const float *w, MatrixDim w_dim, float *in_deriv, MatrixDim in_deriv_dim,
+                             const float *relu_out, int relu_stride, const float *drop_out,
+                             int drop_stride, int perm_r);
+
+/* MaxpoolComponent on channels-last data (in_height = 1, plain mode): in [N][W][C] ->
+ * out [N][W/pw][C/pc], comparison order, sentinel and tie behaviour of _maxpool_prop /
+ * _maxpool_backprop (cnsl-cu-kernels.cu:231-308).  out_relu (may be NULL) additionally receives
+ * max(out, 0): the ReLU that follows the pool.  ref_ld > 0: out / out_relu are written (backward: out
+ * is read) in the reference layout, rows [c][w] with pitch ref_ld -- the pool feeds an affine layer;
+ * out_deriv and in_deriv are always channels-last.  Backward writes every element of in_deriv (the
+ * zero fill of nnet0/nnet-component-nnet0.cc:889 included); relu_gate != 0 multiplies by [in > 0],
+ * the backward pass of the ReLU that precedes the pool. */
+void cudaF_maxpool_prop_cl(cudaStream_t st, const float *in, int N, int W, int C, int pool_width_dim,
+                           int pool_channel_dim, float *out, float *out_relu, int ref_ld);
+void cudaF_maxpool_backprop_cl(cudaStream_t st, const float *in, const float *out, int ref_ld,
+                               const float *out_deriv, int N, int W, int C, int pool_width_dim,
+                               int pool_channel_dim, float *in_deriv, int relu_gate);
+
+/* Column sums of several matrices in one launch (deterministic, two-stage).  Per job:
+ *   KCNN_COLSUM_STORE        dst0[c]  = sum_r src[r][c]                     (float: a bias gradient)
+ *   KCNN_COLSUM_AXPY         dst0[c] += alpha * sum                         (float: bias += lr * db, :775 / :1137)
+ *   KCNN_COLSUM_STATS_RELU   dst0[c] += sum ; dst1[c] += #{src[r][c] > 0}   (double: NonlinearComponent::UpdateStats
+ *   KCNN_COLSUM_STATS_VALUE  dst0[c] += sum                                  of a ReLU / softmax, :337-363)
+ * perm_w > 0: src is a channels-last activation [rows][perm_w][perm_c] viewed as rows x (perm_w*perm_c)
+ * and column w*perm_c + ch is accumulated into element ch*perm_w + w (the reference's [c][w] order).
+ * scratch: kcnn_colsum_batch_scratch_bytes() bytes, zero-filled ONCE by the caller before first use. */
+#define KCNN_COLSUM_STORE 0
+#define KCNN_COLSUM_AXPY 1
+#define KCNN_COLSUM_STATS_RELU 2
+#define KCNN_COLSUM_STATS_VALUE 3
+typedef struct {
+  const float *src;
+  int rows, cols, ld;
+  int op;
+  int perm_w, perm_c;
+  void *dst0, *dst1;
+  float alpha;
+} KcnnColsumJob;
+size_t kcnn_colsum_batch_scratch_bytes(const KcnnColsumJob *jobs, int njobs);
+void cudaF_colsum_batch(cudaStream_t st, const KcnnColsumJob *jobs, int njobs, void *scratch);
+
+/* Softmax + cross-entropy objective / derivative + softmax backward in one kernel, bit-identical to
+ * cudaF_softmax_fprop -> cudaF_xent_deriv -> cudaF_softmax_bprop.  logits == NULL: post already holds
+ * the posteriors.  Also advances the num_seeds (<= 4) dropout seeds.  Returns 0 (nothing launched)
+ * for rows longer than 4096 columns. */
+int cudaF_softmax_xent(cudaStream_t st, const float *logits, MatrixDim logits_dim, float *post,
+                       MatrixDim post_dim, const int *labels, float *d_logits, MatrixDim d_dim,
+                       double *objf_accum, unsigned long long *const *seeds, int num_seeds);
+void cudaF_bump_seeds(cudaStream_t st, unsigned long long *const *seeds, int num_seeds);
 
 #ifdef __cplusplus
 }

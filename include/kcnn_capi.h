@@ -201,12 +201,16 @@ double kcnn_nnet_running_objf(kcnn_nnet *n);
  * second call with the same buffers / configuration and replayed from then on
  * (KCNN_NNET_GRAPH=0 keeps every step eager). */
 int kcnn_nnet_train_step(kcnn_nnet *n, const float *feats, int rows, int stride, const int *labels);
-/* Fusion of adjacent components in the forward pass ([Convolution | FullyConnected] + ReLU as
- * one launch); default on.  With fusion the pre-activation kcnn_nnet_activation(c + 1) of a
- * fused pair is not filled. */
+/* Fusion (default on): the fused plan when the model and math mode allow it, else
+ * [Convolution | FullyConnected] + ReLU as one launch.  With fusion the pre-activation
+ * kcnn_nnet_activation(c + 1) of a fused pair is not filled.  0 = component by component. */
 int kcnn_nnet_set_fusion(kcnn_nnet *n, int on);
 /* 1 when the most recent train step of this network was a graph replay, else 0. */
 int kcnn_nnet_last_step_replayed(const kcnn_nnet *n);
+/* 1 when the network's current configuration (model, rows, math mode) runs as the fused plan of
+ * csrc/nnet2/nnet-fused.cc (channels-last activations, element-wise components inside the GEMM
+ * epilogues), 0 when it runs component by component.  Valid after the first forward pass. */
+int kcnn_nnet_fused_active(const kcnn_nnet *n);
 
 /* ---- gradient all-reduce over NVLink peer memory (kernels_p2p.cu) ---------------------------
  * Replaces the reference's file-based nnet-am-average (egs/steps/nnet0/train_conv_dropout.sh:

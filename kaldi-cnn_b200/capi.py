@@ -91,7 +91,31 @@ _PROTOS = {
     "cudaF_softmax_fprop": [S, P, M, P, M],
     "cudaF_softmax_bprop": [S, P, M, P, M, P, M],
     "cudaF_xent_deriv": [S, P, M, P, P, M, P],
+    # fused training step: channels-last activations
+    "kcnn_conv_time_shape_ok": [I, I, I, I, I, I],
+    "kcnn_conv_full_shape_ok": [I, I, I, I, I, I],
+    "cudaF_cl_to_ref": [S, P, I, I, I, P, I],
+    "cudaF_conv_time_fprop_cl": [S, P, I, I, I, I, I, I, P, M, P, P, I, I, I],
+    "cudaF_conv_time_dgrad_cl": [S, P, I, I, I, I, I, I, P, M, P, P],
+    "cudaF_conv_time_wgrad_cl": [S, P, P, I, I, I, I, I, I, P, M, P, M, I, F, F, F],
+    "cudaF_conv_full_fprop_cl": [S, P, M, I, I, I, I, I, P, M, P, P, I],
+    "cudaF_conv_full_dgrad_cl": [S, P, I, I, I, I, I, I, P, M, P, M],
+    "cudaF_conv_full_wgrad_cl": [S, P, M, P, I, I, I, I, I, P, M, P, M, I, F, F, F],
+    "cudaF_affine_fprop_fused": [S, P, M, P, M, P, P, M, I, P, M, F, F, F, P],
+    "cudaF_affine_dgrad_fused": [S, P, M, P, M, P, M, P, I, P, I, I],
+    "cudaF_maxpool_prop_cl": [S, P, I, I, I, I, I, P, P, I],
+    "cudaF_maxpool_backprop_cl": [S, P, P, I, P, I, I, I, I, I, P, I],
+    "kcnn_colsum_batch_scratch_bytes": [P, I],
+    "cudaF_colsum_batch": [S, P, I, P],
+    "cudaF_softmax_xent": [S, P, M, P, M, P, P, M, P, P, I],
+    "cudaF_bump_seeds": [S, P, I],
 }
+
+
+class ColsumJob(ctypes.Structure):
+    """KcnnColsumJob of include/cnsl-cu-kernels.h"""
+    _fields_ = [("src", c_void_p), ("rows", c_int), ("cols", c_int), ("ld", c_int), ("op", c_int),
+                ("perm_w", c_int), ("perm_c", c_int), ("dst0", c_void_p), ("dst1", c_void_p), ("alpha", c_float)]
 _RESTYPES = {
     "kcnn_get_stream": c_void_p,
     "kcnn_launch_count": ctypes.c_ulonglong,
@@ -103,6 +127,18 @@ _RESTYPES = {
     "cudaF_conv2d_fprop_staged": c_int,
     "cudaF_conv2d_fprop_act": c_int,
     "cudaF_affine_wgrad_sgd": c_int,
+    "kcnn_conv_time_shape_ok": c_int,
+    "kcnn_conv_full_shape_ok": c_int,
+    "cudaF_conv_time_fprop_cl": c_int,
+    "cudaF_conv_time_dgrad_cl": c_int,
+    "cudaF_conv_time_wgrad_cl": c_int,
+    "cudaF_conv_full_fprop_cl": c_int,
+    "cudaF_conv_full_dgrad_cl": c_int,
+    "cudaF_conv_full_wgrad_cl": c_int,
+    "cudaF_affine_fprop_fused": c_int,
+    "cudaF_affine_dgrad_fused": c_int,
+    "kcnn_colsum_batch_scratch_bytes": c_size_t,
+    "cudaF_softmax_xent": c_int,
 }
 
 _lib = None

@@ -79,6 +79,7 @@ PROTOS = {
     "kcnn_nnet_running_objf": ([H], ctypes.c_double),
     "kcnn_nnet_last_step_replayed": ([H], c_int),
     "kcnn_nnet_set_fusion": ([H, I], c_int),
+    "kcnn_nnet_fused_active": ([H], c_int),
     "kcnn_p2p_flag_floats": ([], c_size_t),
     "kcnn_p2p_allreduce_f32": ([P, P, I, I, c_size_t, c_size_t, c_size_t, I], c_int),
     "kcnn_p2p_allreduce_multicast_f32": ([P, P, ctypes.c_ulonglong, I, I, c_size_t, c_size_t, c_size_t, I], c_int),

@@ -307,6 +307,11 @@ class Nnet:
     def last_step_replayed(self):
         return bool(_lib().kcnn_nnet_last_step_replayed(self.h))
 
+    @property
+    def fused_active(self):
+        """True when the step runs as the fused plan (csrc/nnet2/nnet-fused.cc); valid after a forward."""
+        return bool(_lib().kcnn_nnet_fused_active(self.h))
+
     # ---- data parallel -----------------------------------------------------------
     def gradient_floats(self):
         return int(_lib().kcnn_nnet_gradient_floats(self.h))

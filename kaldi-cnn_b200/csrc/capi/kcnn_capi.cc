@@ -645,4 +645,9 @@ int kcnn_nnet_last_step_replayed(const kcnn_nnet *n) {
   return (h->updater != NULL && h->updater->LastStepReplayed()) ? 1 : 0;
 }
 
+int kcnn_nnet_fused_active(const kcnn_nnet *n) {
+  const NnetHandle *h = N(n);
+  return (h->updater != NULL && h->updater->FusedActive()) ? 1 : 0;
+}
+
 }  // extern "C"

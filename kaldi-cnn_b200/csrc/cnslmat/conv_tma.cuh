@@ -154,18 +154,23 @@ inline void launch_pack(cudaStream_t st, const float *in, int ld, int N, int C, 
 
 // stage[(s*R + pos)][map] -> out[n0 + s][(col0 + map) * R + pos]: per sample ONE contiguous run of
 // maps * R floats (the reference's [map][pos] layout), written 512 bytes per warp instruction.
+// Only tile rows [rb, re) are written (the whole tile, or a cluster split-K slice).
 __device__ __forceinline__ void store_maps_transposed(const float *stage, int tid, int n0, int nb, int R,
                                                       int col0, int maps, int num_samples, float *out, int ldo,
-                                                      const float *bias, const FastDiv &div_r, bool relu = false) {
+                                                      const float *bias, const FastDiv &div_r, bool relu,
+                                                      int rb, int re) {
   const int total = maps * R;
   for (int s = 0; s < nb; s++) {
     const int n = n0 + s;
     if (n >= num_samples) break;
+    const int p0 = max(0, rb - s * R), p1 = min(R, re - s * R);
+    if (p0 >= p1) continue;
     float *orow = out + (size_t)n * ldo + (size_t)col0 * R;
     const float *srow = stage + s * R * PITCH;
     for (int idx = tid; idx < total; idx += 128) {
       uint32_t g, pos;
       div_r.divmod((uint32_t)idx, g, pos);
+      if ((int)pos < p0 || (int)pos >= p1) continue;
       float v = srow[pos * PITCH + g];
       if (bias) v += __ldg(bias + col0 + g);
       if (relu) v = v > 0.0f ? v : 0.0f;
@@ -177,15 +182,17 @@ __device__ __forceinline__ void store_maps_transposed(const float *stage, int ti
 // Rows of the GEMM are (sample, position) with R positions per sample and NB = 128 / R
 // samples per tile; the K-blocks walk taps t (outer) x 32-wide slices of the reduced
 // channel axis (inner).  kBMn: fprop (B = kernel as [k rows][g]) ; !kBMn: dgrad (B rows c).
-// kPartial: split-K -- blockIdx.z owns K-blocks [z*kb_per_split, ...) and writes its tile
-// rows to workspace[z][(n*R + pos)][map]; conv_rows_reduce_kernel sums the splits into the
-// reference layout.  Used when the tile grid alone would leave most SMs idle (conv5 / conv6 of
-// nnet.config: 32 - 64 tiles with 24 - 48 K-blocks each).
-template <bool kBMn_, bool kPartial = false>
+// blockIdx.z owns K-blocks [z*kb_per_split, ...): the splits of a tile are one cluster (gemm_tma.cuh,
+// kClusterK), used when the tile grid alone would leave most SMs idle (conv5 / conv6 of nnet.config:
+// 32 - 64 tiles with 24 - 48 K-blocks each).
+// Output layout: out_cl = 0 the reference's rows [map][R] (the tile is transposed on the way out: folds
+// _convmat_to_out / TpBlock); out_cl = 1 channels-last [N][R][maps], which IS the tile, row-major --
+// the layout the next convolution's tensor maps read, so activations and derivatives flow through a
+// stack of time-axis layers without any staging copy (NnetMinibatchUpdater's fused step).
+template <bool kBMn_>
 struct ConvRowsProb {
   static constexpr bool kAMn = false, kBMn = kBMn_;
-  int kb_per_split;        // kPartial
-  float *workspace;        // kPartial: [splits][num_samples * R][out_maps]
+  int kb_per_split;
   int num_samples;         // N
   int R;                   // positions per sample in the OUTPUT (OW for fprop, W for dgrad)
   int nb;                  // samples per tile
@@ -193,21 +200,17 @@ struct ConvRowsProb {
   int inner_blocks;        // ceil(reduced channels / 32)
   int a_w0, a_wstep;       // A position coordinate = a_w0 + a_wstep * t
   int out_maps;            // GEMM N: G (fprop) or C (dgrad)
-  float *out;              // [N][ldo], sample rows hold [map][R]
+  float *out;              // out_cl ? [N][R][out_maps] : [N][ldo] rows holding [map][R]
   int ldo;
-  const float *bias;       // per map or nullptr
-  int relu;                // rectify after the bias (RectifiedLinearComponent fused)
+  int out_cl;
+  RowsEpi epi;             // bias / ReLU (fprop), ReLU mask of the producer (dgrad)
   FastDiv div_inner, div_r;
 
   __device__ __forceinline__ void kb_range(int z, int &b, int &e) const {
     const int total = taps * inner_blocks;
-    if (kPartial) {
-      b = z * kb_per_split;
-      e = min(total, b + kb_per_split);
-      if (e < b) e = b;
-    } else {
-      b = 0; e = total;
-    }
+    b = z * kb_per_split;
+    e = min(total, b + kb_per_split);
+    if (e < b) e = b;
   }
   __device__ __forceinline__ uint32_t tx_bytes() const { return (uint32_t)(nb * R * 128 + B_STAGE_BYTES); }
   template <bool kPair>
@@ -225,86 +228,25 @@ struct ConvRowsProb {
       tma_load_3d<kPair>(b_addr, mb, i0, (int)t, col0, bar);
     }
   }
-  __device__ __forceinline__ void prefetch(int, int, int) const {}
+  __device__ __forceinline__ void prefetch(int tid, int mt, int nt) const {
+    if (out_cl && epi.mask_x != nullptr)
+      prefetch_tile_l2(tid, mt * nb * R, nt * BN, min(num_samples * R, (mt + 1) * nb * R), out_maps, epi.mask_x,
+                       epi.mask_x, epi.ld_mx, IdentityRow());
+  }
   template <int kRows>
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z, int rb, int re) const {
     const int col0 = nt * BN;
     if (col0 >= out_maps) return;
-    if (kPartial) {
-      const int M = num_samples * R, m0 = mt * nb * R;
+    if (out_cl) {
       SgdCoef none = {0.f, 0.f, 0.f};
-      store_rows<EPI_STORE, kRows>(stage, tid, m0, col0, min(M, m0 + nb * R), out_maps,
-                                   workspace + (size_t)z * M * out_maps, out_maps, nullptr, nullptr, none,
-                                   IdentityRow());
+      store_rows<EPI_STORE, kRows>(stage, tid, mt * nb * R, col0, num_samples * R, out_maps, out, ldo, nullptr, none,
+                                   IdentityRow(), rb, min(re, nb * R), epi);
     } else {
       store_maps_transposed(stage, tid, mt * nb, nb, R, col0, min(BN, out_maps - col0), num_samples, out, ldo,
-                            bias, div_r, relu != 0);
+                            epi.bias_n, div_r, epi.relu != 0, rb, re);
     }
   }
 };
-
-// out[n][g*R + pos] = sum_z ws[z][(n*R + pos)][g] (+ bias[g]); one thread per (row m, 4 maps).
-__global__ void __launch_bounds__(256)
-conv_rows_reduce_kernel(const float *__restrict__ ws, int splits, int M, int maps, int R, float *__restrict__ out,
-                        int ldo, const float *__restrict__ bias, FastDiv div_g4, FastDiv div_r, int relu) {
-  kcnn::pdl_prologue();
-  const int g4n = maps >> 2;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)M * g4n) return;
-  uint32_t m, g4, n, pos;
-  div_g4.divmod((uint32_t)t, m, g4);
-  div_r.divmod(m, n, pos);
-  const int g = (int)g4 << 2;
-  const size_t e = (size_t)m * maps + g;
-  float4 s = __ldg(reinterpret_cast<const float4 *>(ws + e));
-  for (int z = 1; z < splits; z++) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (size_t)z * M * maps + e));
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-  }
-  if (bias) { s.x += __ldg(bias + g); s.y += __ldg(bias + g + 1); s.z += __ldg(bias + g + 2); s.w += __ldg(bias + g + 3); }
-  if (relu) {
-    s.x = s.x > 0.0f ? s.x : 0.0f; s.y = s.y > 0.0f ? s.y : 0.0f;
-    s.z = s.z > 0.0f ? s.z : 0.0f; s.w = s.w > 0.0f ? s.w : 0.0f;
-  }
-  float *o = out + (size_t)n * ldo + (size_t)g * R + pos;
-  o[0] = s.x; o[R] = s.y; o[2 * R] = s.z; o[3 * R] = s.w;
-}
-
-// Split count for a fprop / dgrad tile grid (1 = no split).
-inline int conv_rows_splits(long long tiles, int num_kb, int maps) {
-  if ((maps & 3) != 0 || tiles > kNumSMs / 2 || num_kb < 16) return 1;
-  long long want = kNumSMs / tiles;
-  if (want > num_kb / 8) want = num_kb / 8;
-  if (want > 8) want = 8;
-  return (int)(want < 1 ? 1 : want);
-}
-
-// Launches one fprop / dgrad problem, split over K when that fills the machine.
-template <bool kBMn>
-inline bool launch_conv_rows(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, ConvRowsProb<kBMn> p,
-                             dim3 grid) {
-  const int num_kb = p.taps * p.inner_blocks;
-  int splits = conv_rows_splits((long long)grid.x * grid.y, num_kb, p.out_maps);
-  int per = (num_kb + splits - 1) / splits;
-  splits = (num_kb + per - 1) / per;
-  const int M = p.num_samples * p.R;
-  float *ws = splits > 1 ? scratch(SCRATCH_SPLITK_ROWS, (size_t)splits * M * p.out_maps * sizeof(float)) : nullptr;
-  if (splits <= 1 || !ws) {
-    p.kb_per_split = num_kb; p.workspace = nullptr;
-    launch_prob(st, ma, mb, p, grid, num_kb);
-    return true;
-  }
-  ConvRowsProb<kBMn, true> q;
-  q.num_samples = p.num_samples; q.R = p.R; q.nb = p.nb; q.taps = p.taps; q.inner_blocks = p.inner_blocks;
-  q.a_w0 = p.a_w0; q.a_wstep = p.a_wstep; q.out_maps = p.out_maps; q.out = p.out; q.ldo = p.ldo; q.bias = p.bias;
-  q.relu = p.relu;
-  q.div_inner = p.div_inner; q.div_r = p.div_r; q.kb_per_split = per; q.workspace = ws;
-  launch_prob(st, ma, mb, q, dim3(grid.x, grid.y, splits), per);
-  KCNN_LAUNCH(conv_rows_reduce_kernel, ceil_div_u((long long)M * (p.out_maps >> 2), 256), 256, 0, st, ws, splits, M,
-              p.out_maps, p.R, p.out, p.ldo, p.bias, FastDiv((uint32_t)(p.out_maps >> 2)), FastDiv((uint32_t)p.R),
-              p.relu);
-  return true;
-}
 
 // ------------------------------------------- full-height kernels (KH = H, OH = 1) --
 //
@@ -320,8 +262,8 @@ struct ConvFullFpropProb {
   int num_samples, OW, nb, ks, j_blocks, G;
   float *out;
   int ldo;
-  const float *bias;
-  int relu;
+  int out_cl;              // as ConvRowsProb
+  RowsEpi epi;
   FastDiv div_jb, div_ow;
 
   int total_kb;            // C * j_blocks
@@ -340,11 +282,17 @@ struct ConvFullFpropProb {
   }
   __device__ __forceinline__ void prefetch(int, int, int) const {}
   template <int kRows>
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z, int rb, int re) const {
     const int g0 = nt * BN;
     if (g0 >= G) return;
-    store_maps_transposed(stage, tid, mt * nb, nb, OW, g0, min(BN, G - g0), num_samples, out, ldo, bias, div_ow,
-                          relu != 0);
+    if (out_cl) {
+      SgdCoef none = {0.f, 0.f, 0.f};
+      store_rows<EPI_STORE, kRows>(stage, tid, mt * nb * OW, g0, num_samples * OW, G, out, ldo, nullptr, none,
+                                   IdentityRow(), rb, min(re, nb * OW), epi);
+    } else {
+      store_maps_transposed(stage, tid, mt * nb, nb, OW, g0, min(BN, G - g0), num_samples, out, ldo, epi.bias_n,
+                            div_ow, epi.relu != 0, rb, re);
+    }
   }
 };
 
@@ -373,7 +321,7 @@ struct ConvFullDgradProb {
   }
   __device__ __forceinline__ void prefetch(int, int, int) const {}
   template <int kRows>
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z, int, int) const {
     const int n0 = mt * nb, c0 = nt * nbc;
     const int chans = min(nbc, C - c0);
     const int hw = H * W;
@@ -409,6 +357,8 @@ struct KernelRow {
 
 // kFull: full-height kernels, A straight from the input through the 4-D window map, rows m in
 // kernel order c*ks + j (ks % 32 == 0); div_c then divides by ks.
+// kEpi = EPI_SGD: the momentum / weight-decay step runs on the (cluster-reduced) tile, the gradient
+// is never written; EPI_STORE: dK goes to `out` (data-parallel mode, gradient checks).
 template <int kEpi, bool kFull = false>
 struct ConvWgradProb {
   static constexpr bool kAMn = true, kBMn = true;
@@ -419,7 +369,6 @@ struct ConvWgradProb {
   int kb_per_split;
   float *out;              // kernel-shaped [C*KW][ldo]: row c*KW + kw
   int ldo;
-  float *workspace;        // [splits][M][G]
   float *aux;              // EPI_SGD: prev_grad (same shape as out)
   SgdCoef sgd;
   FastDiv div_nb, div_c;
@@ -458,16 +407,15 @@ struct ConvWgradProb {
     }
   }
   template <int kRows>
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z, int rb, int re) const {
     const int m0 = mt * BM, g0 = nt * BN;
-    if (kEpi == EPI_PARTIAL) {
-      store_rows<EPI_STORE, kRows>(stage, tid, m0, g0, M, G, workspace + (size_t)z * M * G, G, nullptr, nullptr,
-                                   sgd, IdentityRow());
-    } else if (kFull) {
-      store_rows<kEpi, kRows>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, IdentityRow());
+    RowsEpi none = {};
+    none.vec = 1;
+    if (kFull) {
+      store_rows<kEpi, kRows>(stage, tid, m0, g0, M, G, out, ldo, aux, sgd, IdentityRow(), rb, re, none);
     } else {
       KernelRow rm; rm.div_c = div_c; rm.KW = KW; rm.C = C;
-      store_rows<kEpi, kRows>(stage, tid, m0, g0, M, G, out, ldo, nullptr, aux, sgd, rm);
+      store_rows<kEpi, kRows>(stage, tid, m0, g0, M, G, out, ldo, aux, sgd, rm, rb, re, none);
     }
   }
 };
@@ -508,6 +456,124 @@ inline bool encode_act_map(CUtensorMap *map, const float *act, int N, int R, int
   return encode_map(map, act, 3, dims, str, box, mn_major);
 }
 
+// Where a forward / input-gradient GEMM puts its result.
+struct ConvOut {
+  float *out;
+  int ldo;                 // cl: unused (dense); else the row pitch of the reference-layout matrix
+  bool cl;                 // channels-last [N][R][maps] instead of rows [map][R]
+  const float *bias;       // per map or nullptr
+  bool relu;
+  const float *mask;       // cl only: same shape as out; out = mask > 0 ? out : 0 (the producer's ReLU backward)
+};
+
+template <bool kBMn>
+inline void launch_conv_rows(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, ConvRowsProb<kBMn> p,
+                             dim3 grid) {
+  const int num_kb = p.taps * p.inner_blocks;
+  int splits = pick_splits((long long)grid.x * grid.y, num_kb);
+  const int per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + per - 1) / per;
+  p.kb_per_split = per;
+  launch_prob(st, ma, mb, p, dim3(grid.x, grid.y, splits), per);
+}
+
+template <class Prob>
+inline void fill_conv_out(Prob &p, const ConvOut &o, int maps) {
+  p.out = o.out; p.out_cl = o.cl ? 1 : 0; p.ldo = o.cl ? maps : o.ldo;
+  p.epi = rows_epi_none();
+  p.epi.bias_n = o.bias; p.epi.relu = o.relu ? 1 : 0;
+  if (o.cl && o.mask) { p.epi.mask_x = o.mask; p.epi.ld_mx = maps; }
+  p.epi.vec = rows_epi_vec_ok(p.epi) ? 1 : 0;
+}
+
+// Y[(n,ow), g] = sum_{kw,c} xcl[n, ow+kw-pw, c] K[(c,kw), g]   from a channels-last input [N][W][C]
+inline bool conv_rows_fprop(cudaStream_t st, const ConvShape &q, const float *xcl, const float *kernel, int ld_k,
+                            const ConvOut &o) {
+  if (!conv_tma_shape_ok(q) || !host_aligned16(xcl)) return false;
+  if (o.cl && !host_aligned16(o.out)) return false;
+  const int nb = 128 / q.OW;
+  CUtensorMap ma, mb;
+  if (!encode_act_map(&ma, xcl, q.N, q.W, q.C, (unsigned)q.OW, (unsigned)nb, false)) return false;
+  if (!encode_kernel_map(&mb, kernel, ld_k, q.C, q.KW, q.G, 32, true)) return false;
+  ConvRowsProb<true> p;
+  p.num_samples = q.N; p.R = q.OW; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.C + 31) / 32;
+  p.a_w0 = -q.pw; p.a_wstep = 1; p.out_maps = q.G;
+  fill_conv_out(p, o, q.G);
+  p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.OW);
+  launch_conv_rows(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1));
+  return true;
+}
+
+// dX[(n,w), c] = sum_{kw,g} dycl[n, w+pw-kw, g] K[(c,kw), g]   from a channels-last out_deriv [N][OW][G]
+inline bool conv_rows_dgrad(cudaStream_t st, const ConvShape &q, const float *dycl, const float *kernel, int ld_k,
+                            const ConvOut &o) {
+  if (!conv_tma_shape_ok(q) || !host_aligned16(dycl)) return false;
+  if (o.cl && !host_aligned16(o.out)) return false;
+  const int nb = 128 / q.W;
+  CUtensorMap da, db;
+  if (!encode_act_map(&da, dycl, q.N, q.OW, q.G, (unsigned)q.W, (unsigned)nb, false)) return false;
+  if (!encode_kernel_map(&db, kernel, ld_k, q.C, q.KW, q.G, 128, false)) return false;
+  ConvRowsProb<false> p;
+  p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
+  p.a_w0 = q.pw; p.a_wstep = -1; p.out_maps = q.C;
+  fill_conv_out(p, o, q.C);
+  p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.W);
+  launch_conv_rows(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
+  return true;
+}
+
+// Where a weight-gradient GEMM puts its result: sgd != nullptr -> the momentum / weight-decay step on
+// (w = kernel, prev) in the epilogue, the gradient is never written; else w receives dK.
+struct ConvWgradOut {
+  float *w; int ld_w;
+  float *prev; int ld_p;
+  const SgdCoef *sgd;
+};
+inline bool conv_wgrad_out_ok(const ConvWgradOut &o) {
+  if ((o.ld_w & 3) != 0 || !host_aligned16(o.w)) return false;
+  if (o.sgd && (o.ld_p != o.ld_w || !host_aligned16(o.prev))) return false;
+  return true;
+}
+
+template <bool kFull>
+inline void launch_conv_wgrad(cudaStream_t st, const CUtensorMap &wa, const CUtensorMap &wb, const ConvWgradOut &o,
+                              int C, int KW, int G, int M, int pw, int N, int OW, uint32_t div_c) {
+  const int n_blocks = (N + 31) / 32;
+  const int total_kb = OW * n_blocks;
+  int splits = pick_splits((long long)ceil_div_u(M, BM) * ceil_div_u(G, BN), total_kb);
+  const int per = (total_kb + splits - 1) / splits;
+  splits = (total_kb + per - 1) / per;
+  dim3 grid(ceil_div_u(M, BM), ceil_div_u(G, BN), splits);
+  SgdCoef none = {0.f, 0.f, 0.f};
+  auto fill = [&](auto &p) {
+    p.C = C; p.KW = KW; p.G = G; p.M = M; p.pw = pw; p.n_blocks = n_blocks; p.total_kb = total_kb;
+    p.kb_per_split = per; p.out = o.w; p.ldo = o.ld_w; p.aux = o.prev;
+    p.sgd = o.sgd ? *o.sgd : none;
+    p.div_nb = FastDiv((uint32_t)n_blocks); p.div_c = FastDiv(div_c);
+  };
+  if (o.sgd) {
+    ConvWgradProb<EPI_SGD, kFull> p; fill(p);
+    launch_prob(st, wa, wb, p, grid, per);
+  } else {
+    ConvWgradProb<EPI_STORE, kFull> p; fill(p);
+    launch_prob(st, wa, wb, p, grid, per);
+  }
+}
+
+// dK[(c,kw), g] = sum_{ow,n} xcl[n, ow+kw-pw, c] dycl[n, ow, g]
+inline bool conv_rows_wgrad(cudaStream_t st, const ConvShape &q, const float *xcl, const float *dycl,
+                            const ConvWgradOut &o) {
+  if (!conv_tma_shape_ok(q) || !conv_wgrad_out_ok(o)) return false;
+  const int Cp = (q.C + 31) & ~31;
+  CUtensorMap wa, wb;
+  if (!encode_act_map(&wa, xcl, q.N, q.W, q.C, 1, 32, true)) return false;
+  if (!encode_act_map(&wb, dycl, q.N, q.OW, q.G, 1, 32, true)) return false;
+  launch_conv_wgrad<false>(st, wa, wb, o, q.C, q.KW, q.G, q.KW * Cp, q.pw, q.N, q.OW, (uint32_t)Cp);
+  return true;
+}
+
+// ---- the bare-component path: reference-layout matrices in and out, staging copies per call ----
+
 // staging (optional): caller-owned [N*W*C] floats that receive the channels-last copy of `in`
 // and stay valid after the call, so the matching Backprop can skip its own pack of in_value.
 inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int ld_in, const float *kernel,
@@ -516,28 +582,21 @@ inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int
   if (!conv_tma_shape_ok(q)) return false;
   float *xcl = staging ? staging : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
   if (!xcl || !host_aligned16(xcl)) return false;
-  const int nb = 128 / q.OW;
-  CUtensorMap ma, mb;
-  if (!encode_act_map(&ma, xcl, q.N, q.W, q.C, (unsigned)q.OW, (unsigned)nb, false)) return false;
-  if (!encode_kernel_map(&mb, kernel, ld_k, q.C, q.KW, q.G, 32, true)) return false;
+  CUtensorMap probe;                              // nothing may fail after the pack has been launched
+  if (!encode_kernel_map(&probe, kernel, ld_k, q.C, q.KW, q.G, 32, true)) return false;
   launch_pack(st, in, ld_in, q.N, q.C, q.W, xcl, nullptr);
-  ConvRowsProb<true> p;
-  p.num_samples = q.N; p.R = q.OW; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.C + 31) / 32;
-  p.a_w0 = -q.pw; p.a_wstep = 1; p.out_maps = q.G; p.out = out; p.ldo = ldo; p.bias = bias; p.relu = relu ? 1 : 0;
-  p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.OW);
-  launch_conv_rows(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1));
-  return true;
+  ConvOut o = {out, ldo, false, bias, relu, nullptr};
+  return conv_rows_fprop(st, q, xcl, kernel, ld_k, o);
 }
 
 // Everything ConvolutionComponent::Backprop needs (reference nnet0/nnet-component-nnet0.cc:
 // 461-544 + 738-777) from ONE channels-last copy of out_deriv and one of in_value:
 //   in_deriv (optional)            dgrad GEMM
-//   kernel gradient                wgrad GEMM, split-K
+//   kernel gradient                wgrad GEMM (cluster split-K)
 //   bias gradient                  column sums, first stage inside the out_deriv pack
 // With sgd != nullptr the weight step  prev = m prev + a_decay K + a_grad dK ; K += prev  runs in
-// the wgrad epilogue / split-K reduction on (kernel, prev) and the gradient is never
-// written; otherwise kernel_grad receives dK.  The bias partial sums are returned for the
-// caller's final column-sum stage.
+// the wgrad epilogue on (kernel, prev) and the gradient is never written; otherwise kernel_grad
+// receives dK.  The bias partial sums are returned for the caller's final column-sum stage.
 struct ConvBackward {
   const float *in_value; int ld_iv;
   const float *out_deriv; int ld_od;
@@ -548,22 +607,15 @@ struct ConvBackward {
   const SgdCoef *sgd;
   const float *staged_x;                  // optional: channels-last copy of in_value left by conv_fprop
   bool want_bias;
-  float *bias_dst;                        // optional: where the bias column sums go, so that the
-  float bias_alpha; int bias_accumulate;  //   split-K reduction launch can finish them too
-  float *bias_partial; int bias_rows;     // out: partial sums (bias_done == false: caller reduces)
-  bool bias_done;                         // out
+  float *bias_partial; int bias_rows;     // out: partial sums (the caller reduces them)
 };
 
 inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) {
   if (!conv_tma_shape_ok(q)) return false;
   const bool do_dgrad = b.in_deriv != nullptr;
   const bool do_wgrad = b.sgd != nullptr || b.kernel_grad != nullptr;
-  float *wout = b.sgd ? b.kernel : b.kernel_grad;
-  const int ld_w = b.sgd ? b.ld_k : b.ld_kg;
-  if (do_wgrad) {
-    if ((ld_w & 3) != 0 || !host_aligned16(wout)) return false;
-    if (b.sgd && (b.ld_p != b.ld_k || !host_aligned16(b.prev))) return false;
-  }
+  ConvWgradOut wo = {b.sgd ? b.kernel : b.kernel_grad, b.sgd ? b.ld_k : b.ld_kg, b.prev, b.ld_p, b.sgd};
+  if (do_wgrad && !conv_wgrad_out_ok(wo)) return false;
   float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float));
   const bool have_x = b.staged_x != nullptr && host_aligned16(b.staged_x);
   float *xcl = !do_wgrad ? nullptr
@@ -571,84 +623,26 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
                         : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
   const int prow = pack_partial_rows(q.N, q.OW);
   float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float)) : nullptr;
-  if (!dycl || (do_wgrad && !xcl) || (b.want_bias && !bpart)) return false;
-
-  const int Cp = (q.C + 31) & ~31;
-  const int M = q.KW * Cp;
-  const int n_blocks = (q.N + 31) / 32;
-  const int total_kb = q.OW * n_blocks;
-  int splits = 1, per = total_kb;
-  float *ws = nullptr;
-  CUtensorMap wa, wb, da, db;
-  if (do_wgrad) {
-    splits = pick_splits((long long)ceil_div_u(M, BM) * ceil_div_u(q.G, BN), total_kb);
-    per = (total_kb + splits - 1) / splits;
-    splits = (total_kb + per - 1) / per;
-    if (splits > 1) {
-      ws = scratch(SCRATCH_SPLITK, (size_t)splits * M * q.G * sizeof(float));
-      if (!ws) return false;
-    }
-    if (!encode_act_map(&wa, xcl, q.N, q.W, q.C, 1, 32, true)) return false;
-    if (!encode_act_map(&wb, dycl, q.N, q.OW, q.G, 1, 32, true)) return false;
-  }
-  const int nb = 128 / q.W;
-  if (do_dgrad) {
-    if (!encode_act_map(&da, dycl, q.N, q.OW, q.G, (unsigned)q.W, (unsigned)nb, false)) return false;
-    if (!encode_kernel_map(&db, b.kernel, b.ld_k, q.C, q.KW, q.G, 128, false)) return false;
-  }
+  if (!dycl || !host_aligned16(dycl) || (do_wgrad && (!xcl || !host_aligned16(xcl))) || (b.want_bias && !bpart))
+    return false;
+  CUtensorMap probe;
+  if (!encode_kernel_map(&probe, b.kernel ? b.kernel : wo.w, b.kernel ? b.ld_k : wo.ld_w, q.C, q.KW, q.G, 128, false))
+    return false;
   // ---- nothing can fail past this point
   launch_pack(st, b.out_deriv, b.ld_od, q.N, q.G, q.OW, dycl, bpart);
-  b.bias_partial = bpart; b.bias_rows = prow; b.bias_done = false;
-  // The input-gradient GEMM and the weight-gradient GEMM both read the staging copy just made
-  // and each fills well under half of the SMs: they run as two branches.  The kernel matrix is
-  // WRITTEN by the momentum step (the split-K reduction, or the EPI_SGD epilogue when there is
-  // no split), which therefore stays behind the join: dgrad must see the old weights.
-  ForkJoin fj(st, do_dgrad && do_wgrad && (splits > 1 || !b.sgd));
+  b.bias_partial = bpart; b.bias_rows = prow;
+  // Without the in-place SGD step (data-parallel mode) the input-gradient and the weight-gradient GEMM
+  // are independent readers of the staging copy: two branches.  With it the weight gradient WRITES the
+  // kernel matrix dgrad reads, so it runs behind dgrad.
+  ForkJoin fj(st, do_dgrad && do_wgrad && !b.sgd);
   cudaStream_t wst = fj.active() ? fj.side() : st;
   if (do_dgrad) {
-    ConvRowsProb<false> p;
-    p.num_samples = q.N; p.R = q.W; p.nb = nb; p.taps = q.KW; p.inner_blocks = (q.G + 31) / 32;
-    p.a_w0 = q.pw; p.a_wstep = -1; p.out_maps = q.C; p.out = b.in_deriv; p.ldo = b.ld_id; p.bias = nullptr; p.relu = 0;
-    p.div_inner = FastDiv((uint32_t)p.inner_blocks); p.div_r = FastDiv((uint32_t)q.W);
-    launch_conv_rows(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, BN), 1));
+    ConvOut o = {b.in_deriv, b.ld_id, false, nullptr, false, nullptr};
+    conv_rows_dgrad(st, q, dycl, b.kernel, b.ld_k, o);
   }
   if (!do_wgrad) return true;
   if (!have_x) launch_pack(wst, b.in_value, b.ld_iv, q.N, q.C, q.W, xcl, nullptr);
-  dim3 grid(ceil_div_u(M, BM), ceil_div_u(q.G, BN), splits);
-  SgdCoef none = {0.f, 0.f, 0.f};
-  auto fill = [&](auto &p) {
-    p.C = q.C; p.KW = q.KW; p.G = q.G; p.M = M; p.pw = q.pw; p.n_blocks = n_blocks; p.total_kb = total_kb;
-    p.kb_per_split = per; p.out = wout; p.ldo = ld_w; p.workspace = ws; p.aux = b.prev;
-    p.sgd = b.sgd ? *b.sgd : none;
-    p.div_nb = FastDiv((uint32_t)n_blocks); p.div_c = FastDiv((uint32_t)Cp);
-  };
-  KernelRow rm;
-  rm.div_c = FastDiv((uint32_t)Cp); rm.KW = q.KW; rm.C = q.C;
-  if (splits > 1) {
-    ConvWgradProb<EPI_PARTIAL> p; fill(p);
-    launch_prob(wst, wa, wb, p, grid, per);
-    fj.join();
-    const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
-    ColSumTail tail = {nullptr, 0, 0, nullptr, 0.f, 0};
-    unsigned tail_blocks = 0;
-    if (b.want_bias && b.bias_dst) {
-      tail = ColSumTail{bpart, prow, q.G, b.bias_dst, b.bias_alpha, b.bias_accumulate};
-      tail_blocks = colsum_tail_blocks(q.G);
-      b.bias_done = true;
-    }
-    if (b.sgd)
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, KernelRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
-                  wout, ld_w, nullptr, b.prev, *b.sgd, rm, tail, blocks, 0);
-    else
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, KernelRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
-                  wout, ld_w, nullptr, nullptr, none, rm, tail, blocks, 0);
-  } else if (b.sgd) {
-    ConvWgradProb<EPI_SGD> p; fill(p);
-    launch_prob(st, wa, wb, p, grid, per);
-  } else {
-    ConvWgradProb<EPI_STORE> p; fill(p);
-    launch_prob(wst, wa, wb, p, grid, per);
-  }
+  conv_rows_wgrad(wst, q, xcl, dycl, wo);
   return true;
 }
 
@@ -677,18 +671,52 @@ inline bool encode_window_map(CUtensorMap *map, const float *in, int ld, const C
 }
 
 inline bool conv_full_fprop(cudaStream_t st, const ConvFullShape &q, const float *in, int ld_in,
-                            const float *kernel, int ld_k, const float *bias, float *out, int ldo,
-                            bool relu = false) {
+                            const float *kernel, int ld_k, const ConvOut &o) {
   if (!conv_full_shape_ok(q)) return false;
+  if (o.cl && (!host_aligned16(o.out) || (q.G & 3) != 0)) return false;
   const int ks = q.KW * q.H, nb = 128 / q.OW;
   CUtensorMap ma, mb;
   if (!encode_window_map(&ma, in, ld_in, q, (unsigned)q.OW, (unsigned)nb, false)) return false;
   if (!encode_2d(&mb, Matrix{kernel, q.C * ks, q.G, ld_k}, 32, true)) return false;
   ConvFullFpropProb p;
   p.num_samples = q.N; p.OW = q.OW; p.nb = nb; p.ks = ks; p.j_blocks = (ks + 31) / 32; p.G = q.G;
-  p.total_kb = q.C * p.j_blocks; p.out = out; p.ldo = ldo; p.bias = bias; p.relu = relu ? 1 : 0;
+  p.total_kb = q.C * p.j_blocks;
+  fill_conv_out(p, o, q.G);
   p.div_jb = FastDiv((uint32_t)p.j_blocks); p.div_ow = FastDiv((uint32_t)q.OW);
   launch_prob(st, ma, mb, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.G, BN), 1), p.total_kb);
+  return true;
+}
+
+// in_deriv (reference layout) from a channels-last out_deriv [N][OW][G]
+inline bool conv_full_dgrad(cudaStream_t st, const ConvFullShape &q, const float *dycl, const float *kernel,
+                            int ld_k, float *in_deriv, int ld_id) {
+  if (!conv_full_shape_ok(q) || !host_aligned16(dycl)) return false;
+  const int ks = q.KW * q.H;
+  const int nb = 128 / q.W, nbc = 128 / q.H;
+  CUtensorMap da, db;
+  if (!encode_act_map(&da, dycl, q.N, q.OW, q.G, (unsigned)q.W, (unsigned)nb, false)) return false;
+  unsigned long long dims[3] = {(unsigned long long)q.G, (unsigned long long)ks, (unsigned long long)q.C};
+  unsigned long long str[2] = {(unsigned long long)ld_k * 4, (unsigned long long)ld_k * 4 * ks};
+  unsigned box[3] = {32, (unsigned)q.H, (unsigned)nbc};
+  if (!encode_map(&db, kernel, 3, dims, str, box, false)) return false;
+  ConvFullDgradProb p;
+  p.num_samples = q.N; p.W = q.W; p.H = q.H; p.C = q.C; p.nb = nb; p.nbc = nbc;
+  p.g_blocks = (q.G + 31) / 32; p.total_kb = q.KW * p.g_blocks; p.out = in_deriv; p.ldo = ld_id;
+  p.div_gb = FastDiv((uint32_t)p.g_blocks); p.div_h = FastDiv((uint32_t)q.H);
+  launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, nbc), 1), p.total_kb);
+  return true;
+}
+
+// kernel gradient from the input itself (4-D window map) and a channels-last out_deriv
+inline bool conv_full_wgrad(cudaStream_t st, const ConvFullShape &q, const float *in, int ld_in, const float *dycl,
+                            const ConvWgradOut &o) {
+  if (!conv_full_shape_ok(q) || !conv_wgrad_out_ok(o) || !host_aligned16(dycl)) return false;
+  const int ks = q.KW * q.H;
+  if ((ks & 31) != 0) return false;                         // M atoms must not straddle channels
+  CUtensorMap wa, wb;
+  if (!encode_window_map(&wa, in, ld_in, q, 1, 32, true)) return false;
+  if (!encode_act_map(&wb, dycl, q.N, q.OW, q.G, 1, 32, true)) return false;
+  launch_conv_wgrad<true>(st, wa, wb, o, q.C, q.KW, q.G, q.C * ks, 0, q.N, q.OW, (uint32_t)ks);
   return true;
 }
 
@@ -699,88 +727,27 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
   const int ks = q.KW * q.H;
   const bool do_dgrad = b.in_deriv != nullptr;
   const bool do_wgrad = b.sgd != nullptr || b.kernel_grad != nullptr;
-  float *wout = b.sgd ? b.kernel : b.kernel_grad;
-  const int ld_w = b.sgd ? b.ld_k : b.ld_kg;
-  if (do_wgrad) {
-    if ((ks & 31) != 0) return false;                       // M atoms must not straddle channels
-    if ((ld_w & 3) != 0 || !host_aligned16(wout)) return false;
-    if (b.sgd && (b.ld_p != b.ld_k || !host_aligned16(b.prev))) return false;
-  }
+  ConvWgradOut wo = {b.sgd ? b.kernel : b.kernel_grad, b.sgd ? b.ld_k : b.ld_kg, b.prev, b.ld_p, b.sgd};
+  if (do_wgrad && (!conv_wgrad_out_ok(wo) || (ks & 31) != 0)) return false;
   float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float));
   const int prow = pack_partial_rows(q.N, q.OW);
   float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float)) : nullptr;
-  if (!dycl || (b.want_bias && !bpart)) return false;
-  const int M = q.C * ks;
-  const int n_blocks = (q.N + 31) / 32;
-  const int total_kb = q.OW * n_blocks;
-  int splits = 1, per = total_kb;
-  float *ws = nullptr;
-  CUtensorMap wa, wb, da, db;
-  if (do_wgrad) {
-    splits = pick_splits((long long)ceil_div_u(M, BM) * ceil_div_u(q.G, BN), total_kb);
-    per = (total_kb + splits - 1) / splits;
-    splits = (total_kb + per - 1) / per;
-    if (splits > 1) {
-      ws = scratch(SCRATCH_SPLITK, (size_t)splits * M * q.G * sizeof(float));
-      if (!ws) return false;
-    }
-    if (!encode_window_map(&wa, b.in_value, b.ld_iv, q, 1, 32, true)) return false;
-    if (!encode_act_map(&wb, dycl, q.N, q.OW, q.G, 1, 32, true)) return false;
-  }
-  const int nb = 128 / q.W, nbc = 128 / q.H;
+  if (!dycl || !host_aligned16(dycl) || (b.want_bias && !bpart)) return false;
+  CUtensorMap probe;
+  if (do_wgrad && !encode_window_map(&probe, b.in_value, b.ld_iv, q, 1, 32, true)) return false;
   if (do_dgrad) {
-    if (!encode_act_map(&da, dycl, q.N, q.OW, q.G, (unsigned)q.W, (unsigned)nb, false)) return false;
     unsigned long long dims[3] = {(unsigned long long)q.G, (unsigned long long)ks, (unsigned long long)q.C};
     unsigned long long str[2] = {(unsigned long long)b.ld_k * 4, (unsigned long long)b.ld_k * 4 * ks};
-    unsigned box[3] = {32, (unsigned)q.H, (unsigned)nbc};
-    if (!encode_map(&db, b.kernel, 3, dims, str, box, false)) return false;
+    unsigned box[3] = {32, (unsigned)q.H, (unsigned)(128 / q.H)};
+    if (!encode_map(&probe, b.kernel, 3, dims, str, box, false)) return false;
   }
   // ---- nothing can fail past this point
   launch_pack(st, b.out_deriv, b.ld_od, q.N, q.G, q.OW, dycl, bpart);
-  b.bias_partial = bpart; b.bias_rows = prow; b.bias_done = false;
-  ForkJoin fj(st, do_dgrad && do_wgrad && (splits > 1 || !b.sgd));      // see conv_backward()
+  b.bias_partial = bpart; b.bias_rows = prow;
+  ForkJoin fj(st, do_dgrad && do_wgrad && !b.sgd);           // see conv_backward()
   cudaStream_t wst = fj.active() ? fj.side() : st;
-  if (do_dgrad) {
-    ConvFullDgradProb p;
-    p.num_samples = q.N; p.W = q.W; p.H = q.H; p.C = q.C; p.nb = nb; p.nbc = nbc;
-    p.g_blocks = (q.G + 31) / 32; p.total_kb = q.KW * p.g_blocks; p.out = b.in_deriv; p.ldo = b.ld_id;
-    p.div_gb = FastDiv((uint32_t)p.g_blocks); p.div_h = FastDiv((uint32_t)q.H);
-    launch_prob(st, da, db, p, dim3(ceil_div_u(q.N, nb), ceil_div_u(q.C, nbc), 1), p.total_kb);
-  }
-  if (!do_wgrad) return true;
-  dim3 grid(ceil_div_u(M, BM), ceil_div_u(q.G, BN), splits);
-  SgdCoef none = {0.f, 0.f, 0.f};
-  auto fill = [&](auto &p) {
-    p.C = q.C; p.KW = q.KW; p.G = q.G; p.M = M; p.pw = 0; p.n_blocks = n_blocks; p.total_kb = total_kb;
-    p.kb_per_split = per; p.out = wout; p.ldo = ld_w; p.workspace = ws; p.aux = b.prev;
-    p.sgd = b.sgd ? *b.sgd : none;
-    p.div_nb = FastDiv((uint32_t)n_blocks); p.div_c = FastDiv((uint32_t)ks);
-  };
-  if (splits > 1) {
-    ConvWgradProb<EPI_PARTIAL, true> p; fill(p);
-    launch_prob(wst, wa, wb, p, grid, per);
-    fj.join();
-    const unsigned blocks = ceil_div_u(((long long)M * q.G) >> 2, 256);
-    ColSumTail tail = {nullptr, 0, 0, nullptr, 0.f, 0};
-    unsigned tail_blocks = 0;
-    if (b.want_bias && b.bias_dst) {
-      tail = ColSumTail{bpart, prow, q.G, b.bias_dst, b.bias_alpha, b.bias_accumulate};
-      tail_blocks = colsum_tail_blocks(q.G);
-      b.bias_done = true;
-    }
-    if (b.sgd)
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M, q.G,
-                  wout, ld_w, nullptr, b.prev, *b.sgd, IdentityRow(), tail, blocks, 0);
-    else
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks + tail_blocks, 256, 0, st, ws, splits, M,
-                  q.G, wout, ld_w, nullptr, nullptr, none, IdentityRow(), tail, blocks, 0);
-  } else if (b.sgd) {
-    ConvWgradProb<EPI_SGD, true> p; fill(p);
-    launch_prob(st, wa, wb, p, grid, per);
-  } else {
-    ConvWgradProb<EPI_STORE, true> p; fill(p);
-    launch_prob(wst, wa, wb, p, grid, per);
-  }
+  if (do_dgrad) conv_full_dgrad(st, q, dycl, b.kernel, b.ld_k, b.in_deriv, b.ld_id);
+  if (do_wgrad) conv_full_wgrad(wst, q, b.in_value, b.ld_iv, dycl, wo);
   return true;
 }
 

@@ -155,9 +155,29 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ void cluster_sync_all() {
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  cluster_arrive();
+  cluster_wait();
+}
+// 128-bit load from the shared memory of a CTA of this cluster (address from mapa)
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(cluster_addr)
+               : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
@@ -186,10 +206,20 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <class Prob, bool kPair, int STAGES>
+//
+// kClusterK: split-K WITHOUT a workspace or a second launch.  The gridDim.z K-splits of one
+// output tile form a thread-block cluster (1, 1, S): every CTA accumulates its K range in TMEM
+// and drains it to its staging tile as usual; after a cluster barrier CTA z sums rows
+// [z * 128/S, (z+1) * 128/S) of all S staging tiles through distributed shared memory, in split
+// order 0..S-1 (the summation order of the former splitk_reduce_kernel: same bits), and runs the
+// problem's epilogue -- bias / ReLU / mask, transposed store, or the momentum SGD step -- on just
+// those rows.  The reduction is spread over the S CTAs and costs ~1 us (DSMEM ~20 B/clk/SM)
+// instead of a 7-16 us launch that re-reads S partial tiles from L2.
+template <class Prob, bool kPair, int STAGES, bool kClusterK = false>
 __global__ void __launch_bounds__(THREADS, STAGES <= 2 ? 3 : (STAGES <= 3 ? 2 : 1))
 tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const Prob prob) {
+  static_assert(!(kPair && kClusterK), "cluster split-K uses one CTA per tile");
   kcnn::pdl_trigger();
   constexpr int kCols = kPair ? 2 * BN : BN;        // TMEM columns = accumulator columns per CTA
   constexpr int BAR_OFFSET = Ring<STAGES>::BAR_OFFSET;
@@ -308,10 +338,41 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      prob.template store<8>(stage, tid, mt, kPair ? 2 * (int)blockIdx.y + h : (int)blockIdx.y, (int)blockIdx.z);
-      if (h + 1 < kCols / BN) asm volatile("bar.sync 1, 128;" ::: "memory");     // staging is reused
+      if (!kClusterK) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        prob.template store<8>(stage, tid, mt, kPair ? 2 * (int)blockIdx.y + h : (int)blockIdx.y, (int)blockIdx.z,
+                               0, BM);
+        if (h + 1 < kCols / BN) asm volatile("bar.sync 1, 128;" ::: "memory");     // staging is reused
+      }
     }
+  }
+
+  if (kClusterK) {
+    cluster_sync_all();                          // every split's partial tile sits in its CTA's staging buffer
+    const int S = (int)cluster_nctarank(), me = (int)cluster_ctarank();
+    const int rp = (BM + S - 1) / S;
+    const int rb = min(BM, me * rp), re = min(BM, rb + rp);
+    if (warp >= 2) {
+      float *stage = reinterpret_cast<float *>(smem_gen);
+      const int wl = (t - 64) >> 5;
+      for (int r = rb + wl; r < re; r += 4) {
+        float *mine = stage + r * PITCH + 4 * lane;
+        const uint32_t a = smem_u32(mine);
+        float4 v[8];
+#pragma unroll
+        for (int z = 0; z < 8; z++)
+          if (z < S) v[z] = ld_dsmem_v4(map_to_cta(a, (uint32_t)z));
+        float4 s = v[0];
+#pragma unroll
+        for (int z = 1; z < 8; z++)
+          if (z < S) { s.x += v[z].x; s.y += v[z].y; s.z += v[z].z; s.w += v[z].w; }
+        *reinterpret_cast<float4 *>(mine) = s;    // rows [rb, re) of MY buffer are read by nobody else
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    cluster_arrive();                            // this CTA no longer reads its peers' shared memory
+    if (warp >= 2)
+      prob.template store<8>(reinterpret_cast<float *>(smem_gen), t - 64, mt, (int)blockIdx.y, 0, rb, re);
   }
 
   tc_fence_before();
@@ -325,6 +386,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kCols)
                    : "memory");
   }
+  if (kClusterK) cluster_wait();                 // my staging buffer stays alive until every peer has read it
 }
 
 // ---- persistent variant ------------------------------------------------------------------
@@ -474,7 +536,7 @@ tma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
       tc_fence_before();
       mbar_arrive_local(acc_empty(buf));                           // TMEM buffer may be overwritten
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      prob.template store<16>(stage, tid, mt, nt, z);
+      prob.template store<16>(stage, tid, mt, nt, z, 0, BM);
     }
   }
 
@@ -491,8 +553,7 @@ tma_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
 
 // What the epilogue does with the accumulator tile.
 enum EpiMode {
-  EPI_STORE = 0,      // out = acc (+ bias_n)
-  EPI_PARTIAL = 1,    // workspace[z] = acc           (split-K)
+  EPI_STORE = 0,      // out = acc (+ bias_n) (ReLU / mask / dropout: RowsEpi)
   EPI_SGD = 2,        // prev = m prev - lr wd W + lr acc ; W += prev   (out = W, aux = prev)
 };
 
@@ -508,38 +569,67 @@ __device__ __forceinline__ void sgd_apply(float &w, float &p, float g, const Sgd
   w = w + p;
 }
 
-// Row-major 128-column segment store shared by the dense and the weight-gradient
-// problems: tid -> (row group, 4 columns); each warp instruction writes one 512-byte
-// row segment.  row_of(m) maps a tile row to the output row; a negative result marks a padding
-// row of the GEMM that has no output row (skipped).
+// Element-wise work fused into a row-major EPI_STORE epilogue (all optional):
+//   forward   out = relu?(acc + bias_n) ; out2 = out .* dropout-scale(seed, row, col)
+//             (RectifiedLinearComponent + DropoutComponent::Propagate, upstream nnet2/nnet-component.cc:
+//             799-806, 3592-3620, applied where the pre-activation is still in shared memory)
+//   backward  out = mask_x > 0 ? acc : 0                      (ReLU backward of the PRODUCER, :813-827)
+//             out = mask_x > 0 ? acc * mask_y / mask_x : 0    (dropout backward :3634-3636, then ReLU backward)
+//   layout    perm_r > 0: column n = g * perm_r + pos of the logical matrix (the reference's [map][pos]
+//             order) is written to column pos * perm_g + g (channels-last [pos][map])
+struct RowsEpi {
+  const float *bias_n;
+  int relu;
+  const float *mask_x; int ld_mx;
+  const float *mask_y; int ld_my;
+  float *out2; int ld_o2;
+  float dp, low, high;
+  const unsigned long long *seed;
+  int perm_r, perm_g;
+  FastDiv div_r;
+  int vec;               // host: every pointer above is 16-byte aligned with pitches % 4 == 0
+};
+inline RowsEpi rows_epi_none() {
+  RowsEpi e;
+  e.bias_n = nullptr; e.relu = 0; e.mask_x = nullptr; e.ld_mx = 0; e.mask_y = nullptr; e.ld_my = 0;
+  e.out2 = nullptr; e.ld_o2 = 0; e.dp = 0.f; e.low = 0.f; e.high = 0.f; e.seed = nullptr;
+  e.perm_r = 0; e.perm_g = 0; e.div_r = FastDiv(1); e.vec = 1;
+  return e;
+}
+inline bool rows_epi_vec_ok(const RowsEpi &e) {
+  if (e.mask_x && (!host_aligned16(e.mask_x) || (e.ld_mx & 3))) return false;
+  if (e.mask_y && (!host_aligned16(e.mask_y) || (e.ld_my & 3))) return false;
+  if (e.out2 && (!host_aligned16(e.out2) || (e.ld_o2 & 3))) return false;
+  return true;
+}
+
+// Row-major 128-column segment store shared by the dense, the channels-last convolution and the
+// weight-gradient problems: tid -> (warp, 4 columns); each warp instruction writes one 512-byte
+// row segment.  Tile rows [rb, re) are stored (the whole tile, or this CTA's slice of a cluster
+// split-K reduction), warp w taking rows rb + w, rb + w + 4, ...  row_of(m) maps a tile row to
+// the output row; a negative result marks a padding row of the GEMM that has no output row.
 template <int kEpi, int kRows, class RowMap>
 __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, int n0, int M, int N,
-                                           float *obase, int ld, const float *bias_n, float *aux,
-                                           const SgdCoef &sgd, RowMap row_of, bool relu = false) {
+                                           float *obase, int ld, float *aux, const SgdCoef &sgd, RowMap row_of,
+                                           int rb, int re, const RowsEpi &e) {
   const int wl = tid >> 5, lane = tid & 31;
   const int n = n0 + 4 * lane;
+  if (re > M - m0) re = M - m0;
   const bool vec_ok = (n + 3 < N) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15u) == 0);
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (kEpi == EPI_STORE && bias_n) {
-    if (n < N) bias4.x = __ldg(bias_n + n);
-    if (n + 1 < N) bias4.y = __ldg(bias_n + n + 1);
-    if (n + 2 < N) bias4.z = __ldg(bias_n + n + 2);
-    if (n + 3 < N) bias4.w = __ldg(bias_n + n + 3);
-  }
   if (kEpi == EPI_SGD && vec_ok) {
     // nnet0/nnet-component-nnet0.cc:767-773, 1138-1142 on the tile: W and prev_grad rows are
     // read in batches of kRows rows (2 kRows independent 128-bit loads per thread in flight; the
     // lines were L2-prefetched by Problem::prefetch while the main loop ran), updated, written back.
     constexpr int RB = kRows;
 #pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += RB) {
+    for (int r0 = rb + wl; r0 < re; r0 += 4 * RB) {
       float4 w[RB], pv[RB];
       size_t roff[RB];
       bool okr[RB];
 #pragma unroll
       for (int i = 0; i < RB; i++) {
-        const int mt = wl * 32 + r0 + i;
-        const int row = m0 + mt < M ? row_of(m0 + mt) : -1;
+        const int mt = r0 + 4 * i;
+        const int row = mt < re ? row_of(m0 + mt) : -1;
         okr[i] = row >= 0;
         roff[i] = (size_t)(okr[i] ? row : 0) * ld + n;
         if (okr[i]) {
@@ -549,7 +639,7 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
       }
 #pragma unroll
       for (int i = 0; i < RB; i++) {
-        const int mt = wl * 32 + r0 + i;
+        const int mt = r0 + 4 * i;
         if (!okr[i]) continue;
         const float4 a = *reinterpret_cast<const float4 *>(stage + mt * PITCH + 4 * lane);
         sgd_apply(w[i].x, pv[i].x, a.x, sgd); sgd_apply(w[i].y, pv[i].y, a.y, sgd);
@@ -560,10 +650,81 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
     }
     return;
   }
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kEpi == EPI_STORE && e.bias_n) {
+    if (n < N) bias4.x = __ldg(e.bias_n + n);
+    if (n + 1 < N) bias4.y = __ldg(e.bias_n + n + 1);
+    if (n + 2 < N) bias4.z = __ldg(e.bias_n + n + 2);
+    if (n + 3 < N) bias4.w = __ldg(e.bias_n + n + 3);
+  }
+  if (kEpi == EPI_STORE && vec_ok && e.mask_x == nullptr && e.out2 == nullptr && e.perm_r == 0) {
+    // the common case (bias / ReLU only) as a tight loop of independent 128-bit moves
+#pragma unroll 8
+    for (int mt = rb + wl; mt < re; mt += 4) {
+      const int row = row_of(m0 + mt);
+      if (row < 0) continue;
+      float4 a = *reinterpret_cast<const float4 *>(stage + mt * PITCH + 4 * lane);
+      a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+      if (e.relu) {
+        a.x = a.x > 0.0f ? a.x : 0.0f; a.y = a.y > 0.0f ? a.y : 0.0f;
+        a.z = a.z > 0.0f ? a.z : 0.0f; a.w = a.w > 0.0f ? a.w : 0.0f;
+      }
+      *reinterpret_cast<float4 *>(obase + (size_t)row * ld + n) = a;
+    }
+    return;
+  }
+  const bool evec = vec_ok && e.vec != 0;
+  if (kEpi == EPI_STORE && evec && e.mask_x != nullptr && e.out2 == nullptr) {
+    // Backward gates: the mask rows come from global memory.  The compiler may not move a load
+    // above the previous row's store (possible aliasing), which left ONE row of loads in flight per
+    // warp -- 32 dependent DRAM / L2 round trips per tile.  So: all loads of kRows rows first (2 kRows
+    // independent 128-bit loads per thread), then the arithmetic and the stores.
+    constexpr int RB = kRows;
+    const bool has_y = e.mask_y != nullptr;
+#pragma unroll 1
+    for (int r0 = rb + wl; r0 < re; r0 += 4 * RB) {
+      float4 x[RB], y[RB];
+      int rw[RB];
+#pragma unroll
+      for (int i = 0; i < RB; i++) {
+        const int mt = r0 + 4 * i;
+        rw[i] = mt < re ? row_of(m0 + mt) : -1;
+        if (rw[i] >= 0) {
+          x[i] = __ldg(reinterpret_cast<const float4 *>(e.mask_x + (size_t)rw[i] * e.ld_mx + n));
+          if (has_y) y[i] = __ldg(reinterpret_cast<const float4 *>(e.mask_y + (size_t)rw[i] * e.ld_my + n));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RB; i++) {
+        if (rw[i] < 0) continue;
+        float4 a = *reinterpret_cast<const float4 *>(stage + (r0 + 4 * i) * PITCH + 4 * lane);
+        a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+        if (has_y) {       // d * y / x, the order of dropout_bprop_kernel, then the ReLU gate
+          a.x = x[i].x > 0.0f ? a.x * y[i].x / x[i].x : 0.0f; a.y = x[i].y > 0.0f ? a.y * y[i].y / x[i].y : 0.0f;
+          a.z = x[i].z > 0.0f ? a.z * y[i].z / x[i].z : 0.0f; a.w = x[i].w > 0.0f ? a.w * y[i].w / x[i].w : 0.0f;
+        } else {
+          a.x = x[i].x > 0.0f ? a.x : 0.0f; a.y = x[i].y > 0.0f ? a.y : 0.0f;
+          a.z = x[i].z > 0.0f ? a.z : 0.0f; a.w = x[i].w > 0.0f ? a.w : 0.0f;
+        }
+        if (e.perm_r > 0) {
+          const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            uint32_t g, pos;
+            e.div_r.divmod((uint32_t)(n + j), g, pos);
+            obase[(size_t)rw[i] * ld + (size_t)pos * e.perm_g + g] = av[j];
+          }
+        } else {
+          *reinterpret_cast<float4 *>(obase + (size_t)rw[i] * ld + n) = a;
+        }
+      }
+    }
+    return;
+  }
+  unsigned long long seed = 0;
+  if (kEpi == EPI_STORE && e.out2) seed = *e.seed;
 #pragma unroll 4
-  for (int r = 0; r < 32; r++) {
-    const int mt = wl * 32 + r;
-    if (m0 + mt >= M) break;
+  for (int mt = rb + wl; mt < re; mt += 4) {
     const int row = row_of(m0 + mt);
     if (row < 0) continue;
     float4 a = *reinterpret_cast<const float4 *>(stage + mt * PITCH + 4 * lane);
@@ -580,19 +741,73 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
           prow[j] = pv;
           orow[j] = w;
         }
-    } else {
-      a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-      if (relu) {       // RectifiedLinearComponent::Propagate fused: x > 0 ? x : 0
-        a.x = a.x > 0.0f ? a.x : 0.0f; a.y = a.y > 0.0f ? a.y : 0.0f;
-        a.z = a.z > 0.0f ? a.z : 0.0f; a.w = a.w > 0.0f ? a.w : 0.0f;
-      }
-      if (vec_ok) {
-        *reinterpret_cast<float4 *>(orow) = a;
+      continue;
+    }
+    a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+    if (e.relu) {       // RectifiedLinearComponent::Propagate fused: x > 0 ? x : 0
+      a.x = a.x > 0.0f ? a.x : 0.0f; a.y = a.y > 0.0f ? a.y : 0.0f;
+      a.z = a.z > 0.0f ? a.z : 0.0f; a.w = a.w > 0.0f ? a.w : 0.0f;
+    }
+    if (e.mask_x) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = make_float4(1.f, 1.f, 1.f, 1.f);
+      const float *xr = e.mask_x + (size_t)row * e.ld_mx + n;
+      const float *yr = e.mask_y ? e.mask_y + (size_t)row * e.ld_my + n : nullptr;
+      if (evec) {
+        x = __ldg(reinterpret_cast<const float4 *>(xr));
+        if (yr) y = __ldg(reinterpret_cast<const float4 *>(yr));
       } else {
-        if (n < N) orow[0] = a.x;
-        if (n + 1 < N) orow[1] = a.y;
-        if (n + 2 < N) orow[2] = a.z;
-        if (n + 3 < N) orow[3] = a.w;
+        if (n < N) x.x = __ldg(xr);
+        if (n + 1 < N) x.y = __ldg(xr + 1);
+        if (n + 2 < N) x.z = __ldg(xr + 2);
+        if (n + 3 < N) x.w = __ldg(xr + 3);
+        if (yr) {
+          if (n < N) y.x = __ldg(yr);
+          if (n + 1 < N) y.y = __ldg(yr + 1);
+          if (n + 2 < N) y.z = __ldg(yr + 2);
+          if (n + 3 < N) y.w = __ldg(yr + 3);
+        }
+      }
+      if (yr) {          // d * y / x, the order of dropout_bprop_kernel, then the ReLU gate
+        a.x = x.x > 0.0f ? a.x * y.x / x.x : 0.0f; a.y = x.y > 0.0f ? a.y * y.y / x.y : 0.0f;
+        a.z = x.z > 0.0f ? a.z * y.z / x.z : 0.0f; a.w = x.w > 0.0f ? a.w * y.w / x.w : 0.0f;
+      } else {
+        a.x = x.x > 0.0f ? a.x : 0.0f; a.y = x.y > 0.0f ? a.y : 0.0f;
+        a.z = x.z > 0.0f ? a.z : 0.0f; a.w = x.w > 0.0f ? a.w : 0.0f;
+      }
+    }
+    if (e.perm_r > 0) {
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (n + j < N) {
+          uint32_t g, pos;
+          e.div_r.divmod((uint32_t)(n + j), g, pos);
+          obase[(size_t)row * ld + (size_t)pos * e.perm_g + g] = av[j];
+        }
+      continue;
+    }
+    if (vec_ok) {
+      *reinterpret_cast<float4 *>(orow) = a;
+    } else {
+      if (n < N) orow[0] = a.x;
+      if (n + 1 < N) orow[1] = a.y;
+      if (n + 2 < N) orow[2] = a.z;
+      if (n + 3 < N) orow[3] = a.w;
+    }
+    if (e.out2) {
+      float4 d = a;
+      d.x *= dropout_scale_at(seed, (unsigned long long)row, N, n, e.dp, e.low, e.high);
+      d.y *= dropout_scale_at(seed, (unsigned long long)row, N, n + 1, e.dp, e.low, e.high);
+      d.z *= dropout_scale_at(seed, (unsigned long long)row, N, n + 2, e.dp, e.low, e.high);
+      d.w *= dropout_scale_at(seed, (unsigned long long)row, N, n + 3, e.dp, e.low, e.high);
+      float *o2 = e.out2 + (size_t)row * e.ld_o2 + n;
+      if (evec) {
+        *reinterpret_cast<float4 *>(o2) = d;
+      } else {
+        if (n < N) o2[0] = d.x;
+        if (n + 1 < N) o2[1] = d.y;
+        if (n + 2 < N) o2[2] = d.z;
+        if (n + 3 < N) o2[3] = d.w;
       }
     }
   }
@@ -627,11 +842,9 @@ struct DenseProb {
   int kb_per_split;
   float *out;              // row-major [M][ldo]
   int ldo;
-  const float *bias_n;     // per column, or nullptr
-  float *workspace;        // [splits][M][N] partials
   float *aux;              // EPI_SGD: prev_grad, same shape / pitch as out
   SgdCoef sgd;
-  int relu;                // EPI_STORE: max(., 0) after the bias
+  RowsEpi epi;             // EPI_STORE: bias, ReLU, masks, dropout, channels-last columns
 
   __device__ __forceinline__ void kb_range(int z, int &b, int &e) const {
     const int total = (K + BK - 1) / BK;
@@ -659,101 +872,16 @@ struct DenseProb {
   }
   __device__ __forceinline__ void prefetch(int tid, int mt, int nt) const {
     if (kEpi == EPI_SGD) prefetch_tile_l2(tid, mt * BM, nt * BN, M, N, out, aux, ldo, IdentityRow());
+    if (kEpi == EPI_STORE && epi.mask_x != nullptr)
+      prefetch_tile_l2(tid, mt * BM, nt * BN, M, N, epi.mask_x,
+                       (epi.mask_y && epi.ld_my == epi.ld_mx) ? epi.mask_y : epi.mask_x, epi.ld_mx, IdentityRow());
   }
   template <int kRows>
-  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z) const {
+  __device__ __forceinline__ void store(const float *stage, int tid, int mt, int nt, int z, int rb, int re) const {
     const int m0 = mt * BM, n0 = nt * BN;
-    if (kEpi == EPI_PARTIAL)
-      store_rows<EPI_STORE, kRows>(stage, tid, m0, n0, M, N, workspace + (size_t)z * M * N, N, nullptr, nullptr,
-                                   sgd, IdentityRow());
-    else
-      store_rows<kEpi, kRows>(stage, tid, m0, n0, M, N, out, ldo, bias_n, aux, sgd, IdentityRow(), relu != 0);
+    store_rows<kEpi, kRows>(stage, tid, m0, n0, M, N, out, ldo, aux, sgd, IdentityRow(), rb, re, epi);
   }
 };
-
-// Optional tail of the split-K reduction: the last stage of a per-column sum (the convolution's
-// bias gradient from the pack kernel's partial rows), run by extra blocks of the same launch:
-//   dst[c] = alpha * sum_r partial[r][c]  (+ dst[c] when accumulate)
-struct ColSumTail {
-  const float *partial;   // [rows][cols], nullptr = no tail
-  int rows, cols;
-  float *dst;
-  float alpha;
-  int accumulate;
-};
-constexpr int kColSumTailCols = 32;      // columns per tail block (256 threads = 32 columns x 8 row groups)
-inline unsigned colsum_tail_blocks(int cols) { return (unsigned)((cols + kColSumTailCols - 1) / kColSumTailCols); }
-
-// out[row_of(m)][n] = sum_z ws[z][m][n] (+ bias_n[n]), or the SGD update with that sum as the
-// gradient.  N % 4 == 0, 16-byte aligned rows (checked by the launchers).
-template <int kEpi, class RowMap>
-__global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float *__restrict__ ws, int splits, int M, int N, float *__restrict__ out, int ldo,
-                     const float *__restrict__ bias_n, float *__restrict__ aux, SgdCoef sgd, RowMap row_of,
-                     ColSumTail tail, unsigned main_blocks, int relu) {
-  kcnn::pdl_prologue();
-  if (blockIdx.x >= main_blocks) {
-    // kColSumTailCols columns per block: 32 lanes x 8 row groups, 4 independent loads in flight
-    // per thread (a single thread walking all rows of a column made this tail, not the
-    // reduction, the duration of the launch: ~13 us for 128 rows); fixed summation order.
-    __shared__ float red[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = (int)(blockIdx.x - main_blocks) * kColSumTailCols + tx;
-    const bool live = tail.partial != nullptr && c < tail.cols;
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-    if (live) {
-      const float *p = tail.partial + c;
-      const size_t ld = (size_t)tail.cols;
-      int r = ty;
-      for (; r + 24 < tail.rows; r += 32) {
-        s0 += __ldg(p + (size_t)r * ld);
-        s1 += __ldg(p + (size_t)(r + 8) * ld);
-        s2 += __ldg(p + (size_t)(r + 16) * ld);
-        s3 += __ldg(p + (size_t)(r + 24) * ld);
-      }
-      for (; r < tail.rows; r += 8) s0 += __ldg(p + (size_t)r * ld);
-    }
-    red[ty][tx] = (s0 + s1) + (s2 + s3);
-    __syncthreads();
-    if (ty == 0 && live) {
-      float s = red[0][tx];
-#pragma unroll
-      for (int i = 1; i < 8; i++) s += red[i][tx];
-      tail.dst[c] = tail.accumulate ? fmaf(tail.alpha, s, tail.dst[c]) : tail.alpha * s;
-    }
-    return;
-  }
-  const long long total4 = ((long long)M * N) >> 2;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  const long long e = i << 2;
-  const int m = (int)(e / N), n = (int)(e - (long long)m * N);
-  float4 s = __ldg(reinterpret_cast<const float4 *>(ws + e));
-  for (int z = 1; z < splits; z++) {
-    float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (size_t)z * M * N + e));
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-  }
-  const int row = row_of(m);
-  if (row < 0) return;
-  const size_t off = (size_t)row * ldo + n;
-  if (kEpi == EPI_SGD) {
-    float4 w = *reinterpret_cast<const float4 *>(out + off);
-    float4 pv = *reinterpret_cast<const float4 *>(aux + off);
-    sgd_apply(w.x, pv.x, s.x, sgd); sgd_apply(w.y, pv.y, s.y, sgd);
-    sgd_apply(w.z, pv.z, s.z, sgd); sgd_apply(w.w, pv.w, s.w, sgd);
-    *reinterpret_cast<float4 *>(aux + off) = pv;
-    *reinterpret_cast<float4 *>(out + off) = w;
-  } else {
-    if (bias_n) {
-      s.x += __ldg(bias_n + n); s.y += __ldg(bias_n + n + 1); s.z += __ldg(bias_n + n + 2); s.w += __ldg(bias_n + n + 3);
-    }
-    if (relu) {
-      s.x = s.x > 0.0f ? s.x : 0.0f; s.y = s.y > 0.0f ? s.y : 0.0f;
-      s.z = s.z > 0.0f ? s.z : 0.0f; s.w = s.w > 0.0f ? s.w : 0.0f;
-    }
-    *reinterpret_cast<float4 *>(out + off) = s;
-  }
-}
 
 // ------------------------------------------------------------------- host side --
 
@@ -768,14 +896,13 @@ bool enabled();                          // KCNN_TMA=0 disables the TMA paths
 bool pair_enabled();                     // KCNN_TMA_PAIR=1 opts in to the 2-CTA (cta_group::2) tiles
 bool deep_ring_enabled();                // KCNN_TMA_DEEP=0 keeps 3 stages for one-wave grids
 bool persistent_enabled();               // KCNN_TMA_PERSIST=0 keeps multi-wave grids on one tile per CTA
+bool cluster_k_enabled();                // KCNN_TMA_CLUSTERK=0: no split-K (small grids then leave SMs idle)
 
 // Grow-only device scratch, one buffer per slot (kernels_gemm.cu).  Returns nullptr when it
 // would have to grow while the stream is being captured; callers then take another path.
-// SCRATCH_SPLITK_ROWS: partials of the convolution fprop / dgrad split; its own slot because
-// inside a convolution's Backprop the dgrad GEMM runs CONCURRENTLY with the weight-gradient GEMM
-// (kcnn::ForkJoin), whose partials live in SCRATCH_SPLITK.
-enum ScratchSlot { SCRATCH_SPLITK = 0, SCRATCH_XCL = 1, SCRATCH_DYCL = 2, SCRATCH_BIAS = 3, SCRATCH_SPLITK_ROWS = 4,
-                   SCRATCH_SLOTS = 5 };
+// Only the bare-component path (a Component called outside NnetMinibatchUpdater's fused step)
+// uses it: channels-last staging copies and the bias-gradient partial sums of the pack kernel.
+enum ScratchSlot { SCRATCH_XCL = 0, SCRATCH_DYCL = 1, SCRATCH_BIAS = 2, SCRATCH_SLOTS = 3 };
 float *scratch(int slot, size_t bytes);
 
 // Tensor map of rank 2 to 4 over FP32 data; dims[0] is the contiguous axis, strides_bytes[i]
@@ -820,22 +947,22 @@ inline bool encode_2d(CUtensorMap *map, const Matrix &m, int box_rows, bool mn_m
 
 struct Epilogue {
   int mode = EPI_STORE;
-  const float *bias_n = nullptr;
   float *aux = nullptr;          // EPI_SGD: prev_grad
   SgdCoef sgd = {0.f, 0.f, 0.f};
-  int relu = 0;                  // EPI_STORE: rectify after the bias
+  RowsEpi rows = rows_epi_none();
 };
 
+// K-splits of one output tile = CTAs of one cluster (tma_gemm_kernel<..., kClusterK>): as many as
+// fit one wave of the machine, at least 8 K-blocks each, at most the portable cluster size.
+constexpr int kMaxClusterK = 8;
 inline int pick_splits(long long tiles, int num_kb) {
-  if (tiles >= 100) return 1;
-  long long want = (2 * kNumSMs) / tiles;
-  long long max_by_k = num_kb / 8;            // at least 8 K-blocks per split
+  if (!cluster_k_enabled() || tiles * 2 > kNumSMs) return 1;
+  long long want = kNumSMs / tiles;
+  long long max_by_k = num_kb / 8;
   if (want > max_by_k) want = max_by_k;
-  if (want > 16) want = 16;
+  if (want > kMaxClusterK) want = kMaxClusterK;
   return (int)(want < 1 ? 1 : want);
 }
-
-
 
 // One tile per CTA; kPair launches 2-CTA clusters.
 template <class Prob, bool kPair, int kStages>
@@ -848,6 +975,19 @@ void launch_variant(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &m
     attr_set = true;
   }
   launch_kernel(kernel, grid, dim3(THREADS), (size_t)smem, st, kPair ? 2u : 1u, ma, mb, p);
+}
+
+// Cluster split-K: grid.z K-splits per tile, one cluster (1, 1, grid.z) each, 1 CTA per SM.
+template <class Prob>
+void launch_cluster_k(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 grid) {
+  auto kernel = tma_gemm_kernel<Prob, false, 6, true>;
+  constexpr int smem = Ring<6>::SMEM_TOTAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  launch_kernel_cluster(kernel, grid, dim3(THREADS), (size_t)smem, st, dim3(1, 1, grid.z), ma, mb, p);
 }
 
 template <class Prob>
@@ -869,7 +1009,9 @@ void launch_persistent(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap
 template <class Prob>
 void launch_prob(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Prob &p, dim3 grid,
                  int kb_per_tile, bool pair = false) {
-  if (pair) {
+  if (grid.z > 1) {
+    launch_cluster_k<Prob>(st, ma, mb, p, grid);
+  } else if (pair) {
     launch_variant<Prob, true, 3>(st, ma, mb, p, dim3((grid.x + 1) & ~1u, (grid.y + 1) / 2, grid.z));
   } else if ((long long)grid.x * grid.y * grid.z <= kNumSMs && deep_ring_enabled()) {
     launch_variant<Prob, false, 6>(st, ma, mb, p, grid);
@@ -898,39 +1040,18 @@ bool gemm(cudaStream_t st, const Matrix &a, const Matrix &b, int M, int N, int K
   if (!encode_2d(&ma, a, kAMn ? BK : BM, kAMn)) return false;
   if (!encode_2d(&mb, b, kBMn ? BK : BN, kBMn)) return false;
   const int num_kb = (K + BK - 1) / BK;
-  const bool out_vec = (N & 3) == 0 && (ldo & 3) == 0 && host_aligned16(out);
   const bool pair = use_pair(M, N);
   int splits = 1;
-  if (allow_split && out_vec) {
-    long long ctas = pair ? (long long)(2 * ceil_div_u(M, 2 * BM)) * ceil_div_u(N, 2 * BN)
-                          : (long long)ceil_div_u(M, BM) * ceil_div_u(N, BN);
-    splits = pick_splits(ctas, num_kb);
-  }
+  if (allow_split && !pair) splits = pick_splits((long long)ceil_div_u(M, BM) * ceil_div_u(N, BN), num_kb);
   int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;
-  float *ws = nullptr;
-  if (splits > 1) {
-    ws = scratch(SCRATCH_SPLITK, (size_t)splits * M * N * sizeof(float));
-    if (!ws) { splits = 1; per = num_kb; }
-  }
   dim3 grid(ceil_div_u(M, BM), ceil_div_u(N, BN), splits);
   auto fill = [&](auto &p) {
     p.M = M; p.N = N; p.K = K; p.kb_per_split = per;
-    p.out = out; p.ldo = ldo; p.bias_n = epi.bias_n; p.workspace = ws; p.aux = epi.aux; p.sgd = epi.sgd;
-    p.relu = epi.relu;
+    p.out = out; p.ldo = ldo; p.aux = epi.aux; p.sgd = epi.sgd;
+    p.epi = epi.rows; p.epi.vec = rows_epi_vec_ok(epi.rows) ? 1 : 0;
   };
-  if (splits > 1) {
-    DenseProb<kAMn, kBMn, EPI_PARTIAL> p; fill(p);
-    launch_prob(st, ma, mb, p, grid, per, pair);
-    const unsigned blocks = ceil_div_u(((long long)M * N) >> 2, 256);
-    if (epi.mode == EPI_SGD)
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_SGD, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
-                  nullptr, epi.aux, epi.sgd, IdentityRow(), ColSumTail{nullptr, 0, 0, nullptr, 0.f, 0}, blocks, 0);
-    else
-      KCNN_LAUNCH((splitk_reduce_kernel<EPI_STORE, IdentityRow>), blocks, 256, 0, st, ws, splits, M, N, out, ldo,
-                  epi.bias_n, nullptr, epi.sgd, IdentityRow(), ColSumTail{nullptr, 0, 0, nullptr, 0.f, 0}, blocks,
-                  epi.relu);
-  } else if (epi.mode == EPI_SGD) {
+  if (epi.mode == EPI_SGD) {
     DenseProb<kAMn, kBMn, EPI_SGD> p; fill(p);
     launch_prob(st, ma, mb, p, grid, per, pair);
   } else {

@@ -69,9 +69,12 @@ class ForkJoin {
   cudaEvent_t join_ev_;
 };
 
+// cluster: thread-block cluster shape ((1,1,1) = none).  x = 2 pairs two CTAs of a TPC
+// (cta_group::2 tiles); z = S makes the S K-splits of one output tile a cluster, reduced
+// through distributed shared memory (gemm_tma.cuh).
 template <class... KArgs, class... Args>
-inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                          unsigned cluster_x, Args &&...args) {
+inline void launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  dim3 cluster, Args &&...args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -79,9 +82,9 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   cfg.stream = stream;
   cudaLaunchAttribute at[2];
   unsigned n = 0;
-  if (cluster_x > 1) {
+  if (cluster.x * cluster.y * cluster.z > 1) {
     at[n].id = cudaLaunchAttributeClusterDimension;
-    at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    at[n].val.clusterDim.x = cluster.x; at[n].val.clusterDim.y = cluster.y; at[n].val.clusterDim.z = cluster.z;
     n++;
   }
   if (pdl_enabled()) {
@@ -95,6 +98,12 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   count_launch();
 }
 
+template <class... KArgs, class... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          unsigned cluster_x, Args &&...args) {
+  launch_kernel_cluster(kernel, grid, block, smem, stream, dim3(cluster_x, 1, 1), static_cast<Args &&>(args)...);
+}
+
 #define KCNN_LAUNCH(kernel, grid, block, smem, stream, ...) \
   ::kcnn::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), 1u, __VA_ARGS__)
 
@@ -106,7 +115,7 @@ inline unsigned int ceil_div_u(long long a, long long b) {
 // decompose flat indices into (row, channel, w, h) many times per element.
 struct FastDiv {
   uint32_t d, mul, shr;
-  FastDiv() : d(1), mul(0), shr(0) {}
+  __host__ __device__ FastDiv() : d(1), mul(0), shr(0) {}
   explicit FastDiv(uint32_t divisor) : d(divisor) {
     if (d == 1) { mul = 0; shr = 0; return; }
     uint32_t l = 0;
@@ -136,6 +145,24 @@ __device__ __forceinline__ bool aligned16(const void *p) {
 
 inline bool host_aligned16(const void *p) {
   return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+// Counter-based uniform of the dropout mask (splitmix64 finaliser): a pure function of
+// (seed, element index), so the forward kernel, a fused GEMM epilogue and a replayed CUDA
+// graph all draw the same mask from the same device-resident seed.
+__host__ __device__ __forceinline__ uint32_t mix32(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 32);
+}
+// scale of element (row, col) of a [rows x cols] matrix: `low` with probability dp, else `high`
+__device__ __forceinline__ float dropout_scale_at(unsigned long long seed, unsigned long long row, int cols, int col,
+                                                  float dp, float low, float high) {
+  const unsigned long long base = seed * 0x100000001B3ull + row * (unsigned long long)cols;
+  const float r = (mix32(base + (unsigned long long)col) >> 8) * (1.0f / 16777216.0f);
+  return (r - dp > 0.0f) ? high : low;
 }
 
 }  // namespace kcnn

@@ -83,6 +83,15 @@ bool persistent_enabled() {
   return v == 1;
 }
 
+bool cluster_k_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_TMA_CLUSTERK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool deep_ring_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -291,7 +300,8 @@ int cudaF_conv2d_fprop_act(cudaStream_t st, int math, const float *in, MatrixDim
   //  kcnn_conv2d_staging_floats() was non-zero AND the math mode is the tensor-core one.)
   if (math == KCNN_MATH_TF32_TC && concat && KH == H && H > 1 && ph == 0 && pw == 0) {
     tma::ConvFullShape fs = {q.N, H, W, C, KW, G, q.OW};
-    if (tma::conv_full_fprop(st, fs, in, id.stride, kernel, kd.stride, bias, out, od.stride, relu)) return 0;
+    tma::ConvOut o = {out, od.stride, false, bias, relu, nullptr};
+    if (tma::conv_full_fprop(st, fs, in, id.stride, kernel, kd.stride, o)) return 0;
   }
   // the generic kernels below have no activation in their epilogue: one in-place pass after them
   struct ReluAfter {
@@ -401,9 +411,8 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
     tma::ConvBackward b = {};
     b.in_value = in_value; b.ld_iv = ivd.stride; b.out_deriv = out_deriv; b.ld_od = odd.stride;
     b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride; b.want_bias = bias_grad != nullptr;
-    b.bias_dst = bias_grad; b.bias_alpha = 1.0f; b.bias_accumulate = 0;
     if (tma::conv_backward(st, cs, b)) {
-      if (bias_grad && !b.bias_done) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
+      if (bias_grad) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
       return;
     }
   }
@@ -412,9 +421,8 @@ void cudaF_conv2d_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
     tma::ConvBackward b = {};
     b.in_value = in_value; b.ld_iv = ivd.stride; b.out_deriv = out_deriv; b.ld_od = odd.stride;
     b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride; b.want_bias = bias_grad != nullptr;
-    b.bias_dst = bias_grad; b.bias_alpha = 1.0f; b.bias_accumulate = 0;
     if (tma::conv_full_backward(st, fs, b)) {
-      if (bias_grad && !b.bias_done) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
+      if (bias_grad) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
       return;
     }
   }
@@ -459,16 +467,12 @@ int cudaF_conv2d_backward(cudaStream_t st, int math, const float *in_value, Matr
   b.staged_x = time_axis ? staged_input : nullptr;
   if (apply) {
     b.prev = prev_grad; b.ld_p = pd.stride; b.sgd = &coef;
-    b.bias_dst = bias; b.bias_alpha = a_grad; b.bias_accumulate = 1;        // bias += lr * db
   } else {
     b.kernel_grad = kernel_grad; b.ld_kg = kgd.stride;
-    b.bias_dst = bias_grad; b.bias_alpha = 1.0f; b.bias_accumulate = 0;
   }
   if (!(time_axis ? tma::conv_backward(st, cs, b) : tma::conv_full_backward(st, fs, b))) return 0;
-  if (!b.bias_done) {
-    if (apply) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias, a_grad, 1);
-    else       launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
-  }
+  if (apply) launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias, a_grad, 1);    // bias += lr * db
+  else       launch_colsum(st, b.bias_partial, b.bias_rows, G, G, 1, bias_grad);
   return 1;
 }
 
@@ -487,7 +491,7 @@ int cudaF_affine_wgrad_sgd(cudaStream_t st, int math, const float *in_value, Mat
   if (!tma::gemm<true, true>(st, tma::Matrix{out_deriv, K, M, odd.stride}, tma::Matrix{in_value, K, N, ivd.stride},
                              M, N, K, w, wd.stride, epi, true))
     return 0;
-  launch_colsum(st, out_deriv, odd.rows, odd.stride, M, 1, bias, a_grad, 1);
+  if (bias) launch_colsum(st, out_deriv, odd.rows, odd.stride, M, 1, bias, a_grad, 1);
   return 1;
 }
 
@@ -508,7 +512,7 @@ void cudaF_affine_fprop_act(cudaStream_t st, int math, const float *in, MatrixDi
   check_int32(id, "affine input"); check_int32(od, "affine output"); check_int32(wd, "affine weights");
   // out = 1 bias^T + in W^T : A(m, k) = in[m, k], B(k, n) = W[n, k]
   if (math == KCNN_MATH_TF32_TC && tma::enabled()) {
-    tma::Epilogue epi; epi.bias_n = bias; epi.relu = act == KCNN_ACT_RELU ? 1 : 0;
+    tma::Epilogue epi; epi.rows.bias_n = bias; epi.rows.relu = act == KCNN_ACT_RELU ? 1 : 0;
     if (tma::gemm<false, false>(st, tma::Matrix{in, M, K, id.stride}, tma::Matrix{w, N, K, wd.stride}, M, N, K,
                                 out, od.stride, epi, true))
       return;
@@ -556,6 +560,102 @@ void cudaF_affine_wgrad(cudaStream_t st, int math, const float *in_value, Matrix
   Op33 b = make_op(in_value, make_linear(N, 1), make_linear(K, ivd.stride), 1, 1);
   Out33 o = make_out(w_grad, make_linear(M, wgd.stride), make_linear(N, 1), nullptr);
   launch_gemm<false, false, true>(st, math, a, b, o, M, N, K, false, nullptr);
+}
+
+// ---- (4) the fused training step: channels-last activations (nnet2/nnet-fused.cc) -------------
+
+int kcnn_conv_time_shape_ok(int N, int W, int C, int pw, int KW, int G) {
+  tma::ConvShape cs = {N, W, C, pw, KW, G, W + 2 * pw - KW + 1};
+  return tma::conv_tma_shape_ok(cs) && tma::encode_tiled_fn() != nullptr ? 1 : 0;
+}
+
+int kcnn_conv_full_shape_ok(int N, int H, int W, int C, int KW, int G) {
+  tma::ConvFullShape fs = {N, H, W, C, KW, G, W - KW + 1};
+  return tma::conv_full_shape_ok(fs) && ((KW * H) & 31) == 0 && (G & 3) == 0 && tma::encode_tiled_fn() != nullptr ? 1 : 0;
+}
+
+int cudaF_conv_time_fprop_cl(cudaStream_t st, const float *x, int N, int W, int C, int pw, int KW, int G,
+                             const float *kernel, MatrixDim kd, const float *bias, float *out, int out_cl,
+                             int ldo, int relu) {
+  if (N == 0) return 1;
+  tma::ConvShape cs = {N, W, C, pw, KW, G, W + 2 * pw - KW + 1};
+  tma::ConvOut o = {out, ldo, out_cl != 0, bias, relu != 0, nullptr};
+  return tma::conv_rows_fprop(st, cs, x, kernel, kd.stride, o) ? 1 : 0;
+}
+
+int cudaF_conv_time_dgrad_cl(cudaStream_t st, const float *dy, int N, int W, int C, int pw, int KW, int G,
+                             const float *kernel, MatrixDim kd, float *dx, const float *mask) {
+  if (N == 0) return 1;
+  tma::ConvShape cs = {N, W, C, pw, KW, G, W + 2 * pw - KW + 1};
+  tma::ConvOut o = {dx, 0, true, nullptr, false, mask};
+  return tma::conv_rows_dgrad(st, cs, dy, kernel, kd.stride, o) ? 1 : 0;
+}
+
+int cudaF_conv_time_wgrad_cl(cudaStream_t st, const float *x, const float *dy, int N, int W, int C, int pw,
+                             int KW, int G, float *w, MatrixDim wd, float *prev_grad, MatrixDim pd, int apply,
+                             float momentum, float a_decay, float a_grad) {
+  if (N == 0) return 1;
+  tma::ConvShape cs = {N, W, C, pw, KW, G, W + 2 * pw - KW + 1};
+  tma::SgdCoef coef = {momentum, a_decay, a_grad};
+  tma::ConvWgradOut o = {w, wd.stride, apply ? prev_grad : nullptr, pd.stride, apply ? &coef : nullptr};
+  if (!host_aligned16(x) || !host_aligned16(dy)) return 0;
+  return tma::conv_rows_wgrad(st, cs, x, dy, o) ? 1 : 0;
+}
+
+int cudaF_conv_full_fprop_cl(cudaStream_t st, const float *in, MatrixDim id, int H, int W, int C, int KW, int G,
+                             const float *kernel, MatrixDim kd, const float *bias, float *out, int relu) {
+  if (id.rows == 0) return 1;
+  tma::ConvFullShape fs = {id.rows, H, W, C, KW, G, W - KW + 1};
+  tma::ConvOut o = {out, 0, true, bias, relu != 0, nullptr};
+  return tma::conv_full_fprop(st, fs, in, id.stride, kernel, kd.stride, o) ? 1 : 0;
+}
+
+int cudaF_conv_full_dgrad_cl(cudaStream_t st, const float *dy, int N, int H, int W, int C, int KW, int G,
+                             const float *kernel, MatrixDim kd, float *in_deriv, MatrixDim idd) {
+  if (N == 0) return 1;
+  tma::ConvFullShape fs = {N, H, W, C, KW, G, W - KW + 1};
+  return tma::conv_full_dgrad(st, fs, dy, kernel, kd.stride, in_deriv, idd.stride) ? 1 : 0;
+}
+
+int cudaF_conv_full_wgrad_cl(cudaStream_t st, const float *in, MatrixDim id, const float *dy, int H, int W, int C,
+                             int KW, int G, float *w, MatrixDim wd, float *prev_grad, MatrixDim pd, int apply,
+                             float momentum, float a_decay, float a_grad) {
+  if (id.rows == 0) return 1;
+  tma::ConvFullShape fs = {id.rows, H, W, C, KW, G, W - KW + 1};
+  tma::SgdCoef coef = {momentum, a_decay, a_grad};
+  tma::ConvWgradOut o = {w, wd.stride, apply ? prev_grad : nullptr, pd.stride, apply ? &coef : nullptr};
+  return tma::conv_full_wgrad(st, fs, in, id.stride, dy, o) ? 1 : 0;
+}
+
+int cudaF_affine_fprop_fused(cudaStream_t st, const float *in, MatrixDim id, const float *w, MatrixDim wd,
+                             const float *bias, float *out, MatrixDim od, int relu, float *drop_out,
+                             MatrixDim dd, float dp, float low, float high, const unsigned long long *seed_dev) {
+  const int M = id.rows, N = wd.rows, K = wd.cols;
+  if (M == 0 || N == 0) return 1;
+  if (!tma::enabled()) return 0;
+  tma::Epilogue epi;
+  epi.rows.bias_n = bias; epi.rows.relu = relu ? 1 : 0;
+  if (drop_out) {
+    epi.rows.out2 = drop_out; epi.rows.ld_o2 = dd.stride;
+    epi.rows.dp = dp; epi.rows.low = low; epi.rows.high = high; epi.rows.seed = seed_dev;
+  }
+  return tma::gemm<false, false>(st, tma::Matrix{in, M, K, id.stride}, tma::Matrix{w, N, K, wd.stride}, M, N, K, out,
+                                 od.stride, epi, true) ? 1 : 0;
+}
+
+int cudaF_affine_dgrad_fused(cudaStream_t st, const float *out_deriv, MatrixDim odd, const float *w, MatrixDim wd,
+                             float *in_deriv, MatrixDim idd, const float *relu_out, int relu_stride,
+                             const float *drop_out, int drop_stride, int perm_r) {
+  const int M = odd.rows, N = wd.cols, K = wd.rows;
+  if (M == 0 || N == 0) return 1;
+  if (!tma::enabled()) return 0;
+  if (perm_r > 0 && (N % perm_r) != 0) return 0;
+  tma::Epilogue epi;
+  if (relu_out) { epi.rows.mask_x = relu_out; epi.rows.ld_mx = relu_stride; }
+  if (relu_out && drop_out) { epi.rows.mask_y = drop_out; epi.rows.ld_my = drop_stride; }
+  if (perm_r > 0) { epi.rows.perm_r = perm_r; epi.rows.perm_g = N / perm_r; epi.rows.div_r = FastDiv((uint32_t)perm_r); }
+  return tma::gemm<false, true>(st, tma::Matrix{out_deriv, M, K, odd.stride}, tma::Matrix{w, K, N, wd.stride}, M, N, K,
+                                in_deriv, idd.stride, epi, true) ? 1 : 0;
 }
 
 }  // extern "C"

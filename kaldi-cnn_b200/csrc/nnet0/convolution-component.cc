@@ -541,6 +541,22 @@ void ConvolutionComponent::ApplyGradient(int32 total_num_samples) {
   CU_SAFE_CALL(cudaGetLastError());
 }
 
+bool ConvolutionComponent::GetStepTarget(int32 num_rows, StepTarget *t) {
+  if (is_gradient_ || num_rows <= 0) return false;
+  EnsureGradBuffers();
+  double learning_rate = learning_rate_ / num_rows;                 // reference :767
+  t->w = linear_params_.Data(); t->wd = linear_params_.Dim();
+  t->prev = prev_grad_.Data(); t->pd = prev_grad_.Dim();
+  t->bias = bias_params_.Data(); t->bias_dim = bias_params_.Dim();
+  t->w_grad = w_grad_.data; t->gd.rows = w_grad_.rows; t->gd.cols = w_grad_.cols; t->gd.stride = w_grad_.stride;
+  t->b_grad = b_grad_.data;
+  t->deferred = deferred_;
+  t->momentum = momentum_;
+  t->a_decay = -1 * learning_rate * weight_decay_;
+  t->a_grad = learning_rate;
+  return true;
+}
+
 // reference :738-777
 void ConvolutionComponent::Update(const CuMatrixBase<BaseFloat> &in_value,
                                   const CuMatrixBase<BaseFloat> &out_deriv) {

@@ -60,6 +60,8 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   inline int32 KernelDim() const { return kernel_height_ * kernel_width_ * in_channel_; }
   inline int32 Kernel_height() const { return kernel_height_; }
   inline int32 Kernel_width() const { return kernel_width_; }
+  inline int32 In_pad_height() const { return in_pad_height_; }
+  inline int32 In_pad_width() const { return in_pad_width_; }
 
   void Init(BaseFloat learning_rate, int32 in_height, int32 in_width, int32 in_channels,
             int32 in_pad_height, int32 in_pad_width, int32 kernel_height, int32 kernel_width,
@@ -118,6 +120,7 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   /// propagated: Backprop then reuses Propagate's channels-last staging copy instead of
   /// packing in_value again.  Off by default: a bare Component makes no such assumption.
   virtual void SetInputPersists(bool on) { input_persists_ = on; staged_src_ = NULL; }
+  virtual bool GetStepTarget(int32 num_rows, StepTarget *t);
   virtual uint64 StepSignature() const {
     uint64 h = HashValue(learning_rate_, 13);
     h = HashValue(weight_decay_, h); h = HashValue(momentum_, h);
@@ -219,6 +222,14 @@ class MaxpoolComponent : public nnet2::Component {
   /// off (reference-exact routing); plain mode only.
   void SetIndexRouting(bool on) { index_routing_ = on; }
   bool IndexRouting() const { return index_routing_; }
+  int32 In_height() const { return in_height_; }
+  int32 In_width() const { return in_width_; }
+  int32 In_channel() const { return in_channel_; }
+  int32 Pool_height_dim() const { return pool_height_dim_; }
+  int32 Pool_width_dim() const { return pool_width_dim_; }
+  int32 Pool_channel_dim() const { return pool_channel_dim_; }
+  bool Overlap() const { return overlap_; }
+  bool Overlap2D() const { return overlap2D_; }
 
  protected:
   int32 input_dim_;
@@ -265,6 +276,7 @@ class FullyConnectedComponent : public nnet2::AffineComponent {
   virtual void UpdateSimple(const CuMatrixBase<BaseFloat> &in_value,
                             const CuMatrixBase<BaseFloat> &out_deriv);
   virtual void ApplyGradient(int32 total_num_samples);
+  virtual bool GetStepTarget(int32 num_rows, StepTarget *t);
   virtual uint64 StepSignature() const {
     uint64 h = nnet2::AffineComponent::StepSignature();
     h = HashValue(weight_decay_, h); h = HashValue(momentum_, h);

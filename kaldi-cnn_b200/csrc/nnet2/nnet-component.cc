@@ -271,13 +271,7 @@ relu_bprop_stats_kernel(const float *__restrict__ y, ::MatrixDim yd, const float
   }
 }
 
-__device__ __forceinline__ uint32_t mix32(uint64_t x) {     // splitmix64 finaliser
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return (uint32_t)(x >> 32);
-}
+using kcnn::mix32;      // splitmix64 finaliser shared with the fused affine epilogue (kcnn_common.cuh)
 
 // The mask is a pure function of (seed, element index i*cols + j).  Each thread owns up to four
 // adjacent columns of one row (128-bit accesses when kVec4).
@@ -556,6 +550,16 @@ DropoutComponent::~DropoutComponent() {
   if (seed_dev_) CuDevice::Instantiate().Free(seed_dev_);
 }
 
+unsigned long long *DropoutComponent::SeedDevice() const {
+  if (seed_dev_ == NULL) {
+    seed_dev_ = static_cast<unsigned long long *>(CuDevice::Instantiate().Malloc(sizeof(unsigned long long)));
+    unsigned long long s0 = CuDevice::Instantiate().NextRandSeed();
+    CU_SAFE_CALL(cudaMemcpyAsync(seed_dev_, &s0, sizeof(s0), cudaMemcpyHostToDevice, Str()));
+    CU_SAFE_CALL(cudaStreamSynchronize(Str()));
+  }
+  return seed_dev_;
+}
+
 Component *DropoutComponent::Copy() const {
   return new DropoutComponent(dim_, dropout_proportion_, dropout_scale_);
 }
@@ -577,12 +581,7 @@ void DropoutComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &out_
   // five passes, :3600-3620).  The mask is a pure function of (seed, element); the seed
   // lives on the device and is bumped by a one-thread kernel, so a replayed CUDA graph
   // draws a fresh mask every step.
-  if (seed_dev_ == NULL) {
-    seed_dev_ = static_cast<unsigned long long *>(CuDevice::Instantiate().Malloc(sizeof(unsigned long long)));
-    unsigned long long s0 = CuDevice::Instantiate().NextRandSeed();
-    CU_SAFE_CALL(cudaMemcpyAsync(seed_dev_, &s0, sizeof(s0), cudaMemcpyHostToDevice, Str()));
-    CU_SAFE_CALL(cudaStreamSynchronize(Str()));
-  }
+  SeedDevice();
   const bool v4 = rows_vec4(out->NumCols(), {in.Stride(), out->Stride()}, {in.Data(), out->Data()});
   const int units = v4 ? out->NumCols() / 4 : out->NumCols();
   const unsigned grid = kcnn::ceil_div_u((long long)out->NumRows() * units, 256);

@@ -170,6 +170,20 @@ class UpdatableComponent : public Component {
   /// The caller owns the activation buffers and promises that Backprop's in_value is the
   /// unmodified matrix last given to Propagate (lets a component keep per-input scratch).
   virtual void SetInputPersists(bool) {}
+  /// Raw views of the parameters, the momentum state and the gradient buffers, with the SGD
+  /// coefficients of one minibatch of num_rows rows (lr = learning_rate_ / num_rows, reference
+  /// nnet0/nnet-component-nnet0.cc:767, 1136): what NnetMinibatchUpdater's fused step hands to the
+  /// kernels directly.  Returns false for components without a momentum / weight-decay update.
+  struct StepTarget {
+    float *w; ::MatrixDim wd;          // linear_params_
+    float *prev; ::MatrixDim pd;       // prev_grad_
+    float *bias; int32 bias_dim;       // bias_params_
+    float *w_grad; ::MatrixDim gd;     // gradient buffers (deferred / data-parallel mode)
+    float *b_grad;
+    bool deferred;
+    float momentum, a_decay, a_grad;
+  };
+  virtual bool GetStepTarget(int32 /*num_rows*/, StepTarget * /*t*/) { return false; }
 
  protected:
   BaseFloat learning_rate_;
@@ -197,6 +211,8 @@ class NonlinearComponent : public Component {
   void AddToCount(double frames) { count_ += frames; }
   /// Host copies of the diagnostics.
   void GetStats(Vector<double> *value_sum, Vector<double> *deriv_sum) const;
+  /// Device accumulators [2 x dim]: value sums, then derivative sums (allocated on first use).
+  double *StatsDevice() { EnsureStats(); return stats_; }
 
  protected:
   friend class RectifiedLinearComponent;
@@ -272,6 +288,10 @@ class DropoutComponent : public Component {
   virtual void Write(std::ostream &os, bool binary) const;
   virtual std::string Type() const { return "DropoutComponent"; }
   void SetDropoutScale(BaseFloat scale) { dropout_scale_ = scale; }
+  BaseFloat DropoutProportion() const { return dropout_proportion_; }
+  BaseFloat DropoutScale() const { return dropout_scale_; }
+  /// Device-resident seed counter of the mask (created, from CuDevice's seed, on first use).
+  unsigned long long *SeedDevice() const;
   virtual uint64 StepSignature() const {
     return HashValue(seed_dev_, HashValue(dropout_scale_, HashValue(dropout_proportion_, 7)));
   }

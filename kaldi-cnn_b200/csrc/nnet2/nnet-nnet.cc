@@ -108,7 +108,8 @@ struct NnetMinibatchUpdater::GraphState {
 
 NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
     : graph_(new GraphState), last_replayed_(false), fuse_(true),
-      nnet_(nnet), num_rows_(0), labels_(NULL), objf_dev_(NULL) {
+      nnet_(nnet), num_rows_(0), fused_(NULL), step_labels_(NULL), labels_(NULL), objf_dev_(NULL) {
+  FusedInit();
   objf_dev_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double)));
   CU_SAFE_CALL(cudaMemsetAsync(objf_dev_, 0, sizeof(double), Str()));
   const char *fe = getenv("KCNN_NNET_FUSE");
@@ -119,6 +120,7 @@ NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
 NnetMinibatchUpdater::~NnetMinibatchUpdater() {
   DropGraph();
   delete graph_;
+  FusedDestroy();
   SetInputPersists(false);
   CuDevice::Instantiate().Free(objf_dev_);
 }
@@ -149,11 +151,17 @@ void NnetMinibatchUpdater::ForwardRange(const CuMatrixBase<BaseFloat> &feats, in
       info_.push_back(ChunkInfo(dim, num_rows_, 0, 0));
       forward_[c + 1].Resize(num_rows_, dim, kUndefined);
     }
+    derivs_.clear();
+    derivs_.resize(L + 1);
   }
   // the input is used in place (a borrowed view), not copied
   if (first == 0)
     forward_[0].Borrow(const_cast<BaseFloat *>(feats.Data()), feats.NumRows(), feats.NumCols(),
                        feats.Stride());
+  if (PlanFused()) {
+    FusedForward(first, last, step_labels_);
+    return;
+  }
   for (int32 c = first; c <= last; c++) {
     const Component &comp = nnet_->GetComponent(c);
     if (fuse_ && c + 1 <= last && !comp.BackpropNeedsOutput()) {
@@ -172,10 +180,11 @@ void NnetMinibatchUpdater::ForwardRange(const CuMatrixBase<BaseFloat> &feats, in
 }
 
 void NnetMinibatchUpdater::ComputeObjfAndDeriv(const int32 *labels_dev) {
+  if (FusedObjf(labels_dev)) return;
   const CuMatrix<BaseFloat> &post = forward_.back();
-  deriv_a_.Resize(post.NumRows(), post.NumCols(), kUndefined);
-  cudaF_xent_deriv(Str(), post.Data(), post.Dim(), labels_dev, deriv_a_.Data(), deriv_a_.Dim(),
-                   objf_dev_);
+  CuMatrix<BaseFloat> &d = derivs_.back();
+  d.Resize(post.NumRows(), post.NumCols(), kUndefined);
+  cudaF_xent_deriv(Str(), post.Data(), post.Dim(), labels_dev, d.Data(), d.Dim(), objf_dev_);
   CU_SAFE_CALL(cudaGetLastError());
 }
 
@@ -183,11 +192,18 @@ void NnetMinibatchUpdater::Backward(int32 last, int32 first) {
   const int32 L = nnet_->NumComponents();
   if (last < 0) last = L - 1;
   KALDI_ASSERT(first >= 0 && last < L && !forward_.empty());
-  // deriv_a_ holds d objf / d output-of-component[last]
+  if (FusedActive()) {
+    FusedBackward(last, first);
+    return;
+  }
+  // derivs_[c + 1] holds d objf / d output-of-component[c]; every buffer keeps its storage from
+  // step to step (a same-size Resize inside Backprop is a no-op), so a recorded graph of the step
+  // never points at memory the device cache could hand to someone else.
   for (int32 c = last; c >= first; c--) {
     Component &comp = nnet_->GetComponent(c);
-    comp.Backprop(info_[c], info_[c + 1], forward_[c], forward_[c + 1], deriv_a_, &comp, &deriv_b_);
-    deriv_a_.Swap(&deriv_b_);
+    if (derivs_[c].NumRows() != num_rows_ || derivs_[c].NumCols() != comp.InputDim())
+      derivs_[c].Resize(num_rows_, comp.InputDim(), kUndefined);
+    comp.Backprop(info_[c], info_[c + 1], forward_[c], forward_[c + 1], derivs_[c + 1], &comp, &derivs_[c]);
   }
 }
 
@@ -229,7 +245,14 @@ uint64 NnetMinibatchUpdater::StepKey(const CuMatrixBase<BaseFloat> &feats, const
 }
 
 void NnetMinibatchUpdater::EagerStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) {
-  Forward(feats);
+  step_labels_ = labels_dev;          // lets the fused plan finish softmax + objective inside the forward pass
+  try {
+    Forward(feats);
+  } catch (...) {
+    step_labels_ = NULL;
+    throw;
+  }
+  step_labels_ = NULL;
   ComputeObjfAndDeriv(labels_dev);
   Backward();
 }

@@ -69,9 +69,14 @@ class NnetMinibatchUpdater {
   /// stream (the legacy default stream cannot be captured): otherwise, or with
   /// KCNN_NNET_GRAPH=0, every step runs eagerly.
   void TrainStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev);
-  /// Fusion of adjacent components inside Forward (default on; KCNN_NNET_FUSE=0 turns it off):
-  /// [Convolution | FullyConnected | Affine] + RectifiedLinear run as one launch through
-  /// Component::PropagateRelu.  The skipped pre-activation Activation(c + 1) is then NOT filled.
+  /// Fusion (default on; KCNN_NNET_FUSE=0 turns it off).  With the tensor-core math mode and a model
+  /// made of the hot path's layers (Convolution / Maxpool / FullyConnected with ReLU, dropout and a
+  /// final softmax) the whole step runs as the FUSED PLAN of nnet-fused.cc: channels-last
+  /// activations between the time-axis layers, element-wise components inside the GEMM epilogues,
+  /// weight gradients beside the next input gradient, batched column sums (KCNN_NNET_PLAN=0 keeps
+  /// the component-by-component path).  Otherwise only [Convolution | FullyConnected | Affine] +
+  /// RectifiedLinear are merged, through Component::PropagateRelu.  Either way the pre-activation
+  /// Activation(c + 1) of a fused pair is NOT filled.
   void SetFusion(bool on) { fuse_ = on; }
   bool Fusion() const { return fuse_; }
   /// True when the last TrainStep was a graph replay.
@@ -86,8 +91,14 @@ class NnetMinibatchUpdater {
   void GradientBucket(int32 c, size_t *offset, size_t *length) const;
   void SetDeferredUpdate(bool on);
   const CuMatrix<BaseFloat> &Output() const { return forward_.back(); }
-  const CuMatrix<BaseFloat> &Activation(int32 i) const { return forward_[i]; }
-  const CuMatrix<BaseFloat> &InputDeriv() const { return deriv_a_; }
+  /// Output of component i - 1 in the reference layout (a channels-last buffer of the fused plan is
+  /// converted into a side buffer on demand).
+  const CuMatrix<BaseFloat> &Activation(int32 i) { return FusedActive() ? FusedActivation(i) : forward_[i]; }
+  /// Derivative with respect to the network input.  The fused plan does not compute it (nothing
+  /// trains below the first layer): the matrix is then empty.
+  const CuMatrix<BaseFloat> &InputDeriv() const { return derivs_.empty() ? empty_ : derivs_[0]; }
+  /// True when the current configuration runs as the fused plan.
+  bool FusedActive() const;
   double *ObjfDevice() { return objf_dev_; }
   double GetObjfAndReset();      // synchronises
   int32 NumRows() const { return num_rows_; }
@@ -103,9 +114,25 @@ class NnetMinibatchUpdater {
   bool fuse_;
   Nnet *nnet_;
   int32 num_rows_;
+  // ---- fused plan (nnet-fused.cc)
+  struct FusedOp;
+  struct FusedState;
+  FusedState *fused_;
+  void FusedInit();
+  void FusedDestroy();
+  bool PlanFused();
+  const CuMatrix<BaseFloat> &FusedActivation(int32 i);
+  void FusedForward(int32 first, int32 last, const int32 *labels_dev);
+  bool FusedObjf(const int32 *labels_dev);
+  void FusedBackward(int32 last, int32 first);
+  const int32 *step_labels_;                    // TrainStep: labels known while the forward pass runs
+
   std::vector<CuMatrix<BaseFloat> > forward_;   // [0] = copy-free view of the input
   std::vector<ChunkInfo> info_;
-  CuMatrix<BaseFloat> deriv_a_, deriv_b_;
+  // derivs_[i] = d objf / d forward_[i]: one buffer per activation, sized once -- nothing is
+  // allocated or returned to the device cache while a step (or its recorded graph) runs
+  std::vector<CuMatrix<BaseFloat> > derivs_;
+  CuMatrix<BaseFloat> empty_;
   const int32 *labels_;
   double *objf_dev_;
   std::vector<size_t> bucket_off_, bucket_len_;

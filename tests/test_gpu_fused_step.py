@@ -1,0 +1,285 @@
+"""The fused training step of NnetMinibatchUpdater (csrc/nnet2/nnet-fused.cc): channels-last
+activations between the time-axis layers, ReLU / dropout inside the GEMM epilogues, cluster
+split-K, batched column sums -- against
+
+  * the CPU oracle's whole training step (oracle/cpu_nnet.py: the reference's Propagate /
+    Backprop / Update chain of nnet0/nnet-component-nnet0.cc:423-446, 461-544, 738-777, 869-892,
+    1133-1143 and the stock ReLU / dropout / softmax of nnet2/nnet-component.cc:799-827, 930-1000,
+    3592-3637, op for op): objective and EVERY updated parameter, at the benchmarked size too
+    (C2 + intermap pooling, N = 512);
+  * the component-by-component path of the same library (every Component called separately in
+    the reference layout): activations, parameters, momentum, statistics.
+
+Tolerances (max-norm relative): TF32 tensor-core path 1e-3 on outputs and
+updated parameters.  The weight STEP (new - old) of each layer is additionally held to a fraction of
+its own Frobenius norm, and the momentum to the same fraction of its max-norm: 2e-2 at the benchmarked
+size, 6e-2 for the small test models.  That bound is not a rounding-error bound: under TF32 rounding of
+the forward activations a few ReLU gates and max-pool winners of near-tied units flip, and every flip
+is an O(1) change of that unit's gradient; the effect averages out with the number of rows x positions
+a gradient sums over (measured in max-norm: 4-8e-2 at N = 96, <= 2e-2 at N = 512).  The
+component-by-component path of the same library shows the same numbers (the two paths agree to 2e-5,
+last test group).  Max-pool routing inside the step is exact (its inputs are bit-identical in both
+paths up to the layout)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from kaldi_cnn_b200 import components as kc  # noqa: E402
+from oracle.cpu_nnet import CpuNnet  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# conv (full height, 8x4: kernel rows = 32) + ReLU -> intermap pool -> 2 time-axis convs (the second
+# feeds a time pool, then ReLU) -> FC + ReLU + dropout -> FC -> softmax: every op kind of the plan and
+# every layout transition (channels-last -> channels-last, pool -> affine, affine -> channels-last).
+CFG = """
+ConvolutionComponent in-height=8 in-width=13 in-channel=1 kernel-height=8 kernel-width=4 stride=1 group=32 out-height=1 out-width=10 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5
+RectifiedLinearComponent dim=320
+MaxpoolComponent in-height=1 in-width=10 in-channel=32 pool-height-dim=1 pool-width-dim=1 pool-channel-dim=2
+ConvolutionComponent in-height=1 in-width=10 in-channel=16 kernel-height=1 kernel-width=3 stride=1 group=64 out-height=1 out-width=8 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5
+RectifiedLinearComponent dim=512
+ConvolutionComponent in-height=1 in-width=8 in-channel=64 kernel-height=1 kernel-width=3 stride=1 group=64 out-height=1 out-width=6 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5
+MaxpoolComponent in-height=1 in-width=6 in-channel=64 pool-height-dim=1 pool-width-dim=2 pool-channel-dim=1
+RectifiedLinearComponent dim=192
+FullyConnectedComponent input-dim=192 output-dim=256 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.1 weight-decay=0.0005 momentum=0.9
+RectifiedLinearComponent dim=256
+DropoutComponent dim=256 dropout-proportion=0.5 dropout-scale=0.0
+FullyConnectedComponent input-dim=256 output-dim=40 learning-rate=0.02 param-stddev=0.05 bias-stddev=0 weight-decay=0.0005 momentum=0.9
+SoftmaxComponent dim=40
+"""
+
+# a convolution feeding the affine stack directly, with a padded time-axis layer in between
+CFG_CONV_TO_FC = """
+ConvolutionComponent in-height=8 in-width=7 in-channel=2 kernel-height=8 kernel-width=4 stride=1 group=64 out-height=1 out-width=4 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5
+RectifiedLinearComponent dim=256
+ConvolutionComponent in-height=1 in-width=4 in-pad-width=1 in-channel=64 kernel-height=1 kernel-width=3 stride=1 group=96 out-height=1 out-width=4 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5
+RectifiedLinearComponent dim=384
+FullyConnectedComponent input-dim=384 output-dim=128 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.1 weight-decay=0.0005 momentum=0.9
+RectifiedLinearComponent dim=128
+FullyConnectedComponent input-dim=128 output-dim=24 learning-rate=0.02 param-stddev=0.05 bias-stddev=0 weight-decay=0.0005 momentum=0.9
+SoftmaxComponent dim=24
+"""
+
+UPDATABLE = ("ConvolutionComponent", "FullyConnectedComponent")
+
+
+def g(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def rel(a, r):
+    a, r = np.asarray(a, np.float64), np.asarray(r, np.float64)
+    return float(np.abs(a - r).max() / max(np.abs(r).max(), 1e-30))
+
+
+def params(net):
+    out = []
+    for i in range(net.num_components):
+        c = net.component(i)
+        if c.type in UPDATABLE:
+            out.append([g(c.params(k)) for k in range(3)])
+    return out
+
+
+def copy_params_to_oracle(net, cpu):
+    """Initial parameters of the device model into the oracle model (the two draw different random numbers)."""
+    for i in range(net.num_components):
+        c = net.component(i)
+        L = cpu.layers[i]
+        assert L["kind"] == c.type, (i, L["kind"], c.type)
+        if c.type == "ConvolutionComponent":
+            L["lin"], L["bias"], L["prev"] = g(c.params(0)), g(c.params(1))[0], g(c.params(2))
+            L["wd"], L["mom"] = c.weight_decay_momentum()
+        elif c.type == "FullyConnectedComponent":
+            L["W"], L["bias"], L["prev"] = g(c.params(0)), g(c.params(1))[0], g(c.params(2))
+            L["wd"], L["mom"] = c.weight_decay_momentum()
+
+
+def dropout_masks(net, cpu):
+    """The masks the device step drew, recovered from its activations (dropout out / in); where the
+    input is 0 the mask value is irrelevant to both passes (0 * m forward, ReLU gate backward)."""
+    masks = []
+    for i, L in enumerate(cpu.layers):
+        if L["kind"] == "DropoutComponent":
+            x, y = g(net.activation(i)), g(net.activation(i + 1))
+            hi = (1.0 - L["dp"] * L["scale"]) / (1.0 - L["dp"])
+            m = np.where(x != 0, y / np.where(x != 0, x, 1), hi).astype(np.float32)
+            vals = np.unique(np.round(m[x != 0], 5))
+            assert set(vals) <= {np.float32(round(hi, 5)), np.float32(round(L["scale"], 5))}, vals
+            frac = float((np.abs(m[x != 0] - hi) < 1e-4).mean())
+            assert abs(frac - (1 - L["dp"])) < 0.05, frac            # about 1 - dp of the units are kept
+            masks.append(m)
+    return masks
+
+
+def step_vs_oracle(cfg, N, seed, steps=1, tol_out=1e-3, tol_step=2e-2):
+    kc.set_math_mode(1)
+    kc.set_rand_seed(seed)
+    net = kc.Nnet.from_config(cfg)
+    cpu = CpuNnet(cfg, seed=seed)
+    copy_params_to_oracle(net, cpu)
+    rng = np.random.default_rng(seed + 1)
+    kc.use_current_stream()
+    report = {}
+    for s in range(steps):
+        before = params(net)
+        x = rng.standard_normal((N, net.input_dim)).astype(np.float32)
+        lab = rng.integers(0, net.output_dim, N).astype(np.int32)
+        xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+        net.train_step(xd, ld)
+        assert net.fused_active, "the model was expected to run as the fused plan"
+        objf = net.objf_and_reset()
+        post = g(net.activation(net.num_components))
+        cpu.forward(x, dropout_masks=dropout_masks(net, cpu))
+        objf_ref = cpu.backward(lab.astype(np.int64), update=True)
+        report["objf"] = abs(objf - objf_ref) / abs(objf_ref)
+        report["posteriors"] = rel(post, cpu.acts[-1])
+        assert report["objf"] <= tol_out and report["posteriors"] <= tol_out, report
+        after = params(net)
+        k = 0
+        for i, L in enumerate(cpu.layers):
+            if L["kind"] not in UPDATABLE:
+                continue
+            w_ref = L["lin"] if L["kind"] == "ConvolutionComponent" else L["W"]
+            refs = (w_ref, L["bias"][None, :], L["prev"])
+            for which, name in enumerate(("weights", "bias", "momentum")):
+                new, old, ref = after[k][which], before[k][which], refs[which]
+                e_val = rel(new, ref)
+                d_ref = ref.astype(np.float64) - old
+                e_step = float(np.linalg.norm(new.astype(np.float64) - ref) / max(np.linalg.norm(d_ref), 1e-30))
+                report["comp%d %s" % (i, name)] = (e_val, e_step)
+                # the momentum matrix IS a (smoothed) gradient: it carries the gradient's accumulated error
+                assert e_val <= (tol_step if name == "momentum" else tol_out), (s, i, name, e_val)
+                assert e_step <= tol_step, (s, i, name, e_step)
+            k += 1
+    kc.set_math_mode(0)
+    return report
+
+
+def test_fused_step_matches_the_oracle_step():
+    rep = step_vs_oracle(CFG, 96, seed=3, steps=3, tol_step=6e-2)
+    print(rep)
+
+
+def test_fused_step_conv_into_affine_and_padding():
+    rep = step_vs_oracle(CFG_CONV_TO_FC, 80, seed=5, steps=2, tol_step=6e-2)
+    print(rep)
+
+
+def test_benchmarked_model_full_size_step_vs_oracle():
+    """The bench.py workload itself (C2 + intermap pooling, N = 512): one whole training step,
+    objective and every updated parameter against oracle.cpu_nnet.CpuNnet."""
+    cfg = open(os.path.join(ROOT, "kaldi-cnn_b200", "configs", "nnet_c2_intermap.config")).read()
+    cfg = "\n".join(l for l in cfg.splitlines() if not l.startswith("SpliceComponent"))
+    rep = step_vs_oracle(cfg, 512, seed=42, steps=1)
+    print(rep)
+
+
+def _counts_and_stats(net):
+    text = net.write(binary=False).decode()
+    counts = [float(x) for x in re.findall(r"<Count>\s+(\S+)", text)]
+    sums = [np.array([float(v) for v in m.split()]) for m in re.findall(r"<ValueSum>\s+\[([^\]]*)\]", text)]
+    dsums = [np.array([float(v) for v in m.split()]) for m in re.findall(r"<DerivSum>\s+\[([^\]]*)\]", text)]
+    return counts, sums, dsums
+
+
+@pytest.mark.parametrize("cfg", [CFG, CFG_CONV_TO_FC], ids=["pools", "conv-to-fc"])
+def test_fused_plan_equals_component_path(cfg):
+    """Same model, same batches: the fused plan against the component-by-component path (fusion off).
+    Activations are compared in the reference layout (kcnn_nnet_activation converts), max-pool outputs
+    bit for bit where their inputs are; parameters, momentum and the NonlinearComponent statistics
+    (upstream nnet2/nnet-component.cc:337-363) to rounding-order accuracy."""
+    kc.set_math_mode(1)
+    N = 64
+    nets = []
+    for fuse in (True, False):
+        kc.set_rand_seed(21)
+        net = kc.Nnet.from_config(cfg)
+        net.set_fusion(fuse)
+        nets.append(net)
+    a, b = nets
+    rng = np.random.default_rng(8)
+    kc.use_current_stream()
+    types = [a.component(i).type for i in range(a.num_components)]
+    for step in range(3):
+        x = torch.from_numpy(rng.standard_normal((N, a.input_dim)).astype(np.float32)).cuda()
+        lab = torch.from_numpy(rng.integers(0, a.output_dim, N).astype(np.int32)).cuda()
+        for net in nets:
+            if step == 0:
+                kc.set_rand_seed(5)               # the dropout seed is drawn at the first forward pass
+            net.train_step(x, lab)
+        assert a.fused_active and not b.fused_active
+        oa, ob = a.objf_and_reset(), b.objf_and_reset()
+        assert abs(oa - ob) <= 1e-5 * abs(ob), (step, oa, ob)
+        for i, t in enumerate(types):
+            # outputs that exist in both paths: everything but the pre-activation in front of a fused ReLU
+            if i + 1 < len(types) and types[i + 1] == "RectifiedLinearComponent" and t in UPDATABLE:
+                continue
+            ya, yb = g(a.activation(i + 1)), g(b.activation(i + 1))
+            assert ya.shape == yb.shape
+            if step == 0 and t in ("RectifiedLinearComponent", "MaxpoolComponent", "DropoutComponent") and i < 3:
+                assert np.array_equal(ya, yb), (i, t)          # same GEMM, same bits, exact pooling on top
+            assert rel(ya, yb) <= 2e-5, (step, i, t, rel(ya, yb))
+    for pa, pb in zip(params(a), params(b)):
+        for which in range(3):
+            assert rel(pa[which], pb[which]) <= 2e-5, which
+    ca, sa, da = _counts_and_stats(a)
+    cb, sb, db = _counts_and_stats(b)
+    assert ca == cb and all(c == 3 * N for c in ca)
+    for u, v in zip(sa + da, sb + db):
+        assert u.shape == v.shape and np.allclose(u, v, rtol=1e-4, atol=1e-3), float(np.abs(u - v).max())
+    kc.set_math_mode(0)
+
+
+def test_fused_graph_replay_equals_eager_and_is_deterministic():
+    """TrainStep (softmax + objective inside the forward pass, the whole plan recorded into one CUDA
+    graph with its side-stream branches) gives the eager plan's numbers, and two identical runs give
+    identical bits (the batched column sums and the cluster reduction have a fixed order)."""
+    kc.set_math_mode(1)
+    N = 64
+    results = []
+    for run in range(2):
+        nets = []
+        for _ in range(2):
+            kc.set_rand_seed(11)
+            nets.append(kc.Nnet.from_config(CFG))
+        a, b = nets
+        rng = np.random.default_rng(5)
+        stream = torch.cuda.Stream()
+        x = torch.empty(N, a.input_dim, device="cuda")
+        lab = torch.empty(N, dtype=torch.int32, device="cuda")
+        replayed = []
+        with torch.cuda.stream(stream):
+            kc.use_current_stream()
+            for step in range(6):
+                x.copy_(torch.from_numpy(rng.standard_normal((N, a.input_dim)).astype(np.float32)))
+                lab.copy_(torch.from_numpy(rng.integers(0, a.output_dim, N).astype(np.int32)))
+                stream.synchronize()
+                if step == 0:
+                    kc.set_rand_seed(77)
+                a.train_step_graph(x, lab)                     # eager, record + launch, replay ...
+                replayed.append(a.last_step_replayed)
+                if step == 0:
+                    kc.set_rand_seed(77)
+                b.train_step(x, lab)                           # always eager, objective as a separate kernel
+                oa, ob = a.objf_and_reset(), b.objf_and_reset()
+                assert a.fused_active and b.fused_active
+                assert np.isfinite(oa) and abs(oa - ob) <= 1e-6 * abs(ob), (step, oa, ob)
+            stream.synchronize()
+        assert replayed == [False, True, True, True, True, True], replayed
+        pa, pb = params(a), params(b)
+        for u, v in zip(pa, pb):
+            for which in range(3):
+                assert np.array_equal(u[which], v[which]), which          # same kernels, same order: same bits
+        results.append(pa)
+        assert _counts_and_stats(a)[0] == _counts_and_stats(b)[0]
+    for u, v in zip(*results):
+        for which in range(3):
+            assert np.array_equal(u[which], v[which])
+    kc.set_math_mode(0)
+    kc.use_current_stream()
