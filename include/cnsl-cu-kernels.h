@@ -337,6 +337,13 @@ void cudaF_softmax_fprop(cudaStream_t st, const float *in, MatrixDim in_dim, flo
 void cudaF_softmax_bprop(cudaStream_t st, const float *out_value, MatrixDim out_value_dim,
                          const float *out_deriv, MatrixDim out_deriv_dim, float *in_deriv,
                          MatrixDim in_deriv_dim);
+/* NormalizeComponent (:576-639): out = in * max(2^-66, |row|^2 / D)^-0.5 per row, and its derivative
+ * in_deriv = f out_deriv - (f == 2^33 ? 0 : f^3) / D (out_deriv . in) in. */
+void cudaF_normalize_fprop(cudaStream_t st, const float *in, MatrixDim in_dim, float *out,
+                           MatrixDim out_dim);
+void cudaF_normalize_bprop(cudaStream_t st, const float *in_value, MatrixDim in_value_dim,
+                           const float *out_deriv, MatrixDim out_deriv_dim, float *in_deriv,
+                           MatrixDim in_deriv_dim);
 /* Hard-label cross-entropy: deriv[i, label_i] = 1 / post[i, label_i], else 0;
  * objf_accum[0] += sum_i log post[i, label_i] (double, device). */
 void cudaF_xent_deriv(cudaStream_t st, const float *post, MatrixDim post_dim,

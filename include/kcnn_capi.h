@@ -109,6 +109,19 @@ int kcnn_component_backprop_needs_output(const kcnn_component *c);
 int kcnn_component_propagate(const kcnn_component *c, int num_chunks,
                              const float *in, int in_rows, int in_cols, int in_stride,
                              float *out, int out_rows, int out_cols, int out_stride);
+/* The same two calls for components whose chunks hold several frames (SpliceComponent, reference
+ * nnet2/nnet-component.cc:2640-2848): in_info = ChunkInfo(input_dim, num_chunks, in_first_offset,
+ * in_last_offset), out_info likewise -- `in` has num_chunks * (in_last - in_first + 1) rows, `out`
+ * num_chunks * (out_last - out_first + 1).  backprop_chunks is for components that need neither
+ * in_value nor out_value. */
+int kcnn_component_propagate_chunks(const kcnn_component *c, int num_chunks, int in_first_offset,
+                                    int in_last_offset, int out_first_offset, int out_last_offset,
+                                    const float *in, int in_rows, int in_cols, int in_stride,
+                                    float *out, int out_rows, int out_cols, int out_stride);
+int kcnn_component_backprop_chunks(const kcnn_component *c, int num_chunks, int in_first_offset,
+                                   int in_last_offset, int out_first_offset, int out_last_offset,
+                                   const float *out_deriv, int od_rows, int od_stride,
+                                   float *in_deriv, int id_stride);
 /* Component::Backprop(in_info, out_info, in_value, out_value, out_deriv, to_update,
  * in_deriv).  in_value / out_value may be NULL when BackpropNeedsInput / Output is false.
  * to_update may be NULL (no update), c itself (ordinary SGD) or another component. */
@@ -156,7 +169,8 @@ kcnn_component *kcnn_nnet_component(kcnn_nnet *n, int index);   /* borrowed, do 
 int kcnn_nnet_input_dim(const kcnn_nnet *n);
 int kcnn_nnet_output_dim(const kcnn_nnet *n);
 
-/* Forward through every component; feats is [rows x input_dim] on the device. */
+/* Forward through every component; feats is [rows x input_dim] on the device (rows = examples x
+ * kcnn_nnet_frames_per_example()). */
 int kcnn_nnet_forward(kcnn_nnet *n, const float *feats, int rows, int stride);
 /* Propagate through components [first, last] only (first == 0 binds feats as the input; the
  * activations below first must come from an earlier call on the same batch). */
@@ -179,9 +193,15 @@ int kcnn_nnet_set_gradient_arena(kcnn_nnet *n, float *base);
 int kcnn_nnet_gradient_bucket(const kcnn_nnet *n, int component, size_t *offset, size_t *length);
 int kcnn_nnet_apply_gradients(kcnn_nnet *n, int total_rows);
 
+/* Input rows per training example: 1, or -- when the network starts with a SpliceComponent
+ * (nnet.config line 1) -- the span of its context: an nnet2 training example carries left-context + 1 +
+ * right-context frames of input_dim features for its one labelled frame, and the feature matrix holds
+ * the examples' frames back to back.  For a run of consecutive offsets the library then reads the
+ * convolution's [C][W][H] window straight from those rows (no copy, no launch). */
+int kcnn_nnet_frames_per_example(kcnn_nnet *n);
 /* The whole step from HOST memory, the call a non-CUDA host makes: copies feats
- * [rows x input_dim, packed] and labels[rows] to the device, runs forward, objective,
- * backward + update, and returns the minibatch objective in *objf (synchronous). */
+ * [rows * kcnn_nnet_frames_per_example() x input_dim, packed] and labels[rows] to the device, runs
+ * forward, objective, backward + update, and returns the minibatch objective in *objf (synchronous). */
 int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const int *labels_host,
                                    int rows, double *objf);
 /* Pipelined form of the call above for a host that streams minibatches: the caller's buffers

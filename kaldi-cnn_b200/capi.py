@@ -91,6 +91,8 @@ _PROTOS = {
     "cudaF_softmax_fprop": [S, P, M, P, M],
     "cudaF_softmax_bprop": [S, P, M, P, M, P, M],
     "cudaF_xent_deriv": [S, P, M, P, P, M, P],
+    "cudaF_normalize_fprop": [S, P, M, P, M],
+    "cudaF_normalize_bprop": [S, P, M, P, M, P, M],
     # fused training step: channels-last activations
     "kcnn_conv_time_shape_ok": [I, I, I, I, I, I],
     "kcnn_conv_full_shape_ok": [I, I, I, I, I, I],

@@ -42,6 +42,8 @@ PROTOS = {
     "kcnn_component_backprop_needs_output": ([H], c_int),
     "kcnn_component_propagate": ([H, I] + MAT + MAT, c_int),
     "kcnn_component_backprop": ([H, I, P, I, P, I, P, I, I, H, P, I], c_int),
+    "kcnn_component_propagate_chunks": ([H, I, I, I, I, I] + MAT + MAT, c_int),
+    "kcnn_component_backprop_chunks": ([H, I, I, I, I, I, P, I, I, P, I], c_int),
     "kcnn_component_params": ([H, I, PP, PI, PI, PI], c_int),
     "kcnn_component_set_learning_rate": ([H, F], c_int),
     "kcnn_component_learning_rate": ([H], c_float),
@@ -80,6 +82,7 @@ PROTOS = {
     "kcnn_nnet_last_step_replayed": ([H], c_int),
     "kcnn_nnet_set_fusion": ([H, I], c_int),
     "kcnn_nnet_fused_active": ([H], c_int),
+    "kcnn_nnet_frames_per_example": ([H], c_int),
     "kcnn_p2p_flag_floats": ([], c_size_t),
     "kcnn_p2p_allreduce_f32": ([P, P, I, I, c_size_t, c_size_t, c_size_t, I], c_int),
     "kcnn_p2p_allreduce_multicast_f32": ([P, P, ctypes.c_ulonglong, I, I, c_size_t, c_size_t, c_size_t, I], c_int),

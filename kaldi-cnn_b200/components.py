@@ -276,7 +276,7 @@ class Nnet:
         objf = ctypes.c_double()
         _check(_lib().kcnn_nnet_train_minibatch_host(
             self.h, feats_np.ctypes.data_as(ctypes.c_void_p), labels_np.ctypes.data_as(ctypes.c_void_p),
-            feats_np.shape[0], ctypes.byref(objf)))
+            labels_np.shape[0], ctypes.byref(objf)))
         return objf.value
 
     def train_minibatch_host_async(self, feats_np, labels_np):
@@ -285,7 +285,7 @@ class Nnet:
         use_current_stream()
         _check(_lib().kcnn_nnet_train_minibatch_host_async(
             self.h, feats_np.ctypes.data_as(ctypes.c_void_p), labels_np.ctypes.data_as(ctypes.c_void_p),
-            feats_np.shape[0]))
+            labels_np.shape[0]))
 
     @property
     def running_objf(self):
@@ -306,6 +306,11 @@ class Nnet:
     @property
     def last_step_replayed(self):
         return bool(_lib().kcnn_nnet_last_step_replayed(self.h))
+
+    @property
+    def frames_per_example(self):
+        """Input rows per training example (the Splice front end's context span; 1 without one)."""
+        return int(_lib().kcnn_nnet_frames_per_example(self.h))
 
     @property
     def fused_active(self):

@@ -11,6 +11,7 @@
 #include <limits>
 #include <string>
 #include <type_traits>
+#include <vector>
 
 #include "base/kaldi-error.h"
 #include "base/kaldi-types.h"
@@ -114,6 +115,36 @@ inline void ReadBasicType(std::istream &is, bool binary, T *t) {
   if (is.fail()) KALDI_ERR << "Read failure in ReadBasicType, file position is " << is.tellg()
                            << ", next char is " << is.peek();
 }
+// Floating-point values: a binary stream may hold them as float OR double (a Kaldi built with
+// --double-precision writes 8-byte reals); either width is accepted and converted, as upstream does.
+template <class Real>
+inline void ReadReal(std::istream &is, bool binary, Real *t) {
+  KALDI_ASSERT(t != NULL);
+  if (binary) {
+    const int c = is.peek();
+    if (c == static_cast<int>(sizeof(float))) {
+      float f;
+      is.get();
+      is.read(reinterpret_cast<char *>(&f), sizeof(f));
+      *t = static_cast<Real>(f);
+    } else if (c == static_cast<int>(sizeof(double))) {
+      double d;
+      is.get();
+      is.read(reinterpret_cast<char *>(&d), sizeof(d));
+      *t = static_cast<Real>(d);
+    } else {
+      KALDI_ERR << "ReadBasicType: expected float or double, saw " << c << ", at file position " << is.tellg();
+    }
+  } else {
+    is >> *t;
+  }
+  if (is.fail()) KALDI_ERR << "ReadBasicType: failed to read, at file position " << is.tellg();
+}
+template <>
+inline void ReadBasicType<float>(std::istream &is, bool binary, float *f) { ReadReal(is, binary, f); }
+template <>
+inline void ReadBasicType<double>(std::istream &is, bool binary, double *d) { ReadReal(is, binary, d); }
+
 template <>
 inline void ReadBasicType<bool>(std::istream &is, bool binary, bool *b) {
   KALDI_ASSERT(b != NULL);
@@ -123,6 +154,53 @@ inline void ReadBasicType<bool>(std::istream &is, bool binary, bool *b) {
   else if (c == 'F') { *b = false; is.get(); }
   else KALDI_ERR << "Read failure in ReadBasicType<bool>, file position is " << is.tellg()
                  << ", next char is " << c;
+}
+
+// std::vector of integers: binary = size byte, int32 count, raw values; text = "[ 1 2 3 ]\n".
+template <class T>
+inline void WriteIntegerVector(std::ostream &os, bool binary, const std::vector<T> &v) {
+  if (binary) {
+    char sz = sizeof(T);
+    os.write(&sz, 1);
+    int32 vecsz = static_cast<int32>(v.size());
+    os.write(reinterpret_cast<const char *>(&vecsz), sizeof(vecsz));
+    if (vecsz != 0) os.write(reinterpret_cast<const char *>(&v[0]), sizeof(T) * vecsz);
+  } else {
+    os << "[ ";
+    for (size_t i = 0; i < v.size(); i++) os << v[i] << " ";
+    os << "]\n";
+  }
+  if (os.fail()) KALDI_ERR << "Write failure in WriteIntegerVector.";
+}
+
+template <class T>
+inline void ReadIntegerVector(std::istream &is, bool binary, std::vector<T> *v) {
+  KALDI_ASSERT(v != NULL);
+  v->clear();
+  if (binary) {
+    int sz = is.peek();
+    if (sz != static_cast<int>(sizeof(T)))
+      KALDI_ERR << "ReadIntegerVector: expected element size " << sizeof(T) << ", saw " << sz;
+    is.get();
+    int32 vecsz;
+    is.read(reinterpret_cast<char *>(&vecsz), sizeof(vecsz));
+    if (is.fail() || vecsz < 0) KALDI_ERR << "ReadIntegerVector: bad vector size";
+    v->resize(vecsz);
+    if (vecsz > 0) is.read(reinterpret_cast<char *>(&(*v)[0]), sizeof(T) * vecsz);
+  } else {
+    is >> std::ws;
+    if (is.peek() != static_cast<int>('[')) KALDI_ERR << "ReadIntegerVector: expected [";
+    is.get();
+    is >> std::ws;
+    while (is.peek() != static_cast<int>(']')) {
+      long long x;
+      is >> x >> std::ws;
+      if (is.fail()) KALDI_ERR << "ReadIntegerVector: bad element";
+      v->push_back(static_cast<T>(x));
+    }
+    is.get();
+  }
+  if (is.fail()) KALDI_ERR << "ReadIntegerVector: read failure at file position " << is.tellg();
 }
 
 }  // namespace kaldi

@@ -71,7 +71,7 @@ struct NnetHandle {
       if (copy_stream) cudaStreamDestroy(copy_stream);
       pin_objf = NULL; copy_stream = NULL; rows = 0; dim = 0;
     }
-    void Ensure(int r, int d) {
+    void Ensure(int r, int d, int labels) {      // r feature rows (frames), d columns, `labels` examples
       if (r == rows && d == dim && copy_stream != NULL) return;
       Release();
       CU_SAFE_CALL(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
@@ -79,9 +79,9 @@ struct NnetHandle {
       pin_objf[0] = pin_objf[1] = 0.0;
       for (int i = 0; i < 2; i++) {
         CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_feats[i]), sizeof(float) * (size_t)r * d));
-        CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_labels[i]), sizeof(int32) * (size_t)r));
+        CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_labels[i]), sizeof(int32) * (size_t)labels));
         dev_feats[i].Resize(r, d, kUndefined);
-        dev_labels[i] = static_cast<int32 *>(CuDevice::Instantiate().Malloc(sizeof(int32) * (size_t)r));
+        dev_labels[i] = static_cast<int32 *>(CuDevice::Instantiate().Malloc(sizeof(int32) * (size_t)labels));
         CU_SAFE_CALL(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
         CU_SAFE_CALL(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
       }
@@ -303,6 +303,32 @@ int kcnn_component_propagate(const kcnn_component *c, int num_chunks, const floa
             out_info(ocols, num_chunks, 0, orows / (num_chunks > 0 ? num_chunks : 1) - 1);
   View I(in, ir, ic, is), O(out, orows, ocols, os);
   C(c)->Propagate(in_info, out_info, I, static_cast<CuMatrixBase<BaseFloat> *>(&O));
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_component_propagate_chunks(const kcnn_component *c, int num_chunks, int in_first_offset, int in_last_offset,
+                                    int out_first_offset, int out_last_offset, const float *in, int ir, int ic,
+                                    int is, float *out, int orows, int ocols, int os) {
+  KCNN_TRY
+  ChunkInfo in_info(ic, num_chunks, in_first_offset, in_last_offset),
+            out_info(ocols, num_chunks, out_first_offset, out_last_offset);
+  View I(in, ir, ic, is), O(out, orows, ocols, os);
+  C(c)->Propagate(in_info, out_info, I, static_cast<CuMatrixBase<BaseFloat> *>(&O));
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_component_backprop_chunks(const kcnn_component *c, int num_chunks, int in_first_offset, int in_last_offset,
+                                   int out_first_offset, int out_last_offset, const float *od, int od_rows, int ods,
+                                   float *id, int ids) {
+  KCNN_TRY
+  const Component *comp = C(c);
+  ChunkInfo in_info(comp->InputDim(), num_chunks, in_first_offset, in_last_offset),
+            out_info(comp->OutputDim(), num_chunks, out_first_offset, out_last_offset);
+  View none(NULL, 0, 0, 0), OD(od, od_rows, comp->OutputDim(), ods);
+  Borrowed ID(id, in_info.NumRows(), comp->InputDim(), ids);
+  comp->Backprop(in_info, out_info, none, none, OD, NULL, &ID.m);
   return 0;
   KCNN_CATCH(-1)
 }
@@ -556,21 +582,28 @@ int kcnn_nnet_apply_gradients(kcnn_nnet *n, int total_rows) {
   KCNN_CATCH(-1)
 }
 
+int kcnn_nnet_frames_per_example(kcnn_nnet *n) {
+  KCNN_TRY
+  return N(n)->U().FramesPerExample();
+  KCNN_CATCH(-1)
+}
+
 int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const int *labels_host,
                                    int rows, double *objf) {
   KCNN_TRY
   NnetHandle *h = N(n);
   const int dim = h->nnet.InputDim();
+  const int frames = rows * h->U().FramesPerExample();
   cudaStream_t st = CuDevice::Instantiate().Stream();
-  if (h->host_feats.NumRows() != rows || h->host_feats.NumCols() != dim)
-    h->host_feats.Resize(rows, dim, kUndefined);
+  if (h->host_feats.NumRows() != frames || h->host_feats.NumCols() != dim)
+    h->host_feats.Resize(frames, dim, kUndefined);
   if (h->host_labels_rows != rows) {
     if (h->host_labels_dev) CuDevice::Instantiate().Free(h->host_labels_dev);
     h->host_labels_dev = static_cast<int32 *>(CuDevice::Instantiate().Malloc(sizeof(int32) * rows));
     h->host_labels_rows = rows;
   }
   CU_SAFE_CALL(cudaMemcpy2DAsync(h->host_feats.Data(), sizeof(float) * h->host_feats.Stride(), feats_host,
-                                 sizeof(float) * dim, sizeof(float) * dim, rows, cudaMemcpyHostToDevice, st));
+                                 sizeof(float) * dim, sizeof(float) * dim, frames, cudaMemcpyHostToDevice, st));
   CU_SAFE_CALL(cudaMemcpyAsync(h->host_labels_dev, labels_host, sizeof(int32) * rows,
                                cudaMemcpyHostToDevice, st));
   h->U().TrainStep(h->host_feats, h->host_labels_dev);
@@ -587,17 +620,18 @@ int kcnn_nnet_train_minibatch_host_async(kcnn_nnet *n, const float *feats_host, 
   const int dim = h->nnet.InputDim();
   cudaStream_t st = CuDevice::Instantiate().Stream();
   NnetHandle::Pipe &p = h->pipe;
-  p.Ensure(rows, dim);
+  const int frames = rows * h->U().FramesPerExample();
+  p.Ensure(frames, dim, rows);
   const int s = (int)(p.step & 1ull);
   // the pinned slot is free once ITS previous copy (two calls ago) has run; then the caller's
   // buffers are staged and belong to the caller again as soon as this call returns
   CU_SAFE_CALL(cudaEventSynchronize(p.copied[s]));
-  memcpy(p.pin_feats[s], feats_host, sizeof(float) * (size_t)rows * dim);
+  memcpy(p.pin_feats[s], feats_host, sizeof(float) * (size_t)frames * dim);
   memcpy(p.pin_labels[s], labels_host, sizeof(int32) * (size_t)rows);
   // the device slot is free once the step that read it (two calls ago) has finished
   CU_SAFE_CALL(cudaStreamWaitEvent(p.copy_stream, p.done[s], 0));
   CU_SAFE_CALL(cudaMemcpy2DAsync(p.dev_feats[s].Data(), sizeof(float) * p.dev_feats[s].Stride(), p.pin_feats[s],
-                                 sizeof(float) * dim, sizeof(float) * dim, rows, cudaMemcpyHostToDevice,
+                                 sizeof(float) * dim, sizeof(float) * dim, frames, cudaMemcpyHostToDevice,
                                  p.copy_stream));
   CU_SAFE_CALL(cudaMemcpyAsync(p.dev_labels[s], p.pin_labels[s], sizeof(int32) * rows, cudaMemcpyHostToDevice,
                                p.copy_stream));

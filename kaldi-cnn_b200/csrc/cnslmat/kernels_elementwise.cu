@@ -239,6 +239,38 @@ xent_deriv_kernel(const float *__restrict__ post, int post_stride, const int *__
   deriv[(size_t)i * deriv_stride + j] = v;
 }
 
+// NormalizeComponent (upstream nnet2/nnet-component.cc:576-639): one block per row.
+//   f = max(2^-66, |x|^2 / D)^-0.5 ; fprop: y = f x ; bprop: dx = f dy - (f == 2^33 ? 0 : f^3) / D (dy . x) x
+template <bool kBackward>
+__global__ void __launch_bounds__(256)
+normalize_kernel(const float *__restrict__ in, int in_stride, const float *__restrict__ od, int od_stride,
+                 float *__restrict__ out, int out_stride, int cols) {
+  kcnn::pdl_prologue();
+  __shared__ float scratch[32];
+  const float *x = in + (size_t)blockIdx.x * in_stride;
+  const float *d = kBackward ? od + (size_t)blockIdx.x * od_stride : nullptr;
+  float *o = out + (size_t)blockIdx.x * out_stride;
+  float ss = 0.0f, dot = 0.0f;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float v = __ldg(x + j);
+    ss = fmaf(v, v, ss);
+    if (kBackward) dot = fmaf(__ldg(d + j), v, dot);
+  }
+  ss = block_reduce(ss, scratch, false);
+  if (kBackward) dot = block_reduce(dot, scratch, false);
+  const float floor_p = 1.3552527156068805e-20f;                     // 2^-66, kNormFloor
+  float p = ss * (1.0f / (float)cols);
+  if (p < floor_p) p = floor_p;
+  const float f = 1.0f / sqrtf(p);
+  if (!kBackward) {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) o[j] = __ldg(x + j) * f;
+    return;
+  }
+  const float g = (p == floor_p) ? 0.0f : f * f * f;                 // ReplaceValue(1 / sqrt(floor), 0), ApplyPow(3)
+  const float c = (-1.0f / (float)cols) * (dot * g);
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) o[j] = fmaf(c, __ldg(x + j), f * __ldg(d + j));
+}
+
 static bool vec4_ok(int cols, std::initializer_list<int> strides,
                     std::initializer_list<const void *> ptrs) {
   if (cols % 4) return false;
@@ -321,6 +353,18 @@ void cudaF_softmax_bprop(cudaStream_t st, const float *ov, MatrixDim ovd, const 
   else
     KCNN_LAUNCH(softmax_bprop_kernel<false>, idd.rows, 256, 0, st, ov, ovd.stride, od, odd.stride, id,
                 idd.stride, idd.cols);
+}
+
+void cudaF_normalize_fprop(cudaStream_t st, const float *in, MatrixDim id, float *out, MatrixDim od) {
+  if (od.rows == 0 || od.cols == 0) return;
+  KCNN_LAUNCH(normalize_kernel<false>, od.rows, 256, 0, st, in, id.stride, nullptr, 0, out, od.stride, od.cols);
+}
+
+void cudaF_normalize_bprop(cudaStream_t st, const float *in_value, MatrixDim ivd, const float *out_deriv,
+                           MatrixDim odd, float *in_deriv, MatrixDim idd) {
+  if (idd.rows == 0 || idd.cols == 0) return;
+  KCNN_LAUNCH(normalize_kernel<true>, idd.rows, 256, 0, st, in_value, ivd.stride, out_deriv, odd.stride, in_deriv,
+              idd.stride, idd.cols);
 }
 
 void cudaF_xent_deriv(cudaStream_t st, const float *post, MatrixDim pd, const int *labels,

@@ -1,5 +1,7 @@
 // matrix/kaldi-matrix-io.cc -- shim: Kaldi's matrix / vector stream formats
 // ("FM " / "FV " headers in binary mode; " [ ... ]" in text mode).
+#include <cctype>
+#include <cstdio>
 #include <cstdlib>
 #include "matrix/matrix-lib.h"
 
@@ -41,17 +43,24 @@ void MatrixBase<Real>::Write(std::ostream &os, bool binary) const {
   }
 }
 
+// One number of a text matrix / vector.  Characters are consumed one at a time up to (not including)
+// white space or a bracket, so a closing bracket glued to the last number ("1.5]") stays in the stream
+// without any putback (an ifstream only guarantees one character of putback).
 static bool ParseReal(std::istream &is, double *v) {
+  is >> std::ws;
   std::string tok;
-  is >> tok;
-  if (is.fail()) return false;
-  // the closing bracket may be glued to the last number
-  const char *s = tok.c_str();
+  for (;;) {
+    const int c = is.peek();
+    if (c == EOF) break;
+    const char ch = static_cast<char>(c);
+    if (isspace(static_cast<unsigned char>(ch)) || ch == ']' || ch == '[') break;
+    tok.push_back(ch);
+    is.get();
+  }
+  if (tok.empty()) return false;
   char *end = NULL;
-  *v = strtod(s, &end);
-  if (end == s) return false;
-  for (const char *p = tok.c_str() + tok.size(); p != end; ) is.putback(*--p);
-  return true;
+  *v = strtod(tok.c_str(), &end);
+  return end == tok.c_str() + tok.size();
 }
 
 template <typename Real>

@@ -64,6 +64,10 @@ Component *Component::NewComponentOfType(const std::string &component_type) {
     ans = new AffineComponent();
   } else if (component_type == "DropoutComponent") {
     ans = new DropoutComponent();
+  } else if (component_type == "NormalizeComponent") {
+    ans = new NormalizeComponent();
+  } else if (component_type == "SpliceComponent") {
+    ans = new SpliceComponent();
   } else if (component_type == "ConvolutionComponent") {       // reference :112-113
     ans = new cnsl::nnet0::ConvolutionComponent();
   } else if (component_type == "MaxpoolComponent") {           // reference :114-115
@@ -496,6 +500,231 @@ void SoftmaxComponent::Backprop(const ChunkInfo &, const ChunkInfo &, const CuMa
                       in_deriv->Data(), in_deriv->Dim());
   if (to_update != NULL)
     dynamic_cast<NonlinearComponent *>(to_update)->UpdateStats(out_value, false);
+}
+
+// --------------------------------------------------------- NormalizeComponent --
+
+// reference :580-592 (CopyFromMat, AddDiagMat2, ApplyFloor, ApplyPow, MulRowsVec) as one kernel
+void NormalizeComponent::Propagate(const ChunkInfo &, const ChunkInfo &, const CuMatrixBase<BaseFloat> &in,
+                                   CuMatrixBase<BaseFloat> *out) const {
+  KALDI_ASSERT(in.NumRows() == out->NumRows() && in.NumCols() == out->NumCols());
+  cudaF_normalize_fprop(Str(), in.Data(), in.Dim(), out->Data(), out->Dim());
+  CU_SAFE_CALL(cudaGetLastError());
+}
+
+// reference :616-639 as one kernel
+void NormalizeComponent::Backprop(const ChunkInfo &, const ChunkInfo &, const CuMatrixBase<BaseFloat> &in_value,
+                                  const CuMatrixBase<BaseFloat> &, const CuMatrixBase<BaseFloat> &out_deriv,
+                                  Component *, CuMatrix<BaseFloat> *in_deriv) const {
+  KALDI_ASSERT(in_value.NumRows() == out_deriv.NumRows() && in_value.NumCols() == out_deriv.NumCols());
+  in_deriv->Resize(out_deriv.NumRows(), out_deriv.NumCols(), kUndefined);
+  cudaF_normalize_bprop(Str(), in_value.Data(), in_value.Dim(), out_deriv.Data(), out_deriv.Dim(), in_deriv->Data(),
+                        in_deriv->Dim());
+  CU_SAFE_CALL(cudaGetLastError());
+}
+
+// ------------------------------------------------------------ SpliceComponent --
+
+namespace {
+// out[(chunk, oi)][c * dim + j] = in[(chunk, map[c][oi])][j]; the last const_dim columns come from
+// input frame oi of the chunk.  One thread per output element, rows contiguous.
+__global__ void __launch_bounds__(256)
+splice_fprop_kernel(const float *__restrict__ in, int in_stride, float *__restrict__ out, int out_stride,
+                    long long total, int out_cols, int dim, int const_dim, int num_splice, int in_chunk,
+                    int out_chunk, const int *__restrict__ map, kcnn::FastDiv div_cols, kcnn::FastDiv div_dim,
+                    kcnn::FastDiv div_oc) {
+  kcnn::pdl_prologue();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t row, col, chunk, oi;
+  div_cols.divmod((uint32_t)t, row, col);
+  div_oc.divmod(row, chunk, oi);
+  int src_row, src_col;
+  if ((int)col < num_splice * dim) {
+    uint32_t c, j;
+    div_dim.divmod(col, c, j);
+    src_row = (int)chunk * in_chunk + __ldg(map + c * out_chunk + oi);
+    src_col = (int)j;
+  } else {
+    src_row = (int)chunk * in_chunk + (int)oi;
+    src_col = dim + ((int)col - num_splice * dim);
+  }
+  out[(size_t)row * out_stride + col] = __ldg(in + (size_t)src_row * in_stride + src_col);
+}
+
+// in_deriv[(chunk, ii)][j] = sum over (c, oi) with map[c][oi] == ii of out_deriv[(chunk, oi)][c * dim + j]
+// (gather form of the reference's CopyRows + AddMat chain, :2745-2848; fixed summation order c, oi)
+__global__ void __launch_bounds__(256)
+splice_bprop_kernel(const float *__restrict__ od, int od_stride, float *__restrict__ id, int id_stride,
+                    long long total, int in_cols, int dim, int const_dim, int num_splice, int in_chunk,
+                    int out_chunk, const int *__restrict__ map, kcnn::FastDiv div_cols, kcnn::FastDiv div_ic) {
+  kcnn::pdl_prologue();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t row, col, chunk, ii;
+  div_cols.divmod((uint32_t)t, row, col);
+  div_ic.divmod(row, chunk, ii);
+  float s = 0.0f;
+  if ((int)col < dim) {
+    for (int c = 0; c < num_splice; c++)
+      for (int oi = 0; oi < out_chunk; oi++)
+        if (__ldg(map + c * out_chunk + oi) == (int)ii)
+          s += __ldg(od + ((size_t)chunk * out_chunk + oi) * od_stride + c * dim + col);
+  } else if ((int)ii < out_chunk) {
+    s = __ldg(od + ((size_t)chunk * out_chunk + ii) * od_stride + num_splice * dim + ((int)col - dim));
+  }
+  id[(size_t)row * id_stride + col] = s;
+}
+}  // namespace
+
+SpliceComponent::~SpliceComponent() {
+  if (map_dev_) CuDevice::Instantiate().Free(map_dev_);
+}
+
+void SpliceComponent::Init(int32 input_dim, std::vector<int32> context, int32 const_component_dim) {
+  input_dim_ = input_dim;
+  const_component_dim_ = const_component_dim;
+  context_ = context;
+  KALDI_ASSERT(context_.size() > 0);
+  KALDI_ASSERT(input_dim_ > 0 && context_.front() <= 0 && context_.back() >= 0);
+  for (size_t i = 1; i < context_.size(); i++) KALDI_ASSERT(context_[i] > context_[i - 1]);   // sorted, unique
+  KALDI_ASSERT(const_component_dim_ >= 0 && const_component_dim_ < input_dim_);
+}
+
+// "input-dim=40 left-context=10 right-context=10 [const-component-dim=0]" or "input-dim=40 context=-2:0:2"
+void SpliceComponent::InitFromString(std::string args) {
+  const std::string orig_args(args);
+  int32 input_dim = 0, left_context = 0, right_context = 0, const_component_dim = 0;
+  std::vector<int32> context;
+  const bool in_dim_ok = ParseFromString("input-dim", &args, &input_dim);
+  const bool context_ok = ParseFromString("context", &args, &context);
+  const bool left_ok = ParseFromString("left-context", &args, &left_context);
+  const bool right_ok = ParseFromString("right-context", &args, &right_context);
+  ParseFromString("const-component-dim", &args, &const_component_dim);
+  if (!(in_dim_ok && (context_ok || (left_ok && right_ok))) || !args.empty() || input_dim <= 0)
+    KALDI_ERR << "Invalid initializer for layer of type " << Type() << ": \"" << orig_args << "\"";
+  if (left_ok && right_ok) {
+    KALDI_ASSERT(context.size() == 0);
+    for (int32 i = -left_context; i <= right_context; i++) context.push_back(i);
+  }
+  Init(input_dim, context, const_component_dim);
+}
+
+int32 SpliceComponent::OutputDim() const {
+  return (input_dim_ - const_component_dim_) * static_cast<int32>(context_.size()) + const_component_dim_;
+}
+
+bool SpliceComponent::IsContiguousWindow() const {
+  if (const_component_dim_ != 0 || context_.empty()) return false;
+  for (size_t i = 1; i < context_.size(); i++)
+    if (context_[i] != context_[i - 1] + 1) return false;
+  return true;
+}
+
+std::string SpliceComponent::Info() const {
+  std::stringstream stream;
+  stream << Component::Info() << ", context=";
+  for (size_t i = 0; i < context_.size(); i++) stream << context_[i] << " ";
+  if (const_component_dim_ != 0) stream << ", const_component_dim=" << const_component_dim_;
+  return stream.str();
+}
+
+const int32 *SpliceComponent::FrameMap(const ChunkInfo &in_info, const ChunkInfo &out_info) const {
+  const int32 out_chunk = out_info.ChunkSize(), num_splice = static_cast<int32>(context_.size());
+  std::vector<int32> map(static_cast<size_t>(num_splice) * out_chunk);
+  for (int32 c = 0; c < num_splice; c++)
+    for (int32 oi = 0; oi < out_chunk; oi++)
+      map[c * out_chunk + oi] = in_info.GetIndex(out_info.GetOffset(oi) + context_[c]);     // reference :2670-2676
+  const uint64 key = HashBytes(map.data(), sizeof(int32) * map.size(), 1469598103934665603ull) | 1;
+  if (key != map_key_ || map.size() != map_len_) {
+    if (map_dev_) CuDevice::Instantiate().Free(map_dev_);
+    map_dev_ = static_cast<int32 *>(CuDevice::Instantiate().Malloc(sizeof(int32) * map.size()));
+    CU_SAFE_CALL(cudaMemcpyAsync(map_dev_, map.data(), sizeof(int32) * map.size(), cudaMemcpyHostToDevice, Str()));
+    CU_SAFE_CALL(cudaStreamSynchronize(Str()));
+    map_len_ = map.size();
+    map_key_ = key;
+  }
+  return map_dev_;
+}
+
+// reference :2640-2722: one gather kernel instead of one CopyRows per context offset
+void SpliceComponent::Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                                const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) const {
+  in_info.Check();
+  out_info.Check();
+  in_info.CheckSize(in);
+  out_info.CheckSize(*out);
+  KALDI_ASSERT(in_info.NumChunks() == out_info.NumChunks());
+  const int32 in_chunk = in_info.ChunkSize(), out_chunk = out_info.ChunkSize();
+  if (out_chunk <= 0) KALDI_ERR << "Splicing features: output will have zero dimension. Probably a code error.";
+  const int32 dim = input_dim_ - const_component_dim_, num_splice = static_cast<int32>(context_.size());
+  const int32 *map = FrameMap(in_info, out_info);
+  const long long total = (long long)out->NumRows() * out->NumCols();
+  if (total == 0) return;
+  KCNN_LAUNCH(splice_fprop_kernel, kcnn::ceil_div_u(total, 256), 256, 0, Str(), in.Data(), in.Stride(), out->Data(),
+              out->Stride(), total, out->NumCols(), dim, const_component_dim_, num_splice, in_chunk, out_chunk, map,
+              kcnn::FastDiv((uint32_t)out->NumCols()), kcnn::FastDiv((uint32_t)dim), kcnn::FastDiv((uint32_t)out_chunk));
+  CU_SAFE_CALL(cudaGetLastError());
+}
+
+// reference :2724-2848
+void SpliceComponent::Backprop(const ChunkInfo &in_info, const ChunkInfo &out_info, const CuMatrixBase<BaseFloat> &,
+                               const CuMatrixBase<BaseFloat> &, const CuMatrixBase<BaseFloat> &out_deriv, Component *,
+                               CuMatrix<BaseFloat> *in_deriv) const {
+  in_info.Check();
+  out_info.Check();
+  out_info.CheckSize(out_deriv);
+  in_deriv->Resize(in_info.NumRows(), in_info.NumCols(), kUndefined);
+  KALDI_ASSERT(in_info.NumChunks() == out_info.NumChunks() && OutputDim() == out_deriv.NumCols());
+  const int32 in_chunk = in_info.ChunkSize(), out_chunk = out_info.ChunkSize();
+  const int32 dim = input_dim_ - const_component_dim_, num_splice = static_cast<int32>(context_.size());
+  const int32 *map = FrameMap(in_info, out_info);
+  const long long total = (long long)in_deriv->NumRows() * in_deriv->NumCols();
+  if (total == 0) return;
+  KCNN_LAUNCH(splice_bprop_kernel, kcnn::ceil_div_u(total, 256), 256, 0, Str(), out_deriv.Data(), out_deriv.Stride(),
+              in_deriv->Data(), in_deriv->Stride(), total, in_deriv->NumCols(), dim, const_component_dim_, num_splice,
+              in_chunk, out_chunk, map, kcnn::FastDiv((uint32_t)in_deriv->NumCols()), kcnn::FastDiv((uint32_t)in_chunk));
+  CU_SAFE_CALL(cudaGetLastError());
+}
+
+Component *SpliceComponent::Copy() const {
+  SpliceComponent *ans = new SpliceComponent();
+  ans->Init(input_dim_, context_, const_component_dim_);
+  return ans;
+}
+
+// token stream of reference :2857-2890 (either <LeftContext> <RightContext> or <Context> on input)
+void SpliceComponent::Read(std::istream &is, bool binary) {
+  ExpectOneOrTwoTokens(is, binary, "<SpliceComponent>", "<InputDim>");
+  ReadBasicType(is, binary, &input_dim_);
+  std::string token;
+  ReadToken(is, false, &token);
+  context_.clear();
+  if (token == "<LeftContext>") {
+    int32 left_context = 0, right_context = 0;
+    ReadBasicType(is, binary, &left_context);
+    ExpectToken(is, binary, "<RightContext>");
+    ReadBasicType(is, binary, &right_context);
+    for (int32 i = -left_context; i <= right_context; i++) context_.push_back(i);
+  } else if (token == "<Context>") {
+    ReadIntegerVector(is, binary, &context_);
+  } else {
+    KALDI_ERR << "Unknown token" << token << ", the model might be corrupted";
+  }
+  ExpectToken(is, binary, "<ConstComponentDim>");
+  ReadBasicType(is, binary, &const_component_dim_);
+  ExpectToken(is, binary, "</SpliceComponent>");
+}
+
+void SpliceComponent::Write(std::ostream &os, bool binary) const {
+  WriteToken(os, binary, "<SpliceComponent>");
+  WriteToken(os, binary, "<InputDim>");
+  WriteBasicType(os, binary, input_dim_);
+  WriteToken(os, binary, "<Context>");
+  WriteIntegerVector(os, binary, context_);
+  WriteToken(os, binary, "<ConstComponentDim>");
+  WriteBasicType(os, binary, const_component_dim_);
+  WriteToken(os, binary, "</SpliceComponent>");
 }
 
 // ----------------------------------------------------------- DropoutComponent --

@@ -273,6 +273,74 @@ class SoftmaxComponent : public NonlinearComponent {
   SoftmaxComponent &operator=(const SoftmaxComponent &other);  // Disallow.
 };
 
+/// reference nnet2/nnet-component.cc:576-639.  Scales every row to unit root-mean-square (floor 2^-66
+/// on the mean square); the statistics of NonlinearComponent are carried but not updated, as upstream.
+class NormalizeComponent : public NonlinearComponent {
+ public:
+  explicit NormalizeComponent(int32 dim) : NonlinearComponent(dim) {}
+  explicit NormalizeComponent(const NormalizeComponent &other) : NonlinearComponent(other) {}
+  NormalizeComponent() {}
+  virtual std::string Type() const { return "NormalizeComponent"; }
+  virtual Component *Copy() const { return new NormalizeComponent(*this); }
+  virtual bool BackpropNeedsInput() const { return true; }
+  virtual bool BackpropNeedsOutput() const { return true; }
+  using Component::Propagate;
+  virtual void Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                         const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) const;
+  virtual void Backprop(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                        const CuMatrixBase<BaseFloat> &in_value,
+                        const CuMatrixBase<BaseFloat> &out_value,
+                        const CuMatrixBase<BaseFloat> &out_deriv, Component *to_update,
+                        CuMatrix<BaseFloat> *in_deriv) const;
+ private:
+  NormalizeComponent &operator=(const NormalizeComponent &other);  // Disallow.
+};
+
+/// reference nnet2/nnet-component.h:1092-1129, .cc:2524-2866.  Splices the frames at the offsets in
+/// `context` around each output frame: the front end that turns [chunks x frames, input-dim] filterbank
+/// rows into the [C][W][H] window the first convolution reads (nnet.config line 1).  The last
+/// const-component-dim columns are copied once instead of being spliced.
+class SpliceComponent : public Component {
+ public:
+  SpliceComponent() : input_dim_(0), const_component_dim_(0), map_dev_(NULL), map_len_(0), map_key_(0) {}
+  virtual ~SpliceComponent();
+  void Init(int32 input_dim, std::vector<int32> context, int32 const_component_dim = 0);
+  virtual std::string Type() const { return "SpliceComponent"; }
+  virtual std::string Info() const;
+  virtual void InitFromString(std::string args);
+  virtual int32 InputDim() const { return input_dim_; }
+  virtual int32 OutputDim() const;
+  virtual std::vector<int32> Context() const { return context_; }
+  int32 ConstComponentDim() const { return const_component_dim_; }
+  /// True when the context is a run of consecutive offsets and nothing is held constant: a chunk of
+  /// context.size() input frames with ONE output frame is then a plain reshape of the input rows.
+  bool IsContiguousWindow() const;
+  using Component::Propagate;
+  virtual void Propagate(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                         const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) const;
+  virtual void Backprop(const ChunkInfo &in_info, const ChunkInfo &out_info,
+                        const CuMatrixBase<BaseFloat> &in_value,
+                        const CuMatrixBase<BaseFloat> &out_value,
+                        const CuMatrixBase<BaseFloat> &out_deriv, Component *to_update,
+                        CuMatrix<BaseFloat> *in_deriv) const;
+  virtual bool BackpropNeedsInput() const { return false; }
+  virtual bool BackpropNeedsOutput() const { return false; }
+  virtual Component *Copy() const;
+  virtual void Read(std::istream &is, bool binary);
+  virtual void Write(std::ostream &os, bool binary) const;
+ private:
+  KALDI_DISALLOW_COPY_AND_ASSIGN(SpliceComponent);
+  /// Device table [context.size() x out_chunk_size] of the input frame (within a chunk) each spliced
+  /// block of each output frame of a chunk comes from; cached per (in_info, out_info) shape.
+  const int32 *FrameMap(const ChunkInfo &in_info, const ChunkInfo &out_info) const;
+  int32 input_dim_;
+  std::vector<int32> context_;
+  int32 const_component_dim_;
+  mutable int32 *map_dev_;
+  mutable size_t map_len_;
+  mutable uint64 map_key_;
+};
+
 /// reference nnet2/nnet-component.cc:3560-3640.  out = in .* mask, where a proportion
 /// dp of the mask is dropout_scale and the rest (1 - dp*scale)/(1 - dp).
 class DropoutComponent : public Component {

@@ -105,8 +105,8 @@ bool NnetMinibatchUpdater::PlanFused() {
   key = Component::HashValue(fuse_, key);
   key = Component::HashValue(L, key);
   // the first op reads the caller's buffer through a tensor map: its alignment is part of the plan
-  key = Component::HashValue(reinterpret_cast<uintptr_t>(forward_[0].Data()) & 15u, key);
-  key = Component::HashValue(forward_[0].Stride() & 3, key);
+  key = Component::HashValue(reinterpret_cast<uintptr_t>(forward_[base_].Data()) & 15u, key);
+  key = Component::HashValue(forward_[base_].Stride() & 3, key);
   for (int32 c = 0; c < L; c++) {
     const Component &comp = nnet_->GetComponent(c);
     key = Component::HashValue(&comp, key);
@@ -128,14 +128,15 @@ bool NnetMinibatchUpdater::PlanFused() {
   F.fork_fc = fork_fc != 0;
   if (!enabled || !fuse_ || CuDevice::Instantiate().MathMode() != KCNN_MATH_TF32_TC || num_rows_ <= 0 || L < 2)
     return false;
-  if ((reinterpret_cast<uintptr_t>(forward_[0].Data()) & 15u) != 0 || (forward_[0].Stride() & 3) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(forward_[base_].Data()) & 15u) != 0 || (forward_[base_].Stride() & 3) != 0)
+    return false;
 
   // ---- group the components into ops
   std::vector<FusedOp> ops;
   std::vector<int32> op_of_comp(L, -1);
   int32 producer = -1;
   bool seen_updatable = false;
-  for (int32 c = 0; c < L;) {
+  for (int32 c = base_; c < L;) {          // (a Splice front end is a view of the input, not an op)
     Component &comp = nnet_->GetComponent(c);
     FusedOp op;
     memset(&op, 0, sizeof(op));
@@ -151,11 +152,11 @@ bool NnetMinibatchUpdater::PlanFused() {
       op.W = cv->In_width(); op.C = cv->In_channels(); op.OW = cv->Out_width(); op.G = cv->Group();
       if (cv->In_height() == 1 && cv->Kernel_height() == 1 && cv->In_pad_height() == 0 && cv->Out_height() == 1) {
         op.kind = FusedOp::kConvTime;
-        if (c == 0) return false;                      // a time-axis layer on the raw input: component path
+        if (c == base_) return false;                  // a time-axis layer on the raw input: component path
         if (!kcnn_conv_time_shape_ok(num_rows_, op.W, op.C, cv->In_pad_width(), cv->Kernel_width(), op.G))
           return false;
       } else if (cv->Kernel_height() == cv->In_height() && cv->In_pad_height() == 0 && cv->In_pad_width() == 0 &&
-                 cv->Out_height() == 1 && c == 0) {
+                 cv->Out_height() == 1 && c == base_) {
         op.kind = FusedOp::kConvFull;
         if (!kcnn_conv_full_shape_ok(num_rows_, cv->In_height(), op.W, op.C, cv->Kernel_width(), op.G)) return false;
       } else {
@@ -350,7 +351,7 @@ void NnetMinibatchUpdater::FusedForward(int32 first, int32 last, const int32 *la
       case FusedOp::kSoftmax: {
         CuMatrix<BaseFloat> &post = forward_[op.out];
         bool fused = false;
-        if (labels_dev != NULL && first == 0) {
+        if (labels_dev != NULL && first == base_) {
           // the whole step is known: softmax, objective, derivative and softmax backward at once
           derivs_[op.in].Resize(num_rows_, in.NumCols(), kUndefined);
           fused = cudaF_softmax_xent(st, in.Data(), in.Dim(), post.Data(), post.Dim(), labels_dev,

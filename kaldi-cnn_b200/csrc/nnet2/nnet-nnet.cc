@@ -108,8 +108,9 @@ struct NnetMinibatchUpdater::GraphState {
 
 NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
     : graph_(new GraphState), last_replayed_(false), fuse_(true),
-      nnet_(nnet), num_rows_(0), fused_(NULL), step_labels_(NULL), labels_(NULL), objf_dev_(NULL) {
+      nnet_(nnet), num_rows_(0), fused_(NULL), step_labels_(NULL), base_(0), labels_(NULL), objf_dev_(NULL) {
   FusedInit();
+  if (nnet_->NumComponents() > 1 && dynamic_cast<SpliceComponent *>(&nnet_->GetComponent(0)) != NULL) base_ = 1;
   objf_dev_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double)));
   CU_SAFE_CALL(cudaMemsetAsync(objf_dev_, 0, sizeof(double), Str()));
   const char *fe = getenv("KCNN_NNET_FUSE");
@@ -136,28 +137,61 @@ void NnetMinibatchUpdater::Forward(const CuMatrixBase<BaseFloat> &feats) {
   ForwardRange(feats, 0, nnet_->NumComponents() - 1);
 }
 
+int32 NnetMinibatchUpdater::FramesPerExample() const {
+  if (base_ == 0) return 1;
+  const std::vector<int32> ctx = nnet_->GetComponent(0).Context();
+  return ctx.back() - ctx.front() + 1;
+}
+
 void NnetMinibatchUpdater::ForwardRange(const CuMatrixBase<BaseFloat> &feats, int32 first, int32 last) {
   const int32 L = nnet_->NumComponents();
   KALDI_ASSERT(L > 0 && feats.NumCols() == nnet_->InputDim());
   KALDI_ASSERT(first >= 0 && last < L);
-  if (num_rows_ != feats.NumRows() || static_cast<int32>(forward_.size()) != L + 1) {
-    num_rows_ = feats.NumRows();
+  const int32 span = FramesPerExample();
+  if (feats.NumRows() % span != 0)
+    KALDI_ERR << "the input has " << feats.NumRows() << " rows, not a multiple of the " << span
+              << " frames per example the SpliceComponent needs";
+  const int32 rows = feats.NumRows() / span;
+  if (num_rows_ != rows || static_cast<int32>(forward_.size()) != L + 1) {
+    num_rows_ = rows;
     forward_.clear();
     forward_.resize(L + 1);
     info_.clear();
-    info_.push_back(ChunkInfo(nnet_->InputDim(), num_rows_, 0, 0));
+    info_.push_back(ChunkInfo(nnet_->InputDim(), num_rows_, 0, span - 1));
     for (int32 c = 0; c < L; c++) {
       int32 dim = nnet_->GetComponent(c).OutputDim();
-      info_.push_back(ChunkInfo(dim, num_rows_, 0, 0));
-      forward_[c + 1].Resize(num_rows_, dim, kUndefined);
+      if (c < base_) {          // the Splice output: one frame per example, at offset left-context
+        const int32 left = -nnet_->GetComponent(0).Context().front();
+        info_.push_back(ChunkInfo(dim, num_rows_, left, left));
+      } else {
+        info_.push_back(ChunkInfo(dim, num_rows_, 0, 0));
+        forward_[c + 1].Resize(num_rows_, dim, kUndefined);
+      }
     }
     derivs_.clear();
     derivs_.resize(L + 1);
   }
   // the input is used in place (a borrowed view), not copied
-  if (first == 0)
+  if (first == 0) {
     forward_[0].Borrow(const_cast<BaseFloat *>(feats.Data()), feats.NumRows(), feats.NumCols(),
                        feats.Stride());
+    if (base_ == 1) {
+      const SpliceComponent &sp = static_cast<const SpliceComponent &>(nnet_->GetComponent(0));
+      if (sp.IsContiguousWindow() && feats.Stride() == feats.NumCols()) {
+        // [examples * span x dim] dense IS [examples x span * dim]: the Splice is a change of view
+        forward_[1].Borrow(const_cast<BaseFloat *>(feats.Data()), num_rows_, span * feats.NumCols(),
+                           span * feats.NumCols());
+      } else {
+        // gapped context / constant columns / pitched input: gather into a buffer of our own
+        if (splice_out_.NumRows() != num_rows_ || splice_out_.NumCols() != sp.OutputDim())
+          splice_out_.Resize(num_rows_, sp.OutputDim(), kUndefined);
+        forward_[1].Borrow(splice_out_.Data(), num_rows_, sp.OutputDim(), splice_out_.Stride());
+        sp.Propagate(info_[0], info_[1], forward_[0], static_cast<CuMatrixBase<BaseFloat> *>(&forward_[1]));
+      }
+    }
+  }
+  if (first < base_) first = base_;
+  if (last < first) return;
   if (PlanFused()) {
     FusedForward(first, last, step_labels_);
     return;
@@ -192,6 +226,8 @@ void NnetMinibatchUpdater::Backward(int32 last, int32 first) {
   const int32 L = nnet_->NumComponents();
   if (last < 0) last = L - 1;
   KALDI_ASSERT(first >= 0 && last < L && !forward_.empty());
+  if (first < base_) first = base_;       // nothing trains below the Splice front end (nnet2 stops there too)
+  if (last < first) return;
   if (FusedActive()) {
     FusedBackward(last, first);
     return;

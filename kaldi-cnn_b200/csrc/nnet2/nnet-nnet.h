@@ -20,8 +20,8 @@ class Nnet {
   Nnet() {}
   ~Nnet() { Destroy(); }
   /// One component per config line ("Type key=value ..."), as nnet-init does.
-  /// SpliceComponent lines are skipped when skip_splice is set: the benchmark feeds
-  /// already-spliced [N x 40*21] windows.
+  /// skip_splice drops SpliceComponent lines (the caller then feeds already-spliced windows,
+  /// [N x 40*21] for nnet.config); by default the Splice front end is part of the network.
   void Init(std::istream &is, bool skip_splice = false);
   void Read(std::istream &is, bool binary);
   void Write(std::ostream &os, bool binary) const;
@@ -47,7 +47,16 @@ class NnetMinibatchUpdater {
   explicit NnetMinibatchUpdater(Nnet *nnet);
   ~NnetMinibatchUpdater();
   /// feats: device [num_rows x InputDim()].  Runs Propagate through all components.
+  /// With a SpliceComponent in front (nnet.config line 1) feats holds the FRAMES of the training
+  /// examples, FramesPerExample() consecutive rows per example (nnet2's NnetExample: left-context + 1 +
+  /// right-context input frames for one output frame), and the network has
+  /// feats.NumRows() / FramesPerExample() rows from the Splice output on.  When the context is a run of
+  /// consecutive offsets and the rows of feats are dense, that output is the SAME memory viewed as
+  /// [examples x frames * dim] -- the [C][W][H] window of the first convolution -- so the front end
+  /// costs no copy and no launch; otherwise SpliceComponent::Propagate gathers it.
   void Forward(const CuMatrixBase<BaseFloat> &feats);
+  /// Input rows per training example: the span of the SpliceComponent's context, 1 without one.
+  int32 FramesPerExample() const;
   /// Propagate through components [first, last] only.  first == 0 binds `feats` as the input;
   /// otherwise the activations below `first` must come from an earlier call on the same batch.
   /// (Lets the data-parallel step run the layers whose weights are up to date while the
@@ -126,6 +135,7 @@ class NnetMinibatchUpdater {
   bool FusedObjf(const int32 *labels_dev);
   void FusedBackward(int32 last, int32 first);
   const int32 *step_labels_;                    // TrainStep: labels known while the forward pass runs
+  int32 base_;                                  // 1 when component 0 is the Splice front end, else 0
 
   std::vector<CuMatrix<BaseFloat> > forward_;   // [0] = copy-free view of the input
   std::vector<ChunkInfo> info_;
@@ -133,6 +143,7 @@ class NnetMinibatchUpdater {
   // allocated or returned to the device cache while a step (or its recorded graph) runs
   std::vector<CuMatrix<BaseFloat> > derivs_;
   CuMatrix<BaseFloat> empty_;
+  CuMatrix<BaseFloat> splice_out_;              // Splice output when it cannot be a view of the input
   const int32 *labels_;
   double *objf_dev_;
   std::vector<size_t> bucket_off_, bucket_len_;

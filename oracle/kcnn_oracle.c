@@ -145,6 +145,93 @@ void oraF_softmax_backprop(const float *out_value, int rows, int cols, int ov_st
   }
 }
 
+/* DropoutComponent::Propagate.  nnet2/nnet-component.cc:3592-3620, pass for pass on a matrix of
+ * uniform [0, 1) draws (the reference fills `out` with CuRand::RandUniform first):
+ *   out = u ; out += -dp ; out = heaviside(out) ; out *= (high - low) [if != 1] ;
+ *   out += low [if != 0] ; out *= in.        high = (1 - dp*low) / (1 - dp). */
+void oraF_dropout_propagate(const float *in, int rows, int cols, int in_stride, const float *uniform,
+                            int u_stride, float dp, float low_scale, float *out, int out_stride) {
+  float high_scale = (1.0 - (dp * low_scale)) / (1.0 - dp);
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) {
+      float v = uniform[(size_t)i * u_stride + j];
+      v = v + (-dp);                                        /* Add(-dp) */
+      v = v > 0.0f ? 1.0f : 0.0f;                           /* ApplyHeaviside */
+      if ((high_scale - low_scale) != 1.0f) v = v * (high_scale - low_scale);
+      if (low_scale != 0.0f) v = v + low_scale;
+      out[(size_t)i * out_stride + j] = v * in[(size_t)i * in_stride + j];       /* MulElements(in) */
+    }
+}
+
+/* DropoutComponent::Backprop.  :3622-3637: in_deriv->AddMatMatDivMat(out_deriv, out_value, in_value),
+ * element-wise a * b / c, and a where c == 0 (Kaldi cu-kernels _add_mat_mat_div_mat). */
+void oraF_dropout_backprop(const float *in_value, int rows, int cols, int iv_stride,
+                           const float *out_value, int ov_stride, const float *out_deriv, int od_stride,
+                           float *in_deriv, int id_stride) {
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) {
+      float a = out_deriv[(size_t)i * od_stride + j], b = out_value[(size_t)i * ov_stride + j],
+            c = in_value[(size_t)i * iv_stride + j];
+      in_deriv[(size_t)i * id_stride + j] = c == 0.0f ? a : a * b / c;
+    }
+}
+
+/* NormalizeComponent::Propagate / Backprop.  nnet2/nnet-component.cc:576-639.
+ *   f = (max(2^-66, row . row / D))^-0.5 ; out = f * in
+ *   in_deriv = f * out_deriv - (f == 2^33 ? 0 : f^3) / D * (out_deriv . in) * in */
+void oraF_normalize_propagate(const float *in, int rows, int cols, int in_stride, float *out,
+                              int out_stride) {
+  const float kNormFloor = (float)pow(2.0, -66);
+  for (int i = 0; i < rows; i++) {
+    const float *x = in + (size_t)i * in_stride;
+    float p = 0.0f;
+    for (int j = 0; j < cols; j++) p += (1.0f / cols) * x[j] * x[j];    /* AddDiagMat2(1/D, in, kNoTrans, 0) */
+    if (p < kNormFloor) p = kNormFloor;                                  /* ApplyFloor */
+    float f = powf(p, -0.5f);                                            /* ApplyPow(-0.5) */
+    for (int j = 0; j < cols; j++) out[(size_t)i * out_stride + j] = x[j] * f;   /* MulRowsVec */
+  }
+}
+
+void oraF_normalize_backprop(const float *in_value, int rows, int cols, int iv_stride,
+                             const float *out_deriv, int od_stride, float *in_deriv, int id_stride) {
+  const float kNormFloor = (float)pow(2.0, -66);
+  for (int i = 0; i < rows; i++) {
+    const float *x = in_value + (size_t)i * iv_stride;
+    const float *d = out_deriv + (size_t)i * od_stride;
+    float *o = in_deriv + (size_t)i * id_stride;
+    float p = 0.0f;
+    for (int j = 0; j < cols; j++) p += (1.0f / cols) * x[j] * x[j];
+    if (p < kNormFloor) p = kNormFloor;
+    float f = powf(p, -0.5f);
+    for (int j = 0; j < cols; j++) o[j] = f * d[j];                      /* AddDiagVecMat(1, in_norm, out_deriv, 0) */
+    float g = f;
+    if (g == (float)(1.0 / sqrt((double)kNormFloor))) g = 0.0f;          /* ReplaceValue(1/sqrt(floor), 0) */
+    g = g * g * g;                                                       /* ApplyPow(3) */
+    float dot = 0.0f;
+    for (int j = 0; j < cols; j++) dot += d[j] * x[j];                   /* AddDiagMatMat */
+    dot *= g;                                                            /* MulElements */
+    for (int j = 0; j < cols; j++) o[j] += (-1.0f / cols) * dot * x[j];  /* AddDiagVecMat(-1/D, ., in_value, 1) */
+  }
+}
+
+/* NonlinearComponent::UpdateStats.  nnet2/nnet-component.cc:337-363: a FLOAT row-sum vector of
+ * out_value (and of the derivative matrix, when given) is added to the DOUBLE accumulators;
+ * count += rows.  deriv may be NULL (softmax). */
+void oraF_nonlin_update_stats(const float *out_value, int rows, int cols, int ov_stride, const float *deriv,
+                              int d_stride, double *value_sum, double *deriv_sum, double *count) {
+  *count += rows;
+  for (int j = 0; j < cols; j++) {
+    float t = 0.0f;                                                      /* temp.AddRowSumMat(1, out_value, 0) */
+    for (int i = 0; i < rows; i++) t += out_value[(size_t)i * ov_stride + j];
+    value_sum[j] += (double)t;
+    if (deriv) {
+      float u = 0.0f;
+      for (int i = 0; i < rows; i++) u += deriv[(size_t)i * d_stride + j];
+      deriv_sum[j] += (double)u;
+    }
+  }
+}
+
 /* Host threads the GEMMs may use (bench.py's CPU legs set it to the box's core count;
  * tests leave it alone).  Returns the number in effect; 1 when built without OpenMP. */
 int ora_set_num_threads(int n) {

@@ -75,6 +75,17 @@ double oraF_xent_objf_and_deriv(const float *post, int rows, int cols, int p_str
 void oraF_softmax_backprop(const float *out_value, int rows, int cols, int ov_stride,
                            const float *out_deriv, int od_stride, float *in_deriv,
                            int id_stride);
+void oraF_dropout_propagate(const float *in, int rows, int cols, int in_stride, const float *uniform,
+                            int u_stride, float dp, float low_scale, float *out, int out_stride);
+void oraF_dropout_backprop(const float *in_value, int rows, int cols, int iv_stride,
+                           const float *out_value, int ov_stride, const float *out_deriv, int od_stride,
+                           float *in_deriv, int id_stride);
+void oraF_normalize_propagate(const float *in, int rows, int cols, int in_stride, float *out,
+                              int out_stride);
+void oraF_normalize_backprop(const float *in_value, int rows, int cols, int iv_stride,
+                             const float *out_deriv, int od_stride, float *in_deriv, int id_stride);
+void oraF_nonlin_update_stats(const float *out_value, int rows, int cols, int ov_stride, const float *deriv,
+                              int d_stride, double *value_sum, double *deriv_sum, double *count);
 
 #ifdef __cplusplus
 }

@@ -286,3 +286,50 @@ def softmax_backprop(out_value, out_deriv):
     n = out_value.shape[1]
     lib().oraF_softmax_backprop(_p(out_value), out_value.shape[0], n, n, _p(out_deriv), n, _p(o), n)
     return o
+
+
+def dropout_propagate(x, uniform, dp, low_scale):
+    """DropoutComponent::Propagate on a given matrix of uniform draws."""
+    x, uniform = _c(x, np.float32), _c(uniform, np.float32)
+    out = np.zeros_like(x)
+    n = x.shape[1]
+    lib().oraF_dropout_propagate(_p(x), x.shape[0], n, n, _p(uniform), n, ctypes.c_float(dp),
+                                 ctypes.c_float(low_scale), _p(out), n)
+    return out
+
+
+def dropout_backprop(in_value, out_value, out_deriv):
+    in_value, out_value, out_deriv = (_c(a, np.float32) for a in (in_value, out_value, out_deriv))
+    o = np.zeros_like(in_value)
+    n = in_value.shape[1]
+    lib().oraF_dropout_backprop(_p(in_value), in_value.shape[0], n, n, _p(out_value), n, _p(out_deriv), n, _p(o), n)
+    return o
+
+
+def normalize_propagate(x):
+    x = _c(x, np.float32)
+    out = np.zeros_like(x)
+    n = x.shape[1]
+    lib().oraF_normalize_propagate(_p(x), x.shape[0], n, n, _p(out), n)
+    return out
+
+
+def normalize_backprop(in_value, out_deriv):
+    in_value, out_deriv = _c(in_value, np.float32), _c(out_deriv, np.float32)
+    o = np.zeros_like(in_value)
+    n = in_value.shape[1]
+    lib().oraF_normalize_backprop(_p(in_value), in_value.shape[0], n, n, _p(out_deriv), n, _p(o), n)
+    return o
+
+
+def nonlin_update_stats(out_value, deriv, value_sum, deriv_sum, count):
+    """NonlinearComponent::UpdateStats: returns (value_sum, deriv_sum, count) after one call."""
+    out_value = _c(out_value, np.float32)
+    n = out_value.shape[1]
+    vs = np.ascontiguousarray(value_sum, dtype=np.float64).copy()
+    ds = np.ascontiguousarray(deriv_sum, dtype=np.float64).copy()
+    cnt = ctypes.c_double(count)
+    d = None if deriv is None else _c(deriv, np.float32)
+    lib().oraF_nonlin_update_stats(_p(out_value), out_value.shape[0], n, n, _p(d) if d is not None else None, n,
+                                   _p(vs), _p(ds), ctypes.byref(cnt))
+    return vs, ds, cnt.value

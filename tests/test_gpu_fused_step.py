@@ -142,6 +142,7 @@ def step_vs_oracle(cfg, N, seed, steps=1, tol_out=1e-3, tol_step=2e-2):
         assert report["objf"] <= tol_out and report["posteriors"] <= tol_out, report
         after = params(net)
         k = 0
+        bad = []
         for i, L in enumerate(cpu.layers):
             if L["kind"] not in UPDATABLE:
                 continue
@@ -154,9 +155,10 @@ def step_vs_oracle(cfg, N, seed, steps=1, tol_out=1e-3, tol_step=2e-2):
                 e_step = float(np.linalg.norm(new.astype(np.float64) - ref) / max(np.linalg.norm(d_ref), 1e-30))
                 report["comp%d %s" % (i, name)] = (e_val, e_step)
                 # the momentum matrix IS a (smoothed) gradient: it carries the gradient's accumulated error
-                assert e_val <= (tol_step if name == "momentum" else tol_out), (s, i, name, e_val)
-                assert e_step <= tol_step, (s, i, name, e_step)
+                if e_val > (tol_step if name == "momentum" else tol_out) or e_step > tol_step:
+                    bad.append((s, i, name, e_val, e_step))
             k += 1
+        assert not bad, (bad, report)
     kc.set_math_mode(0)
     return report
 
@@ -283,3 +285,62 @@ def test_fused_graph_replay_equals_eager_and_is_deterministic():
             assert np.array_equal(u[which], v[which])
     kc.set_math_mode(0)
     kc.use_current_stream()
+
+
+SPLICE_LINE = "SpliceComponent input-dim=8 left-context=6 right-context=6 const-component-dim=0\n"
+
+
+@pytest.mark.parametrize("fuse", [True, False], ids=["plan", "components"])
+def test_splice_front_end_is_a_view_of_the_frames(fuse):
+    """with the SpliceComponent of nnet.config in front, the network takes the FRAMES of the
+    training examples ([N * 13 x 8] here, 13 = left + 1 + right) and conv1 reads its [C][W][H] window
+    straight from those rows.  Same numbers, bit for bit, as the spliced [N x 104] matrix fed to the model
+    without the Splice line; a gapped context (not a view: SpliceComponent::Propagate gathers) against the
+    explicitly gathered input."""
+    kc.set_math_mode(1)
+    N = 64
+    rng = np.random.default_rng(17)
+    frames = rng.standard_normal((N * 13, 8)).astype(np.float32)
+    lab = rng.integers(0, 40, N).astype(np.int32)
+    kc.use_current_stream()
+    nets = []
+    for cfg in (SPLICE_LINE + CFG.lstrip("\n"), CFG):
+        kc.set_rand_seed(31)
+        net = kc.Nnet.from_config(cfg, skip_splice=False)
+        net.set_fusion(fuse)
+        nets.append(net)
+    a, b = nets
+    assert a.frames_per_example == 13 and b.frames_per_example == 1 and a.input_dim == 8 and b.input_dim == 104
+    fd, ld = torch.from_numpy(frames).cuda(), torch.from_numpy(lab).cuda()
+    for step in range(2):
+        for net, x in ((a, fd), (b, fd.view(N, 104))):
+            if step == 0:
+                kc.set_rand_seed(5)
+            net.train_step(x, ld)
+        assert a.fused_active == fuse and b.fused_active == fuse
+        assert a.objf_and_reset() == b.objf_and_reset()
+    for pa, pb in zip(params(a), params(b)):
+        for which in range(3):
+            assert np.array_equal(pa[which], pb[which])
+    # host entry point: rows = examples, the matrix holds rows * frames_per_example frames
+    oa = a.train_minibatch_host(frames, lab)
+    ob = b.train_minibatch_host(frames.reshape(N, 104), lab)
+    assert oa == ob
+    # gapped context: every second frame
+    kc.set_rand_seed(31)
+    c = kc.Nnet.from_config("SpliceComponent input-dim=8 context=-12:-10:-8:-6:-4:-2:0:2:4:6:8:10:12\n" + CFG.lstrip("\n"),
+                            skip_splice=False)
+    c.set_fusion(fuse)
+    kc.set_rand_seed(31)
+    d = kc.Nnet.from_config(CFG)
+    d.set_fusion(fuse)
+    assert c.frames_per_example == 25
+    wide = rng.standard_normal((N * 25, 8)).astype(np.float32)
+    gathered = wide.reshape(N, 25, 8)[:, ::2, :].reshape(N, 104).copy()
+    for net, x in ((c, torch.from_numpy(wide).cuda()), (d, torch.from_numpy(gathered).cuda())):
+        kc.set_rand_seed(5)
+        net.train_step(x, ld)
+    assert c.objf_and_reset() == d.objf_and_reset()
+    for pa, pb in zip(params(c), params(d)):
+        assert np.array_equal(pa[0], pb[0])
+    kc.set_math_mode(0)
