@@ -48,6 +48,16 @@ cudaStream_t kcnn_get_stream(void);
  * reset (bench.py reports it as "gpu_launches"). */
 unsigned long long kcnn_launch_count(void);
 void kcnn_reset_launch_count(void);
+/* Per-launch timing for the benchmark's roofline table: between _start and _stop every kernel this
+ * library launches (outside stream capture) is bracketed by CUDA events on its stream and tagged with the
+ * label and algorithmic FLOPs / bytes announced last by kcnn_profile_label (the work is attributed to the
+ * first launch under a label).  _stop synchronises the device and returns the number of records; _get
+ * returns record i: demangled kernel name, label, duration in ms, work, grid. */
+void kcnn_profile_start(void);
+int kcnn_profile_stop(void);
+void kcnn_profile_label(const char *label, double flops, double bytes);
+int kcnn_profile_get(int i, char *kernel, int kernel_len, char *label, int label_len, float *ms,
+                     double *flops, double *bytes, unsigned int *grid3);
 /* "sm_100a" build tag and the ABI revision of this header. */
 const char *kcnn_build_info(void);
 int kcnn_abi_version(void);

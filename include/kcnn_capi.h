@@ -225,6 +225,9 @@ int kcnn_nnet_train_step(kcnn_nnet *n, const float *feats, int rows, int stride,
  * [Convolution | FullyConnected] + ReLU as one launch.  With fusion the pre-activation
  * kcnn_nnet_activation(c + 1) of a fused pair is not filled.  0 = component by component. */
 int kcnn_nnet_set_fusion(kcnn_nnet *n, int on);
+/* CUDA-graph recording of kcnn_nnet_train_step / _host / _host_async (default on); 0 runs every step's
+ * launches eagerly (profiling, debugging). */
+int kcnn_nnet_set_graphs(kcnn_nnet *n, int on);
 /* 1 when the most recent train step of this network was a graph replay, else 0. */
 int kcnn_nnet_last_step_replayed(const kcnn_nnet *n);
 /* 1 when the network's current configuration (model, rows, math mode) runs as the fused plan of
@@ -253,8 +256,63 @@ int kcnn_p2p_allreduce_f32(void *stream, const unsigned long long *peer_bases, i
 int kcnn_p2p_allreduce_multicast_f32(void *stream, const unsigned long long *peer_bases,
                                      unsigned long long multicast_base, int rank, int world, size_t offset_floats,
                                      size_t count_floats, size_t flag_offset_floats, int channel);
-/* 1 when a barrier of this rank gave up waiting for a peer (synchronises the device). */
+/* 1 when a barrier of this rank gave up waiting for a peer (synchronises the device).  The wait is
+ * bounded by wall-clock time (KCNN_P2P_TIMEOUT_MS, default 20000); a kernel whose barrier timed out
+ * skips its stores, so neither gradients nor weights are overwritten with a partial sum. */
 int kcnn_p2p_error(const float *local_base, size_t flag_offset_floats);
+const unsigned int *kcnn_p2p_error_word(const float *local_base, size_t flag_offset_floats, int channel);
+
+/* Reduce-scatter + momentum SGD + all-gather of one layer's bucket in ONE kernel (kernels_p2p.cu).
+ * The symmetric allocation holds the gradient arena and, param_delta_floats further on, a parameter
+ * arena with the same layout.  Rank r sums its slice of the bucket over all ranks (peer loads in rank
+ * order, or in the NVSwitch when multicast_base != 0), applies
+ *     prev = momentum*prev + decay_alpha*W + grad_alpha*g ; W += prev      (first weight_floats floats)
+ *     b += grad_alpha*g                                                       (the rest: the bias)
+ * -- nnet0/nnet-component-nnet0.cc:767-775, 1136-1142 -- with ITS momentum matrix prev_grad (local,
+ * indexed like the bucket) and stores the new values to every rank's parameter arena.  Same results as
+ * kcnn_p2p_allreduce_f32 followed by the per-rank update, without the second pass. */
+int kcnn_p2p_reduce_sgd_f32(void *stream, const unsigned long long *peer_bases, unsigned long long multicast_base,
+                            int rank, int world, size_t offset_floats, size_t count_floats, size_t weight_floats,
+                            size_t param_delta_floats, float *prev_grad, float momentum, float decay_alpha,
+                            float grad_alpha, size_t flag_offset_floats, int channel);
+
+/* Symmetric memory from CUDA IPC handles: kcnn_ipc_alloc returns zero-filled device memory and its
+ * 64-byte cudaIpcMemHandle_t; the host sends the handle to the other ranks (any transport) and each
+ * maps it with kcnn_ipc_open (peer access is enabled on first use). */
+int kcnn_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+int kcnn_ipc_open(const unsigned char *handle64, void **ptr);
+int kcnn_ipc_close(void *ptr);
+int kcnn_ipc_free(void *ptr);
+
+/* ---- the data-parallel trainer (csrc/nnet2/nnet-dp.h: NnetDataParallel) -------------------------------
+ * One process per GPU.  kcnn_nnet_dp_arena_floats() floats of symmetric memory per rank (zero-filled;
+ * kcnn_ipc_alloc, or any allocation every rank can map), peer_bases[p] = rank p's arena as mapped here.
+ * create moves the network's parameters into the arena and defers the updates; all ranks must start from
+ * identical parameters.  rotate = backward of the batch in the pipeline with one fused reduce + SGD +
+ * broadcast kernel per layer, forward of the next batch behind the updates, objective of the next batch;
+ * recorded into a CUDA graph on the second call with the same buffers.  feats: device [rows_local *
+ * kcnn_nnet_frames_per_example() x input_dim]; labels: device int32 [rows_local].
+ * The host-buffer form stages the caller's buffers through pinned memory and a copy stream, two device
+ * slots, like kcnn_nnet_train_minibatch_host_async: call it once per minibatch (the first call primes the
+ * pipeline), then kcnn_nnet_dp_finish.  The objective accumulates per rank (kcnn_nnet_objf_and_reset). */
+typedef struct kcnn_nnet_dp kcnn_nnet_dp;
+size_t kcnn_nnet_dp_arena_floats(kcnn_nnet *n);
+kcnn_nnet_dp *kcnn_nnet_dp_create(kcnn_nnet *n, int rank, int world, float *local_base,
+                                  const unsigned long long *peer_bases, unsigned long long multicast_base);
+void kcnn_nnet_dp_delete(kcnn_nnet_dp *dp);
+int kcnn_nnet_dp_prime(kcnn_nnet_dp *dp, const float *feats, int rows, int stride, const int *labels);
+int kcnn_nnet_dp_rotate(kcnn_nnet_dp *dp, const float *feats_next, int rows, int stride, const int *labels_next,
+                        int rows_global);
+int kcnn_nnet_dp_finish(kcnn_nnet_dp *dp, int rows_global);
+int kcnn_nnet_dp_train_minibatch_host_async(kcnn_nnet_dp *dp, const float *feats_host, const int *labels_host,
+                                            int rows_local, int rows_global);
+/* 1 when a barrier timed out on this rank (a peer is missing): the update of that step was skipped and the
+ * replicas may have diverged.  synchronise != 0 waits for the enqueued work first. */
+int kcnn_nnet_dp_failed(kcnn_nnet_dp *dp, int synchronise);
+/* Completes every rank's momentum matrices (they are updated by the owner of each slice only); call on
+ * all ranks before writing a checkpoint. */
+int kcnn_nnet_dp_gather_momentum(kcnn_nnet_dp *dp);
+int kcnn_nnet_dp_last_rotate_replayed(const kcnn_nnet_dp *dp);
 
 #ifdef __cplusplus
 }

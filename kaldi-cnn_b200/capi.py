@@ -40,6 +40,12 @@ _PROTOS = {
     "kcnn_reset_launch_count": [],
     "kcnn_build_info": [],
     "kcnn_abi_version": [],
+    "kcnn_profile_start": [],
+    "kcnn_profile_stop": [],
+    "kcnn_profile_label": [ctypes.c_char_p, ctypes.c_double, ctypes.c_double],
+    "kcnn_profile_get": [I, ctypes.c_char_p, I, ctypes.c_char_p, I, ctypes.POINTER(c_float),
+                         ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                         ctypes.POINTER(ctypes.c_uint)],
     # legacy launchers
     "cudaF_span_row_to_convmat": [Dim3, Dim3, P, M, P, M, I, I, I, I, I, I],
     "cudaF_convmat_to_out": [Dim3, Dim3, P, M, P, M, I, I, I],
@@ -123,6 +129,8 @@ _RESTYPES = {
     "kcnn_launch_count": ctypes.c_ulonglong,
     "kcnn_build_info": ctypes.c_char_p,
     "kcnn_abi_version": c_int,
+    "kcnn_profile_stop": c_int,
+    "kcnn_profile_get": c_int,
     "kcnn_conv2d_wgrad_workspace": c_size_t,
     "cudaF_conv2d_backward": c_int,
     "kcnn_conv2d_staging_floats": c_size_t,

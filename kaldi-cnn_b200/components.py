@@ -303,6 +303,10 @@ class Nnet:
         """[Convolution | FullyConnected] + ReLU as one launch in the forward pass (default on)."""
         _check(_lib().kcnn_nnet_set_fusion(self.h, int(bool(on))))
 
+    def set_graphs(self, on):
+        """CUDA-graph recording of train_step_graph / train_minibatch_host* (default on)."""
+        _check(_lib().kcnn_nnet_set_graphs(self.h, int(bool(on))))
+
     @property
     def last_step_replayed(self):
         return bool(_lib().kcnn_nnet_last_step_replayed(self.h))

@@ -13,6 +13,7 @@
 #include "cnsl-cu-kernels.h"
 #include "nnet0/nnet-component-nnet0.h"
 #include "nnet2/nnet-nnet.h"
+#include "nnet2/nnet-dp.h"
 
 using namespace kaldi;
 using namespace kaldi::nnet2;
@@ -679,9 +680,170 @@ int kcnn_nnet_last_step_replayed(const kcnn_nnet *n) {
   return (h->updater != NULL && h->updater->LastStepReplayed()) ? 1 : 0;
 }
 
+int kcnn_nnet_set_graphs(kcnn_nnet *n, int on) {
+  KCNN_TRY
+  N(n)->U().SetGraphs(on != 0);
+  return 0;
+  KCNN_CATCH(-1)
+}
+
 int kcnn_nnet_fused_active(const kcnn_nnet *n) {
   const NnetHandle *h = N(n);
   return (h->updater != NULL && h->updater->FusedActive()) ? 1 : 0;
+}
+
+}  // extern "C"
+
+// ---- data-parallel trainer -------------------------------------------------------------------
+
+namespace {
+// Host-buffer pipeline of the data-parallel step.  Three slots: while rotation j runs -- backward of
+// batch j-1 (which still reads that batch's input for the first layer's weight gradient) and forward
+// of batch j -- batch j+1 is being staged and copied.
+struct DpHandle {
+  NnetHandle *net;
+  NnetDataParallel *dp;
+  enum { kSlots = 3 };
+  float *pin_feats[kSlots]; int32 *pin_labels[kSlots]; double *pin_objf;
+  CuMatrix<BaseFloat> dev_feats[kSlots]; int32 *dev_labels[kSlots];
+  cudaStream_t copy_stream; cudaEvent_t copied[kSlots], done[kSlots];
+  int frames, dim, labels; unsigned long long call;
+  DpHandle() : net(NULL), dp(NULL), pin_objf(NULL), copy_stream(NULL), frames(0), dim(0), labels(0), call(0) {
+    for (int i = 0; i < kSlots; i++) { pin_feats[i] = NULL; pin_labels[i] = NULL; dev_labels[i] = NULL; copied[i] = NULL; done[i] = NULL; }
+  }
+  void Release() {
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    for (int i = 0; i < kSlots; i++) {
+      if (pin_feats[i]) cudaFreeHost(pin_feats[i]);
+      if (pin_labels[i]) cudaFreeHost(pin_labels[i]);
+      if (dev_labels[i]) CuDevice::Instantiate().Free(dev_labels[i]);
+      if (copied[i]) cudaEventDestroy(copied[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+      pin_feats[i] = NULL; pin_labels[i] = NULL; dev_labels[i] = NULL; copied[i] = NULL; done[i] = NULL;
+      dev_feats[i].Resize(0, 0);
+    }
+    if (pin_objf) cudaFreeHost(pin_objf);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    pin_objf = NULL; copy_stream = NULL; frames = 0; dim = 0; labels = 0;
+  }
+  void Ensure(int f, int d, int l) {
+    if (f == frames && d == dim && l == labels && copy_stream != NULL) return;
+    if (call != 0) KALDI_ERR << "the minibatch shape must not change while a batch is in the pipeline";
+    Release();
+    CU_SAFE_CALL(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_objf), sizeof(double)));
+    pin_objf[0] = 0.0;
+    for (int i = 0; i < kSlots; i++) {
+      CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_feats[i]), sizeof(float) * (size_t)f * d));
+      CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&pin_labels[i]), sizeof(int32) * (size_t)l));
+      dev_feats[i].Resize(f, d, kUndefined);
+      dev_labels[i] = static_cast<int32 *>(CuDevice::Instantiate().Malloc(sizeof(int32) * (size_t)l));
+      CU_SAFE_CALL(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+      CU_SAFE_CALL(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    frames = f; dim = d; labels = l;
+  }
+  ~DpHandle() {
+    if (CuDevice::Instantiate().Enabled()) cudaStreamSynchronize(CuDevice::Instantiate().Stream());
+    delete dp;
+    Release();
+  }
+};
+inline DpHandle *D(kcnn_nnet_dp *d) { return reinterpret_cast<DpHandle *>(d); }
+}  // namespace
+
+extern "C" {
+
+size_t kcnn_nnet_dp_arena_floats(kcnn_nnet *n) {
+  KCNN_TRY
+  return NnetDataParallel::ArenaFloats(&N(n)->U());
+  KCNN_CATCH(0)
+}
+
+kcnn_nnet_dp *kcnn_nnet_dp_create(kcnn_nnet *n, int rank, int world, float *local_base,
+                                  const unsigned long long *peer_bases, unsigned long long multicast_base) {
+  KCNN_TRY
+  DpHandle *h = new DpHandle();
+  try {
+    h->net = N(n);
+    h->dp = new NnetDataParallel(&h->net->nnet, &h->net->U(), rank, world, local_base, peer_bases, multicast_base);
+  } catch (...) { delete h; throw; }
+  return reinterpret_cast<kcnn_nnet_dp *>(h);
+  KCNN_CATCH(NULL)
+}
+
+void kcnn_nnet_dp_delete(kcnn_nnet_dp *dp) { delete D(dp); }
+
+int kcnn_nnet_dp_prime(kcnn_nnet_dp *dp, const float *feats, int rows, int stride, const int *labels) {
+  KCNN_TRY
+  View F(feats, rows, D(dp)->net->nnet.InputDim(), stride);
+  D(dp)->dp->Prime(F, labels);
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_dp_rotate(kcnn_nnet_dp *dp, const float *feats_next, int rows, int stride, const int *labels_next,
+                        int rows_global) {
+  KCNN_TRY
+  View F(feats_next, rows, D(dp)->net->nnet.InputDim(), stride);
+  D(dp)->dp->Rotate(F, labels_next, rows_global);
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_dp_finish(kcnn_nnet_dp *dp, int rows_global) {
+  KCNN_TRY
+  D(dp)->dp->Finish(rows_global);
+  D(dp)->call = 0;
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_dp_train_minibatch_host_async(kcnn_nnet_dp *dp, const float *feats_host, const int *labels_host,
+                                            int rows_local, int rows_global) {
+  KCNN_TRY
+  DpHandle *h = D(dp);
+  const int dim = h->net->nnet.InputDim();
+  const int frames = rows_local * h->net->U().FramesPerExample();
+  cudaStream_t st = CuDevice::Instantiate().Stream();
+  h->Ensure(frames, dim, rows_local);
+  const int s = (int)(h->call % DpHandle::kSlots);
+  CU_SAFE_CALL(cudaEventSynchronize(h->copied[s]));                 // the pinned slot's previous copy has run
+  memcpy(h->pin_feats[s], feats_host, sizeof(float) * (size_t)frames * dim);
+  memcpy(h->pin_labels[s], labels_host, sizeof(int32) * (size_t)rows_local);
+  // the device slot was last read by the backward pass of the rotation two calls ago
+  if (h->call >= 2) CU_SAFE_CALL(cudaStreamWaitEvent(h->copy_stream, h->done[(h->call - 2) % DpHandle::kSlots], 0));
+  CU_SAFE_CALL(cudaMemcpy2DAsync(h->dev_feats[s].Data(), sizeof(float) * h->dev_feats[s].Stride(), h->pin_feats[s],
+                                 sizeof(float) * dim, sizeof(float) * dim, frames, cudaMemcpyHostToDevice,
+                                 h->copy_stream));
+  CU_SAFE_CALL(cudaMemcpyAsync(h->dev_labels[s], h->pin_labels[s], sizeof(int32) * rows_local, cudaMemcpyHostToDevice,
+                               h->copy_stream));
+  CU_SAFE_CALL(cudaEventRecord(h->copied[s], h->copy_stream));
+  CU_SAFE_CALL(cudaStreamWaitEvent(st, h->copied[s], 0));
+  if (h->call == 0) h->dp->Prime(h->dev_feats[s], h->dev_labels[s]);
+  else h->dp->Rotate(h->dev_feats[s], h->dev_labels[s], rows_global);
+  CU_SAFE_CALL(cudaMemcpyAsync(h->pin_objf, h->net->U().ObjfDevice(), sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU_SAFE_CALL(cudaEventRecord(h->done[s], st));
+  h->call++;
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_dp_failed(kcnn_nnet_dp *dp, int synchronise) {
+  KCNN_TRY
+  return D(dp)->dp->Failed(synchronise != 0) ? 1 : 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_dp_gather_momentum(kcnn_nnet_dp *dp) {
+  KCNN_TRY
+  D(dp)->dp->GatherMomentum();
+  return 0;
+  KCNN_CATCH(-1)
+}
+
+int kcnn_nnet_dp_last_rotate_replayed(const kcnn_nnet_dp *dp) {
+  return reinterpret_cast<const DpHandle *>(dp)->dp->LastRotateReplayed() ? 1 : 0;
 }
 
 }  // extern "C"

@@ -21,6 +21,14 @@ extern cudaStream_t g_legacy_stream;
 
 inline void count_launch() { ++g_launch_count; }
 
+// Per-launch timing for bench.py's roofline table (kcnn_profile_start / _stop / _get in kcnn_lib.cu):
+// while recording, every launch of the library is bracketed by a pair of CUDA events on its own stream
+// and tagged with the label / algorithmic work the caller announced last (kcnn_profile_label).  Off the
+// hot path: one predictable branch per launch when not recording; never records inside a stream capture.
+extern bool g_profile_on;
+void profile_before(const void *kernel, dim3 grid, cudaStream_t st);
+void profile_after(cudaStream_t st);
+
 // Programmatic dependent launch (PDL): every kernel of the library starts with
 // pdl_prologue() -- "let the NEXT kernel of the stream be scheduled as soon as all my CTAs
 // have started; wait until the PREVIOUS kernel has completed and flushed" -- and is launched
@@ -94,7 +102,9 @@ inline void launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   }
   cfg.attrs = at;
   cfg.numAttrs = n;
+  if (g_profile_on) profile_before(reinterpret_cast<const void *>(kernel), grid, stream);
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (g_profile_on) profile_after(stream);
   count_launch();
 }
 

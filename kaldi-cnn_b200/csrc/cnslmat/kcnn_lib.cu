@@ -2,11 +2,51 @@
 
 #include "kcnn_common.cuh"
 
+#include <cxxabi.h>
+#include <dlfcn.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
 
 namespace kcnn {
 unsigned long long g_launch_count = 0;
 cudaStream_t g_legacy_stream = 0;
+bool g_profile_on = false;
+
+namespace {
+struct LaunchRec {
+  const void *kernel;
+  dim3 grid;
+  std::string label;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+  bool open;
+};
+std::vector<LaunchRec> g_recs;
+std::string g_label;
+double g_label_flops = 0.0, g_label_bytes = 0.0;
+}  // namespace
+
+void profile_before(const void *kernel, dim3 grid, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+  LaunchRec r;
+  r.kernel = kernel; r.grid = grid; r.label = g_label; r.flops = g_label_flops; r.bytes = g_label_bytes;
+  r.open = false;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaEventRecord(r.e0, st);
+  r.open = true;
+  g_recs.push_back(r);
+  g_label_flops = 0.0; g_label_bytes = 0.0;        // the work belongs to the FIRST launch under a label
+}
+
+void profile_after(cudaStream_t st) {
+  if (g_recs.empty() || !g_recs.back().open) return;
+  cudaEventRecord(g_recs.back().e1, st);
+  g_recs.back().open = false;
+}
 
 bool pdl_enabled() {
   static int v = -1;
@@ -77,6 +117,50 @@ void kcnn_set_stream(cudaStream_t stream) { kcnn::g_legacy_stream = stream; }
 cudaStream_t kcnn_get_stream(void) { return kcnn::g_legacy_stream; }
 unsigned long long kcnn_launch_count(void) { return kcnn::g_launch_count; }
 void kcnn_reset_launch_count(void) { kcnn::g_launch_count = 0; }
+/* ---- per-launch timing (bench.py) ---- */
+void kcnn_profile_start(void) {
+  for (size_t i = 0; i < kcnn::g_recs.size(); i++) { cudaEventDestroy(kcnn::g_recs[i].e0); cudaEventDestroy(kcnn::g_recs[i].e1); }
+  kcnn::g_recs.clear();
+  kcnn::g_label.clear();
+  kcnn::g_profile_on = true;
+}
+int kcnn_profile_stop(void) {
+  kcnn::g_profile_on = false;
+  cudaDeviceSynchronize();
+  return (int)kcnn::g_recs.size();
+}
+void kcnn_profile_label(const char *label, double flops, double bytes) {
+  if (!kcnn::g_profile_on) return;
+  kcnn::g_label = label ? label : "";
+  kcnn::g_label_flops = flops;
+  kcnn::g_label_bytes = bytes;
+}
+int kcnn_profile_get(int i, char *kernel, int kernel_len, char *label, int label_len, float *ms, double *flops,
+                     double *bytes, unsigned int *grid3) {
+  if (i < 0 || i >= (int)kcnn::g_recs.size()) return -1;
+  const kcnn::LaunchRec &r = kcnn::g_recs[i];
+  float t = 0.f;
+  if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
+  if (ms) *ms = t;
+  if (flops) *flops = r.flops;
+  if (bytes) *bytes = r.bytes;
+  if (grid3) { grid3[0] = r.grid.x; grid3[1] = r.grid.y; grid3[2] = r.grid.z; }
+  if (label && label_len > 0) { strncpy(label, r.label.c_str(), label_len - 1); label[label_len - 1] = 0; }
+  if (kernel && kernel_len > 0) {
+    std::string name = "?";
+    Dl_info info;
+    if (dladdr(r.kernel, &info) && info.dli_sname) {
+      int status = 0;
+      char *dem = abi::__cxa_demangle(info.dli_sname, NULL, NULL, &status);
+      name = (status == 0 && dem) ? dem : info.dli_sname;
+      free(dem);
+    }
+    strncpy(kernel, name.c_str(), kernel_len - 1);
+    kernel[kernel_len - 1] = 0;
+  }
+  return 0;
+}
+
 const char *kcnn_build_info(void) {
   return "kaldi-cnn_b200 sm_100a (compute_100a) nvcc " __DATE__;
 }

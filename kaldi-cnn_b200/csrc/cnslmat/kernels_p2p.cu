@@ -28,6 +28,7 @@
 #include "kcnn_common.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace kcnn {
 namespace p2p {
@@ -61,25 +62,40 @@ struct Peers {
   float *buf[kMaxRanks];          // base of each rank's symmetric allocation (this process's mapping)
 };
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // One lane per peer: publish `epoch` in the peer's flag word for (slot, me), then wait until the
-// peer has published it in mine.  A bounded spin: a rank that never arrives leaves an error
-// mark instead of a hung GPU.
-__device__ __forceinline__ void cross_barrier(const Peers &pr, size_t flag_off, int which, int slot, int rank,
-                                              int world, uint32_t epoch) {
+// peer has published it in mine.  The wait is bounded by WALL-CLOCK time (timeout_ns, default 20 s:
+// a first-step cudaMalloc, a graph capture or a checkpoint write on a peer must not trip it): a rank
+// that never arrives leaves an error mark instead of a hung GPU, and the barrier then returns false
+// in every thread of the CTA -- the caller skips its stores, so that neither gradients nor weights are
+// overwritten with a partial sum.  kcnn_p2p_error() / NnetDataParallel report the mark to the host.
+__device__ __forceinline__ bool cross_barrier(const Peers &pr, size_t flag_off, int which, int slot, int rank,
+                                              int world, uint32_t epoch, unsigned long long timeout_ns) {
+  __shared__ int s_failed;
   const int t = threadIdx.x;
+  if (t == 0) s_failed = 0;
+  __syncthreads();
   if (t < world && t != rank) {
     uint32_t *theirs = reinterpret_cast<uint32_t *>(pr.buf[t] + flag_off) + which + slot * kMaxRanks + rank;
     const uint32_t *mine = reinterpret_cast<const uint32_t *>(pr.buf[rank] + flag_off) + which + slot * kMaxRanks + t;
     st_release_sys(theirs, epoch);
-    unsigned long long spins = 0;
+    const unsigned long long t0 = global_ns();
+    unsigned int spins = 0;
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (++spins > (1ull << 25)) {          // seconds, not forever
+      if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) {
         reinterpret_cast<uint32_t *>(pr.buf[rank] + flag_off)[kError] = 1u;
+        s_failed = 1;
         break;
       }
     }
   }
   __syncthreads();
+  return s_failed == 0;
 }
 
 // In-switch reduction (NVLS): one 128-bit multimem.ld_reduce on the MULTICAST address of an
@@ -99,7 +115,8 @@ __device__ __forceinline__ void multimem_st_f4(float *mc, const float4 &v) {
 
 // mc: multicast mapping of the same symmetric allocation (nullptr: two-shot over unicast peers)
 __global__ void __launch_bounds__(kThreads)
-p2p_allreduce_kernel(Peers pr, float *mc, int rank, int world, size_t off, size_t n4, size_t flag_off) {
+p2p_allreduce_kernel(Peers pr, float *mc, int rank, int world, size_t off, size_t n4, size_t flag_off,
+                     unsigned long long timeout_ns) {
   const int b = blockIdx.x, G = gridDim.x, t = threadIdx.x;
   __shared__ uint32_t s_epoch;
   uint32_t *my_flags = reinterpret_cast<uint32_t *>(pr.buf[rank] + flag_off);
@@ -107,7 +124,10 @@ p2p_allreduce_kernel(Peers pr, float *mc, int rank, int world, size_t off, size_
   __syncthreads();
   const uint32_t epoch = s_epoch;
 
-  cross_barrier(pr, flag_off, kReady, b, rank, world, epoch);
+  if (!cross_barrier(pr, flag_off, kReady, b, rank, world, epoch, timeout_ns)) {
+    if (t == 0) my_flags[kEpoch + b] = epoch;
+    return;                                              // a peer is missing: leave the arena as it is
+  }
 
   const size_t per = (n4 + world - 1) / world;
   const size_t lo = (size_t)rank * per;
@@ -159,7 +179,113 @@ p2p_allreduce_kernel(Peers pr, float *mc, int rank, int world, size_t off, size_
   }
   __threadfence_system();                                // my stores, before anyone is told
   __syncthreads();
-  cross_barrier(pr, flag_off, kDone, b, rank, world, epoch);
+  cross_barrier(pr, flag_off, kDone, b, rank, world, epoch, timeout_ns);
+  if (t == 0) my_flags[kEpoch + b] = epoch;
+}
+
+// ---- reduce-scatter + momentum SGD + all-gather in ONE kernel -------------------------------------
+//
+// The data-parallel step of round 1 all-reduced every gradient bucket and then ran the SGD pass on
+// every rank: each rank read 147 MB of reduced gradients back and re-did the same 733 MB
+// read-modify-write of (W, prev_grad) that all other ranks did too.  Here the OWNER of a slice does
+// the update once:
+//   the symmetric allocation holds [gradient arena | parameter arena | flags]; the parameter arena
+//   is laid out exactly like the gradient arena (per layer: W rows x pitch, then the bias), so element
+//   i of a bucket has its gradient at G[i] and its weight at G[i + param_delta];
+//   barrier A   every rank has finished this layer's backward (its gradients are written AND its
+//               input-gradient GEMM no longer reads the weights)
+//   rank r, for its slice of the bucket:  g = sum over ranks of G_p[i]   (peer loads in rank order, or
+//               one multimem.ld_reduce inside the NVSwitch)
+//               weights:  prev = m prev + a_decay W + a_grad g ; W += prev     (reference
+//               nnet0/nnet-component-nnet0.cc:767-773, 1138-1142 -- the same sgd_apply as everywhere;
+//               prev_grad is touched by the owner only, so momentum is SHARDED over the ranks)
+//               bias:     b += a_grad g                                          (:775, :1137)
+//               the NEW weights are stored to every rank's parameter arena (peer stores / multimem.st)
+//   barrier B   all replicas hold the new weights.
+// NVLink traffic is that of the all-reduce; HBM traffic per rank drops from ~1.0 GB to ~0.37 GB per
+// step and the separate apply pass (0.12 ms) disappears.  Bit-identical to all-reduce + apply (same
+// summation order, same sgd_apply, one owner per element).
+struct SgdBucket {
+  size_t off;              // floats: start of the bucket in the gradient arena
+  size_t n4;               // float4 units in the bucket
+  size_t w4;               // float4 units of the weight matrix (the rest is the bias)
+  size_t param_delta;      // floats from a gradient element to its parameter
+  float *prev;             // LOCAL momentum matrix, indexed like the weight part of the bucket
+  float momentum, a_decay, a_grad;
+};
+
+__device__ __forceinline__ void sgd4(float4 &w, float4 &p, const float4 &g, const SgdBucket &k) {
+  float *wv = &w.x, *pv = &p.x;
+  const float *gv = &g.x;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    pv[j] = pv[j] * k.momentum;
+    pv[j] = fmaf(k.a_decay, wv[j], pv[j]);
+    pv[j] = fmaf(k.a_grad, gv[j], pv[j]);
+    wv[j] = wv[j] + pv[j];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+p2p_reduce_sgd_kernel(Peers pr, float *mc, int rank, int world, SgdBucket k, size_t flag_off,
+                      unsigned long long timeout_ns) {
+  const int b = blockIdx.x, G = gridDim.x, t = threadIdx.x;
+  __shared__ uint32_t s_epoch;
+  uint32_t *my_flags = reinterpret_cast<uint32_t *>(pr.buf[rank] + flag_off);
+  if (t == 0) s_epoch = my_flags[kEpoch + b] + 1u;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  if (!cross_barrier(pr, flag_off, kReady, b, rank, world, epoch, timeout_ns)) {
+    if (t == 0) my_flags[kEpoch + b] = epoch;
+    return;                                              // no partial update: weights stay as they are
+  }
+  const size_t per = (k.n4 + world - 1) / world;
+  const size_t lo = (size_t)rank * per;
+  const size_t hi = lo + per < k.n4 ? lo + per : k.n4;
+  const size_t step = (size_t)G * kThreads;
+  constexpr int U = 2;
+  float *wmine = pr.buf[rank] + k.off + k.param_delta;
+  for (size_t i0 = lo + (size_t)b * kThreads + t; i0 < hi; i0 += U * step) {
+    float4 g[U], w[U], p[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + u * step;
+      if (i >= hi) continue;
+      w[u] = *reinterpret_cast<const float4 *>(wmine + 4 * i);
+      if (i < k.w4) p[u] = *reinterpret_cast<const float4 *>(k.prev + 4 * i);
+      if (mc != nullptr) {
+        g[u] = multimem_ld_reduce_f4(mc + k.off + 4 * i);
+      } else {
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < world; q++) {                // rank order: the summation order of the all-reduce
+          const float *src = pr.buf[q] + k.off + 4 * i;
+          const float4 v = q == rank ? *reinterpret_cast<const float4 *>(src) : ld_volatile_f4(src);
+          g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + u * step;
+      if (i >= hi) continue;
+      if (i < k.w4) {
+        sgd4(w[u], p[u], g[u], k);
+        *reinterpret_cast<float4 *>(k.prev + 4 * i) = p[u];
+      } else {
+        w[u].x = fmaf(k.a_grad, g[u].x, w[u].x); w[u].y = fmaf(k.a_grad, g[u].y, w[u].y);
+        w[u].z = fmaf(k.a_grad, g[u].z, w[u].z); w[u].w = fmaf(k.a_grad, g[u].w, w[u].w);
+      }
+      if (mc != nullptr) {
+        multimem_st_f4(mc + k.off + k.param_delta + 4 * i, w[u]);
+      } else {
+        for (int q = 0; q < world; q++)
+          *reinterpret_cast<float4 *>(pr.buf[q] + k.off + k.param_delta + 4 * i) = w[u];
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  cross_barrier(pr, flag_off, kDone, b, rank, world, epoch, timeout_ns);
   if (t == 0) my_flags[kEpoch + b] = epoch;
 }
 
@@ -172,6 +298,27 @@ extern "C" {
 
 size_t kcnn_p2p_flag_floats(void) { return (size_t)p2p::kChannelWords * 2; }   // two channels
 
+static unsigned long long p2p_timeout_ns() {
+  static long long v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_P2P_TIMEOUT_MS");
+    v = e ? atoll(e) : 20000;
+    if (v < 1) v = 1;
+  }
+  return (unsigned long long)v * 1000000ull;
+}
+
+static int p2p_max_ctas() {
+  static int max_ctas = -1;
+  if (max_ctas < 0) {
+    const char *e = getenv("KCNN_P2P_CTAS");
+    max_ctas = e ? atoi(e) : 32;
+    if (max_ctas < 1) max_ctas = 1;
+    if (max_ctas > p2p::kMaxCtas) max_ctas = p2p::kMaxCtas;
+  }
+  return max_ctas;
+}
+
 static int p2p_launch(void *stream, const unsigned long long *peer_bases, unsigned long long mc_base, int rank,
                       int world, size_t offset_floats, size_t count_floats, size_t flag_offset_floats, int channel) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -182,13 +329,7 @@ static int p2p_launch(void *stream, const unsigned long long *peer_bases, unsign
   p2p::Peers pr;
   for (int p = 0; p < p2p::kMaxRanks; p++)
     pr.buf[p] = p < world ? reinterpret_cast<float *>(static_cast<uintptr_t>(peer_bases[p])) : nullptr;
-  static int max_ctas = -1;
-  if (max_ctas < 0) {
-    const char *e = getenv("KCNN_P2P_CTAS");
-    max_ctas = e ? atoi(e) : 32;
-    if (max_ctas < 1) max_ctas = 1;
-    if (max_ctas > p2p::kMaxCtas) max_ctas = p2p::kMaxCtas;
-  }
+  const int max_ctas = p2p_max_ctas();
   const size_t n4 = count_floats >> 2;
   const size_t per = (n4 + world - 1) / world;
   size_t want = (per + p2p::kThreads * 4 - 1) / (p2p::kThreads * 4);       // one pass of 4 units per thread
@@ -196,9 +337,61 @@ static int p2p_launch(void *stream, const unsigned long long *peer_bases, unsign
   const unsigned grid = (unsigned)(want < (size_t)max_ctas ? want : (size_t)max_ctas);
   KCNN_LAUNCH(p2p::p2p_allreduce_kernel, grid, p2p::kThreads, 0, st, pr,
               reinterpret_cast<float *>(static_cast<uintptr_t>(mc_base)), rank, world, offset_floats, n4,
-              flag_offset_floats + (size_t)channel * p2p::kChannelWords);
+              flag_offset_floats + (size_t)channel * p2p::kChannelWords, p2p_timeout_ns());
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+
+int kcnn_p2p_reduce_sgd_f32(void *stream, const unsigned long long *peer_bases, unsigned long long multicast_base,
+                            int rank, int world, size_t offset_floats, size_t count_floats, size_t weight_floats,
+                            size_t param_delta_floats, float *prev_grad, float momentum, float decay_alpha,
+                            float grad_alpha, size_t flag_offset_floats, int channel) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (world < 1 || world > p2p::kMaxRanks || rank < 0 || rank >= world) return -1;
+  if (channel < 0 || channel > 1) return -1;
+  if ((count_floats & 3) || (offset_floats & 3) || (flag_offset_floats & 3) || (weight_floats & 3) ||
+      (param_delta_floats & 3) || weight_floats > count_floats)
+    return -1;
+  if (count_floats == 0) return 0;
+  p2p::Peers pr;
+  for (int p = 0; p < p2p::kMaxRanks; p++)
+    pr.buf[p] = p < world ? reinterpret_cast<float *>(static_cast<uintptr_t>(peer_bases[p])) : nullptr;
+  p2p::SgdBucket k;
+  k.off = offset_floats; k.n4 = count_floats >> 2; k.w4 = weight_floats >> 2; k.param_delta = param_delta_floats;
+  k.prev = prev_grad; k.momentum = momentum; k.a_decay = decay_alpha; k.a_grad = grad_alpha;
+  const size_t per = (k.n4 + world - 1) / world;
+  size_t want = (per + p2p::kThreads * 2 - 1) / (p2p::kThreads * 2);
+  if (want < 1) want = 1;
+  const int max_ctas = p2p_max_ctas();
+  const unsigned grid = (unsigned)(want < (size_t)max_ctas ? want : (size_t)max_ctas);
+  KCNN_LAUNCH(p2p::p2p_reduce_sgd_kernel, grid, p2p::kThreads, 0, st, pr,
+              reinterpret_cast<float *>(static_cast<uintptr_t>(multicast_base)), rank, world, k,
+              flag_offset_floats + (size_t)channel * p2p::kChannelWords, p2p_timeout_ns());
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+/* ---- symmetric memory from CUDA IPC handles (no framework involved) -------------------------------
+ * Each rank allocates its arena with kcnn_ipc_alloc, sends the 64-byte handle to its peers by whatever
+ * means the host has (MPI, a socket, torch.distributed.all_gather_object ...), and maps the peers'
+ * arenas with kcnn_ipc_open (peer access is enabled on first use). */
+int kcnn_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64) {
+  if (!ptr || !handle64 || bytes == 0) return -1;
+  if (cudaMalloc(ptr, bytes) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cudaMemset(*ptr, 0, bytes) != cudaSuccess) { cudaGetLastError(); return -1; }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, *ptr) != cudaSuccess) { cudaGetLastError(); cudaFree(*ptr); *ptr = nullptr; return -1; }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int kcnn_ipc_open(const unsigned char *handle64, void **ptr) {
+  if (!ptr || !handle64) return -1;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  if (cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return 0;
+}
+int kcnn_ipc_close(void *ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? 0 : (cudaGetLastError(), -1); }
+int kcnn_ipc_free(void *ptr) { return cudaFree(ptr) == cudaSuccess ? 0 : (cudaGetLastError(), -1); }
 
 int kcnn_p2p_allreduce_f32(void *stream, const unsigned long long *peer_bases, int rank, int world,
                            size_t offset_floats, size_t count_floats, size_t flag_offset_floats, int channel) {
@@ -211,6 +404,12 @@ int kcnn_p2p_allreduce_multicast_f32(void *stream, const unsigned long long *pee
   if (multicast_base == 0ull) return -1;
   return p2p_launch(stream, peer_bases, multicast_base, rank, world, offset_floats, count_floats,
                     flag_offset_floats, channel);
+}
+
+/* Device address of the error word of one flag channel (for an asynchronous copy to pinned memory). */
+const unsigned int *kcnn_p2p_error_word(const float *local_base, size_t flag_offset_floats, int channel) {
+  return reinterpret_cast<const unsigned int *>(local_base + flag_offset_floats) + channel * p2p::kChannelWords +
+         p2p::kError;
 }
 
 /* 1 when a barrier of this rank gave up waiting for a peer (the arena contents are then undefined). */

@@ -14,9 +14,10 @@ static inline void Need(const char *what) { CuDevice::Instantiate().RequireEnabl
 // ------------------------------------------------------------------ CuVector --
 
 template <typename Real> void CuVector<Real>::Destroy() {
-  if (this->data_) CuDevice::Instantiate().Free(this->data_);
+  if (this->data_ && owns_) CuDevice::Instantiate().Free(this->data_);
   this->data_ = NULL;
   this->dim_ = 0;
+  owns_ = true;
 }
 
 template <typename Real> void CuVector<Real>::Resize(MatrixIndexT dim, MatrixResizeType t) {

@@ -49,20 +49,25 @@ class CuVectorBase {
 template <typename Real>
 class CuVector : public CuVectorBase<Real> {
  public:
-  CuVector() {}
-  CuVector(MatrixIndexT dim, MatrixResizeType t = kSetZero) { Resize(dim, t); }
-  CuVector(const CuVectorBase<Real> &v) { Resize(v.Dim(), kUndefined); this->CopyFromVec(v); }
-  CuVector(const CuVector<Real> &v) : CuVectorBase<Real>() { Resize(v.Dim(), kUndefined); this->CopyFromVec(v); }
-  CuVector(const VectorBase<Real> &v) { Resize(v.Dim(), kUndefined); this->CopyFromVec(v); }
+  CuVector() : owns_(true) {}
+  CuVector(MatrixIndexT dim, MatrixResizeType t = kSetZero) : owns_(true) { Resize(dim, t); }
+  CuVector(const CuVectorBase<Real> &v) : owns_(true) { Resize(v.Dim(), kUndefined); this->CopyFromVec(v); }
+  CuVector(const CuVector<Real> &v) : CuVectorBase<Real>(), owns_(true) { Resize(v.Dim(), kUndefined); this->CopyFromVec(v); }
+  CuVector(const VectorBase<Real> &v) : owns_(true) { Resize(v.Dim(), kUndefined); this->CopyFromVec(v); }
   ~CuVector() { Destroy(); }
   CuVector<Real> &operator=(const CuVectorBase<Real> &o) { Resize(o.Dim(), kUndefined); this->CopyFromVec(o); return *this; }
   CuVector<Real> &operator=(const CuVector<Real> &o) { Resize(o.Dim(), kUndefined); this->CopyFromVec(o); return *this; }
   CuVector<Real> &operator=(const VectorBase<Real> &o) { Resize(o.Dim(), kUndefined); this->CopyFromVec(o); return *this; }
   void Resize(MatrixIndexT dim, MatrixResizeType t = kSetZero);
+  /// B200 extension (as CuMatrix::Borrow): become a non-owning view of caller-provided device memory --
+  /// the data-parallel trainer keeps every parameter in one NVLink-visible arena.  A Resize to the same
+  /// dimension keeps the view.
+  void Borrow(Real *data, MatrixIndexT dim) { Destroy(); this->data_ = data; this->dim_ = dim; owns_ = false; }
   void Read(std::istream &is, bool binary);
   void Write(std::ostream &os, bool binary) const;
  private:
   void Destroy();
+  bool owns_;
 };
 
 template <typename Real>

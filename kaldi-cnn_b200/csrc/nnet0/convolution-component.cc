@@ -4,6 +4,7 @@
 #include <sstream>
 
 #include "nnet0/nnet-component-nnet0.h"
+#include "nnet0/component-fields.h"
 #include "util/common-utils.h"
 #include "cnsl-cu-kernels.h"
 
@@ -54,142 +55,158 @@ ConvolutionComponent::ConvolutionComponent(const CuMatrix<BaseFloat> &linear_par
   prev_grad_.Resize(linear_params_.NumRows(), linear_params_.NumCols(), kSetZero);
 }
 
-// reference :232-275
+// ---- geometry, configuration ---------------------------------------------------------------------
+// One table for the scalar members: config key (nnet.config line, reference :323-385), model-file token
+// (reference :556-666) and the member.  The ORDER is the model stream's.  "in-pad-*" are the only optional
+// geometry keys.  Weight decay and momentum are in the stream but -- see InitFromString -- not settable
+// from a config line.
+FieldList ConvolutionComponent::StreamFields() {
+  const FieldList::Need opt = FieldList::kOptional;
+  FieldList f;
+  f.Int("in-height", "<in_height>", &in_height_)
+      .Int("in-width", "<in_width>", &in_width_)
+      .Int("in-channel", "<in_channel>", &in_channel_)
+      .Int("kernel-height", "<kernel_height>", &kernel_height_)
+      .Int("kernel-width", "<kernel_width>", &kernel_width_)
+      .Int("stride", "<stride>", &stride_)
+      .Int("in-pad-height", "<padding_height>", &in_pad_height_, opt)
+      .Int("in-pad-width", "<padding_width>", &in_pad_width_, opt)
+      .Int("group", "<group>", &group_)
+      .Int("out-height", "<out_height>", &out_height_)
+      .Int("out-width", "<out_width>", &out_width_)
+      .Float("learning-rate", "<LearningRate>", &learning_rate_)
+      .Float(NULL, "<WeightDecay>", &weight_decay_)
+      .Float(NULL, "<Momentum>", &momentum_)
+      .Matrix("<LinearParams>", &linear_params_)
+      .Vector("<BiasParams>", &bias_params_)
+      .Matrix("<PrevGrad>", &prev_grad_)
+      .Bool(NULL, "<IsGradient>", &is_gradient_, opt);       // [17]: optional on input
+  return f;
+}
+static const size_t kConvOptionalFrom = 17;
+
+// The checks of reference :232-275 / :349-360 on the shape members.  The reference parses "stride" but
+// its Conv2D only implements stride 1 (cnslmat/conv2D.cc:59-60) and silently mis-sizes the output for
+// anything else; that is an error here.
+void ConvolutionComponent::CheckGeometry() const {
+  KALDI_ASSERT(in_pad_height_ >= 0 && "in-pad-height should be positive");
+  KALDI_ASSERT(in_pad_width_ >= 0 && "in-pad-width should be positive");
+  KALDI_ASSERT(stride_ != 0);
+  KALDI_ASSERT(out_height_ == 1 + (in_height_ + 2 * in_pad_height_ - kernel_height_) / stride_ &&
+               "out-height == 1 + (in-height + 2*in-pad-height - kernel-height) / stride");
+  KALDI_ASSERT(out_width_ == 1 + (in_width_ + 2 * in_pad_width_ - kernel_width_) / stride_ &&
+               "out-width == 1 + (in-width + 2*in-pad-width - kernel-width) / stride");
+  if (stride_ != 1)
+    KALDI_ERR << "ConvolutionComponent: stride=" << stride_ << " is not implemented (only stride 1)";
+}
+
+void ConvolutionComponent::SetShape(BaseFloat learning_rate, int32 in_height, int32 in_width,
+                                    int32 in_channels, int32 in_pad_height, int32 in_pad_width,
+                                    int32 kernel_height, int32 kernel_width, int32 stride, int32 group,
+                                    int32 out_height, int32 out_width, BaseFloat weight_decay,
+                                    BaseFloat momentum) {
+  in_height_ = in_height; in_width_ = in_width; in_channel_ = in_channels;
+  in_pad_height_ = in_pad_height; in_pad_width_ = in_pad_width;
+  kernel_height_ = kernel_height; kernel_width_ = kernel_width;
+  stride_ = stride; group_ = group;
+  out_height_ = out_height; out_width_ = out_width;
+  weight_decay_ = weight_decay; momentum_ = momentum;
+  CheckGeometry();
+  UpdatableComponent::Init(learning_rate);
+}
+
+// Random start (reference :232-275): W ~ N(0, param_stddev^2), bias ~ N(0, bias_stddev^2) (random, unlike
+// the fully connected layer), momentum matrix zero.  Weights are drawn before the bias.
 void ConvolutionComponent::Init(BaseFloat learning_rate, int32 in_height, int32 in_width,
                                 int32 in_channels, int32 in_pad_height, int32 in_pad_width,
                                 int32 kernel_height, int32 kernel_width, int32 stride, int32 group,
                                 int32 out_height, int32 out_width, BaseFloat param_stddev,
                                 BaseFloat bias_stddev, BaseFloat weight_decay, BaseFloat momentum) {
-  in_height_ = in_height; in_width_ = in_width; in_channel_ = in_channels;
-  in_pad_height_ = in_pad_height; in_pad_width_ = in_pad_width;
-  kernel_height_ = kernel_height; kernel_width_ = kernel_width;
-  stride_ = stride; group_ = group;
-  out_height_ = out_height; out_width_ = out_width;
-  weight_decay_ = weight_decay; momentum_ = momentum;
-
-  KALDI_ASSERT(in_pad_height_ >= 0);
-  KALDI_ASSERT(in_pad_width_ >= 0);
-  KALDI_ASSERT(stride != 0);
-  KALDI_ASSERT(out_height_ == 1 + (in_height + (2 * in_pad_height) - kernel_height) / stride);
-  KALDI_ASSERT(out_width_ == 1 + (in_width + (2 * in_pad_width) - kernel_width) / stride);
-  // The reference parses "stride" but its Conv2D only implements stride 1
-  // (cnslmat/conv2D.cc:59-60); anything else silently mis-sizes the output there.
-  if (stride != 1)
-    KALDI_ERR << "ConvolutionComponent: stride=" << stride << " is not implemented (only stride 1)";
-
-  UpdatableComponent::Init(learning_rate);
-  linear_params_.Resize(KernelDim(), group);
-  bias_params_.Resize(group);
-  prev_grad_.Resize(KernelDim(), group);
+  SetShape(learning_rate, in_height, in_width, in_channels, in_pad_height, in_pad_width, kernel_height,
+           kernel_width, stride, group, out_height, out_width, weight_decay, momentum);
   KALDI_ASSERT(param_stddev >= 0.0);
+  linear_params_.Resize(KernelDim(), group, kUndefined);
   linear_params_.SetRandn();
   linear_params_.Scale(param_stddev);
-  prev_grad_.SetZero();
+  bias_params_.Resize(group, kUndefined);
   bias_params_.SetRandn();
   bias_params_.Scale(bias_stddev);
+  prev_grad_.Resize(KernelDim(), group, kSetZero);
 }
 
-// reference :277-321.  The matrix file holds [KernelDim()+1 x group]: weights, then bias.
-// (The reference sizes the bias as kernel_dim and reads a column, App. C.3 -- a defect
-// of an unused path; the bias here is the last ROW, one value per output map.)
+// Start from a matrix file (reference :277-321) holding [KernelDim()+1 x group]: the weights, then one
+// row of biases.  (The reference sizes the bias as kernel_dim and reads a column, App. C.3 -- a defect of
+// a path nothing uses; here the bias is the last ROW, one value per output map.)
 void ConvolutionComponent::Init(BaseFloat learning_rate, int32 in_height, int32 in_width,
                                 int32 in_channels, int32 in_pad_height, int32 in_pad_width,
                                 int32 kernel_height, int32 kernel_width, int32 stride, int32 group,
                                 int32 out_height, int32 out_width, BaseFloat weight_decay,
                                 BaseFloat momentum, std::string matrix_filename) {
-  in_height_ = in_height; in_width_ = in_width; in_channel_ = in_channels;
-  in_pad_height_ = in_pad_height; in_pad_width_ = in_pad_width;
-  kernel_height_ = kernel_height; kernel_width_ = kernel_width;
-  stride_ = stride; group_ = group;
-  out_height_ = out_height; out_width_ = out_width;
-  weight_decay_ = weight_decay; momentum_ = momentum;
-  if (stride != 1)
-    KALDI_ERR << "ConvolutionComponent: stride=" << stride << " is not implemented (only stride 1)";
-  UpdatableComponent::Init(learning_rate);
-  Matrix<BaseFloat> mat;
-  ReadKaldiObject(matrix_filename, &mat);
-  KALDI_ASSERT(mat.NumCols() >= 1);
-  int32 num_group = mat.NumCols(), kernel_dim = mat.NumRows() - 1;
-  KALDI_ASSERT(num_group == Group());
-  KALDI_ASSERT(kernel_dim == KernelDim());
-  Matrix<BaseFloat> w(kernel_dim, num_group);
-  Vector<BaseFloat> b(num_group);
-  for (int32 r = 0; r < kernel_dim; r++)
-    for (int32 c = 0; c < num_group; c++) w(r, c) = mat(r, c);
-  for (int32 c = 0; c < num_group; c++) b(c) = mat(kernel_dim, c);
+  SetShape(learning_rate, in_height, in_width, in_channels, in_pad_height, in_pad_width, kernel_height,
+           kernel_width, stride, group, out_height, out_width, weight_decay, momentum);
+  Matrix<BaseFloat> w_then_b;
+  ReadKaldiObject(matrix_filename, &w_then_b);
+  KALDI_ASSERT(w_then_b.NumCols() == Group() && w_then_b.NumRows() == KernelDim() + 1);
+  Matrix<BaseFloat> w(KernelDim(), Group(), kUndefined);
+  Vector<BaseFloat> b(Group(), kUndefined);
+  for (int32 c = 0; c < Group(); c++) {
+    for (int32 r = 0; r < KernelDim(); r++) w(r, c) = w_then_b(r, c);
+    b(c) = w_then_b(KernelDim(), c);
+  }
   linear_params_ = w;
   bias_params_ = b;
-  prev_grad_.Resize(KernelDim(), group);
-  prev_grad_.SetZero();
+  prev_grad_.Resize(KernelDim(), group, kSetZero);
 }
 
-// reference :323-385.  Key order and the quirk of App. C.2 are kept: "weight-decay" and
-// "momentum" are consumed AFTER Init, so the config values are swallowed but not
-// applied -- a freshly initialised conv layer runs with the constructor defaults
-// (0.0002 / 0.9) until SetWeightDecay / SetMomentum / Read change them.
+// Config line (reference :323-385).  A quirk of the reference is kept: "weight-decay"
+// and "momentum" are accepted on the line but NOT applied -- a freshly initialised convolution runs with
+// the constructor defaults (0.0002 / 0.9) until SetWeightDecay / SetMomentum / Read change them; models
+// trained with the reference depend on it.
 void ConvolutionComponent::InitFromString(std::string args) {
-  std::string orig_args(args);
-  bool ok = true;
-  BaseFloat learning_rate = learning_rate_;
-  BaseFloat weight_decay = weight_decay_, momentum = momentum_;
-  std::string matrix_filename;
-  int32 in_height = 0, in_width = 0, in_channel = 0, in_pad_height = 0, in_pad_width = 0,
-        kernel_height = 0, kernel_width = 0, stride = 1, group = 0, out_height = 0, out_width = 0;
-
-  ok = ok && ParseFromString("learning-rate", &args, &learning_rate);   // mandatory here
-  ok = ok && ParseFromString("in-height", &args, &in_height);
-  ok = ok && ParseFromString("in-width", &args, &in_width);
-  ok = ok && ParseFromString("in-channel", &args, &in_channel);
-  ParseFromString("in-pad-height", &args, &in_pad_height);
-  ParseFromString("in-pad-width", &args, &in_pad_width);
-  ok = ok && ParseFromString("kernel-height", &args, &kernel_height);
-  ok = ok && ParseFromString("kernel-width", &args, &kernel_width);
-  ok = ok && ParseFromString("stride", &args, &stride);
-  ok = ok && ParseFromString("group", &args, &group);
-  ok = ok && ParseFromString("out-height", &args, &out_height);
-  ok = ok && ParseFromString("out-width", &args, &out_width);
-  if (!ok) KALDI_ERR << "Bad initializer " << orig_args;
-  KALDI_ASSERT(stride != 0);
-  KALDI_ASSERT(out_height == 1 + (in_height + (2 * in_pad_height) - kernel_height) / stride &&
-               "out_height_ == 1 + (in_height + (2*in_pad_height) - kernel_height) / stride ");
-  KALDI_ASSERT(out_width == 1 + (in_width + (2 * in_pad_width) - kernel_width) / stride &&
-               "out_width == 1 + (in_width + (2*in_pad_width) - kernel_width) / stride");
-  KALDI_ASSERT(in_pad_height >= 0 && "in-pad-height should be positive");
-  KALDI_ASSERT(in_pad_width >= 0 && "in-pad-width should be positive");
-
-  if (ParseFromString("matrix", &args, &matrix_filename)) {
-    Init(learning_rate, in_height, in_width, in_channel, in_pad_height, in_pad_width, kernel_height,
-         kernel_width, stride, group, out_height, out_width, weight_decay, momentum, matrix_filename);
-  } else {
-    BaseFloat param_stddev = 1.0 / std::sqrt(kernel_height * kernel_width), bias_stddev = 1.0;
+  const std::string line(args);
+  ConvolutionComponent parsed;                         // the table's members, filled from the line
+  parsed.learning_rate_ = learning_rate_;
+  if (!parsed.StreamFields().ParseConfig(&args)) KALDI_ERR << "Bad initializer " << line;
+  parsed.CheckGeometry();
+  std::string matrix;
+  BaseFloat param_stddev = 1.0 / std::sqrt(static_cast<BaseFloat>(parsed.kernel_height_ * parsed.kernel_width_)),
+            bias_stddev = 1.0, ignored = 0.0;
+  const bool from_matrix = ParseFromString("matrix", &args, &matrix);
+  if (!from_matrix) {
     ParseFromString("param-stddev", &args, &param_stddev);
     ParseFromString("bias-stddev", &args, &bias_stddev);
-    Init(learning_rate, in_height, in_width, in_channel, in_pad_height, in_pad_width, kernel_height,
-         kernel_width, stride, group, out_height, out_width, param_stddev, bias_stddev, weight_decay,
-         momentum);
   }
-  ParseFromString("weight-decay", &args, &weight_decay);   // consumed, not applied (C.2)
-  ParseFromString("momentum", &args, &momentum);
+  ParseFromString("weight-decay", &args, &ignored);     // accepted, not applied
+  ParseFromString("momentum", &args, &ignored);
   if (!args.empty()) KALDI_ERR << "Could not process these elements in initializer: " << args;
+  const ConvolutionComponent &g = parsed;
+  if (from_matrix)
+    Init(g.learning_rate_, g.in_height_, g.in_width_, g.in_channel_, g.in_pad_height_, g.in_pad_width_,
+         g.kernel_height_, g.kernel_width_, g.stride_, g.group_, g.out_height_, g.out_width_, weight_decay_,
+         momentum_, matrix);
+  else
+    Init(g.learning_rate_, g.in_height_, g.in_width_, g.in_channel_, g.in_pad_height_, g.in_pad_width_,
+         g.kernel_height_, g.kernel_width_, g.stride_, g.group_, g.out_height_, g.out_width_, param_stddev,
+         bias_stddev, weight_decay_, momentum_);
 }
 
-// reference :387-421
+static BaseFloat Rms(const CuMatrixBase<BaseFloat> &m) {
+  return std::sqrt(TraceMatMat(m, m, kTrans) / (static_cast<BaseFloat>(m.NumRows()) * m.NumCols()));
+}
+
+// The fields the reference prints (:387-421), grouped the same way.
 std::string ConvolutionComponent::Info() const {
-  std::stringstream stream;
-  BaseFloat linear_params_size = static_cast<BaseFloat>(linear_params_.NumRows()) *
-                                 static_cast<BaseFloat>(linear_params_.NumCols());
-  BaseFloat linear_stddev = std::sqrt(TraceMatMat(linear_params_, linear_params_, kTrans) / linear_params_size),
-            bias_stddev = std::sqrt(VecVec(bias_params_, bias_params_) / bias_params_.Dim());
-  stream << Type() << ", input-dim=" << InputDim() << " ( in-height=" << In_height()
-         << ", in-width=" << In_width() << ", in-channels=" << In_channels()
-         << "), output-dim=" << OutputDim() << " ( out-height=" << Out_height()
-         << ", out-width=" << Out_width() << ", group-num=" << Group()
-         << "), kernel-dim=" << KernelDim() << " ( kernel-height=" << Kernel_height()
-         << ", kernel-width=" << Kernel_width() << "), ( padding-height=" << in_pad_height_
-         << ", padding-width=" << in_pad_width_ << "), linear-params-stddev=" << linear_stddev
-         << ", bias-params-stddev=" << bias_stddev << ", learning-rate=" << LearningRate()
-         << ", weight-decay=" << weight_decay_ << ", momentum=" << momentum_;
-  return stream.str();
+  std::ostringstream os;
+  os << Type() << ", input-dim=" << InputDim() << " ( in-height=" << in_height_ << ", in-width=" << in_width_
+     << ", in-channels=" << in_channel_ << "), output-dim=" << OutputDim() << " ( out-height=" << out_height_
+     << ", out-width=" << out_width_ << ", group-num=" << group_ << "), kernel-dim=" << KernelDim()
+     << " ( kernel-height=" << kernel_height_ << ", kernel-width=" << kernel_width_
+     << "), ( padding-height=" << in_pad_height_ << ", padding-width=" << in_pad_width_
+     << "), linear-params-stddev=" << Rms(linear_params_)
+     << ", bias-params-stddev=" << std::sqrt(VecVec(bias_params_, bias_params_) / bias_params_.Dim())
+     << ", learning-rate=" << learning_rate_ << ", weight-decay=" << weight_decay_
+     << ", momentum=" << momentum_;
+  return os.str();
 }
 
 // reference :423-446: [PaddingZero] -> Conv2D -> AddMatRepVec, here ONE implicit GEMM
@@ -317,82 +334,35 @@ void ConvolutionComponent::SetZero(bool treat_as_gradient) {      // reference :
   if (treat_as_gradient) is_gradient_ = true;
 }
 
-// Serialisation: token order of reference :556-666, written from one table so Read and
-// Write cannot drift apart.
+// Model stream (reference :556-666): the table above, then -- on input only -- the <AvgInput> /
+// <AvgInputCount> pair some old files carry (read and discarded, :603-610) and an optional <IsGradient>.
 void ConvolutionComponent::Read(std::istream &is, bool binary) {
-  const std::string beg = "<" + Type() + ">", end = "</" + Type() + ">";
-  ExpectOneOrTwoTokens(is, binary, beg, "<in_height>");
-  ReadBasicType(is, binary, &in_height_);
-  struct { const char *tok; int32 *field; } ints[] = {
-      {"<in_width>", &in_width_}, {"<in_channel>", &in_channel_},
-      {"<kernel_height>", &kernel_height_}, {"<kernel_width>", &kernel_width_},
-      {"<stride>", &stride_}, {"<padding_height>", &in_pad_height_},
-      {"<padding_width>", &in_pad_width_}, {"<group>", &group_},
-      {"<out_height>", &out_height_}, {"<out_width>", &out_width_}};
-  for (size_t i = 0; i < sizeof(ints) / sizeof(ints[0]); i++) {
-    ExpectToken(is, binary, ints[i].tok);
-    ReadBasicType(is, binary, ints[i].field);
-  }
-  ExpectToken(is, binary, "<LearningRate>");
-  ReadBasicType(is, binary, &learning_rate_);
-  ExpectToken(is, binary, "<WeightDecay>");
-  ReadBasicType(is, binary, &weight_decay_);
-  ExpectToken(is, binary, "<Momentum>");
-  ReadBasicType(is, binary, &momentum_);
-  ExpectToken(is, binary, "<LinearParams>");
-  linear_params_.Read(is, binary);
-  ExpectToken(is, binary, "<BiasParams>");
-  bias_params_.Read(is, binary);
-  ExpectToken(is, binary, "<PrevGrad>");
-  prev_grad_.Read(is, binary);
+  const FieldList f = StreamFields();
+  const std::string end = "</" + Type() + ">";
+  ExpectOneOrTwoTokens(is, binary, "<" + Type() + ">", f.FirstToken());
+  f.Read(is, binary, /*skip_first_token=*/true, 0, kConvOptionalFrom);
+  is_gradient_ = false;
   std::string tok;
-  ReadToken(is, binary, &tok);
-  if (tok == "<AvgInput>") {   // back-compatibility (:603-610): discard
-    CuVector<BaseFloat> avg_input;
-    avg_input.Read(is, binary);
-    BaseFloat avg_input_count;
-    ExpectToken(is, binary, "<AvgInputCount>");
-    ReadBasicType(is, binary, &avg_input_count);
-    ReadToken(is, binary, &tok);
-  }
-  if (tok == "<IsGradient>") {
-    ReadBasicType(is, binary, &is_gradient_);
-    ExpectToken(is, binary, end);
-  } else {
-    is_gradient_ = false;
-    KALDI_ASSERT(tok == end);
+  for (ReadToken(is, binary, &tok); tok != end; ReadToken(is, binary, &tok)) {
+    if (tok == "<AvgInput>") {
+      CuVector<BaseFloat> unused;
+      unused.Read(is, binary);
+    } else if (tok == "<AvgInputCount>") {
+      BaseFloat unused;
+      ReadBasicType(is, binary, &unused);
+    } else if (tok == "<IsGradient>") {
+      ReadBasicType(is, binary, &is_gradient_);
+    } else {
+      KALDI_ERR << "Unexpected token " << tok << " in " << Type();
+    }
   }
   workspace_rows_ = -1;
 }
 
 void ConvolutionComponent::Write(std::ostream &os, bool binary) const {
-  const std::string beg = "<" + Type() + ">", end = "</" + Type() + ">";
-  WriteToken(os, binary, beg);
-  struct { const char *tok; int32 value; } ints[] = {
-      {"<in_height>", in_height_}, {"<in_width>", in_width_}, {"<in_channel>", in_channel_},
-      {"<kernel_height>", kernel_height_}, {"<kernel_width>", kernel_width_},
-      {"<stride>", stride_}, {"<padding_height>", in_pad_height_},
-      {"<padding_width>", in_pad_width_}, {"<group>", group_},
-      {"<out_height>", out_height_}, {"<out_width>", out_width_}};
-  for (size_t i = 0; i < sizeof(ints) / sizeof(ints[0]); i++) {
-    WriteToken(os, binary, ints[i].tok);
-    WriteBasicType(os, binary, ints[i].value);
-  }
-  WriteToken(os, binary, "<LearningRate>");
-  WriteBasicType(os, binary, learning_rate_);
-  WriteToken(os, binary, "<WeightDecay>");
-  WriteBasicType(os, binary, weight_decay_);
-  WriteToken(os, binary, "<Momentum>");
-  WriteBasicType(os, binary, momentum_);
-  WriteToken(os, binary, "<LinearParams>");
-  linear_params_.Write(os, binary);
-  WriteToken(os, binary, "<BiasParams>");
-  bias_params_.Write(os, binary);
-  WriteToken(os, binary, "<PrevGrad>");
-  prev_grad_.Write(os, binary);
-  WriteToken(os, binary, "<IsGradient>");
-  WriteBasicType(os, binary, is_gradient_);
-  WriteToken(os, binary, end);
+  WriteToken(os, binary, "<" + Type() + ">");
+  const_cast<ConvolutionComponent *>(this)->StreamFields().Write(os, binary);
+  WriteToken(os, binary, "</" + Type() + ">");
 }
 
 BaseFloat ConvolutionComponent::DotProduct(const UpdatableComponent &other_in) const {   // :670-675
@@ -402,22 +372,11 @@ BaseFloat ConvolutionComponent::DotProduct(const UpdatableComponent &other_in) c
          VecVec(bias_params_, other->bias_params_);
 }
 
-Component *ConvolutionComponent::Copy() const {      // reference :679-705 (includes prev_grad_)
-  ConvolutionComponent *ans = new ConvolutionComponent();
-  ans->learning_rate_ = learning_rate_;
-  ans->linear_params_ = linear_params_;
-  ans->bias_params_ = bias_params_;
-  ans->is_gradient_ = is_gradient_;
-  ans->in_height_ = in_height_; ans->in_width_ = in_width_; ans->in_channel_ = in_channel_;
-  ans->kernel_height_ = kernel_height_; ans->kernel_width_ = kernel_width_;
-  ans->stride_ = stride_;
-  ans->in_pad_height_ = in_pad_height_; ans->in_pad_width_ = in_pad_width_;
-  ans->group_ = group_;
-  ans->out_height_ = out_height_; ans->out_width_ = out_width_;
-  ans->weight_decay_ = weight_decay_;
-  ans->momentum_ = momentum_;
-  ans->prev_grad_ = prev_grad_;
-  return ans;
+// reference :679-705; the momentum matrix is part of the copy (the copy CONSTRUCTOR zeroes it).
+Component *ConvolutionComponent::Copy() const {
+  ConvolutionComponent *c = new ConvolutionComponent(*this);
+  c->prev_grad_ = prev_grad_;
+  return c;
 }
 
 void ConvolutionComponent::PerturbParams(BaseFloat stddev) {     // reference :706-714
@@ -489,6 +448,24 @@ void ConvolutionComponent::SetGradientStorage(float *base) {
   b_grad_.data = base + (size_t)stride * KernelDim(); b_grad_.rows = 1; b_grad_.cols = group_;
   b_grad_.stride = group_;
   grad_external_ = true;
+}
+
+void ConvolutionComponent::SetParameterStorage(float *base) {
+  const int32 rows = linear_params_.NumRows(), cols = linear_params_.NumCols(), dim = bias_params_.Dim();
+  const int32 stride = CuDevice::PitchInElements(cols, sizeof(BaseFloat));
+  CuMatrix<BaseFloat> w(linear_params_);
+  CuVector<BaseFloat> b(bias_params_);
+  if (base != NULL) {
+    linear_params_.Borrow(base, rows, cols, stride);
+    bias_params_.Borrow(base + (size_t)stride * rows, dim);
+    linear_params_.CopyFromMat(w);
+    bias_params_.CopyFromVec(b);
+  } else {
+    linear_params_.Swap(&w);
+    bias_params_.Borrow(NULL, 0);
+    bias_params_ = b;
+  }
+  staged_src_ = NULL;
 }
 
 std::vector<UpdatableComponent::GradBuffer> ConvolutionComponent::GradientBuffers() {

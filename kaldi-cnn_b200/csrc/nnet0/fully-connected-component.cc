@@ -5,6 +5,7 @@
 #include <sstream>
 
 #include "nnet0/nnet-component-nnet0.h"
+#include "nnet0/component-fields.h"
 #include "util/common-utils.h"
 #include "cnsl-cu-kernels.h"
 
@@ -14,137 +15,128 @@ namespace nnet0 {
 static inline cudaStream_t Str() { return CuDevice::Instantiate().Stream(); }
 static inline int Math() { return CuDevice::Instantiate().MathMode(); }
 
-// reference :980-999 (no <IsGradient> in this component's stream)
+// ---- construction, configuration, (de)serialisation ---------------------------------------------
+// What the reference does here (nnet0/nnet-component-nnet0.cc:980-1131) is fixed by its files: the model
+// stream is <LearningRate> <LinearParams> <BiasParams> <WeightDecay> <Momentum> <PrevGrad> (no
+// <IsGradient>), the config keys are learning-rate / weight-decay / momentum / matrix / input-dim /
+// output-dim / param-stddev / bias-stddev.  Both are declared once, as FieldLists, and walked.
+
+FieldList FullyConnectedComponent::StreamFields() {
+  FieldList f;
+  f.Float("learning-rate", "<LearningRate>", &learning_rate_)
+      .Matrix("<LinearParams>", &linear_params_)
+      .Vector("<BiasParams>", &bias_params_)
+      .Float("weight-decay", "<WeightDecay>", &weight_decay_)
+      .Float("momentum", "<Momentum>", &momentum_)
+      .Matrix("<PrevGrad>", &prev_grad_);
+  return f;
+}
+
 void FullyConnectedComponent::Read(std::istream &is, bool binary) {
-  const std::string beg = "<" + Type() + ">", end = "</" + Type() + ">";
-  ExpectOneOrTwoTokens(is, binary, beg, "<LearningRate>");
-  ReadBasicType(is, binary, &learning_rate_);
-  ExpectToken(is, binary, "<LinearParams>");
-  linear_params_.Read(is, binary);
-  ExpectToken(is, binary, "<BiasParams>");
-  bias_params_.Read(is, binary);
-  ExpectToken(is, binary, "<WeightDecay>");
-  ReadBasicType(is, binary, &weight_decay_);
-  ExpectToken(is, binary, "<Momentum>");
-  ReadBasicType(is, binary, &momentum_);
-  ExpectToken(is, binary, "<PrevGrad>");
-  prev_grad_.Read(is, binary);
-  ExpectToken(is, binary, end);
+  const FieldList f = StreamFields();
+  ExpectOneOrTwoTokens(is, binary, "<" + Type() + ">", f.FirstToken());
+  f.Read(is, binary, /*skip_first_token=*/true);
+  ExpectToken(is, binary, "</" + Type() + ">");
 }
 
-// reference :1001-1020
 void FullyConnectedComponent::Write(std::ostream &os, bool binary) const {
-  const std::string beg = "<" + Type() + ">", end = "</" + Type() + ">";
-  WriteToken(os, binary, beg);
-  WriteToken(os, binary, "<LearningRate>");
-  WriteBasicType(os, binary, learning_rate_);
-  WriteToken(os, binary, "<LinearParams>");
-  linear_params_.Write(os, binary);
-  WriteToken(os, binary, "<BiasParams>");
-  bias_params_.Write(os, binary);
-  WriteToken(os, binary, "<WeightDecay>");
-  WriteBasicType(os, binary, weight_decay_);
-  WriteToken(os, binary, "<Momentum>");
-  WriteBasicType(os, binary, momentum_);
-  WriteToken(os, binary, "<PrevGrad>");
-  prev_grad_.Write(os, binary);
-  WriteToken(os, binary, end);
+  WriteToken(os, binary, "<" + Type() + ">");
+  const_cast<FullyConnectedComponent *>(this)->StreamFields().Write(os, binary);
+  WriteToken(os, binary, "</" + Type() + ">");
 }
 
-// reference :1022-1045: the bias is CONSTANT bias_stddev (not random), wd and momentum
-// must be positive.
+void FullyConnectedComponent::SetHyper(BaseFloat learning_rate, BaseFloat weight_decay, BaseFloat momentum) {
+  UpdatableComponent::Init(learning_rate);
+  weight_decay_ = weight_decay;
+  momentum_ = momentum;
+}
+
+// Random start (reference :1022-1045): W ~ N(0, param_stddev^2); the bias is the CONSTANT bias_stddev;
+// weight decay and momentum must be positive; the momentum matrix starts at zero.
 void FullyConnectedComponent::Init(BaseFloat learning_rate, int32 input_dim, int32 output_dim,
                                    BaseFloat param_stddev, BaseFloat bias_stddev,
                                    BaseFloat weight_decay, BaseFloat momentum) {
-  UpdatableComponent::Init(learning_rate);
-  KALDI_ASSERT(input_dim > 0 && output_dim > 0);
-  linear_params_.Resize(output_dim, input_dim);
-  bias_params_.Resize(output_dim);
-  KALDI_ASSERT(output_dim > 0 && input_dim > 0 && param_stddev >= 0.0);
+  KALDI_ASSERT(input_dim > 0 && output_dim > 0 && param_stddev >= 0.0);
+  KALDI_ASSERT(weight_decay > 0.0 && momentum > 0.0);
+  SetHyper(learning_rate, weight_decay, momentum);
+  linear_params_.Resize(output_dim, input_dim, kUndefined);
   linear_params_.SetRandn();
   linear_params_.Scale(param_stddev);
-  bias_params_.SetZero();
-  bias_params_.Add(bias_stddev);
-  weight_decay_ = weight_decay;
-  KALDI_ASSERT(weight_decay_ > 0.0);
-  momentum_ = momentum;
-  KALDI_ASSERT(momentum_ > 0.0);
-  prev_grad_.Resize(output_dim, input_dim);
-  prev_grad_.SetZero();
+  bias_params_.Resize(output_dim, kUndefined);
+  bias_params_.Set(bias_stddev);
+  prev_grad_.Resize(output_dim, input_dim, kSetZero);
 }
 
-// reference :1048-1064 (prev_grad_ is seeded with the weights there, App. C.3; kept)
+// Start from a [W | b] matrix file (reference :1048-1064).  The reference seeds the momentum matrix
+// with the weights themselves; kept, since the first update depends on it.
 void FullyConnectedComponent::Init(BaseFloat learning_rate, BaseFloat weight_decay,
                                    BaseFloat momentum, std::string matrix_filename) {
-  UpdatableComponent::Init(learning_rate);
-  weight_decay_ = weight_decay;
-  momentum_ = momentum;
-  CuMatrix<BaseFloat> mat;
-  ReadKaldiObject(matrix_filename, &mat);
-  KALDI_ASSERT(mat.NumCols() >= 2);
-  int32 input_dim = mat.NumCols() - 1, output_dim = mat.NumRows();
-  linear_params_.Resize(output_dim, input_dim);
-  bias_params_.Resize(output_dim);
-  linear_params_.CopyFromMat(mat.Range(0, output_dim, 0, input_dim));
-  bias_params_.CopyColFromMat(mat, input_dim);
-  prev_grad_.Resize(output_dim, input_dim);
-  prev_grad_.CopyFromMat(mat.Range(0, output_dim, 0, input_dim));
+  SetHyper(learning_rate, weight_decay, momentum);
+  CuMatrix<BaseFloat> w_and_b;
+  ReadKaldiObject(matrix_filename, &w_and_b);
+  KALDI_ASSERT(w_and_b.NumCols() >= 2);
+  const int32 rows = w_and_b.NumRows(), cols = w_and_b.NumCols() - 1;
+  linear_params_ = w_and_b.Range(0, rows, 0, cols);
+  prev_grad_ = linear_params_;
+  bias_params_.Resize(rows, kUndefined);
+  bias_params_.CopyColFromMat(w_and_b, cols);
 }
 
-// reference :1066-1100 (unlike the convolution, weight-decay / momentum ARE applied)
+// reference :1066-1100.  Unlike the convolution, weight-decay / momentum of the config line ARE applied.
 void FullyConnectedComponent::InitFromString(std::string args) {
-  std::string orig_args(args);
-  std::string matrix_filename;
-  BaseFloat learning_rate = learning_rate_;
-  BaseFloat weight_decay = weight_decay_, momentum = momentum_;
-  int32 input_dim = -1, output_dim = -1;
-  ParseFromString("learning-rate", &args, &learning_rate);   // optional.
-  ParseFromString("weight-decay", &args, &weight_decay);
-  ParseFromString("momentum", &args, &momentum);
-  if (ParseFromString("matrix", &args, &matrix_filename)) {
-    Init(learning_rate, weight_decay, momentum, matrix_filename);
-    if (ParseFromString("input-dim", &args, &input_dim))
-      KALDI_ASSERT(input_dim == InputDim() && "input-dim mismatch vs. matrix.");
-    if (ParseFromString("output-dim", &args, &output_dim))
-      KALDI_ASSERT(output_dim == OutputDim() && "output-dim mismatch vs. matrix.");
+  const std::string line(args);
+  struct {
+    BaseFloat learning_rate, weight_decay, momentum, param_stddev, bias_stddev;
+    int32 input_dim, output_dim;
+  } o = {learning_rate_, weight_decay_, momentum_, -1.0f, 1.0f, -1, -1};
+  std::string matrix;
+  FieldList keys;
+  keys.Float("learning-rate", NULL, &o.learning_rate, FieldList::kOptional)
+      .Float("weight-decay", NULL, &o.weight_decay, FieldList::kOptional)
+      .Float("momentum", NULL, &o.momentum, FieldList::kOptional)
+      .Int("input-dim", NULL, &o.input_dim, FieldList::kOptional)
+      .Int("output-dim", NULL, &o.output_dim, FieldList::kOptional)
+      .Float("param-stddev", NULL, &o.param_stddev, FieldList::kOptional)
+      .Float("bias-stddev", NULL, &o.bias_stddev, FieldList::kOptional);
+  keys.ParseConfig(&args);
+  const bool from_matrix = ParseFromString("matrix", &args, &matrix);
+  if (from_matrix) {
+    Init(o.learning_rate, o.weight_decay, o.momentum, matrix);
+    KALDI_ASSERT((o.input_dim < 0 || o.input_dim == InputDim()) && "input-dim mismatch vs. matrix.");
+    KALDI_ASSERT((o.output_dim < 0 || o.output_dim == OutputDim()) && "output-dim mismatch vs. matrix.");
   } else {
-    bool ok = true;
-    ok = ok && ParseFromString("input-dim", &args, &input_dim);
-    ok = ok && ParseFromString("output-dim", &args, &output_dim);
-    BaseFloat param_stddev = 1.0 / std::sqrt(input_dim), bias_stddev = 1.0;
-    ParseFromString("param-stddev", &args, &param_stddev);
-    ParseFromString("bias-stddev", &args, &bias_stddev);
-    if (!ok) KALDI_ERR << "Bad initializer " << orig_args;
-    Init(learning_rate, input_dim, output_dim, param_stddev, bias_stddev, weight_decay, momentum);
+    if (o.input_dim < 0 || o.output_dim < 0) KALDI_ERR << "Bad initializer " << line;
+    if (o.param_stddev < 0) o.param_stddev = 1.0 / std::sqrt(static_cast<BaseFloat>(o.input_dim));
+    Init(o.learning_rate, o.input_dim, o.output_dim, o.param_stddev, o.bias_stddev, o.weight_decay,
+         o.momentum);
   }
   if (!args.empty()) KALDI_ERR << "Could not process these elements in initializer: " << args;
 }
 
-// reference :1102-1119
-std::string FullyConnectedComponent::Info() const {
-  std::stringstream stream;
-  BaseFloat linear_params_size = static_cast<BaseFloat>(linear_params_.NumRows()) *
-                                 static_cast<BaseFloat>(linear_params_.NumCols());
-  BaseFloat linear_stddev = std::sqrt(TraceMatMat(linear_params_, linear_params_, kTrans) / linear_params_size),
-            bias_stddev = std::sqrt(VecVec(bias_params_, bias_params_) / bias_params_.Dim());
-  stream << Type() << ", input-dim=" << InputDim() << ", output-dim=" << OutputDim()
-         << ", linear-params-stddev=" << linear_stddev << ", bias-params-stddev=" << bias_stddev
-         << ", learning-rate=" << LearningRate() << ", weight-decay=" << weight_decay_
-         << ", momentum=" << momentum_;
-  return stream.str();
+// Root mean square of the entries (what nnet2's Info() strings call "stddev").
+static BaseFloat Rms(const CuMatrixBase<BaseFloat> &m) {
+  return std::sqrt(TraceMatMat(m, m, kTrans) / (static_cast<BaseFloat>(m.NumRows()) * m.NumCols()));
 }
 
-// reference :1121-1131
+// Same fields as the reference prints (:1102-1119): dims, parameter RMS, then the hyper-parameters.
+std::string FullyConnectedComponent::Info() const {
+  std::ostringstream os;
+  os << Type() << ", input-dim=" << InputDim() << ", output-dim=" << OutputDim()
+     << ", linear-params-stddev=" << Rms(linear_params_)
+     << ", bias-params-stddev=" << std::sqrt(VecVec(bias_params_, bias_params_) / bias_params_.Dim()) << ", "
+     << const_cast<FullyConnectedComponent *>(this)->StreamFields().Describe();
+  return os.str();
+}
+
 Component *FullyConnectedComponent::Copy() const {
-  FullyConnectedComponent *ans = new FullyConnectedComponent();
-  ans->learning_rate_ = learning_rate_;
-  ans->linear_params_ = linear_params_;
-  ans->bias_params_ = bias_params_;
-  ans->weight_decay_ = weight_decay_;
-  ans->momentum_ = momentum_;
-  ans->prev_grad_ = prev_grad_;
-  ans->is_gradient_ = is_gradient_;
-  return ans;
+  FullyConnectedComponent *c = new FullyConnectedComponent();
+  // the state is exactly what the stream carries, plus the gradient flag
+  c->SetHyper(learning_rate_, weight_decay_, momentum_);
+  c->linear_params_ = linear_params_;
+  c->bias_params_ = bias_params_;
+  c->prev_grad_ = prev_grad_;
+  c->is_gradient_ = is_gradient_;
+  return c;
 }
 
 // The SGD step of reference :1133-1143 on an already computed gradient:

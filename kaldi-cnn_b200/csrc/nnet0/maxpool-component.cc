@@ -1,10 +1,12 @@
 // nnet0/maxpool-component.cc -- MaxpoolComponent for the B200 build.
-// Follows reference src/nnet0/nnet-component-nnet0.cc:779-978.
+// Behaviour of reference src/nnet0/nnet-component-nnet0.cc:779-978 (config keys, model stream, geometry
+// checks, Propagate / Backprop semantics); the glue is table-driven (nnet0/component-fields.h).
 
 #include <cmath>
 #include <sstream>
 
 #include "nnet0/nnet-component-nnet0.h"
+#include "nnet0/component-fields.h"
 #include "util/common-utils.h"
 #include "cnsl-cu-kernels.h"
 
@@ -17,75 +19,90 @@ MaxpoolComponent::~MaxpoolComponent() {
   if (index_) CuDevice::Instantiate().Free(index_);
 }
 
-// reference :779-812
-void MaxpoolComponent::Init(int32 input_dim, int32 output_dim, int32 in_height, int32 in_width,
-                            int32 in_channel, int32 pool_height_dim, int32 pool_width_dim,
-                            int32 pool_channel_dim, bool overlap, bool overlap2D) {
-  input_dim_ = input_dim;
-  output_dim_ = output_dim;
-  in_height_ = in_height;
-  in_width_ = in_width;
-  in_channel_ = in_channel;
-  pool_height_dim_ = pool_height_dim;
-  pool_width_dim_ = pool_width_dim;
-  pool_channel_dim_ = pool_channel_dim;
-  overlap_ = overlap;
-  overlap2D_ = overlap2D;
+// ---- geometry ------------------------------------------------------------------------------------
+// Output maps per (h, w) position for the three pooling modes of the reference (:779-812, :832-850):
+//   plain      C / pool_channel_dim            (windows tile the maps)
+//   overlap    C - pool_channel_dim + 1        (window slides over the maps, step 1)
+//   overlap2D  (sqrt(C) - pool_channel_dim + 1)^2   (maps arranged as a sqrt(C) x sqrt(C) grid, square window)
+// 0 = the geometry is not valid.
+static int32 PooledMaps(int32 in_channel, int32 pool_channel_dim, bool overlap, bool overlap2D) {
+  if (in_channel <= 0 || pool_channel_dim <= 0 || (overlap && overlap2D)) return 0;
+  if (overlap2D) {
+    // as the reference computes it (double sqrt, truncation of the square), so that a config the
+    // reference accepts gives the same output-dim here
+    int32 maps = pow((sqrt(in_channel) - pool_channel_dim + 1), 2);
+    return maps > 0 ? maps : 0;
+  }
+  if (overlap) return in_channel >= pool_channel_dim ? in_channel - pool_channel_dim + 1 : 0;
+  return in_channel % pool_channel_dim == 0 ? in_channel / pool_channel_dim : 0;
+}
 
-  KALDI_ASSERT((in_height_ * in_width_ * in_channel_) == input_dim_);
-  KALDI_ASSERT(input_dim_ > 0 && output_dim_ > 0 && pool_height_dim_ > 0 && pool_width_dim_ > 0 &&
-               pool_channel_dim_ > 0);
-  KALDI_ASSERT(in_height_ % pool_height_dim_ == 0);
-  KALDI_ASSERT(in_width_ % pool_width_dim_ == 0);
-  KALDI_ASSERT((overlap && overlap2D) != true);
+FieldList MaxpoolComponent::StreamFields() {
+  FieldList f;
+  f.Int(NULL, "<InputDim>", &input_dim_)
+      .Int("in-height", "<in_height>", &in_height_)
+      .Int("in-width", "<in_width>", &in_width_)
+      .Int("in-channel", "<in_channel>", &in_channel_)
+      .Int(NULL, "<OutputDim>", &output_dim_)
+      .Int("pool-height-dim", "<PoolHeightDim>", &pool_height_dim_)
+      .Int("pool-width-dim", "<PoolWidthDim>", &pool_width_dim_)
+      .Int("pool-channel-dim", "<PoolChannelDim>", &pool_channel_dim_)
+      .Bool("overlap", "<Overlap>", &overlap_, FieldList::kOptional)          // [8], [9]: absent from
+      .Bool("overlap2D", "<Overlap2D>", &overlap2D_, FieldList::kOptional);   // older model files
+  return f;
+}
+static const size_t kMaxpoolOptionalFrom = 8;
 
-  if (overlap2D) {   // pooling region = pool_channel_dim x pool_channel_dim on a sqrt(C) x sqrt(C) map
+// Checks what the reference's Init asserts (:791-811).
+void MaxpoolComponent::Check() const {
+  KALDI_ASSERT(input_dim_ > 0 && output_dim_ > 0 && in_height_ * in_width_ * in_channel_ == input_dim_);
+  KALDI_ASSERT(pool_height_dim_ > 0 && pool_width_dim_ > 0 && pool_channel_dim_ > 0);
+  KALDI_ASSERT(in_height_ % pool_height_dim_ == 0 && in_width_ % pool_width_dim_ == 0);
+  KALDI_ASSERT(!(overlap_ && overlap2D_));
+  const int32 maps = PooledMaps(in_channel_, pool_channel_dim_, overlap_, overlap2D_);
+  KALDI_ASSERT(maps > 0);
+  if (overlap_ || overlap2D_) {      // sliding windows run over the maps only
     KALDI_ASSERT(pool_height_dim_ == 1 && pool_width_dim_ == 1);
-    int32 output_channel = output_dim_ / (in_height_ * in_width_);
-    int32 expected_output_channel = pow((sqrt(in_channel_) - pool_channel_dim_ + 1), 2);
-    KALDI_ASSERT(output_channel == expected_output_channel);
-  } else if (overlap) {
-    KALDI_ASSERT(pool_height_dim_ == 1 && pool_width_dim_ == 1);
-    KALDI_ASSERT(input_dim_ / in_channel_ * (in_channel_ - pool_channel_dim_ + 1) == output_dim_);
+    KALDI_ASSERT(output_dim_ == in_height_ * in_width_ * maps);
   } else {
-    KALDI_ASSERT(input_dim_ % output_dim_ == 0);
-    KALDI_ASSERT(in_channel_ % pool_channel_dim_ == 0);
-    KALDI_ASSERT(input_dim_ / (pool_height_dim_ * pool_width_dim_ * pool_channel_dim_) == output_dim_);
+    KALDI_ASSERT(output_dim_ == (in_height_ / pool_height_dim_) * (in_width_ / pool_width_dim_) * maps);
   }
 }
 
-// reference :814-867
+void MaxpoolComponent::Init(int32 input_dim, int32 output_dim, int32 in_height, int32 in_width,
+                            int32 in_channel, int32 pool_height_dim, int32 pool_width_dim,
+                            int32 pool_channel_dim, bool overlap, bool overlap2D) {
+  input_dim_ = input_dim; output_dim_ = output_dim;
+  in_height_ = in_height; in_width_ = in_width; in_channel_ = in_channel;
+  pool_height_dim_ = pool_height_dim; pool_width_dim_ = pool_width_dim; pool_channel_dim_ = pool_channel_dim;
+  overlap_ = overlap; overlap2D_ = overlap2D;
+  Check();
+}
+
+// Config line (reference :814-867): the six geometry keys are required, overlap / overlap2D optional;
+// input-dim and output-dim follow from them.
 void MaxpoolComponent::InitFromString(std::string args) {
-  std::string orig_args(args);
-  int32 in_height = 1, in_width = 1, in_channel = 1;
-  int32 pool_height_dim = 1, pool_width_dim = 1, pool_channel_dim = 1;
-  bool overlap = false, overlap2D = false;
-
-  bool ok = ParseFromString("in-height", &args, &in_height) &&
-            ParseFromString("in-width", &args, &in_width) &&
-            ParseFromString("in-channel", &args, &in_channel) &&
-            ParseFromString("pool-height-dim", &args, &pool_height_dim) &&
-            ParseFromString("pool-width-dim", &args, &pool_width_dim) &&
-            ParseFromString("pool-channel-dim", &args, &pool_channel_dim);
-  ParseFromString("overlap", &args, &overlap);
-  ParseFromString("overlap2D", &args, &overlap2D);
-
-  int32 input_dim = in_height * in_width * in_channel;
-  int32 output_dim = 0;
-  if (ok && in_channel > 0 && pool_height_dim > 0 && pool_width_dim > 0 && pool_channel_dim > 0) {
-    if (overlap2D) {
-      int32 output_channel = pow((sqrt(in_channel) - pool_channel_dim + 1), 2);
-      output_dim = input_dim / in_channel * output_channel;
-    } else if (overlap) {
-      output_dim = input_dim / in_channel * (in_channel - pool_channel_dim + 1);
-    } else {
-      output_dim = input_dim / (pool_height_dim * pool_width_dim * pool_channel_dim);
+  const std::string line(args);
+  MaxpoolComponent parsed;
+  parsed.in_height_ = parsed.in_width_ = parsed.in_channel_ = 1;
+  parsed.pool_height_dim_ = parsed.pool_width_dim_ = parsed.pool_channel_dim_ = 1;
+  bool ok = parsed.StreamFields().ParseConfig(&args) && args.empty();
+  ok = ok && parsed.pool_height_dim_ > 0 && parsed.pool_width_dim_ > 0;
+  int32 positions = 0, maps = 0;
+  if (ok) {
+    maps = PooledMaps(parsed.in_channel_, parsed.pool_channel_dim_, parsed.overlap_, parsed.overlap2D_);
+    positions = parsed.in_height_ * parsed.in_width_;
+    if (!parsed.overlap_ && !parsed.overlap2D_) {
+      // as the reference: one integer division of the whole input dim (the divisibility of H and W is
+      // asserted by Init)
+      positions = parsed.in_height_ * parsed.in_width_ / (parsed.pool_height_dim_ * parsed.pool_width_dim_);
     }
   }
-  if (!ok || !args.empty() || output_dim <= 0)
-    KALDI_ERR << "Invalid initializer for layer of type " << Type() << ": \"" << orig_args << "\"";
-  Init(input_dim, output_dim, in_height, in_width, in_channel, pool_height_dim, pool_width_dim,
-       pool_channel_dim, overlap, overlap2D);
+  if (!ok || maps <= 0 || positions <= 0)
+    KALDI_ERR << "Invalid initializer for layer of type " << Type() << ": \"" << line << "\"";
+  Init(parsed.in_height_ * parsed.in_width_ * parsed.in_channel_, positions * maps, parsed.in_height_,
+       parsed.in_width_, parsed.in_channel_, parsed.pool_height_dim_, parsed.pool_width_dim_,
+       parsed.pool_channel_dim_, parsed.overlap_, parsed.overlap2D_);
 }
 
 // reference :869-880
@@ -147,80 +164,28 @@ void MaxpoolComponent::Backprop(const ChunkInfo &, const ChunkInfo &,
   CU_SAFE_CALL(cudaGetLastError());
 }
 
-// reference :894-934
+// Model stream (reference :894-959): eight ints, then <Overlap> / <Overlap2D> -- which files written
+// before those modes existed do not have.  (The reference's reader asks for one token too many when
+// only <Overlap> is present, :925-928, and can then only fail; such a stream is accepted here.)
 void MaxpoolComponent::Read(std::istream &is, bool binary) {
-  const std::string beg = "<" + Type() + ">", end = "</" + Type() + ">";
-  ExpectOneOrTwoTokens(is, binary, beg, "<InputDim>");
-  ReadBasicType(is, binary, &input_dim_);
-  ExpectToken(is, binary, "<in_height>");
-  ReadBasicType(is, binary, &in_height_);
-  ExpectToken(is, binary, "<in_width>");
-  ReadBasicType(is, binary, &in_width_);
-  ExpectToken(is, binary, "<in_channel>");
-  ReadBasicType(is, binary, &in_channel_);
-  ExpectToken(is, binary, "<OutputDim>");
-  ReadBasicType(is, binary, &output_dim_);
-  ExpectToken(is, binary, "<PoolHeightDim>");
-  ReadBasicType(is, binary, &pool_height_dim_);
-  ExpectToken(is, binary, "<PoolWidthDim>");
-  ReadBasicType(is, binary, &pool_width_dim_);
-  ExpectToken(is, binary, "<PoolChannelDim>");
-  ReadBasicType(is, binary, &pool_channel_dim_);
-  std::string tok;
-  ReadToken(is, binary, &tok);
-  overlap_ = false;
-  overlap2D_ = false;
-  if (tok == "<Overlap>") {       // newer files; older ones end right here
-    ReadBasicType(is, binary, &overlap_);
-    ReadToken(is, binary, &tok);
-    if (tok == "<Overlap2D>") {
-      ReadBasicType(is, binary, &overlap2D_);
-      ExpectToken(is, binary, end);
-    } else {
-      // the reference reads ONE MORE token here (ExpectToken after ReadToken, :925-928),
-      // which can only fail; accept the closing token that was just read.
-      KALDI_ASSERT(tok == end);
-    }
-  } else {
-    KALDI_ASSERT(tok == end);
-  }
+  const FieldList f = StreamFields();
+  ExpectOneOrTwoTokens(is, binary, "<" + Type() + ">", f.FirstToken());
+  f.Read(is, binary, /*skip_first_token=*/true, 0, kMaxpoolOptionalFrom);
+  overlap_ = overlap2D_ = false;
+  f.ReadTail(is, binary, kMaxpoolOptionalFrom, "</" + Type() + ">");
 }
 
-// reference :936-959
 void MaxpoolComponent::Write(std::ostream &os, bool binary) const {
-  WriteToken(os, binary, "<MaxpoolComponent>");
-  WriteToken(os, binary, "<InputDim>");
-  WriteBasicType(os, binary, input_dim_);
-  WriteToken(os, binary, "<in_height>");
-  WriteBasicType(os, binary, in_height_);
-  WriteToken(os, binary, "<in_width>");
-  WriteBasicType(os, binary, in_width_);
-  WriteToken(os, binary, "<in_channel>");
-  WriteBasicType(os, binary, in_channel_);
-  WriteToken(os, binary, "<OutputDim>");
-  WriteBasicType(os, binary, output_dim_);
-  WriteToken(os, binary, "<PoolHeightDim>");
-  WriteBasicType(os, binary, pool_height_dim_);
-  WriteToken(os, binary, "<PoolWidthDim>");
-  WriteBasicType(os, binary, pool_width_dim_);
-  WriteToken(os, binary, "<PoolChannelDim>");
-  WriteBasicType(os, binary, pool_channel_dim_);
-  WriteToken(os, binary, "<Overlap>");
-  WriteBasicType(os, binary, overlap_);
-  WriteToken(os, binary, "<Overlap2D>");
-  WriteBasicType(os, binary, overlap2D_);
-  WriteToken(os, binary, "</MaxpoolComponent>");
+  WriteToken(os, binary, "<" + Type() + ">");
+  const_cast<MaxpoolComponent *>(this)->StreamFields().Write(os, binary);
+  WriteToken(os, binary, "</" + Type() + ">");
 }
 
-// reference :961-978
 std::string MaxpoolComponent::Info() const {
-  std::stringstream stream;
-  stream << Type() << " input-dim=" << input_dim_ << " ( in-height=" << in_height_
-         << ", in-width=" << in_width_ << ", in-channels=" << in_channel_
-         << "), output-dim=" << output_dim_ << ", pool_height_dim_= " << pool_height_dim_
-         << ", pool_width_dim_ = " << pool_width_dim_ << ", pool_channel_dim_ = " << pool_channel_dim_
-         << ", max-pool-overlap_ = " << overlap_ << ", max-pool-overlap_2D = " << overlap2D_;
-  return stream.str();
+  std::ostringstream os;
+  os << Type() << ", input-dim=" << input_dim_ << ", output-dim=" << output_dim_ << ", "
+     << const_cast<MaxpoolComponent *>(this)->StreamFields().Describe();
+  return os.str();
 }
 
 }  // namespace nnet0

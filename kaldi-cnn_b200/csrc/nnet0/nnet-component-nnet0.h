@@ -32,6 +32,8 @@ using namespace kaldi::nnet2;
 namespace cnsl {
 namespace nnet0 {
 
+class FieldList;   // nnet0/component-fields.h: config keys + model-file tokens of a component, declared once
+
 /// 2-D convolution over [C][W][H] activations (H fastest), stride 1, optional zero
 /// padding.  "group" is the number of OUTPUT maps (filters), not channel grouping.
 ///   in  [num_chunks x in_height*in_width*in_channel]
@@ -115,6 +117,7 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   virtual void ApplyGradient(int32 total_num_samples);
   virtual size_t GradientFloats() const;
   virtual void SetGradientStorage(float *base);
+  virtual void SetParameterStorage(float *base);
   /// Opt-in for a caller that OWNS the activation buffers (NnetMinibatchUpdater) and so can
   /// promise that the matrix given to Backprop as in_value is, unmodified, the one last
   /// propagated: Backprop then reuses Propagate's channels-last staging copy instead of
@@ -137,6 +140,12 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   void ComputeGradient(const CuMatrixBase<BaseFloat> &in_value,
                        const CuMatrixBase<BaseFloat> &out_deriv);
   void EnsureGradBuffers();
+  FieldList StreamFields();
+  void CheckGeometry() const;
+  void SetShape(BaseFloat learning_rate, int32 in_height, int32 in_width, int32 in_channels,
+                int32 in_pad_height, int32 in_pad_width, int32 kernel_height, int32 kernel_width,
+                int32 stride, int32 group, int32 out_height, int32 out_width, BaseFloat weight_decay,
+                BaseFloat momentum);
   void PropagateAct(const ChunkInfo &in_info, const CuMatrixBase<BaseFloat> &in,
                     CuMatrixBase<BaseFloat> *out, int act) const;
 
@@ -232,6 +241,8 @@ class MaxpoolComponent : public nnet2::Component {
   bool Overlap2D() const { return overlap2D_; }
 
  protected:
+  FieldList StreamFields();
+  void Check() const;
   int32 input_dim_;
   int32 output_dim_;
   int32 in_height_;
@@ -285,6 +296,8 @@ class FullyConnectedComponent : public nnet2::AffineComponent {
 
  protected:
   KALDI_DISALLOW_COPY_AND_ASSIGN(FullyConnectedComponent);
+  FieldList StreamFields();
+  void SetHyper(BaseFloat learning_rate, BaseFloat weight_decay, BaseFloat momentum);
   BaseFloat weight_decay_;
   BaseFloat momentum_;
   CuMatrix<BaseFloat> prev_grad_;   // for momentum

@@ -1016,6 +1016,23 @@ void AffineComponent::SetGradientStorage(float *base) {
   grad_external_ = true;
 }
 
+void AffineComponent::SetParameterStorage(float *base) {
+  const int32 rows = linear_params_.NumRows(), cols = linear_params_.NumCols(), dim = bias_params_.Dim();
+  const int32 stride = CuDevice::PitchInElements(cols, sizeof(BaseFloat));
+  CuMatrix<BaseFloat> w(linear_params_);
+  CuVector<BaseFloat> b(bias_params_);
+  if (base != NULL) {
+    linear_params_.Borrow(base, rows, cols, stride);
+    bias_params_.Borrow(base + (size_t)stride * rows, dim);
+    linear_params_.CopyFromMat(w);
+    bias_params_.CopyFromVec(b);
+  } else {
+    linear_params_.Swap(&w);                 // w owns its copy: linear_params_ is an ordinary matrix again
+    bias_params_.Borrow(NULL, 0);
+    bias_params_ = b;
+  }
+}
+
 std::vector<UpdatableComponent::GradBuffer> AffineComponent::GradientBuffers() {
   EnsureGradBuffers();
   std::vector<GradBuffer> v;

@@ -184,6 +184,11 @@ class UpdatableComponent : public Component {
     float momentum, a_decay, a_grad;
   };
   virtual bool GetStepTarget(int32 /*num_rows*/, StepTarget * /*t*/) { return false; }
+  /// Move linear_params_ and bias_params_ into caller-provided device memory laid out like the
+  /// gradient bucket (GradientFloats(): W rows x pitch, then the bias), keeping their values; NULL moves
+  /// them back into memory of their own.  The data-parallel trainer keeps all parameters in one
+  /// NVLink-visible arena so that the owner of a slice can write the updated weights to every replica.
+  virtual void SetParameterStorage(float * /*base*/) {}
 
  protected:
   BaseFloat learning_rate_;
@@ -430,6 +435,7 @@ class AffineComponent : public UpdatableComponent {
   virtual std::vector<GradBuffer> GradientBuffers();
   virtual size_t GradientFloats() const;
   virtual void SetGradientStorage(float *base);
+  virtual void SetParameterStorage(float *base);
   virtual uint64 StepSignature() const {
     uint64 h = HashValue(learning_rate_, 11);
     h = HashValue(linear_params_.Data(), h); h = HashValue(bias_params_.Data(), h);

@@ -26,6 +26,7 @@
 // stays as it was: it runs whenever the model, the math mode (FP32) or an alignment is outside
 // this plan, and it is what the parity tests compare the fused step with.
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -43,6 +44,14 @@ using cnsl::nnet0::FullyConnectedComponent;
 using cnsl::nnet0::MaxpoolComponent;
 
 static inline cudaStream_t Str() { return CuDevice::Instantiate().Stream(); }
+
+// Label + algorithmic work of the next launch, for the benchmark's per-launch roofline table
+// (kcnn_profile_*; a no-op unless a recording is running).  FLOPs / bytes as SURVEY 8d counts them.
+static void Tag(int32 comp, const char *what, double flops, double bytes) {
+  char buf[96];
+  snprintf(buf, sizeof(buf), "comp%d %s", comp, what);
+  kcnn_profile_label(buf, flops, bytes);
+}
 
 struct NnetMinibatchUpdater::FusedOp {
   enum Kind { kConvFull, kConvTime, kPool, kAffine, kSoftmax };
@@ -70,6 +79,7 @@ struct NnetMinibatchUpdater::FusedState {
   cudaEvent_t join_ev;
   void *colsum_scratch[2];                      // [0] statistics launch, [1] bias launch
   size_t colsum_bytes[2];
+  std::vector<KcnnColsumJob> pending_stats;     // statistics of a backward pass issued in several ranges
   bool objf_done;                               // the forward pass already ran softmax + objective
   bool fork_fc;
   FusedState() : valid(false), key(0), side(NULL), join_ev(NULL), objf_done(false), fork_fc(false) {
@@ -303,6 +313,8 @@ void NnetMinibatchUpdater::FusedForward(int32 first, int32 last, const int32 *la
     switch (op.kind) {
       case FusedOp::kConvFull: {
         ConvolutionComponent &cv = static_cast<ConvolutionComponent &>(comp);
+        Tag(op.comp, "conv fprop (+bias+ReLU)", 2.0 * num_rows_ * op.OW * op.G * cv.KernelDim(),
+            4.0 * ((double)num_rows_ * (cv.InputDim() + op.OW * op.G) + (double)cv.KernelDim() * op.G));
         ok = cudaF_conv_full_fprop_cl(st, in.Data(), in.Dim(), cv.In_height(), cv.In_width(), cv.In_channels(),
                                       cv.Kernel_width(), cv.Group(), cv.LinearParams().Data(), cv.LinearParams().Dim(),
                                       cv.BiasParams().Data(), forward_[op.out].Data(), op.relu >= 0);
@@ -311,6 +323,8 @@ void NnetMinibatchUpdater::FusedForward(int32 first, int32 last, const int32 *la
       case FusedOp::kConvTime: {
         ConvolutionComponent &cv = static_cast<ConvolutionComponent &>(comp);
         CuMatrix<BaseFloat> &out = forward_[op.out];
+        Tag(op.comp, "conv fprop (+bias+ReLU)", 2.0 * num_rows_ * op.OW * op.G * cv.KernelDim(),
+            4.0 * ((double)num_rows_ * (op.W * op.C + op.OW * op.G) + (double)cv.KernelDim() * op.G));
         ok = cudaF_conv_time_fprop_cl(st, in.Data(), num_rows_, op.W, op.C, cv.In_pad_width(), cv.Kernel_width(), op.G,
                                       cv.LinearParams().Data(), cv.LinearParams().Dim(), cv.BiasParams().Data(),
                                       out.Data(), F.act_cl[op.out], out.Stride(), op.relu >= 0);
@@ -319,6 +333,7 @@ void NnetMinibatchUpdater::FusedForward(int32 first, int32 last, const int32 *la
       case FusedOp::kPool: {
         MaxpoolComponent &mp = static_cast<MaxpoolComponent &>(comp);
         CuMatrix<BaseFloat> &pool = forward_[op.comp + 1];
+        Tag(op.comp, "maxpool fwd (+ReLU)", 0.0, 4.0 * num_rows_ * (op.W * op.C + op.OW * op.G));
         cudaF_maxpool_prop_cl(st, in.Data(), num_rows_, op.W, op.C, mp.Pool_width_dim(), mp.Pool_channel_dim(),
                               pool.Data(), op.relu >= 0 ? forward_[op.out].Data() : NULL,
                               F.act_cl[op.out] ? 0 : pool.Stride());
@@ -343,6 +358,8 @@ void NnetMinibatchUpdater::FusedForward(int32 first, int32 last, const int32 *la
           drop = forward_[op.out].Data();
           dd = forward_[op.out].Dim();
         }
+        Tag(op.comp, "affine fprop (+bias+ReLU+dropout)", 2.0 * num_rows_ * fc.InputDim() * fc.OutputDim(),
+            4.0 * ((double)num_rows_ * (fc.InputDim() + fc.OutputDim()) + (double)fc.InputDim() * fc.OutputDim()));
         ok = cudaF_affine_fprop_fused(st, in.Data(), in.Dim(), fc.LinearParams().Data(), fc.LinearParams().Dim(),
                                       fc.BiasParams().Data(), out.Data(), out.Dim(), op.relu >= 0, drop, dd, dp, low,
                                       high, seed);
@@ -351,7 +368,8 @@ void NnetMinibatchUpdater::FusedForward(int32 first, int32 last, const int32 *la
       case FusedOp::kSoftmax: {
         CuMatrix<BaseFloat> &post = forward_[op.out];
         bool fused = false;
-        if (labels_dev != NULL && first == base_) {
+        Tag(op.comp, "softmax + x-ent + softmax bwd", 0.0, 12.0 * num_rows_ * in.NumCols());
+        if (labels_dev != NULL) {
           // the whole step is known: softmax, objective, derivative and softmax backward at once
           derivs_[op.in].Resize(num_rows_, in.NumCols(), kUndefined);
           fused = cudaF_softmax_xent(st, in.Data(), in.Dim(), post.Data(), post.Dim(), labels_dev,
@@ -379,6 +397,7 @@ bool NnetMinibatchUpdater::FusedObjf(const int32 *labels_dev) {
   CuMatrix<BaseFloat> &post = forward_[op.out];
   derivs_[op.in].Resize(num_rows_, post.NumCols(), kUndefined);
   ::MatrixDim none = {0, 0, 0};
+  Tag(op.comp, "x-ent + softmax bwd", 0.0, 8.0 * num_rows_ * post.NumCols());
   if (!cudaF_softmax_xent(Str(), NULL, none, post.Data(), post.Dim(), labels_dev, derivs_[op.in].Data(),
                           derivs_[op.in].Dim(), objf_dev_, NULL, 0))
     KALDI_ERR << "fused step: softmax row too long";
@@ -394,7 +413,9 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
   const int32 o_first = F.op_of_comp[first], o_last = F.op_of_comp[last];
   KALDI_ASSERT(F.ops[o_first].comp == first && F.ops[o_last].last == last &&
                "Backward: the range must not cut through a fused group of components");
-  std::vector<KcnnColsumJob> stat_jobs, bias_jobs;
+  std::vector<KcnnColsumJob> &stat_jobs = F.pending_stats;
+  std::vector<KcnnColsumJob> bias_jobs;
+  if (last == nnet_->NumComponents() - 1) stat_jobs.clear();     // a new backward pass starts at the top
   bool forked = false;
   size_t ev = 0;
   auto fork = [&]() -> cudaStream_t {          // work issued on the returned stream runs beside what follows on st
@@ -450,6 +471,7 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
       MaxpoolComponent &mp = static_cast<MaxpoolComponent &>(comp);
       const CuMatrix<BaseFloat> &pool = forward_[op.comp + 1];
       KALDI_ASSERT(gy == NULL);
+      Tag(op.comp, "maxpool bwd (+ReLU gate)", 0.0, 4.0 * num_rows_ * (2.0 * op.W * op.C + 2.0 * op.OW * op.G));
       cudaF_maxpool_backprop_cl(st, x.Data(), pool.Data(), F.act_cl[op.comp + 1] ? 0 : pool.Stride(), dy.Data(),
                                 num_rows_, op.W, op.C, mp.Pool_width_dim(), mp.Pool_channel_dim(),
                                 derivs_[op.in].Data(), gx != NULL);
@@ -466,9 +488,14 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
         int perm_r = 0;
         if (F.der_cl[op.in]) perm_r = F.ops[op.producer].OW;
         CuMatrix<BaseFloat> &dx = derivs_[op.in];
+        Tag(op.comp, "affine dgrad (+ReLU/dropout gate)", 2.0 * num_rows_ * t.wd.rows * t.wd.cols,
+            4.0 * ((double)num_rows_ * (t.wd.rows + 2.0 * t.wd.cols) + (double)t.wd.rows * t.wd.cols));
         ok = cudaF_affine_dgrad_fused(st, dy.Data(), dy.Dim(), t.w, t.wd, dx.Data(), dx.Dim(), gx, ldx, gy, ldy, perm_r);
       }
       cudaStream_t ws = (F.fork_fc && op.need_dgrad) ? fork() : st;
+      // with the SGD step in the epilogue W and prev_grad are read and written: 16 B per weight
+      Tag(op.comp, apply ? "affine wgrad + SGD" : "affine wgrad", 2.0 * num_rows_ * t.wd.rows * t.wd.cols,
+          (apply ? 16.0 : 4.0) * t.wd.rows * t.wd.cols + 4.0 * num_rows_ * (t.wd.rows + t.wd.cols));
       if (apply)
         ok = ok && cudaF_affine_wgrad_sgd(ws, KCNN_MATH_TF32_TC, x.Data(), x.Dim(), dy.Data(), dy.Dim(), t.w, t.wd, t.prev,
                                           t.pd, NULL, t.momentum, t.a_decay, t.a_grad);
@@ -482,10 +509,14 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
       KALDI_ASSERT(gy == NULL);
       if (op.need_dgrad) {
         KALDI_ASSERT(op.kind == FusedOp::kConvTime);
+        Tag(op.comp, "conv dgrad (+ReLU gate)", 2.0 * num_rows_ * op.OW * op.G * cv.KernelDim(),
+            4.0 * ((double)num_rows_ * (2.0 * op.W * op.C + op.OW * op.G) + (double)cv.KernelDim() * op.G));
         ok = cudaF_conv_time_dgrad_cl(st, dy.Data(), num_rows_, op.W, op.C, cv.In_pad_width(), cv.Kernel_width(), op.G,
                                       t.w, t.wd, derivs_[op.in].Data(), gx);
       }
       cudaStream_t ws = op.need_dgrad ? fork() : st;      // the update writes the kernel dgrad reads: behind it
+      Tag(op.comp, apply ? "conv wgrad + SGD" : "conv wgrad", 2.0 * num_rows_ * op.OW * op.G * cv.KernelDim(),
+          4.0 * ((double)num_rows_ * (x.NumCols() + op.OW * op.G)) + (apply ? 16.0 : 4.0) * cv.KernelDim() * op.G);
       if (op.kind == FusedOp::kConvTime)
         ok = ok && cudaF_conv_time_wgrad_cl(ws, x.Data(), dy.Data(), num_rows_, op.W, op.C, cv.In_pad_width(),
                                             cv.Kernel_width(), op.G, wout, wod, t.prev, t.pd, apply, t.momentum,
@@ -505,6 +536,8 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
   cudaStream_t cst = (F.side != NULL && forked) ? F.side : st;
   std::vector<KcnnColsumJob> *lists[2] = {&stat_jobs, &bias_jobs};
   for (int k = 0; k < 2; k++) {
+    // the statistics of ALL nonlinearities go in one launch, when the pass reaches the bottom
+    if (k == 0 && first != base_) continue;
     if (lists[k]->empty()) continue;
     const size_t need = kcnn_colsum_batch_scratch_bytes(&(*lists[k])[0], static_cast<int>(lists[k]->size()));
     if (need > F.colsum_bytes[k]) {
@@ -514,8 +547,13 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
       F.colsum_bytes[k] = need;
       CU_SAFE_CALL(cudaMemsetAsync(F.colsum_scratch[k], 0, need, cst));
     }
+    double bytes = 0.0;
+    for (size_t j = 0; j < lists[k]->size(); j++) bytes += 4.0 * (*lists[k])[j].rows * (*lists[k])[j].cols;
+    Tag(-1, k == 0 ? "nonlinearity statistics (all layers, batched column sums)"
+                   : "bias gradients + update (batched column sums)", 0.0, bytes);
     cudaF_colsum_batch(cst, &(*lists[k])[0], static_cast<int>(lists[k]->size()), F.colsum_scratch[k]);
   }
+  if (first == base_) stat_jobs.clear();
   if (forked) {
     cudaEventRecord(F.join_ev, F.side);
     cudaStreamWaitEvent(st, F.join_ev, 0);

@@ -107,7 +107,7 @@ struct NnetMinibatchUpdater::GraphState {
 };
 
 NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
-    : graph_(new GraphState), last_replayed_(false), fuse_(true),
+    : graph_(new GraphState), last_replayed_(false), graphs_on_(true), fuse_(true),
       nnet_(nnet), num_rows_(0), fused_(NULL), step_labels_(NULL), base_(0), labels_(NULL), objf_dev_(NULL) {
   FusedInit();
   if (nnet_->NumComponents() > 1 && dynamic_cast<SpliceComponent *>(&nnet_->GetComponent(0)) != NULL) base_ = 1;
@@ -143,7 +143,8 @@ int32 NnetMinibatchUpdater::FramesPerExample() const {
   return ctx.back() - ctx.front() + 1;
 }
 
-void NnetMinibatchUpdater::ForwardRange(const CuMatrixBase<BaseFloat> &feats, int32 first, int32 last) {
+void NnetMinibatchUpdater::ForwardRange(const CuMatrixBase<BaseFloat> &feats, int32 first, int32 last,
+                                        const int32 *labels_dev) {
   const int32 L = nnet_->NumComponents();
   KALDI_ASSERT(L > 0 && feats.NumCols() == nnet_->InputDim());
   KALDI_ASSERT(first >= 0 && last < L);
@@ -193,7 +194,7 @@ void NnetMinibatchUpdater::ForwardRange(const CuMatrixBase<BaseFloat> &feats, in
   if (first < base_) first = base_;
   if (last < first) return;
   if (PlanFused()) {
-    FusedForward(first, last, step_labels_);
+    FusedForward(first, last, labels_dev != NULL ? labels_dev : step_labels_);
     return;
   }
   for (int32 c = first; c <= last; c++) {
@@ -296,7 +297,7 @@ void NnetMinibatchUpdater::EagerStep(const CuMatrixBase<BaseFloat> &feats, const
 void NnetMinibatchUpdater::TrainStep(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) {
   last_replayed_ = false;
   cudaStream_t st = Str();
-  const bool capturable = GraphsEnabled() && st != 0 && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  const bool capturable = graphs_on_ && GraphsEnabled() && st != 0 && st != cudaStreamLegacy && st != cudaStreamPerThread;
   if (!capturable) { EagerStep(feats, labels_dev); return; }
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cs);

@@ -61,7 +61,9 @@ class NnetMinibatchUpdater {
   /// otherwise the activations below `first` must come from an earlier call on the same batch.
   /// (Lets the data-parallel step run the layers whose weights are up to date while the
   /// gradients of the others are still being all-reduced.)
-  void ForwardRange(const CuMatrixBase<BaseFloat> &feats, int32 first, int32 last);
+  /// labels_dev (optional, device int32 [num_rows]): when the range ends with the softmax, the fused plan
+  /// then computes objective and derivative in the same kernel (ComputeObjfAndDeriv becomes a no-op).
+  void ForwardRange(const CuMatrixBase<BaseFloat> &feats, int32 first, int32 last, const int32 *labels_dev = NULL);
   /// labels: device int32 [num_rows].  Writes the cross-entropy derivative at the output
   /// and accumulates sum_i log p[i, label_i] into the device objective.
   void ComputeObjfAndDeriv(const int32 *labels_dev);
@@ -90,6 +92,9 @@ class NnetMinibatchUpdater {
   bool Fusion() const { return fuse_; }
   /// True when the last TrainStep was a graph replay.
   bool LastStepReplayed() const { return last_replayed_; }
+  /// TrainStep records / replays CUDA graphs (default, KCNN_NNET_GRAPH=0 turns it off for the process);
+  /// off: every TrainStep runs its launches eagerly (profiling, debugging).
+  void SetGraphs(bool on) { if (!on) DropGraph(); graphs_on_ = on; }
   /// ApplyGradient(total_rows) on every updatable component (deferred-update mode).
   void ApplyGradients(int32 total_rows);
   /// Total floats of gradient storage; SetGradientArena places every component's
@@ -120,6 +125,7 @@ class NnetMinibatchUpdater {
   struct GraphState;                 // recorded steps + the host-side effects of one step
   GraphState *graph_;
   bool last_replayed_;
+  bool graphs_on_;
   bool fuse_;
   Nnet *nnet_;
   int32 num_rows_;

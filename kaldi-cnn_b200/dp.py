@@ -46,6 +46,133 @@ def late_components(net, updatable, min_floats=1 << 20):
     return late
 
 
+class NativeDataParallel:
+    """The data-parallel trainer of the library itself (csrc/nnet2/nnet-dp.cc, C ABI kcnn_nnet_dp_*):
+    schedule, streams, graph capture and the per-layer fused reduce + SGD + broadcast kernel are C++ /
+    CUDA; this class only performs the rendezvous a host must do -- allocate the symmetric arena, send
+    its handle to the peers, map theirs -- and forwards calls.
+
+    Arena exchange: CUDA IPC handles (kcnn_ipc_alloc / kcnn_ipc_open) carried by
+    dist.all_gather_object, i.e. no framework-private API.  multicast=True asks for the in-switch (NVLS)
+    form of the kernel, which needs a multicast mapping of the arena; the only provider in this image is
+    torch's symmetric memory, so that variant allocates through it (and raises when it is unavailable)."""
+
+    def __init__(self, net, dist, multicast=False):
+        import ctypes
+        import torch
+        from . import capi
+        self.lib = L = capi.lib()
+        self.net, self.dist = net, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        floats = int(L.kcnn_nnet_dp_arena_floats(net.h))
+        if floats == 0:
+            raise RuntimeError(L.kcnn_last_error().decode())
+        self._ipc_local, self._ipc_peers, self._symm = None, [], None
+        mc = 0
+        if multicast:
+            import torch.distributed._symmetric_memory as symm
+            group = dist.group.WORLD
+            try:
+                symm.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+            self._symm = symm.empty(floats, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+            hdl = symm.rendezvous(self._symm, group)
+            self._symm.zero_()
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if mc == 0:
+                raise RuntimeError("symmetric memory has no multicast mapping on this platform")
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            local = self._symm.data_ptr()
+            self._hdl = hdl
+        else:
+            ptr = ctypes.c_void_p()
+            handle = (ctypes.c_ubyte * 64)()
+            if L.kcnn_ipc_alloc(ctypes.c_size_t(floats * 4), ctypes.byref(ptr), handle) != 0:
+                raise RuntimeError("kcnn_ipc_alloc failed")
+            self._ipc_local = ptr.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle))
+            ptrs = []
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(ptr.value)
+                    continue
+                q = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(hb)
+                if L.kcnn_ipc_open(buf, ctypes.byref(q)) != 0:
+                    raise RuntimeError("kcnn_ipc_open failed for rank %d (no peer access?)" % r)
+                self._ipc_peers.append(q.value)
+                ptrs.append(q.value)
+            local = ptr.value
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.multicast_base = mc
+        self.bases = (ctypes.c_ulonglong * self.world)(*ptrs)
+        self.h = ctypes.c_void_p(L.kcnn_nnet_dp_create(net.h, self.rank, self.world, ctypes.c_void_p(local), self.bases,
+                                                       ctypes.c_ulonglong(mc)))
+        if not self.h:
+            raise RuntimeError(L.kcnn_last_error().decode())
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.kcnn_last_error().decode())
+
+    def prime(self, feats, labels):
+        import ctypes
+        from . import capi
+        d = capi.mdim(feats)
+        self._check(self.lib.kcnn_nnet_dp_prime(self.h, ctypes.c_void_p(feats.data_ptr()), d.rows, d.stride,
+                                                ctypes.c_void_p(labels.data_ptr())))
+
+    def rotate(self, feats_next, labels_next, rows_global):
+        import ctypes
+        from . import capi
+        d = capi.mdim(feats_next)
+        self._check(self.lib.kcnn_nnet_dp_rotate(self.h, ctypes.c_void_p(feats_next.data_ptr()), d.rows, d.stride,
+                                                 ctypes.c_void_p(labels_next.data_ptr()), int(rows_global)))
+
+    def finish(self, rows_global):
+        self._check(self.lib.kcnn_nnet_dp_finish(self.h, int(rows_global)))
+
+    def train_minibatch_host_async(self, feats_np, labels_np, rows_global):
+        import ctypes
+        self._check(self.lib.kcnn_nnet_dp_train_minibatch_host_async(
+            self.h, feats_np.ctypes.data_as(ctypes.c_void_p), labels_np.ctypes.data_as(ctypes.c_void_p),
+            labels_np.shape[0], int(rows_global)))
+
+    def failed(self, synchronise=True):
+        return bool(self.lib.kcnn_nnet_dp_failed(self.h, int(synchronise)))
+
+    def gather_momentum(self):
+        self._check(self.lib.kcnn_nnet_dp_gather_momentum(self.h))
+
+    @property
+    def last_rotate_replayed(self):
+        return bool(self.lib.kcnn_nnet_dp_last_rotate_replayed(self.h))
+
+    def close(self):
+        """Parameters move back into the components; the arena is released."""
+        import torch
+        torch.cuda.synchronize()
+        self.dist.barrier()
+        if self.h:
+            self.lib.kcnn_nnet_dp_delete(self.h)
+            self.h = None
+        torch.cuda.synchronize()
+        self.dist.barrier()
+        import ctypes
+        for q in self._ipc_peers:
+            self.lib.kcnn_ipc_close(ctypes.c_void_p(q))
+        self._ipc_peers = []
+        self.dist.barrier()
+        if self._ipc_local:
+            self.lib.kcnn_ipc_free(ctypes.c_void_p(self._ipc_local))
+            self._ipc_local = None
+
+
 class _Done:
     """What dist.all_reduce(async_op=True) returns, for the peer-memory path: wait() makes the
     CURRENT stream wait for the reduction (an event wait, capturable into a CUDA graph)."""

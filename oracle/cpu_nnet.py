@@ -30,11 +30,28 @@ def parse_config(text, skip_splice=True):
     return layers
 
 
+def tf32_operand(a, mode):
+    """What a TF32 tensor-core instruction sees of an fp32 GEMM operand: sign, 8 exponent bits, 10 mantissa
+    bits.  mode "trunc": the low 13 bits are ignored; "rna": round to nearest, ties away from zero
+    (cvt.rna.tf32.f32).  Test-only model of the DEVICE arithmetic; the reference itself is fp32."""
+    if mode is None:
+        return a
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    if mode == "rna":
+        u = u + np.uint32(0x1000)
+    return (u & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 class CpuNnet:
-    def __init__(self, config_text, seed=42, dtype=np.float32, backend=None):
+    def __init__(self, config_text, seed=42, dtype=np.float32, backend=None, gemm_operands=None):
         """backend: None = C restatement (oracle.py); or an object with the same functions
-        (oracle/ref.py wraps the compiled reference)."""
+        (oracle/ref.py wraps the compiled reference).
+        gemm_operands: None = the reference's fp32 arithmetic; "trunc" / "rna" = the same op chain with the
+        two operands of every matrix product reduced to TF32 first (tf32_operand) -- the arithmetic of the
+        device's TF32 tensor-core path, so a test can hold that path to a rounding-error bound instead of
+        a bound that has to absorb flipped ReLU gates and max-pool winners."""
         self.o = backend or ora
+        self.ops = gemm_operands
         self.dtype = dtype
         rng = np.random.default_rng(seed)
         self.layers = []
@@ -81,16 +98,17 @@ class CpuNnet:
 
     def forward(self, x, dropout_masks=None):
         o, acts = self.o, [np.ascontiguousarray(x, dtype=self.dtype)]
+        t = lambda m: tf32_operand(m, self.ops)
         self.masks = []
         for i, L in enumerate(self.layers):
             a, k = acts[-1], L["kind"]
             if k == "ConvolutionComponent":
-                y = o.conv_propagate(a, L["lin"], L["bias"], L["H"], L["W"], L["C"], L["ph"], L["pw"], L["KH"],
+                y = o.conv_propagate(t(a), t(L["lin"]), L["bias"], L["H"], L["W"], L["C"], L["ph"], L["pw"], L["KH"],
                                      L["KW"], L["G"], dtype=self.dtype)
             elif k == "MaxpoolComponent":
                 y = o.maxpool_prop(a, L["H"], L["W"], L["ph"], L["pw"], L["pc"], dtype=self.dtype)
             elif k == "FullyConnectedComponent":
-                y = o.fc_propagate(a, L["W"], L["bias"], dtype=self.dtype)
+                y = o.fc_propagate(t(a), t(L["W"]), L["bias"], dtype=self.dtype)
             elif k == "RectifiedLinearComponent":
                 y = np.maximum(a, 0)
             elif k == "DropoutComponent":
@@ -110,6 +128,7 @@ class CpuNnet:
 
     def backward(self, labels, update=True):
         o = self.o
+        t = lambda m: tf32_operand(m, self.ops)
         post = self.acts[-1]
         n = post.shape[0]
         objf = float(np.log(post[np.arange(n), labels].astype(np.float64)).sum())
@@ -119,19 +138,27 @@ class CpuNnet:
         for i in range(len(self.layers) - 1, -1, -1):
             L, a, y, k = self.layers[i], self.acts[i], self.acts[i + 1], self.layers[i]["kind"]
             if k == "ConvolutionComponent":
-                din = o.conv_backprop(d, L["lin"], L["H"], L["W"], L["C"], L["ph"], L["pw"], L["KH"], L["KW"],
+                din = o.conv_backprop(t(d), t(L["lin"]), L["H"], L["W"], L["C"], L["ph"], L["pw"], L["KH"], L["KW"],
                                       L["G"], dtype=self.dtype)
                 if update:
-                    L["lin"], L["bias"], L["prev"], _, _ = o.conv_update(
-                        a, d, L["lin"], L["bias"], L["prev"], L["H"], L["W"], L["C"], L["ph"], L["pw"], L["KH"],
-                        L["KW"], L["G"], L["lr"], L["wd"], L["mom"], dtype=self.dtype)
+                    args = (L["H"], L["W"], L["C"], L["ph"], L["pw"], L["KH"], L["KW"], L["G"], L["lr"], L["wd"],
+                            L["mom"])
+                    lin, bias, prev, _, _ = o.conv_update(t(a), t(d), L["lin"], L["bias"], L["prev"], *args,
+                                                          dtype=self.dtype)
+                    if self.ops is not None:     # the bias gradient is a column sum, not a matrix product
+                        bias = o.conv_update(a, d, L["lin"], L["bias"], L["prev"], *args, dtype=self.dtype)[1]
+                    L["lin"], L["bias"], L["prev"] = lin, bias, prev
             elif k == "MaxpoolComponent":
                 din = o.maxpool_backprop(a, y, d, L["H"], L["W"], L["ph"], L["pw"], L["pc"], dtype=self.dtype)
             elif k == "FullyConnectedComponent":
-                din = o.fc_backprop(d, L["W"], dtype=self.dtype)
+                din = o.fc_backprop(t(d), t(L["W"]), dtype=self.dtype)
                 if update:
-                    L["W"], L["bias"], L["prev"] = o.fc_update(a, d, L["W"], L["bias"], L["prev"], L["lr"],
-                                                               L["wd"], L["mom"], dtype=self.dtype)
+                    Wn, bias, prev = o.fc_update(t(a), t(d), L["W"], L["bias"], L["prev"], L["lr"], L["wd"],
+                                                 L["mom"], dtype=self.dtype)
+                    if self.ops is not None:
+                        bias = o.fc_update(a, d, L["W"], L["bias"], L["prev"], L["lr"], L["wd"], L["mom"],
+                                           dtype=self.dtype)[1]
+                    L["W"], L["bias"], L["prev"] = Wn, bias, prev
             elif k == "RectifiedLinearComponent":
                 din = np.where(y > 0, d, 0).astype(self.dtype)
             elif k == "DropoutComponent":

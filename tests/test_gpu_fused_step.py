@@ -10,16 +10,23 @@ split-K, batched column sums -- against
   * the component-by-component path of the same library (every Component called separately in
     the reference layout): activations, parameters, momentum, statistics.
 
-Tolerances (max-norm relative): TF32 tensor-core path 1e-3 on outputs and
-updated parameters.  The weight STEP (new - old) of each layer is additionally held to a fraction of
-its own Frobenius norm, and the momentum to the same fraction of its max-norm: 2e-2 at the benchmarked
-size, 6e-2 for the small test models.  That bound is not a rounding-error bound: under TF32 rounding of
-the forward activations a few ReLU gates and max-pool winners of near-tied units flip, and every flip
-is an O(1) change of that unit's gradient; the effect averages out with the number of rows x positions
-a gradient sums over (measured in max-norm: 4-8e-2 at N = 96, <= 2e-2 at N = 512).  The
-component-by-component path of the same library shows the same numbers (the two paths agree to 2e-5,
-last test group).  Max-pool routing inside the step is exact (its inputs are bit-identical in both
-paths up to the layout)."""
+Two oracles, two bounds:
+
+  * gemm_operands="trunc": CpuNnet with the two operands of every matrix product cut to TF32 (what
+    tcgen05.mma kind::tf32 reads of an fp32 operand; everything else -- accumulation, bias, gates, pooling,
+    SGD -- fp32 as in the reference).  Against this model the device step is held to a ROUNDING bound:
+    objective / posteriors 1e-4 max-norm relative, every weight / bias / momentum step 2e-3 of its own
+    Frobenius norm (what is left is fp32 summation order and the rare activation that lands on the other
+    side of a TF32 cut because of it).
+  * the reference's own fp32 arithmetic: 1e-3 max-norm relative on outputs and updated parameters
+    (BASELINE.md section 5).  The weight STEP (new - old) of each layer is then only held to 2e-2 of its
+    Frobenius norm at the benchmarked size (8e-2 for the small models): under TF32 rounding of the forward
+    activations a few ReLU gates and max-pool winners of near-tied units flip, every flip is an O(1)
+    change of that unit's gradient, and the effect averages out with the rows x positions a gradient sums
+    over.  The first bound shows those flips are the whole difference.
+
+Max-pool routing inside the step is exact (its inputs are bit-identical in both device paths up to the
+layout)."""
 import os
 import re
 
@@ -117,11 +124,14 @@ def dropout_masks(net, cpu):
     return masks
 
 
-def step_vs_oracle(cfg, N, seed, steps=1, tol_out=1e-3, tol_step=2e-2):
+TF32_MODEL = os.environ.get("KCNN_TEST_TF32_MODEL", "trunc")
+
+
+def step_vs_oracle(cfg, N, seed, steps=1, tol_out=1e-3, tol_step=2e-2, gemm_operands=None):
     kc.set_math_mode(1)
     kc.set_rand_seed(seed)
     net = kc.Nnet.from_config(cfg)
-    cpu = CpuNnet(cfg, seed=seed)
+    cpu = CpuNnet(cfg, seed=seed, gemm_operands=gemm_operands)
     copy_params_to_oracle(net, cpu)
     rng = np.random.default_rng(seed + 1)
     kc.use_current_stream()
@@ -154,8 +164,8 @@ def step_vs_oracle(cfg, N, seed, steps=1, tol_out=1e-3, tol_step=2e-2):
                 d_ref = ref.astype(np.float64) - old
                 e_step = float(np.linalg.norm(new.astype(np.float64) - ref) / max(np.linalg.norm(d_ref), 1e-30))
                 report["comp%d %s" % (i, name)] = (e_val, e_step)
-                # the momentum matrix IS a (smoothed) gradient: it carries the gradient's accumulated error
-                if e_val > (tol_step if name == "momentum" else tol_out) or e_step > tol_step:
+                # the momentum matrix IS a (smoothed) gradient: it is held to the step bound only
+                if (name != "momentum" and e_val > tol_out) or e_step > tol_step:
                     bad.append((s, i, name, e_val, e_step))
             k += 1
         assert not bad, (bad, report)
@@ -163,22 +173,30 @@ def step_vs_oracle(cfg, N, seed, steps=1, tol_out=1e-3, tol_step=2e-2):
     return report
 
 
-def test_fused_step_matches_the_oracle_step():
-    rep = step_vs_oracle(CFG, 96, seed=3, steps=3, tol_step=6e-2)
+STRICT = dict(tol_out=1e-4, tol_step=2e-3, gemm_operands=TF32_MODEL)
+
+
+@pytest.mark.parametrize("bound", ["tf32-operand-model", "fp32-reference"])
+def test_fused_step_matches_the_oracle_step(bound):
+    kw = STRICT if bound == "tf32-operand-model" else dict(tol_step=8e-2)
+    rep = step_vs_oracle(CFG, 96, seed=3, steps=3, **kw)
     print(rep)
 
 
-def test_fused_step_conv_into_affine_and_padding():
-    rep = step_vs_oracle(CFG_CONV_TO_FC, 80, seed=5, steps=2, tol_step=6e-2)
+@pytest.mark.parametrize("bound", ["tf32-operand-model", "fp32-reference"])
+def test_fused_step_conv_into_affine_and_padding(bound):
+    kw = STRICT if bound == "tf32-operand-model" else dict(tol_step=8e-2)
+    rep = step_vs_oracle(CFG_CONV_TO_FC, 80, seed=5, steps=2, **kw)
     print(rep)
 
 
-def test_benchmarked_model_full_size_step_vs_oracle():
+@pytest.mark.parametrize("bound", ["tf32-operand-model", "fp32-reference"])
+def test_benchmarked_model_full_size_step_vs_oracle(bound):
     """The bench.py workload itself (C2 + intermap pooling, N = 512): one whole training step,
     objective and every updated parameter against oracle.cpu_nnet.CpuNnet."""
     cfg = open(os.path.join(ROOT, "kaldi-cnn_b200", "configs", "nnet_c2_intermap.config")).read()
     cfg = "\n".join(l for l in cfg.splitlines() if not l.startswith("SpliceComponent"))
-    rep = step_vs_oracle(cfg, 512, seed=42, steps=1)
+    rep = step_vs_oracle(cfg, 512, seed=42, steps=1, **(STRICT if bound == "tf32-operand-model" else {}))
     print(rep)
 
 

