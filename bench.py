@@ -587,11 +587,14 @@ def run_ours(args):
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 net.train_minibatch_host_async(hx_np, hl_np)
+            t_calls = time.perf_counter() - t0
             net.objf_and_reset()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             e2e = {"value": N * args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 8, "ms_per_step": dt / args.steps * 1e3,
+                   "host_ms_in_calls_per_step": t_calls / args.steps * 1e3,
+                   "graph_replayed": bool(net.last_step_replayed),
                    "api": "kcnn_nnet_train_minibatch_host_async (include/kcnn_capi.h): staged through pinned "
                           "buffers, copy stream, library-recorded CUDA graph per slot",
                    "sync_api": {"value": N * args.steps / dt_sync, "ms_per_step": dt_sync / args.steps * 1e3,

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <sstream>
 #include <string>
 
@@ -117,6 +118,48 @@ int WriteToBuffer(const std::string &s, char **data, size_t *len) {
 struct Borrowed {
   CuMatrix<BaseFloat> m;
   Borrowed(float *p, int r, int c, int s) { m.Borrow(p, r, c, s); }
+};
+
+// Host -> device copy of a dense [rows x cols] host matrix into a pitched device matrix: one linear copy
+// when the device pitch equals the row length (a 2-D copy of ten thousand 160-byte rows is a descriptor
+// per row), else the pitched form.
+void CopyRowsToDevice(CuMatrix<BaseFloat> &dst, const float *src, int rows, int cols, cudaStream_t stream) {
+  if (dst.Stride() == cols) {
+    CU_SAFE_CALL(cudaMemcpyAsync(dst.Data(), src, sizeof(float) * (size_t)rows * cols, cudaMemcpyHostToDevice, stream));
+  } else {
+    CU_SAFE_CALL(cudaMemcpy2DAsync(dst.Data(), sizeof(float) * dst.Stride(), src, sizeof(float) * cols,
+                                   sizeof(float) * cols, rows, cudaMemcpyHostToDevice, stream));
+  }
+}
+
+// KCNN_HOST_TIMING=1: where the host thread spends its time inside the pipelined entry points, printed
+// every 256 calls (diagnostics; off by default, two clock reads per phase when on).
+struct HostPhaseTimer {
+  enum { kPhases = 8 };
+  static bool On() { static const bool on = getenv("KCNN_HOST_TIMING") != NULL; return on; }
+  struct Acc { double us[kPhases]; const char *name[kPhases]; long calls; };
+  static Acc &Get() { static Acc a = {}; return a; }
+  const char *what;
+  std::chrono::steady_clock::time_point last;
+  explicit HostPhaseTimer(const char *w) : what(w) { if (On()) last = std::chrono::steady_clock::now(); }
+  void Mark(int phase, const char *name) {
+    if (!On()) return;
+    std::chrono::steady_clock::time_point now = std::chrono::steady_clock::now();
+    Acc &a = Get();
+    a.us[phase] += std::chrono::duration<double, std::micro>(now - last).count();
+    a.name[phase] = name;
+    last = now;
+  }
+  ~HostPhaseTimer() {
+    if (!On()) return;
+    Acc &a = Get();
+    if (++a.calls % 256 == 0) {
+      fprintf(stderr, "%s, host us per call:", what);
+      for (int i = 0; i < kPhases; i++)
+        if (a.name[i]) { fprintf(stderr, "  %s %.1f", a.name[i], a.us[i] / 256.0); a.us[i] = 0.0; }
+      fprintf(stderr, "\n");
+    }
+  }
 };
 
 void CheckShape(const CuMatrix<BaseFloat> &m, float *p, const char *what) {
@@ -603,8 +646,7 @@ int kcnn_nnet_train_minibatch_host(kcnn_nnet *n, const float *feats_host, const 
     h->host_labels_dev = static_cast<int32 *>(CuDevice::Instantiate().Malloc(sizeof(int32) * rows));
     h->host_labels_rows = rows;
   }
-  CU_SAFE_CALL(cudaMemcpy2DAsync(h->host_feats.Data(), sizeof(float) * h->host_feats.Stride(), feats_host,
-                                 sizeof(float) * dim, sizeof(float) * dim, frames, cudaMemcpyHostToDevice, st));
+  CopyRowsToDevice(h->host_feats, feats_host, frames, dim, st);
   CU_SAFE_CALL(cudaMemcpyAsync(h->host_labels_dev, labels_host, sizeof(int32) * rows,
                                cudaMemcpyHostToDevice, st));
   h->U().TrainStep(h->host_feats, h->host_labels_dev);
@@ -624,24 +666,28 @@ int kcnn_nnet_train_minibatch_host_async(kcnn_nnet *n, const float *feats_host, 
   const int frames = rows * h->U().FramesPerExample();
   p.Ensure(frames, dim, rows);
   const int s = (int)(p.step & 1ull);
+  HostPhaseTimer tm("kcnn_nnet_train_minibatch_host_async");
   // the pinned slot is free once ITS previous copy (two calls ago) has run; then the caller's
   // buffers are staged and belong to the caller again as soon as this call returns
   CU_SAFE_CALL(cudaEventSynchronize(p.copied[s]));
+  tm.Mark(0, "wait for the staging slot");
   memcpy(p.pin_feats[s], feats_host, sizeof(float) * (size_t)frames * dim);
   memcpy(p.pin_labels[s], labels_host, sizeof(int32) * (size_t)rows);
+  tm.Mark(1, "stage into pinned memory");
   // the device slot is free once the step that read it (two calls ago) has finished
   CU_SAFE_CALL(cudaStreamWaitEvent(p.copy_stream, p.done[s], 0));
-  CU_SAFE_CALL(cudaMemcpy2DAsync(p.dev_feats[s].Data(), sizeof(float) * p.dev_feats[s].Stride(), p.pin_feats[s],
-                                 sizeof(float) * dim, sizeof(float) * dim, frames, cudaMemcpyHostToDevice,
-                                 p.copy_stream));
+  CopyRowsToDevice(p.dev_feats[s], p.pin_feats[s], frames, dim, p.copy_stream);
   CU_SAFE_CALL(cudaMemcpyAsync(p.dev_labels[s], p.pin_labels[s], sizeof(int32) * rows, cudaMemcpyHostToDevice,
                                p.copy_stream));
   CU_SAFE_CALL(cudaEventRecord(p.copied[s], p.copy_stream));
   CU_SAFE_CALL(cudaStreamWaitEvent(st, p.copied[s], 0));
+  tm.Mark(2, "enqueue the copies");
   h->U().TrainStep(p.dev_feats[s], p.dev_labels[s]);
+  tm.Mark(3, "TrainStep (graph launch)");
   // the running objective comes back to the host after every step, without a synchronisation
   CU_SAFE_CALL(cudaMemcpyAsync(p.pin_objf + s, h->U().ObjfDevice(), sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_SAFE_CALL(cudaEventRecord(p.done[s], st));
+  tm.Mark(4, "objective read-back + event");
   p.step++;
   return 0;
   KCNN_CATCH(-1)
@@ -813,9 +859,7 @@ int kcnn_nnet_dp_train_minibatch_host_async(kcnn_nnet_dp *dp, const float *feats
   memcpy(h->pin_labels[s], labels_host, sizeof(int32) * (size_t)rows_local);
   // the device slot was last read by the backward pass of the rotation two calls ago
   if (h->call >= 2) CU_SAFE_CALL(cudaStreamWaitEvent(h->copy_stream, h->done[(h->call - 2) % DpHandle::kSlots], 0));
-  CU_SAFE_CALL(cudaMemcpy2DAsync(h->dev_feats[s].Data(), sizeof(float) * h->dev_feats[s].Stride(), h->pin_feats[s],
-                                 sizeof(float) * dim, sizeof(float) * dim, frames, cudaMemcpyHostToDevice,
-                                 h->copy_stream));
+  CopyRowsToDevice(h->dev_feats[s], h->pin_feats[s], frames, dim, h->copy_stream);
   CU_SAFE_CALL(cudaMemcpyAsync(h->dev_labels[s], h->pin_labels[s], sizeof(int32) * rows_local, cudaMemcpyHostToDevice,
                                h->copy_stream));
   CU_SAFE_CALL(cudaEventRecord(h->copied[s], h->copy_stream));

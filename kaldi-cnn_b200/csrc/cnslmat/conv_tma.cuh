@@ -580,7 +580,7 @@ inline bool conv_fprop(cudaStream_t st, const ConvShape &q, const float *in, int
                        int ld_k, const float *bias, float *out, int ldo, float *staging = nullptr,
                        bool relu = false) {
   if (!conv_tma_shape_ok(q)) return false;
-  float *xcl = staging ? staging : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
+  float *xcl = staging ? staging : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float), st);
   if (!xcl || !host_aligned16(xcl)) return false;
   CUtensorMap probe;                              // nothing may fail after the pack has been launched
   if (!encode_kernel_map(&probe, kernel, ld_k, q.C, q.KW, q.G, 32, true)) return false;
@@ -616,13 +616,13 @@ inline bool conv_backward(cudaStream_t st, const ConvShape &q, ConvBackward &b) 
   const bool do_wgrad = b.sgd != nullptr || b.kernel_grad != nullptr;
   ConvWgradOut wo = {b.sgd ? b.kernel : b.kernel_grad, b.sgd ? b.ld_k : b.ld_kg, b.prev, b.ld_p, b.sgd};
   if (do_wgrad && !conv_wgrad_out_ok(wo)) return false;
-  float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float));
+  float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float), st);
   const bool have_x = b.staged_x != nullptr && host_aligned16(b.staged_x);
   float *xcl = !do_wgrad ? nullptr
                : have_x ? const_cast<float *>(b.staged_x)
-                        : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float));
+                        : scratch(SCRATCH_XCL, (size_t)q.N * q.W * q.C * sizeof(float), st);
   const int prow = pack_partial_rows(q.N, q.OW);
-  float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float)) : nullptr;
+  float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float), st) : nullptr;
   if (!dycl || !host_aligned16(dycl) || (do_wgrad && (!xcl || !host_aligned16(xcl))) || (b.want_bias && !bpart))
     return false;
   CUtensorMap probe;
@@ -729,9 +729,9 @@ inline bool conv_full_backward(cudaStream_t st, const ConvFullShape &q, ConvBack
   const bool do_wgrad = b.sgd != nullptr || b.kernel_grad != nullptr;
   ConvWgradOut wo = {b.sgd ? b.kernel : b.kernel_grad, b.sgd ? b.ld_k : b.ld_kg, b.prev, b.ld_p, b.sgd};
   if (do_wgrad && (!conv_wgrad_out_ok(wo) || (ks & 31) != 0)) return false;
-  float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float));
+  float *dycl = scratch(SCRATCH_DYCL, (size_t)q.N * q.OW * q.G * sizeof(float), st);
   const int prow = pack_partial_rows(q.N, q.OW);
-  float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float)) : nullptr;
+  float *bpart = b.want_bias ? scratch(SCRATCH_BIAS, (size_t)prow * q.G * sizeof(float), st) : nullptr;
   if (!dycl || !host_aligned16(dycl) || (b.want_bias && !bpart)) return false;
   CUtensorMap probe;
   if (do_wgrad && !encode_window_map(&probe, b.in_value, b.ld_iv, q, 1, 32, true)) return false;

@@ -903,7 +903,7 @@ bool cluster_k_enabled();                // KCNN_TMA_CLUSTERK=0: no split-K (sma
 // Only the bare-component path (a Component called outside NnetMinibatchUpdater's fused step)
 // uses it: channels-last staging copies and the bias-gradient partial sums of the pack kernel.
 enum ScratchSlot { SCRATCH_XCL = 0, SCRATCH_DYCL = 1, SCRATCH_BIAS = 2, SCRATCH_SLOTS = 3 };
-float *scratch(int slot, size_t bytes);
+float *scratch(int slot, size_t bytes, cudaStream_t st);
 
 // Tensor map of rank 2 to 4 over FP32 data; dims[0] is the contiguous axis, strides_bytes[i]
 // is the pitch of dims[i + 1].  mn_major picks the 32-byte-atom swizzle.

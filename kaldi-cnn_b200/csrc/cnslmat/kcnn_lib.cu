@@ -1,5 +1,6 @@
 // kaldi-cnn_b200/csrc/cnslmat/kcnn_lib.cu -- library state of libkaldicnn_b200.so.
 
+#include <mutex>
 #include "kcnn_common.cuh"
 
 #include <cxxabi.h>
@@ -61,8 +62,13 @@ bool pdl_enabled() {
 }
 
 namespace {
+// One side stream and one fork / join event pair per DEVICE, created on first use under a mutex.  A
+// ForkJoin region belongs to the stream that opened it; two streams of one device forking at the same time
+// would share the side stream (correct -- it is ordered by the events -- but serialised).
 struct SideState { cudaStream_t stream; cudaEvent_t fork, join; bool tried; };
-SideState g_side = {nullptr, nullptr, nullptr, false};
+constexpr int kMaxDevices = 32;
+SideState g_side[kMaxDevices] = {};
+std::mutex g_side_mu;
 
 SideState *side_state(cudaStream_t main) {
   static int enabled = -1;
@@ -71,7 +77,11 @@ SideState *side_state(cudaStream_t main) {
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
   if (!enabled) return nullptr;
-  if (!g_side.tried) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  SideState &g = g_side[dev];
+  if (!g.tried) {
     // created on first use, never while the caller's stream is being captured (the warm-up
     // steps that precede any capture get here first)
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -79,15 +89,15 @@ SideState *side_state(cudaStream_t main) {
       cudaGetLastError();
       return nullptr;
     }
-    g_side.tried = true;
-    if (cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) != cudaSuccess) {
+    g.tried = true;
+    if (cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g.join, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
-      g_side.stream = nullptr;
+      g.stream = nullptr;
     }
   }
-  return g_side.stream ? &g_side : nullptr;
+  return g.stream ? &g : nullptr;
 }
 }  // namespace
 

@@ -98,11 +98,11 @@ cl_to_ref_kernel(const float *__restrict__ in, long long total, int W, int C, fl
 // -------------------------------------------------------------------------- batched colsum --
 
 constexpr int kColsumMaxJobs = 12;
-constexpr int kColsumRowsPerBlock = 256;
+constexpr int kColsumRowsPerBlock = 64;     // 8 warps x 8 rows: one fully unrolled pass of colsum_rows
 
 struct ColsumJobDev {
   const float *src;
-  int rows, cols, ld, op, perm_w, perm_c;
+  int rows, cols, ld, op, perm_w, perm_c, vec;
   void *dst0, *dst1;
   float alpha;
   int first_block, col_blocks, row_splits, rows_per;
@@ -114,10 +114,58 @@ struct ColsumBatchDev {
   int njobs;
 };
 
+constexpr int kColsumCols = 128;          // columns per block: 32 lanes x 4
+
+__device__ __forceinline__ void add4(float4 &a, const float4 &b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void cnt4(float4 &c, const float4 &v) {
+  c.x += v.x > 0.0f ? 1.0f : 0.0f; c.y += v.y > 0.0f ? 1.0f : 0.0f;
+  c.z += v.z > 0.0f ? 1.0f : 0.0f; c.w += v.w > 0.0f ? 1.0f : 0.0f;
+}
+// four adjacent columns of one row: one 128-bit load when the job allows it (16-byte aligned base and pitch;
+// lanes past `cols` then read the row's padding, which is never stored), else guarded scalar loads
+template <bool kVec>
+__device__ __forceinline__ float4 colsum_ld(const float *p, int col, int cols) {
+  if (kVec) return __ldg(reinterpret_cast<const float4 *>(p));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  v.x = __ldg(p);
+  if (col + 1 < cols) v.y = __ldg(p + 1);
+  if (col + 2 < cols) v.z = __ldg(p + 2);
+  if (col + 3 < cols) v.w = __ldg(p + 3);
+  return v;
+}
+
+// rows [r0, r1) of 4 columns, rows r0 + ty, r0 + ty + 8, ...: eight 128-bit loads in flight per thread, four
+// independent accumulators combined in a fixed order (the result does not depend on timing)
+template <bool kVec>
+__device__ __forceinline__ void colsum_rows(const float *p, size_t ld, int col, int cols, int r0, int r1, int ty,
+                                            bool stats2, float4 &sum, float4 &cnt) {
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0, c0 = s0, c1 = s0;
+  int r = r0 + ty;
+  for (; r + 56 < r1; r += 64) {
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = colsum_ld<kVec>(p + (size_t)(r + 8 * i) * ld, col, cols);
+    add4(s0, v[0]); add4(s1, v[1]); add4(s2, v[2]); add4(s3, v[3]);
+    add4(s0, v[4]); add4(s1, v[5]); add4(s2, v[6]); add4(s3, v[7]);
+    if (stats2) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) cnt4((i & 1) ? c1 : c0, v[i]);
+    }
+  }
+  for (; r < r1; r += 8) {
+    const float4 v = colsum_ld<kVec>(p + (size_t)r * ld, col, cols);
+    add4(s0, v);
+    if (stats2) cnt4(c0, v);
+  }
+  add4(s0, s1); add4(s2, s3); add4(s0, s2);
+  add4(c0, c1);
+  sum = s0; cnt = c0;
+}
+
 __global__ void __launch_bounds__(256)
 colsum_batch_kernel(const ColsumBatchDev batch, float *__restrict__ scratch, unsigned int *__restrict__ counters) {
   kcnn::pdl_prologue();
-  __shared__ float red0[8][33], red1[8][33];
+  __shared__ float4 red0[8][33], red1[8][33];
   __shared__ int is_last;
   int ji = 0;
   while (ji + 1 < batch.njobs && (int)blockIdx.x >= batch.job[ji + 1].first_block) ji++;
@@ -125,42 +173,33 @@ colsum_batch_kernel(const ColsumBatchDev batch, float *__restrict__ scratch, uns
   const int local = (int)blockIdx.x - J.first_block;
   const int cb = local % J.col_blocks, rs = local / J.col_blocks;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = cb * 32 + tx;
+  const int col = cb * kColsumCols + tx * 4;
   const bool stats2 = J.op == KCNN_COLSUM_STATS_RELU;
   const int r0 = rs * J.rows_per, r1 = min(J.rows, r0 + J.rows_per);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, c0 = 0.f, c1 = 0.f;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), cnt = sum;
   if (col < J.cols) {
-    const float *p = J.src + col;
-    int r = r0 + ty;
-    for (; r + 24 < r1; r += 32) {
-      const float a = __ldg(p + (size_t)r * J.ld), b = __ldg(p + (size_t)(r + 8) * J.ld);
-      const float c = __ldg(p + (size_t)(r + 16) * J.ld), d = __ldg(p + (size_t)(r + 24) * J.ld);
-      s0 += a; s1 += b; s2 += c; s3 += d;
-      if (stats2) {
-        c0 += (a > 0.0f ? 1.0f : 0.0f) + (c > 0.0f ? 1.0f : 0.0f);
-        c1 += (b > 0.0f ? 1.0f : 0.0f) + (d > 0.0f ? 1.0f : 0.0f);
-      }
-    }
-    for (; r < r1; r += 8) {
-      const float a = __ldg(p + (size_t)r * J.ld);
-      s0 += a;
-      if (stats2) c0 += a > 0.0f ? 1.0f : 0.0f;
-    }
+    if (J.vec) colsum_rows<true>(J.src + col, (size_t)J.ld, col, J.cols, r0, r1, ty, stats2, sum, cnt);
+    else       colsum_rows<false>(J.src + col, (size_t)J.ld, col, J.cols, r0, r1, ty, stats2, sum, cnt);
   }
-  red0[ty][tx] = (s0 + s1) + (s2 + s3);
-  red1[ty][tx] = c0 + c1;
+  red0[ty][tx] = sum;
+  red1[ty][tx] = cnt;
   __syncthreads();
   float *part = scratch + J.scratch_off;
   const size_t second = (size_t)J.row_splits * J.cols;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
   if (ty == 0 && col < J.cols) {
-    float a = red0[0][tx], b = red1[0][tx];
+    float4 sa = red0[0][tx], sb = red1[0][tx];
 #pragma unroll
-    for (int i = 1; i < 8; i++) { a += red0[i][tx]; b += red1[i][tx]; }
-    if (J.row_splits == 1) {
-      red0[0][tx] = a; red1[0][tx] = b;               // single stage: finish below
-    } else {
-      part[(size_t)rs * J.cols + col] = a;
-      if (stats2) part[second + (size_t)rs * J.cols + col] = b;
+    for (int i = 1; i < 8; i++) { add4(sa, red0[i][tx]); add4(sb, red1[i][tx]); }
+    a[0] = sa.x; a[1] = sa.y; a[2] = sa.z; a[3] = sa.w;
+    b[0] = sb.x; b[1] = sb.y; b[2] = sb.z; b[3] = sb.w;
+    if (J.row_splits > 1) {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (col + k < J.cols) {
+          part[(size_t)rs * J.cols + col + k] = a[k];
+          if (stats2) part[second + (size_t)rs * J.cols + col + k] = b[k];
+        }
     }
   }
   if (J.row_splits > 1) {
@@ -175,36 +214,69 @@ colsum_batch_kernel(const ColsumBatchDev batch, float *__restrict__ scratch, uns
     if (!is_last) return;
     __threadfence();
   }
-  if (ty != 0 || col >= J.cols) return;
-  float a, b = 0.f;
-  if (J.row_splits == 1) {
-    a = red0[0][tx]; b = red1[0][tx];
-  } else {
-    a = 0.f;
-    for (int z = 0; z < J.row_splits; z++) {
-      a += __ldcg(part + (size_t)z * J.cols + col);
-      if (stats2) b += __ldcg(part + second + (size_t)z * J.cols + col);
+  if (J.row_splits > 1) {
+    // second stage, by the block that arrived last: warp ty sums splits ty, ty + 8, ... of its 4 columns
+    // (loads of different splits are independent: four in flight per column), then the 8 warps' sums
+    // are combined in warp order -- a fixed order, like the first stage
+    float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
+    if (col < J.cols) {
+      float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int z0 = ty; z0 < J.row_splits; z0 += 32) {
+        float va[4][4], vb[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int z = z0 + 8 * u;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const bool ok = z < J.row_splits && col + k < J.cols;
+            va[u][k] = ok ? __ldcg(part + (size_t)z * J.cols + col + k) : 0.f;
+            vb[u][k] = (ok && stats2) ? __ldcg(part + second + (size_t)z * J.cols + col + k) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) { pa[k] += va[u][k]; pb[k] += vb[u][k]; }
+      }
+      fa = make_float4(pa[0], pa[1], pa[2], pa[3]);
+      fb = make_float4(pb[0], pb[1], pb[2], pb[3]);
     }
+    __syncthreads();                       // red0 / red1 of the first stage have been consumed
+    red0[ty][tx] = fa;
+    red1[ty][tx] = fb;
+    __syncthreads();
+    if (ty != 0 || col >= J.cols) return;
+    float4 sa = red0[0][tx], sb = red1[0][tx];
+#pragma unroll
+    for (int i = 1; i < 8; i++) { add4(sa, red0[i][tx]); add4(sb, red1[i][tx]); }
+    a[0] = sa.x; a[1] = sa.y; a[2] = sa.z; a[3] = sa.w;
+    b[0] = sb.x; b[1] = sb.y; b[2] = sb.z; b[3] = sb.w;
   }
-  int oc = col;
-  if (J.perm_w > 0) oc = (col % J.perm_c) * J.perm_w + col / J.perm_c;     // channels-last column -> [c][w] index
-  switch (J.op) {
-    case KCNN_COLSUM_STORE: static_cast<float *>(J.dst0)[oc] = a; break;
-    case KCNN_COLSUM_AXPY: {
-      float *d = static_cast<float *>(J.dst0);
-      d[oc] = fmaf(J.alpha, a, d[oc]);
-      break;
+  if (ty != 0 || col >= J.cols) return;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int c = col + k;
+    if (c >= J.cols) break;
+    int oc = c;
+    if (J.perm_w > 0) oc = (c % J.perm_c) * J.perm_w + c / J.perm_c;     // channels-last column -> [c][w] index
+    switch (J.op) {
+      case KCNN_COLSUM_STORE: static_cast<float *>(J.dst0)[oc] = a[k]; break;
+      case KCNN_COLSUM_AXPY: {
+        float *d = static_cast<float *>(J.dst0);
+        d[oc] = fmaf(J.alpha, a[k], d[oc]);
+        break;
+      }
+      case KCNN_COLSUM_STATS_RELU:
+        static_cast<double *>(J.dst0)[oc] += (double)a[k];
+        static_cast<double *>(J.dst1)[oc] += (double)b[k];
+        break;
+      default: static_cast<double *>(J.dst0)[oc] += (double)a[k]; break;      // KCNN_COLSUM_STATS_VALUE
     }
-    case KCNN_COLSUM_STATS_RELU:
-      static_cast<double *>(J.dst0)[oc] += (double)a;
-      static_cast<double *>(J.dst1)[oc] += (double)b;
-      break;
-    default: static_cast<double *>(J.dst0)[oc] += (double)a; break;      // KCNN_COLSUM_STATS_VALUE
   }
 }
 
 static void colsum_layout(const KcnnColsumJob &j, int &col_blocks, int &row_splits, int &rows_per) {
-  col_blocks = (j.cols + 31) / 32;
+  col_blocks = (j.cols + kColsumCols - 1) / kColsumCols;
   row_splits = (j.rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
   if (row_splits > 64) row_splits = 64;
   if (row_splits < 1) row_splits = 1;
@@ -377,7 +449,7 @@ size_t kcnn_colsum_batch_scratch_bytes(const KcnnColsumJob *jobs, int njobs) {
 void cudaF_colsum_batch(cudaStream_t st, const KcnnColsumJob *jobs, int njobs, void *scratch) {
   // layout of `scratch` (zero-filled once by the caller): all counters first, then the partial sums
   size_t counters = 0;
-  for (int i = 0; i < njobs; i++) counters += (size_t)((jobs[i].cols + 31) / 32);
+  for (int i = 0; i < njobs; i++) counters += (size_t)((jobs[i].cols + kColsumCols - 1) / kColsumCols);
   unsigned int *cnt = static_cast<unsigned int *>(scratch);
   float *part = reinterpret_cast<float *>(cnt + ((counters + 3) & ~(size_t)3));
   size_t coff = 0;
@@ -394,6 +466,7 @@ void cudaF_colsum_batch(cudaStream_t st, const KcnnColsumJob *jobs, int njobs, v
         ColsumJobDev &d = b.job[b.njobs++];
         d.src = j.src; d.rows = j.rows; d.cols = j.cols; d.ld = j.ld; d.op = j.op; d.perm_w = j.perm_w;
         d.perm_c = j.perm_c; d.dst0 = j.dst0; d.dst1 = j.dst1; d.alpha = j.alpha;
+        d.vec = ((reinterpret_cast<uintptr_t>(j.src) & 15u) == 0 && j.ld % 4 == 0) ? 1 : 0;
         d.first_block = blocks; d.col_blocks = cb; d.row_splits = rs; d.rows_per = rp;
         d.scratch_off = soff; d.counter_off = (int)coff;
         blocks += cb * rs;

@@ -13,6 +13,7 @@
 //   dgrad  dX[n,c,w,h]  = sum_{g,kw,kh} dY[n,g,w+pw-kw,h+ph-kh] K[c,kw,kh,g]
 //   wgrad  dK[c,kw,kh,g]= sum_{n,ow,oh} Xp[n,c,ow+kw,oh+kh] dY[n,g,ow,oh]
 
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -101,23 +102,33 @@ bool deep_ring_enabled() {
   return v == 1;
 }
 
-// Grow-only device scratch, one buffer per slot.  Grown with cudaMalloc, so the first call
-// of a shape must happen outside stream capture (warm-up steps do that); outgrown buffers
-// are kept alive because CUDA graphs captured earlier still point at them.
-float *scratch(int slot, size_t bytes) {
-  static float *buf[SCRATCH_SLOTS] = {};
-  static size_t cap[SCRATCH_SLOTS] = {};
-  if (bytes > cap[slot]) {
+// Grow-only device scratch, one buffer per (device, slot).  Grown with cudaMalloc, so the first call of a
+// shape must happen outside stream capture (warm-up steps do that; while `st` is being captured a buffer
+// that would have to grow is refused and the caller takes another path); outgrown buffers are kept alive
+// because CUDA graphs captured earlier still point at them.  The table is per device and guarded by a
+// mutex; the CONTENTS of a slot belong to whoever launched last, so the bare-component path that uses it
+// is limited to one stream per device at a time (NnetMinibatchUpdater's fused step never comes here).
+float *scratch(int slot, size_t bytes, cudaStream_t st) {
+  constexpr int kMaxDevices = 32;
+  static float *buf[kMaxDevices][SCRATCH_SLOTS] = {};
+  static size_t cap[kMaxDevices][SCRATCH_SLOTS] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lock(mu);
+  if (bytes > cap[dev][slot]) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(g_legacy_stream, &cs);
-    if (cs != cudaStreamCaptureStatusNone) return nullptr;
-    size_t want = bytes > 2 * cap[slot] ? bytes : 2 * cap[slot];
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    size_t want = bytes > 2 * cap[dev][slot] ? bytes : 2 * cap[dev][slot];
     float *p = nullptr;
     if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    buf[slot] = p;
-    cap[slot] = want;
+    buf[dev][slot] = p;
+    cap[dev][slot] = want;
   }
-  return buf[slot];
+  return buf[dev][slot];
 }
 
 }  // namespace tma

@@ -33,12 +33,15 @@ def parse_config(text, skip_splice=True):
 def tf32_operand(a, mode):
     """What a TF32 tensor-core instruction sees of an fp32 GEMM operand: sign, 8 exponent bits, 10 mantissa
     bits.  mode "trunc": the low 13 bits are ignored; "rna": round to nearest, ties away from zero
-    (cvt.rna.tf32.f32).  Test-only model of the DEVICE arithmetic; the reference itself is fp32."""
+    (cvt.rna.tf32.f32); "rne": round to nearest, ties to even.  Test-only model of the DEVICE arithmetic;
+    the reference itself is fp32."""
     if mode is None:
         return a
     u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
     if mode == "rna":
         u = u + np.uint32(0x1000)
+    elif mode == "rne":
+        u = u + np.uint32(0x0FFF) + ((u >> np.uint32(13)) & np.uint32(1))
     return (u & np.uint32(0xFFFFE000)).view(np.float32)
 
 

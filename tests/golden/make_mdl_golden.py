@@ -69,7 +69,7 @@ def conv_values():
     KH, KW, C, G = 2, 3, 2, 3
     lin = (rng.integers(-40, 40, (KH * KW * C, G)) / 64.0).astype(np.float32)      # exact in "%.7g"
     bias = np.array([0.5, -0.25, 0.125], np.float32)
-    prev = (rng.integers(-40, 40, (KH * KW * C, G)) / 4096.0).astype(np.float32)
+    prev = (rng.integers(-40, 40, (KH * KW * C, G)) / 128.0).astype(np.float32)       # <= 7 significant digits: exact in "%.7g"
     return dict(in_height=4, in_width=5, in_channel=C, kernel_height=KH, kernel_width=KW, stride=1, padding_height=0,
                 padding_width=1, group=G, out_height=3, out_width=5, lr=0.02, wd=0.0002, mom=0.9, lin=lin, bias=bias,
                 prev=prev)
@@ -112,7 +112,7 @@ def fc_stream(binary):
     rng = np.random.default_rng(7)
     lin = (rng.integers(-64, 64, (3, 4)) / 128.0).astype(np.float32)
     bias = np.array([1.0, 1.0, 1.0], np.float32)
-    prev = (rng.integers(-64, 64, (3, 4)) / 8192.0).astype(np.float32)
+    prev = (rng.integers(-64, 64, (3, 4)) / 128.0).astype(np.float32)
     w = W(binary)
     w.tok("<FullyConnectedComponent>")
     w.tok("<LearningRate>"); w.f32(0.008)

@@ -57,3 +57,56 @@ def run():
             assert v <= tol * 4, "smoke parity failed (math=%d): %s rel err %.3g" % (math, k, v)
         print("smoke ok math=%d: %s" % (math, ", ".join("%s %.2e" % kv for kv in checks.items())))
     kc.set_math_mode(0)
+    fused_step()
+
+
+FUSED_CFG = """
+ConvolutionComponent in-height=8 in-width=13 in-channel=1 kernel-height=8 kernel-width=4 stride=1 group=32 out-height=1 out-width=10 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5
+RectifiedLinearComponent dim=320
+MaxpoolComponent in-height=1 in-width=10 in-channel=32 pool-height-dim=1 pool-width-dim=1 pool-channel-dim=2
+ConvolutionComponent in-height=1 in-width=10 in-channel=16 kernel-height=1 kernel-width=3 stride=1 group=64 out-height=1 out-width=8 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.5
+MaxpoolComponent in-height=1 in-width=8 in-channel=64 pool-height-dim=1 pool-width-dim=2 pool-channel-dim=1
+RectifiedLinearComponent dim=256
+FullyConnectedComponent input-dim=256 output-dim=128 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.1 weight-decay=0.0005 momentum=0.9
+RectifiedLinearComponent dim=128
+FullyConnectedComponent input-dim=128 output-dim=24 learning-rate=0.02 param-stddev=0.05 bias-stddev=0 weight-decay=0.0005 momentum=0.9
+SoftmaxComponent dim=24
+"""
+
+
+def fused_step():
+    """One whole training step of a small conv / pool / FC network through NnetMinibatchUpdater's fused
+    plan (the path bench.py times) against the CPU oracle's step: objective and updated weights."""
+    import torch
+    from kaldi_cnn_b200 import components as kc
+    from oracle.cpu_nnet import CpuNnet
+    kc.set_math_mode(1)
+    kc.set_rand_seed(7)
+    net = kc.Nnet.from_config(FUSED_CFG)
+    cpu = CpuNnet(FUSED_CFG, seed=7)
+    g = lambda t: t.detach().cpu().numpy().copy()
+    upd = [i for i in range(net.num_components) if net.component(i).type in ("ConvolutionComponent", "FullyConnectedComponent")]
+    for i in upd:
+        c, L = net.component(i), cpu.layers[i]
+        L["lin" if c.type == "ConvolutionComponent" else "W"] = g(c.params(0))
+        L["bias"], L["prev"] = g(c.params(1))[0], g(c.params(2))
+        L["wd"], L["mom"] = c.weight_decay_momentum()
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((64, net.input_dim)).astype(np.float32)
+    lab = rng.integers(0, net.output_dim, 64).astype(np.int32)
+    kc.use_current_stream()
+    net.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda())
+    assert net.fused_active, "smoke: the fused plan did not engage"
+    objf = net.objf_and_reset()
+    cpu.forward(x)
+    objf_ref = cpu.backward(lab.astype(np.int64), update=True)
+    assert abs(objf - objf_ref) <= 1e-3 * abs(objf_ref), (objf, objf_ref)
+    worst = 0.0
+    for i in upd:
+        L = cpu.layers[i]
+        ref = L["lin"] if "lin" in L else L["W"]
+        got = g(net.component(i).params(0))
+        worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+    assert worst <= 1e-3, worst
+    kc.set_math_mode(0)
+    print("smoke ok fused step: objf %.6f (oracle %.6f), updated weights max rel err %.2e" % (objf, objf_ref, worst))

@@ -23,6 +23,7 @@ N = 512
 CONVS = [  # (H, W, C, KH, KW, G) of nnet.config (+ intermap variant's conv2)
     (40, 21, 1, 40, 4, 128), (1, 18, 64, 1, 3, 128), (1, 16, 128, 1, 3, 256), (1, 14, 256, 1, 3, 256),
     (1, 6, 256, 1, 3, 512), (1, 4, 512, 1, 3, 512),
+    (1, 8, 2000, 1, 5, 2000),      # C3(iii), SURVEY 8d (fbank_conv.sh:251), at its own batch of 256 (below)
 ]
 
 
@@ -30,9 +31,10 @@ def _dot(a, b):
     return float((a.double() * b.double()).sum())
 
 
-@pytest.mark.parametrize("shape", CONVS, ids=["conv%d" % (i + 1) for i in range(len(CONVS))])
+@pytest.mark.parametrize("shape", CONVS, ids=["conv%d" % (i + 1) for i in range(6)] + ["c3iii"])
 def test_conv_adjoint_identities_and_linearity_full_size(shape):
     H, W, C, KH, KW, G = shape
+    N = 256 if C == 2000 else 512
     OH, OW = H - KH + 1, W - KW + 1
     L = lib()
     g = torch.Generator(device="cuda"); g.manual_seed(sum(shape))

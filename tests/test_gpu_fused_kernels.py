@@ -90,6 +90,7 @@ CONV_SHAPES = [  # N, W, C, pw, KW, G
     (50, 4, 512, 0, 3, 512),       # conv6
     (33, 9, 40, 1, 3, 72),         # padding, ragged tiles, C and G not multiples of 32
     (16, 8, 200, 0, 5, 200),       # C3(iii)-like, scaled
+    (32, 8, 2000, 0, 5, 2000),     # C3(iii) itself (fbank_conv.sh:251: C = G = 2000, 1x5), reduced batch
 ]
 
 
