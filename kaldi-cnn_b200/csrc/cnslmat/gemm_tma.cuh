@@ -603,6 +603,13 @@ inline bool rows_epi_vec_ok(const RowsEpi &e) {
   return true;
 }
 
+// The dropout scale of one unit recovered from its activations, y / x with y = x * scale (x > 0).  The
+// reference's backward pass divides exactly like this (out_deriv * out_value / in_value); the IEEE division
+// sequence, though, is ~20 dependent instructions per element on a warp that has its scheduler to itself --
+// measured (ncu, profiles/r02_gated_dgrad.md): the gated FC2 input-gradient GEMM executed 6.6 M warp
+// instructions against 2.8 M ungated and took 73 us against 42.  MUFU.RCP + FMUL is within 2 ulp of it.
+__device__ __forceinline__ float gate_ratio(float y, float x) { return __fdividef(y, x); }
+
 // Row-major 128-column segment store shared by the dense, the channels-last convolution and the
 // weight-gradient problems: tid -> (warp, 4 columns); each warp instruction writes one 512-byte
 // row segment.  Tile rows [rb, re) are stored (the whole tile, or this CTA's slice of a cluster
@@ -699,9 +706,11 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
         if (rw[i] < 0) continue;
         float4 a = *reinterpret_cast<const float4 *>(stage + (r0 + 4 * i) * PITCH + 4 * lane);
         a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-        if (has_y) {       // d * y / x, the order of dropout_bprop_kernel, then the ReLU gate
-          a.x = x[i].x > 0.0f ? a.x * y[i].x / x[i].x : 0.0f; a.y = x[i].y > 0.0f ? a.y * y[i].y / x[i].y : 0.0f;
-          a.z = x[i].z > 0.0f ? a.z * y[i].z / x[i].z : 0.0f; a.w = x[i].w > 0.0f ? a.w * y[i].w / x[i].w : 0.0f;
+        if (has_y) {       // d * (y / x): dropout_bprop_kernel's gate, then the ReLU gate (see gate_ratio)
+          a.x = x[i].x > 0.0f ? a.x * gate_ratio(y[i].x, x[i].x) : 0.0f;
+          a.y = x[i].y > 0.0f ? a.y * gate_ratio(y[i].y, x[i].y) : 0.0f;
+          a.z = x[i].z > 0.0f ? a.z * gate_ratio(y[i].z, x[i].z) : 0.0f;
+          a.w = x[i].w > 0.0f ? a.w * gate_ratio(y[i].w, x[i].w) : 0.0f;
         } else {
           a.x = x[i].x > 0.0f ? a.x : 0.0f; a.y = x[i].y > 0.0f ? a.y : 0.0f;
           a.z = x[i].z > 0.0f ? a.z : 0.0f; a.w = x[i].w > 0.0f ? a.w : 0.0f;
@@ -767,9 +776,9 @@ __device__ __forceinline__ void store_rows(const float *stage, int tid, int m0, 
           if (n + 3 < N) y.w = __ldg(yr + 3);
         }
       }
-      if (yr) {          // d * y / x, the order of dropout_bprop_kernel, then the ReLU gate
-        a.x = x.x > 0.0f ? a.x * y.x / x.x : 0.0f; a.y = x.y > 0.0f ? a.y * y.y / x.y : 0.0f;
-        a.z = x.z > 0.0f ? a.z * y.z / x.z : 0.0f; a.w = x.w > 0.0f ? a.w * y.w / x.w : 0.0f;
+      if (yr) {          // d * (y / x): dropout_bprop_kernel's gate, then the ReLU gate (see gate_ratio)
+        a.x = x.x > 0.0f ? a.x * gate_ratio(y.x, x.x) : 0.0f; a.y = x.y > 0.0f ? a.y * gate_ratio(y.y, x.y) : 0.0f;
+        a.z = x.z > 0.0f ? a.z * gate_ratio(y.z, x.z) : 0.0f; a.w = x.w > 0.0f ? a.w * gate_ratio(y.w, x.w) : 0.0f;
       } else {
         a.x = x.x > 0.0f ? a.x : 0.0f; a.y = x.y > 0.0f ? a.y : 0.0f;
         a.z = x.z > 0.0f ? a.z : 0.0f; a.w = x.w > 0.0f ? a.w : 0.0f;

@@ -34,14 +34,14 @@ namespace kcnn {
 namespace p2p {
 
 constexpr int kMaxRanks = 8;
-constexpr int kMaxCtas = 64;
+constexpr int kMaxCtas = 128;
 constexpr int kThreads = 512;
 // uint32 words of one flag channel
 constexpr int kReady = 0;                            // [kMaxCtas][kMaxRanks]
 constexpr int kDone = kMaxCtas * kMaxRanks;          // [kMaxCtas][kMaxRanks]
 constexpr int kEpoch = 2 * kMaxCtas * kMaxRanks;     // [kMaxCtas]   (local)
 constexpr int kError = kEpoch + kMaxCtas;            // [1]          (local): spin limit hit
-constexpr int kChannelWords = 2048;
+constexpr int kChannelWords = 4096;
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -226,6 +226,66 @@ __device__ __forceinline__ void sgd4(float4 &w, float4 &p, const float4 &g, cons
   }
 }
 
+// One pass over this rank's slice [lo, hi) of a bucket.  kWorld ranks (compile time, so that the peer
+// loads of a unit are independent instructions), U units per thread: all U * kWorld gradient loads and the
+// 2 U loads of (W, prev) are issued before the first add -- a peer load over NVLink takes ~2 us, so the
+// bytes in flight per SM decide the link throughput (measured at 2 GPUs: U = 2 with a serial loop over the
+// ranks kept ~0.5 MB in flight per GPU and moved ~260 GB/s).  Sum order = rank order, as in the all-reduce.
+template <int kWorld, int U>
+__device__ __forceinline__ void reduce_sgd_slice(const Peers &pr, float *mc, int rank, int world, const SgdBucket &k,
+                                                 size_t lo, size_t hi, int b, int G, int t) {
+  const size_t step = (size_t)G * kThreads;
+  float *wmine = pr.buf[rank] + k.off + k.param_delta;
+  for (size_t i0 = lo + (size_t)b * kThreads + t; i0 < hi; i0 += U * step) {
+    float4 v[U][kWorld], w[U], p[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + u * step;
+      if (i >= hi) continue;
+      if (mc != nullptr) {
+        v[u][0] = multimem_ld_reduce_f4(mc + k.off + 4 * i);
+      } else {
+#pragma unroll
+        for (int q = 0; q < kWorld; q++) {
+          if (q >= world) continue;
+          const float *src = pr.buf[q] + k.off + 4 * i;
+          v[u][q] = q == rank ? *reinterpret_cast<const float4 *>(src) : ld_volatile_f4(src);
+        }
+      }
+      w[u] = *reinterpret_cast<const float4 *>(wmine + 4 * i);
+      if (i < k.w4) p[u] = *reinterpret_cast<const float4 *>(k.prev + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + u * step;
+      if (i >= hi) continue;
+      float4 g;
+      if (mc != nullptr) {
+        g = v[u][0];
+      } else {
+        g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < kWorld; q++)
+          if (q < world) { g.x += v[u][q].x; g.y += v[u][q].y; g.z += v[u][q].z; g.w += v[u][q].w; }
+      }
+      if (i < k.w4) {
+        sgd4(w[u], p[u], g, k);
+        *reinterpret_cast<float4 *>(k.prev + 4 * i) = p[u];
+      } else {
+        w[u].x = fmaf(k.a_grad, g.x, w[u].x); w[u].y = fmaf(k.a_grad, g.y, w[u].y);
+        w[u].z = fmaf(k.a_grad, g.z, w[u].z); w[u].w = fmaf(k.a_grad, g.w, w[u].w);
+      }
+      if (mc != nullptr) {
+        multimem_st_f4(mc + k.off + k.param_delta + 4 * i, w[u]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < kWorld; q++)
+          if (q < world) *reinterpret_cast<float4 *>(pr.buf[q] + k.off + k.param_delta + 4 * i) = w[u];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 p2p_reduce_sgd_kernel(Peers pr, float *mc, int rank, int world, SgdBucket k, size_t flag_off,
                       unsigned long long timeout_ns) {
@@ -242,47 +302,10 @@ p2p_reduce_sgd_kernel(Peers pr, float *mc, int rank, int world, SgdBucket k, siz
   const size_t per = (k.n4 + world - 1) / world;
   const size_t lo = (size_t)rank * per;
   const size_t hi = lo + per < k.n4 ? lo + per : k.n4;
-  const size_t step = (size_t)G * kThreads;
-  constexpr int U = 2;
-  float *wmine = pr.buf[rank] + k.off + k.param_delta;
-  for (size_t i0 = lo + (size_t)b * kThreads + t; i0 < hi; i0 += U * step) {
-    float4 g[U], w[U], p[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + u * step;
-      if (i >= hi) continue;
-      w[u] = *reinterpret_cast<const float4 *>(wmine + 4 * i);
-      if (i < k.w4) p[u] = *reinterpret_cast<const float4 *>(k.prev + 4 * i);
-      if (mc != nullptr) {
-        g[u] = multimem_ld_reduce_f4(mc + k.off + 4 * i);
-      } else {
-        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < world; q++) {                // rank order: the summation order of the all-reduce
-          const float *src = pr.buf[q] + k.off + 4 * i;
-          const float4 v = q == rank ? *reinterpret_cast<const float4 *>(src) : ld_volatile_f4(src);
-          g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + u * step;
-      if (i >= hi) continue;
-      if (i < k.w4) {
-        sgd4(w[u], p[u], g[u], k);
-        *reinterpret_cast<float4 *>(k.prev + 4 * i) = p[u];
-      } else {
-        w[u].x = fmaf(k.a_grad, g[u].x, w[u].x); w[u].y = fmaf(k.a_grad, g[u].y, w[u].y);
-        w[u].z = fmaf(k.a_grad, g[u].z, w[u].z); w[u].w = fmaf(k.a_grad, g[u].w, w[u].w);
-      }
-      if (mc != nullptr) {
-        multimem_st_f4(mc + k.off + k.param_delta + 4 * i, w[u]);
-      } else {
-        for (int q = 0; q < world; q++)
-          *reinterpret_cast<float4 *>(pr.buf[q] + k.off + k.param_delta + 4 * i) = w[u];
-      }
-    }
-  }
+  if (mc != nullptr)   reduce_sgd_slice<1, 8>(pr, mc, rank, world, k, lo, hi, b, G, t);
+  else if (world <= 2) reduce_sgd_slice<2, 4>(pr, mc, rank, world, k, lo, hi, b, G, t);
+  else if (world <= 4) reduce_sgd_slice<4, 2>(pr, mc, rank, world, k, lo, hi, b, G, t);
+  else                 reduce_sgd_slice<8, 1>(pr, mc, rank, world, k, lo, hi, b, G, t);
   __threadfence_system();
   __syncthreads();
   cross_barrier(pr, flag_off, kDone, b, rank, world, epoch, timeout_ns);
@@ -312,7 +335,7 @@ static int p2p_max_ctas() {
   static int max_ctas = -1;
   if (max_ctas < 0) {
     const char *e = getenv("KCNN_P2P_CTAS");
-    max_ctas = e ? atoi(e) : 32;
+    max_ctas = e ? atoi(e) : 64;
     if (max_ctas < 1) max_ctas = 1;
     if (max_ctas > p2p::kMaxCtas) max_ctas = p2p::kMaxCtas;
   }

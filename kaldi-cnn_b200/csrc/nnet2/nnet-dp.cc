@@ -30,6 +30,7 @@ NnetDataParallel::NnetDataParallel(Nnet *nnet, NnetMinibatchUpdater *updater, in
   grad_floats_ = updater_->GradientFloats();
   flag_off_ = 2 * grad_floats_;
   updater_->SetDeferredUpdate(true);
+  updater_->SetDeferredJoin(true);
   updater_->SetGradientArena(base_);                         // [0, grad_floats_): one bucket per layer, top first
   comm_[0] = comm_[1] = NULL;
   int lo = 0, hi = 0;
@@ -71,6 +72,7 @@ NnetDataParallel::~NnetDataParallel() {
     cudaEventDestroy(layers_[i].done);
   }
   updater_->SetDeferredUpdate(false);
+  updater_->SetDeferredJoin(false);
   if (error_pinned_) cudaFreeHost(error_pinned_);
 }
 
@@ -87,7 +89,9 @@ void NnetDataParallel::ReduceAndUpdate(const Layer &l, int32 rows_global) {
   UpdatableComponent *u = static_cast<UpdatableComponent *>(&nnet_->GetComponent(l.comp));
   UpdatableComponent::StepTarget t;
   if (!u->GetStepTarget(rows_global, &t)) KALDI_ERR << "NnetDataParallel: lost the update target";
-  CU_SAFE_CALL(cudaEventRecord(l.ready, Str()));
+  // the layer's gradients complete on the updater's weight-gradient branch (or on the compute stream when
+  // the range had none); that branch starts behind the layer's input-gradient GEMM, the last reader of W
+  CU_SAFE_CALL(cudaEventRecord(l.ready, updater_->GradientStream()));
   CU_SAFE_CALL(cudaStreamWaitEvent(comm_[l.channel], l.ready, 0));
   if (kcnn_p2p_reduce_sgd_f32(comm_[l.channel], &peers_[0], multicast_, rank_, world_, l.off, l.len, l.weight_floats,
                               grad_floats_, t.prev, t.momentum, t.a_decay, t.a_grad, flag_off_, l.channel) != 0)
@@ -103,6 +107,7 @@ void NnetDataParallel::BackwardWithUpdates(int32 rows_global) {
     hi = layers_[i].comp - 1;
   }
   if (hi >= 0) updater_->Backward(hi, 0);
+  updater_->JoinSide();
 }
 
 void NnetDataParallel::ForwardBehindUpdates(const CuMatrixBase<BaseFloat> &feats, const int32 *labels) {

@@ -554,11 +554,18 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
     cudaF_colsum_batch(cst, &(*lists[k])[0], static_cast<int>(lists[k]->size()), F.colsum_scratch[k]);
   }
   if (first == base_) stat_jobs.clear();
-  if (forked) {
+  grad_stream_ = forked ? F.side : st;
+  if (forked && !deferred_join_) {
     cudaEventRecord(F.join_ev, F.side);
     cudaStreamWaitEvent(st, F.join_ev, 0);
   }
   CU_SAFE_CALL(cudaGetLastError());
+}
+
+void NnetMinibatchUpdater::JoinSide() {
+  if (fused_ == NULL || fused_->side == NULL || fused_->join_ev == NULL) return;
+  CU_SAFE_CALL(cudaEventRecord(fused_->join_ev, fused_->side));
+  CU_SAFE_CALL(cudaStreamWaitEvent(Str(), fused_->join_ev, 0));
 }
 
 }  // namespace nnet2

@@ -108,7 +108,7 @@ struct NnetMinibatchUpdater::GraphState {
 
 NnetMinibatchUpdater::NnetMinibatchUpdater(Nnet *nnet)
     : graph_(new GraphState), last_replayed_(false), graphs_on_(true), fuse_(true),
-      nnet_(nnet), num_rows_(0), fused_(NULL), step_labels_(NULL), base_(0), labels_(NULL), objf_dev_(NULL) {
+      nnet_(nnet), num_rows_(0), fused_(NULL), deferred_join_(false), grad_stream_(NULL), step_labels_(NULL), base_(0), labels_(NULL), objf_dev_(NULL) {
   FusedInit();
   if (nnet_->NumComponents() > 1 && dynamic_cast<SpliceComponent *>(&nnet_->GetComponent(0)) != NULL) base_ = 1;
   objf_dev_ = static_cast<double *>(CuDevice::Instantiate().Malloc(sizeof(double)));
@@ -228,6 +228,7 @@ void NnetMinibatchUpdater::Backward(int32 last, int32 first) {
   if (last < 0) last = L - 1;
   KALDI_ASSERT(first >= 0 && last < L && !forward_.empty());
   if (first < base_) first = base_;       // nothing trains below the Splice front end (nnet2 stops there too)
+  grad_stream_ = CuDevice::Instantiate().Stream();
   if (last < first) return;
   if (FusedActive()) {
     FusedBackward(last, first);

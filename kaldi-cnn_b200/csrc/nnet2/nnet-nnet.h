@@ -104,6 +104,14 @@ class NnetMinibatchUpdater {
   /// Offset (floats) of component c's bucket inside the arena and its length.
   void GradientBucket(int32 c, size_t *offset, size_t *length) const;
   void SetDeferredUpdate(bool on);
+  /// Data-parallel trainer: Backward(last, first) is called once per updatable layer.  With the deferred
+  /// join the weight-gradient branch of a range (side stream) is NOT joined into the compute stream when
+  /// the call returns -- the next range's input-gradient GEMMs run beside it, as they do inside one
+  /// whole-network call; GradientStream() is the stream on which the range's gradients complete (record
+  /// the "gradients ready" event there) and JoinSide() joins the branch once the pass is over.
+  void SetDeferredJoin(bool on) { deferred_join_ = on; }
+  cudaStream_t GradientStream() const { return grad_stream_; }
+  void JoinSide();
   const CuMatrix<BaseFloat> &Output() const { return forward_.back(); }
   /// Output of component i - 1 in the reference layout (a channels-last buffer of the fused plan is
   /// converted into a side buffer on demand).
@@ -140,6 +148,8 @@ class NnetMinibatchUpdater {
   void FusedForward(int32 first, int32 last, const int32 *labels_dev);
   bool FusedObjf(const int32 *labels_dev);
   void FusedBackward(int32 last, int32 first);
+  bool deferred_join_;
+  cudaStream_t grad_stream_;
   const int32 *step_labels_;                    // TrainStep: labels known while the forward pass runs
   int32 base_;                                  // 1 when component 0 is the Splice front end, else 0
 
