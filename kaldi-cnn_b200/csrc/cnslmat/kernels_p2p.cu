@@ -335,7 +335,7 @@ static int p2p_max_ctas() {
   static int max_ctas = -1;
   if (max_ctas < 0) {
     const char *e = getenv("KCNN_P2P_CTAS");
-    max_ctas = e ? atoi(e) : 64;
+    max_ctas = e ? atoi(e) : 32;
     if (max_ctas < 1) max_ctas = 1;
     if (max_ctas > p2p::kMaxCtas) max_ctas = p2p::kMaxCtas;
   }

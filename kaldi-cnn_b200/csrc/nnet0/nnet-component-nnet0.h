@@ -118,11 +118,6 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   virtual size_t GradientFloats() const;
   virtual void SetGradientStorage(float *base);
   virtual void SetParameterStorage(float *base);
-  /// Opt-in for a caller that OWNS the activation buffers (NnetMinibatchUpdater) and so can
-  /// promise that the matrix given to Backprop as in_value is, unmodified, the one last
-  /// propagated: Backprop then reuses Propagate's channels-last staging copy instead of
-  /// packing in_value again.  Off by default: a bare Component makes no such assumption.
-  virtual void SetInputPersists(bool on) { input_persists_ = on; staged_src_ = NULL; }
   virtual bool GetStepTarget(int32 num_rows, StepTarget *t);
   virtual uint64 StepSignature() const {
     uint64 h = HashValue(learning_rate_, 13);
@@ -135,6 +130,11 @@ class ConvolutionComponent : public nnet2::UpdatableComponent {
   }
 
  protected:
+  /// (nnet2::UpdatableComponent, reachable by NnetMinibatchUpdater only.)  With the promise that the
+  /// matrix given to Backprop as in_value is, unmodified, the one last propagated, Backprop reuses
+  /// Propagate's channels-last staging copy instead of packing in_value again.  Off by default: a bare
+  /// Component makes no such assumption.
+  virtual void SetInputPersists(bool on) { input_persists_ = on; staged_src_ = NULL; }
   virtual void Update(const CuMatrixBase<BaseFloat> &in_value,
                       const CuMatrixBase<BaseFloat> &out_deriv);
   void ComputeGradient(const CuMatrixBase<BaseFloat> &in_value,

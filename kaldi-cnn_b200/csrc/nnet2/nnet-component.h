@@ -64,6 +64,8 @@ class ChunkInfo {
   std::vector<int32> offsets_;
 };
 
+class NnetMinibatchUpdater;
+
 class Component {
  public:
   Component() : index_(-1) {}
@@ -167,9 +169,6 @@ class UpdatableComponent : public Component {
   /// Place the gradient buffers in caller-provided storage (one flat all-reduce bucket).
   virtual size_t GradientFloats() const { return 0; }
   virtual void SetGradientStorage(float * /*base*/) {}
-  /// The caller owns the activation buffers and promises that Backprop's in_value is the
-  /// unmodified matrix last given to Propagate (lets a component keep per-input scratch).
-  virtual void SetInputPersists(bool) {}
   /// Raw views of the parameters, the momentum state and the gradient buffers, with the SGD
   /// coefficients of one minibatch of num_rows rows (lr = learning_rate_ / num_rows, reference
   /// nnet0/nnet-component-nnet0.cc:767, 1136): what NnetMinibatchUpdater's fused step hands to the
@@ -191,6 +190,12 @@ class UpdatableComponent : public Component {
   virtual void SetParameterStorage(float * /*base*/) {}
 
  protected:
+  /// "Backprop's in_value is, unmodified, the matrix last given to Propagate" -- lets a component keep
+  /// per-input scratch between the two calls (ConvolutionComponent: the channels-last staging copy).
+  /// Only NnetMinibatchUpdater, which OWNS the activation buffers, can make that promise; it is not part
+  /// of the public interface because nothing checks the contents.
+  friend class NnetMinibatchUpdater;
+  virtual void SetInputPersists(bool) {}
   BaseFloat learning_rate_;
  private:
   const UpdatableComponent &operator=(const UpdatableComponent &other);  // Disallow.
