@@ -82,7 +82,8 @@ struct NnetMinibatchUpdater::FusedState {
   std::vector<KcnnColsumJob> pending_stats;     // statistics of a backward pass issued in several ranges
   bool objf_done;                               // the forward pass already ran softmax + objective
   bool fork_fc;
-  FusedState() : valid(false), key(0), side(NULL), join_ev(NULL), objf_done(false), fork_fc(false) {
+  bool stats_issued;                            // this backward pass sent its statistics out at the top
+  FusedState() : valid(false), key(0), side(NULL), join_ev(NULL), objf_done(false), fork_fc(false), stats_issued(false) {
     colsum_scratch[0] = colsum_scratch[1] = NULL;
     colsum_bytes[0] = colsum_bytes[1] = 0;
   }
@@ -438,10 +439,9 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
     *x = r.Data(); *ldx = r.Stride();
     if (p.dropout >= 0) { *y = forward_[p.out].Data(); *ldy = forward_[p.out].Stride(); }
   };
-  for (int32 i = o_last; i >= o_first; i--) {
-    const FusedOp &op = F.ops[i];
-    Component &comp = nnet_->GetComponent(op.comp);
-    // statistics of the fused nonlinearities (NonlinearComponent::UpdateStats, done in Backprop upstream)
+  // statistics of the fused nonlinearities (NonlinearComponent::UpdateStats, done in Backprop upstream):
+  // they read forward activations only
+  auto stats_of = [&](const FusedOp &op) {
     if (op.relu >= 0) {
       NonlinearComponent &nl = static_cast<NonlinearComponent &>(nnet_->GetComponent(op.relu));
       const CuMatrix<BaseFloat> &y = forward_[op.relu + 1];
@@ -453,14 +453,48 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
       nl.AddToCount(num_rows_);
     }
     if (op.kind == FusedOp::kSoftmax) {
-      NonlinearComponent &nl = static_cast<NonlinearComponent &>(comp);
+      NonlinearComponent &nl = static_cast<NonlinearComponent &>(nnet_->GetComponent(op.comp));
       const CuMatrix<BaseFloat> &y = forward_[op.out];
       KcnnColsumJob j = {y.Data(), y.NumRows(), y.NumCols(), y.Stride(), KCNN_COLSUM_STATS_VALUE, 0, 0,
                          nl.StatsDevice(), NULL, 0.f};
       stat_jobs.push_back(j);
       nl.AddToCount(num_rows_);
-      continue;                                  // derivs_[op.in] was written with the objective
     }
+  };
+  auto launch_colsums = [&](std::vector<KcnnColsumJob> &jobs, int k, cudaStream_t cst) {
+    if (jobs.empty()) return;
+    const size_t need = kcnn_colsum_batch_scratch_bytes(&jobs[0], static_cast<int>(jobs.size()));
+    if (need > F.colsum_bytes[k]) {
+      // (first, eager, step only: a captured step finds the buffer in place)
+      if (F.colsum_scratch[k]) CuDevice::Instantiate().Free(F.colsum_scratch[k]);
+      F.colsum_scratch[k] = CuDevice::Instantiate().Malloc(need);
+      F.colsum_bytes[k] = need;
+      CU_SAFE_CALL(cudaMemsetAsync(F.colsum_scratch[k], 0, need, cst));
+    }
+    double bytes = 0.0;
+    for (size_t j = 0; j < jobs.size(); j++) bytes += 4.0 * jobs[j].rows * jobs[j].cols;
+    Tag(-1, k == 0 ? "nonlinearity statistics (all layers, batched column sums)"
+                   : "bias gradients + update (batched column sums)", 0.0, bytes);
+    cudaF_colsum_batch(cst, &jobs[0], static_cast<int>(jobs.size()), F.colsum_scratch[k]);
+  };
+  // A pass that starts at the top and will reach the bottom (one call, or the data-parallel trainer's
+  // layer-by-layer calls): the statistics of ALL layers go out first, on the side branch, instead of at the
+  // end of the pass on the compute stream (32 us of the critical path for the benchmarked model).
+  const bool whole_pass = last == nnet_->NumComponents() - 1 && (first == base_ || deferred_join_);
+  if (whole_pass && F.side != NULL) {
+    for (int32 i = o_last; i >= 0; i--) stats_of(F.ops[i]);
+    cudaStream_t ss = fork();
+    launch_colsums(stat_jobs, 0, ss);
+    stat_jobs.clear();
+    F.stats_issued = true;
+  } else if (last == nnet_->NumComponents() - 1) {
+    F.stats_issued = false;
+  }
+  for (int32 i = o_last; i >= o_first; i--) {
+    const FusedOp &op = F.ops[i];
+    Component &comp = nnet_->GetComponent(op.comp);
+    if (!F.stats_issued) stats_of(op);
+    if (op.kind == FusedOp::kSoftmax) continue;  // derivs_[op.in] was written with the objective
     const CuMatrix<BaseFloat> &dy = derivs_[op.out];
     const CuMatrix<BaseFloat> &x = forward_[op.in];
     const float *gx, *gy;
@@ -532,27 +566,11 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
     if (!ok) KALDI_ERR << "fused step: component " << op.comp << " (" << comp.Type() << ") was planned but a "
                        << "backward kernel rejected the shape";
   }
-  // every column sum of the range: two launches beside the tail of the GEMM chain
+  // the bias gradients of the range (and, for a pass issued in partial ranges, the statistics once it has
+  // reached the bottom): one launch each, beside the tail of the GEMM chain
   cudaStream_t cst = (F.side != NULL && forked) ? F.side : st;
-  std::vector<KcnnColsumJob> *lists[2] = {&stat_jobs, &bias_jobs};
-  for (int k = 0; k < 2; k++) {
-    // the statistics of ALL nonlinearities go in one launch, when the pass reaches the bottom
-    if (k == 0 && first != base_) continue;
-    if (lists[k]->empty()) continue;
-    const size_t need = kcnn_colsum_batch_scratch_bytes(&(*lists[k])[0], static_cast<int>(lists[k]->size()));
-    if (need > F.colsum_bytes[k]) {
-      // (first, eager, step only: a captured step finds the buffer in place)
-      if (F.colsum_scratch[k]) CuDevice::Instantiate().Free(F.colsum_scratch[k]);
-      F.colsum_scratch[k] = CuDevice::Instantiate().Malloc(need);
-      F.colsum_bytes[k] = need;
-      CU_SAFE_CALL(cudaMemsetAsync(F.colsum_scratch[k], 0, need, cst));
-    }
-    double bytes = 0.0;
-    for (size_t j = 0; j < lists[k]->size(); j++) bytes += 4.0 * (*lists[k])[j].rows * (*lists[k])[j].cols;
-    Tag(-1, k == 0 ? "nonlinearity statistics (all layers, batched column sums)"
-                   : "bias gradients + update (batched column sums)", 0.0, bytes);
-    cudaF_colsum_batch(cst, &(*lists[k])[0], static_cast<int>(lists[k]->size()), F.colsum_scratch[k]);
-  }
+  if (!F.stats_issued && first == base_) launch_colsums(stat_jobs, 0, cst);
+  launch_colsums(bias_jobs, 1, cst);
   if (first == base_) stat_jobs.clear();
   grad_stream_ = forked ? F.side : st;
   if (forked && !deferred_join_) {
