@@ -636,6 +636,7 @@ def run_ours(args):
             tol = 1e-3 if math == 1 else 1e-5
             rank_parity = {"rows": "%d x 32 vs 1 x %d" % (world, 32 * world), "steps": 4,
                            "max_rel_diff_params_and_momentum": worst, "tolerance": tol * 4,
+                           "norms": "weights / biases max-norm relative, momentum Frobenius relative",
                            "ok": bool(worst is not None and worst <= tol * 4 and identical and not failed),
                            "ranks_bit_identical": identical, "model": "C2 + intermap pooling, dropout lines removed "
                            "(a rank's dropout mask is indexed by its local row)"}
