@@ -43,6 +43,10 @@ const char *kcnn_last_error(void);
 /* CuDevice::PrintProfile / AccuProfile switch (reference cnslmat/conv2D.cc:110). */
 void kcnn_enable_profile(int on);
 void kcnn_print_profile(void);
+/* Caching allocator of the device layer: bytes held (live + cached), and bytes kept out of circulation
+ * because a recorded CUDA graph may still address them (0 in steady state: the trainers size their buffers
+ * before they record). */
+size_t kcnn_device_bytes_pinned_by_graphs(void);
 /* Bytes currently held by the caching device allocator. */
 size_t kcnn_device_bytes_allocated(void);
 
@@ -275,6 +279,17 @@ int kcnn_p2p_reduce_sgd_f32(void *stream, const unsigned long long *peer_bases, 
                             int rank, int world, size_t offset_floats, size_t count_floats, size_t weight_floats,
                             size_t param_delta_floats, float *prev_grad, float momentum, float decay_alpha,
                             float grad_alpha, size_t flag_offset_floats, int channel);
+
+/* The same for up to 8 (small) buckets between one pair of peer barriers: one launch for a stack of small
+ * layers whose gradients become available together. */
+typedef struct {
+  size_t offset_floats, count_floats, weight_floats;    /* as the arguments of kcnn_p2p_reduce_sgd_f32 */
+  float *prev_grad;
+  float momentum, decay_alpha, grad_alpha;
+} KcnnSgdBucket;
+int kcnn_p2p_reduce_sgd_multi_f32(void *stream, const unsigned long long *peer_bases, unsigned long long multicast_base,
+                                  int rank, int world, int num_buckets, const KcnnSgdBucket *buckets,
+                                  size_t param_delta_floats, size_t flag_offset_floats, int channel);
 
 /* Symmetric memory from CUDA IPC handles: kcnn_ipc_alloc returns zero-filled device memory and its
  * 64-byte cudaIpcMemHandle_t; the host sends the handle to the other ranks (any transport) and each

@@ -41,6 +41,11 @@ def use_current_stream():
     _lib().kcnn_set_compute_stream(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
 
 
+def bytes_pinned_by_graphs():
+    """Bytes of the device cache kept out of circulation because a recorded CUDA graph may address them."""
+    return int(_lib().kcnn_device_bytes_pinned_by_graphs())
+
+
 def set_math_mode(mode):
     _lib().kcnn_set_math_mode(int(mode))
 

@@ -181,6 +181,7 @@ void kcnn_set_compute_stream(void *s) { CuDevice::Instantiate().SetStream(static
 void kcnn_set_math_mode(int mode) { CuDevice::Instantiate().SetMathMode(mode); }
 int kcnn_get_math_mode(void) { return CuDevice::Instantiate().MathMode(); }
 void kcnn_set_rand_seed(unsigned long long seed) { CuDevice::Instantiate().SetRandSeed(seed); }
+size_t kcnn_device_bytes_pinned_by_graphs(void) { return CuDevice::Instantiate().BytesPinnedByGraphs(); }
 const char *kcnn_last_error(void) { return g_last_error.c_str(); }
 void kcnn_enable_profile(int on) { CuDevice::Instantiate().EnableProfile(on != 0); }
 void kcnn_print_profile(void) { CuDevice::Instantiate().PrintProfile(); }

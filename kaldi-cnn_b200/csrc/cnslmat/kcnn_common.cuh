@@ -34,8 +34,8 @@ void profile_after(cudaStream_t st);
 // have started; wait until the PREVIOUS kernel has completed and flushed" -- and is launched
 // with the programmatic-stream-serialization attribute, so the launch latency and the
 // prologue of kernel i+1 (barrier init, TMEM allocation, tensor-map fetch) hide under the
-// tail of kernel i instead of adding ~90 serial gaps to a training step.  Without the
-// attribute (the default; KCNN_PDL=1 turns it on) both instructions are no-ops.
+// tail of kernel i instead of adding serial gaps to a training step.  Without the attribute
+// (KCNN_PDL=0) both instructions are no-ops.
 __device__ __forceinline__ void pdl_prologue() {
 #if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -57,7 +57,7 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
-bool pdl_enabled();      // kcnn_lib.cu: KCNN_PDL=1 turns the launch attribute on
+bool pdl_enabled();      // kcnn_lib.cu: the launch attribute; on unless KCNN_PDL=0
 
 // Fork / join of independent launches inside one library call (e.g. the input-gradient and
 // the weight-gradient GEMM of a convolution: small grids that leave most SMs idle when run

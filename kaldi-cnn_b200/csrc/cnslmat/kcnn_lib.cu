@@ -52,11 +52,13 @@ void profile_after(cudaStream_t st) {
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    // Opt-in: measured on the C2 step it LOSES 2.5 % (0.859 vs 0.837 ms) -- the early-scheduled
-    // dependents take SM slots from the tail of the running kernel and gain little, because
-    // a captured graph already keeps kernel-to-kernel gaps near 1 us.
+    // On by default (KCNN_PDL=0 turns it off).  With the 76-launch step of round 1 it LOST 2.5 % (0.859 vs
+    // 0.837 ms: the early-scheduled dependents took SM slots from the tail of the running kernel); with
+    // the 33 fatter launches of the fused plan it gains 2.6 % (0.641 -> 0.624 ms, identical parameters):
+    // the prologue of the next GEMM (tensor-map fetch, barrier init, TMEM allocation) hides under the
+    // epilogue of the current one.
     const char *e = getenv("KCNN_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }

@@ -26,6 +26,7 @@
 // bookkeeping.  CTA b only ever waits for CTA b of its peers: no co-residency assumption.
 
 #include "kcnn_common.cuh"
+#include "kcnn_capi.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -117,6 +118,7 @@ __device__ __forceinline__ void multimem_st_f4(float *mc, const float4 &v) {
 __global__ void __launch_bounds__(kThreads)
 p2p_allreduce_kernel(Peers pr, float *mc, int rank, int world, size_t off, size_t n4, size_t flag_off,
                      unsigned long long timeout_ns) {
+  kcnn::pdl_wait();            // (no early trigger: what follows a collective waits for all of it)
   const int b = blockIdx.x, G = gridDim.x, t = threadIdx.x;
   __shared__ uint32_t s_epoch;
   uint32_t *my_flags = reinterpret_cast<uint32_t *>(pr.buf[rank] + flag_off);
@@ -289,6 +291,7 @@ __device__ __forceinline__ void reduce_sgd_slice(const Peers &pr, float *mc, int
 __global__ void __launch_bounds__(kThreads)
 p2p_reduce_sgd_kernel(Peers pr, float *mc, int rank, int world, SgdBucket k, size_t flag_off,
                       unsigned long long timeout_ns) {
+  kcnn::pdl_wait();
   const int b = blockIdx.x, G = gridDim.x, t = threadIdx.x;
   __shared__ uint32_t s_epoch;
   uint32_t *my_flags = reinterpret_cast<uint32_t *>(pr.buf[rank] + flag_off);
@@ -306,6 +309,46 @@ p2p_reduce_sgd_kernel(Peers pr, float *mc, int rank, int world, SgdBucket k, siz
   else if (world <= 2) reduce_sgd_slice<2, 4>(pr, mc, rank, world, k, lo, hi, b, G, t);
   else if (world <= 4) reduce_sgd_slice<4, 2>(pr, mc, rank, world, k, lo, hi, b, G, t);
   else                 reduce_sgd_slice<8, 1>(pr, mc, rank, world, k, lo, hi, b, G, t);
+  __threadfence_system();
+  __syncthreads();
+  cross_barrier(pr, flag_off, kDone, b, rank, world, epoch, timeout_ns);
+  if (t == 0) my_flags[kEpoch + b] = epoch;
+}
+
+// Several (small) layers' buckets between ONE pair of barriers: the convolution stack of the benchmarked
+// model is six buckets of 20 K .. 790 K floats whose gradients all exist when the backward pass reaches the
+// bottom; one launch and two peer barriers instead of six and twelve.  Same per-bucket slices and arithmetic
+// as p2p_reduce_sgd_kernel, bucket after bucket.
+constexpr int kMaxBuckets = 8;
+struct SgdBucketList {
+  SgdBucket b[kMaxBuckets];
+  int n;
+};
+
+__global__ void __launch_bounds__(kThreads)
+p2p_reduce_sgd_multi_kernel(Peers pr, float *mc, int rank, int world, SgdBucketList list, size_t flag_off,
+                            unsigned long long timeout_ns) {
+  kcnn::pdl_wait();
+  const int b = blockIdx.x, G = gridDim.x, t = threadIdx.x;
+  __shared__ uint32_t s_epoch;
+  uint32_t *my_flags = reinterpret_cast<uint32_t *>(pr.buf[rank] + flag_off);
+  if (t == 0) s_epoch = my_flags[kEpoch + b] + 1u;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  if (!cross_barrier(pr, flag_off, kReady, b, rank, world, epoch, timeout_ns)) {
+    if (t == 0) my_flags[kEpoch + b] = epoch;
+    return;
+  }
+  for (int j = 0; j < list.n; j++) {
+    const SgdBucket &k = list.b[j];
+    const size_t per = (k.n4 + world - 1) / world;
+    const size_t lo = (size_t)rank * per;
+    const size_t hi = lo + per < k.n4 ? lo + per : k.n4;
+    if (mc != nullptr)   reduce_sgd_slice<1, 8>(pr, mc, rank, world, k, lo, hi, b, G, t);
+    else if (world <= 2) reduce_sgd_slice<2, 4>(pr, mc, rank, world, k, lo, hi, b, G, t);
+    else if (world <= 4) reduce_sgd_slice<4, 2>(pr, mc, rank, world, k, lo, hi, b, G, t);
+    else                 reduce_sgd_slice<8, 1>(pr, mc, rank, world, k, lo, hi, b, G, t);
+  }
   __threadfence_system();
   __syncthreads();
   cross_barrier(pr, flag_off, kDone, b, rank, world, epoch, timeout_ns);
@@ -388,6 +431,41 @@ int kcnn_p2p_reduce_sgd_f32(void *stream, const unsigned long long *peer_bases, 
   const unsigned grid = (unsigned)(want < (size_t)max_ctas ? want : (size_t)max_ctas);
   KCNN_LAUNCH(p2p::p2p_reduce_sgd_kernel, grid, p2p::kThreads, 0, st, pr,
               reinterpret_cast<float *>(static_cast<uintptr_t>(multicast_base)), rank, world, k,
+              flag_offset_floats + (size_t)channel * p2p::kChannelWords, p2p_timeout_ns());
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int kcnn_p2p_reduce_sgd_multi_f32(void *stream, const unsigned long long *peer_bases, unsigned long long multicast_base,
+                                  int rank, int world, int num_buckets, const KcnnSgdBucket *buckets,
+                                  size_t param_delta_floats, size_t flag_offset_floats, int channel) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (world < 1 || world > p2p::kMaxRanks || rank < 0 || rank >= world) return -1;
+  if (channel < 0 || channel > 1 || num_buckets < 1 || num_buckets > p2p::kMaxBuckets || buckets == nullptr) return -1;
+  if ((flag_offset_floats & 3) || (param_delta_floats & 3)) return -1;
+  p2p::Peers pr;
+  for (int p = 0; p < p2p::kMaxRanks; p++)
+    pr.buf[p] = p < world ? reinterpret_cast<float *>(static_cast<uintptr_t>(peer_bases[p])) : nullptr;
+  p2p::SgdBucketList list;
+  list.n = 0;
+  size_t largest = 0;
+  for (int j = 0; j < num_buckets; j++) {
+    const KcnnSgdBucket &q = buckets[j];
+    if ((q.count_floats & 3) || (q.offset_floats & 3) || (q.weight_floats & 3) || q.weight_floats > q.count_floats)
+      return -1;
+    if (q.count_floats == 0) continue;
+    p2p::SgdBucket &k = list.b[list.n++];
+    k.off = q.offset_floats; k.n4 = q.count_floats >> 2; k.w4 = q.weight_floats >> 2; k.param_delta = param_delta_floats;
+    k.prev = q.prev_grad; k.momentum = q.momentum; k.a_decay = q.decay_alpha; k.a_grad = q.grad_alpha;
+    const size_t per = (k.n4 + world - 1) / world;
+    if (per > largest) largest = per;
+  }
+  if (list.n == 0) return 0;
+  size_t want = (largest + p2p::kThreads * 2 - 1) / (p2p::kThreads * 2);
+  if (want < 1) want = 1;
+  const int max_ctas = p2p_max_ctas();
+  const unsigned grid = (unsigned)(want < (size_t)max_ctas ? want : (size_t)max_ctas);
+  KCNN_LAUNCH(p2p::p2p_reduce_sgd_multi_kernel, grid, p2p::kThreads, 0, st, pr,
+              reinterpret_cast<float *>(static_cast<uintptr_t>(multicast_base)), rank, world, list,
               flag_offset_floats + (size_t)channel * p2p::kChannelWords, p2p_timeout_ns());
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -8,7 +8,7 @@ namespace kaldi {
 
 CuDevice::CuDevice()
     : enabled_(false), profile_(false), math_mode_(KCNN_MATH_FP32_SIMT), rand_seed_(5489),
-      stream_(0), bytes_allocated_(0) {
+      stream_(0), live_graphs_(0), bytes_allocated_(0) {
   const char *m = getenv("KCNN_MATH");
   if (m && (std::string(m) == "tf32" || std::string(m) == "1")) math_mode_ = KCNN_MATH_TF32_TC;
 }
@@ -65,13 +65,42 @@ void *CuDevice::Malloc(size_t bytes) {
     bytes_allocated_ += sz;
   }
   live_[p] = sz;
+  if (Capturing()) graph_blocks_[p] = sz;
   return p;
+}
+
+bool CuDevice::Capturing() const {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream_, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+
+void CuDevice::GraphDestroyed() {
+  if (live_graphs_ > 0) live_graphs_--;
+  if (live_graphs_ > 0) return;
+  for (size_t i = 0; i < graph_pinned_.size(); i++) free_[graph_pinned_[i].second].push_back(graph_pinned_[i].first);
+  graph_pinned_.clear();
+  graph_blocks_.clear();          // blocks still live are ordinary blocks again: no graph is left to address them
+}
+
+size_t CuDevice::BytesPinnedByGraphs() const {
+  size_t b = 0;
+  for (size_t i = 0; i < graph_pinned_.size(); i++) b += graph_pinned_[i].second;
+  return b;
 }
 
 void CuDevice::Free(void *ptr) {
   if (!ptr) return;
   std::map<void *, size_t>::iterator it = live_.find(ptr);
   if (it == live_.end()) { cudaFree(ptr); return; }
+  std::map<void *, size_t>::iterator gb = graph_blocks_.find(ptr);
+  if (gb != graph_blocks_.end() || Capturing()) {
+    // a recorded (or recording) step addresses this block: keep it out of circulation (cu-device.h)
+    graph_pinned_.push_back(std::make_pair(ptr, it->second));
+    if (gb != graph_blocks_.end()) graph_blocks_.erase(gb);
+    live_.erase(it);
+    return;
+  }
   // Stream-ordered reuse: all work is issued on one stream (Stream()), so a block
   // handed out again is only touched by later work on that same stream.
   free_[it->second].push_back(ptr);

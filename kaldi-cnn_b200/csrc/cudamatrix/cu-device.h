@@ -53,6 +53,16 @@ class CuDevice {
   void Free(void *ptr);
   void ReleaseCache();
   size_t BytesAllocated() const { return bytes_allocated_; }
+  /// Recorded CUDA graphs bake device addresses in.  A block that is handed out or returned WHILE the
+  /// compute stream is being captured is therefore pinned: when it is freed it does not go back to the
+  /// cache (where the next Malloc of that size class -- a held-out batch, a second network, a staging
+  /// slot -- would receive memory a later replay still writes to) until every recorded graph has been
+  /// destroyed.  NnetMinibatchUpdater / NnetDataParallel report their graph executables here; their own
+  /// buffers are sized before the capture, so in steady state nothing is pinned.
+  void GraphRecorded() { live_graphs_++; }
+  void GraphDestroyed();
+  void CaptureAbandoned() { if (live_graphs_ == 0) { live_graphs_ = 1; GraphDestroyed(); } }
+  size_t BytesPinnedByGraphs() const;
 
   /// Rows are pitched to a multiple of 16 bytes so 128-bit and TMA paths apply.
   static int32 PitchInElements(int32 cols, size_t elem_size) {
@@ -72,6 +82,10 @@ class CuDevice {
   int math_mode_;
   unsigned long long rand_seed_;
   cudaStream_t stream_;
+  int live_graphs_;
+  std::map<void *, size_t> graph_blocks_;                  // live blocks handed out during a capture
+  std::vector<std::pair<void *, size_t> > graph_pinned_;   // freed blocks a graph may still address
+  bool Capturing() const;
   std::map<std::string, double> profile_map_;
   std::map<size_t, std::vector<void *> > free_;
   std::map<void *, size_t> live_;

@@ -49,10 +49,26 @@ NnetDataParallel::NnetDataParallel(Nnet *nnet, NnetMinibatchUpdater *updater, in
     if (!u->GetStepTarget(1, &t)) KALDI_ERR << "NnetDataParallel: lost the update target";
     l.weight_floats = (size_t)t.wd.rows * t.wd.stride;
     KALDI_ASSERT(t.w == base_ + grad_floats_ + l.off && t.pd.stride == t.wd.stride && l.weight_floats <= l.len);
-    l.channel = l.len >= (1u << 20) ? 0 : 1;                 // convolution buckets must not queue behind the FC stack
-    CU_SAFE_CALL(cudaEventCreateWithFlags(&l.ready, cudaEventDisableTiming));
-    CU_SAFE_CALL(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
     layers_.push_back(l);
+  }
+  static int group_small = -1;
+  if (group_small < 0) {
+    const char *e = getenv("KCNN_DP_GROUP");             // KCNN_DP_GROUP=0: one launch per layer
+    group_small = (e && e[0] == '0') ? 0 : 1;
+  }
+  for (size_t i = 0; i < layers_.size(); i++) {
+    const bool small = layers_[i].len < (1u << 20);
+    if (group_small && small && !groups_.empty() && groups_.back().channel == 1 &&
+        groups_.back().last == (int32)i - 1 && groups_.back().last - groups_.back().first + 1 < 8) {
+      groups_.back().last = (int32)i;
+      continue;
+    }
+    Group g;
+    g.first = g.last = (int32)i;
+    g.channel = small ? 1 : 0;                           // convolution buckets must not queue behind the FC stack
+    CU_SAFE_CALL(cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming));
+    CU_SAFE_CALL(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    groups_.push_back(g);
   }
   CU_SAFE_CALL(cudaMallocHost(reinterpret_cast<void **>(&error_pinned_), 2 * sizeof(unsigned int)));
   error_pinned_[0] = error_pinned_[1] = 0u;
@@ -68,8 +84,10 @@ NnetDataParallel::~NnetDataParallel() {
     // parameters leave the arena (which belongs to the caller) with their current values
     UpdatableComponent *u = dynamic_cast<UpdatableComponent *>(&nnet_->GetComponent(layers_[i].comp));
     if (u) { u->SetParameterStorage(NULL); u->SetGradientStorage(NULL); }
-    cudaEventDestroy(layers_[i].ready);
-    cudaEventDestroy(layers_[i].done);
+  }
+  for (size_t i = 0; i < groups_.size(); i++) {
+    cudaEventDestroy(groups_[i].ready);
+    cudaEventDestroy(groups_[i].done);
   }
   updater_->SetDeferredUpdate(false);
   updater_->SetDeferredJoin(false);
@@ -78,33 +96,48 @@ NnetDataParallel::~NnetDataParallel() {
 
 void NnetDataParallel::DropGraphs() {
   for (size_t i = 0; i < graphs_.size(); i++)
-    if (graphs_[i].exec) cudaGraphExecDestroy(graphs_[i].exec);
+    if (graphs_[i].exec) { cudaGraphExecDestroy(graphs_[i].exec); CuDevice::Instantiate().GraphDestroyed(); }
   graphs_.clear();
   seen_.clear();
 }
 
-// One kernel per layer on the layer's communication stream, behind everything the compute stream has
-// issued so far (the layer's weight gradient, bias gradient and input gradient).
-void NnetDataParallel::ReduceAndUpdate(const Layer &l, int32 rows_global) {
-  UpdatableComponent *u = static_cast<UpdatableComponent *>(&nnet_->GetComponent(l.comp));
-  UpdatableComponent::StepTarget t;
-  if (!u->GetStepTarget(rows_global, &t)) KALDI_ERR << "NnetDataParallel: lost the update target";
-  // the layer's gradients complete on the updater's weight-gradient branch (or on the compute stream when
-  // the range had none); that branch starts behind the layer's input-gradient GEMM, the last reader of W
-  CU_SAFE_CALL(cudaEventRecord(l.ready, updater_->GradientStream()));
-  CU_SAFE_CALL(cudaStreamWaitEvent(comm_[l.channel], l.ready, 0));
-  if (kcnn_p2p_reduce_sgd_f32(comm_[l.channel], &peers_[0], multicast_, rank_, world_, l.off, l.len, l.weight_floats,
-                              grad_floats_, t.prev, t.momentum, t.a_decay, t.a_grad, flag_off_, l.channel) != 0)
-    KALDI_ERR << "kcnn_p2p_reduce_sgd_f32 rejected its arguments";
-  CU_SAFE_CALL(cudaEventRecord(l.done, comm_[l.channel]));
+// One kernel per group on the group's communication stream, behind everything the backward pass has issued
+// for its layers (weight gradients, bias gradients, and the input-gradient GEMMs that read the weights).
+void NnetDataParallel::ReduceAndUpdate(const Group &g, int32 rows_global) {
+  KcnnSgdBucket b[8];
+  int n = 0;
+  for (int32 i = g.first; i <= g.last; i++) {
+    const Layer &l = layers_[i];
+    UpdatableComponent *u = static_cast<UpdatableComponent *>(&nnet_->GetComponent(l.comp));
+    UpdatableComponent::StepTarget t;
+    if (!u->GetStepTarget(rows_global, &t)) KALDI_ERR << "NnetDataParallel: lost the update target";
+    b[n].offset_floats = l.off; b[n].count_floats = l.len; b[n].weight_floats = l.weight_floats;
+    b[n].prev_grad = t.prev; b[n].momentum = t.momentum; b[n].decay_alpha = t.a_decay; b[n].grad_alpha = t.a_grad;
+    n++;
+  }
+  // the gradients complete on the updater's weight-gradient branch (or on the compute stream when the
+  // range had none); that branch starts behind the layers' input-gradient GEMMs, the last readers of W
+  CU_SAFE_CALL(cudaEventRecord(g.ready, updater_->GradientStream()));
+  CU_SAFE_CALL(cudaStreamWaitEvent(comm_[g.channel], g.ready, 0));
+  int rc;
+  if (n == 1)
+    rc = kcnn_p2p_reduce_sgd_f32(comm_[g.channel], &peers_[0], multicast_, rank_, world_, b[0].offset_floats,
+                                 b[0].count_floats, b[0].weight_floats, grad_floats_, b[0].prev_grad, b[0].momentum,
+                                 b[0].decay_alpha, b[0].grad_alpha, flag_off_, g.channel);
+  else
+    rc = kcnn_p2p_reduce_sgd_multi_f32(comm_[g.channel], &peers_[0], multicast_, rank_, world_, n, b, grad_floats_,
+                                       flag_off_, g.channel);
+  if (rc != 0) KALDI_ERR << "kcnn_p2p_reduce_sgd rejected its arguments";
+  CU_SAFE_CALL(cudaEventRecord(g.done, comm_[g.channel]));
 }
 
 void NnetDataParallel::BackwardWithUpdates(int32 rows_global) {
   int32 hi = nnet_->NumComponents() - 1;
-  for (size_t i = layers_.size(); i-- > 0;) {                // top layer first: the order backward produces them
-    updater_->Backward(hi, layers_[i].comp);
-    ReduceAndUpdate(layers_[i], rows_global);
-    hi = layers_[i].comp - 1;
+  for (size_t i = groups_.size(); i-- > 0;) {                // top group first: the order backward produces them
+    const int32 lowest = layers_[groups_[i].first].comp;
+    updater_->Backward(hi, lowest);
+    ReduceAndUpdate(groups_[i], rows_global);
+    hi = lowest - 1;
   }
   if (hi >= 0) updater_->Backward(hi, 0);
   updater_->JoinSide();
@@ -113,11 +146,11 @@ void NnetDataParallel::BackwardWithUpdates(int32 rows_global) {
 void NnetDataParallel::ForwardBehindUpdates(const CuMatrixBase<BaseFloat> &feats, const int32 *labels) {
   const int32 L = nnet_->NumComponents();
   int32 first = 0;
-  for (size_t i = 0; i < layers_.size(); i++) {
-    const int32 c = layers_[i].comp;
+  for (size_t i = 0; i < groups_.size(); i++) {
+    const int32 c = layers_[groups_[i].first].comp;
     if (c > first) { updater_->ForwardRange(feats, first, c - 1, NULL); first = c; }
-    CU_SAFE_CALL(cudaStreamWaitEvent(Str(), layers_[i].done, 0));     // this layer's new weights are in place
-    const int32 last = i + 1 < layers_.size() ? layers_[i + 1].comp - 1 : L - 1;
+    CU_SAFE_CALL(cudaStreamWaitEvent(Str(), groups_[i].done, 0));     // this group's new weights are in place
+    const int32 last = i + 1 < groups_.size() ? layers_[groups_[i + 1].first].comp - 1 : L - 1;
     updater_->ForwardRange(feats, first, last, last == L - 1 ? labels : NULL);
     first = last + 1;
   }
@@ -202,13 +235,15 @@ void NnetDataParallel::Rotate(const CuMatrixBase<BaseFloat> &feats_next, const i
   }
   cudaGraphExec_t exec = NULL;
   if (ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { ok = false; exec = NULL; }
+  if (ok) CuDevice::Instantiate().GraphRecorded();
+  else CuDevice::Instantiate().CaptureAbandoned();
   if (g) cudaGraphDestroy(g);
   Recorded r;
   r.key = key;
   r.exec = exec;
   r.count_delta.assign(L, 0.0);
   if (graphs_.size() >= 4) {
-    if (graphs_[0].exec) cudaGraphExecDestroy(graphs_[0].exec);
+    if (graphs_[0].exec) { cudaGraphExecDestroy(graphs_[0].exec); CuDevice::Instantiate().GraphDestroyed(); }
     graphs_.erase(graphs_.begin());
   }
   if (!ok) {
@@ -233,7 +268,7 @@ void NnetDataParallel::Rotate(const CuMatrixBase<BaseFloat> &feats_next, const i
 void NnetDataParallel::Finish(int32 rows_global) {
   if (!primed_) return;
   BackwardWithUpdates(rows_global);
-  for (size_t i = 0; i < layers_.size(); i++) CU_SAFE_CALL(cudaStreamWaitEvent(Str(), layers_[i].done, 0));
+  for (size_t i = 0; i < groups_.size(); i++) CU_SAFE_CALL(cudaStreamWaitEvent(Str(), groups_[i].done, 0));
   primed_ = false;
 }
 
@@ -249,7 +284,7 @@ bool NnetDataParallel::Failed(bool synchronise) {
 
 void NnetDataParallel::GatherMomentum() {
   cudaStream_t st = Str();
-  for (size_t i = 0; i < layers_.size(); i++) CU_SAFE_CALL(cudaStreamWaitEvent(st, layers_[i].done, 0));
+  for (size_t i = 0; i < groups_.size(); i++) CU_SAFE_CALL(cudaStreamWaitEvent(st, groups_[i].done, 0));
   for (size_t i = 0; i < layers_.size(); i++) {
     const Layer &l = layers_[i];
     UpdatableComponent *u = static_cast<UpdatableComponent *>(&nnet_->GetComponent(l.comp));

@@ -61,13 +61,19 @@ class NnetDataParallel {
   struct Layer {
     int32 comp;
     size_t off, len, weight_floats;       // bucket in the gradient arena (floats)
+  };
+  // Consecutive small layers (the convolution stack) share ONE reduce + SGD + broadcast launch: their
+  // gradients all exist when the backward pass reaches the lowest of them, and the next forward pass needs
+  // the lowest first.  A large layer (FC) is a group of its own, reduced as soon as its gradient exists.
+  struct Group {
+    int32 first, last;                    // layers_[first .. last], network order
     int32 channel;                        // 0: big buckets (FC stack), 1: small (convolutions)
     cudaEvent_t ready, done;
   };
   void BackwardWithUpdates(int32 rows_global);
   void ForwardBehindUpdates(const CuMatrixBase<BaseFloat> &feats, const int32 *labels);
   void RotateEager(const CuMatrixBase<BaseFloat> &feats_next, const int32 *labels_next, int32 rows_global);
-  void ReduceAndUpdate(const Layer &l, int32 rows_global);
+  void ReduceAndUpdate(const Group &g, int32 rows_global);
   void DropGraphs();
 
   Nnet *nnet_;
@@ -78,6 +84,7 @@ class NnetDataParallel {
   unsigned long long multicast_;
   size_t grad_floats_, flag_off_;
   std::vector<Layer> layers_;             // network order
+  std::vector<Group> groups_;             // network order
   cudaStream_t comm_[2];
   unsigned int *error_pinned_;            // [2]: the error words of the two channels, copied back per step
   bool primed_, last_replayed_;

@@ -258,7 +258,7 @@ static bool GraphsEnabled() {
 
 void NnetMinibatchUpdater::DropGraph() {
   for (size_t i = 0; i < graph_->entries.size(); i++)
-    if (graph_->entries[i].exec) cudaGraphExecDestroy(graph_->entries[i].exec);
+    if (graph_->entries[i].exec) { cudaGraphExecDestroy(graph_->entries[i].exec); CuDevice::Instantiate().GraphDestroyed(); }
   graph_->entries.clear();
   graph_->seen.clear();
 }
@@ -353,9 +353,11 @@ void NnetMinibatchUpdater::TrainStep(const CuMatrixBase<BaseFloat> &feats, const
   }
   cudaGraphExec_t exec = NULL;
   if (ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { ok = false; exec = NULL; }
+  if (ok) CuDevice::Instantiate().GraphRecorded();
+  else CuDevice::Instantiate().CaptureAbandoned();
   if (g) cudaGraphDestroy(g);
   if (graph_->entries.size() >= 4) {                  // oldest out
-    if (graph_->entries[0].exec) cudaGraphExecDestroy(graph_->entries[0].exec);
+    if (graph_->entries[0].exec) { cudaGraphExecDestroy(graph_->entries[0].exec); CuDevice::Instantiate().GraphDestroyed(); }
     graph_->entries.erase(graph_->entries.begin());
   }
   GraphState::Entry e;

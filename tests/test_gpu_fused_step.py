@@ -254,10 +254,12 @@ def test_fused_plan_equals_component_path(cfg):
             assert ya.shape == yb.shape
             if step == 0 and t in ("RectifiedLinearComponent", "MaxpoolComponent", "DropoutComponent") and i < 3:
                 assert np.array_equal(ya, yb), (i, t)          # same GEMM, same bits, exact pooling on top
-            assert rel(ya, yb) <= 2e-5, (step, i, t, rel(ya, yb))
+            # later steps: the two paths sum bias gradients / gate dropout in different (both valid) orders,
+            # a last-bit difference in a weight can land on the other side of a TF32 rounding boundary
+            assert rel(ya, yb) <= (2e-5 if step == 0 else 1e-4), (step, i, t, rel(ya, yb))
     for pa, pb in zip(params(a), params(b)):
         for which in range(3):
-            assert rel(pa[which], pb[which]) <= 2e-5, which
+            assert rel(pa[which], pb[which]) <= 1e-4, which
     ca, sa, da = _counts_and_stats(a)
     cb, sb, db = _counts_and_stats(b)
     assert ca == cb and all(c == 3 * N for c in ca)
@@ -311,6 +313,56 @@ def test_fused_graph_replay_equals_eager_and_is_deterministic():
     for u, v in zip(*results):
         for which in range(3):
             assert np.array_equal(u[which], v[which])
+    kc.set_math_mode(0)
+    kc.use_current_stream()
+
+
+def test_recorded_step_and_later_allocations_do_not_alias():
+    """a recorded step bakes device addresses in.  Everything the step touches is sized before the
+    capture (nothing is pinned in steady state), and memory allocated AFTER the recording -- a second network
+    of the same shapes, which asks the caching allocator for exactly the size classes the first one uses --
+    is not written by replays of the first network's graph."""
+    kc.set_math_mode(1)
+    N = 64
+    rng = np.random.default_rng(9)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        kc.use_current_stream()
+        kc.set_rand_seed(3)
+        a = kc.Nnet.from_config(CFG)
+        x = torch.from_numpy(rng.standard_normal((N, a.input_dim)).astype(np.float32)).cuda()
+        lab = torch.from_numpy(rng.integers(0, a.output_dim, N).astype(np.int32)).cuda()
+        stream.synchronize()
+        for _ in range(3):
+            a.train_step_graph(x, lab)
+        assert a.last_step_replayed
+        assert kc.bytes_pinned_by_graphs() == 0
+        kc.set_rand_seed(4)
+        b = kc.Nnet.from_config(CFG)                     # allocated after a's graph exists
+        held = [kc.Component.from_string(
+            "FullyConnectedComponent input-dim=192 output-dim=256 learning-rate=0.02 param-stddev=0.05 bias-stddev=0.1 "
+            "weight-decay=0.0005 momentum=0.9") for _ in range(4)]
+        stream.synchronize()
+        before_b = params(b)
+        before_h = [g(h.params(0)) for h in held]
+        for _ in range(4):
+            a.train_step_graph(x, lab)                   # replays
+        assert a.last_step_replayed
+        stream.synchronize()
+        for u, v in zip(before_b, params(b)):
+            for which in range(3):
+                assert np.array_equal(u[which], v[which])
+        for u, h in zip(before_h, held):
+            assert np.array_equal(u, g(h.params(0)))
+        # and b trains on its own, recording its own graph, without disturbing a
+        pa = params(a)
+        for _ in range(3):
+            b.train_step_graph(x, lab)
+        stream.synchronize()
+        for u, v in zip(pa, params(a)):
+            for which in range(3):
+                assert np.array_equal(u[which], v[which])
+        assert np.isfinite(a.objf_and_reset()) and np.isfinite(b.objf_and_reset())
     kc.set_math_mode(0)
     kc.use_current_stream()
 
