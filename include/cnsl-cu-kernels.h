@@ -55,6 +55,9 @@ void kcnn_reset_launch_count(void);
  * returns record i: demangled kernel name, label, duration in ms, work, grid. */
 void kcnn_profile_start(void);
 int kcnn_profile_stop(void);
+/* 1 between _start and _stop.  Callers that fork work onto side streams keep everything on ONE stream while
+ * this is set, so that a record is the duration of its kernel alone and not of a kernel sharing the SMs. */
+int kcnn_profile_active(void);
 void kcnn_profile_label(const char *label, double flops, double bytes);
 int kcnn_profile_get(int i, char *kernel, int kernel_len, char *label, int label_len, float *ms,
                      double *flops, double *bytes, unsigned int *grid3);

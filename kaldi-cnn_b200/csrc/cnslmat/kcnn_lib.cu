@@ -136,6 +136,7 @@ void kcnn_profile_start(void) {
   kcnn::g_label.clear();
   kcnn::g_profile_on = true;
 }
+int kcnn_profile_active(void) { return kcnn::g_profile_on ? 1 : 0; }
 int kcnn_profile_stop(void) {
   kcnn::g_profile_on = false;
   cudaDeviceSynchronize();

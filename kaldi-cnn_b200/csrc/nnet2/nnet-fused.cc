@@ -421,6 +421,7 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
   size_t ev = 0;
   auto fork = [&]() -> cudaStream_t {          // work issued on the returned stream runs beside what follows on st
     if (F.side == NULL || ev >= F.fork_ev.size()) return st;
+    if (kcnn_profile_active()) return st;      // per-launch timing: one stream, nothing shares the SMs
     if (cudaEventRecord(F.fork_ev[ev], st) != cudaSuccess || cudaStreamWaitEvent(F.side, F.fork_ev[ev], 0) != cudaSuccess) {
       cudaGetLastError();
       return st;
