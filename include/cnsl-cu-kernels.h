@@ -48,6 +48,9 @@ cudaStream_t kcnn_get_stream(void);
  * reset (bench.py reports it as "gpu_launches"). */
 unsigned long long kcnn_launch_count(void);
 void kcnn_reset_launch_count(void);
+/* Programmatic dependent launch for the library's launches from now on (default on; KCNN_PDL=0 in the
+ * environment disables it for good).  Returns the previous setting. */
+int kcnn_set_pdl(int on);
 /* Per-launch timing for the benchmark's roofline table: between _start and _stop every kernel this
  * library launches (outside stream capture) is bracketed by CUDA events on its stream and tagged with the
  * label and algorithmic FLOPs / bytes announced last by kcnn_profile_label (the work is attributed to the

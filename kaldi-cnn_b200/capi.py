@@ -43,6 +43,7 @@ _PROTOS = {
     "kcnn_profile_start": [],
     "kcnn_profile_stop": [],
     "kcnn_profile_active": [],
+    "kcnn_set_pdl": [I],
     "kcnn_profile_label": [ctypes.c_char_p, ctypes.c_double, ctypes.c_double],
     "kcnn_profile_get": [I, ctypes.c_char_p, I, ctypes.c_char_p, I, ctypes.POINTER(c_float),
                          ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
@@ -132,6 +133,7 @@ _RESTYPES = {
     "kcnn_abi_version": c_int,
     "kcnn_profile_stop": c_int,
     "kcnn_profile_active": c_int,
+    "kcnn_set_pdl": c_int,
     "kcnn_profile_get": c_int,
     "kcnn_conv2d_wgrad_workspace": c_size_t,
     "cudaF_conv2d_backward": c_int,

@@ -49,18 +49,26 @@ void profile_after(cudaStream_t st) {
   g_recs.back().open = false;
 }
 
-bool pdl_enabled() {
+// On by default (KCNN_PDL=0 turns it off for good; kcnn_set_pdl() switches it at run time -- the setting is
+// read at launch, so a recorded graph keeps what it was recorded with).  With the 76-launch step of round 1
+// it LOST 2.5 % (0.859 vs 0.837 ms: the early-scheduled dependents took SM slots from the tail of the running
+// kernel); with the 33 fatter launches of the fused plan it gains 2.6 % (0.641 -> 0.624 ms, identical
+// parameters): the prologue of the next GEMM (tensor-map fetch, barrier init, TMEM allocation) hides under
+// the epilogue of the current one.  The data-parallel trainer switches it OFF for its launches: dependents
+// parked on the SMs get in the way of the communication kernels and of the weight-gradient branch (2 GPUs:
+// 0.823 ms without, 0.969 ms with).
+static int g_pdl = -1;
+static bool pdl_allowed() {
   static int v = -1;
   if (v < 0) {
-    // On by default (KCNN_PDL=0 turns it off).  With the 76-launch step of round 1 it LOST 2.5 % (0.859 vs
-    // 0.837 ms: the early-scheduled dependents took SM slots from the tail of the running kernel); with
-    // the 33 fatter launches of the fused plan it gains 2.6 % (0.641 -> 0.624 ms, identical parameters):
-    // the prologue of the next GEMM (tensor-map fetch, barrier init, TMEM allocation) hides under the
-    // epilogue of the current one.
     const char *e = getenv("KCNN_PDL");
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
+}
+bool pdl_enabled() {
+  if (g_pdl < 0) g_pdl = pdl_allowed() ? 1 : 0;
+  return g_pdl == 1;
 }
 
 namespace {
@@ -135,6 +143,11 @@ void kcnn_profile_start(void) {
   kcnn::g_recs.clear();
   kcnn::g_label.clear();
   kcnn::g_profile_on = true;
+}
+int kcnn_set_pdl(int on) {
+  const int before = kcnn::pdl_enabled() ? 1 : 0;
+  kcnn::g_pdl = (on && kcnn::pdl_allowed()) ? 1 : 0;
+  return before;
 }
 int kcnn_profile_active(void) { return kcnn::g_profile_on ? 1 : 0; }
 int kcnn_profile_stop(void) {

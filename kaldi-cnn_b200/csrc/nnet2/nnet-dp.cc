@@ -15,6 +15,26 @@ namespace nnet2 {
 
 static inline cudaStream_t Str() { return CuDevice::Instantiate().Stream(); }
 
+// Programmatic dependent launch off for everything the trainer launches or records (measured at 2 GPUs:
+// 0.823 ms per step without, 0.969 ms with -- dependents parked on the SMs get in the way of the
+// communication kernels and of the weight-gradient branch); KCNN_DP_PDL=1 keeps the library default.
+namespace {
+struct NoPdl {
+  int before;
+  bool active;
+  NoPdl() : before(1), active(true) {
+    static int keep = -1;
+    if (keep < 0) {
+      const char *e = getenv("KCNN_DP_PDL");
+      keep = (e && e[0] == '1') ? 1 : 0;
+    }
+    active = keep == 0;
+    if (active) before = kcnn_set_pdl(0);
+  }
+  ~NoPdl() { if (active) kcnn_set_pdl(before); }
+};
+}  // namespace
+
 size_t NnetDataParallel::ArenaFloats(NnetMinibatchUpdater *updater) {
   return 2 * updater->GradientFloats() + kcnn_p2p_flag_floats();
 }
@@ -159,6 +179,7 @@ void NnetDataParallel::ForwardBehindUpdates(const CuMatrixBase<BaseFloat> &feats
 }
 
 void NnetDataParallel::Prime(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) {
+  NoPdl no_pdl;
   updater_->ForwardRange(feats, 0, nnet_->NumComponents() - 1, labels_dev);
   updater_->ComputeObjfAndDeriv(labels_dev);
   primed_ = true;
@@ -176,6 +197,7 @@ void NnetDataParallel::RotateEager(const CuMatrixBase<BaseFloat> &feats_next, co
 
 void NnetDataParallel::Rotate(const CuMatrixBase<BaseFloat> &feats_next, const int32 *labels_next,
                               int32 rows_global) {
+  NoPdl no_pdl;
   if (!primed_) KALDI_ERR << "NnetDataParallel::Rotate: Prime() the pipeline with the first batch";
   last_replayed_ = false;
   cudaStream_t st = Str();
@@ -266,6 +288,7 @@ void NnetDataParallel::Rotate(const CuMatrixBase<BaseFloat> &feats_next, const i
 }
 
 void NnetDataParallel::Finish(int32 rows_global) {
+  NoPdl no_pdl;
   if (!primed_) return;
   BackwardWithUpdates(rows_global);
   for (size_t i = 0; i < groups_.size(); i++) CU_SAFE_CALL(cudaStreamWaitEvent(Str(), groups_[i].done, 0));
