@@ -15,20 +15,29 @@ namespace nnet2 {
 
 static inline cudaStream_t Str() { return CuDevice::Instantiate().Stream(); }
 
-// Programmatic dependent launch off for everything the trainer launches or records (measured at 2 GPUs:
-// 0.823 ms per step without, 0.969 ms with -- dependents parked on the SMs get in the way of the
-// communication kernels and of the weight-gradient branch); KCNN_DP_PDL=1 keeps the library default.
+// Programmatic dependent launch only in the FORWARD half of what the trainer launches or records: in the
+// backward half dependents parked on the SMs get in the way of the communication kernels and of the
+// weight-gradient branch.
 namespace {
+// KCNN_DP_PDL: fwd (default) on in the forward half of the rotation only, 0 off everywhere, 1 on everywhere,
+// bwd backward half only.  Measured at 2 GPUs: fwd 0.810 ms, off 0.821 ms, bwd 0.982 ms, on 0.969 ms.
+static int DpPdlMode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("KCNN_DP_PDL");
+    mode = 1;
+    if (e && e[0] == '0') mode = 0;
+    else if (e && e[0] == '1') mode = 3;
+    else if (e && e[0] == 'f') mode = 1;
+    else if (e && e[0] == 'b') mode = 2;
+  }
+  return mode;
+}
 struct NoPdl {
   int before;
   bool active;
-  NoPdl() : before(1), active(true) {
-    static int keep = -1;
-    if (keep < 0) {
-      const char *e = getenv("KCNN_DP_PDL");
-      keep = (e && e[0] == '1') ? 1 : 0;
-    }
-    active = keep == 0;
+  explicit NoPdl(int part = 3) : before(1), active(true) {     // part: 1 forward, 2 backward, 3 both
+    active = (DpPdlMode() & part) != part;
     if (active) before = kcnn_set_pdl(0);
   }
   ~NoPdl() { if (active) kcnn_set_pdl(before); }
@@ -152,6 +161,7 @@ void NnetDataParallel::ReduceAndUpdate(const Group &g, int32 rows_global) {
 }
 
 void NnetDataParallel::BackwardWithUpdates(int32 rows_global) {
+  NoPdl no_pdl(2);
   int32 hi = nnet_->NumComponents() - 1;
   for (size_t i = groups_.size(); i-- > 0;) {                // top group first: the order backward produces them
     const int32 lowest = layers_[groups_[i].first].comp;
@@ -164,6 +174,7 @@ void NnetDataParallel::BackwardWithUpdates(int32 rows_global) {
 }
 
 void NnetDataParallel::ForwardBehindUpdates(const CuMatrixBase<BaseFloat> &feats, const int32 *labels) {
+  NoPdl no_pdl(1);
   const int32 L = nnet_->NumComponents();
   int32 first = 0;
   for (size_t i = 0; i < groups_.size(); i++) {
@@ -179,7 +190,7 @@ void NnetDataParallel::ForwardBehindUpdates(const CuMatrixBase<BaseFloat> &feats
 }
 
 void NnetDataParallel::Prime(const CuMatrixBase<BaseFloat> &feats, const int32 *labels_dev) {
-  NoPdl no_pdl;
+  NoPdl no_pdl(1);
   updater_->ForwardRange(feats, 0, nnet_->NumComponents() - 1, labels_dev);
   updater_->ComputeObjfAndDeriv(labels_dev);
   primed_ = true;
@@ -197,7 +208,6 @@ void NnetDataParallel::RotateEager(const CuMatrixBase<BaseFloat> &feats_next, co
 
 void NnetDataParallel::Rotate(const CuMatrixBase<BaseFloat> &feats_next, const int32 *labels_next,
                               int32 rows_global) {
-  NoPdl no_pdl;
   if (!primed_) KALDI_ERR << "NnetDataParallel::Rotate: Prime() the pipeline with the first batch";
   last_replayed_ = false;
   cudaStream_t st = Str();
@@ -288,7 +298,6 @@ void NnetDataParallel::Rotate(const CuMatrixBase<BaseFloat> &feats_next, const i
 }
 
 void NnetDataParallel::Finish(int32 rows_global) {
-  NoPdl no_pdl;
   if (!primed_) return;
   BackwardWithUpdates(rows_global);
   for (size_t i = 0; i < groups_.size(); i++) CU_SAFE_CALL(cudaStreamWaitEvent(Str(), groups_[i].done, 0));

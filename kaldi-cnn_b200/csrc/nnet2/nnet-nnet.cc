@@ -230,6 +230,18 @@ void NnetMinibatchUpdater::Backward(int32 last, int32 first) {
   if (first < base_) first = base_;       // nothing trains below the Splice front end (nnet2 stops there too)
   grad_stream_ = CuDevice::Instantiate().Stream();
   if (last < first) return;
+  // KCNN_NNET_PDL_BWD=0: programmatic dependent launch in the forward pass only (see nnet-dp.cc: in the
+  // data-parallel rotation the backward half is better off without it)
+  static int pdl_bwd = -1;
+  if (pdl_bwd < 0) {
+    const char *e = getenv("KCNN_NNET_PDL_BWD");
+    pdl_bwd = (e && e[0] == '0') ? 0 : 1;
+  }
+  struct Scope {
+    int before; bool on;
+    explicit Scope(bool off) : before(1), on(off) { if (on) before = kcnn_set_pdl(0); }
+    ~Scope() { if (on) kcnn_set_pdl(before); }
+  } scope(pdl_bwd == 0);
   if (FusedActive()) {
     FusedBackward(last, first);
     return;
