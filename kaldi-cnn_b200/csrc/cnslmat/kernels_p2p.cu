@@ -320,6 +320,7 @@ p2p_reduce_sgd_kernel(Peers pr, float *mc, int rank, int world, SgdBucket k, siz
 // bottom; one launch and two peer barriers instead of six and twelve.  Same per-bucket slices and arithmetic
 // as p2p_reduce_sgd_kernel, bucket after bucket.
 constexpr int kMaxBuckets = 8;
+template <int V> struct IntTag { static constexpr int value = V; };
 struct SgdBucketList {
   SgdBucket b[kMaxBuckets];
   int n;
@@ -339,16 +340,23 @@ p2p_reduce_sgd_multi_kernel(Peers pr, float *mc, int rank, int world, SgdBucketL
     if (t == 0) my_flags[kEpoch + b] = epoch;
     return;
   }
-  for (int j = 0; j < list.n; j++) {
-    const SgdBucket &k = list.b[j];
-    const size_t per = (k.n4 + world - 1) / world;
-    const size_t lo = (size_t)rank * per;
-    const size_t hi = lo + per < k.n4 ? lo + per : k.n4;
-    if (mc != nullptr)   reduce_sgd_slice<1, 8>(pr, mc, rank, world, k, lo, hi, b, G, t);
-    else if (world <= 2) reduce_sgd_slice<2, 4>(pr, mc, rank, world, k, lo, hi, b, G, t);
-    else if (world <= 4) reduce_sgd_slice<4, 2>(pr, mc, rank, world, k, lo, hi, b, G, t);
-    else                 reduce_sgd_slice<8, 1>(pr, mc, rank, world, k, lo, hi, b, G, t);
-  }
+  // (the list is indexed with a run-time j: from shared memory, not from a local copy of the parameters)
+  __shared__ SgdBucket sb[kMaxBuckets];
+  if (t < list.n) sb[t] = list.b[t];
+  __syncthreads();
+  auto all_buckets = [&](auto tag_world, auto tag_u) {
+    for (int j = 0; j < list.n; j++) {
+      const SgdBucket k = sb[j];
+      const size_t per = (k.n4 + world - 1) / world;
+      const size_t lo = (size_t)rank * per;
+      const size_t hi = lo + per < k.n4 ? lo + per : k.n4;
+      reduce_sgd_slice<decltype(tag_world)::value, decltype(tag_u)::value>(pr, mc, rank, world, k, lo, hi, b, G, t);
+    }
+  };
+  if (mc != nullptr)   all_buckets(IntTag<1>(), IntTag<8>());
+  else if (world <= 2) all_buckets(IntTag<2>(), IntTag<4>());
+  else if (world <= 4) all_buckets(IntTag<4>(), IntTag<2>());
+  else                 all_buckets(IntTag<8>(), IntTag<1>());
   __threadfence_system();
   __syncthreads();
   cross_barrier(pr, flag_off, kDone, b, rank, world, epoch, timeout_ns);

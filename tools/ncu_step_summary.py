@@ -38,33 +38,35 @@ def main():
     labels = {}
     for k in read_bench(bench)["step_kernels"]:
         key = (family(k["kernel"]), "x".join(str(g) for g in k.get("grid", [])))
-        labels.setdefault(key, []).append(k["label"])
-    agg = {}
+        labels.setdefault(key, []).append((k["ms"], k["label"]))
+    METRICS = (("time_us", "gpu__time_duration.sum"), ("dram_read_bytes", "dram__bytes_read.sum"),
+               ("dram_write_bytes", "dram__bytes_write.sum"), ("l2_to_sm_bytes", "l1tex__m_xbar2l1tex_read_bytes.sum"),
+               ("lts_pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+               ("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+               ("tensor_pipe_pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+               ("warp_inst", "smsp__inst_executed.sum"))
+    launches = {}
     for r in rows[2:]:
         grid = r[col["Grid Size"]].strip("() ").replace(" ", "").replace(",", "x")
         key = (family(r[col["Kernel Name"]]), grid)
-        if key not in labels:
-            continue
-        a = agg.setdefault(key, {"n": 0, "time_us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0,
-                                 "l2_to_sm_bytes": 0.0, "lts_pct": 0.0, "dram_pct": 0.0, "tensor_pipe_pct": 0.0,
-                                 "warp_inst": 0.0})
-        a["n"] += 1
-        for name, metric in (("time_us", "gpu__time_duration.sum"), ("dram_read_bytes", "dram__bytes_read.sum"),
-                             ("dram_write_bytes", "dram__bytes_write.sum"),
-                             ("l2_to_sm_bytes", "l1tex__m_xbar2l1tex_read_bytes.sum"),
-                             ("lts_pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
-                             ("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
-                             ("tensor_pipe_pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
-                             ("warp_inst", "smsp__inst_executed.sum")):
-            v = val(r, metric)
-            if v is not None:
-                a[name] += v
+        if key in labels:
+            launches.setdefault(key, []).append({name: (val(r, metric) or 0.0) for name, metric in METRICS})
     out = []
-    for key, a in agg.items():
-        n = a.pop("n")
-        row = {"kernel": "%s [%s]" % (" / ".join(sorted(set(labels[key]))), key[0]), "grid": key[1], "launches": n}
-        row.update({k: v / n for k, v in a.items()})
-        out.append(row)
+    for key, ls in launches.items():
+        names = sorted(labels[key], reverse=True)                 # longest first (bench event timing)
+        ls.sort(key=lambda a: -a["time_us"])                      # longest first (ncu)
+        # several layers can share one kernel family + grid (the persistent weight-gradient kernel always
+        # launches one CTA per SM): pair them up by duration rank when the counts allow it
+        if len(names) > 1 and len(ls) % len(names) == 0:
+            per = len(ls) // len(names)
+            groups = [([names[i][1]], ls[i * per:(i + 1) * per]) for i in range(len(names))]
+        else:
+            groups = [(sorted(set(n for _, n in names)), ls)]
+        for lab, g in groups:
+            row = {"kernel": "%s [%s]" % (" / ".join(lab), key[0]), "grid": key[1], "launches": len(g)}
+            for name, _ in METRICS:
+                row[name] = sum(a[name] for a in g) / len(g)
+            out.append(row)
     out.sort(key=lambda r: -r["time_us"] * r["launches"])
     json.dump(out, sys.stdout, indent=1)
     print()
