@@ -127,21 +127,33 @@ class NativeDataParallel:
         self._check(self.lib.kcnn_nnet_dp_prime(self.h, ctypes.c_void_p(feats.data_ptr()), d.rows, d.stride,
                                                 ctypes.c_void_p(labels.data_ptr())))
 
+    def _raise_if_failed(self, synchronise):
+        """A peer barrier timed out on this rank (a peer is missing or stalled for longer than
+        KCNN_P2P_TIMEOUT_MS): the update of that step was skipped, the replicas may have diverged.  The
+        asynchronous form reads the error words the trainer copies to pinned memory with every rotation --
+        no synchronisation, so it reports a failure one or two steps late but every step."""
+        if self.failed(synchronise):
+            raise RuntimeError("kaldi-cnn_b200 data parallel: a peer-memory barrier timed out on rank %d; "
+                               "the step's update was skipped and the replicas may have diverged" % self.dist.get_rank())
+
     def rotate(self, feats_next, labels_next, rows_global):
         import ctypes
         from . import capi
         d = capi.mdim(feats_next)
         self._check(self.lib.kcnn_nnet_dp_rotate(self.h, ctypes.c_void_p(feats_next.data_ptr()), d.rows, d.stride,
                                                  ctypes.c_void_p(labels_next.data_ptr()), int(rows_global)))
+        self._raise_if_failed(False)
 
     def finish(self, rows_global):
         self._check(self.lib.kcnn_nnet_dp_finish(self.h, int(rows_global)))
+        self._raise_if_failed(True)
 
     def train_minibatch_host_async(self, feats_np, labels_np, rows_global):
         import ctypes
         self._check(self.lib.kcnn_nnet_dp_train_minibatch_host_async(
             self.h, feats_np.ctypes.data_as(ctypes.c_void_p), labels_np.ctypes.data_as(ctypes.c_void_p),
             labels_np.shape[0], int(rows_global)))
+        self._raise_if_failed(False)
 
     def failed(self, synchronise=True):
         return bool(self.lib.kcnn_nnet_dp_failed(self.h, int(synchronise)))
@@ -421,3 +433,8 @@ class PipelinedDataParallelStep:
                 w.wait()
             net.apply_component_gradient(c, rows_global)
         self.primed = False
+        # a barrier of the peer-memory all-reduce that gave up leaves an error mark: check it at
+        # every synchronisation point of the pipeline
+        if self.peer is not None and self.peer.failed():
+            raise RuntimeError("kaldi-cnn_b200 data parallel: a peer-memory barrier timed out; the reduced "
+                               "gradients of that step are not valid")

@@ -139,6 +139,7 @@ def _pipelined_worker(rank, world, port, n_global, out):
         for x, y in batches[1:]:
             step.rotate(x[b:e], y[b:e], n_global)
         step.finish(n_global)
+        assert peer.polled >= 1
         np.savez(os.path.join(out, "prank%d.npz" % rank), k=net.k, kb=net.kb, w=net.w, wb=net.wb, kp=net.kp)
     finally:
         dist.destroy_process_group()
@@ -273,6 +274,10 @@ class _FakePeer:
     def all_reduce(self, offset, length, channel=0):
         self.calls.append((int(offset), int(length), int(channel)))
         return dist.all_reduce(self.arena[offset:offset + length], async_op=True)
+
+    def failed(self):
+        self.polled = getattr(self, "polled", 0) + 1      # the step must ask at its synchronisation points
+        return False
 
 
 def _peer_worker(rank, world, port, n_global, out):
