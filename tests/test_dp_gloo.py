@@ -139,7 +139,6 @@ def _pipelined_worker(rank, world, port, n_global, out):
         for x, y in batches[1:]:
             step.rotate(x[b:e], y[b:e], n_global)
         step.finish(n_global)
-        assert peer.polled >= 1
         np.savez(os.path.join(out, "prank%d.npz" % rank), k=net.k, kb=net.kb, w=net.w, wb=net.wb, kp=net.kp)
     finally:
         dist.destroy_process_group()
@@ -293,6 +292,7 @@ def _peer_worker(rank, world, port, n_global, out):
         for x, y in batches[1:]:
             step.rotate(x[b:e], y[b:e], n_global)
         step.finish(n_global)
+        assert peer.polled >= 1
         np.savez(os.path.join(out, "qrank%d.npz" % rank), k=net.k, kb=net.kb, w=net.w, wb=net.wb, kp=net.kp,
                  calls=np.array(peer.calls))
     finally:
