@@ -480,7 +480,7 @@ def run_ours(args):
             # broadcast kernel per layer.  auto: in-switch (NVLS) form from 4 GPUs when a multicast mapping can be
             # had, else the two-shot form over CUDA-IPC peer memory; all ranks agree through one MIN all-reduce.
             from kaldi_cnn_b200.dp import NativeDataParallel
-            modes = {"auto": ["nvls", "ipc"] if world > 2 else ["ipc"], "nvls": ["nvls"], "p2p": ["ipc"], "ipc": ["ipc"]}[args.dp_reduce]
+            modes = {"auto": ["ipc"], "nvls": ["nvls"], "p2p": ["ipc"], "ipc": ["ipc"]}[args.dp_reduce]
             for mode in modes:
                 try:
                     dp = NativeDataParallel(net, dist, multicast=mode == "nvls")
