@@ -233,12 +233,12 @@ __device__ __forceinline__ void sgd4(float4 &w, float4 &p, const float4 &g, cons
 // 2 U loads of (W, prev) are issued before the first add -- a peer load over NVLink takes ~2 us, so the
 // bytes in flight per SM decide the link throughput (measured at 2 GPUs: U = 2 with a serial loop over the
 // ranks kept ~0.5 MB in flight per GPU and moved ~260 GB/s).  Sum order = rank order, as in the all-reduce.
-template <int kWorld, int U>
+template <int kWorld, int U, int kT = kThreads>
 __device__ __forceinline__ void reduce_sgd_slice(const Peers &pr, float *mc, int rank, int world, const SgdBucket &k,
                                                  size_t lo, size_t hi, int b, int G, int t) {
-  const size_t step = (size_t)G * kThreads;
+  const size_t step = (size_t)G * kT;
   float *wmine = pr.buf[rank] + k.off + k.param_delta;
-  for (size_t i0 = lo + (size_t)b * kThreads + t; i0 < hi; i0 += U * step) {
+  for (size_t i0 = lo + (size_t)b * kT + t; i0 < hi; i0 += U * step) {
     float4 v[U][kWorld], w[U], p[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -363,6 +363,52 @@ p2p_reduce_sgd_multi_kernel(Peers pr, float *mc, int rank, int world, SgdBucketL
   if (t == 0) my_flags[kEpoch + b] = epoch;
 }
 
+// "Light" form of the two kernels above: 256 threads and at most 64 registers per thread (16 K registers per
+// CTA, no shared memory to speak of), so that a communication CTA fits on an SM NEXT TO a GEMM CTA (192 threads
+// x 118 registers, ~200 KB of shared memory).  The 512-thread form needs 124 registers per thread -- a whole
+// SM's register file per CTA -- and can only run where no GEMM CTA is resident.  Fewer loads in flight per
+// thread (U halved); twice the CTAs.  Measured (step, ms): 2 GPUs 0.780 -> 0.766, 8 GPUs 0.870 -> 0.845.
+// The default; KCNN_P2P_LIGHT=0 selects the 512-thread form.
+constexpr int kLightThreads = 256;
+
+template <bool kMulti>
+__global__ void __launch_bounds__(kLightThreads, 4)
+p2p_reduce_sgd_light_kernel(Peers pr, float *mc, int rank, int world, SgdBucketList list, size_t flag_off,
+                            unsigned long long timeout_ns) {
+  kcnn::pdl_wait();
+  const int b = blockIdx.x, G = gridDim.x, t = threadIdx.x;
+  __shared__ uint32_t s_epoch;
+  __shared__ SgdBucket sb[kMaxBuckets];
+  uint32_t *my_flags = reinterpret_cast<uint32_t *>(pr.buf[rank] + flag_off);
+  if (t == 0) s_epoch = my_flags[kEpoch + b] + 1u;
+  if (t < list.n) sb[t] = list.b[t];
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  if (!cross_barrier(pr, flag_off, kReady, b, rank, world, epoch, timeout_ns)) {
+    if (t == 0) my_flags[kEpoch + b] = epoch;
+    return;
+  }
+  auto all_buckets = [&](auto tag_world, auto tag_u) {
+    const int n = kMulti ? list.n : 1;
+    for (int j = 0; j < n; j++) {
+      const SgdBucket k = sb[j];
+      const size_t per = (k.n4 + world - 1) / world;
+      const size_t lo = (size_t)rank * per;
+      const size_t hi = lo + per < k.n4 ? lo + per : k.n4;
+      reduce_sgd_slice<decltype(tag_world)::value, decltype(tag_u)::value, kLightThreads>(pr, mc, rank, world, k, lo, hi,
+                                                                                          b, G, t);
+    }
+  };
+  if (mc != nullptr)   all_buckets(IntTag<1>(), IntTag<4>());
+  else if (world <= 2) all_buckets(IntTag<2>(), IntTag<2>());
+  else if (world <= 4) all_buckets(IntTag<4>(), IntTag<1>());
+  else                 all_buckets(IntTag<8>(), IntTag<1>());
+  __threadfence_system();
+  __syncthreads();
+  cross_barrier(pr, flag_off, kDone, b, rank, world, epoch, timeout_ns);
+  if (t == 0) my_flags[kEpoch + b] = epoch;
+}
+
 }  // namespace p2p
 }  // namespace kcnn
 
@@ -380,6 +426,15 @@ static unsigned long long p2p_timeout_ns() {
     if (v < 1) v = 1;
   }
   return (unsigned long long)v * 1000000ull;
+}
+
+static bool p2p_light() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("KCNN_P2P_LIGHT");          // default on; 0 selects the 512-thread form
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 static int p2p_max_ctas() {
@@ -433,9 +488,22 @@ int kcnn_p2p_reduce_sgd_f32(void *stream, const unsigned long long *peer_bases, 
   k.off = offset_floats; k.n4 = count_floats >> 2; k.w4 = weight_floats >> 2; k.param_delta = param_delta_floats;
   k.prev = prev_grad; k.momentum = momentum; k.a_decay = decay_alpha; k.a_grad = grad_alpha;
   const size_t per = (k.n4 + world - 1) / world;
+  const int max_ctas = p2p_max_ctas();
+  if (p2p_light()) {
+    p2p::SgdBucketList list;
+    list.b[0] = k;
+    list.n = 1;
+    size_t want = (per + p2p::kLightThreads * 2 - 1) / (p2p::kLightThreads * 2);
+    if (want < 1) want = 1;
+    const size_t cap = (size_t)(2 * max_ctas < p2p::kMaxCtas ? 2 * max_ctas : p2p::kMaxCtas);
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    KCNN_LAUNCH(p2p::p2p_reduce_sgd_light_kernel<false>, grid, p2p::kLightThreads, 0, st, pr,
+                reinterpret_cast<float *>(static_cast<uintptr_t>(multicast_base)), rank, world, list,
+                flag_offset_floats + (size_t)channel * p2p::kChannelWords, p2p_timeout_ns());
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   size_t want = (per + p2p::kThreads * 2 - 1) / (p2p::kThreads * 2);
   if (want < 1) want = 1;
-  const int max_ctas = p2p_max_ctas();
   const unsigned grid = (unsigned)(want < (size_t)max_ctas ? want : (size_t)max_ctas);
   KCNN_LAUNCH(p2p::p2p_reduce_sgd_kernel, grid, p2p::kThreads, 0, st, pr,
               reinterpret_cast<float *>(static_cast<uintptr_t>(multicast_base)), rank, world, k,
@@ -468,9 +536,19 @@ int kcnn_p2p_reduce_sgd_multi_f32(void *stream, const unsigned long long *peer_b
     if (per > largest) largest = per;
   }
   if (list.n == 0) return 0;
+  const int max_ctas = p2p_max_ctas();
+  if (p2p_light()) {
+    size_t want = (largest + p2p::kLightThreads * 2 - 1) / (p2p::kLightThreads * 2);
+    if (want < 1) want = 1;
+    const size_t cap = (size_t)(2 * max_ctas < p2p::kMaxCtas ? 2 * max_ctas : p2p::kMaxCtas);
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    KCNN_LAUNCH(p2p::p2p_reduce_sgd_light_kernel<true>, grid, p2p::kLightThreads, 0, st, pr,
+                reinterpret_cast<float *>(static_cast<uintptr_t>(multicast_base)), rank, world, list,
+                flag_offset_floats + (size_t)channel * p2p::kChannelWords, p2p_timeout_ns());
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   size_t want = (largest + p2p::kThreads * 2 - 1) / (p2p::kThreads * 2);
   if (want < 1) want = 1;
-  const int max_ctas = p2p_max_ctas();
   const unsigned grid = (unsigned)(want < (size_t)max_ctas ? want : (size_t)max_ctas);
   KCNN_LAUNCH(p2p::p2p_reduce_sgd_multi_kernel, grid, p2p::kThreads, 0, st, pr,
               reinterpret_cast<float *>(static_cast<uintptr_t>(multicast_base)), rank, world, list,
