@@ -99,40 +99,89 @@ def base_config(args, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons DURING the timed region: NVML polled from a thread (a
+    timed region of a few milliseconds still gets samples; `nvidia-smi -lms 100` as a subprocess, the
+    recipe's form, needs hundreds of milliseconds to produce its first line and is the fallback)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.samples, self.stop_flag, self.thread, self.nvml, self.handle = gpu_index, [], False, None, None, None
+        self.smi = None
+
+    def _handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        self.nvml = pynvml
+        try:
+            pr = torch.cuda.get_device_properties(self.gpu)
+            bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            return pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        k = 0
+        while not self.stop_flag:
+            try:                                      # two NVML calls per sample (each costs a few ms); power less often
+                clk = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                if k % 4 == 0:
+                    self.power = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((clk, self.max_clock, self.power, why))
+            except Exception:
+                pass
+            k += 1
+            time.sleep(0.001)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            self.handle = self._handle()
+            self.max_clock = self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+            self.power = self.nvml.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.thread = None
+            try:                      # fallback: the subprocess form
+                q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                     "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.smi = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                             "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                            stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.smi = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(x[0] for x in self.samples)
+            reasons = set()
+            for x in self.samples:
+                for bit, name in self.REASONS:
+                    if x[3] & bit:
+                        reasons.add(name)
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None,
+                    "sm_max_mhz": float(max(x[1] for x in self.samples)) if self.samples else None,
+                    "power_w_max": max(x[2] for x in self.samples) if self.samples else None,
+                    "samples": len(sm), "reasons": sorted(reasons), "source": "NVML polled from a thread inside the timed region"}
+        if self.smi is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML and nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.smi.terminate()
         try:
-            self.proc.wait(timeout=2)
+            out = self.smi.communicate(timeout=2)[0]
         except Exception:
-            self.proc.kill()
+            self.smi.kill()
+            out = ""
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in out.splitlines():
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -145,7 +194,8 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 100"}
 
 
 def peaks():

@@ -42,6 +42,7 @@
 #define KCNN_GEMM_TMA_CUH_
 
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm_tc.cuh"
 
@@ -1010,7 +1011,15 @@ void launch_persistent(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap
     attr_set = true;
   }
   long long total = (long long)tiles.x * tiles.y * tiles.z;
-  unsigned ctas = (unsigned)(total < kNumSMs ? total : kNumSMs);
+  // KCNN_TMA_PERSIST_CTAS: fewer than one CTA per SM leaves SMs to whatever runs beside this kernel (in the
+  // training step: the input-gradient chain on the compute stream while this runs on the side branch)
+  static int cap = -1;
+  if (cap < 0) {
+    const char *e = getenv("KCNN_TMA_PERSIST_CTAS");
+    cap = e ? atoi(e) : kNumSMs;
+    if (cap < 1 || cap > kNumSMs) cap = kNumSMs;
+  }
+  unsigned ctas = (unsigned)(total < cap ? total : cap);
   launch_kernel(kernel, dim3(ctas), dim3(THREADS), (size_t)PRing::SMEM_TOTAL, st, 1u, ma, mb, p, (int)tiles.x,
                 (int)tiles.y, (int)tiles.z);
 }
