@@ -100,8 +100,9 @@ def base_config(args, world):
 
 class ClockSampler:
     """SM clock, power and throttle reasons DURING the timed region: NVML polled from a thread (a
-    timed region of a few milliseconds still gets samples; `nvidia-smi -lms 100` as a subprocess, the
-    recipe's form, needs hundreds of milliseconds to produce its first line and is the fallback)."""
+    timed region of a few milliseconds still gets its sample: the first is taken as the region starts;
+    `nvidia-smi -lms 100` as a subprocess, the recipe's form, needs hundreds of milliseconds to produce
+    its first line and is the fallback)."""
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
@@ -122,20 +123,29 @@ class ClockSampler:
             idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
             return pynvml.nvmlDeviceGetHandleByIndex(idx)
 
-    def _poll(self):
+    def _sample(self):
         n, h = self.nvml, self.handle
-        k = 0
+        try:
+            clk = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+            why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.samples.append((clk, self.max_clock, self.power, why, time.perf_counter()))
+        except Exception:
+            pass
+
+    def _poll(self):
+        # NOT a tight loop: at a 1 - 2 ms period the queries themselves slowed a 2-GPU step from 0.77 to 1.58 ms,
+        # and even ONE query inside a 38 ms region cost 0.1 ms per step (it stalls the queried GPU for a few
+        # ms, and one slow rank stalls every peer barrier).  First sample now (the caller has warm-up steps in
+        # flight), then one every 250 ms.
         while not self.stop_flag:
-            try:                                      # two NVML calls per sample (each costs a few ms); power less often
-                clk = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
-                why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                if k % 4 == 0:
-                    self.power = n.nvmlDeviceGetPowerUsage(h) / 1000.0
-                self.samples.append((clk, self.max_clock, self.power, why))
-            except Exception:
-                pass
-            k += 1
-            time.sleep(0.001)
+            self._sample()
+            for _ in range(250):
+                if self.stop_flag:
+                    break
+                time.sleep(0.001)
+
+    def mark_region(self):
+        self.region_t0 = time.perf_counter()
 
     def start(self):
         try:
@@ -158,8 +168,16 @@ class ClockSampler:
 
     def stop(self):
         if self.thread is not None:
+            t_end = time.perf_counter()
             self.stop_flag = True
             self.thread.join(timeout=1.0)
+            self._sample()                               # right after the timed region
+            try:
+                self.power = max(self.power, self.nvml.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:
+                pass
+            t0 = getattr(self, "region_t0", 0.0)
+            inside = sum(1 for x in self.samples if t0 <= x[4] <= t_end)
             sm = sorted(x[0] for x in self.samples)
             reasons = set()
             for x in self.samples:
@@ -168,8 +186,11 @@ class ClockSampler:
                         reasons.add(name)
             return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None,
                     "sm_max_mhz": float(max(x[1] for x in self.samples)) if self.samples else None,
-                    "power_w_max": max(x[2] for x in self.samples) if self.samples else None,
-                    "samples": len(sm), "reasons": sorted(reasons), "source": "NVML polled from a thread inside the timed region"}
+                    "power_w_max": self.power,
+                    "samples": len(sm), "samples_inside_timed_region": inside, "reasons": sorted(reasons),
+                    "source": "NVML: one sample under the load of the last warm-up steps, one every 250 ms inside "
+                              "the timed region, one right after it (a query stalls the queried GPU for a few ms, "
+                              "so none is forced into a short region)"}
         if self.smi is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML and nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -576,13 +597,21 @@ def run_ours(args):
                 step()
         else:
             launches_per_step = None
+        # Clocks: the first sample is taken while a last batch of warm-up steps is running (the GPU is under
+        # the load of the timed loop, but an NVML query costs the queried GPU a few ms -- see ClockSampler --
+        # so it must not land in a timed region that may be only 12 ms long), further samples every 250 ms
+        # inside the timed region, the last one right after it.
+        sampler = ClockSampler(local)
+        for _ in range(8):
+            step()
+            post_step()
+        if rank == 0:
+            sampler.start()
         stream.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
+        sampler.mark_region()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
