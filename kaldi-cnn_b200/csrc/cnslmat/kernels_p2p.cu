@@ -9,8 +9,10 @@
 // hold most of an SM's shared memory, so the concurrent GEMMs (one ~200 KB CTA per SM, grids of
 // 128 / 148 CTAs) lose SMs and fall into a second wave: measured at 2 GPUs, 0.83 ms for the
 // step without the reduction vs 1.04 ms with it, and fewer channels only make the reduction the
-// critical path (NCCL_MAX_CTAS = 8: 1.24 ms).  The kernel below needs no shared memory and 32
-// registers per thread, so its CTAs co-reside with the GEMM CTAs instead of displacing them.
+// critical path (NCCL_MAX_CTAS = 8: 1.24 ms).  The kernels below need (next to) no shared memory and
+// at most 64 registers per thread, so their CTAs co-reside with the GEMM CTAs instead of displacing them
+// (the one variant that did not -- 124 registers x 512 threads -- is kept behind KCNN_P2P_LIGHT=0 and is
+// 3 % slower per step at 8 GPUs).
 //
 // Algorithm (two-shot, every byte crosses NVLink once in each direction):
 //   every rank's gradient arena lives at the same offset of a symmetric allocation whose
