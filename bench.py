@@ -579,8 +579,16 @@ def run_ours(args):
             else:
                 dp.rotate(feats[k], labels[k], N * world)      # NnetDataParallel::Rotate: eager, record, replay
 
+        dp_launches_per_step = None
         if dp is not None:
             dp.prime(feats[nbuf - 1], labels[nbuf - 1])
+            # launches of one rotation, counted by the library on the FIRST one: NnetDataParallel::Rotate runs a
+            # buffer's first rotation eagerly (the recorded graph later replays exactly those kernels)
+            L.kcnn_reset_launch_count()
+            step()
+            post_step()
+            if not dp.last_rotate_replayed:
+                dp_launches_per_step = int(L.kcnn_launch_count())
         for _ in range(2 * nbuf + warm):          # every buffer: one eager step, one recorded, then replays
             step()
             post_step()
@@ -596,7 +604,7 @@ def run_ours(args):
             for _ in range(2 * nbuf):
                 step()
         else:
-            launches_per_step = None
+            launches_per_step = dp_launches_per_step
         # Clocks: the first sample is taken while a last batch of warm-up steps is running (the GPU is under
         # the load of the timed loop, but an NVML query costs the queried GPU a few ms -- see ClockSampler --
         # so it must not land in a timed region that may be only 12 ms long), further samples every 250 ms
