@@ -221,7 +221,7 @@ int kcnn_nnet_train_minibatch_host_async(kcnn_nnet *n, const float *feats_host, 
 double kcnn_nnet_running_objf(kcnn_nnet *n);
 /* The same step on DEVICE buffers, asynchronous on the compute stream (read the objective
  * with kcnn_nnet_objf_and_reset).  Both calls go through NnetMinibatchUpdater::TrainStep: on a
- * non-default compute stream the ~85 launches of a step are recorded into a CUDA graph on the
+ * non-default compute stream the launches of a step (33 for the benchmarked model) are recorded into a CUDA graph on the
  * second call with the same buffers / configuration and replayed from then on
  * (KCNN_NNET_GRAPH=0 keeps every step eager). */
 int kcnn_nnet_train_step(kcnn_nnet *n, const float *feats, int rows, int stride, const int *labels);

@@ -73,7 +73,7 @@ class NnetMinibatchUpdater {
   void Backward(int32 last = -1, int32 first = 0);
   /// One whole training step on device buffers: Forward(feats), ComputeObjfAndDeriv(labels),
   /// Backward() -- what NnetUpdater does per minibatch.  The first call for a given (feats,
-  /// labels, configuration) runs the ~85 launches eagerly (buffers and scratch get sized); the
+  /// labels, configuration) runs the launches eagerly (buffers and scratch get sized); the
   /// second captures them into a CUDA graph; from then on a step is ONE cudaGraphLaunch.  The
   /// graph is dropped and re-captured when the buffers or any component's StepSignature()
   /// (parameter addresses, learning rate, momentum, ...) change.  Needs a non-default compute
