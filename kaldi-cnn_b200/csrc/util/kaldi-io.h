@@ -25,7 +25,7 @@ template <class C>
 void ReadKaldiObject(const std::string &filename, C *c) {
   std::ifstream is(filename.c_str(), std::ios::binary);
   if (!is.is_open()) KALDI_ERR << "Could not open " << filename;
-  bool binary;
+  bool binary = false;
   if (!InitKaldiInputStream(is, &binary)) KALDI_ERR << "Bad header in " << filename;
   c->Read(is, binary);
 }
