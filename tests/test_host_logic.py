@@ -204,3 +204,134 @@ def test_peer_memory_launchers_validate_their_arguments(L):
     assert call(3, 2, 0, 1024, 1024, 4096, 0) == -1
     assert call(0, 2, 0, 0, 0, 4096, 0) == 0
     assert L.kcnn_p2p_allreduce_multicast_f32(None, bases, ctypes.c_ulonglong(0), 0, 2, 0, 1024, 4096, 0) == -1
+
+
+# ---- the element-wise glue of the C2 model: no parameters, so the host side runs here ----
+
+def _i32(v):
+    import struct
+    return b"\x04" + struct.pack("<i", v)
+
+
+def _f32(v):
+    import struct
+    return b"\x04" + struct.pack("<f", v)
+
+
+def _nonlinear_stream(kind, dim, binary):
+    """NonlinearComponent::Write (nnet2/nnet-component.cc:398-412) of a component that has not seen data: empty
+    double-precision statistics vectors ("DV" + int32 0 in binary mode, " [ ]\\n" in text mode), count 0.0."""
+    if binary:
+        return (b"<%s> <Dim> " % kind + _i32(dim) + b"<ValueSum> DV " + _i32(0) + b"<DerivSum> DV " + _i32(0) +
+                b"<Count> \x08" + b"\x00" * 8 + b"</%s> " % kind)
+    return b"<%s> <Dim> %d <ValueSum>  [ ]\n<DerivSum>  [ ]\n<Count> 0 </%s> " % (kind, dim, kind)
+
+
+@pytest.mark.parametrize("kind, dim", [(b"RectifiedLinearComponent", 256), (b"SoftmaxComponent", 3454),
+                                       (b"NormalizeComponent", 32)])
+def test_nonlinear_components_host_side(L, kind, dim):
+    h = new(L, "%s dim=%d" % (kind.decode(), dim))                    # InitFromString :418-427
+    assert h, err(L)
+    assert L.kcnn_component_type(ctypes.c_void_p(h)) == kind
+    assert L.kcnn_component_input_dim(ctypes.c_void_p(h)) == dim == L.kcnn_component_output_dim(ctypes.c_void_p(h))
+    for binary in (False, True):
+        want = _nonlinear_stream(kind, dim, binary)
+        assert write(L, h, binary) == want
+        r = L.kcnn_component_read(want, len(want), int(binary))
+        assert r, err(L)
+        assert write(L, r, not binary) == _nonlinear_stream(kind, dim, not binary)
+        L.kcnn_component_delete(ctypes.c_void_p(r))
+    L.kcnn_component_delete(ctypes.c_void_p(h))
+    assert not new(L, "%s dim=%d extra=1" % (kind.decode(), dim))
+    assert "Invalid initializer for layer of type " + kind.decode() in err(L)
+    assert not new(L, kind.decode())
+    assert "Invalid initializer" in err(L)
+
+
+def test_dropout_component_host_side(L):
+    """DropoutComponent::InitFromString / Write (nnet2/nnet-component.cc:3548-3581): <Dim>, <DropoutScale>,
+    <DropoutProportion> in that order; defaults dropout-proportion 0.5, dropout-scale 0."""
+    h = new(L, "DropoutComponent dim=16 dropout-proportion=0.2 dropout-scale=0.5")
+    assert h, err(L)
+    assert write(L, h, False) == b"<DropoutComponent> <Dim> 16 <DropoutScale> 0.5 <DropoutProportion> 0.2 </DropoutComponent> "
+    assert write(L, h, True) == (b"<DropoutComponent> <Dim> " + _i32(16) + b"<DropoutScale> " + _f32(0.5) +
+                                 b"<DropoutProportion> " + _f32(0.2) + b"</DropoutComponent> ")
+    # BackpropNeedsInput / Output: the backward pass is d * y / x (:3634-3636)
+    assert L.kcnn_component_backprop_needs_input(ctypes.c_void_p(h)) == 1
+    assert L.kcnn_component_backprop_needs_output(ctypes.c_void_p(h)) == 1
+    L.kcnn_component_delete(ctypes.c_void_p(h))
+    d = new(L, "DropoutComponent dim=16")                  # defaults: proportion 0.5, scale 0 (:3551)
+    assert d, err(L)
+    assert write(L, d, False) == b"<DropoutComponent> <Dim> 16 <DropoutScale> 0 <DropoutProportion> 0.5 </DropoutComponent> "
+    L.kcnn_component_delete(ctypes.c_void_p(d))
+    for bad in ("DropoutComponent dropout-proportion=0.2", "DropoutComponent dim=0", "DropoutComponent dim=16 keep=1"):
+        assert not new(L, bad)
+        assert "Invalid initializer for layer of type DropoutComponent" in err(L)
+
+
+def test_splice_component_host_side(L):
+    """SpliceComponent::InitFromString / Write (nnet2/nnet-component.cc:2549-2572, 2854-2863): left / right
+    context expands to consecutive offsets, `context=` takes an explicit list, const-component-dim columns are
+    not spliced; output-dim = (input-dim - const) * |context| + const."""
+    h = new(L, "SpliceComponent input-dim=40 left-context=10 right-context=10")     # egs/exp/nnet/nnet.config:1
+    assert h, err(L)
+    assert L.kcnn_component_input_dim(ctypes.c_void_p(h)) == 40
+    assert L.kcnn_component_output_dim(ctypes.c_void_p(h)) == 40 * 21
+    ctx = " ".join(str(i) for i in range(-10, 11))
+    assert write(L, h, False) == ("<SpliceComponent> <InputDim> 40 <Context> [ %s ]\n<ConstComponentDim> 0 "
+                                  "</SpliceComponent> " % ctx).encode()
+    L.kcnn_component_delete(ctypes.c_void_p(h))
+    g = new(L, "SpliceComponent input-dim=40 context=-2:0:3 const-component-dim=4")
+    assert g, err(L)
+    assert L.kcnn_component_output_dim(ctypes.c_void_p(g)) == 36 * 3 + 4
+    import struct
+    want = (b"<SpliceComponent> <InputDim> " + _i32(40) + b"<Context> " + _i32(3) + struct.pack("<iii", -2, 0, 3) +
+            b"<ConstComponentDim> " + _i32(4) + b"</SpliceComponent> ")
+    assert write(L, g, True) == want
+    r = L.kcnn_component_read(want, len(want), 1)
+    assert r, err(L)
+    assert write(L, r, False) == b"<SpliceComponent> <InputDim> 40 <Context> [ -2 0 3 ]\n<ConstComponentDim> 4 </SpliceComponent> "
+    L.kcnn_component_delete(ctypes.c_void_p(r))
+    L.kcnn_component_delete(ctypes.c_void_p(g))
+    for bad in ("SpliceComponent input-dim=40", "SpliceComponent left-context=1 right-context=1",
+                "SpliceComponent input-dim=0 left-context=1 right-context=1",
+                "SpliceComponent input-dim=40 left-context=1 right-context=1 more=1"):
+        assert not new(L, bad)
+        assert "Invalid initializer for layer of type SpliceComponent" in err(L), err(L)
+
+
+def test_chunk_info_checks_come_before_the_device(L):
+    """ChunkInfo::CheckSize / Check (nnet2/nnet-component.cc:2580-2622): MaxpoolComponent::Propagate checks both
+    matrices against their ChunkInfo first (nnet0/nnet-component-nnet0.cc:874-875) -- a wrong chunk count or an
+    inverted offset range is an assertion, a consistent call reaches the device layer (and fails: none here)."""
+    h = ctypes.c_void_p(new(L, POOL))
+    x = (ctypes.c_float * (8 * 1024))()
+    y = (ctypes.c_float * (8 * 256))()
+    assert L.kcnn_component_propagate(h, 3, x, 4, 1024, 1024, y, 4, 256, 256) == -1      # 4 rows are not 3 chunks
+    assert "CheckSize" in err(L)
+    assert L.kcnn_component_propagate_chunks(h, 2, 0, 2, 0, 1, x, 4, 1024, 1024, y, 4, 256, 256) == -1
+    assert "CheckSize" in err(L)                                                       # 2 chunks x 3 frames != 4 rows
+    assert L.kcnn_component_propagate_chunks(h, 2, 1, 0, 0, 1, x, 4, 1024, 1024, y, 4, 256, 256) == -1
+    assert "KALDI_ASSERT" in err(L)                                                    # last offset < first offset
+    assert L.kcnn_component_propagate_chunks(h, 2, 0, 1, 0, 1, x, 4, 1024, 1024, y, 4, 256, 256) == -1
+    assert "no CUDA device is selected" in err(L)                                      # consistent: reaches the device
+    L.kcnn_component_delete(h)
+
+
+def test_model_with_only_glue_parses_like_nnet_config(L):
+    """Nnet::Init over config text: one component per line, '#' comments and blank lines skipped, dimensions
+    must chain (Nnet::Check), skip_splice drops the SpliceComponent line."""
+    cfg = ("# front end\nSpliceComponent input-dim=40 left-context=10 right-context=10\n\n"
+           "RectifiedLinearComponent dim=840\nNormalizeComponent dim=840\nSoftmaxComponent dim=840\n")
+    n = L.kcnn_nnet_new_from_config(cfg.encode(), 0)
+    assert n, err(L)
+    assert L.kcnn_nnet_num_components(ctypes.c_void_p(n)) == 4
+    assert L.kcnn_nnet_input_dim(ctypes.c_void_p(n)) == 40 and L.kcnn_nnet_output_dim(ctypes.c_void_p(n)) == 840
+    # (kcnn_nnet_frames_per_example belongs to the updater, which owns streams and buffers: device only)
+    assert L.kcnn_nnet_frames_per_example(ctypes.c_void_p(n)) == -1 and "no CUDA device" in err(L)
+    L.kcnn_nnet_delete(ctypes.c_void_p(n))
+    m = L.kcnn_nnet_new_from_config(cfg.encode(), 1)
+    assert m, err(L)
+    assert L.kcnn_nnet_num_components(ctypes.c_void_p(m)) == 3 and L.kcnn_nnet_input_dim(ctypes.c_void_p(m)) == 840
+    L.kcnn_nnet_delete(ctypes.c_void_p(m))
+    assert not L.kcnn_nnet_new_from_config(cfg.replace("dim=840\nSoftmax", "dim=841\nSoftmax").encode(), 0)
