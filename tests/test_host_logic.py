@@ -335,3 +335,29 @@ def test_model_with_only_glue_parses_like_nnet_config(L):
     assert L.kcnn_nnet_num_components(ctypes.c_void_p(m)) == 3 and L.kcnn_nnet_input_dim(ctypes.c_void_p(m)) == 840
     L.kcnn_nnet_delete(ctypes.c_void_p(m))
     assert not L.kcnn_nnet_new_from_config(cfg.replace("dim=840\nSoftmax", "dim=841\nSoftmax").encode(), 0)
+
+
+def test_reals_of_either_width_are_read(L):
+    """Upstream's ReadBasicType<float> accepts 4- and 8-byte reals (a model written by a double-precision Kaldi);
+    in text mode a real may be followed directly by the next token's '<' (peek-based parsing, no multi-char putback)."""
+    import struct
+    wide = (b"<DropoutComponent> <Dim> " + _i32(16) + b"<DropoutScale> \x08" + struct.pack("<d", 0.5) +
+            b"<DropoutProportion> \x08" + struct.pack("<d", float(struct.unpack("<f", struct.pack("<f", 0.2))[0])) +
+            b"</DropoutComponent> ")
+    r = L.kcnn_component_read(wide, len(wide), 1)
+    assert r, err(L)
+    assert write(L, r, False) == b"<DropoutComponent> <Dim> 16 <DropoutScale> 0.5 <DropoutProportion> 0.2 </DropoutComponent> "
+    L.kcnn_component_delete(ctypes.c_void_p(r))
+    bad = wide.replace(b"<DropoutScale> \x08", b"<DropoutScale> \x03")
+    assert not L.kcnn_component_read(bad, len(bad), 1)                 # a size byte that is neither 4 nor 8
+    for txt in (b"<DropoutComponent> <Dim> 16 <DropoutScale> 5e-1 <DropoutProportion> 0.2 </DropoutComponent> ",
+                b"<DropoutComponent>  <Dim>  16\n<DropoutScale>\t0.5 <DropoutProportion> .2 </DropoutComponent>\n"):
+        t = L.kcnn_component_read(txt, len(txt), 0)
+        assert t, err(L)
+        assert write(L, t, True) == (b"<DropoutComponent> <Dim> " + _i32(16) + b"<DropoutScale> " + _f32(0.5) +
+                                     b"<DropoutProportion> " + _f32(0.2) + b"</DropoutComponent> ")
+        L.kcnn_component_delete(ctypes.c_void_p(t))
+    for txt in (b"<DropoutComponent> <Dim> 16 <DropoutScale> abc <DropoutProportion> 0.2 </DropoutComponent> ",
+                b"<DropoutComponent> <Dim> 16 <DropoutProportion> 0.2 <DropoutScale> 0.5 </DropoutComponent> ",
+                b"<DropoutComponent> <Dim> 16 <DropoutScale> 0.5 <DropoutProportion> 0.2 "):
+        assert not L.kcnn_component_read(txt, len(txt), 0)             # bad number / token order / missing end token
