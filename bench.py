@@ -850,6 +850,15 @@ def main():
                     help="strong scaling: fix the GLOBAL minibatch (rows per GPU = global / GPUs); 0 = weak scaling, "
                          "--batch rows per GPU")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: one process per GPU through torchrun, as the driver does
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                                  str(args.gpus), "--master-addr", "127.0.0.1", "--master-port", str(port),
+                                  os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         run_reference_arm(args)
     else:

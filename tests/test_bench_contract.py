@@ -37,6 +37,19 @@ def test_reference_arm_other_ranks_exit_quietly():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_gpus_n_without_a_launcher_starts_one_process_per_gpu():
+    """`python bench.py --gpus 2` outside torchrun re-executes itself through torch.distributed.run (one process per
+    GPU, 127.0.0.1 rendezvous); checked here with the CPU arm: exactly ONE line, from rank 0, with n_gpus 2."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--cpu-rows", "16"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
+
+
 def test_product_arm_has_no_cpu_path():
     import torch
     if torch.cuda.is_available():
