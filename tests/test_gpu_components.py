@@ -208,6 +208,11 @@ def test_maxpool_overlap_component(ora):
 
 @pytest.mark.parametrize("math", [0, 1])
 def test_fully_connected_component_two_steps(ora, math):
+    """Propagate / Backprop / UpdateSimple (nnet2/nnet-component.cc:1216-1258, nnet0/nnet-component-nnet0.cc:
+    1133-1143) over two steps (the second exercises the momentum) against the oracle.  The update's order of
+    operations (AddRowSumMat for the bias, Scale + AddMat + AddMatMat for prev_grad_, AddMat for W) is pinned by
+    the oracle's restatement only: those stock Kaldi routines are not in /root/reference, unlike the cnslmat
+    kernels the convolution chains are checked against (tests/test_gpu_reference_chains.py)."""
     kc.set_math_mode(math)
     kc.set_rand_seed(43)
     comp = kc.Component.from_string("FullyConnectedComponent input-dim=256 output-dim=1024 learning-rate=0.02 "

@@ -144,6 +144,11 @@ def test_affine_fprop_dgrad_wgrad(ora, N, din, dout, math, layout):
 
 
 def test_sgd_momentum_update_matches_oracle_rounding(ora):
+    """prev = m prev - lr wd W + lr dW ; W += prev  (nnet0/nnet-component-nnet0.cc:767-773, 1138-1142), bit for bit.
+    What pins this: the reference performs it with stock Kaldi calls (CuMatrix::Scale / AddMat, :769-773) whose
+    sources are NOT part of /root/reference, so there is no reference binary to run next to it -- the expected
+    values are this NumPy restatement of those calls' arithmetic (one rounding per AddMat, fused multiply-add), the
+    same order the oracle's C port uses.  It is the one row where "green" rests on a restatement alone."""
     rng = np.random.default_rng(5)
     R, Cc = 97, 130
     w = rng.standard_normal((R, Cc)).astype(np.float32)
