@@ -1,0 +1,148 @@
+"""The oracle's WHOLE training step (oracle/cpu_nnet.py: CpuNnet -- the checker the GPU step is held to in
+tests/test_gpu_fused_step.py) pinned against an independent formulation: the same network written with
+torch.nn.functional on the CPU in FP64, gradients by autograd, the update written out from the reference's
+formulas.  Nothing of the oracle's index algebra (PaddingZero / FlipMat / TpBlock / ModPermuteRow chains,
+both dgrad branches) is shared with conv2d / max_pool3d / autograd, so agreement to 1e-12 pins
+
+  * Propagate of every layer kind and the [C][W][H] layout (cnsl-cu-kernels.cu:28-32),
+  * Backprop (nnet0/nnet-component-nnet0.cc:461-544, 881-892; nnet2/nnet-component.cc:813-827, 985-1000,
+    1246-1247, 3634-3636) -- the input derivative of the network and, through the updated parameters,
+    every intermediate derivative,
+  * Update (nnet0/nnet-component-nnet0.cc:738-777, 1133-1143): lr = learning_rate / N, prev = m prev - lr wd W
+    + lr dW, W += prev, b += lr db; the convolution ignoring the config line's weight-decay / momentum
+    (SURVEY App. C.2), over two steps so that the momentum term is exercised.
+
+CPU only; torch here is the independent reference, never the product."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.cpu_nnet import CpuNnet
+
+CONFIG = """
+ConvolutionComponent in-height=6 in-width=9 in-channel=2 kernel-height=3 kernel-width=4 stride=1 group=4 out-height=4 out-width=6 learning-rate=0.03 param-stddev=0.3 bias-stddev=0.5 weight-decay=0.5 momentum=0.1
+MaxpoolComponent in-height=4 in-width=6 in-channel=4 pool-height-dim=2 pool-width-dim=3 pool-channel-dim=2
+RectifiedLinearComponent dim=8
+ConvolutionComponent in-height=2 in-width=2 in-channel=2 in-pad-height=0 in-pad-width=1 kernel-height=1 kernel-width=2 stride=1 group=3 out-height=2 out-width=3 learning-rate=0.05 param-stddev=0.4 bias-stddev=0.5
+RectifiedLinearComponent dim=18
+DropoutComponent dim=18 dropout-proportion=0.3 dropout-scale=0.25
+FullyConnectedComponent input-dim=18 output-dim=7 learning-rate=0.02 param-stddev=0.3 bias-stddev=0.1 weight-decay=0.001 momentum=0.8
+RectifiedLinearComponent dim=7
+FullyConnectedComponent input-dim=7 output-dim=5 learning-rate=0.04 param-stddev=0.4 bias-stddev=0.2
+SoftmaxComponent dim=5
+"""
+# the same stack where the convolution's input derivative takes the OTHER branch of Backprop (:499-528 vs
+# :529-540): a wide kernel on a short output
+CONFIG_B = """
+ConvolutionComponent in-height=5 in-width=8 in-channel=3 kernel-height=5 kernel-width=6 stride=1 group=4 out-height=1 out-width=3 learning-rate=0.03 param-stddev=0.3 bias-stddev=0.5
+RectifiedLinearComponent dim=12
+ConvolutionComponent in-height=1 in-width=3 in-channel=4 in-pad-height=0 in-pad-width=1 kernel-height=1 kernel-width=3 stride=1 group=5 out-height=1 out-width=3 learning-rate=0.05 param-stddev=0.4 bias-stddev=0.5
+MaxpoolComponent in-height=1 in-width=3 in-channel=5 pool-height-dim=1 pool-width-dim=3 pool-channel-dim=1
+FullyConnectedComponent input-dim=5 output-dim=4 learning-rate=0.02 param-stddev=0.3 bias-stddev=0.1
+SoftmaxComponent dim=4
+"""
+
+
+class TorchNet:
+    """The same layers on torch tensors that share NOTHING with the oracle but the parameter values."""
+
+    def __init__(self, oracle_net):
+        self.layers = []
+        for L in oracle_net.layers:
+            T = dict(L)
+            for k in ("lin", "bias", "prev", "W"):
+                if isinstance(L.get(k), np.ndarray):        # ("W" is the FC matrix OR a layer's width)
+                    T[k] = torch.tensor(np.array(L[k], dtype=np.float64), requires_grad=k in ("lin", "bias", "W"))
+            self.layers.append(T)
+
+    def forward(self, x, masks):
+        a, mi = x, 0
+        for L in self.layers:
+            k = L["kind"]
+            n = a.shape[0]
+            if k == "ConvolutionComponent":
+                # activations [C][W][H], H fastest; kernel row (c KW + kw) KH + kh, column g
+                w = L["lin"].t().reshape(L["G"], L["C"], L["KW"], L["KH"])
+                y = F.conv2d(a.reshape(n, L["C"], L["W"], L["H"]), w, L["bias"], padding=(L["pw"], L["ph"]))
+                a = y.reshape(n, -1)
+            elif k == "MaxpoolComponent":
+                y = F.max_pool3d(a.reshape(n, 1, L["C"], L["W"], L["H"]), (L["pc"], L["pw"], L["ph"]))
+                a = y.reshape(n, -1)
+            elif k == "FullyConnectedComponent":
+                a = a @ L["W"].t() + L["bias"]
+            elif k == "RectifiedLinearComponent":
+                a = torch.relu(a)
+            elif k == "DropoutComponent":
+                a = a * masks[mi]
+                mi += 1
+            elif k == "SoftmaxComponent":
+                a = torch.log_softmax(a, dim=1)
+        return a                                   # log posteriors
+
+    def step(self, x, labels, masks):
+        n = x.shape[0]
+        x = x.clone().requires_grad_(True)
+        objf = self.forward(x, masks)[torch.arange(n), labels].sum()          # sum_i log p[i, label_i]
+        params = [L[k] for L in self.layers for k in ("lin", "W", "bias") if torch.is_tensor(L.get(k))]
+        grads = torch.autograd.grad(objf, [x] + params)
+        g = dict(zip([id(p) for p in params], grads[1:]))
+        with torch.no_grad():
+            for L in self.layers:
+                wk = "lin" if "lin" in L else "W" if torch.is_tensor(L.get("W")) else None
+                if wk is None:
+                    continue
+                lr = L["lr"] / n                                               # :767, :1136
+                L["prev"] = L["mom"] * L["prev"] - lr * L["wd"] * L[wk] + lr * g[id(L[wk])]
+                L[wk] += L["prev"]
+                L["bias"] += lr * g[id(L["bias"])]
+        return float(objf.detach()), grads[0].numpy()
+
+
+def _masks(net, n, rng):
+    ms = []
+    for L in net.layers:
+        if L["kind"] == "DropoutComponent":
+            hi = (1.0 - L["dp"] * L["scale"]) / (1.0 - L["dp"])               # nnet2/nnet-component.cc:3605-3615
+            ms.append(np.where(rng.random((n, 18)) > L["dp"], hi, L["scale"]))
+    return ms
+
+
+@pytest.mark.parametrize("config", [CONFIG, CONFIG_B], ids=["all-layer-kinds", "other-dgrad-branch"])
+def test_oracle_training_step_against_autograd(config):
+    rng = np.random.default_rng(77)
+    n = 6
+    net = CpuNnet(config, seed=5, dtype=np.float64)
+    ref = TorchNet(net)
+    conv0 = net.layers[0]
+    assert (conv0["wd"], conv0["mom"]) == (0.0002, 0.9)      # App. C.2: the config line's values are not applied
+    nout = net.layers[-1]["dim"]
+    for step in range(2):
+        x = rng.standard_normal((n, net.input_dim))
+        labels = rng.integers(0, nout, n)
+        masks = _masks(net, n, rng)
+        post = net.forward(x, dropout_masks=masks)
+        objf = net.backward(labels, update=True)
+        t_objf, t_dx = ref.step(torch.tensor(x), torch.tensor(labels), [torch.tensor(m) for m in masks])
+        assert np.allclose(post.sum(axis=1), 1.0, atol=1e-12)
+        assert abs(objf - t_objf) <= 1e-12 * max(1.0, abs(t_objf)), (step, objf, t_objf)
+        assert np.abs(net.input_deriv - t_dx).max() <= 1e-12 * max(1.0, np.abs(t_dx).max()), step
+        assert np.abs(t_dx).max() > 1e-4                      # the comparison is not of zeros
+        for i, (L, T) in enumerate(zip(net.layers, ref.layers)):
+            for k in ("lin", "W", "bias", "prev"):
+                if isinstance(L.get(k), np.ndarray):
+                    want = T[k].detach().numpy()
+                    err = np.abs(np.asarray(L[k]) - want).max() / max(np.abs(want).max(), 1e-30)
+                    assert err <= 1e-11, (step, i, L["kind"], k, err)
+
+
+def test_both_dgrad_branches_are_covered():
+    """Between them the convolutions of the two configurations take both branches of Backprop
+    (nnet0/nnet-component-nnet0.cc:499-528 no-flip, :529-540 flip; the rule of SURVEY 8a11)."""
+    from oracle import oracle as ora
+    taken = set()
+    for config in (CONFIG, CONFIG_B):
+        for L in CpuNnet(config, seed=1, dtype=np.float64).layers:
+            if L["kind"] == "ConvolutionComponent":
+                taken.add(bool(ora.conv_backprop_uses_flip(L["ph"], L["pw"], L["KH"], L["KW"], L["OH"], L["OW"])))
+    assert taken == {True, False}
