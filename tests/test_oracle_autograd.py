@@ -146,3 +146,52 @@ def test_both_dgrad_branches_are_covered():
             if L["kind"] == "ConvolutionComponent":
                 taken.add(bool(ora.conv_backprop_uses_flip(L["ph"], L["pw"], L["KH"], L["KW"], L["OH"], L["OW"])))
     assert taken == {True, False}
+
+
+def test_glue_oracles_against_autograd():
+    """The FP32 restatements of the element-wise glue (oracle.py: normalize / softmax / dropout / relu, after
+    nnet2/nnet-component.cc:576-639, 930-1000, 3592-3637, 799-827) against autograd of their defining formulas."""
+    from oracle import oracle as ora
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((7, 33)).astype(np.float32)
+    x[2] *= 1e-12                                                # a row whose mean square is under the floor 2^-66
+    dy = rng.standard_normal((7, 33)).astype(np.float32)
+    xt = torch.tensor(x.astype(np.float64), requires_grad=True)
+    # NormalizeComponent: y = x * max(mean(x^2), 2^-66)^-1/2; a floored row passes no derivative through the norm
+    yt = xt * torch.clamp((xt * xt).mean(dim=1, keepdim=True), min=2.0 ** -66) ** -0.5
+    (gt,) = torch.autograd.grad(yt, xt, torch.tensor(dy.astype(np.float64)))
+    y, g = ora.normalize_propagate(x), ora.normalize_backprop(x, dy)
+    assert np.abs(y - yt.detach().numpy()).max() <= 1e-5 * np.abs(yt.detach().numpy()).max()
+    for r in range(7):                                           # row by row: row 2 is 1e12 times larger
+        want = gt[r].numpy()
+        assert np.abs(g[r] - want).max() <= 2e-5 * np.abs(want).max(), r
+    assert np.abs(y[2] - x[2] * 2.0 ** 33).max() <= 1e-5 * np.abs(x[2] * 2.0 ** 33).max()
+    # SoftmaxComponent: Backprop is y * (d - <y, d>)
+    x = rng.standard_normal((5, 11)).astype(np.float32) * 3
+    xt = torch.tensor(x.astype(np.float64), requires_grad=True)
+    yt = torch.softmax(xt, dim=1)
+    d = rng.standard_normal((5, 11)).astype(np.float32)
+    (gt,) = torch.autograd.grad(yt, xt, torch.tensor(d.astype(np.float64)))
+    y = ora.softmax_propagate(x)
+    assert np.abs(y - yt.detach().numpy()).max() <= 1e-6
+    assert np.abs(ora.softmax_backprop(y, d) - gt.numpy()).max() <= 1e-5 * max(1.0, np.abs(gt.numpy()).max())
+    # RectifiedLinearComponent: the gate is the OUTPUT (> 0)
+    y = ora.relu_propagate(x)
+    assert np.array_equal(y, np.maximum(x, 0))
+    assert np.array_equal(ora.relu_backprop(y, d), np.where(x > 0, d, 0).astype(np.float32))
+    # DropoutComponent: out = in * mask with mask in {scale, (1 - p scale) / (1 - p)}; Backprop = d * out / in
+    u = rng.random((5, 11)).astype(np.float32)
+    p, lo = 0.3, 0.25
+    out = ora.dropout_propagate(x, u, p, lo)
+    ratio = out / x
+    hi = (1 - p * lo) / (1 - p)
+    assert np.all((np.abs(ratio - lo) < 1e-6) | (np.abs(ratio - hi) < 1e-6))
+    assert np.abs(ora.dropout_backprop(x, out, d) - d * ratio).max() <= 1e-6 * np.abs(d).max() * hi
+    # cross-entropy: objf = sum log p[label], derivative 1 / p at the label
+    lab = rng.integers(0, 11, 5).astype(np.int32)
+    y = ora.softmax_propagate(x)
+    objf, dd = ora.xent_objf_and_deriv(y, lab)
+    want = np.zeros_like(y)
+    want[np.arange(5), lab] = 1.0 / y[np.arange(5), lab]
+    assert np.allclose(dd, want, rtol=1e-6)
+    assert abs(objf - np.log(y[np.arange(5), lab].astype(np.float64)).sum()) <= 1e-5
