@@ -171,20 +171,22 @@ def test_shard_rows_partitions_exactly():
         shard_rows(4, 2, 2)
 
 
-def test_world_size_2_gloo_matches_single_process(tmp_path):
-    n = 12
+@pytest.mark.parametrize("world, n", [(2, 12), (4, 14)], ids=["world2", "world4-ragged"])
+def test_world_size_2_gloo_matches_single_process(tmp_path, world, n):
+    """P ranks x their row shards (14 rows over 4 ranks: 4 + 4 + 3 + 3) == one process x all rows, two steps;
+    the replicas stay bit-identical."""
     x, y = _data(n)
     ref = OracleNet()
     single = DataParallelStep(ref, ref.arena, [0, 2], None, 1)
     for _ in range(2):
         single(x, y, n)
-    mp.spawn(_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
-    got = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in (0, 1)]
+    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
     want = dict(k=ref.k, kb=ref.kb, w=ref.w, wb=ref.wb, kp=ref.kp)
     for name, w in want.items():
-        for r in (0, 1):
+        for r in range(world):
             assert np.abs(got[r][name] - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-30), (name, r)
-        assert np.array_equal(got[0][name], got[1][name])          # replicas stay bit-identical
+            assert np.array_equal(got[0][name], got[r][name])      # replicas stay bit-identical
 
 
 def test_world_gt_1_needs_a_process_group():
