@@ -96,6 +96,7 @@ NnetDataParallel::NnetDataParallel(Nnet *nnet, NnetMinibatchUpdater *updater, in
     g.first = g.last = (int32)i;
     g.channel = small ? 1 : 0;                           // convolution buckets must not queue behind the FC stack
     CU_SAFE_CALL(cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming));
+    CU_SAFE_CALL(cudaEventCreateWithFlags(&g.ready_compute, cudaEventDisableTiming));
     CU_SAFE_CALL(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     groups_.push_back(g);
   }
@@ -116,6 +117,7 @@ NnetDataParallel::~NnetDataParallel() {
   }
   for (size_t i = 0; i < groups_.size(); i++) {
     cudaEventDestroy(groups_[i].ready);
+    cudaEventDestroy(groups_[i].ready_compute);
     cudaEventDestroy(groups_[i].done);
   }
   updater_->SetDeferredUpdate(false);
@@ -148,6 +150,13 @@ void NnetDataParallel::ReduceAndUpdate(const Group &g, int32 rows_global) {
   // range had none); that branch starts behind the layers' input-gradient GEMMs, the last readers of W
   CU_SAFE_CALL(cudaEventRecord(g.ready, updater_->GradientStream()));
   CU_SAFE_CALL(cudaStreamWaitEvent(comm_[g.channel], g.ready, 0));
+  // ... and behind the compute stream too: the branch exists as soon as the pass has sent its statistics out,
+  // but an affine layer's weight gradient and the first layer's (no input gradient to run beside) are issued
+  // on the compute stream, as are the input-gradient GEMMs that still read the weights this kernel replaces
+  if (updater_->GradientStream() != Str()) {
+    CU_SAFE_CALL(cudaEventRecord(g.ready_compute, Str()));
+    CU_SAFE_CALL(cudaStreamWaitEvent(comm_[g.channel], g.ready_compute, 0));
+  }
   int rc;
   if (n == 1)
     rc = kcnn_p2p_reduce_sgd_f32(comm_[g.channel], &peers_[0], multicast_, rank_, world_, b[0].offset_floats,

@@ -68,7 +68,7 @@ class NnetDataParallel {
   struct Group {
     int32 first, last;                    // layers_[first .. last], network order
     int32 channel;                        // 0: big buckets (FC stack), 1: small (convolutions)
-    cudaEvent_t ready, done;
+    cudaEvent_t ready, ready_compute, done;   // gradients complete (branch / compute stream), update complete
   };
   void BackwardWithUpdates(int32 rows_global);
   void ForwardBehindUpdates(const CuMatrixBase<BaseFloat> &feats, const int32 *labels);

@@ -418,6 +418,7 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
   std::vector<KcnnColsumJob> bias_jobs;
   if (last == nnet_->NumComponents() - 1) stat_jobs.clear();     // a new backward pass starts at the top
   bool forked = false;
+  bool dirty = false;                          // st has produced a derivative the side branch is not ordered behind yet
   size_t ev = 0;
   auto fork = [&]() -> cudaStream_t {          // work issued on the returned stream runs beside what follows on st
     if (F.side == NULL || ev >= F.fork_ev.size()) return st;
@@ -428,8 +429,16 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
     }
     ev++;
     forked = true;
+    dirty = false;
     return F.side;
   };
+  // The bias column sums of the range run on the side branch at the end and read EVERY out_deriv of the range.
+  // A weight gradient that stays on st (an affine layer's; the first layer's, which has no input gradient to
+  // run beside) does not fork, so derivatives produced on st since the last fork -- e.g. by the max-pool backward
+  // between conv2 and conv1 -- would be read by the side branch without an ordering.  Called before such a
+  // weight gradient is issued for the LAST op of the range (every producer of the range has been issued by
+  // then): one more edge st -> side, placed where it costs the side branch nothing.
+  auto order_side = [&]() { if (forked && dirty) fork(); };
   // gate of the op that produced forward_[op.in]: its ReLU (and dropout) backward, applied by the consumer
   auto gate = [&](const FusedOp &op, const float **x, int *ldx, const float **y, int *ldy) {
     *x = NULL; *y = NULL; *ldx = 0; *ldy = 0;
@@ -510,6 +519,7 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
       cudaF_maxpool_backprop_cl(st, x.Data(), pool.Data(), F.act_cl[op.comp + 1] ? 0 : pool.Stride(), dy.Data(),
                                 num_rows_, op.W, op.C, mp.Pool_width_dim(), mp.Pool_channel_dim(),
                                 derivs_[op.in].Data(), gx != NULL);
+      dirty = true;
       continue;
     }
     UpdatableComponent &uc = static_cast<UpdatableComponent &>(comp);
@@ -526,8 +536,10 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
         Tag(op.comp, "affine dgrad (+ReLU/dropout gate)", 2.0 * num_rows_ * t.wd.rows * t.wd.cols,
             4.0 * ((double)num_rows_ * (t.wd.rows + 2.0 * t.wd.cols) + (double)t.wd.rows * t.wd.cols));
         ok = cudaF_affine_dgrad_fused(st, dy.Data(), dy.Dim(), t.w, t.wd, dx.Data(), dx.Dim(), gx, ldx, gy, ldy, perm_r);
+        dirty = true;
       }
       cudaStream_t ws = (F.fork_fc && op.need_dgrad) ? fork() : st;
+      if (ws == st && i == o_first) order_side();
       // with the SGD step in the epilogue W and prev_grad are read and written: 16 B per weight
       Tag(op.comp, apply ? "affine wgrad + SGD" : "affine wgrad", 2.0 * num_rows_ * t.wd.rows * t.wd.cols,
           (apply ? 16.0 : 4.0) * t.wd.rows * t.wd.cols + 4.0 * num_rows_ * (t.wd.rows + t.wd.cols));
@@ -548,8 +560,10 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
             4.0 * ((double)num_rows_ * (2.0 * op.W * op.C + op.OW * op.G) + (double)cv.KernelDim() * op.G));
         ok = cudaF_conv_time_dgrad_cl(st, dy.Data(), num_rows_, op.W, op.C, cv.In_pad_width(), cv.Kernel_width(), op.G,
                                       t.w, t.wd, derivs_[op.in].Data(), gx);
+        dirty = true;
       }
       cudaStream_t ws = op.need_dgrad ? fork() : st;      // the update writes the kernel dgrad reads: behind it
+      if (ws == st && i == o_first) order_side();
       Tag(op.comp, apply ? "conv wgrad + SGD" : "conv wgrad", 2.0 * num_rows_ * op.OW * op.G * cv.KernelDim(),
           4.0 * ((double)num_rows_ * (x.NumCols() + op.OW * op.G)) + (apply ? 16.0 : 4.0) * cv.KernelDim() * op.G);
       if (op.kind == FusedOp::kConvTime)
@@ -569,6 +583,7 @@ void NnetMinibatchUpdater::FusedBackward(int32 last, int32 first) {
   }
   // the bias gradients of the range (and, for a pass issued in partial ranges, the statistics once it has
   // reached the bottom): one launch each, beside the tail of the GEMM chain
+  order_side();                                // (nothing to do unless the range ended on a pooling layer)
   cudaStream_t cst = (F.side != NULL && forked) ? F.side : st;
   if (!F.stats_issued && first == base_) launch_colsums(stat_jobs, 0, cst);
   launch_colsums(bias_jobs, 1, cst);
