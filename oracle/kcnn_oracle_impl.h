@@ -20,15 +20,20 @@
  *   against the reference's GPU path rebuilt from its own kernels (span_row_to_convmat,
  *   convmat_to_out, add_mat_rep_vec from oracle/_ref) and the cuBLAS SGEMM Kaldi's AddMatMat
  *   calls: tests/ref_conv_check.py, test_reference_conv2d_chain (<= 1e-5).
- *   PARITY UNPINNED for a11 / a12 (ConvolutionComponent Backprop / Update) and a14
- *   (FullyConnectedComponent): the host code that chains the kernels there is a patch on
- *   Kaldi r4510 and cannot be compiled in this image (no Kaldi tree, no BLAS headers;
- *   SURVEY 8c), and it ships no golden vectors or known-answer tests.  What
- *   pins the restatement there: the independent NumPy / einsum formulation of the same
- *   index algebra (oracle/oracle_np.py, tests/test_oracle_einsum.py, <= 1e-12 in FP64,
- *   both Backprop branches), the reference's finite-difference method in FP64 (gradients
- *   against the pinned forward pass), and the committed fixtures (tests/golden/,
- *   tests/test_golden.py).
+ *   PINNED for a11 / a12 (ConvolutionComponent Backprop, both input-gradient branches, and the
+ *   gradient of Update) against the reference's OWN kernels chained in the host order of
+ *   nnet0/nnet-component-nnet0.cc:461-544, 738-777 (PaddingZero, span_row_to_convmat, FlipMat,
+ *   TpBlock, TpInsideBlock, ModPermuteRow from oracle/_ref + the cuBLAS SGEMM behind AddMatMat):
+ *   tests/test_gpu_reference_chains.py, incl. C1a / C1b at N = 256 (<= 1e-5).  The host file that
+ *   makes those calls is a patch on Kaldi r4510 and cannot itself be compiled in this image (no
+ *   Kaldi tree, no BLAS headers), and it ships no golden vectors.
+ *   RESTATEMENT ONLY for the momentum / weight-decay arithmetic of the updates (:767-775,
+ *   :1136-1142: stock Kaldi Scale / AddMat / AddRowSumMat, whose sources are not in
+ *   /root/reference) and for a14's FullyConnectedComponent: pinned by independent formulations --
+ *   NumPy / einsum (oracle/oracle_np.py, tests/test_oracle_einsum.py, <= 1e-12 in FP64), the
+ *   reference's finite-difference method in FP64, torch autograd of the whole training step in
+ *   FP64 (tests/test_oracle_autograd.py, <= 1e-12 on objective, input derivative and every updated
+ *   weight / bias / momentum matrix over two steps), and the committed fixtures (tests/golden/).
  *
  * Every function cites the reference lines it follows
  * (paths relative to /root/reference/src).
