@@ -36,6 +36,9 @@ def L():
     import torch
     if torch.cuda.is_available():
         pytest.skip("host-only checks: they assert the behaviour of a machine without a CUDA device")
+    if not os.path.exists(capi.LIB_PATH):                # a fresh checkout: build first (nvcc cross-compiles)
+        import __graft_entry__
+        __graft_entry__.build()
     lib = capi.load()
     assert lib.kcnn_select_gpu(b"optional") == 1       # 1 = no device, library stays disabled (no CPU path)
     return lib

@@ -20,10 +20,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "kaldi-cnn_b200", "lib", "libkaldicnn_b200.so")
 
 
+def _ensure_lib():
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("needs cuobjdump")
+    if not os.path.exists(LIB):                          # a fresh checkout: build first (nvcc cross-compiles)
+        sys.path.insert(0, ROOT)
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="module")
 def table():
-    if shutil.which("cuobjdump") is None or not os.path.exists(LIB):
-        pytest.skip("needs cuobjdump and the built library")
+    _ensure_lib()
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_resources.py"), LIB], capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -39,8 +47,7 @@ def table():
 
 
 def test_only_sm_100a_code_is_embedded():
-    if shutil.which("cuobjdump") is None or not os.path.exists(LIB):
-        pytest.skip("needs cuobjdump and the built library")
+    _ensure_lib()
     out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
